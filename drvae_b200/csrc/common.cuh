@@ -1,0 +1,214 @@
+// Shared device helpers for the drvae_b200 kernels (sm_100a only).
+//
+// Everything here is plumbing for the hot path named in SURVEY.md §8: PTX wrappers for
+// mbarrier / bulk-copy (TMA) / tcgen05 (TMEM + UMMA), the "chunk8" operand layout, and the
+// watchdog that turns a would-be hang into a trapped, reported error.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "drvae_b200 kernels are written for sm_100a (B200) only"
+#endif
+
+namespace drvae {
+
+typedef __nv_bfloat16 bf16;
+
+// ---------------------------------------------------------------------------------------------
+// chunk8 layout.  Every GEMM operand (activations, pre-activation gradients, bf16 weight
+// shadows) lives in HBM as  buf[feature/8][row][feature%8]  (bf16), i.e. one 16-byte "atom" per
+// (row, 8-feature chunk), rows contiguous inside a chunk.  `rcap` is the row capacity (row
+// stride between chunks).  A [rows x 8k] slab of this buffer is already the no-swizzle UMMA
+// canonical layout, K-major when the contraction runs over features and MN-major when it runs
+// over rows, so one storage format feeds forward, dX and dW GEMMs with plain 1-D bulk copies.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ long long c8_index(int row, int feat, int rcap) {
+  return ((long long)(feat >> 3) * rcap + row) * 8 + (feat & 7);
+}
+
+// Device error word: kernels write a code here before trapping so the host can say what hung.
+struct DebugWord {
+  unsigned int code;
+  unsigned int info[7];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// ---------------------------------------------------------------------------------------------
+// mbarrier
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a barrier that never completes (wrong tx byte count, lost commit) becomes a
+// trapped kernel with a code in the debug word instead of a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, DebugWord* dbg, uint32_t code) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
+      if (dbg) {
+        dbg->code = code;
+        dbg->info[0] = blockIdx.x;
+        dbg->info[1] = blockIdx.y;
+        dbg->info[2] = blockIdx.z;
+        dbg->info[3] = threadIdx.x;
+        dbg->info[4] = parity;
+        __threadfence_system();
+      }
+      __trap();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 1-D bulk copy global -> shared (TMA engine, SASS UBLKCP), completion on an mbarrier.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// tcgen05: TMEM allocation, UMMA issue, commit, TMEM loads
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], kind::f16 (bf16 in, fp32 accumulate), issued by ONE thread.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive on an mbarrier once all previously issued UMMAs of this thread have completed.
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns: thread t of the warp reads TMEM lane (lane_base + t).
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  __syncwarp();  // .sync.aligned: make sure the warp is converged after predicated epilogue stores
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory matrix descriptor, no-swizzle ("interleave") canonical layout.
+// Field meaning follows cute::UMMA::SmemDescriptor (start>>4 | LBO>>4 @16 | SBO>>4 @32 |
+// version=1 @46 | layout_type=0 @61).  For a K-major operand SBO is the byte distance between
+// 8-row groups and LBO between the two 8-element K halves of one K=16 step; for an MN-major
+// operand SBO is the distance between 8-element MN chunks and LBO between 8-row K groups.
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+// UMMA instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, bf16 A and B,
+// majors selectable, M = 128, N = bn.
+__device__ __forceinline__ uint32_t umma_idesc_bf16(int bn, int a_mn_major, int b_mn_major) {
+  uint32_t d = 0;
+  d |= 1u << 4;                       // c_format = F32
+  d |= 1u << 7;                       // a_format = BF16
+  d |= 1u << 10;                      // b_format = BF16
+  d |= (uint32_t)(a_mn_major & 1) << 15;
+  d |= (uint32_t)(b_mn_major & 1) << 16;
+  d |= (uint32_t)(bn >> 3) << 17;     // n_dim
+  d |= (uint32_t)(128 >> 4) << 24;    // m_dim
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------------
+// small math helpers shared by epilogues and row kernels
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
+// d ELU / d pre, recovered from the stored (bf16-rounded) activation h: 1 if h > 0 else h + 1.
+__device__ __forceinline__ float elu1_grad_from_out(float h) { return h > 0.f ? 1.f : h + 1.f; }
+// torch.nn.Softplus(beta=1, threshold=20)
+__device__ __forceinline__ float softplus20(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+__device__ __forceinline__ float sigmoid_sp(float x) { return x > 20.f ? 1.f : 1.f / (1.f + expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+__device__ __forceinline__ void unpack_bf16x8(const uint4& q, float (&f)[8]) {
+  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(p[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack_bf16x8(const float* f) {
+  uint4 q;
+  q.x = pack_bf16x2(f[0], f[1]);
+  q.y = pack_bf16x2(f[2], f[3]);
+  q.z = pack_bf16x2(f[4], f[5]);
+  q.w = pack_bf16x2(f[6], f[7]);
+  return q;
+}
+
+}  // namespace drvae

@@ -1,0 +1,655 @@
+// Grouped (one problem per ensemble member) GEMM on tcgen05 tensor cores with fused epilogues.
+//
+// One kernel template serves every linear layer of the DrVAE / PVAE / VFAE step
+// (reference: src/blocks.py:95-164 MLP, :243-301 DiagGaussianModule, :304-361
+// DiagGaussianModuleLinear, :364-416 DiagGaussianSigmaModule) in three contraction modes over
+// the same chunk8 operand storage (see common.cuh):
+//   GEMM_NT  forward        D[rows, out]  = X[rows, in]   . W[out, in]^T     (A, B K-major)
+//   GEMM_DX  input grad     D[rows, in]   = dY[rows, out] . W[out, in]       (A K-major, B MN-major)
+//   GEMM_DW  weight grad    D[out, in]    = dY[rows, out]^T . X[rows, in]    (A, B MN-major)
+// Operand tiles are moved global->shared with 1-D bulk copies (TMA engine) into the no-swizzle
+// UMMA canonical layout, multiplied with tcgen05.mma (bf16 in, fp32 accumulate in TMEM) by one
+// elected thread, and the accumulator tile is read back with tcgen05.ld by four epilogue warps
+// that apply the layer's epilogue (bias/ELU, ELU', Gaussian log-density + its gradient, ...).
+//
+// A slow SIMT kernel with the *same* operand format and the *same* epilogue code is kept as a
+// validation reference for the tensor-core mainloop (tests only; never selected implicitly).
+#pragma once
+
+#include "common.cuh"
+
+namespace drvae {
+
+enum { GEMM_NT = 0, GEMM_DX = 1, GEMM_DW = 2 };
+
+enum {
+  EPI_STORE_F32 = 0,  // (+bias) -> fp32 row-major
+  EPI_ELU_C8 = 1,     // +bias (+class bias) -> ELU -> bf16 chunk8
+  EPI_DACT_C8 = 2,    // * ELU'(stored activation) -> bf16 chunk8
+  EPI_GRAD = 3,       // weight gradient -> flat fp32 grad buffer in the reference tensor layout
+  EPI_DECLOSS = 4,    // decoder heads: Gaussian log-density partials + d loss / d pre-activation
+  EPI_DECOUT = 5,     // decoder heads at inference: mu and sigma as fp32 row-major
+  EPI_LIN_C8 = 6      // +bias -> bf16 chunk8 (no activation)
+};
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_MAX_STAGES = 6;
+constexpr int GEMM_A_STAGE_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
+constexpr int GEMM_THREADS = 128;
+
+struct GemmOperand {
+  const bf16* base;        // model 0
+  long long model_stride;  // elements between ensemble members
+  int rcap;                // row capacity of the chunk8 buffer
+  int nchunks;             // feature chunks that exist in the buffer
+  int row0;                // first row of the view
+};
+
+struct GemmProblem {
+  GemmOperand A, B;
+  int mode;
+  int M, N, K;      // static upper bounds of D rows / D cols / contraction length
+  const int* dyn;   // per-model dynamic extent: rows of D (NT, DX) or contraction rows (DW); may be null
+  int dyn_stride;   // ints between models in `dyn`
+  int BN;           // N tile (multiple of 16, <= 256)
+  int tiles_n;
+  int tiles_m;
+  int nstages;
+  int ksplit;       // >1: contraction split across blockIdx.y (EPI_GRAD accumulates atomically)
+  int desc_variant; // debug knob for descriptor bring-up (0 = designed encoding)
+  DebugWord* dbg;
+};
+
+struct EpiParams {
+  // fp32 row-major output (EPI_STORE_F32, EPI_DECOUT mu)
+  float* out_f32;
+  long long out_f32_ms;
+  int out_ld;
+  int out_row0;
+  // second fp32 output (EPI_DECOUT sigma)
+  float* out2_f32;
+  // bf16 chunk8 output
+  bf16* out_c8;
+  long long out_c8_ms;
+  int out_c8_rcap;
+  int out_c8_row0;
+  int n_valid;  // valid output columns (features)
+  // bias: derived fp32 vector of length >= tiles_n*BN (constant offsets folded in, zero padded)
+  const float* bias;
+  long long bias_ms;
+  // per-class bias rows (one-hot y folded out of the GEMM): clsb[cls*clsb_ld + col]
+  const float* clsb;
+  long long clsb_ms;
+  int clsb_ld;
+  const int* row_cls;  // class of each D row
+  long long row_cls_ms;
+  // stored activation for EPI_DACT_C8 (same geometry as the chunk8 output)
+  const bf16* act;
+  long long act_ms;
+  int act_rcap;
+  int act_row0;
+  // EPI_GRAD: D row = shadow row -> (tensor which, row n); D col = input feature k
+  float* grad;
+  long long grad_ms;
+  int g_ntens;
+  int g_off[2];
+  int g_rows[2];
+  int g_ld;
+  int g_kvalid;
+  int ilv_block;
+  int ilv_stride;
+  // EPI_DECLOSS / EPI_DECOUT
+  const float* tgt;  // fp32 targets [R0cap][X] row-major
+  long long tgt_ms;
+  int X;             // feature count (= n_valid / ... ) of the data space
+  const int* counts; // per-model counts block (see plan.h CNT_*)
+  int counts_stride;
+  const float* coefs;  // per-model coefficient block (COEF_*)
+  int coefs_stride;
+  int L;
+  float* part;  // [tiles_n][Rdcap] row partial log-densities
+  long long part_ms;
+  int part_rcap;
+  int write_dy;  // 0 in eval mode (loss only)
+};
+
+// Offsets inside the per-model counts / coefficient blocks (written by rowmap_kernel).
+enum { CNT_N = 0, CNT_NP, CNT_NLAB, CNT_R0, CNT_LN, CNT_RD, CNT_F, CNT_FL, CNT_LNP, CNT_SIZE = 16 };
+enum {
+  COEF_RECL = 0,  // 1 / (L * Nglobal)
+  COEF_PERT,      // beta_pert * pertloss_rate / (L * max(1, Np_global))
+  COEF_KLZ2,      // beta_pert * kl_qz2pz2_rate / (L * Nglobal)
+  COEF_KLD,       // 1 / (L * Nglobal)
+  COEF_YL,        // beta_yr * yloss_rate / (L * max(1, Nlab_global))
+  COEF_INV_N,
+  COEF_INV_NP,
+  COEF_INV_NLAB,
+  COEF_SIZE = 16
+};
+
+struct RowCtx {
+  int model;
+  int row;     // D row (global within the problem)
+  bool valid;  // row < dynamic extent
+  int cls;
+  // DECLOSS
+  const float* trow;
+  float coef;
+  float lsum;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Epilogue pieces (shared by the tensor-core and the SIMT validation kernels).  Each call handles
+// 16 consecutive D columns [col0, col0+16) of one D row held by the calling thread.
+// ---------------------------------------------------------------------------------------------
+template <int EPI>
+__device__ __forceinline__ void epi_begin(const EpiParams& e, RowCtx& rc) {
+  rc.cls = 0;
+  rc.lsum = 0.f;
+  rc.trow = nullptr;
+  rc.coef = 0.f;
+  if (EPI == EPI_ELU_C8) {
+    if (e.row_cls && rc.valid) rc.cls = e.row_cls[rc.model * e.row_cls_ms + rc.row];
+  }
+  if (EPI == EPI_DECLOSS || EPI == EPI_DECOUT) {
+    if (rc.valid && e.tgt) {
+      const int* cnt = e.counts + (long long)rc.model * e.counts_stride;
+      const float* cf = e.coefs + (long long)rc.model * e.coefs_stride;
+      const int N = cnt[CNT_N], Np = cnt[CNT_NP];
+      const int LN = e.L * N, LNp = e.L * Np;
+      int t;
+      float c;
+      if (rc.row < LN) {
+        t = rc.row % N;
+        c = cf[COEF_RECL];
+      } else if (rc.row < LN + LNp) {
+        t = N + (rc.row - LN) % Np;
+        c = cf[COEF_RECL];
+      } else {
+        t = N + (rc.row - LN - LNp) % Np;
+        c = cf[COEF_PERT];
+      }
+      rc.trow = e.tgt + rc.model * e.tgt_ms + (long long)t * e.X;
+      rc.coef = c;
+    }
+  }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epi_chunk(const EpiParams& e, RowCtx& rc, int col0, float (&acc)[16], bool atomic) {
+  if (EPI == EPI_STORE_F32) {
+    if (!rc.valid) return;
+    float* o = e.out_f32 + rc.model * e.out_f32_ms + (long long)(e.out_row0 + rc.row) * e.out_ld;
+    const float* b = e.bias ? e.bias + rc.model * e.bias_ms : nullptr;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      int c = col0 + i;
+      if (c < e.n_valid) o[c] = acc[i] + (b ? b[c] : 0.f);
+    }
+  } else if (EPI == EPI_ELU_C8 || EPI == EPI_LIN_C8 || EPI == EPI_DACT_C8) {
+    float v[16];
+    if (EPI == EPI_DACT_C8) {
+      const uint4* a =
+          reinterpret_cast<const uint4*>(e.act + rc.model * e.act_ms) + ((long long)(col0 >> 3) * e.act_rcap + e.act_row0 + rc.row);
+      uint4 q0 = a[0];
+      uint4 q1 = a[e.act_rcap];
+      float h[16];
+      float h0[8], h1[8];
+      unpack_bf16x8(q0, h0);
+      unpack_bf16x8(q1, h1);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        h[i] = h0[i];
+        h[8 + i] = h1[i];
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        bool ok = rc.valid && (col0 + i) < e.n_valid;
+        v[i] = ok ? acc[i] * elu1_grad_from_out(h[i]) : 0.f;
+      }
+    } else {
+      const float* b = e.bias + rc.model * e.bias_ms;
+      const float* cb = e.clsb ? e.clsb + rc.model * e.clsb_ms + (long long)rc.cls * e.clsb_ld : nullptr;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        int c = col0 + i;
+        bool ok = rc.valid && c < e.n_valid;
+        float x = acc[i] + b[c] + (cb ? cb[c] : 0.f);
+        if (EPI == EPI_ELU_C8) x = elu1(x);
+        v[i] = ok ? x : 0.f;
+      }
+    }
+    uint4* o = reinterpret_cast<uint4*>(e.out_c8 + rc.model * e.out_c8_ms) +
+               ((long long)(col0 >> 3) * e.out_c8_rcap + e.out_c8_row0 + rc.row);
+    o[0] = pack_bf16x8(v);
+    o[e.out_c8_rcap] = pack_bf16x8(v + 8);
+  } else if (EPI == EPI_GRAD) {
+    // rc.row is a shadow row; decode (tensor, row) through the interleave map.
+    int blk = rc.row / e.ilv_stride;
+    int rem = rc.row - blk * e.ilv_stride;
+    int which = rem / e.ilv_block;
+    int n = blk * e.ilv_block + (rem - which * e.ilv_block);
+    if (which >= e.g_ntens || n >= e.g_rows[which]) return;
+    float* g = e.grad + rc.model * e.grad_ms + e.g_off[which] + (long long)n * e.g_ld;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      int k = col0 + i;
+      if (k < e.g_kvalid) {
+        if (atomic)
+          atomicAdd(g + k, acc[i]);
+        else
+          g[k] = acc[i];
+      }
+    }
+  }
+}
+
+// Decoder heads: acc_mu / acc_sg are the mu and sigma pre-activations of features
+// [f0, f0+16) of one decoder row.  Reference math: src/blocks.py:410-416 (mu, softplus(.)+1e-3)
+// and :230-234 (Gaussian log-density with sigma parametrisation).
+template <int EPI>
+__device__ __forceinline__ void epi_dec_chunk(const EpiParams& e, RowCtx& rc, int f0, int ccol_mu, int ccol_sg,
+                                              float (&acc_mu)[16], float (&acc_sg)[16]) {
+  const float* b = e.bias + rc.model * e.bias_ms;
+  if (EPI == EPI_DECOUT) {
+    if (!rc.valid) return;
+    float* om = e.out_f32 + rc.model * e.out_f32_ms + (long long)(e.out_row0 + rc.row) * e.out_ld;
+    float* os = e.out2_f32 + rc.model * e.out_f32_ms + (long long)(e.out_row0 + rc.row) * e.out_ld;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      int f = f0 + i;
+      if (f < e.X) {
+        om[f] = acc_mu[i] + b[ccol_mu + i];
+        os[f] = softplus20(acc_sg[i] + b[ccol_sg + i]) + 1e-3f;
+      }
+    }
+    return;
+  }
+  // EPI_DECLOSS
+  float dmu[16], dsg[16];
+  float ls = 0.f;
+  const float LOG2PI = 1.8378770664093453f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    int f = f0 + i;
+    bool ok = rc.valid && f < e.X;
+    float mu = acc_mu[i] + b[ccol_mu + i];
+    float sp = acc_sg[i] + b[ccol_sg + i];
+    float sg = softplus20(sp) + 1e-3f;
+    float t = ok ? rc.trow[f] : 0.f;
+    float d = t - mu;
+    float inv = 1.f / sg;
+    float inv2 = inv * inv;
+    float lp = -0.5f * (LOG2PI + logf(sg * sg) + d * d * inv2);
+    ls += ok ? lp : 0.f;
+    // d CMPL / d mu = -coef * (t - mu) / sg^2 ;  d CMPL / d sg = -coef * (-1/sg + (t-mu)^2 / sg^3)
+    float gmu = -rc.coef * d * inv2;
+    float gsg = -rc.coef * (d * d * inv2 * inv - inv);
+    dmu[i] = ok ? gmu : 0.f;
+    dsg[i] = ok ? gsg * sigmoid_sp(sp) : 0.f;
+  }
+  rc.lsum += ls;
+  if (e.write_dy) {
+    uint4* o = reinterpret_cast<uint4*>(e.out_c8 + rc.model * e.out_c8_ms);
+    long long r = e.out_c8_row0 + rc.row;
+    o[(long long)(ccol_mu >> 3) * e.out_c8_rcap + r] = pack_bf16x8(dmu);
+    o[(long long)((ccol_mu >> 3) + 1) * e.out_c8_rcap + r] = pack_bf16x8(dmu + 8);
+    o[(long long)(ccol_sg >> 3) * e.out_c8_rcap + r] = pack_bf16x8(dsg);
+    o[(long long)((ccol_sg >> 3) + 1) * e.out_c8_rcap + r] = pack_bf16x8(dsg + 8);
+  }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epi_end(const EpiParams& e, RowCtx& rc, int tile_n) {
+  if (EPI == EPI_DECLOSS) {
+    // every row of the tile writes (0 for padding rows) so the reducer can read the padded range
+    e.part[rc.model * e.part_ms + (long long)tile_n * e.part_rcap + rc.row] = rc.valid ? rc.lsum : 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tile geometry shared by both kernels
+// ---------------------------------------------------------------------------------------------
+struct TileInfo {
+  int model, tile_m, tile_n, m0, n0;
+  int Mrows;  // valid D rows
+  int Kc;     // contraction length, multiple of 16
+  int kb_begin, kb_end;
+  bool active;
+};
+
+__device__ __forceinline__ TileInfo gemm_tile_info(const GemmProblem& p) {
+  TileInfo t;
+  t.model = blockIdx.z;
+  t.tile_n = blockIdx.x % p.tiles_n;
+  t.tile_m = blockIdx.x / p.tiles_n;
+  t.m0 = t.tile_m * GEMM_BM;
+  t.n0 = t.tile_n * p.BN;
+  int dyn = p.dyn ? p.dyn[(long long)t.model * p.dyn_stride] : -1;
+  if (p.mode == GEMM_DW) {
+    t.Mrows = p.M;
+    int k = dyn >= 0 ? min(dyn, p.K) : p.K;
+    t.Kc = (k + 15) & ~15;
+  } else {
+    t.Mrows = dyn >= 0 ? min(dyn, p.M) : p.M;
+    t.Kc = p.K;
+  }
+  int nkb = (t.Kc + GEMM_BK - 1) / GEMM_BK;
+  int per = (nkb + p.ksplit - 1) / p.ksplit;
+  t.kb_begin = min(nkb, (int)blockIdx.y * per);
+  t.kb_end = min(nkb, t.kb_begin + per);
+  t.active = t.m0 < t.Mrows && (t.kb_end > t.kb_begin || blockIdx.y == 0);
+  return t;
+}
+
+template <int EPI>
+__device__ __forceinline__ void run_epilogue_row(const GemmProblem& p, const EpiParams& e, const TileInfo& t, RowCtx& rc,
+                                                 uint32_t taddr_row, bool have_acc, bool atomic) {
+  epi_begin<EPI>(e, rc);
+  if (EPI == EPI_DECLOSS || EPI == EPI_DECOUT) {
+    const int hb = p.BN >> 1;
+    for (int c = 0; c < hb; c += 16) {
+      float am[16], as[16];
+      if (have_acc) {
+        tmem_ld16(taddr_row + c, am);
+        tmem_ld16(taddr_row + hb + c, as);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) am[i] = as[i] = 0.f;
+      }
+      epi_dec_chunk<EPI>(e, rc, t.tile_n * hb + c, t.n0 + c, t.n0 + hb + c, am, as);
+    }
+  } else {
+    for (int c = 0; c < p.BN; c += 16) {
+      float acc[16];
+      if (have_acc) {
+        tmem_ld16(taddr_row + c, acc);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+      }
+      epi_chunk<EPI>(e, rc, t.n0 + c, acc, atomic);
+    }
+  }
+  epi_end<EPI>(e, rc, t.tile_n);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tensor-core kernel: warp 0 = bulk-copy producer, warp 1 lane 0 = UMMA issuer + TMEM owner,
+// all four warps = epilogue (warp w reads TMEM lanes [32w, 32w+32)).
+// ---------------------------------------------------------------------------------------------
+template <int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const GemmProblem p, const EpiParams e) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t full_bar[GEMM_MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[GEMM_MAX_STAGES];
+  __shared__ __align__(8) uint64_t acc_bar;
+  __shared__ uint32_t tmem_base_s;
+
+  const TileInfo t = gemm_tile_info(p);
+  if (!t.active) return;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nkb = t.kb_end - t.kb_begin;
+  const int BN = p.BN;
+  const int b_stage_bytes = BN * GEMM_BK * 2;
+  const int stage_bytes = GEMM_A_STAGE_BYTES + b_stage_bytes;
+  uint32_t ncols = 32;
+  while ((int)ncols < BN) ncols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.nstages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&acc_bar, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1 && nkb > 0) {
+    tmem_alloc(&tmem_base_s, ncols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = nkb > 0 ? tmem_base_s : 0u;
+
+  const bool a_mn = (p.mode == GEMM_DW);
+  const bool b_mn = (p.mode != GEMM_NT);
+
+  if (warp == 0 && nkb > 0) {
+    // ===================== producer: 1-D bulk copies of operand slabs =====================
+    const bf16* Ab = p.A.base + t.model * p.A.model_stride;
+    const bf16* Bb = p.B.base + t.model * p.B.model_stride;
+    for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
+      const int it = kb - t.kb_begin;
+      const int s = it % p.nstages;
+      const uint32_t ph = (it / p.nstages) & 1;
+      if (lane == 0) mbar_wait(&empty_bar[s], ph ^ 1, p.dbg, 0xE0000000u | kb);
+      __syncwarp();
+      const int kw = min(GEMM_BK, t.Kc - kb * GEMM_BK);  // multiple of 16
+      uint8_t* As = smem + (size_t)s * stage_bytes;
+      uint8_t* Bs = As + GEMM_A_STAGE_BYTES;
+      // --- copy descriptors ---
+      int nA, nB;
+      uint32_t bytesA, bytesB;
+      if (!a_mn) {
+        nA = kw >> 3;
+        bytesA = GEMM_BM * 16;
+      } else {
+        nA = min(GEMM_BM >> 3, p.A.nchunks - (t.m0 >> 3));
+        bytesA = kw * 16;
+      }
+      if (!b_mn) {
+        nB = kw >> 3;
+        bytesB = BN * 16;
+      } else {
+        nB = min(BN >> 3, p.B.nchunks - (t.n0 >> 3));
+        bytesB = kw * 16;
+      }
+      if (nA < 0) nA = 0;
+      if (nB < 0) nB = 0;
+      if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], nA * bytesA + nB * bytesB);
+      __syncwarp();
+      for (int c = lane; c < nA + nB; c += 32) {
+        if (c < nA) {
+          const bf16* src;
+          uint8_t* dst;
+          if (!a_mn) {
+            src = Ab + ((long long)(kb * 8 + c) * p.A.rcap + p.A.row0 + t.m0) * 8;
+            dst = As + (size_t)c * (GEMM_BM * 16);
+          } else {
+            src = Ab + ((long long)((t.m0 >> 3) + c) * p.A.rcap + p.A.row0 + kb * GEMM_BK) * 8;
+            dst = As + (size_t)c * (GEMM_BK * 16);
+          }
+          bulk_g2s(dst, src, bytesA, &full_bar[s]);
+        } else {
+          const int cb = c - nA;
+          const bf16* src;
+          uint8_t* dst;
+          if (!b_mn) {
+            src = Bb + ((long long)(kb * 8 + cb) * p.B.rcap + p.B.row0 + t.n0) * 8;
+            dst = Bs + (size_t)cb * (BN * 16);
+          } else {
+            src = Bb + ((long long)((t.n0 >> 3) + cb) * p.B.rcap + p.B.row0 + kb * GEMM_BK) * 8;
+            dst = Bs + (size_t)cb * (GEMM_BK * 16);
+          }
+          bulk_g2s(dst, src, bytesB, &full_bar[s]);
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0 && nkb > 0) {
+    // ===================== UMMA issuer =====================
+    const uint32_t idesc = umma_idesc_bf16(BN, a_mn ? 1 : 0, b_mn ? 1 : 0);
+    uint32_t a_lbo, a_sbo, a_step, b_lbo, b_sbo, b_step;
+    if (!a_mn) {
+      a_lbo = GEMM_BM * 16;  // next 8-wide K chunk
+      a_sbo = 128;           // next 8 rows
+      a_step = 2 * GEMM_BM * 16;
+    } else {
+      a_lbo = 128;           // next 8 contraction rows
+      a_sbo = GEMM_BK * 16;  // next 8-feature MN chunk
+      a_step = 16 * 16;
+    }
+    if (!b_mn) {
+      b_lbo = BN * 16;
+      b_sbo = 128;
+      b_step = 2 * BN * 16;
+    } else {
+      b_lbo = 128;
+      b_sbo = GEMM_BK * 16;
+      b_step = 16 * 16;
+    }
+    if (p.desc_variant & 1) {  // bring-up knob: swapped LBO/SBO meaning
+      uint32_t x = a_lbo;
+      a_lbo = a_sbo;
+      a_sbo = x;
+      x = b_lbo;
+      b_lbo = b_sbo;
+      b_sbo = x;
+    }
+    for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
+      const int it = kb - t.kb_begin;
+      const int s = it % p.nstages;
+      const uint32_t ph = (it / p.nstages) & 1;
+      mbar_wait(&full_bar[s], ph, p.dbg, 0xF0000000u | kb);
+      tc_fence_after();
+      const int kw = min(GEMM_BK, t.Kc - kb * GEMM_BK);
+      const uint32_t As = smem_u32(smem + (size_t)s * stage_bytes);
+      const uint32_t Bs = As + GEMM_A_STAGE_BYTES;
+      for (int j = 0; j < (kw >> 4); ++j) {
+        uint64_t ad = umma_smem_desc(As + j * a_step, a_lbo, a_sbo);
+        uint64_t bd = umma_smem_desc(Bs + j * b_step, b_lbo, b_sbo);
+        umma_bf16(tmem_base, ad, bd, idesc, (it > 0 || j > 0) ? 1u : 0u);
+      }
+      umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs retire
+    }
+    umma_commit(&acc_bar);  // accumulator complete
+  }
+  __syncwarp();
+
+  // ===================== epilogue: TMEM -> registers -> fused math -> HBM =====================
+  if (nkb > 0) {
+    mbar_wait(&acc_bar, 0, p.dbg, 0xA0000000u);
+    tc_fence_after();
+  }
+  RowCtx rc;
+  rc.model = t.model;
+  rc.row = t.m0 + warp * 32 + lane;
+  rc.valid = rc.row < t.Mrows;
+  const uint32_t taddr_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+  run_epilogue_row<EPI>(p, e, t, rc, taddr_row, nkb > 0, p.ksplit > 1);
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1 && nkb > 0) tmem_dealloc(tmem_base, ncols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// SIMT validation kernel: same grid, same operands, same epilogues, plain FFMA dot products.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float simt_ldA(const GemmProblem& p, const bf16* A, int mn, int k) {
+  long long idx = (p.mode == GEMM_DW) ? c8_index(p.A.row0 + k, mn, p.A.rcap) : c8_index(p.A.row0 + mn, k, p.A.rcap);
+  return __bfloat162float(A[idx]);
+}
+__device__ __forceinline__ float simt_ldB(const GemmProblem& p, const bf16* B, int n, int k) {
+  long long idx = (p.mode == GEMM_NT) ? c8_index(p.B.row0 + n, k, p.B.rcap) : c8_index(p.B.row0 + k, n, p.B.rcap);
+  return __bfloat162float(B[idx]);
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS) gemm_simt_kernel(const GemmProblem p, const EpiParams e) {
+  const TileInfo t = gemm_tile_info(p);
+  if (!t.active) return;
+  const bf16* Ab = p.A.base + t.model * p.A.model_stride;
+  const bf16* Bb = p.B.base + t.model * p.B.model_stride;
+  RowCtx rc;
+  rc.model = t.model;
+  rc.row = t.m0 + threadIdx.x;
+  rc.valid = rc.row < t.Mrows;
+  const int k_lo = t.kb_begin * GEMM_BK;
+  const int k_hi = min(t.Kc, t.kb_end * GEMM_BK);
+  const bool a_ok = (p.mode == GEMM_DW) ? ((rc.row >> 3) < p.A.nchunks) : (p.A.row0 + rc.row < p.A.rcap);
+  epi_begin<EPI>(e, rc);
+  auto dot16 = [&](int ncol0, float (&acc)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    if (!a_ok) return;
+    for (int k = k_lo; k < k_hi; ++k) {
+      float a = simt_ldA(p, Ab, rc.row, k);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        int n = ncol0 + i;
+        bool b_ok = (p.mode == GEMM_NT) ? (p.B.row0 + n < p.B.rcap) : ((n >> 3) < p.B.nchunks);
+        if (b_ok) acc[i] = fmaf(a, simt_ldB(p, Bb, n, k), acc[i]);
+      }
+    }
+  };
+  if (EPI == EPI_DECLOSS || EPI == EPI_DECOUT) {
+    const int hb = p.BN >> 1;
+    for (int c = 0; c < hb; c += 16) {
+      float am[16], as[16];
+      dot16(t.n0 + c, am);
+      dot16(t.n0 + hb + c, as);
+      epi_dec_chunk<EPI>(e, rc, t.tile_n * hb + c, t.n0 + c, t.n0 + hb + c, am, as);
+    }
+  } else {
+    for (int c = 0; c < p.BN; c += 16) {
+      float acc[16];
+      dot16(t.n0 + c, acc);
+      epi_chunk<EPI>(e, rc, t.n0 + c, acc, p.ksplit > 1);
+    }
+  }
+  epi_end<EPI>(e, rc, t.tile_n);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host-side launch helper
+// ---------------------------------------------------------------------------------------------
+enum { GEMM_IMPL_TC = 0, GEMM_IMPL_SIMT = 1 };
+
+inline int gemm_pick_stages(int BN) {
+  const int stage = GEMM_A_STAGE_BYTES + BN * GEMM_BK * 2;
+  int s = (100 * 1024) / stage;  // ~100 KB per CTA -> two CTAs per SM
+  if (s < 2) s = 2;
+  if (s > GEMM_MAX_STAGES) s = GEMM_MAX_STAGES;
+  return s;
+}
+
+template <int EPI>
+inline cudaError_t gemm_launch_t(GemmProblem p, const EpiParams& e, int n_models, int impl, cudaStream_t st) {
+  dim3 grid(p.tiles_n * p.tiles_m, p.ksplit, n_models);
+  if (impl == GEMM_IMPL_SIMT) {
+    gemm_simt_kernel<EPI><<<grid, GEMM_THREADS, 0, st>>>(p, e);
+    return cudaGetLastError();
+  }
+  p.nstages = gemm_pick_stages(p.BN);
+  size_t smem = (size_t)p.nstages * (GEMM_A_STAGE_BYTES + p.BN * GEMM_BK * 2);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t err =
+        cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (err != cudaSuccess) return err;
+    attr_set = true;
+  }
+  gemm_tc_kernel<EPI><<<grid, GEMM_THREADS, smem, st>>>(p, e);
+  return cudaGetLastError();
+}
+
+inline cudaError_t gemm_launch(int epi, const GemmProblem& p, const EpiParams& e, int n_models, int impl,
+                               cudaStream_t st) {
+  switch (epi) {
+    case EPI_STORE_F32: return gemm_launch_t<EPI_STORE_F32>(p, e, n_models, impl, st);
+    case EPI_ELU_C8: return gemm_launch_t<EPI_ELU_C8>(p, e, n_models, impl, st);
+    case EPI_LIN_C8: return gemm_launch_t<EPI_LIN_C8>(p, e, n_models, impl, st);
+    case EPI_DACT_C8: return gemm_launch_t<EPI_DACT_C8>(p, e, n_models, impl, st);
+    case EPI_GRAD: return gemm_launch_t<EPI_GRAD>(p, e, n_models, impl, st);
+    case EPI_DECLOSS: return gemm_launch_t<EPI_DECLOSS>(p, e, n_models, impl, st);
+    case EPI_DECOUT: return gemm_launch_t<EPI_DECOUT>(p, e, n_models, impl, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace drvae

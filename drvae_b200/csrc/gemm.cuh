@@ -122,9 +122,9 @@ enum {
   COEF_KLZ2,      // beta_pert * kl_qz2pz2_rate / (L * Nglobal)
   COEF_KLD,       // 1 / (L * Nglobal)
   COEF_YL,        // beta_yr * yloss_rate / (L * max(1, Nlab_global))
-  COEF_INV_N,
-  COEF_INV_NP,
-  COEF_INV_NLAB,
+  COEF_INV_N,       // 1 / Nglobal
+  COEF_PERT_PLAIN,  // 1 / (L * max(1, Np_global))
+  COEF_YL_PLAIN,    // 1 / (L * max(1, Nlab_global))
   COEF_SIZE = 16
 };
 

@@ -1,0 +1,207 @@
+// Optimizer-side kernels: fused Adam over the flat parameter vector (torch.optim.Adam semantics,
+// SURVEY.md Appendix A.6 / reference DGMMixin.py:31-40, :123) that also refreshes the derived
+// kernel-facing copies (bf16 chunk8 weight shadows, fp32 bias / class-bias vectors), bias
+// gradients as column sums of the stored pre-activation gradients, and the Philox ε generator.
+#pragma once
+
+#include "plan.h"
+
+namespace drvae {
+
+__device__ __forceinline__ int seg_find(const Seg* segs, int nseg, int idx) {
+  int lo = 0, hi = nseg - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (segs[mid].off <= idx)
+      lo = mid;
+    else
+      hi = mid - 1;
+  }
+  return lo;
+}
+
+// Write the kernel-facing copy of parameter element `idx` (value `pv`) of model m.
+__device__ __forceinline__ void write_derived(const Seg& s, int idx, float pv, bf16* shadow, float* derived) {
+  if (s.kind == SEG_W) {
+    if (s.wn_g_off >= 0) return;  // weight-normalised layers: shadow = g v / ||v||, written row-wise
+    const int local = idx - s.off;
+    const int n = local / s.cols, k = local - n * s.cols;
+    const int srow = (n / s.ilv_block) * s.ilv_stride + s.which * s.ilv_block + (n % s.ilv_block);
+    if (k < s.kmain)
+      shadow[s.sh_off + c8_index(srow, k, s.sh_rcap)] = __float2bfloat16_rn(pv);
+    else
+      derived[s.clsb_off + (long long)(k - s.kmain) * s.clsb_ld + srow] = pv;
+  } else if (s.kind == SEG_B) {
+    const int n = idx - s.off;
+    const int srow = (n / s.ilv_block) * s.ilv_stride + s.which * s.ilv_block + (n % s.ilv_block);
+    derived[s.bias_off + srow] = pv + s.bias_const;
+  }
+}
+
+struct AdamArgs {
+  MBuf<float> params, grads, m, v;
+  MBuf<bf16> shadow;
+  MBuf<float> derived;
+  const Seg* segs;
+  int nseg;
+  int P;  // parameters per model
+  float lr, beta1, beta2, eps, wd, bc1, bc2;
+  int update;  // 0: only refresh the derived copies from the current parameters
+};
+
+// grid (ceil(P / 1024), n_models), block 256, 4 elements per thread
+__global__ void __launch_bounds__(256) adam_kernel(AdamArgs a) {
+  const int mdl = blockIdx.y;
+  float* p = a.params.at(mdl);
+  const float* g = a.grads.p ? a.grads.at(mdl) : nullptr;
+  float* mm = a.m.p ? a.m.at(mdl) : nullptr;
+  float* vv = a.v.p ? a.v.at(mdl) : nullptr;
+  bf16* sh = a.shadow.at(mdl);
+  float* dv = a.derived.at(mdl);
+  const int base = blockIdx.x * 1024 + threadIdx.x;
+  const float step_size = a.lr / a.bc1;
+  const float inv_sqrt_bc2 = rsqrtf(a.bc2);
+  int si = -1;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int idx = base + u * 256;
+    if (idx >= a.P) break;
+    float pv = p[idx];
+    if (a.update) {
+      // g <- g + wd p ; m <- b1 m + (1-b1) g ; v <- b2 v + (1-b2) g^2 ;
+      // p <- p - (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps)
+      const float gr = g[idx] + a.wd * pv;
+      const float m1 = a.beta1 * mm[idx] + (1.f - a.beta1) * gr;
+      const float v1 = a.beta2 * vv[idx] + (1.f - a.beta2) * gr * gr;
+      mm[idx] = m1;
+      vv[idx] = v1;
+      pv = pv - step_size * (m1 / (sqrtf(v1) * inv_sqrt_bc2 + a.eps));
+      p[idx] = pv;
+    }
+    if (si < 0 || idx < a.segs[si].off || (si + 1 < a.nseg && idx >= a.segs[si + 1].off)) si = seg_find(a.segs, a.nseg, idx);
+    write_derived(a.segs[si], idx, pv, sh, dv);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// bias gradients: column sums of a chunk8 gradient buffer over its valid rows, routed through the
+// shadow-row map to the reference bias tensors; optional per-class sums for the one-hot columns
+// of a class-augmented first layer (d W[:, kin + j] = sum over rows of class j).
+// grid (ceil(nchunks / 4), n_models), block 128 — one warp per 8-feature chunk
+// ---------------------------------------------------------------------------------------------
+struct ColsumArgs {
+  C8Buf src;
+  const int* dyn;
+  int dyn_stride;
+  MBuf<float> grads;
+  int ntens;
+  int b_off[2];
+  int rows_each[2];
+  int ilv_block, ilv_stride;
+  const int* row_cls;  // null: no class columns
+  long long row_cls_ms;
+  int Y;
+  int w_off, ld, kmain;
+};
+
+__global__ void __launch_bounds__(128) colsum_kernel(ColsumArgs a) {
+  const int m = blockIdx.y, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (c >= (a.src.fcap >> 3)) return;
+  const int rows = a.dyn[(long long)m * a.dyn_stride];
+  const uint4* src = reinterpret_cast<const uint4*>(a.src.at(m)) + (long long)c * a.src.rcap;
+  const int* cls = a.row_cls ? a.row_cls + m * a.row_cls_ms : nullptr;
+  float tot[8];
+  float pc[MAXY][8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) tot[k] = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXY; ++j)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) pc[j][k] = 0.f;
+  for (int r = lane; r < rows; r += 32) {
+    float f[8];
+    unpack_bf16x8(src[r], f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tot[k] += f[k];
+    if (cls) {
+      const int cj = cls[r];
+#pragma unroll
+      for (int j = 0; j < MAXY; ++j)
+        if (j == cj) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) pc[j][k] += f[k];
+        }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) tot[k] = warp_sum(tot[k]);
+  if (cls) {
+#pragma unroll
+    for (int j = 0; j < MAXY; ++j)
+      if (j < a.Y) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) pc[j][k] = warp_sum(pc[j][k]);
+      }
+  }
+  if (lane == 0) {
+    float* g = a.grads.at(m);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int srow = c * 8 + k;
+      const int blk = srow / a.ilv_stride;
+      const int rem = srow - blk * a.ilv_stride;
+      const int which = rem / a.ilv_block;
+      const int n = blk * a.ilv_block + (rem - which * a.ilv_block);
+      if (which < a.ntens && n < a.rows_each[which]) {
+        g[a.b_off[which] + n] = tot[k];
+        if (cls) {
+#pragma unroll
+          for (int j = 0; j < MAXY; ++j)
+            if (j < a.Y) g[a.w_off + (long long)n * a.ld + a.kmain + j] = pc[j][k];
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ε generator: Philox4x32-10 + Box-Muller, 4 normals per thread.
+// counter = (i_lo, i_hi, step, model), key = seed.  grid (ceil(n/1024), n_models), block 256
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0;
+    c[1] = n1;
+    c[2] = n2;
+    c[3] = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+
+__global__ void __launch_bounds__(256) philox_normal_kernel(MBuf<float> out, long long n, unsigned long long seed,
+                                                            unsigned int step) {
+  const int m = blockIdx.y;
+  const long long i4 = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i4 * 4 >= n) return;
+  uint32_t c[4] = {(uint32_t)i4, (uint32_t)(i4 >> 32), step, (uint32_t)m};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  const float k = 2.3283064365386963e-10f;  // 2^-32
+  const float u0 = (c[0] + 1.0f) * k, u1 = c[1] * k, u2 = (c[2] + 1.0f) * k, u3 = c[3] * k;
+  const float r0 = sqrtf(-2.f * logf(fminf(u0, 1.f))), r1 = sqrtf(-2.f * logf(fminf(u2, 1.f)));
+  float s0, c0, s1, c1;
+  sincospif(2.f * u1, &s0, &c0);
+  sincospif(2.f * u3, &s1, &c1);
+  float z[4] = {r0 * c0, r0 * s0, r1 * c1, r1 * s1};
+  float* o = out.at(m);
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (i4 * 4 + j < n) o[i4 * 4 + j] = z[j];
+}
+
+}  // namespace drvae

@@ -1,0 +1,1021 @@
+// Plan construction (parameter layout, weight shadows, workspace) and the step executor: the
+// host side of the C ABI in include/drvae_b200.h.  One launch sequence trains every member of
+// the ensemble; all row counts are read on the device, so the sequence is fixed per (plan, N).
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "errors.h"
+#include "gemm.cuh"
+#include "optim.cuh"
+#include "plan.h"
+#include "rowops.cuh"
+
+using namespace drvae;
+
+namespace {
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+struct Tiling {
+  int BN, tiles, cap;
+};
+// N tiling of a feature dimension: tiles of equal width (multiple of 16, <= 256).
+Tiling tile_cap(int n) {
+  const int n16 = round_up(n, 16);
+  Tiling t;
+  t.tiles = cdiv(n16, 256);
+  t.BN = round_up(cdiv(n16, t.tiles), 16);
+  t.cap = t.BN * t.tiles;
+  return t;
+}
+
+struct BufRec {
+  size_t off;       // byte offset in the arena
+  size_t ms_bytes;  // bytes between models
+  size_t bytes;     // used bytes per model
+  int rcap, fcap;
+};
+
+}  // namespace
+
+struct drvae_plan {
+  drvae_arch_t arch;
+  int E;
+  int X, Y, Z, Z3, L, Ncap;
+  int has_pair, has_T, has_clf, has_fprop, clf_in;
+  // parameters
+  std::vector<ParamInfo> tensors;
+  std::vector<Seg> segs;
+  Seg* d_segs = nullptr;
+  int P = 0;
+  int clf_w_off = -1, clf_b_off = -1;
+  // shadows
+  long long shadow_elems = 0;   // bf16 per model
+  long long derived_elems = 0;  // fp32 per model
+  MlpBlock enc, dec, z3b, dz1b;
+  Shadow Tsh;
+  int dec_hb = 0;
+  // workspace
+  size_t arena_bytes = 0;
+  uint8_t* arena = nullptr;
+  std::map<std::string, BufRec> bufs;
+  C8Buf dY5;  // decoder head gradient
+  MBuf<float> eps_own;
+  drvae_eps_layout_t epsl;
+  MBuf<bf16> shadow;
+  MBuf<float> derived;
+  DevView view;  // static part
+  DebugWord* dbg = nullptr;
+  // bound state
+  float *params = nullptr, *adam_m = nullptr, *adam_v = nullptr, *grads = nullptr;
+  int gemm_impl = GEMM_IMPL_TC;
+  long long launches = 0;
+  bool shadows_valid = false;
+};
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// parameter layout
+// ---------------------------------------------------------------------------------------------
+int add_tensor(drvae_plan* pl, const std::string& name, int rows, int cols) {
+  ParamInfo t;
+  t.name = name;
+  t.rows = rows;
+  t.cols = cols;
+  t.off = pl->P;
+  pl->P += rows * (cols > 0 ? cols : 1);
+  pl->tensors.push_back(t);
+  return (int)pl->tensors.size() - 1;
+}
+
+void add_seg_plain(drvae_plan* pl, int tid) {
+  const ParamInfo& t = pl->tensors[tid];
+  Seg s{};
+  s.off = t.off;
+  s.rows = t.rows;
+  s.cols = t.cols > 0 ? t.cols : 1;
+  s.kind = SEG_PLAIN;
+  s.wn_g_off = -1;
+  s.ilv_block = s.ilv_stride = 1 << 30;
+  pl->segs.push_back(s);
+}
+
+// Allocate shadow storage + derived bias for a GEMM weight made of `ntens` reference tensors.
+Shadow make_shadow(drvae_plan* pl, int ntens, const int* w_tid, const int* b_tid, int rows_each, int kin, int class_cols,
+                   int ilv_block, int ilv_stride, int BN, int tiles_n, const float* bias_const) {
+  Shadow sh{};
+  sh.ntens = ntens;
+  sh.kin = kin;
+  sh.kc = round_up(kin, 16);
+  sh.BN = BN;
+  sh.tiles_n = tiles_n;
+  sh.rcap = BN * tiles_n;
+  Tiling tx = tile_cap(kin);
+  sh.BNx = tx.BN;
+  sh.tiles_nx = tx.tiles;
+  sh.ilv_block = ilv_block;
+  sh.ilv_stride = ilv_stride;
+  sh.ld = kin + class_cols;
+  sh.off = pl->shadow_elems;
+  pl->shadow_elems += (long long)(sh.kc / 8) * sh.rcap * 8;
+  sh.bias_off = pl->derived_elems;
+  pl->derived_elems += sh.rcap;
+  sh.clsb_off = -1;
+  if (class_cols > 0) {
+    sh.clsb_off = pl->derived_elems;
+    pl->derived_elems += (long long)class_cols * sh.rcap;
+  }
+  int max_srow = 0;
+  for (int w = 0; w < ntens; ++w) {
+    const ParamInfo& wt = pl->tensors[w_tid[w]];
+    const ParamInfo& bt = pl->tensors[b_tid[w]];
+    sh.w_off[w] = wt.off;
+    sh.b_off[w] = bt.off;
+    sh.rows_each[w] = rows_each;
+    Seg s{};
+    s.off = wt.off;
+    s.rows = wt.rows;
+    s.cols = wt.cols;
+    s.kind = SEG_W;
+    s.sh_off = sh.off;
+    s.sh_rcap = sh.rcap;
+    s.kmain = kin;
+    s.which = w;
+    s.ilv_block = ilv_block;
+    s.ilv_stride = ilv_stride;
+    s.clsb_off = sh.clsb_off;
+    s.clsb_ld = sh.rcap;
+    s.wn_g_off = -1;
+    pl->segs.push_back(s);
+    Seg b{};
+    b.off = bt.off;
+    b.rows = bt.rows;
+    b.cols = 1;
+    b.kind = SEG_B;
+    b.which = w;
+    b.ilv_block = ilv_block;
+    b.ilv_stride = ilv_stride;
+    b.bias_off = sh.bias_off;
+    b.bias_const = bias_const ? bias_const[w] : 0.f;
+    b.wn_g_off = -1;
+    pl->segs.push_back(b);
+    const int n = rows_each - 1;
+    const int srow = (n / ilv_block) * ilv_stride + w * ilv_block + (n % ilv_block);
+    if (srow > max_srow) max_srow = srow;
+  }
+  sh.nout_total = max_srow + 1;
+  return sh;
+}
+
+// blocks.DiagGaussianModule / DiagGaussianSigmaModule: hidden MLP + two heads.
+void build_gauss_block(drvae_plan* pl, MlpBlock& blk, const std::string& prefix, int in_dim, int class_cols, int nh,
+                       const int* widths, int out_dim, bool sigma_heads) {
+  blk.class_aug = class_cols > 0;
+  int prev = in_dim;
+  for (int i = 0; i < nh; ++i) {
+    char nm[160];
+    snprintf(nm, sizeof(nm), "%s.nnet.model.linear%d", prefix.c_str(), i + 1);
+    const int cc = (i == 0) ? class_cols : 0;
+    int w = add_tensor(pl, std::string(nm) + ".weight", widths[i], prev + cc);
+    int b = add_tensor(pl, std::string(nm) + ".bias", widths[i], 0);
+    Tiling t = tile_cap(widths[i]);
+    blk.hidden.push_back(make_shadow(pl, 1, &w, &b, widths[i], prev, cc, 1 << 30, 1 << 30, t.BN, t.tiles, nullptr));
+    blk.widths.push_back(widths[i]);
+    prev = widths[i];
+  }
+  int wt[2], bt[2];
+  if (!sigma_heads) {
+    wt[0] = add_tensor(pl, prefix + ".encoder_mu.linear_mu.weight", out_dim, prev);
+    bt[0] = add_tensor(pl, prefix + ".encoder_mu.linear_mu.bias", out_dim, 0);
+    wt[1] = add_tensor(pl, prefix + ".encoder_lv.linear_lv.weight", out_dim, prev);
+    bt[1] = add_tensor(pl, prefix + ".encoder_lv.linear_lv.bias", out_dim, 0);
+    const float bc[2] = {0.f, -2.f};  // logvar = lin(h) - 2  (blocks.py:296)
+    Tiling t = tile_cap(2 * out_dim);
+    blk.head = make_shadow(pl, 2, wt, bt, out_dim, prev, 0, out_dim, 2 * out_dim, t.BN, t.tiles, bc);
+  } else {
+    wt[0] = add_tensor(pl, prefix + ".encoder_mu.linear_mu.weight", out_dim, prev);
+    bt[0] = add_tensor(pl, prefix + ".encoder_mu.linear_mu.bias", out_dim, 0);
+    wt[1] = add_tensor(pl, prefix + ".encoder_sg.linear_sg.weight", out_dim, prev);
+    bt[1] = add_tensor(pl, prefix + ".encoder_sg.linear_sg.bias", out_dim, 0);
+    const int hb = std::min(128, round_up(out_dim, 16));
+    pl->dec_hb = hb;
+    blk.head = make_shadow(pl, 2, wt, bt, out_dim, prev, 0, hb, 2 * hb, 2 * hb, cdiv(out_dim, hb), nullptr);
+  }
+}
+
+struct ArenaBuilder {
+  size_t total = 0;
+  int E;
+  std::map<std::string, BufRec>* bufs;
+  BufRec take(const std::string& name, size_t bytes_per_model, int rcap = 0, int fcap = 0) {
+    BufRec r;
+    r.off = total;
+    r.bytes = bytes_per_model;
+    r.ms_bytes = (bytes_per_model + 255) / 256 * 256;
+    r.rcap = rcap;
+    r.fcap = fcap;
+    total += r.ms_bytes * E;
+    (*bufs)[name] = r;
+    return r;
+  }
+};
+
+template <class T>
+MBuf<T> mbuf_of(drvae_plan* pl, const BufRec& r) {
+  MBuf<T> b;
+  b.p = reinterpret_cast<T*>(pl->arena + r.off);
+  b.ms = (long long)(r.ms_bytes / sizeof(T));
+  return b;
+}
+C8Buf c8_of(drvae_plan* pl, const BufRec& r) {
+  C8Buf b;
+  b.p = reinterpret_cast<bf16*>(pl->arena + r.off);
+  b.ms = (long long)(r.ms_bytes / sizeof(bf16));
+  b.rcap = r.rcap;
+  b.fcap = r.fcap;
+  return b;
+}
+
+}  // namespace
+
+// =============================================================================================
+// plan creation
+// =============================================================================================
+extern "C" int drvae_plan_create(const drvae_arch_t* a, int n_models, drvae_plan_t** out) {
+  if (!a || !out) return set_error("drvae_plan_create: null argument");
+  if (n_models < 1) return set_error("drvae_plan_create: n_models must be >= 1");
+  if (a->kind < 0 || a->kind > 2) return set_error("drvae_plan_create: unknown model kind");
+  if (a->weight_norm) return set_error("drvae_plan_create: weight_norm=True is not implemented yet (model.wn is False in every shipped configuration)");
+  if (a->dim_x < 1 || a->dim_z1 < 1 || a->L < 1 || a->max_batch < 1) return set_error("drvae_plan_create: bad dimensions");
+  if (a->dim_z1 > 32 * MAXJ) return set_error("drvae_plan_create: dim_z1 > 256 is not supported");
+  if (a->kind != DRVAE_KIND_PVAE && (a->dim_y < 2 || a->dim_y > MAXY)) return set_error("drvae_plan_create: dim_y must be in [2, 8]");
+  if (a->kind != DRVAE_KIND_PVAE && (a->dim_z3 < 1 || a->dim_z3 > 32 * MAXJ)) return set_error("drvae_plan_create: bad dim_z3");
+  if (a->n_enc_z1 < 1 || a->n_enc_z1 > DRVAE_MAX_HIDDEN || a->n_dec_x < 1 || a->n_dec_x > DRVAE_MAX_HIDDEN)
+    return set_error("drvae_plan_create: enc_z1 / dec_x need between 1 and 4 hidden layers");
+  if (a->kind != DRVAE_KIND_PVAE &&
+      (a->n_enc_z3 < 1 || a->n_enc_z3 > DRVAE_MAX_HIDDEN || a->n_dec_z1 < 1 || a->n_dec_z1 > DRVAE_MAX_HIDDEN))
+    return set_error("drvae_plan_create: enc_z3 / dec_z1 need between 1 and 4 hidden layers");
+
+  drvae_plan* pl = new drvae_plan();
+  pl->arch = *a;
+  pl->E = n_models;
+  pl->X = a->dim_x;
+  pl->Y = (a->kind == DRVAE_KIND_PVAE) ? 1 : a->dim_y;
+  pl->Z = a->dim_z1;
+  pl->Z3 = (a->kind == DRVAE_KIND_PVAE) ? 1 : a->dim_z3;
+  pl->L = a->L;
+  pl->Ncap = a->max_batch;
+  pl->has_pair = a->kind != DRVAE_KIND_VFAE;
+  pl->has_T = a->kind != DRVAE_KIND_VFAE;
+  pl->has_clf = a->kind != DRVAE_KIND_PVAE;
+  pl->has_fprop = a->kind != DRVAE_KIND_PVAE;
+  pl->clf_in = (a->kind == DRVAE_KIND_DRVAE) ? 2 * pl->Z : pl->Z;
+  const int X = pl->X, Y = pl->Y, Z = pl->Z, Z3 = pl->Z3, L = pl->L, E = pl->E;
+
+  // ---- parameters in the reference's state_dict order ----
+  build_gauss_block(pl, pl->enc, "encoder_z1", X, 0, a->n_enc_z1, a->enc_z1, Z, false);
+  if (pl->has_T) {
+    // DiagGaussianModuleLinear (blocks.py:304-361): W_mu, bias_mu are bare Parameters
+    int wt[2], bt[2];
+    wt[0] = add_tensor(pl, "decoder_z2Fz1.W_mu", Z, Z);
+    bt[0] = add_tensor(pl, "decoder_z2Fz1.bias_mu", Z, 0);
+    wt[1] = add_tensor(pl, "decoder_z2Fz1.encoder_lv.linear_lv.weight", Z, Z);
+    bt[1] = add_tensor(pl, "decoder_z2Fz1.encoder_lv.linear_lv.bias", Z, 0);
+    const float bc[2] = {0.f, -2.f};
+    Tiling t = tile_cap(2 * Z);
+    pl->Tsh = make_shadow(pl, 2, wt, bt, Z, Z, 0, Z, 2 * Z, t.BN, t.tiles, bc);
+  }
+  if (pl->has_clf) {
+    int w = add_tensor(pl, "encoder_y.decoder_p.linear_p.weight", Y, pl->clf_in);
+    int b = add_tensor(pl, "encoder_y.decoder_p.linear_p.bias", Y, 0);
+    pl->clf_w_off = pl->tensors[w].off;
+    pl->clf_b_off = pl->tensors[b].off;
+    add_seg_plain(pl, w);
+    add_seg_plain(pl, b);
+  }
+  if (pl->has_fprop) {
+    const char* top = (a->kind == DRVAE_KIND_DRVAE) ? "encoder_z3" : "encoder_z2";
+    build_gauss_block(pl, pl->z3b, top, Z, Y, a->n_enc_z3, a->enc_z3, Z3, false);
+    build_gauss_block(pl, pl->dz1b, "decoder_z1", Z3, Y, a->n_dec_z1, a->dec_z1, Z, false);
+  }
+  build_gauss_block(pl, pl->dec, "decoder_x", Z, 0, a->n_dec_x, a->dec_x, X, true);
+  std::sort(pl->segs.begin(), pl->segs.end(), [](const Seg& x, const Seg& y) { return x.off < y.off; });
+
+  // ---- workspace ----
+  const int Ncap = pl->Ncap;
+  const int R0cap = round_up((pl->has_pair ? 2 : 1) * Ncap, 128);
+  const int LNcap = round_up(L * Ncap, 128);
+  const int Rdcap = round_up((pl->has_pair ? 3 : 1) * L * Ncap, 128);
+  const int Flcap = pl->has_fprop ? Y * Ncap : 0;
+  const int Fcap = round_up(std::max(1, L * Flcap), 128);
+  const int Xc = round_up(X, 16);
+  const int Zc = tile_cap(Z).cap, Z3c = tile_cap(Z3).cap;
+
+  ArenaBuilder ab;
+  ab.E = E;
+  ab.bufs = &pl->bufs;
+  auto F32 = [&](const char* n, size_t elems) { return ab.take(n, elems * 4); };
+  auto I32 = [&](const char* n, size_t elems) { return ab.take(n, elems * 4); };
+  auto C8 = [&](const std::string& n, int rcap, int fcap) { return ab.take(n, (size_t)rcap * fcap * 2, rcap, fcap); };
+
+  BufRec r_shadow = ab.take("shadow", (size_t)pl->shadow_elems * 2);
+  BufRec r_derived = F32("derived", pl->derived_elems);
+  // ε block
+  drvae_eps_layout_t& el = pl->epsl;
+  el.off_x1 = 0;
+  el.off_x2 = el.off_x1 + (long long)Ncap * X;
+  el.off_z1 = el.off_x2 + (long long)Ncap * X;
+  el.off_z2 = el.off_z1 + (long long)L * Ncap * Z;
+  el.off_z2f = el.off_z2 + (long long)L * Ncap * Z;
+  el.off_z3 = el.off_z2f + (long long)L * Ncap * Z;
+  el.total = el.off_z3 + (long long)L * Ncap * Y * Z3;
+  BufRec r_eps = F32("eps", el.total);
+  BufRec r_counts = I32("counts", CNT_SIZE), r_coefs = F32("coefs", COEF_SIZE);
+  BufRec r_pair_of = I32("pair_of", Ncap), r_row_of_pair = I32("row_of_pair", Ncap), r_ebase = I32("ebase", Ncap);
+  BufRec r_lab = I32("lab", Ncap), r_ycls = I32("ycls", Ncap), r_e_row = I32("e_row", std::max(1, Flcap));
+  BufRec r_e_jj = I32("e_jj", std::max(1, Flcap)), r_e_cls = I32("e_cls_full", Fcap);
+  BufRec r_tgt = F32("tgt", (size_t)R0cap * X);
+  BufRec r_Ain = C8("Ain", R0cap, Xc);
+  BufRec r_Q = F32("Q", (size_t)R0cap * 2 * Z), r_Z1f = F32("Z1f", (size_t)LNcap * Z);
+  BufRec r_Zdec = C8("Zdec", Rdcap, Zc), r_Z1e = C8("Z1e", Fcap, Zc);
+  BufRec r_PT = F32("PT", (size_t)LNcap * 2 * Z), r_Z2Ff = F32("Z2Ff", (size_t)LNcap * Z);
+  BufRec r_QY = F32("QY", (size_t)LNcap * Y), r_Q3 = F32("Q3", (size_t)Fcap * 2 * Z3);
+  BufRec r_Z3b = C8("Z3b", Fcap, Z3c), r_PZ1 = F32("PZ1", (size_t)Fcap * 2 * Z);
+  BufRec r_klq = F32("klq_row", R0cap), r_klz2 = F32("klz2_row", LNcap), r_yl = F32("yl_row", LNcap);
+  BufRec r_ycat = F32("ycat_row", LNcap), r_kfp = F32("kfp_row", Fcap), r_kfpw = F32("kfpw_row", Fcap);
+  const int dec_tiles = pl->dec.head.tiles_n;
+  BufRec r_part = F32("dec_part", (size_t)dec_tiles * Rdcap);
+  BufRec r_dY5 = C8("dY5", Rdcap, pl->dec.head.rcap);
+  BufRec r_dY9 = C8("dY9", Fcap, pl->has_fprop ? pl->dz1b.head.rcap : 16);
+  BufRec r_dY7 = C8("dY7", Fcap, pl->has_fprop ? pl->z3b.head.rcap : 16);
+  BufRec r_dYT = C8("dYT", LNcap, pl->has_T ? pl->Tsh.rcap : 16);
+  BufRec r_dY2 = C8("dY2", R0cap, pl->enc.head.rcap);
+  BufRec r_dQ1e = F32("dQ1e", (size_t)Fcap * 2 * Z), r_dQ2 = F32("dQ2", (size_t)Ncap * 2 * Z);
+  BufRec r_dZ3 = F32("dZ3", (size_t)Fcap * Z3), r_dZ1e = F32("dZ1e", (size_t)Fcap * Z);
+  BufRec r_dZdec = F32("dZdec", (size_t)Rdcap * Z), r_dZ1T = F32("dZ1T", (size_t)LNcap * Z);
+  BufRec r_DZ1 = F32("DZ1", (size_t)LNcap * Z), r_DZ2F = F32("DZ2F", (size_t)LNcap * Z);
+  BufRec r_dlogit = F32("dlogit", (size_t)LNcap * Y);
+  BufRec r_clfp = F32("clf_part", (size_t)CLF_SPLITS * Y * (pl->clf_in + 1));
+  BufRec r_losses = F32("losses", 8);
+  // per-block activations
+  struct BlkAlloc {
+    MlpBlock* b;
+    const char* nm;
+    int rcap;
+  };
+  BlkAlloc blks[4] = {{&pl->enc, "enc", R0cap}, {&pl->dec, "dec", Rdcap}, {&pl->z3b, "z3", Fcap}, {&pl->dz1b, "dz1", Fcap}};
+  std::vector<std::pair<C8Buf*, BufRec>> pend;
+  for (auto& ba : blks) {
+    ba.b->H.resize(ba.b->hidden.size());
+    ba.b->dPre.resize(ba.b->hidden.size());
+    for (size_t i = 0; i < ba.b->hidden.size(); ++i) {
+      const int fcap = ba.b->hidden[i].rcap;
+      pend.push_back({&ba.b->H[i], C8(std::string(ba.nm) + ".H" + std::to_string(i), ba.rcap, fcap)});
+      pend.push_back({&ba.b->dPre[i], C8(std::string(ba.nm) + ".dPre" + std::to_string(i), ba.rcap, fcap)});
+    }
+  }
+  pl->arena_bytes = ab.total;
+  cudaError_t err = cudaMalloc(&pl->arena, pl->arena_bytes);
+  if (err != cudaSuccess) {
+    delete pl;
+    return set_cuda_error("drvae_plan_create: cudaMalloc(workspace)", err);
+  }
+  cudaMemset(pl->arena, 0, pl->arena_bytes);
+  cudaMalloc(&pl->dbg, sizeof(DebugWord));
+  cudaMemset(pl->dbg, 0, sizeof(DebugWord));
+  cudaMalloc(&pl->d_segs, pl->segs.size() * sizeof(Seg));
+  cudaMemcpy(pl->d_segs, pl->segs.data(), pl->segs.size() * sizeof(Seg), cudaMemcpyHostToDevice);
+  for (auto& pr : pend) *pr.first = c8_of(pl, pr.second);
+
+  pl->shadow = mbuf_of<bf16>(pl, r_shadow);
+  pl->derived = mbuf_of<float>(pl, r_derived);
+  pl->eps_own = mbuf_of<float>(pl, r_eps);
+  pl->dY5 = c8_of(pl, r_dY5);
+
+  DevView& v = pl->view;
+  memset(&v, 0, sizeof(v));
+  v.kind = a->kind;
+  v.X = X;
+  v.Y = Y;
+  v.Z = Z;
+  v.Z3 = Z3;
+  v.L = L;
+  v.Ncap = Ncap;
+  v.Xc = Xc;
+  v.Zc = Zc;
+  v.Z3c = Z3c;
+  v.R0cap = R0cap;
+  v.LNcap = LNcap;
+  v.Rdcap = Rdcap;
+  v.Fcap = Fcap;
+  v.Flcap = Flcap;
+  v.has_pair = pl->has_pair;
+  v.has_T = pl->has_T;
+  v.has_clf = pl->has_clf;
+  v.has_fprop = pl->has_fprop;
+  v.clf_in = pl->clf_in;
+  v.counts = mbuf_of<int>(pl, r_counts);
+  v.coefs = mbuf_of<float>(pl, r_coefs);
+  v.pair_of = mbuf_of<int>(pl, r_pair_of);
+  v.row_of_pair = mbuf_of<int>(pl, r_row_of_pair);
+  v.ebase = mbuf_of<int>(pl, r_ebase);
+  v.lab = mbuf_of<int>(pl, r_lab);
+  v.ycls = mbuf_of<int>(pl, r_ycls);
+  v.e_row = mbuf_of<int>(pl, r_e_row);
+  v.e_jj = mbuf_of<int>(pl, r_e_jj);
+  v.e_cls_full = mbuf_of<int>(pl, r_e_cls);
+  v.tgt = mbuf_of<float>(pl, r_tgt);
+  v.Ain = c8_of(pl, r_Ain);
+  v.Q = mbuf_of<float>(pl, r_Q);
+  v.Z1f = mbuf_of<float>(pl, r_Z1f);
+  v.Zdec = c8_of(pl, r_Zdec);
+  v.Z1e = c8_of(pl, r_Z1e);
+  v.PT = mbuf_of<float>(pl, r_PT);
+  v.Z2Ff = mbuf_of<float>(pl, r_Z2Ff);
+  v.QY = mbuf_of<float>(pl, r_QY);
+  v.Q3 = mbuf_of<float>(pl, r_Q3);
+  v.Z3b = c8_of(pl, r_Z3b);
+  v.PZ1 = mbuf_of<float>(pl, r_PZ1);
+  v.klq_row = mbuf_of<float>(pl, r_klq);
+  v.klz2_row = mbuf_of<float>(pl, r_klz2);
+  v.yl_row = mbuf_of<float>(pl, r_yl);
+  v.ycat_row = mbuf_of<float>(pl, r_ycat);
+  v.kfp_row = mbuf_of<float>(pl, r_kfp);
+  v.kfpw_row = mbuf_of<float>(pl, r_kfpw);
+  v.dec_part = mbuf_of<float>(pl, r_part);
+  v.dec_tiles = dec_tiles;
+  v.dY9 = c8_of(pl, r_dY9);
+  v.dY7 = c8_of(pl, r_dY7);
+  v.dYT = c8_of(pl, r_dYT);
+  v.dY2 = c8_of(pl, r_dY2);
+  v.dQ1e = mbuf_of<float>(pl, r_dQ1e);
+  v.dQ2 = mbuf_of<float>(pl, r_dQ2);
+  v.dZ3 = mbuf_of<float>(pl, r_dZ3);
+  v.dZ1e = mbuf_of<float>(pl, r_dZ1e);
+  v.dZdec = mbuf_of<float>(pl, r_dZdec);
+  v.dZ1T = mbuf_of<float>(pl, r_dZ1T);
+  v.DZ1 = mbuf_of<float>(pl, r_DZ1);
+  v.DZ2F = mbuf_of<float>(pl, r_DZ2F);
+  v.dlogit = mbuf_of<float>(pl, r_dlogit);
+  v.clf_part = mbuf_of<float>(pl, r_clfp);
+  v.losses = mbuf_of<float>(pl, r_losses);
+  v.clf_w_off = pl->clf_w_off;
+  v.clf_b_off = pl->clf_b_off;
+  *out = pl;
+  return 0;
+}
+
+extern "C" int drvae_plan_destroy(drvae_plan_t* pl) {
+  if (!pl) return 0;
+  if (pl->arena) cudaFree(pl->arena);
+  if (pl->dbg) cudaFree(pl->dbg);
+  if (pl->d_segs) cudaFree(pl->d_segs);
+  delete pl;
+  return 0;
+}
+
+extern "C" long long drvae_plan_param_count(const drvae_plan_t* pl) { return pl ? pl->P : -1; }
+extern "C" int drvae_plan_num_tensors(const drvae_plan_t* pl) { return pl ? (int)pl->tensors.size() : -1; }
+extern "C" int drvae_plan_tensor_info(const drvae_plan_t* pl, int index, char* name, int name_cap, int* rows, int* cols,
+                                      long long* offset) {
+  if (!pl || index < 0 || index >= (int)pl->tensors.size()) return set_error("drvae_plan_tensor_info: bad index");
+  const ParamInfo& t = pl->tensors[index];
+  if (name && name_cap > 0) {
+    strncpy(name, t.name.c_str(), name_cap - 1);
+    name[name_cap - 1] = 0;
+  }
+  if (rows) *rows = t.rows;
+  if (cols) *cols = t.cols;
+  if (offset) *offset = t.off;
+  return 0;
+}
+extern "C" int drvae_plan_eps_layout(const drvae_plan_t* pl, drvae_eps_layout_t* out) {
+  if (!pl || !out) return set_error("drvae_plan_eps_layout: null argument");
+  *out = pl->epsl;
+  return 0;
+}
+extern "C" long long drvae_plan_workspace_bytes(const drvae_plan_t* pl) { return pl ? (long long)pl->arena_bytes : -1; }
+extern "C" long long drvae_plan_launch_count(const drvae_plan_t* pl) { return pl ? pl->launches : -1; }
+extern "C" int drvae_set_gemm_impl(drvae_plan_t* pl, int impl) {
+  if (!pl || (impl != GEMM_IMPL_TC && impl != GEMM_IMPL_SIMT)) return set_error("drvae_set_gemm_impl: bad argument");
+  pl->gemm_impl = impl;
+  return 0;
+}
+
+extern "C" int drvae_plan_bind(drvae_plan_t* pl, float* params, float* adam_m, float* adam_v, float* grads) {
+  if (!pl || !params) return set_error("drvae_plan_bind: params must not be null");
+  pl->params = params;
+  pl->adam_m = adam_m;
+  pl->adam_v = adam_v;
+  pl->grads = grads;
+  pl->shadows_valid = false;
+  return 0;
+}
+
+extern "C" int drvae_debug_buffer(drvae_plan_t* pl, const char* name, void** ptr, long long* ms_bytes, long long* bytes,
+                                  int* rcap, int* fcap) {
+  if (!pl || !name) return set_error("drvae_debug_buffer: null argument");
+  auto it = pl->bufs.find(name);
+  if (it == pl->bufs.end()) return set_error("drvae_debug_buffer: unknown buffer");
+  if (ptr) *ptr = pl->arena + it->second.off;
+  if (ms_bytes) *ms_bytes = (long long)it->second.ms_bytes;
+  if (bytes) *bytes = (long long)it->second.bytes;
+  if (rcap) *rcap = it->second.rcap;
+  if (fcap) *fcap = it->second.fcap;
+  return 0;
+}
+
+// =============================================================================================
+// step executor
+// =============================================================================================
+namespace {
+
+struct Exec {
+  drvae_plan* pl;
+  cudaStream_t st;
+  DevView v;
+  int N;
+  cudaError_t err = cudaSuccess;
+  bool ok() const { return err == cudaSuccess; }
+  void chk() {
+    if (err == cudaSuccess) err = cudaGetLastError();
+    pl->launches++;
+  }
+
+  const int* cnt(int which) const { return v.counts.p + which; }
+
+  GemmOperand op_c8(const C8Buf& b, int row0) const { return GemmOperand{b.p, b.ms, b.rcap, b.fcap >> 3, row0}; }
+  GemmOperand op_shadow(const Shadow& s) const {
+    return GemmOperand{pl->shadow.p + s.off, pl->shadow.ms, s.rcap, s.kc >> 3, 0};
+  }
+  EpiParams epi_base() const {
+    EpiParams e;
+    memset(&e, 0, sizeof(e));
+    e.ilv_block = e.ilv_stride = 1 << 30;
+    return e;
+  }
+  void launch(int epi, GemmProblem& p, const EpiParams& e) {
+    if (!ok()) return;
+    p.dbg = pl->dbg;
+    p.desc_variant = 0;
+    if (p.ksplit < 1) p.ksplit = 1;
+    cudaError_t r = gemm_launch(epi, p, e, pl->E, pl->gemm_impl, st);
+    if (r != cudaSuccess) err = r;
+    pl->launches++;
+  }
+
+  // D[rows, W.rcap] = A[rows, kin] . W^T
+  void gemm_nt(const C8Buf& A, int a_row0, const Shadow& W, int epi, EpiParams e, int dyn_which, int row_bound) {
+    GemmProblem p{};
+    p.A = op_c8(A, a_row0);
+    p.B = op_shadow(W);
+    p.mode = GEMM_NT;
+    p.M = row_bound;
+    p.N = W.rcap;
+    p.K = W.kc;
+    p.dyn = cnt(dyn_which);
+    p.dyn_stride = (int)v.counts.ms;
+    p.BN = W.BN;
+    p.tiles_n = W.tiles_n;
+    p.tiles_m = cdiv(row_bound, GEMM_BM);
+    launch(epi, p, e);
+  }
+  // D[rows, kin] = dY[rows, nout] . W
+  void gemm_dx(const C8Buf& dY, const Shadow& W, int epi, EpiParams e, int dyn_which, int row_bound) {
+    GemmProblem p{};
+    p.A = op_c8(dY, 0);
+    p.B = op_shadow(W);
+    p.mode = GEMM_DX;
+    p.M = row_bound;
+    p.N = W.kc;
+    p.K = round_up(W.nout_total, 16);
+    p.dyn = cnt(dyn_which);
+    p.dyn_stride = (int)v.counts.ms;
+    p.BN = W.BNx;
+    p.tiles_n = W.tiles_nx;
+    p.tiles_m = cdiv(row_bound, GEMM_BM);
+    launch(epi, p, e);
+  }
+  // grad W[nout, kin] = dY[rows, nout]^T . Xin[rows, kin]
+  void gemm_dw(const C8Buf& dY, const C8Buf& Xin, int x_row0, const Shadow& W, int dyn_which, int row_bound) {
+    GemmProblem p{};
+    p.A = op_c8(dY, 0);
+    p.B = op_c8(Xin, x_row0);
+    p.mode = GEMM_DW;
+    p.M = W.rcap;
+    p.N = W.kc;
+    p.K = row_bound;
+    p.dyn = cnt(dyn_which);
+    p.dyn_stride = (int)v.counts.ms;
+    p.BN = W.BNx;
+    p.tiles_n = W.tiles_nx;
+    p.tiles_m = cdiv(W.rcap, GEMM_BM);
+    p.ksplit = 1;
+    EpiParams e = epi_base();
+    e.grad = v.grads.p;
+    e.grad_ms = v.grads.ms;
+    e.g_ntens = W.ntens;
+    for (int w = 0; w < W.ntens; ++w) {
+      e.g_off[w] = W.w_off[w];
+      e.g_rows[w] = W.rows_each[w];
+    }
+    e.g_ld = W.ld;
+    e.g_kvalid = W.kin;
+    e.ilv_block = W.ilv_block;
+    e.ilv_stride = W.ilv_stride;
+    launch(EPI_GRAD, p, e);
+  }
+  void colsum(const C8Buf& dY, const Shadow& W, int dyn_which, bool class_cols) {
+    if (!ok()) return;
+    ColsumArgs a{};
+    a.src = dY;
+    a.dyn = cnt(dyn_which);
+    a.dyn_stride = (int)v.counts.ms;
+    a.grads = v.grads;
+    a.ntens = W.ntens;
+    for (int w = 0; w < W.ntens; ++w) {
+      a.b_off[w] = W.b_off[w];
+      a.rows_each[w] = W.rows_each[w];
+    }
+    a.ilv_block = W.ilv_block;
+    a.ilv_stride = W.ilv_stride;
+    a.row_cls = class_cols ? v.e_cls_full.p : nullptr;
+    a.row_cls_ms = v.e_cls_full.ms;
+    a.Y = v.Y;
+    a.w_off = W.w_off[0];
+    a.ld = W.ld;
+    a.kmain = W.kin;
+    dim3 grid(cdiv(dY.fcap >> 3, 4), pl->E);
+    colsum_kernel<<<grid, 128, 0, st>>>(a);
+    chk();
+  }
+
+  EpiParams epi_elu(const Shadow& W, const C8Buf& out, int width, bool class_aug) const {
+    EpiParams e = epi_base();
+    e.out_c8 = out.p;
+    e.out_c8_ms = out.ms;
+    e.out_c8_rcap = out.rcap;
+    e.n_valid = width;
+    e.bias = pl->derived.p + W.bias_off;
+    e.bias_ms = pl->derived.ms;
+    if (class_aug) {
+      e.clsb = pl->derived.p + W.clsb_off;
+      e.clsb_ms = pl->derived.ms;
+      e.clsb_ld = W.rcap;
+      e.row_cls = v.e_cls_full.p;
+      e.row_cls_ms = v.e_cls_full.ms;
+    }
+    return e;
+  }
+  EpiParams epi_f32(float* out, long long ms, int ld, int n_valid, const Shadow* bias_of) const {
+    EpiParams e = epi_base();
+    e.out_f32 = out;
+    e.out_f32_ms = ms;
+    e.out_ld = ld;
+    e.n_valid = n_valid;
+    if (bias_of) {
+      e.bias = pl->derived.p + bias_of->bias_off;
+      e.bias_ms = pl->derived.ms;
+    }
+    return e;
+  }
+  EpiParams epi_dact(const C8Buf& act, const C8Buf& out, int width) const {
+    EpiParams e = epi_base();
+    e.out_c8 = out.p;
+    e.out_c8_ms = out.ms;
+    e.out_c8_rcap = out.rcap;
+    e.act = act.p;
+    e.act_ms = act.ms;
+    e.act_rcap = act.rcap;
+    e.n_valid = width;
+    return e;
+  }
+
+  // hidden layers of a block: in -> H[0] -> ... -> H[n-1]
+  void block_hidden_fwd(MlpBlock& b, const C8Buf& in, int in_row0, int dyn_which, int row_bound) {
+    for (size_t i = 0; i < b.hidden.size(); ++i) {
+      const C8Buf& src = (i == 0) ? in : b.H[i - 1];
+      gemm_nt(src, i == 0 ? in_row0 : 0, b.hidden[i], EPI_ELU_C8, epi_elu(b.hidden[i], b.H[i], b.widths[i], b.class_aug && i == 0),
+              dyn_which, row_bound);
+    }
+  }
+  // backward of a block given the head gradient rows dYh; optionally the input gradient as fp32
+  void block_bwd(MlpBlock& b, const C8Buf& dYh, const C8Buf& in, int in_row0, int in_feat, float* dx_out, long long dx_ms,
+                 int dyn_which, int row_bound) {
+    const int n = (int)b.hidden.size();
+    gemm_dw(dYh, b.H[n - 1], 0, b.head, dyn_which, row_bound);
+    colsum(dYh, b.head, dyn_which, false);
+    gemm_dx(dYh, b.head, EPI_DACT_C8, epi_dact(b.H[n - 1], b.dPre[n - 1], b.widths[n - 1]), dyn_which, row_bound);
+    for (int i = n - 1; i >= 0; --i) {
+      const C8Buf& src = (i == 0) ? in : b.H[i - 1];
+      gemm_dw(b.dPre[i], src, i == 0 ? in_row0 : 0, b.hidden[i], dyn_which, row_bound);
+      colsum(b.dPre[i], b.hidden[i], dyn_which, b.class_aug && i == 0);
+      if (i > 0) {
+        gemm_dx(b.dPre[i], b.hidden[i], EPI_DACT_C8, epi_dact(b.H[i - 1], b.dPre[i - 1], b.widths[i - 1]), dyn_which, row_bound);
+      } else if (dx_out) {
+        gemm_dx(b.dPre[0], b.hidden[0], EPI_STORE_F32, epi_f32(dx_out, dx_ms, in_feat, in_feat, nullptr), dyn_which, row_bound);
+      }
+    }
+  }
+};
+
+int fill_view(drvae_plan* pl, Exec& ex, const drvae_batch_t* b, const drvae_noise_t* nz, const drvae_hparams_t* hp,
+              bool need_grad) {
+  if (!pl->params) return set_error("drvae: plan has no bound parameters (drvae_plan_bind)");
+  if (!b || !b->x1) return set_error("drvae: batch.x1 is null");
+  if (b->N < 1 || b->N > pl->Ncap) return set_error("drvae: batch.N exceeds the plan's max_batch");
+  if (pl->has_pair && (!b->x2 || !b->has_x2)) return set_error("drvae: this model needs x2 and has_x2");
+  if (pl->has_clf && (!b->y || !b->has_y)) return set_error("drvae: this model needs y and has_y");
+  if (need_grad && !pl->grads) return set_error("drvae: no gradient buffer bound");
+  DevView& v = ex.v;
+  v = pl->view;
+  const int N = b->N;
+  ex.N = N;
+  v.N = N;
+  v.need_grad = need_grad;
+  const long long rowsX = (long long)N * pl->X;
+  v.x1 = MBuf<const float>{b->x1, rowsX};
+  v.x2 = MBuf<const float>{b->x2, rowsX};
+  v.y = MBuf<const int>{b->y, N};
+  v.has_x2 = MBuf<const int>{b->has_x2, N};
+  v.has_y = MBuf<const int>{b->has_y, N};
+  const float* eps = (nz && nz->eps) ? nz->eps : pl->eps_own.p;
+  const long long ems = (nz && nz->eps) ? pl->epsl.total : pl->eps_own.ms;
+  v.eps_x1 = MBuf<const float>{eps + pl->epsl.off_x1, ems};
+  v.eps_x2 = MBuf<const float>{eps + pl->epsl.off_x2, ems};
+  v.eps_z1 = MBuf<const float>{eps + pl->epsl.off_z1, ems};
+  v.eps_z2 = MBuf<const float>{eps + pl->epsl.off_z2, ems};
+  v.eps_z2f = MBuf<const float>{eps + pl->epsl.off_z2f, ems};
+  v.eps_z3 = MBuf<const float>{eps + pl->epsl.off_z3, ems};
+  v.params = MBuf<float>{pl->params, pl->P};
+  v.grads = MBuf<float>{pl->grads, pl->P};
+  v.adam_m = MBuf<float>{pl->adam_m, pl->P};
+  v.adam_v = MBuf<float>{pl->adam_v, pl->P};
+  StepScalars& s = v.s;
+  s.kl_min = hp->kl_min;
+  s.noise_std = hp->noise_std;
+  s.beta_pert = hp->beta_pert;
+  s.pertloss_rate = hp->pertloss_rate;
+  s.kl_qz2pz2_rate = hp->kl_qz2pz2_rate;
+  s.yloss_rate = hp->yloss_rate;
+  s.training = hp->training;
+  s.add_noise = hp->add_noise;
+  s.gN = hp->global_N;
+  s.gNp = hp->global_Np;
+  s.gNlab = hp->global_Nlab;
+  for (int j = 0; j < 8; ++j) s.log_prior[j] = hp->log_prior_y[j];
+  return 0;
+}
+
+int run_adam(drvae_plan* pl, const drvae_hparams_t* hp, int update, cudaStream_t st) {
+  if (!pl->params) return set_error("drvae: plan has no bound parameters");
+  if (update && (!pl->adam_m || !pl->adam_v || !pl->grads)) return set_error("drvae: Adam needs bound moments and gradients");
+  AdamArgs a{};
+  a.params = MBuf<float>{pl->params, pl->P};
+  a.grads = MBuf<float>{pl->grads, pl->P};
+  a.m = MBuf<float>{pl->adam_m, pl->P};
+  a.v = MBuf<float>{pl->adam_v, pl->P};
+  a.shadow = pl->shadow;
+  a.derived = pl->derived;
+  a.segs = pl->d_segs;
+  a.nseg = (int)pl->segs.size();
+  a.P = pl->P;
+  a.update = update;
+  if (update) {
+    const double t = (double)hp->step + 1.0;
+    a.lr = hp->lr;
+    a.beta1 = hp->beta1;
+    a.beta2 = hp->beta2;
+    a.eps = hp->adam_eps;
+    a.wd = hp->weight_decay;
+    a.bc1 = (float)(1.0 - pow((double)hp->beta1, t));
+    a.bc2 = (float)(1.0 - pow((double)hp->beta2, t));
+  }
+  dim3 grid(cdiv(pl->P, 1024), pl->E);
+  adam_kernel<<<grid, 256, 0, st>>>(a);
+  pl->launches++;
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return set_cuda_error("adam_kernel", err);
+  pl->shadows_valid = true;
+  return 0;
+}
+
+// forward (+ optional backward) of one minibatch per model
+int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, const drvae_hparams_t* hp, float* losses_out,
+             cudaStream_t st, bool backward) {
+  if (!hp) return set_error("drvae: hparams is null");
+  Exec ex;
+  ex.pl = pl;
+  ex.st = st;
+  int rc = fill_view(pl, ex, b, nz, hp, backward);
+  if (rc) return rc;
+  if (!pl->shadows_valid) {
+    rc = run_adam(pl, hp, 0, st);
+    if (rc) return rc;
+  }
+  DevView& v = ex.v;
+  const int E = pl->E, N = ex.N, L = pl->L;
+  const int R0b = (pl->has_pair ? 2 : 1) * N, LNb = L * N, Rdb = (pl->has_pair ? 3 : 1) * L * N;
+  const int Fb = std::max(1, L * pl->Y * N);
+  auto rows_grid = [&](int rows) { return dim3(cdiv(rows, ROW_WARPS), E); };
+
+  if (!(nz && nz->eps)) {
+    dim3 g(cdiv((int)cdiv((int)pl->epsl.total, 4), 256), E);
+    philox_normal_kernel<<<g, 256, 0, st>>>(pl->eps_own, pl->epsl.total, nz ? nz->seed : 0ULL, (unsigned)hp->step);
+    ex.chk();
+  }
+  rowmap_kernel<<<E, 256, 0, st>>>(v);
+  ex.chk();
+  prep_kernel<<<dim3(round_up(R0b, 128), E), 128, 0, st>>>(v);
+  ex.chk();
+
+  // ---- encoder q(z1|x1), shared with q(z2|x2) (DrVAE.py:408,418) ----
+  ex.block_hidden_fwd(pl->enc, v.Ain, 0, CNT_R0, R0b);
+  ex.gemm_nt(pl->enc.H.back(), 0, pl->enc.head, EPI_STORE_F32, ex.epi_f32(v.Q.p, v.Q.ms, 2 * pl->Z, 2 * pl->Z, &pl->enc.head),
+             CNT_R0, R0b);
+  sample_q1_kernel<<<rows_grid(N + PAD_ROWS), ROW_THREADS, 0, st>>>(v);
+  ex.chk();
+  // ---- p(z2|z1) ----
+  if (pl->has_T) {
+    ex.gemm_nt(v.Zdec, 0, pl->Tsh, EPI_STORE_F32, ex.epi_f32(v.PT.p, v.PT.ms, 2 * pl->Z, 2 * pl->Z, &pl->Tsh), CNT_LN, LNb);
+    T_post_kernel<<<rows_grid(N + PAD_ROWS), ROW_THREADS, 0, st>>>(v);
+    ex.chk();
+  }
+  // ---- decoder p(x|z) on the stacked rows [z1 | z2 | z2f], fused log-density + gradient ----
+  ex.block_hidden_fwd(pl->dec, v.Zdec, 0, CNT_RD, Rdb);
+  {
+    EpiParams e = ex.epi_base();
+    e.out_c8 = pl->dY5.p;
+    e.out_c8_ms = pl->dY5.ms;
+    e.out_c8_rcap = pl->dY5.rcap;
+    e.bias = pl->derived.p + pl->dec.head.bias_off;
+    e.bias_ms = pl->derived.ms;
+    e.tgt = v.tgt.p;
+    e.tgt_ms = v.tgt.ms;
+    e.X = pl->X;
+    e.counts = v.counts.p;
+    e.counts_stride = (int)v.counts.ms;
+    e.coefs = v.coefs.p;
+    e.coefs_stride = (int)v.coefs.ms;
+    e.L = L;
+    e.part = v.dec_part.p;
+    e.part_ms = v.dec_part.ms;
+    e.part_rcap = pl->view.Rdcap;
+    e.write_dy = backward ? 1 : 0;
+    ex.gemm_nt(pl->dec.H.back(), 0, pl->dec.head, EPI_DECLOSS, e, CNT_RD, Rdb);
+  }
+  // ---- label-dependent part: q(z_top|z1,y), p(z1|z_top,y) per (row, class) evaluation ----
+  if (pl->has_fprop) {
+    ex.block_hidden_fwd(pl->z3b, v.Z1e, 0, CNT_F, Fb);
+    ex.gemm_nt(pl->z3b.H.back(), 0, pl->z3b.head, EPI_STORE_F32,
+               ex.epi_f32(v.Q3.p, v.Q3.ms, 2 * pl->Z3, 2 * pl->Z3, &pl->z3b.head), CNT_F, Fb);
+    z3_post_kernel<<<rows_grid(round_up(Fb, 128)), ROW_THREADS, 0, st>>>(v);
+    ex.chk();
+    ex.block_hidden_fwd(pl->dz1b, v.Z3b, 0, CNT_F, Fb);
+    ex.gemm_nt(pl->dz1b.H.back(), 0, pl->dz1b.head, EPI_STORE_F32,
+               ex.epi_f32(v.PZ1.p, v.PZ1.ms, 2 * pl->Z, 2 * pl->Z, &pl->dz1b.head), CNT_F, Fb);
+    pz1_post_kernel<<<rows_grid(round_up(Fb, 128)), ROW_THREADS, 0, st>>>(v);
+    ex.chk();
+  }
+  loss_kernel<<<E, 256, 0, st>>>(v);
+  ex.chk();
+  if (losses_out && ex.ok()) {
+    // losses buffer per model is padded to 256 B in the arena; the caller's is dense [E][8]
+    ex.err = cudaMemcpy2DAsync(losses_out, 8 * sizeof(float), v.losses.p, v.losses.ms * sizeof(float), 8 * sizeof(float), E,
+                               cudaMemcpyDeviceToDevice, st);
+  }
+
+  if (backward && ex.ok()) {
+    if (pl->has_fprop) {
+      ex.block_bwd(pl->dz1b, v.dY9, v.Z3b, 0, pl->Z3, v.dZ3.p, v.dZ3.ms, CNT_F, Fb);
+      z3_back_kernel<<<rows_grid(round_up(Fb, 128)), ROW_THREADS, 0, st>>>(v);
+      ex.chk();
+      ex.block_bwd(pl->z3b, v.dY7, v.Z1e, 0, pl->Z, v.dZ1e.p, v.dZ1e.ms, CNT_F, Fb);
+    }
+    ex.block_bwd(pl->dec, pl->dY5, v.Zdec, 0, pl->Z, v.dZdec.p, v.dZdec.ms, CNT_RD, Rdb);
+    if (pl->has_clf) {
+      clf_back_kernel<<<rows_grid(LNb), ROW_THREADS, 0, st>>>(v);
+      ex.chk();
+      clf_grad_partial_kernel<<<dim3(CLF_SPLITS, E), 256, 0, st>>>(v);
+      ex.chk();
+      clf_grad_reduce_kernel<<<E, 256, 0, st>>>(v);
+      ex.chk();
+    }
+    if (pl->has_T) {
+      T_back_kernel<<<rows_grid(N + PAD_ROWS), ROW_THREADS, 0, st>>>(v);
+      ex.chk();
+      ex.gemm_dw(v.dYT, v.Zdec, 0, pl->Tsh, CNT_LN, LNb);
+      ex.colsum(v.dYT, pl->Tsh, CNT_LN, false);
+      ex.gemm_dx(v.dYT, pl->Tsh, EPI_STORE_F32, ex.epi_f32(v.dZ1T.p, v.dZ1T.ms, pl->Z, pl->Z, nullptr), CNT_LN, LNb);
+    }
+    q_back_kernel<<<rows_grid(N + PAD_ROWS), ROW_THREADS, 0, st>>>(v);
+    ex.chk();
+    ex.block_bwd(pl->enc, v.dY2, v.Ain, 0, pl->X, nullptr, 0, CNT_R0, R0b);
+  }
+  if (!ex.ok()) return set_cuda_error("drvae step launch", ex.err);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int drvae_sync_shadows(drvae_plan_t* pl, void* stream) {
+  if (!pl) return set_error("drvae_sync_shadows: null plan");
+  drvae_hparams_t hp{};
+  return run_adam(pl, &hp, 0, (cudaStream_t)stream);
+}
+
+extern "C" int drvae_train_step(drvae_plan_t* pl, const drvae_batch_t* b, const drvae_noise_t* nz, const drvae_hparams_t* hp,
+                                float* losses_out, void* stream) {
+  if (!pl) return set_error("drvae_train_step: null plan");
+  int rc = run_step(pl, b, nz, hp, losses_out, (cudaStream_t)stream, true);
+  if (rc) return rc;
+  return run_adam(pl, hp, 1, (cudaStream_t)stream);
+}
+
+extern "C" int drvae_loss_forward(drvae_plan_t* pl, const drvae_batch_t* b, const drvae_noise_t* nz, const drvae_hparams_t* hp,
+                                  float* losses_out, void* stream) {
+  if (!pl) return set_error("drvae_loss_forward: null plan");
+  return run_step(pl, b, nz, hp, losses_out, (cudaStream_t)stream, false);
+}
+
+extern "C" int drvae_grad_step(drvae_plan_t* pl, const drvae_batch_t* b, const drvae_noise_t* nz, const drvae_hparams_t* hp,
+                               float* losses_out, void* stream) {
+  if (!pl) return set_error("drvae_grad_step: null plan");
+  return run_step(pl, b, nz, hp, losses_out, (cudaStream_t)stream, true);
+}
+
+extern "C" int drvae_adam_step(drvae_plan_t* pl, const drvae_hparams_t* hp, void* stream) {
+  if (!pl || !hp) return set_error("drvae_adam_step: null argument");
+  return run_adam(pl, hp, 1, (cudaStream_t)stream);
+}
+
+extern "C" int drvae_infer(drvae_plan_t* pl, const float* x1, int N, const drvae_infer_out_t* out, void* stream) {
+  if (!pl || !x1 || !out) return set_error("drvae_infer: null argument");
+  if (!pl->params) return set_error("drvae_infer: plan has no bound parameters");
+  if (N < 1 || N > pl->Ncap) return set_error("drvae_infer: N exceeds the plan's max_batch");
+  cudaStream_t st = (cudaStream_t)stream;
+  drvae_hparams_t hp{};
+  if (!pl->shadows_valid) {
+    int rc = run_adam(pl, &hp, 0, st);
+    if (rc) return rc;
+  }
+  Exec ex;
+  ex.pl = pl;
+  ex.st = st;
+  ex.N = N;
+  DevView& v = ex.v;
+  v = pl->view;
+  v.N = N;
+  v.need_grad = 0;
+  v.x1 = MBuf<const float>{x1, (long long)N * pl->X};
+  v.eps_x1 = MBuf<const float>{pl->eps_own.p, pl->eps_own.ms};  // never read (training = 0)
+  v.eps_x2 = v.eps_x1;
+  v.params = MBuf<float>{pl->params, pl->P};
+  v.s.training = 0;
+  v.s.add_noise = 0;
+  const int E = pl->E;
+  const int rows_dec = pl->has_T ? 2 * N : N;
+  InferView o{out->z1_mu, out->z1_lv, out->z2_mu, out->z2_lv, out->proba, out->pred};
+  auto rows_grid = [&](int rows) { return dim3(cdiv(rows, ROW_WARPS), E); };
+  infer_counts_kernel<<<E, 128, 0, st>>>(v, rows_dec);
+  ex.chk();
+  prep_kernel<<<dim3(round_up(N, 128), E), 128, 0, st>>>(v);
+  ex.chk();
+  ex.block_hidden_fwd(pl->enc, v.Ain, 0, CNT_R0, N);
+  ex.gemm_nt(pl->enc.H.back(), 0, pl->enc.head, EPI_STORE_F32, ex.epi_f32(v.Q.p, v.Q.ms, 2 * pl->Z, 2 * pl->Z, &pl->enc.head),
+             CNT_R0, N);
+  infer_z1_kernel<<<rows_grid(N + PAD_ROWS), ROW_THREADS, 0, st>>>(v, o, rows_dec);
+  ex.chk();
+  if (pl->has_T) {
+    ex.gemm_nt(v.Zdec, 0, pl->Tsh, EPI_STORE_F32, ex.epi_f32(v.PT.p, v.PT.ms, 2 * pl->Z, 2 * pl->Z, &pl->Tsh), CNT_LN, N);
+    infer_z2_kernel<<<rows_grid(N), ROW_THREADS, 0, st>>>(v, o);
+    ex.chk();
+  }
+  if (out->px1_mu || out->px2_mu) {
+    ex.block_hidden_fwd(pl->dec, v.Zdec, 0, CNT_RD, rows_dec);
+    for (int half = 0; half < (pl->has_T ? 2 : 1); ++half) {
+      float* mu = half == 0 ? out->px1_mu : out->px2_mu;
+      float* sg = half == 0 ? out->px1_sg : out->px2_sg;
+      if (!mu || !sg) continue;
+      EpiParams e = ex.epi_base();
+      e.out_f32 = mu;
+      e.out2_f32 = sg;
+      e.out_f32_ms = (long long)N * pl->X;
+      e.out_ld = pl->X;
+      e.bias = pl->derived.p + pl->dec.head.bias_off;
+      e.bias_ms = pl->derived.ms;
+      e.X = pl->X;
+      ex.gemm_nt(pl->dec.H.back(), half * N, pl->dec.head, EPI_DECOUT, e, CNT_N, N);
+    }
+  }
+  if (!ex.ok()) return set_cuda_error("drvae_infer launch", ex.err);
+  return 0;
+}

@@ -1,0 +1,164 @@
+// Plan: everything the step executor needs for one ensemble of identically shaped models —
+// parameter layout (reference state_dict order), bf16 weight shadows, workspace buffers, and the
+// device-visible view of them that the row kernels take by value.
+#pragma once
+
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "drvae_b200.h"
+#include "gemm.cuh"
+
+namespace drvae {
+
+enum { KIND_DRVAE = 0, KIND_PVAE = 1, KIND_VFAE = 2 };
+
+template <class T>
+struct MBuf {  // one buffer per ensemble member, `ms` elements apart
+  T* p;
+  long long ms;
+  __host__ __device__ __forceinline__ T* at(int model) const { return p + (long long)model * ms; }
+};
+
+// chunk8 bf16 buffer (per model)
+struct C8Buf {
+  bf16* p;
+  long long ms;
+  int rcap;
+  int fcap;  // feature capacity (multiple of 8)
+  __host__ __device__ __forceinline__ bf16* at(int model) const { return p + (long long)model * ms; }
+};
+
+// ---------------------------------------------------------------------------------------------
+// parameter tensors and their derived (kernel-facing) copies
+// ---------------------------------------------------------------------------------------------
+enum { SEG_PLAIN = 0, SEG_W = 1, SEG_B = 2, SEG_G = 3 };
+
+struct Seg {
+  int off;   // offset in the flat per-model parameter vector
+  int rows;  // out features (or vector length)
+  int cols;  // in features (1 for vectors)
+  int kind;
+  // SEG_W: bf16 chunk8 shadow [Kc/8][sh_rcap][8]; columns >= kmain are one-hot class columns
+  long long sh_off;
+  int sh_rcap;
+  int kmain;
+  int which, ilv_block, ilv_stride;
+  long long clsb_off;  // fp32 [Y][clsb_ld]
+  int clsb_ld;
+  // SEG_B: fp32 derived bias vector, constant folded in
+  long long bias_off;
+  float bias_const;
+  int wn_g_off;  // >= 0: weight-normalised layer, offset of its `g` vector (shadow written by wn kernel)
+};
+
+struct ParamInfo {
+  std::string name;
+  int rows, cols;  // cols == 0: vector
+  int off;
+};
+
+// One weight matrix as the GEMMs see it (possibly two stacked / interleaved reference tensors).
+struct Shadow {
+  long long off;       // in the bf16 shadow arena (per model)
+  int rcap;            // = tiles_n * BN  (output-feature capacity)
+  int kin;             // true input features that go through the GEMM
+  int kc;              // round_up(kin, 16)
+  int nout_total;      // shadow rows in use
+  int BN, tiles_n;     // forward N tiling
+  int BNx, tiles_nx;   // tiling over input features (dX / dW output columns)
+  long long bias_off;  // fp32 derived bias [rcap]
+  long long clsb_off;  // fp32 derived class bias [Y][rcap] or -1
+  int ntens;
+  int w_off[2];   // flat offsets of the weight tensors
+  int b_off[2];   // flat offsets of the bias tensors
+  int rows_each[2];
+  int ld;         // leading dimension of the weight tensors (kin + class columns)
+  int ilv_block, ilv_stride;
+};
+
+struct MlpBlock {
+  std::vector<Shadow> hidden;   // hidden[i]: layer i (ELU)
+  Shadow head;                  // stacked (mu | lv) or interleaved (mu, sg) heads
+  std::vector<int> widths;      // hidden widths
+  bool class_aug = false;       // first layer input is [z, onehot(y)]
+  std::vector<C8Buf> H;         // activations per hidden layer
+  std::vector<C8Buf> dPre;      // pre-activation gradients per hidden layer
+};
+
+// ---------------------------------------------------------------------------------------------
+// Device-visible view used by the row kernels
+// ---------------------------------------------------------------------------------------------
+struct StepScalars {
+  float kl_min, noise_std;
+  float beta_pert, pertloss_rate, kl_qz2pz2_rate, yloss_rate;
+  int training, add_noise;
+  int gN, gNp, gNlab;  // global normalisers (0 = use local counts)
+  float lr, beta1, beta2, eps, weight_decay;
+  float bc1, bc2;  // 1 - beta^t
+  float log_prior[8];  // log prior_y
+};
+
+struct DevView {
+  int kind, X, Y, Z, Z3, L, N, Ncap;
+  int Xc;            // round_up(X, 16)
+  int Zc, Z3c;       // chunk8 feature capacities of the latent buffers
+  int R0cap, LNcap, Rdcap, Fcap, Flcap;
+  int has_pair, has_T, has_clf, has_fprop, clf_in;
+  int need_grad;
+  // batch (caller memory)
+  MBuf<const float> x1, x2;
+  MBuf<const int> y, has_x2, has_y;
+  // ε (row indexed)
+  MBuf<const float> eps_x1, eps_x2, eps_z1, eps_z2, eps_z2f, eps_z3;
+  // row maps
+  MBuf<int> counts;   // CNT_*
+  MBuf<float> coefs;  // COEF_*
+  MBuf<int> pair_of, row_of_pair, ebase, lab, ycls, e_row, e_jj, e_cls_full;
+  // activations
+  MBuf<float> tgt;  // [R0cap][X]
+  C8Buf Ain;        // [Xc/8][R0cap][8]
+  MBuf<float> Q;    // [R0cap][2Z]   (mu1 | lv1) rows < N, (mu2 | lv2) rows N + p
+  MBuf<float> Z1f;  // [LNcap][Z]
+  C8Buf Zdec;       // rows: z1 (L*N) | z2 (L*Np) | z2f (L*Np)
+  C8Buf Z1e;        // eval-ordered copies of z1
+  MBuf<float> PT;   // [LNcap][2Z]   (p_mu | p_lv) of p(z2|z1)
+  MBuf<float> Z2Ff; // [LNcap][Z]
+  MBuf<float> QY;   // [LNcap][Y]
+  MBuf<float> Q3;   // [Fcap][2*Z3]
+  C8Buf Z3b;        // [Z3c/8][Fcap][8]
+  MBuf<float> PZ1;  // [Fcap][2Z]
+  // per-row loss terms
+  MBuf<float> klq_row;   // [R0cap]  PVAE prior KLs
+  MBuf<float> klz2_row;  // [LNcap]
+  MBuf<float> yl_row;    // [LNcap]
+  MBuf<float> ycat_row;  // [LNcap]
+  MBuf<float> kfp_row;   // [Fcap]   fb(KL3) + fb(KLp) per evaluation
+  MBuf<float> kfpw_row;  // [Fcap]   weighted by q(y)
+  MBuf<float> dec_part;  // [dec_tiles][Rdcap]
+  int dec_tiles;
+  // backward
+  C8Buf dY9, dY7, dYT, dY2;
+  MBuf<float> dQ1e;    // [Fcap][2Z]
+  MBuf<float> dQ2;     // [Ncap][2Z]
+  MBuf<float> dZ3;     // [Fcap][Z3]
+  MBuf<float> dZ1e;    // [Fcap][Z]
+  MBuf<float> dZdec;   // [Rdcap][Z]
+  MBuf<float> dZ1T;    // [LNcap][Z]
+  MBuf<float> DZ1;     // [LNcap][Z]
+  MBuf<float> DZ2F;    // [LNcap][Z]
+  MBuf<float> dlogit;  // [LNcap][Y]
+  MBuf<float> clf_part; // [CLF_SPLITS][Y][clf_in + 1]
+  // parameters
+  MBuf<float> params, grads, adam_m, adam_v;
+  int clf_w_off, clf_b_off;
+  MBuf<float> losses;  // [8]
+  StepScalars s;
+};
+
+constexpr int CLF_SPLITS = 32;
+constexpr int MAXY = 8;   // classes
+constexpr int MAXJ = 8;   // latent dim <= 32 * MAXJ
+
+}  // namespace drvae

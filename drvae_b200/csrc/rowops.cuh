@@ -1,0 +1,886 @@
+// Row-wise kernels of the step: everything between the GEMMs that is local to one minibatch row
+// (or one (row, class) evaluation): row-group bookkeeping, input noise, reparameterised sampling,
+// analytic KL with free bits, the y classifier, and the assembly of d(loss)/d(pre-activation)
+// rows that feed the backward GEMMs.  One warp per row; lane f handles features f, f+32, ...
+//
+// Reference math (file:line in /root/reference/src):
+//   sampling            blocks.py:170-174          z = eps * exp(0.5 logvar) + mu
+//   KL(q||p) per row    blocks.py:180-182
+//   free bits           DGMMixin.py:68-75          max(KL_row, kl_min)
+//   classifier          blocks.py:456-480          clamp(softmax(.), 1e-10, 1-1e-10), log-lik, KL to prior
+//   p(z2|z1)            blocks.py:349-361          mu = z + z W^T + b,  logvar = lin(z) - 2
+//   group logic         DrVAE.py:367-543, PVAE.py:265-409, VFAE.py:268-401
+#pragma once
+
+#include "plan.h"
+
+namespace drvae {
+
+constexpr int ROW_WARPS = 8;            // warps per block in the row kernels
+constexpr int ROW_THREADS = ROW_WARPS * 32;
+constexpr int PAD_ROWS = 128;           // extra "pad duty" warps per launch
+
+__device__ __forceinline__ void st_c8(bf16* base, int rcap, int row, int f, float v) {
+  base[c8_index(row, f, rcap)] = __float2bfloat16_rn(v);
+}
+__device__ __forceinline__ void zero_c8_row(const C8Buf& b, int model, int row, int lane) {
+  uint4* p = reinterpret_cast<uint4*>(b.at(model));
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  for (int c = lane; c < (b.fcap >> 3); c += 32) p[(long long)c * b.rcap + row] = z;
+}
+__device__ __forceinline__ int pad128(int n) { return (n + 127) & ~127; }
+
+// ---------------------------------------------------------------------------------------------
+// rowmap: split the minibatch into the reference's row groups without moving rows.
+// The reference gathers LS / US / LP / UP groups (DrVAE.py:565-608); here every row keeps its
+// place and we only record, per row, its pair index, its evaluation slots for _fprop
+// (1 for a labeled row, dim_y for an unlabeled one) and the batch-level normalisers.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rowmap_kernel(DevView v) {
+  const int m = blockIdx.x, t = threadIdx.x, N = v.N;
+  __shared__ int s_np[256], s_ne[256], s_nl[256];
+  const int* hx = v.has_pair ? v.has_x2.at(m) : nullptr;
+  const int* hy = (v.has_clf && v.has_y.p) ? v.has_y.at(m) : nullptr;
+  const int* yy = (v.has_clf && v.y.p) ? v.y.at(m) : nullptr;
+  const int seg = (N + 255) / 256;
+  const int i0 = min(N, t * seg), i1 = min(N, i0 + seg);
+  int np = 0, ne = 0, nl = 0;
+  for (int i = i0; i < i1; ++i) {
+    const bool pr = hx && hx[i] != 0;
+    const bool lb = hy && hy[i] != 0;
+    np += pr;
+    nl += lb;
+    ne += v.has_fprop ? (lb ? 1 : v.Y) : 0;
+  }
+  s_np[t] = np;
+  s_ne[t] = ne;
+  s_nl[t] = nl;
+  __syncthreads();
+  if (t == 0) {
+    int a = 0, b = 0, c = 0;
+    for (int k = 0; k < 256; ++k) {
+      int x = s_np[k];
+      s_np[k] = a;
+      a += x;
+      x = s_ne[k];
+      s_ne[k] = b;
+      b += x;
+      c += s_nl[k];
+    }
+    const int Np = a, Fl = b, Nlab = c;
+    int* cnt = v.counts.at(m);
+    cnt[CNT_N] = N;
+    cnt[CNT_NP] = Np;
+    cnt[CNT_NLAB] = Nlab;
+    cnt[CNT_R0] = N + Np;
+    cnt[CNT_LN] = v.L * N;
+    cnt[CNT_LNP] = v.L * Np;
+    cnt[CNT_RD] = v.L * (N + 2 * Np);
+    cnt[CNT_FL] = Fl;
+    cnt[CNT_F] = v.L * Fl;
+    const float gN = v.s.gN > 0 ? v.s.gN : N;
+    const float gNp = fmaxf(1.f, v.s.gN > 0 ? v.s.gNp : Np);
+    const float gNl = fmaxf(1.f, v.s.gN > 0 ? v.s.gNlab : Nlab);
+    const float Lf = v.L;
+    float* cf = v.coefs.at(m);
+    cf[COEF_RECL] = 1.f / (Lf * gN);
+    cf[COEF_PERT] = v.s.beta_pert * v.s.pertloss_rate / (Lf * gNp);
+    cf[COEF_KLZ2] = v.s.beta_pert * v.s.kl_qz2pz2_rate / (Lf * gN);
+    cf[COEF_KLD] = 1.f / (Lf * gN);
+    cf[COEF_YL] = v.s.yloss_rate / (Lf * gNl);
+    cf[COEF_INV_N] = 1.f / gN;
+    cf[COEF_PERT_PLAIN] = 1.f / (Lf * gNp);
+    cf[COEF_YL_PLAIN] = 1.f / (Lf * gNl);
+  }
+  __syncthreads();
+  int p = s_np[t], e = s_ne[t];
+  int* pair_of = v.pair_of.at(m);
+  int* row_of_pair = v.row_of_pair.at(m);
+  int* ebase = v.ebase.at(m);
+  int* lab = v.lab.at(m);
+  int* ycls = v.ycls.at(m);
+  int* e_row = v.e_row.at(m);
+  int* e_jj = v.e_jj.at(m);
+  for (int i = i0; i < i1; ++i) {
+    const bool pr = hx && hx[i] != 0;
+    const bool lb = hy && hy[i] != 0;
+    int yi = yy ? yy[i] : 0;
+    yi = min(max(yi, 0), v.Y - 1);
+    pair_of[i] = pr ? p : -1;
+    if (pr) row_of_pair[p++] = i;
+    lab[i] = lb;
+    ycls[i] = yi;
+    ebase[i] = e;
+    if (v.has_fprop) {
+      const int c = lb ? 1 : v.Y;
+      for (int jj = 0; jj < c; ++jj) {
+        e_row[e + jj] = i;
+        e_jj[e + jj] = jj;
+      }
+      e += c;
+    }
+  }
+  __syncthreads();
+  if (v.has_fprop) {
+    const int Fl = v.counts.at(m)[CNT_FL];
+    int* full = v.e_cls_full.at(m);
+    for (int k = t; k < v.L * Fl; k += 256) {
+      const int el = k % Fl;
+      const int i = e_row[el];
+      full[k] = lab[i] ? ycls[i] : e_jj[el];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// prep: encoder input rows.  Row r < N is x1[r]; row N + p is x2 of the p-th pair.  With
+// --train-w-noise the noisy row is ALSO the reconstruction target (DrVAE.py:404-417 adds the
+// noise in place), so the fp32 target copy is written from the same value.
+// grid (R0cap, n_models), block 128
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) prep_kernel(DevView v) {
+  const int m = blockIdx.y, r = blockIdx.x;
+  const int* cnt = v.counts.at(m);
+  const int N = cnt[CNT_N], R0 = cnt[CNT_R0];
+  if (r >= pad128(R0)) return;
+  uint4* ain = reinterpret_cast<uint4*>(v.Ain.at(m));
+  const int nch = v.Xc >> 3;
+  if (r >= R0) {
+    for (int c = threadIdx.x; c < nch; c += 128) ain[(long long)c * v.Ain.rcap + r] = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  const float* src;
+  const float* eps;
+  if (r < N) {
+    src = v.x1.at(m) + (long long)r * v.X;
+    eps = v.eps_x1.at(m) + (long long)r * v.X;
+  } else {
+    const int i = v.row_of_pair.at(m)[r - N];
+    src = v.x2.at(m) + (long long)i * v.X;
+    eps = v.eps_x2.at(m) + (long long)i * v.X;
+  }
+  const bool noisy = v.s.training && v.s.add_noise;
+  float* tg = v.tgt.at(m) + (long long)r * v.X;
+  for (int c = threadIdx.x; c < nch; c += 128) {
+    float a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int f = c * 8 + k;
+      float x = 0.f;
+      if (f < v.X) {
+        x = src[f];
+        if (noisy) x += v.s.noise_std * eps[f];
+        tg[f] = x;
+      }
+      a[k] = x;
+    }
+    ain[(long long)c * v.Ain.rcap + r] = pack_bf16x8(a);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// classifier q(y | u): u = [z1, z2f - z1] (DrVAE) or z1 (VFAE).  Warp-cooperative, fp32.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void classifier_row(const DevView& v, int m, int r, int i, int lane) {
+  const float* Wc = v.params.at(m) + v.clf_w_off;
+  const float* bc = v.params.at(m) + v.clf_b_off;
+  const float* z1 = v.Z1f.at(m) + (long long)r * v.Z;
+  const float* z2f = (v.clf_in > v.Z) ? v.Z2Ff.at(m) + (long long)r * v.Z : nullptr;
+  float acc[MAXY];
+#pragma unroll
+  for (int j = 0; j < MAXY; ++j) acc[j] = 0.f;
+  for (int f = lane; f < v.Z; f += 32) {
+    const float a = z1[f];
+    const float d = z2f ? z2f[f] - a : 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXY; ++j) {
+      if (j < v.Y) {
+        acc[j] = fmaf(Wc[j * v.clf_in + f], a, acc[j]);
+        if (z2f) acc[j] = fmaf(Wc[j * v.clf_in + v.Z + f], d, acc[j]);
+      }
+    }
+  }
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < MAXY; ++j) {
+    if (j < v.Y) {
+      acc[j] = warp_sum(acc[j]) + bc[j];
+      mx = fmaxf(mx, acc[j]);
+    }
+  }
+  float den = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXY; ++j) {
+    if (j < v.Y) {
+      acc[j] = expf(acc[j] - mx);
+      den += acc[j];
+    }
+  }
+  float yl = 0.f, ycat = 0.f;
+  const bool lb = v.lab.at(m)[i] != 0;
+  const int yi = v.ycls.at(m)[i];
+#pragma unroll
+  for (int j = 0; j < MAXY; ++j) {
+    if (j < v.Y) {
+      float q = acc[j] / den;
+      q = fminf(fmaxf(q, 1e-10f), 1.f - 1e-10f);
+      if (lane == 0) v.QY.at(m)[(long long)r * v.Y + j] = q;
+      const float lq = logf(q);
+      if (lb) {
+        if (j == yi) yl = lq;
+      } else {
+        ycat += -q * (v.s.log_prior[j] - lq);
+      }
+    }
+  }
+  if (lane == 0) {
+    v.yl_row.at(m)[r] = yl;
+    v.ycat_row.at(m)[r] = ycat;
+  }
+}
+
+__device__ __forceinline__ float kl_prior_term(float mu, float lv) { return 0.5f * (-lv - 1.f + mu * mu + expf(lv)); }
+__device__ __forceinline__ float kl_term(float muq, float lvq, float mup, float lvp) {
+  const float d = muq - mup;
+  return 0.5f * (lvp - lvq - 1.f + (d * d + expf(lvq)) * expf(-lvp));
+}
+
+// ---------------------------------------------------------------------------------------------
+// sample_q1: after the encoder heads.  Draw z1 (and z2 — from q(z1|x1), as the reference does,
+// DrVAE.py:427) for every MC sample and scatter them to the stacked decoder rows.
+// grid (ceil((Ncap + PAD_ROWS) / ROW_WARPS), n_models)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ROW_THREADS) sample_q1_kernel(DevView v) {
+  const int m = blockIdx.y, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  const int* cnt = v.counts.at(m);
+  const int N = cnt[CNT_N], Np = cnt[CNT_NP], LN = cnt[CNT_LN], Fl = cnt[CNT_FL], F = cnt[CNT_F], Rd = cnt[CNT_RD];
+  if (i >= N) {
+    const int j = i - N;  // pad duty
+    if (j < PAD_ROWS) {
+      if (v.has_fprop && F + j < pad128(F)) zero_c8_row(v.Z1e, m, F + j, lane);
+      if (!v.has_T && Rd + j < pad128(Rd)) zero_c8_row(v.Zdec, m, Rd + j, lane);
+    }
+    return;
+  }
+  const float* q = v.Q.at(m) + (long long)i * 2 * v.Z;
+  const int p = v.pair_of.at(m)[i];
+  const int eb = v.has_fprop ? v.ebase.at(m)[i] : 0;
+  const int ecnt = v.has_fprop ? (v.lab.at(m)[i] ? 1 : v.Y) : 0;
+  bf16* zdec = v.Zdec.at(m);
+  bf16* z1e = v.has_fprop ? v.Z1e.at(m) : nullptr;
+  for (int l = 0; l < v.L; ++l) {
+    const int r = l * N + i;
+    const float* e1 = v.eps_z1.at(m) + ((long long)l * v.Ncap + i) * v.Z;
+    const float* e2 = v.eps_z2.at(m) + ((long long)l * v.Ncap + i) * v.Z;
+    for (int f = lane; f < v.Zc; f += 32) {
+      float z = 0.f, z2 = 0.f;
+      if (f < v.Z) {
+        const float mu = q[f], sd = expf(0.5f * q[v.Z + f]);
+        z = mu + sd * e1[f];
+        v.Z1f.at(m)[(long long)r * v.Z + f] = z;
+        if (p >= 0) z2 = mu + sd * e2[f];
+      }
+      st_c8(zdec, v.Zdec.rcap, r, f, z);
+      if (p >= 0) st_c8(zdec, v.Zdec.rcap, LN + l * Np + p, f, z2);
+      for (int jj = 0; jj < ecnt; ++jj) st_c8(z1e, v.Z1e.rcap, l * Fl + eb + jj, f, z);
+    }
+    if (v.has_clf && !v.has_T) {
+      __syncwarp();
+      classifier_row(v, m, r, i, lane);
+    }
+  }
+  if (v.kind == KIND_PVAE) {  // KL(q1 || N(0,I)) and KL(q2 || N(0,I)) with free bits (PVAE.py:330-372)
+    float k1 = 0.f, k2 = 0.f;
+    const float* q2 = p >= 0 ? v.Q.at(m) + (long long)(N + p) * 2 * v.Z : nullptr;
+    for (int f = lane; f < v.Z; f += 32) {
+      k1 += kl_prior_term(q[f], q[v.Z + f]);
+      if (q2) k2 += kl_prior_term(q2[f], q2[v.Z + f]);
+    }
+    k1 = warp_sum(k1);
+    k2 = warp_sum(k2);
+    if (lane == 0) {
+      v.klq_row.at(m)[i] = fmaxf(k1, v.s.kl_min);
+      if (p >= 0) v.klq_row.at(m)[N + p] = fmaxf(k2, v.s.kl_min);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// T_post: after the p(z2|z1) GEMM.  Residual mean, sample z2f, KL(q(z2|x2) || p(z2|z1)) with free
+// bits for pair rows, and the classifier.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ROW_THREADS) T_post_kernel(DevView v) {
+  const int m = blockIdx.y, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  const int* cnt = v.counts.at(m);
+  const int N = cnt[CNT_N], Np = cnt[CNT_NP], LN = cnt[CNT_LN], LNp = cnt[CNT_LNP], Rd = cnt[CNT_RD];
+  if (i >= N) {
+    const int j = i - N;
+    if (j < PAD_ROWS && Rd + j < pad128(Rd)) zero_c8_row(v.Zdec, m, Rd + j, lane);
+    return;
+  }
+  const int p = v.pair_of.at(m)[i];
+  const float* q2 = p >= 0 ? v.Q.at(m) + (long long)(N + p) * 2 * v.Z : nullptr;
+  bf16* zdec = v.Zdec.at(m);
+  for (int l = 0; l < v.L; ++l) {
+    const int r = l * N + i;
+    float* pt = v.PT.at(m) + (long long)r * 2 * v.Z;
+    const float* z1 = v.Z1f.at(m) + (long long)r * v.Z;
+    const float* ef = v.eps_z2f.at(m) + ((long long)l * v.Ncap + i) * v.Z;
+    float kl = 0.f;
+    for (int f = lane; f < v.Zc; f += 32) {
+      float z2f = 0.f;
+      if (f < v.Z) {
+        const float pmu = pt[f] + z1[f];
+        const float plv = pt[v.Z + f];
+        pt[f] = pmu;
+        z2f = pmu + expf(0.5f * plv) * ef[f];
+        v.Z2Ff.at(m)[(long long)r * v.Z + f] = z2f;
+        if (q2) kl += kl_term(q2[f], q2[v.Z + f], pmu, plv);
+      }
+      if (p >= 0) st_c8(zdec, v.Zdec.rcap, LN + LNp + l * Np + p, f, z2f);
+    }
+    kl = warp_sum(kl);
+    if (lane == 0) v.klz2_row.at(m)[r] = q2 ? fmaxf(kl, v.s.kl_min) : 0.f;
+    if (v.has_clf) {
+      __syncwarp();
+      classifier_row(v, m, r, i, lane);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// z3_post: per (row, class) evaluation e.  Sample the top latent and take fb(KL(q || N(0,I)))
+// (DrVAE.py:341-345, VFAE.py:242-246).  grid (ceil(Fcap / ROW_WARPS), n_models)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void eval_decode(const DevView& v, int m, int e, int Fl, int& l, int& i, int& jj) {
+  l = e / Fl;
+  const int el = e - l * Fl;
+  i = v.e_row.at(m)[el];
+  jj = v.e_jj.at(m)[el];
+}
+
+__global__ void __launch_bounds__(ROW_THREADS) z3_post_kernel(DevView v) {
+  const int m = blockIdx.y, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  const int* cnt = v.counts.at(m);
+  const int F = cnt[CNT_F], Fl = cnt[CNT_FL];
+  if (e >= pad128(F)) return;
+  if (e >= F) {
+    zero_c8_row(v.Z3b, m, e, lane);
+    return;
+  }
+  int l, i, jj;
+  eval_decode(v, m, e, Fl, l, i, jj);
+  const float* q3 = v.Q3.at(m) + (long long)e * 2 * v.Z3;
+  const float* ez = v.eps_z3.at(m) + (((long long)l * v.Ncap + i) * v.Y + jj) * v.Z3;
+  bf16* z3b = v.Z3b.at(m);
+  float kl = 0.f;
+  for (int f = lane; f < v.Z3c; f += 32) {
+    float z = 0.f;
+    if (f < v.Z3) {
+      const float mu = q3[f], lv = q3[v.Z3 + f];
+      z = mu + expf(0.5f * lv) * ez[f];
+      kl += kl_prior_term(mu, lv);
+    }
+    st_c8(z3b, v.Z3b.rcap, e, f, z);
+  }
+  kl = warp_sum(kl);
+  if (lane == 0) v.kfp_row.at(m)[e] = fmaxf(kl, v.s.kl_min);
+}
+
+// weight of evaluation e in the batch KLD: 1 for the true class of a labeled row, q(y=j) otherwise
+__device__ __forceinline__ float eval_weight(const DevView& v, int m, int l, int i, int jj, int N) {
+  if (v.lab.at(m)[i]) return 1.f;
+  return v.QY.at(m)[((long long)l * N + i) * v.Y + jj];
+}
+
+// ---------------------------------------------------------------------------------------------
+// pz1_post: fb(KL(q(z1|x1) || p(z1|z_top,y))) per evaluation, its gradients towards the
+// decoder_z1 heads (dY9) and towards q1 (dQ1e).  DrVAE.py:352-355, VFAE.py:253-256.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ROW_THREADS) pz1_post_kernel(DevView v) {
+  const int m = blockIdx.y, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  const int* cnt = v.counts.at(m);
+  const int N = cnt[CNT_N], F = cnt[CNT_F], Fl = cnt[CNT_FL];
+  if (e >= pad128(F)) return;
+  if (e >= F) {
+    if (v.need_grad) zero_c8_row(v.dY9, m, e, lane);
+    return;
+  }
+  int l, i, jj;
+  eval_decode(v, m, e, Fl, l, i, jj);
+  const float* q1 = v.Q.at(m) + (long long)i * 2 * v.Z;
+  const float* pz = v.PZ1.at(m) + (long long)e * 2 * v.Z;
+  float kl = 0.f;
+  for (int f = lane; f < v.Z; f += 32) kl += kl_term(q1[f], q1[v.Z + f], pz[f], pz[v.Z + f]);
+  kl = warp_sum(kl);
+  const bool act = kl > v.s.kl_min;
+  const float w = eval_weight(v, m, l, i, jj, N);
+  const float ke = v.kfp_row.at(m)[e] + fmaxf(kl, v.s.kl_min);
+  __syncwarp();
+  if (lane == 0) {
+    v.kfp_row.at(m)[e] = ke;
+    v.kfpw_row.at(m)[e] = w * ke;
+  }
+  if (!v.need_grad) return;
+  const float cw = act ? v.coefs.at(m)[COEF_KLD] * w : 0.f;
+  bf16* dy = v.dY9.at(m);
+  float* dq = v.dQ1e.at(m) + (long long)e * 2 * v.Z;
+  for (int f = lane; f < v.Z; f += 32) {
+    const float mu1 = q1[f], lv1 = q1[v.Z + f], mup = pz[f], lvp = pz[v.Z + f];
+    const float d = mu1 - mup, ie = expf(-lvp), ev = expf(lv1);
+    st_c8(dy, v.dY9.rcap, e, f, -cw * d * ie);
+    st_c8(dy, v.dY9.rcap, e, v.Z + f, cw * 0.5f * (1.f - (d * d + ev) * ie));
+    dq[f] = cw * d * ie;
+    dq[v.Z + f] = cw * 0.5f * (ev * ie - 1.f);
+  }
+  for (int f = 2 * v.Z + lane; f < v.dY9.fcap; f += 32) st_c8(dy, v.dY9.rcap, e, f, 0.f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// z3_back: d loss / d (mu3 | lv3) per evaluation = reparameterisation path (dZ3 from the
+// decoder_z1 input gradient) + the direct prior-KL gradient.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ROW_THREADS) z3_back_kernel(DevView v) {
+  const int m = blockIdx.y, lane = threadIdx.x & 31;
+  const int e = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  const int* cnt = v.counts.at(m);
+  const int N = cnt[CNT_N], F = cnt[CNT_F], Fl = cnt[CNT_FL];
+  if (e >= pad128(F)) return;
+  if (e >= F) {
+    zero_c8_row(v.dY7, m, e, lane);
+    return;
+  }
+  int l, i, jj;
+  eval_decode(v, m, e, Fl, l, i, jj);
+  const float* q3 = v.Q3.at(m) + (long long)e * 2 * v.Z3;
+  const float* ez = v.eps_z3.at(m) + (((long long)l * v.Ncap + i) * v.Y + jj) * v.Z3;
+  const float* dz = v.dZ3.at(m) + (long long)e * v.Z3;
+  float kl = 0.f;
+  for (int f = lane; f < v.Z3; f += 32) kl += kl_prior_term(q3[f], q3[v.Z3 + f]);
+  kl = warp_sum(kl);
+  const float w = eval_weight(v, m, l, i, jj, N);
+  const float cw = kl > v.s.kl_min ? v.coefs.at(m)[COEF_KLD] * w : 0.f;
+  bf16* dy = v.dY7.at(m);
+  for (int f = lane; f < v.Z3; f += 32) {
+    const float mu = q3[f], lv = q3[v.Z3 + f];
+    const float g = dz[f];
+    st_c8(dy, v.dY7.rcap, e, f, g + cw * mu);
+    st_c8(dy, v.dY7.rcap, e, v.Z3 + f, g * 0.5f * expf(0.5f * lv) * ez[f] + cw * 0.5f * (expf(lv) - 1.f));
+  }
+  for (int f = 2 * v.Z3 + lane; f < v.dY7.fcap; f += 32) st_c8(dy, v.dY7.rcap, e, f, 0.f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// clf_back: d loss / d logits of q(y|.), pushed back to z1 (DZ1) and z2f (DZ2F).
+//   labeled row   : -yloss_rate/(L max(1,Nlab)) * d log q_y
+//   unlabeled row : 1/(L N) * d [ sum_j q_j k_j + sum_j q_j (log q_j - log prior_j) ]
+// grid (ceil(LNcap / ROW_WARPS), n_models), one warp per stacked row r = l*N + i
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ROW_THREADS) clf_back_kernel(DevView v) {
+  const int m = blockIdx.y, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  const int* cnt = v.counts.at(m);
+  const int N = cnt[CNT_N], LN = cnt[CNT_LN], Fl = cnt[CNT_FL];
+  if (r >= LN) return;
+  const int l = r / N, i = r - l * N;
+  const float* cf = v.coefs.at(m);
+  const float* qy = v.QY.at(m) + (long long)r * v.Y;
+  const bool lb = v.lab.at(m)[i] != 0;
+  const int yi = v.ycls.at(m)[i];
+  float q[MAXY], g[MAXY];
+  float dot = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXY; ++j) {
+    q[j] = 0.f;
+    g[j] = 0.f;
+    if (j < v.Y) {
+      q[j] = qy[j];
+      const bool clamped = !(q[j] > 1e-10f && q[j] < 1.f - 1e-10f);
+      if (lb) {
+        g[j] = (j == yi) ? -cf[COEF_YL] / q[j] : 0.f;
+      } else {
+        const float ke = v.has_fprop ? v.kfp_row.at(m)[l * Fl + v.ebase.at(m)[i] + j] : 0.f;
+        g[j] = cf[COEF_KLD] * (ke + logf(q[j]) - v.s.log_prior[j] + 1.f);
+      }
+      if (clamped) g[j] = 0.f;
+      dot += q[j] * g[j];
+    }
+  }
+  float dl[MAXY];
+#pragma unroll
+  for (int j = 0; j < MAXY; ++j) {
+    dl[j] = (j < v.Y) ? q[j] * (g[j] - dot) : 0.f;
+    if (j < v.Y && lane == 0) v.dlogit.at(m)[(long long)r * v.Y + j] = dl[j];
+  }
+  const float* Wc = v.params.at(m) + v.clf_w_off;
+  const bool two = v.clf_in > v.Z;
+  for (int f = lane; f < v.Z; f += 32) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXY; ++j) {
+      if (j < v.Y) {
+        a = fmaf(dl[j], Wc[j * v.clf_in + f], a);
+        if (two) b = fmaf(dl[j], Wc[j * v.clf_in + v.Z + f], b);
+      }
+    }
+    v.DZ1.at(m)[(long long)r * v.Z + f] = a - b;
+    if (two) v.DZ2F.at(m)[(long long)r * v.Z + f] = b;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// T_back: gradient rows of the p(z2|z1) heads (dYT = [d p_mu | d p_lv]), the KL(q2||p) gradient
+// towards q2 (dQ2) and the residual / classifier contributions to d z1 (DZ1).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ROW_THREADS) T_back_kernel(DevView v) {
+  const int m = blockIdx.y, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  const int* cnt = v.counts.at(m);
+  const int N = cnt[CNT_N], Np = cnt[CNT_NP], LN = cnt[CNT_LN], LNp = cnt[CNT_LNP];
+  if (i >= N) {
+    const int j = i - N;
+    if (j < PAD_ROWS && LN + j < pad128(LN)) zero_c8_row(v.dYT, m, LN + j, lane);
+    return;
+  }
+  const int p = v.pair_of.at(m)[i];
+  const float* q2 = p >= 0 ? v.Q.at(m) + (long long)(N + p) * 2 * v.Z : nullptr;
+  const float ckl = v.coefs.at(m)[COEF_KLZ2];
+  bf16* dy = v.dYT.at(m);
+  float a_mu[MAXJ], a_lv[MAXJ];
+#pragma unroll
+  for (int k = 0; k < MAXJ; ++k) a_mu[k] = a_lv[k] = 0.f;
+  for (int l = 0; l < v.L; ++l) {
+    const int r = l * N + i;
+    const float* pt = v.PT.at(m) + (long long)r * 2 * v.Z;
+    const float* ef = v.eps_z2f.at(m) + ((long long)l * v.Ncap + i) * v.Z;
+    const float* dzd = p >= 0 ? v.dZdec.at(m) + (long long)(LN + LNp + l * Np + p) * v.Z : nullptr;
+    const bool act = q2 && v.klz2_row.at(m)[r] > v.s.kl_min;
+    float* dz1 = v.DZ1.at(m) + (long long)r * v.Z;
+    const float* dz2f_c = v.has_clf ? v.DZ2F.at(m) + (long long)r * v.Z : nullptr;
+#pragma unroll
+    for (int k = 0; k < MAXJ; ++k) {
+      const int f = lane + 32 * k;
+      if (f < v.Z) {
+        const float pmu = pt[f], plv = pt[v.Z + f];
+        float g = (dzd ? dzd[f] : 0.f) + (dz2f_c ? dz2f_c[f] : 0.f);
+        float dpmu = g;
+        float dplv = g * 0.5f * expf(0.5f * plv) * ef[f];
+        if (act) {
+          const float mu2 = q2[f], lv2 = q2[v.Z + f];
+          const float d = mu2 - pmu, ie = expf(-plv), ev = expf(lv2);
+          dpmu += -ckl * d * ie;
+          dplv += ckl * 0.5f * (1.f - (d * d + ev) * ie);
+          a_mu[k] += ckl * d * ie;
+          a_lv[k] += ckl * 0.5f * (ev * ie - 1.f);
+        }
+        dz1[f] = (v.has_clf ? dz1[f] : 0.f) + dpmu;  // residual path mu = z1 + ...
+        st_c8(dy, v.dYT.rcap, r, f, dpmu);
+        st_c8(dy, v.dYT.rcap, r, v.Z + f, dplv);
+      }
+    }
+    for (int f = 2 * v.Z + lane; f < v.dYT.fcap; f += 32) st_c8(dy, v.dYT.rcap, r, f, 0.f);
+  }
+  if (p >= 0) {
+    float* dq2 = v.dQ2.at(m) + (long long)p * 2 * v.Z;
+#pragma unroll
+    for (int k = 0; k < MAXJ; ++k) {
+      const int f = lane + 32 * k;
+      if (f < v.Z) {
+        dq2[f] = a_mu[k];
+        dq2[v.Z + f] = a_lv[k];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// q_back: gradient rows of the encoder heads, dY2 = [d mu | d lv] for q(z1|x1) rows and for
+// q(z2|x2) rows.  Collects every path into z1 / z2 samples and the direct KL gradients.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ROW_THREADS) q_back_kernel(DevView v) {
+  const int m = blockIdx.y, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  const int* cnt = v.counts.at(m);
+  const int N = cnt[CNT_N], Np = cnt[CNT_NP], LN = cnt[CNT_LN], R0 = cnt[CNT_R0], Fl = cnt[CNT_FL];
+  if (i >= N) {
+    const int j = i - N;
+    if (j < PAD_ROWS && R0 + j < pad128(R0)) zero_c8_row(v.dY2, m, R0 + j, lane);
+    return;
+  }
+  const float* q = v.Q.at(m) + (long long)i * 2 * v.Z;
+  const int p = v.pair_of.at(m)[i];
+  const int eb = v.has_fprop ? v.ebase.at(m)[i] : 0;
+  const int ecnt = v.has_fprop ? (v.lab.at(m)[i] ? 1 : v.Y) : 0;
+  const bool have_dz1 = v.has_clf || v.has_T;
+  bf16* dy = v.dY2.at(m);
+  const float cN = v.coefs.at(m)[COEF_INV_N];
+#pragma unroll
+  for (int k = 0; k < MAXJ; ++k) {
+    const int f = lane + 32 * k;
+    if (f >= v.Z) continue;
+    const float mu = q[f], lv = q[v.Z + f];
+    const float hs = 0.5f * expf(0.5f * lv);
+    float amu = 0.f, alv = 0.f;
+    for (int l = 0; l < v.L; ++l) {
+      const long long r = (long long)l * N + i;
+      float g = v.dZdec.at(m)[r * v.Z + f];
+      if (have_dz1) g += v.DZ1.at(m)[r * v.Z + f];
+      if (v.has_T) g += v.dZ1T.at(m)[r * v.Z + f];
+      for (int jj = 0; jj < ecnt; ++jj) {
+        const long long e = (long long)l * Fl + eb + jj;
+        g += v.dZ1e.at(m)[e * v.Z + f];
+        amu += v.dQ1e.at(m)[e * 2 * v.Z + f];
+        alv += v.dQ1e.at(m)[e * 2 * v.Z + v.Z + f];
+      }
+      amu += g;
+      alv += g * hs * v.eps_z1.at(m)[((long long)l * v.Ncap + i) * v.Z + f];
+      if (p >= 0) {
+        const float g2 = v.dZdec.at(m)[((long long)LN + (long long)l * Np + p) * v.Z + f];
+        amu += g2;
+        alv += g2 * hs * v.eps_z2.at(m)[((long long)l * v.Ncap + i) * v.Z + f];
+      }
+    }
+    if (v.kind == KIND_PVAE && v.klq_row.at(m)[i] > v.s.kl_min) {
+      amu += cN * mu;
+      alv += cN * 0.5f * (expf(lv) - 1.f);
+    }
+    st_c8(dy, v.dY2.rcap, i, f, amu);
+    st_c8(dy, v.dY2.rcap, i, v.Z + f, alv);
+    if (p >= 0) {
+      const float* q2 = v.Q.at(m) + (long long)(N + p) * 2 * v.Z;
+      float bmu = v.has_T ? v.dQ2.at(m)[(long long)p * 2 * v.Z + f] : 0.f;
+      float blv = v.has_T ? v.dQ2.at(m)[(long long)p * 2 * v.Z + v.Z + f] : 0.f;
+      if (v.kind == KIND_PVAE && v.klq_row.at(m)[N + p] > v.s.kl_min) {
+        bmu += cN * q2[f];
+        blv += cN * 0.5f * (expf(q2[v.Z + f]) - 1.f);
+      }
+      st_c8(dy, v.dY2.rcap, N + p, f, bmu);
+      st_c8(dy, v.dY2.rcap, N + p, v.Z + f, blv);
+    }
+  }
+  for (int f = 2 * v.Z + lane; f < v.dY2.fcap; f += 32) {
+    st_c8(dy, v.dY2.rcap, i, f, 0.f);
+    if (p >= 0) st_c8(dy, v.dY2.rcap, N + p, f, 0.f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// classifier weight gradient: dWc[j][t] = sum_r dlogit[r][j] * u[r][t], u = [z1, z2f - z1, 1]
+// two stages (row-split partials, then a fixed-order reduction) -> deterministic
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) clf_grad_partial_kernel(DevView v) {
+  const int m = blockIdx.y, split = blockIdx.x;
+  const int LN = v.counts.at(m)[CNT_LN];
+  const int width = v.clf_in + 1;
+  for (int t = threadIdx.x; t < width; t += 256) {
+    float acc[MAXY];
+#pragma unroll
+    for (int j = 0; j < MAXY; ++j) acc[j] = 0.f;
+    for (int r = split; r < LN; r += CLF_SPLITS) {
+      float u;
+      if (t < v.Z)
+        u = v.Z1f.at(m)[(long long)r * v.Z + t];
+      else if (t < v.clf_in)
+        u = v.Z2Ff.at(m)[(long long)r * v.Z + t - v.Z] - v.Z1f.at(m)[(long long)r * v.Z + t - v.Z];
+      else
+        u = 1.f;
+      const float* dl = v.dlogit.at(m) + (long long)r * v.Y;
+#pragma unroll
+      for (int j = 0; j < MAXY; ++j)
+        if (j < v.Y) acc[j] = fmaf(dl[j], u, acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < MAXY; ++j)
+      if (j < v.Y) v.clf_part.at(m)[((long long)split * v.Y + j) * width + t] = acc[j];
+  }
+}
+
+__global__ void __launch_bounds__(256) clf_grad_reduce_kernel(DevView v) {
+  const int m = blockIdx.x;
+  const int width = v.clf_in + 1;
+  for (int k = threadIdx.x; k < v.Y * width; k += 256) {
+    const int j = k / width, t = k - j * width;
+    float s = 0.f;
+    for (int sp = 0; sp < CLF_SPLITS; ++sp) s += v.clf_part.at(m)[((long long)sp * v.Y + j) * width + t];
+    float* g = v.grads.at(m);
+    if (t < v.clf_in)
+      g[v.clf_w_off + j * v.clf_in + t] = s;
+    else
+      g[v.clf_b_off + j] = s;
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// inference (DrVAE.forward, DrVAE.py:253-311): deterministic mu path, no sampling
+// ---------------------------------------------------------------------------------------------
+struct InferView {
+  float *z1_mu, *z1_lv, *z2_mu, *z2_lv, *proba;
+  int* pred;
+};
+
+__global__ void infer_counts_kernel(DevView v, int rows_dec) {
+  const int m = blockIdx.x;
+  if (threadIdx.x == 0) {
+    int* cnt = v.counts.at(m);
+    cnt[CNT_N] = v.N;
+    cnt[CNT_NP] = 0;
+    cnt[CNT_NLAB] = 0;
+    cnt[CNT_R0] = v.N;
+    cnt[CNT_LN] = v.N;
+    cnt[CNT_LNP] = 0;
+    cnt[CNT_RD] = rows_dec;
+    cnt[CNT_FL] = 0;
+    cnt[CNT_F] = 0;
+  }
+  for (int i = threadIdx.x; i < v.N; i += blockDim.x) {
+    v.lab.at(m)[i] = 0;
+    v.ycls.at(m)[i] = 0;
+  }
+}
+
+__device__ __forceinline__ void infer_emit_proba(const DevView& v, const InferView& o, int m, int r, int lane) {
+  if (lane == 0) {
+    const float* q = v.QY.at(m) + (long long)r * v.Y;
+    int best = 0;
+    for (int j = 0; j < v.Y; ++j) {
+      if (o.proba) o.proba[((long long)m * v.N + r) * v.Y + j] = q[j];
+      if (q[j] > q[best]) best = j;
+    }
+    if (o.pred) o.pred[(long long)m * v.N + r] = best;
+  }
+}
+
+// z1 = mu(q(z1|x1)); stage it for the p(z2|z1) and decoder GEMMs.  One warp per row.
+__global__ void __launch_bounds__(ROW_THREADS) infer_z1_kernel(DevView v, InferView o, int rows_dec) {
+  const int m = blockIdx.y, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  const int N = v.N;
+  if (r >= N) {
+    const int j = r - N;
+    if (j < PAD_ROWS && rows_dec + j < pad128(rows_dec)) zero_c8_row(v.Zdec, m, rows_dec + j, lane);
+    return;
+  }
+  const float* q = v.Q.at(m) + (long long)r * 2 * v.Z;
+  bf16* zdec = v.Zdec.at(m);
+  for (int f = lane; f < v.Zc; f += 32) {
+    float z = 0.f;
+    if (f < v.Z) {
+      z = q[f];
+      v.Z1f.at(m)[(long long)r * v.Z + f] = z;
+      if (o.z1_mu) o.z1_mu[((long long)m * N + r) * v.Z + f] = z;
+      if (o.z1_lv) o.z1_lv[((long long)m * N + r) * v.Z + f] = q[v.Z + f];
+    }
+    st_c8(zdec, v.Zdec.rcap, r, f, z);
+  }
+  if (v.has_clf && !v.has_T) {
+    __syncwarp();
+    classifier_row(v, m, r, r, lane);
+    __syncwarp();
+    infer_emit_proba(v, o, m, r, lane);
+  }
+}
+
+// z2 = mu(p(z2|z1)) = z1 + z1 W^T + b; classifier on [z1, z2 - z1].
+__global__ void __launch_bounds__(ROW_THREADS) infer_z2_kernel(DevView v, InferView o) {
+  const int m = blockIdx.y, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+  const int N = v.N;
+  if (r >= N) return;
+  const float* pt = v.PT.at(m) + (long long)r * 2 * v.Z;
+  const float* z1 = v.Z1f.at(m) + (long long)r * v.Z;
+  bf16* zdec = v.Zdec.at(m);
+  for (int f = lane; f < v.Zc; f += 32) {
+    float z = 0.f;
+    if (f < v.Z) {
+      z = z1[f] + pt[f];
+      v.Z2Ff.at(m)[(long long)r * v.Z + f] = z;
+      if (o.z2_mu) o.z2_mu[((long long)m * N + r) * v.Z + f] = z;
+      if (o.z2_lv) o.z2_lv[((long long)m * N + r) * v.Z + f] = pt[v.Z + f];
+    }
+    st_c8(zdec, v.Zdec.rcap, N + r, f, z);
+  }
+  if (v.has_clf) {
+    __syncwarp();
+    classifier_row(v, m, r, r, lane);
+    __syncwarp();
+    infer_emit_proba(v, o, m, r, lane);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// loss: fixed-order reduction of the per-row terms into the reference's loss dictionary
+// (DrVAE.py:610-626, PVAE.py:452-465, VFAE.py:438-458).  out: RECL KLD PERT YL MMD ELBO CMPL.
+// With global normalisers (data parallel) the outputs are this shard's additive share.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum_256(float x, float* sm) {
+  const int t = threadIdx.x;
+  sm[t] = x;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (t < o) sm[t] += sm[t + o];
+    __syncthreads();
+  }
+  const float r = sm[0];
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(256) loss_kernel(DevView v) {
+  __shared__ float sm[256];
+  const int m = blockIdx.x, t = threadIdx.x;
+  const int* cnt = v.counts.at(m);
+  const int LN = cnt[CNT_LN], LNp = cnt[CNT_LNP], Rd = cnt[CNT_RD], F = cnt[CNT_F], R0 = cnt[CNT_R0];
+  const float* cf = v.coefs.at(m);
+  float a_recl = 0.f, a_pert = 0.f;
+  for (int r = t; r < Rd; r += 256) {
+    float s = 0.f;
+    for (int k = 0; k < v.dec_tiles; ++k) s += v.dec_part.at(m)[(long long)k * v.Rdcap + r];
+    if (r < LN + LNp)
+      a_recl += s;
+    else
+      a_pert += s;
+  }
+  float a_klz2 = 0.f, a_yl = 0.f, a_ycat = 0.f, a_kfp = 0.f, a_klq = 0.f;
+  for (int r = t; r < LN; r += 256) {
+    if (v.has_T) a_klz2 += v.klz2_row.at(m)[r];
+    if (v.has_clf) {
+      a_yl += v.yl_row.at(m)[r];
+      a_ycat += v.ycat_row.at(m)[r];
+    }
+  }
+  if (v.has_fprop)
+    for (int e = t; e < F; e += 256) a_kfp += v.kfpw_row.at(m)[e];
+  if (v.kind == KIND_PVAE)
+    for (int r = t; r < R0; r += 256) a_klq += v.klq_row.at(m)[r];
+  a_recl = block_sum_256(a_recl, sm);
+  a_pert = block_sum_256(a_pert, sm);
+  a_klz2 = block_sum_256(a_klz2, sm);
+  a_yl = block_sum_256(a_yl, sm);
+  a_ycat = block_sum_256(a_ycat, sm);
+  a_kfp = block_sum_256(a_kfp, sm);
+  a_klq = block_sum_256(a_klq, sm);
+  if (t == 0) {
+    const float RECL = cf[COEF_RECL] * a_recl;
+    const float PERT = cf[COEF_PERT_PLAIN] * a_pert;
+    const float KLD = cf[COEF_KLZ2] * a_klz2 + cf[COEF_KLD] * (a_kfp + a_ycat) + cf[COEF_INV_N] * a_klq;
+    const float YL = cf[COEF_YL_PLAIN] * a_yl;
+    const float ELBO = RECL + v.s.beta_pert * v.s.pertloss_rate * PERT - KLD;
+    const float CMPL = -ELBO - v.s.yloss_rate * YL;
+    float* o = v.losses.at(m);
+    o[0] = RECL;
+    o[1] = KLD;
+    o[2] = PERT;
+    o[3] = YL;
+    o[4] = 0.f;
+    o[5] = ELBO;
+    o[6] = CMPL;
+    o[7] = 0.f;
+  }
+}
+
+}  // namespace drvae

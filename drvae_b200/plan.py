@@ -1,0 +1,264 @@
+"""Python handle on a C-ABI plan (include/drvae_b200.h): owns the torch tensors the kernels
+borrow (parameters, Adam moments, gradients) and marshals batches / hyper-parameters.
+
+PyTorch is used for device memory and streams only; every computation of the step happens in
+the shared library.  CUDA-only: there is no CPU fallback.
+"""
+import ctypes
+import math
+from collections import OrderedDict
+
+import torch
+
+from . import _lib
+from ._lib import Arch, Batch, EpsLayout, HParams, InferOut, KIND, Noise
+
+LOSS_KEYS = ("RECL", "KLD", "PERT", "YL", "MMD", "ELBO", "CMPL")
+
+
+class _CudaView:
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def anneal_coef(iter_num, iter_max=1000, iter_offset=0):
+    """DGMMixin._compute_anneal_coef (reference src/DGMMixin.py:77-89), 'linear' only."""
+    if iter_num - iter_offset > 0:
+        return min(1., 0.01 + (iter_num - iter_offset) / (1. * iter_max))
+    return 0.01
+
+
+class Plan:
+    def __init__(self, kind, dim_x, dim_y, dim_z1, dim_z3, enc_z1, dec_x, enc_z3=(), dec_z1=(), L=1, max_batch=200,
+                 n_models=1, weight_norm=False, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("drvae_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.kind = kind
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.E = int(n_models)
+        a = Arch()
+        a.kind = KIND[kind]
+        a.dim_x, a.dim_y, a.dim_z1, a.dim_z3 = int(dim_x), int(dim_y), int(dim_z1), int(dim_z3)
+        for name, lst in (("enc_z1", enc_z1), ("dec_x", dec_x), ("enc_z3", enc_z3), ("dec_z1", dec_z1)):
+            lst = [int(h) for h in lst]
+            if len(lst) > _lib.MAX_HIDDEN:
+                raise ValueError("at most %d hidden layers per block are supported" % _lib.MAX_HIDDEN)
+            setattr(a, "n_" + name, len(lst))
+            arr = getattr(a, name)
+            for i, h in enumerate(lst):
+                arr[i] = h
+        a.weight_norm = int(bool(weight_norm))
+        a.L = int(L)
+        a.max_batch = int(max_batch)
+        self.arch = a
+        self.L, self.Ncap = int(L), int(max_batch)
+        self.dim_x, self.dim_y, self.dim_z1, self.dim_z3 = a.dim_x, a.dim_y, a.dim_z1, a.dim_z3
+        h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.drvae_plan_create(ctypes.byref(a), self.E, ctypes.byref(h)), "plan_create")
+        self.h = h
+        self.P = int(self.lib.drvae_plan_param_count(h))
+        self.tensors = []
+        nm = ctypes.create_string_buffer(256)
+        for i in range(self.lib.drvae_plan_num_tensors(h)):
+            r, c, off = ctypes.c_int(), ctypes.c_int(), ctypes.c_longlong()
+            _lib.check(self.lib.drvae_plan_tensor_info(h, i, nm, 256, ctypes.byref(r), ctypes.byref(c), ctypes.byref(off)))
+            self.tensors.append((nm.value.decode(), r.value, c.value, off.value))
+        el = EpsLayout()
+        _lib.check(self.lib.drvae_plan_eps_layout(h, ctypes.byref(el)))
+        self.eps_layout = el
+        kw = dict(dtype=torch.float32, device=self.device)
+        self.params = torch.zeros(self.E, self.P, **kw)
+        self.adam_m = torch.zeros(self.E, self.P, **kw)
+        self.adam_v = torch.zeros(self.E, self.P, **kw)
+        self.grads = torch.zeros(self.E, self.P, **kw)
+        self.losses = torch.zeros(self.E, 8, **kw)
+        _lib.check(self.lib.drvae_plan_bind(h, _ptr(self.params), _ptr(self.adam_m), _ptr(self.adam_v), _ptr(self.grads)))
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.drvae_plan_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # ---- parameters -----------------------------------------------------------------------
+    def tensor_views(self, buf, model=0):
+        """name -> zero-copy view (reference shapes) into buf[model]."""
+        out = OrderedDict()
+        for name, r, c, off in self.tensors:
+            n = r * (c if c > 0 else 1)
+            v = buf[model, off:off + n]
+            out[name] = v.view(r, c) if c > 0 else v
+        return out
+
+    def state_dict(self, model=0):
+        return OrderedDict((k, v.detach().clone()) for k, v in self.tensor_views(self.params, model).items())
+
+    def load_state_dict(self, sd, model=0, strict=True):
+        views = self.tensor_views(self.params, model)
+        missing = [k for k in views if k not in sd]
+        extra = [k for k in sd if k not in views]
+        if strict and (missing or extra):
+            raise KeyError("state_dict mismatch: missing %s unexpected %s" % (missing, extra))
+        with torch.no_grad():
+            for k, v in views.items():
+                if k in sd:
+                    src = sd[k]
+                    if tuple(src.shape) != tuple(v.shape):
+                        raise ValueError("shape mismatch for %s: %s vs %s" % (k, tuple(src.shape), tuple(v.shape)))
+                    v.copy_(src.to(self.device, torch.float32))
+        self.sync_shadows()
+
+    def sync_shadows(self):
+        _lib.check(self.lib.drvae_sync_shadows(self.h, self._stream()), "sync_shadows")
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ---- marshalling ----------------------------------------------------------------------
+    def hparams(self, step, training=True, add_noise=True, noise_std=0.01, beta_pert=1.0, pertloss_rate=0.05,
+                kl_qz2pz2_rate=1.0, yloss_rate=1.0, kl_min=2.0, lr=5e-4, beta1=0.9, beta2=0.999, adam_eps=1e-8,
+                weight_decay=0.05, global_counts=None, prior_y=None):
+        hp = HParams()
+        hp.step, hp.training, hp.add_noise = int(step), int(training), int(add_noise)
+        hp.noise_std, hp.beta_pert, hp.pertloss_rate = noise_std, beta_pert, pertloss_rate
+        hp.kl_qz2pz2_rate, hp.yloss_rate, hp.kl_min = kl_qz2pz2_rate, yloss_rate, kl_min
+        hp.lr, hp.beta1, hp.beta2, hp.adam_eps, hp.weight_decay = lr, beta1, beta2, adam_eps, weight_decay
+        if global_counts is not None:
+            hp.global_N, hp.global_Np, hp.global_Nlab = [int(c) for c in global_counts]
+        ny = max(1, self.dim_y)
+        for j in range(8):
+            if prior_y is None:
+                hp.log_prior_y[j] = math.log(1.0 / ny)
+            else:
+                hp.log_prior_y[j] = math.log(float(prior_y[j])) if j < len(prior_y) else 0.0
+        return hp
+
+    def _batch(self, x1, x2=None, y=None, has_x2=None, has_y=None):
+        def f32(t):
+            if t is None:
+                return None
+            t = t.to(self.device, torch.float32)
+            return t.contiguous()
+
+        def i32(t):
+            if t is None:
+                return None
+            return t.to(self.device, torch.int32).contiguous()
+
+        x1 = f32(x1)
+        if x1.dim() == 2:
+            if self.E != 1:
+                raise ValueError("ensemble plans take batches shaped [n_models, N, dim_x]")
+            N = x1.shape[0]
+        else:
+            if x1.shape[0] != self.E:
+                raise ValueError("first batch dimension must be n_models")
+            N = x1.shape[1]
+        if x1.shape[-1] != self.dim_x:
+            raise ValueError("x1 has %d features, the model has dim_x=%d" % (x1.shape[-1], self.dim_x))
+        keep = [x1, f32(x2), i32(y), i32(has_x2), i32(has_y)]
+        for t in keep[1:]:
+            if t is not None and t.numel() not in (self.E * N, self.E * N * self.dim_x):
+                raise ValueError("batch field has an unexpected number of elements")
+        b = Batch(_ptr(keep[0]), _ptr(keep[1]), _ptr(keep[2]), _ptr(keep[3]), _ptr(keep[4]), int(N))
+        return b, keep
+
+    def _noise(self, eps, seed):
+        if eps is not None:
+            eps = eps.to(self.device, torch.float32).contiguous()
+            if eps.numel() != self.E * self.eps_layout.total:
+                raise ValueError("eps block must have n_models * %d floats" % self.eps_layout.total)
+        return Noise(_ptr(eps), int(seed) & 0xFFFFFFFFFFFFFFFF), eps
+
+    def _run(self, fn, what, batch, hp, eps=None, seed=0):
+        b, keep = self._batch(**batch)
+        nz, keep_eps = self._noise(eps, seed)
+        with torch.cuda.device(self.device):
+            _lib.check(fn(self.h, ctypes.byref(b), ctypes.byref(nz), ctypes.byref(hp), _ptr(self.losses), self._stream()), what)
+        del keep, keep_eps  # stream-ordered: torch's caching allocator keeps them alive for this stream
+        return self.losses
+
+    def train_step(self, batch, hp, eps=None, seed=0):
+        return self._run(self.lib.drvae_train_step, "train_step", batch, hp, eps, seed)
+
+    def grad_step(self, batch, hp, eps=None, seed=0):
+        return self._run(self.lib.drvae_grad_step, "grad_step", batch, hp, eps, seed)
+
+    def loss_forward(self, batch, hp, eps=None, seed=0):
+        return self._run(self.lib.drvae_loss_forward, "loss_forward", batch, hp, eps, seed)
+
+    def adam_step(self, hp):
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.drvae_adam_step(self.h, ctypes.byref(hp), self._stream()), "adam_step")
+
+    def infer(self, x1):
+        x1 = x1.to(self.device, torch.float32).contiguous()
+        if x1.dim() == 2:
+            x1 = x1.unsqueeze(0)
+        E, N = x1.shape[0], x1.shape[1]
+        if E != self.E:
+            raise ValueError("first dimension must be n_models")
+        kw = dict(dtype=torch.float32, device=self.device)
+        Z, X, Y = self.dim_z1, self.dim_x, max(1, self.dim_y)
+        res = OrderedDict()
+        res["z1_mu"], res["z1_lv"] = torch.empty(E, N, Z, **kw), torch.empty(E, N, Z, **kw)
+        res["px1_mu"], res["px1_sg"] = torch.empty(E, N, X, **kw), torch.empty(E, N, X, **kw)
+        if self.kind in ("drvae", "pvae"):
+            res["z2_mu"], res["z2_lv"] = torch.empty(E, N, Z, **kw), torch.empty(E, N, Z, **kw)
+            res["px2_mu"], res["px2_sg"] = torch.empty(E, N, X, **kw), torch.empty(E, N, X, **kw)
+        if self.kind in ("drvae", "vfae"):
+            res["proba"] = torch.empty(E, N, Y, **kw)
+            res["pred"] = torch.empty(E, N, dtype=torch.int32, device=self.device)
+        out = InferOut()
+        for k, v in res.items():
+            setattr(out, k, v.data_ptr())
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.drvae_infer(self.h, _ptr(x1), int(N), ctypes.byref(out), self._stream()), "infer")
+        return res
+
+    # ---- introspection --------------------------------------------------------------------
+    def set_gemm_impl(self, impl):
+        _lib.check(self.lib.drvae_set_gemm_impl(self.h, {"tc": 0, "simt": 1}[impl]))
+
+    def launch_count(self):
+        return int(self.lib.drvae_plan_launch_count(self.h))
+
+    def workspace_bytes(self):
+        return int(self.lib.drvae_plan_workspace_bytes(self.h))
+
+    def debug_buffer(self, name, dtype=torch.float32):
+        """Zero-copy [n_models, elems_per_model] view of a workspace buffer (tests only)."""
+        ptr, ms, nb = ctypes.c_void_p(), ctypes.c_longlong(), ctypes.c_longlong()
+        rcap, fcap = ctypes.c_int(), ctypes.c_int()
+        _lib.check(self.lib.drvae_debug_buffer(self.h, name.encode(), ctypes.byref(ptr), ctypes.byref(ms), ctypes.byref(nb),
+                                               ctypes.byref(rcap), ctypes.byref(fcap)), "debug_buffer")
+        item = {torch.float32: (4, "<f4"), torch.int32: (4, "<i4"), torch.bfloat16: (2, "<i2")}[dtype]
+        per = ms.value // item[0]
+        t = torch.as_tensor(_CudaView(ptr.value, (self.E, per), item[1]), device=self.device)
+        if dtype == torch.bfloat16:
+            t = t.view(torch.bfloat16)
+        return t[:, :nb.value // item[0]], rcap.value, fcap.value
+
+    def debug_c8(self, name, rows, feats, model=0):
+        from .layout import unpack_c8
+        t, rcap, fcap = self.debug_buffer(name, torch.bfloat16)
+        return unpack_c8(t[model].view(fcap // 8, rcap, 8), rows, feats)
+
+
+def losses_to_dict(kind, row):
+    """One row of the [n_models, 8] loss tensor -> the reference's OrderedDict of 0-dim tensors
+    (DrVAE.py:611-626; PVAE has no YL, VFAE has no PERT)."""
+    out = OrderedDict()
+    for i, k in enumerate(LOSS_KEYS):
+        if (kind == "pvae" and k == "YL") or (kind == "vfae" and k == "PERT"):
+            continue
+        out[k] = row[i]
+    return out

@@ -1,17 +1,152 @@
-/* drvae_b200 — C ABI of the B200-native DrVAE / PertVAE / VFAE training step.
+/* drvae_b200 — C ABI of the B200-native (sm_100a) DrVAE / PertVAE / VFAE training step.
  *
- * (bring-up revision: GEMM validation entry only; the step API follows)
+ * This is the drop-in boundary of SURVEY.md §8(b).  The reference (rampasek/DrVAE) has no FFI:
+ * its seam is Python method dispatch on the model object, so each entry point below names the
+ * reference method it replaces (paths relative to /root/reference/src):
+ *
+ *   drvae_train_step    DGMMixin.py:91-126  run_on_batch(train_mode=True): zero_grad,
+ *                       loss_function (DrVAE.py:545, PVAE.py:411, VFAE.py:403), backward, Adam.step
+ *   drvae_loss_forward  DGMMixin.py:110-115 run_on_batch(train_mode=False): eval-mode losses
+ *   drvae_grad_step     the forward+backward half of run_on_batch (for data-parallel runs: the
+ *   + drvae_adam_step   caller all-reduces the flat gradient between the two calls)
+ *   drvae_infer         DrVAE.py:253-311 / PVAE.py:206-246 / VFAE.py:178-215  forward()
+ *   drvae_sync_shadows  after load_state_dict (DGMMixin.py:199-203) or any external write to params
+ *
+ * Conventions
+ *   - plain C, no torch types; every pointer is a DEVICE pointer unless stated otherwise
+ *   - status return: 0 = ok, non-zero = error, text from drvae_last_error() (thread local);
+ *     nothing throws or aborts; there is no CPU fallback
+ *   - ownership: the caller (PyTorch) owns parameters, Adam moments, gradients, batches and
+ *     outputs; the plan owns only its workspace and the bf16 weight shadows
+ *   - all work is enqueued on the caller's stream; calls are asynchronous
+ *   - an "ensemble" is n_models identically shaped, independent models trained in one launch
+ *     sequence (grouped GEMMs); every per-model array is laid out [n_models][...]
  */
 #ifndef DRVAE_B200_H
 #define DRVAE_B200_H
+
 #ifdef __cplusplus
 extern "C" {
 #endif
+
+#define DRVAE_KIND_DRVAE 0
+#define DRVAE_KIND_PVAE 1
+#define DRVAE_KIND_VFAE 2
+#define DRVAE_MAX_HIDDEN 4
+
+typedef struct drvae_plan drvae_plan_t;
+
+/* Architecture = constructor arguments of the reference classes that shape tensors
+ * (DrVAE.py:45-70, PVAE.py:45-63, VFAE.py:42-60) with the run_*.py fixed choices:
+ * type_rec='diag_gaussian', nonlinearity='elu', type_y='discrete', clf_z1z2=True,
+ * use_s=False, use_MMD=False, dropout 0, batch norm off, dim_h_clf=[]. */
+typedef struct {
+  int kind;                /* DRVAE_KIND_* */
+  int dim_x, dim_y;
+  int dim_z1;
+  int dim_z3;              /* DrVAE dim_z3 / VFAE dim_z2 (top latent); ignored for PVAE */
+  int n_enc_z1, enc_z1[DRVAE_MAX_HIDDEN];   /* --enc-z1 */
+  int n_dec_x, dec_x[DRVAE_MAX_HIDDEN];     /* --dec-x  */
+  int n_enc_z3, enc_z3[DRVAE_MAX_HIDDEN];   /* --enc-z3 (DrVAE) / --enc-z2 (VFAE) */
+  int n_dec_z1, dec_z1[DRVAE_MAX_HIDDEN];   /* --dec-z1 */
+  int weight_norm;         /* layers.WeightNormLinear instead of nn.Linear (model.wn) */
+  int L;                   /* --L: Monte-Carlo samples per row */
+  int max_batch;           /* row capacity per model (--batch-size) */
+} drvae_arch_t;
+
+/* One minibatch per model, reference layout (DrVAE.py:956-961): x1, x2 float32 [n_models][N][dim_x]
+ * row-major; y, has_x2, has_y int32 [n_models][N].  Unused fields may be NULL (x2/has_x2 for
+ * VFAE, y/has_y for PVAE).  s is not consumed (use_s=False). */
+typedef struct {
+  const float* x1;
+  const float* x2;
+  const int* y;
+  const int* has_x2;
+  const int* has_y;
+  int N;
+} drvae_batch_t;
+
+/* Noise.  eps != NULL: parity mode, a row-indexed block of standard normals per model laid out
+ * as drvae_eps_layout() reports.  eps == NULL: the step draws its own with Philox4x32-10 keyed by
+ * (seed, step, model). */
+typedef struct {
+  const float* eps;
+  unsigned long long seed;
+} drvae_noise_t;
+
+/* Scalars of one step (reference: DrVAE.py:79-97 internals, run_drvae.py:173-185 ctor call). */
+typedef struct {
+  int step;               /* finished_training_iters before this step (Adam t = step + 1) */
+  int training;           /* 1: train mode (input noise if add_noise), 0: eval mode */
+  int add_noise;          /* --train-w-noise */
+  float noise_std;        /* --noise-var, used as a std multiplier (DrVAE.py:406) */
+  float beta_pert;        /* _compute_anneal_coef(step, itermax, offset), DGMMixin.py:77-89 */
+  float pertloss_rate, kl_qz2pz2_rate, yloss_rate;
+  float kl_min;           /* free bits, 2.0 */
+  float lr, beta1, beta2, adam_eps, weight_decay;
+  int global_N, global_Np, global_Nlab;  /* >0: batch-global normalisers (data-parallel shards) */
+  float log_prior_y[8];   /* log prior over classes ('uniform' -> log(1/dim_y)) */
+} drvae_hparams_t;
+
+/* Layout of the row-indexed eps block (floats, per model; Ncap = max_batch):
+ *   x1   [Ncap][dim_x]            input noise of x1 rows
+ *   x2   [Ncap][dim_x]            input noise of x2 rows (indexed by the row of the pair)
+ *   z1   [L][Ncap][dim_z1]        sample of q(z1|x1)
+ *   z2   [L][Ncap][dim_z1]        second sample of q(z1|x1) used as z2 (reference quirk)
+ *   z2f  [L][Ncap][dim_z1]        sample of p(z2|z1)
+ *   z3   [L][Ncap][dim_y][dim_z3] top latent; slot 0 for a labeled row, slot j for class j */
+typedef struct {
+  long long off_x1, off_x2, off_z1, off_z2, off_z2f, off_z3, total;
+} drvae_eps_layout_t;
+
+/* Outputs of drvae_infer, all [n_models][N][...] device buffers owned by the caller; any may be
+ * NULL.  (DrVAE.py:310-311 dictionary.) */
+typedef struct {
+  float* z1_mu;   float* z1_lv;    /* qz1                       [N][dim_z1] */
+  float* z2_mu;   float* z2_lv;    /* pz2 = p(z2|z1=mu)         [N][dim_z1] (DrVAE, PVAE) */
+  float* proba;   int* pred;       /* clamp(softmax), argmax    [N][dim_y], [N] (DrVAE, VFAE) */
+  float* px1_mu;  float* px1_sg;   /* p(x1|z1)                  [N][dim_x] */
+  float* px2_mu;  float* px2_sg;   /* p(x2|z2)                  [N][dim_x] (DrVAE, PVAE) */
+} drvae_infer_out_t;
+
 const char* drvae_last_error(void);
+
+int drvae_plan_create(const drvae_arch_t* arch, int n_models, drvae_plan_t** out);
+int drvae_plan_destroy(drvae_plan_t* plan);
+
+/* Parameter layout: tensors in the reference's state_dict order, each
+ * row-major at `offset` floats inside the flat per-model vector of drvae_plan_param_count(). */
+long long drvae_plan_param_count(const drvae_plan_t* plan);
+int drvae_plan_num_tensors(const drvae_plan_t* plan);
+int drvae_plan_tensor_info(const drvae_plan_t* plan, int index, char* name, int name_cap, int* rows, int* cols,
+                           long long* offset);
+int drvae_plan_eps_layout(const drvae_plan_t* plan, drvae_eps_layout_t* out);
+long long drvae_plan_workspace_bytes(const drvae_plan_t* plan);
+
+/* Bind caller-owned state: params, adam_m, adam_v, grads are float32 [n_models][param_count]. */
+int drvae_plan_bind(drvae_plan_t* plan, float* params, float* adam_m, float* adam_v, float* grads);
+int drvae_sync_shadows(drvae_plan_t* plan, void* stream);
+
+/* losses_out: float32 [n_models][8] = RECL, KLD, PERT, YL, MMD, ELBO, CMPL, 0 (device). */
+int drvae_train_step(drvae_plan_t* plan, const drvae_batch_t* batch, const drvae_noise_t* noise,
+                     const drvae_hparams_t* hp, float* losses_out, void* stream);
+int drvae_loss_forward(drvae_plan_t* plan, const drvae_batch_t* batch, const drvae_noise_t* noise,
+                       const drvae_hparams_t* hp, float* losses_out, void* stream);
+int drvae_grad_step(drvae_plan_t* plan, const drvae_batch_t* batch, const drvae_noise_t* noise,
+                    const drvae_hparams_t* hp, float* losses_out, void* stream);
+int drvae_adam_step(drvae_plan_t* plan, const drvae_hparams_t* hp, void* stream);
+int drvae_infer(drvae_plan_t* plan, const float* x1, int N, const drvae_infer_out_t* out, void* stream);
+
+/* Introspection for tests and bench.py */
+int drvae_set_gemm_impl(drvae_plan_t* plan, int impl);   /* 0 tcgen05 (default), 1 SIMT validation kernel */
+long long drvae_plan_launch_count(const drvae_plan_t* plan); /* kernels launched by this plan so far */
+int drvae_debug_buffer(drvae_plan_t* plan, const char* name, void** ptr, long long* model_stride_bytes,
+                       long long* bytes, int* rcap, int* fcap);
 int drvae_debug_gemm(int impl, int mode, const void* A, int a_rcap, int a_nchunks, long long a_ms,
                      const void* B, int b_rcap, int b_nchunks, long long b_ms, float* D, int ldd,
                      long long d_ms, int M, int N, int K, int BN, const int* dyn_dev, int ksplit,
                      int desc_variant, int n_models, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,1 +1,8 @@
-"""drvae_b200 — B200-native (sm_100a) training hot path of DrVAE / PertVAE / VFAE."""
+"""drvae_b200 — B200-native (sm_100a) training hot path of DrVAE / PertVAE / VFAE.
+
+Public surface mirrors the reference (rampasek/DrVAE, src/): the DrVAE, PVAE and VFAE classes with
+their constructor arguments, state_dict keys and methods.  Everything they compute goes through the
+C ABI in include/drvae_b200.h; there is no CPU fallback.
+"""
+from .models import DrVAE, PVAE, VFAE  # noqa: F401
+from .plan import Plan  # noqa: F401

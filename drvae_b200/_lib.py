@@ -61,7 +61,8 @@ EXPORTS = ["drvae_last_error", "drvae_plan_create", "drvae_plan_destroy", "drvae
            "drvae_plan_num_tensors", "drvae_plan_tensor_info", "drvae_plan_eps_layout",
            "drvae_plan_workspace_bytes", "drvae_plan_bind", "drvae_sync_shadows", "drvae_train_step",
            "drvae_loss_forward", "drvae_grad_step", "drvae_adam_step", "drvae_infer", "drvae_set_gemm_impl",
-           "drvae_plan_launch_count", "drvae_debug_buffer", "drvae_debug_gemm"]
+           "drvae_plan_launch_count", "drvae_debug_buffer", "drvae_debug_gemm", "drvae_profile_begin",
+           "drvae_profile_end"]
 
 
 def load():
@@ -105,6 +106,10 @@ def load():
     lib.drvae_infer.argtypes = [c_void_p, c_void_p, c_int, P(InferOut), c_void_p]
     lib.drvae_set_gemm_impl.restype = c_int
     lib.drvae_set_gemm_impl.argtypes = [c_void_p, c_int]
+    lib.drvae_profile_begin.restype = c_int
+    lib.drvae_profile_begin.argtypes = [c_void_p]
+    lib.drvae_profile_end.restype = c_int
+    lib.drvae_profile_end.argtypes = [c_void_p, ctypes.c_char_p, c_int]
     lib.drvae_debug_buffer.restype = c_int
     lib.drvae_debug_buffer.argtypes = [c_void_p, ctypes.c_char_p, P(c_void_p), P(c_ll), P(c_ll), P(c_int), P(c_int)]
     lib.drvae_debug_gemm.restype = c_int

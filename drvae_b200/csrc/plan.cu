@@ -78,6 +78,12 @@ struct drvae_plan {
   int gemm_impl = GEMM_IMPL_TC;
   long long launches = 0;
   bool shadows_valid = false;
+  // optional per-launch event timing (bench.py / profiles)
+  bool prof_on = false;
+  std::vector<cudaEvent_t> prof_ev;
+  std::vector<std::string> prof_tags;
+  size_t prof_used = 0;
+  std::map<std::string, std::pair<long long, double>> prof_acc;  // tag -> (launches, ms)
 };
 
 namespace {
@@ -313,7 +319,7 @@ extern "C" int drvae_plan_create(const drvae_arch_t* a, int n_models, drvae_plan
   const int Ncap = pl->Ncap;
   const int R0cap = round_up((pl->has_pair ? 2 : 1) * Ncap, 128);
   const int LNcap = round_up(L * Ncap, 128);
-  const int Rdcap = round_up((pl->has_pair ? 3 : 1) * L * Ncap, 128);
+  const int Rdcap = round_up((pl->has_pair ? 3 : 1) * L * Ncap, 128) + 128;  // +1 tile: inference reads H at row offset N
   const int Flcap = pl->has_fprop ? Y * Ncap : 0;
   const int Fcap = round_up(std::max(1, L * Flcap), 128);
   const int Xc = round_up(X, 16);
@@ -538,14 +544,37 @@ extern "C" int drvae_debug_buffer(drvae_plan_t* pl, const char* name, void** ptr
 // =============================================================================================
 namespace {
 
+void prof_pre(drvae_plan* pl, cudaStream_t st, const std::string& tag) {
+  if (!pl->prof_on) return;
+  if (pl->prof_used + 2 > pl->prof_ev.size()) {
+    for (int i = 0; i < 256; ++i) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      pl->prof_ev.push_back(e);
+    }
+  }
+  pl->prof_tags.push_back(tag);
+  cudaEventRecord(pl->prof_ev[pl->prof_used++], st);
+}
+void prof_post(drvae_plan* pl, cudaStream_t st) {
+  if (!pl->prof_on) return;
+  cudaEventRecord(pl->prof_ev[pl->prof_used++], st);
+}
+
 struct Exec {
   drvae_plan* pl;
   cudaStream_t st;
   DevView v;
   int N;
   cudaError_t err = cudaSuccess;
+  const char* phase = "";
+  std::string sub = "head";  // layer within the current block: h0, h1, ..., head
   bool ok() const { return err == cudaSuccess; }
+  // event bracket around one launch when profiling is on
+  void pre(const std::string& op) { prof_pre(pl, st, std::string(phase) + ":" + op); }
+  void post() { prof_post(pl, st); }
   void chk() {
+    post();
     if (err == cudaSuccess) err = cudaGetLastError();
     pl->launches++;
   }
@@ -562,12 +591,14 @@ struct Exec {
     e.ilv_block = e.ilv_stride = 1 << 30;
     return e;
   }
-  void launch(int epi, GemmProblem& p, const EpiParams& e) {
+  void launch(int epi, GemmProblem& p, const EpiParams& e, const char* op) {
     if (!ok()) return;
     p.dbg = pl->dbg;
     p.desc_variant = 0;
     if (p.ksplit < 1) p.ksplit = 1;
+    pre(op);
     cudaError_t r = gemm_launch(epi, p, e, pl->E, pl->gemm_impl, st);
+    post();
     if (r != cudaSuccess) err = r;
     pl->launches++;
   }
@@ -586,7 +617,7 @@ struct Exec {
     p.BN = W.BN;
     p.tiles_n = W.tiles_n;
     p.tiles_m = cdiv(row_bound, GEMM_BM);
-    launch(epi, p, e);
+    launch(epi, p, e, (std::string(epi == EPI_DECLOSS ? "gemm_nt_decloss." : "gemm_nt.") + sub).c_str());
   }
   // D[rows, kin] = dY[rows, nout] . W
   void gemm_dx(const C8Buf& dY, const Shadow& W, int epi, EpiParams e, int dyn_which, int row_bound) {
@@ -602,7 +633,7 @@ struct Exec {
     p.BN = W.BNx;
     p.tiles_n = W.tiles_nx;
     p.tiles_m = cdiv(row_bound, GEMM_BM);
-    launch(epi, p, e);
+    launch(epi, p, e, ("gemm_dx." + sub).c_str());
   }
   // grad W[nout, kin] = dY[rows, nout]^T . Xin[rows, kin]
   void gemm_dw(const C8Buf& dY, const C8Buf& Xin, int x_row0, const Shadow& W, int dyn_which, int row_bound) {
@@ -631,7 +662,7 @@ struct Exec {
     e.g_kvalid = W.kin;
     e.ilv_block = W.ilv_block;
     e.ilv_stride = W.ilv_stride;
-    launch(EPI_GRAD, p, e);
+    launch(EPI_GRAD, p, e, ("gemm_dw." + sub).c_str());
   }
   void colsum(const C8Buf& dY, const Shadow& W, int dyn_which, bool class_cols) {
     if (!ok()) return;
@@ -654,6 +685,7 @@ struct Exec {
     a.ld = W.ld;
     a.kmain = W.kin;
     dim3 grid(cdiv(dY.fcap >> 3, 4), pl->E);
+    pre("colsum." + sub);
     colsum_kernel<<<grid, 128, 0, st>>>(a);
     chk();
   }
@@ -703,19 +735,23 @@ struct Exec {
   void block_hidden_fwd(MlpBlock& b, const C8Buf& in, int in_row0, int dyn_which, int row_bound) {
     for (size_t i = 0; i < b.hidden.size(); ++i) {
       const C8Buf& src = (i == 0) ? in : b.H[i - 1];
+      sub = "h" + std::to_string(i);
       gemm_nt(src, i == 0 ? in_row0 : 0, b.hidden[i], EPI_ELU_C8, epi_elu(b.hidden[i], b.H[i], b.widths[i], b.class_aug && i == 0),
               dyn_which, row_bound);
     }
+    sub = "head";
   }
   // backward of a block given the head gradient rows dYh; optionally the input gradient as fp32
   void block_bwd(MlpBlock& b, const C8Buf& dYh, const C8Buf& in, int in_row0, int in_feat, float* dx_out, long long dx_ms,
                  int dyn_which, int row_bound) {
     const int n = (int)b.hidden.size();
+    sub = "head";
     gemm_dw(dYh, b.H[n - 1], 0, b.head, dyn_which, row_bound);
     colsum(dYh, b.head, dyn_which, false);
     gemm_dx(dYh, b.head, EPI_DACT_C8, epi_dact(b.H[n - 1], b.dPre[n - 1], b.widths[n - 1]), dyn_which, row_bound);
     for (int i = n - 1; i >= 0; --i) {
       const C8Buf& src = (i == 0) ? in : b.H[i - 1];
+      sub = "h" + std::to_string(i);
       gemm_dw(b.dPre[i], src, i == 0 ? in_row0 : 0, b.hidden[i], dyn_which, row_bound);
       colsum(b.dPre[i], b.hidden[i], dyn_which, b.class_aug && i == 0);
       if (i > 0) {
@@ -724,6 +760,7 @@ struct Exec {
         gemm_dx(b.dPre[0], b.hidden[0], EPI_STORE_F32, epi_f32(dx_out, dx_ms, in_feat, in_feat, nullptr), dyn_which, row_bound);
       }
     }
+    sub = "head";
   }
 };
 
@@ -800,7 +837,9 @@ int run_adam(drvae_plan* pl, const drvae_hparams_t* hp, int update, cudaStream_t
     a.bc2 = (float)(1.0 - pow((double)hp->beta2, t));
   }
   dim3 grid(cdiv(pl->P, 1024), pl->E);
+  prof_pre(pl, st, update ? "opt:adam" : "opt:shadow_sync");
   adam_kernel<<<grid, 256, 0, st>>>(a);
+  prof_post(pl, st);
   pl->launches++;
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return set_cuda_error("adam_kernel", err);
@@ -829,27 +868,35 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
 
   if (!(nz && nz->eps)) {
     dim3 g(cdiv((int)cdiv((int)pl->epsl.total, 4), 256), E);
+    ex.pre("philox_normal");
     philox_normal_kernel<<<g, 256, 0, st>>>(pl->eps_own, pl->epsl.total, nz ? nz->seed : 0ULL, (unsigned)hp->step);
     ex.chk();
   }
+  ex.pre("rowmap");
   rowmap_kernel<<<E, 256, 0, st>>>(v);
   ex.chk();
+  ex.pre("prep");
   prep_kernel<<<dim3(round_up(R0b, 128), E), 128, 0, st>>>(v);
   ex.chk();
 
   // ---- encoder q(z1|x1), shared with q(z2|x2) (DrVAE.py:408,418) ----
+  ex.phase = "enc.fwd";
   ex.block_hidden_fwd(pl->enc, v.Ain, 0, CNT_R0, R0b);
   ex.gemm_nt(pl->enc.H.back(), 0, pl->enc.head, EPI_STORE_F32, ex.epi_f32(v.Q.p, v.Q.ms, 2 * pl->Z, 2 * pl->Z, &pl->enc.head),
              CNT_R0, R0b);
+  ex.pre("sample_q1");
   sample_q1_kernel<<<rows_grid(N + PAD_ROWS), ROW_THREADS, 0, st>>>(v);
   ex.chk();
   // ---- p(z2|z1) ----
+  ex.phase = "T.fwd";
   if (pl->has_T) {
     ex.gemm_nt(v.Zdec, 0, pl->Tsh, EPI_STORE_F32, ex.epi_f32(v.PT.p, v.PT.ms, 2 * pl->Z, 2 * pl->Z, &pl->Tsh), CNT_LN, LNb);
+    ex.pre("T_post");
     T_post_kernel<<<rows_grid(N + PAD_ROWS), ROW_THREADS, 0, st>>>(v);
     ex.chk();
   }
   // ---- decoder p(x|z) on the stacked rows [z1 | z2 | z2f], fused log-density + gradient ----
+  ex.phase = "dec.fwd";
   ex.block_hidden_fwd(pl->dec, v.Zdec, 0, CNT_RD, Rdb);
   {
     EpiParams e = ex.epi_base();
@@ -874,17 +921,22 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
   }
   // ---- label-dependent part: q(z_top|z1,y), p(z1|z_top,y) per (row, class) evaluation ----
   if (pl->has_fprop) {
+    ex.phase = "z3.fwd";
     ex.block_hidden_fwd(pl->z3b, v.Z1e, 0, CNT_F, Fb);
     ex.gemm_nt(pl->z3b.H.back(), 0, pl->z3b.head, EPI_STORE_F32,
                ex.epi_f32(v.Q3.p, v.Q3.ms, 2 * pl->Z3, 2 * pl->Z3, &pl->z3b.head), CNT_F, Fb);
+    ex.pre("z3_post");
     z3_post_kernel<<<rows_grid(round_up(Fb, 128)), ROW_THREADS, 0, st>>>(v);
     ex.chk();
+    ex.phase = "dz1.fwd";
     ex.block_hidden_fwd(pl->dz1b, v.Z3b, 0, CNT_F, Fb);
     ex.gemm_nt(pl->dz1b.H.back(), 0, pl->dz1b.head, EPI_STORE_F32,
                ex.epi_f32(v.PZ1.p, v.PZ1.ms, 2 * pl->Z, 2 * pl->Z, &pl->dz1b.head), CNT_F, Fb);
+    ex.pre("pz1_post");
     pz1_post_kernel<<<rows_grid(round_up(Fb, 128)), ROW_THREADS, 0, st>>>(v);
     ex.chk();
   }
+  ex.pre("loss");
   loss_kernel<<<E, 256, 0, st>>>(v);
   ex.chk();
   if (losses_out && ex.ok()) {
@@ -895,27 +947,39 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
 
   if (backward && ex.ok()) {
     if (pl->has_fprop) {
+      ex.phase = "dz1.bwd";
       ex.block_bwd(pl->dz1b, v.dY9, v.Z3b, 0, pl->Z3, v.dZ3.p, v.dZ3.ms, CNT_F, Fb);
+      ex.pre("z3_back");
       z3_back_kernel<<<rows_grid(round_up(Fb, 128)), ROW_THREADS, 0, st>>>(v);
       ex.chk();
+      ex.phase = "z3.bwd";
       ex.block_bwd(pl->z3b, v.dY7, v.Z1e, 0, pl->Z, v.dZ1e.p, v.dZ1e.ms, CNT_F, Fb);
     }
+    ex.phase = "dec.bwd";
     ex.block_bwd(pl->dec, pl->dY5, v.Zdec, 0, pl->Z, v.dZdec.p, v.dZdec.ms, CNT_RD, Rdb);
     if (pl->has_clf) {
+      ex.phase = "clf.bwd";
+      ex.pre("clf_back");
       clf_back_kernel<<<rows_grid(LNb), ROW_THREADS, 0, st>>>(v);
       ex.chk();
+      ex.pre("clf_grad_partial");
       clf_grad_partial_kernel<<<dim3(CLF_SPLITS, E), 256, 0, st>>>(v);
       ex.chk();
+      ex.pre("clf_grad_reduce");
       clf_grad_reduce_kernel<<<E, 256, 0, st>>>(v);
       ex.chk();
     }
     if (pl->has_T) {
+      ex.phase = "T.bwd";
+      ex.pre("T_back");
       T_back_kernel<<<rows_grid(N + PAD_ROWS), ROW_THREADS, 0, st>>>(v);
       ex.chk();
       ex.gemm_dw(v.dYT, v.Zdec, 0, pl->Tsh, CNT_LN, LNb);
       ex.colsum(v.dYT, pl->Tsh, CNT_LN, false);
       ex.gemm_dx(v.dYT, pl->Tsh, EPI_STORE_F32, ex.epi_f32(v.dZ1T.p, v.dZ1T.ms, pl->Z, pl->Z, nullptr), CNT_LN, LNb);
     }
+    ex.phase = "enc.bwd";
+    ex.pre("q_back");
     q_back_kernel<<<rows_grid(N + PAD_ROWS), ROW_THREADS, 0, st>>>(v);
     ex.chk();
     ex.block_bwd(pl->enc, v.dY2, v.Ain, 0, pl->X, nullptr, 0, CNT_R0, R0b);
@@ -985,17 +1049,21 @@ extern "C" int drvae_infer(drvae_plan_t* pl, const float* x1, int N, const drvae
   const int rows_dec = pl->has_T ? 2 * N : N;
   InferView o{out->z1_mu, out->z1_lv, out->z2_mu, out->z2_lv, out->proba, out->pred};
   auto rows_grid = [&](int rows) { return dim3(cdiv(rows, ROW_WARPS), E); };
+  ex.pre("infer_counts");
   infer_counts_kernel<<<E, 128, 0, st>>>(v, rows_dec);
   ex.chk();
+  ex.pre("prep");
   prep_kernel<<<dim3(round_up(N, 128), E), 128, 0, st>>>(v);
   ex.chk();
   ex.block_hidden_fwd(pl->enc, v.Ain, 0, CNT_R0, N);
   ex.gemm_nt(pl->enc.H.back(), 0, pl->enc.head, EPI_STORE_F32, ex.epi_f32(v.Q.p, v.Q.ms, 2 * pl->Z, 2 * pl->Z, &pl->enc.head),
              CNT_R0, N);
+  ex.pre("infer_z1");
   infer_z1_kernel<<<rows_grid(N + PAD_ROWS), ROW_THREADS, 0, st>>>(v, o, rows_dec);
   ex.chk();
   if (pl->has_T) {
     ex.gemm_nt(v.Zdec, 0, pl->Tsh, EPI_STORE_F32, ex.epi_f32(v.PT.p, v.PT.ms, 2 * pl->Z, 2 * pl->Z, &pl->Tsh), CNT_LN, N);
+    ex.pre("infer_z2");
     infer_z2_kernel<<<rows_grid(N), ROW_THREADS, 0, st>>>(v, o);
     ex.chk();
   }
@@ -1017,5 +1085,41 @@ extern "C" int drvae_infer(drvae_plan_t* pl, const float* x1, int N, const drvae
     }
   }
   if (!ex.ok()) return set_cuda_error("drvae_infer launch", ex.err);
+  return 0;
+}
+
+// ---- optional per-launch timing: events around every launch of the plan, accumulated by tag ----
+extern "C" int drvae_profile_begin(drvae_plan_t* pl) {
+  if (!pl) return set_error("drvae_profile_begin: null plan");
+  pl->prof_on = true;
+  pl->prof_used = 0;
+  pl->prof_tags.clear();
+  pl->prof_acc.clear();
+  return 0;
+}
+extern "C" int drvae_profile_end(drvae_plan_t* pl, char* out, int cap) {
+  if (!pl) return set_error("drvae_profile_end: null plan");
+  pl->prof_on = false;
+  cudaError_t err = cudaDeviceSynchronize();
+  if (err != cudaSuccess) return set_cuda_error("drvae_profile_end", err);
+  for (size_t i = 0; i < pl->prof_tags.size(); ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, pl->prof_ev[2 * i], pl->prof_ev[2 * i + 1]);
+    auto& a = pl->prof_acc[pl->prof_tags[i]];
+    a.first += 1;
+    a.second += ms;
+  }
+  std::string txt;
+  char line[256];
+  for (auto& kv : pl->prof_acc) {
+    snprintf(line, sizeof(line), "%s %lld %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+    txt += line;
+  }
+  if (out && cap > 0) {
+    strncpy(out, txt.c_str(), cap - 1);
+    out[cap - 1] = 0;
+  }
+  pl->prof_used = 0;
+  pl->prof_tags.clear();
   return 0;
 }

@@ -231,6 +231,19 @@ class Plan:
     def launch_count(self):
         return int(self.lib.drvae_plan_launch_count(self.h))
 
+    def profile_begin(self):
+        _lib.check(self.lib.drvae_profile_begin(self.h), "profile_begin")
+
+    def profile_end(self):
+        """-> {tag: (launches, total_ms)} for everything launched since profile_begin()."""
+        buf = ctypes.create_string_buffer(1 << 16)
+        _lib.check(self.lib.drvae_profile_end(self.h, buf, len(buf)), "profile_end")
+        out = {}
+        for line in buf.value.decode().splitlines():
+            tag, n, ms = line.rsplit(" ", 2)
+            out[tag] = (int(n), float(ms))
+        return out
+
     def workspace_bytes(self):
         return int(self.lib.drvae_plan_workspace_bytes(self.h))
 

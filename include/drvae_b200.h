@@ -140,6 +140,10 @@ int drvae_infer(drvae_plan_t* plan, const float* x1, int N, const drvae_infer_ou
 /* Introspection for tests and bench.py */
 int drvae_set_gemm_impl(drvae_plan_t* plan, int impl);   /* 0 tcgen05 (default), 1 SIMT validation kernel */
 long long drvae_plan_launch_count(const drvae_plan_t* plan); /* kernels launched by this plan so far */
+/* Per-launch CUDA-event timing of everything the plan launches between begin and end; `out`
+ * receives lines "phase:kernel launches total_ms". */
+int drvae_profile_begin(drvae_plan_t* plan);
+int drvae_profile_end(drvae_plan_t* plan, char* out, int cap);
 int drvae_debug_buffer(drvae_plan_t* plan, const char* name, void** ptr, long long* model_stride_bytes,
                        long long* bytes, int* rcap, int* fcap);
 int drvae_debug_gemm(int impl, int mode, const void* A, int a_rcap, int a_nchunks, long long a_ms,

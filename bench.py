@@ -270,7 +270,15 @@ def main():
     for tag, (n, tms) in prof.items():
         per = tms / n  # ms per launch
         r = {"kernel": tag, "ms_per_launch": per, "share": tms / total_prof}
-        if tag in dims:
+        base = tag.replace("gemm_dw_adam", "gemm_dw")
+        if base != tag and base in dims:
+            # weight-gradient GEMM with Adam fused into its epilogue: the kernel streams this layer's
+            # optimizer state (read p, m, v; write p, m, v: 24 B/param) -> HBM-bound
+            mm, nn, kk = dims[base]
+            by = 24.0 * (mm * nn + mm) * M  # weights + biases of the layer
+            r.update(bound="hbm", achieved=by / (per * 1e-3) / 1e9, peak=peaks["hbm"], unit="GB/s",
+                     gemm_tflops=2.0 * mm * nn * kk * M / (per * 1e-3) / 1e12)
+        elif tag in dims:
             mm, nn, kk = dims[tag]
             fl = 2.0 * mm * nn * kk * M
             r.update(bound="tensor", achieved=fl / (per * 1e-3) / 1e12, peak=peaks["bf16_sustained"], unit="TFLOP/s")

@@ -146,6 +146,32 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// Two 16-column loads in flight before one wait (decoder heads: mu and sigma halves of a tile).
+__device__ __forceinline__ void tmem_ld16x2(uint32_t taddr0, uint32_t taddr1, float (&v0)[16], float (&v1)[16]) {
+  uint32_t r[16], q[16];
+  __syncwarp();
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr0)
+      : "memory");
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7]),
+        "=r"(q[8]), "=r"(q[9]), "=r"(q[10]), "=r"(q[11]), "=r"(q[12]), "=r"(q[13]), "=r"(q[14]), "=r"(q[15])
+      : "r"(taddr1)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    v0[i] = __uint_as_float(r[i]);
+    v1[i] = __uint_as_float(q[i]);
+  }
+}
+
 // UMMA shared-memory matrix descriptor, no-swizzle ("interleave") canonical layout.
 // Field meaning follows cute::UMMA::SmemDescriptor (start>>4 | LBO>>4 @16 | SBO>>4 @32 |
 // version=1 @46 | layout_type=0 @61).  For a K-major operand SBO is the byte distance between
@@ -176,7 +202,9 @@ __device__ __forceinline__ uint32_t umma_idesc_bf16(int bn, int a_mn_major, int 
 // ---------------------------------------------------------------------------------------------
 // small math helpers shared by epilogues and row kernels
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
+// ELU(alpha=1).  exp(x) - 1 with the fast exponential: the result is stored as bf16 (8 mantissa
+// bits), so the cancellation error near 0 (~6e-8 absolute) is far below the storage rounding.
+__device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
 // d ELU / d pre, recovered from the stored (bf16-rounded) activation h: 1 if h > 0 else h + 1.
 __device__ __forceinline__ float elu1_grad_from_out(float h) { return h > 0.f ? 1.f : h + 1.f; }
 // torch.nn.Softplus(beta=1, threshold=20)

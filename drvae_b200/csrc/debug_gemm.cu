@@ -37,15 +37,19 @@ extern "C" int drvae_debug_gemm(int impl, int mode, const void* A, int a_rcap, i
   EpiParams e{};
   int epi = EPI_STORE_F32;
   if (p.ksplit > 1) {
-    // exercise the atomic path through the gradient epilogue with an identity row map
+    // exercise the atomic path through the gradient epilogue with an identity row map: the
+    // epilogue stores D transposed (reference weight layout [out = D col][in = D row]), so the
+    // caller's buffer holds D^T as [N][M]
     epi = EPI_GRAD;
     e.grad = D;
     e.grad_ms = d_ms;
     e.g_ntens = 1;
     e.g_off[0] = 0;
-    e.g_rows[0] = M;
-    e.g_ld = ldd;
-    e.g_kvalid = N;
+    e.g_boff[0] = 0;
+    e.g_rows[0] = N;
+    e.g_ld = M;
+    e.g_kin = M;
+    e.g_kaug = M;
     e.ilv_block = 1 << 30;
     e.ilv_stride = 1 << 30;
   } else {

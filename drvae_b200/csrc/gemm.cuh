@@ -6,7 +6,13 @@
 // the same chunk8 operand storage (see common.cuh):
 //   GEMM_NT  forward        D[rows, out]  = X[rows, in]   . W[out, in]^T     (A, B K-major)
 //   GEMM_DX  input grad     D[rows, in]   = dY[rows, out] . W[out, in]       (A K-major, B MN-major)
-//   GEMM_DW  weight grad    D[out, in]    = dY[rows, out]^T . X[rows, in]    (A, B MN-major)
+//   GEMM_DW  weight grad    D[in, out]    = X[rows, in]^T . dY[rows, out]    (A, B MN-major)
+// The weight gradient is produced TRANSPOSED (D row = input feature, D column = output feature)
+// so that the 32 lanes of an epilogue warp (32 consecutive D rows) touch 32 consecutive elements
+// of a row of the reference's [out, in] weight tensor: gradient stores — and, in the fused
+// variant, the whole Adam read-modify-write of p, m, v — are 128-byte coalesced.  Every GEMM
+// input carries a ones column (and the one-hot class columns of [z, onehot(y)] inputs) after its
+// last real feature, so the bias and class-column gradients are rows of the same D tile.
 // Operand tiles are moved global->shared with 1-D bulk copies (TMA engine) into the no-swizzle
 // UMMA canonical layout, multiplied with tcgen05.mma (bf16 in, fp32 accumulate in TMEM) by one
 // elected thread, and the accumulator tile is read back with tcgen05.ld by four epilogue warps
@@ -26,17 +32,20 @@ enum {
   EPI_STORE_F32 = 0,  // (+bias) -> fp32 row-major
   EPI_ELU_C8 = 1,     // +bias (+class bias) -> ELU -> bf16 chunk8
   EPI_DACT_C8 = 2,    // * ELU'(stored activation) -> bf16 chunk8
-  EPI_GRAD = 3,       // weight gradient -> flat fp32 grad buffer in the reference tensor layout
+  EPI_GRAD = 3,       // weight (+bias, +class column) gradient -> flat fp32 grad buffer, reference tensor layout
   EPI_DECLOSS = 4,    // decoder heads: Gaussian log-density partials + d loss / d pre-activation
   EPI_DECOUT = 5,     // decoder heads at inference: mu and sigma as fp32 row-major
-  EPI_LIN_C8 = 6      // +bias -> bf16 chunk8 (no activation)
+  EPI_LIN_C8 = 6,     // +bias -> bf16 chunk8 (no activation)
+  EPI_GRAD_ADAM = 7   // as EPI_GRAD, but the gradient never leaves the SM: fused Adam update of p, m, v
+                      // and refresh of the bf16 weight shadow / derived bias in the same epilogue
 };
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_MAX_STAGES = 6;
 constexpr int GEMM_A_STAGE_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
-constexpr int GEMM_THREADS = 128;
+constexpr int GEMM_THREADS = 256;
+constexpr int EPI_GROUPS = GEMM_THREADS / 128;  // column groups: warp w reads TMEM lanes 32*(w%4).., columns of group w/4
 
 struct GemmOperand {
   const bf16* base;        // model 0
@@ -74,11 +83,11 @@ struct EpiParams {
   long long out_c8_ms;
   int out_c8_rcap;
   int out_c8_row0;
-  int n_valid;  // valid output columns (features)
+  int n_valid;  // valid output columns (features); chunk8 outputs get a ones column at n_valid
   // bias: derived fp32 vector of length >= tiles_n*BN (constant offsets folded in, zero padded)
   const float* bias;
   long long bias_ms;
-  // per-class bias rows (one-hot y folded out of the GEMM): clsb[cls*clsb_ld + col]
+  // per-class bias rows (one-hot y folded out of the forward GEMM): clsb[cls*clsb_ld + col]
   const float* clsb;
   long long clsb_ms;
   int clsb_ld;
@@ -89,26 +98,45 @@ struct EpiParams {
   long long act_ms;
   int act_rcap;
   int act_row0;
-  // EPI_GRAD: D row = shadow row -> (tensor which, row n); D col = input feature k
+  // EPI_GRAD / EPI_GRAD_ADAM: D row = input feature k (k == g_kin: ones column -> bias gradient,
+  // k > g_kin: one-hot class columns), D col = shadow row -> (tensor which, row n)
   float* grad;
-  long long grad_ms;
+  long long grad_ms;  // also the model stride of params / adam_m / adam_v
   int g_ntens;
-  int g_off[2];
+  int g_off[2];   // flat offsets of the weight tensors
+  int g_boff[2];  // flat offsets of the bias tensors
   int g_rows[2];
-  int g_ld;
-  int g_kvalid;
+  int g_ld;       // leading dimension of the weight tensors (g_kin + class columns)
+  int g_kin;      // true input features
+  int g_kaug;     // g_kin + 1 + class columns
   int ilv_block;
   int ilv_stride;
+  // EPI_GRAD_ADAM
+  float* adam_p;
+  float* adam_m;
+  float* adam_v;
+  bf16* sh;           // this layer's bf16 chunk8 shadow (model 0)
+  long long sh_ms;
+  int sh_rcap;
+  float* drv;         // derived fp32 arena (model 0)
+  long long drv_ms;
+  long long drv_bias_off;
+  long long drv_clsb_off;
+  int drv_clsb_ld;
+  float bias_const[2];
+  float lr_bc1, beta1, beta2, adam_eps, wd, inv_sqrt_bc2;  // lr_bc1 = lr / (1 - beta1^t)
   // EPI_DECLOSS / EPI_DECOUT
-  const float* tgt;  // fp32 targets [R0cap][X] row-major
-  long long tgt_ms;
-  int X;             // feature count (= n_valid / ... ) of the data space
-  const int* counts; // per-model counts block (see plan.h CNT_*)
+  const float4* tgt4;  // fp32 targets, chunk4 layout [Xc/4][tgt_rcap] float4
+  long long tgt_ms;    // float4 elements between models
+  int tgt_rcap;
+  int X;             // feature count of the data space
+  int Xc;            // feature capacity of tgt4 (multiple of 16)
+  const int* counts; // per-model counts block (CNT_*)
   int counts_stride;
   const float* coefs;  // per-model coefficient block (COEF_*)
   int coefs_stride;
   int L;
-  float* part;  // [tiles_n][Rdcap] row partial log-densities
+  float* part;  // [tiles_n * EPI_GROUPS][Rdcap] row partial log-densities
   long long part_ms;
   int part_rcap;
   int write_dy;  // 0 in eval mode (loss only)
@@ -131,10 +159,11 @@ enum {
 struct RowCtx {
   int model;
   int row;     // D row (global within the problem)
+  int cg;      // column group of the calling warp (0 .. EPI_GROUPS-1)
   bool valid;  // row < dynamic extent
   int cls;
   // DECLOSS
-  const float* trow;
+  int trow;    // target row, -1: none
   float coef;
   float lsum;
 };
@@ -147,13 +176,13 @@ template <int EPI>
 __device__ __forceinline__ void epi_begin(const EpiParams& e, RowCtx& rc) {
   rc.cls = 0;
   rc.lsum = 0.f;
-  rc.trow = nullptr;
+  rc.trow = -1;
   rc.coef = 0.f;
   if (EPI == EPI_ELU_C8) {
     if (e.row_cls && rc.valid) rc.cls = e.row_cls[rc.model * e.row_cls_ms + rc.row];
   }
-  if (EPI == EPI_DECLOSS || EPI == EPI_DECOUT) {
-    if (rc.valid && e.tgt) {
+  if (EPI == EPI_DECLOSS) {
+    if (rc.valid) {
       const int* cnt = e.counts + (long long)rc.model * e.counts_stride;
       const float* cf = e.coefs + (long long)rc.model * e.coefs_stride;
       const int N = cnt[CNT_N], Np = cnt[CNT_NP];
@@ -170,10 +199,18 @@ __device__ __forceinline__ void epi_begin(const EpiParams& e, RowCtx& rc) {
         t = N + (rc.row - LN - LNp) % Np;
         c = cf[COEF_PERT];
       }
-      rc.trow = e.tgt + rc.model * e.tgt_ms + (long long)t * e.X;
+      rc.trow = t;
       rc.coef = c;
     }
   }
+}
+
+// shadow row -> (tensor, row) through the interleave map
+__device__ __forceinline__ void ilv_decode(const EpiParams& e, int srow, int& which, int& n) {
+  const int blk = srow / e.ilv_stride;
+  const int rem = srow - blk * e.ilv_stride;
+  which = rem / e.ilv_block;
+  n = blk * e.ilv_block + (rem - which * e.ilv_block);
 }
 
 template <int EPI>
@@ -182,10 +219,21 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& e, RowCtx& rc, int co
     if (!rc.valid) return;
     float* o = e.out_f32 + rc.model * e.out_f32_ms + (long long)(e.out_row0 + rc.row) * e.out_ld;
     const float* b = e.bias ? e.bias + rc.model * e.bias_ms : nullptr;
+    if (((e.out_ld | e.n_valid) & 3) == 0) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      int c = col0 + i;
-      if (c < e.n_valid) o[c] = acc[i] + (b ? b[c] : 0.f);
+      for (int i = 0; i < 16; i += 4) {
+        const int c = col0 + i;
+        if (c < e.n_valid) {
+          float4 bv = b ? *reinterpret_cast<const float4*>(b + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(o + c) = make_float4(acc[i] + bv.x, acc[i + 1] + bv.y, acc[i + 2] + bv.z, acc[i + 3] + bv.w);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        int c = col0 + i;
+        if (c < e.n_valid) o[c] = acc[i] + (b ? b[c] : 0.f);
+      }
     }
   } else if (EPI == EPI_ELU_C8 || EPI == EPI_LIN_C8 || EPI == EPI_DACT_C8) {
     float v[16];
@@ -209,37 +257,117 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& e, RowCtx& rc, int co
         v[i] = ok ? acc[i] * elu1_grad_from_out(h[i]) : 0.f;
       }
     } else {
-      const float* b = e.bias + rc.model * e.bias_ms;
-      const float* cb = e.clsb ? e.clsb + rc.model * e.clsb_ms + (long long)rc.cls * e.clsb_ld : nullptr;
+      const float* b = e.bias + rc.model * e.bias_ms + col0;
+      const float* cb = e.clsb ? e.clsb + rc.model * e.clsb_ms + (long long)rc.cls * e.clsb_ld + col0 : nullptr;
+      float bb[16];
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) {
+        float4 t = *reinterpret_cast<const float4*>(b + i);
+        if (cb) {
+          float4 u = *reinterpret_cast<const float4*>(cb + i);
+          t.x += u.x;
+          t.y += u.y;
+          t.z += u.z;
+          t.w += u.w;
+        }
+        bb[i] = t.x;
+        bb[i + 1] = t.y;
+        bb[i + 2] = t.z;
+        bb[i + 3] = t.w;
+      }
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         int c = col0 + i;
-        bool ok = rc.valid && c < e.n_valid;
-        float x = acc[i] + b[c] + (cb ? cb[c] : 0.f);
+        float x = acc[i] + bb[i];
         if (EPI == EPI_ELU_C8) x = elu1(x);
-        v[i] = ok ? x : 0.f;
+        // column n_valid is the ones column the next layer's dW turns into its bias gradient
+        v[i] = !rc.valid ? 0.f : (c < e.n_valid ? x : (c == e.n_valid ? 1.f : 0.f));
       }
     }
     uint4* o = reinterpret_cast<uint4*>(e.out_c8 + rc.model * e.out_c8_ms) +
                ((long long)(col0 >> 3) * e.out_c8_rcap + e.out_c8_row0 + rc.row);
     o[0] = pack_bf16x8(v);
     o[e.out_c8_rcap] = pack_bf16x8(v + 8);
-  } else if (EPI == EPI_GRAD) {
-    // rc.row is a shadow row; decode (tensor, row) through the interleave map.
-    int blk = rc.row / e.ilv_stride;
-    int rem = rc.row - blk * e.ilv_stride;
-    int which = rem / e.ilv_block;
-    int n = blk * e.ilv_block + (rem - which * e.ilv_block);
-    if (which >= e.g_ntens || n >= e.g_rows[which]) return;
-    float* g = e.grad + rc.model * e.grad_ms + e.g_off[which] + (long long)n * e.g_ld;
+  } else if (EPI == EPI_GRAD || EPI == EPI_GRAD_ADAM) {
+    const int k = rc.row;  // input feature (or ones / class column)
+    if (k >= e.g_kaug) return;
+    // flat parameter index of (column i): weight W[n][k], bias b[n] or class column W[n][kin + j]
+    int idx[16];
+    bool ok[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-      int k = col0 + i;
-      if (k < e.g_kvalid) {
-        if (atomic)
-          atomicAdd(g + k, acc[i]);
-        else
-          g[k] = acc[i];
+      int which, n;
+      ilv_decode(e, col0 + i, which, n);
+      ok[i] = which < e.g_ntens && n < e.g_rows[which];
+      const int w = ok[i] ? which : 0;
+      if (k < e.g_kin)
+        idx[i] = e.g_off[w] + n * e.g_ld + k;
+      else if (k == e.g_kin)
+        idx[i] = e.g_boff[w] + n;
+      else
+        idx[i] = e.g_off[w] + n * e.g_ld + (k - 1);
+    }
+    if (EPI == EPI_GRAD) {
+      float* g = e.grad + rc.model * e.grad_ms;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        if (ok[i]) {
+          if (atomic)
+            atomicAdd(g + idx[i], acc[i]);
+          else
+            g[idx[i]] = acc[i];
+        }
+      }
+    } else {
+      // torch.optim.Adam, same expression order as adam_kernel
+      float* P = e.adam_p + rc.model * e.grad_ms;
+      float* M1 = e.adam_m + rc.model * e.grad_ms;
+      float* V2 = e.adam_v + rc.model * e.grad_ms;
+      float pv[16], mv[16], vv[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        pv[i] = ok[i] ? P[idx[i]] : 0.f;
+        mv[i] = ok[i] ? M1[idx[i]] : 0.f;
+        vv[i] = ok[i] ? V2[idx[i]] : 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float gr = acc[i] + e.wd * pv[i];
+        const float m1 = e.beta1 * mv[i] + (1.f - e.beta1) * gr;
+        const float v1 = e.beta2 * vv[i] + (1.f - e.beta2) * gr * gr;
+        pv[i] = pv[i] - e.lr_bc1 * (m1 / (sqrtf(v1) * e.inv_sqrt_bc2 + e.adam_eps));
+        mv[i] = m1;
+        vv[i] = v1;
+      }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        if (ok[i]) {
+          P[idx[i]] = pv[i];
+          M1[idx[i]] = mv[i];
+          V2[idx[i]] = vv[i];
+        }
+      }
+      // kernel-facing copies
+      if (k < e.g_kin) {
+        bf16* sh = e.sh + rc.model * e.sh_ms;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (ok[i]) sh[c8_index(col0 + i, k, e.sh_rcap)] = __float2bfloat16_rn(pv[i]);
+      } else if (k == e.g_kin) {
+        float* d = e.drv + rc.model * e.drv_ms + e.drv_bias_off;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          if (ok[i]) {
+            int which, n;
+            ilv_decode(e, col0 + i, which, n);
+            d[col0 + i] = pv[i] + e.bias_const[which];
+          }
+        }
+      } else {
+        float* d = e.drv + rc.model * e.drv_ms + e.drv_clsb_off + (long long)(k - e.g_kin - 1) * e.drv_clsb_ld;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (ok[i]) d[col0 + i] = pv[i];
       }
     }
   }
@@ -252,6 +380,14 @@ template <int EPI>
 __device__ __forceinline__ void epi_dec_chunk(const EpiParams& e, RowCtx& rc, int f0, int ccol_mu, int ccol_sg,
                                               float (&acc_mu)[16], float (&acc_sg)[16]) {
   const float* b = e.bias + rc.model * e.bias_ms;
+  float bmu[16], bsg[16];
+#pragma unroll
+  for (int i = 0; i < 16; i += 4) {
+    const float4 t = *reinterpret_cast<const float4*>(b + ccol_mu + i);
+    const float4 u = *reinterpret_cast<const float4*>(b + ccol_sg + i);
+    bmu[i] = t.x, bmu[i + 1] = t.y, bmu[i + 2] = t.z, bmu[i + 3] = t.w;
+    bsg[i] = u.x, bsg[i + 1] = u.y, bsg[i + 2] = u.z, bsg[i + 3] = u.w;
+  }
   if (EPI == EPI_DECOUT) {
     if (!rc.valid) return;
     float* om = e.out_f32 + rc.model * e.out_f32_ms + (long long)(e.out_row0 + rc.row) * e.out_ld;
@@ -260,13 +396,23 @@ __device__ __forceinline__ void epi_dec_chunk(const EpiParams& e, RowCtx& rc, in
     for (int i = 0; i < 16; ++i) {
       int f = f0 + i;
       if (f < e.X) {
-        om[f] = acc_mu[i] + b[ccol_mu + i];
-        os[f] = softplus20(acc_sg[i] + b[ccol_sg + i]) + 1e-3f;
+        om[f] = acc_mu[i] + bmu[i];
+        os[f] = softplus20(acc_sg[i] + bsg[i]) + 1e-3f;
       }
     }
     return;
   }
   // EPI_DECLOSS
+  float tg[16];
+  {
+    const float4* t4 = e.tgt4 + rc.model * e.tgt_ms + (long long)(f0 >> 2) * e.tgt_rcap + (rc.trow < 0 ? 0 : rc.trow);
+#pragma unroll
+    for (int i = 0; i < 16; i += 4) {
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (rc.trow >= 0 && f0 + i < e.Xc) t = t4[(long long)(i >> 2) * e.tgt_rcap];
+      tg[i] = t.x, tg[i + 1] = t.y, tg[i + 2] = t.z, tg[i + 3] = t.w;
+    }
+  }
   float dmu[16], dsg[16];
   float ls = 0.f;
   const float LOG2PI = 1.8378770664093453f;
@@ -274,20 +420,22 @@ __device__ __forceinline__ void epi_dec_chunk(const EpiParams& e, RowCtx& rc, in
   for (int i = 0; i < 16; ++i) {
     int f = f0 + i;
     bool ok = rc.valid && f < e.X;
-    float mu = acc_mu[i] + b[ccol_mu + i];
-    float sp = acc_sg[i] + b[ccol_sg + i];
-    float sg = softplus20(sp) + 1e-3f;
-    float t = ok ? rc.trow[f] : 0.f;
-    float d = t - mu;
-    float inv = 1.f / sg;
+    float mu = acc_mu[i] + bmu[i];
+    float sp = acc_sg[i] + bsg[i];
+    // softplus and its derivative from one exponential: e = exp(sp); softplus = log1p(e); sigmoid = e / (1 + e)
+    float ex = __expf(fminf(sp, 20.f));
+    float sg = (sp > 20.f ? sp : (ex < 1e-3f ? ex * (1.f - 0.5f * ex) : __logf(1.f + ex))) + 1e-3f;
+    float sig = sp > 20.f ? 1.f : __fdividef(ex, 1.f + ex);
+    float d = tg[i] - mu;
+    float inv = __fdividef(1.f, sg);
     float inv2 = inv * inv;
-    float lp = -0.5f * (LOG2PI + logf(sg * sg) + d * d * inv2);
+    float lp = -0.5f * (LOG2PI + 2.f * __logf(sg) + d * d * inv2);
     ls += ok ? lp : 0.f;
     // d CMPL / d mu = -coef * (t - mu) / sg^2 ;  d CMPL / d sg = -coef * (-1/sg + (t-mu)^2 / sg^3)
     float gmu = -rc.coef * d * inv2;
     float gsg = -rc.coef * (d * d * inv2 * inv - inv);
     dmu[i] = ok ? gmu : 0.f;
-    dsg[i] = ok ? gsg * sigmoid_sp(sp) : 0.f;
+    dsg[i] = ok ? gsg * sig : 0.f;
   }
   rc.lsum += ls;
   if (e.write_dy) {
@@ -304,7 +452,7 @@ template <int EPI>
 __device__ __forceinline__ void epi_end(const EpiParams& e, RowCtx& rc, int tile_n) {
   if (EPI == EPI_DECLOSS) {
     // every row of the tile writes (0 for padding rows) so the reducer can read the padded range
-    e.part[rc.model * e.part_ms + (long long)tile_n * e.part_rcap + rc.row] = rc.valid ? rc.lsum : 0.f;
+    e.part[rc.model * e.part_ms + (long long)(tile_n * EPI_GROUPS + rc.cg) * e.part_rcap + rc.row] = rc.valid ? rc.lsum : 0.f;
   }
 }
 
@@ -349,11 +497,10 @@ __device__ __forceinline__ void run_epilogue_row(const GemmProblem& p, const Epi
   epi_begin<EPI>(e, rc);
   if (EPI == EPI_DECLOSS || EPI == EPI_DECOUT) {
     const int hb = p.BN >> 1;
-    for (int c = 0; c < hb; c += 16) {
+    for (int c = rc.cg * 16; c < hb; c += 16 * EPI_GROUPS) {
       float am[16], as[16];
       if (have_acc) {
-        tmem_ld16(taddr_row + c, am);
-        tmem_ld16(taddr_row + hb + c, as);
+        tmem_ld16x2(taddr_row + c, taddr_row + hb + c, am, as);
       } else {
 #pragma unroll
         for (int i = 0; i < 16; ++i) am[i] = as[i] = 0.f;
@@ -361,7 +508,7 @@ __device__ __forceinline__ void run_epilogue_row(const GemmProblem& p, const Epi
       epi_dec_chunk<EPI>(e, rc, t.tile_n * hb + c, t.n0 + c, t.n0 + hb + c, am, as);
     }
   } else {
-    for (int c = 0; c < p.BN; c += 16) {
+    for (int c = rc.cg * 16; c < p.BN; c += 16 * EPI_GROUPS) {
       float acc[16];
       if (have_acc) {
         tmem_ld16(taddr_row + c, acc);
@@ -377,10 +524,10 @@ __device__ __forceinline__ void run_epilogue_row(const GemmProblem& p, const Epi
 
 // ---------------------------------------------------------------------------------------------
 // Tensor-core kernel: warp 0 = bulk-copy producer, warp 1 lane 0 = UMMA issuer + TMEM owner,
-// all four warps = epilogue (warp w reads TMEM lanes [32w, 32w+32)).
+// all eight warps = epilogue (warp w reads TMEM lanes [32(w%4), 32(w%4)+32), columns of group w/4).
 // ---------------------------------------------------------------------------------------------
 template <int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const GemmProblem p, const EpiParams e) {
+__global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const GemmProblem p, const EpiParams e) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[GEMM_MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[GEMM_MAX_STAGES];
@@ -537,9 +684,10 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const GemmProblem
   }
   RowCtx rc;
   rc.model = t.model;
-  rc.row = t.m0 + warp * 32 + lane;
+  rc.row = t.m0 + (warp & 3) * 32 + lane;
+  rc.cg = warp >> 2;
   rc.valid = rc.row < t.Mrows;
-  const uint32_t taddr_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const uint32_t taddr_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
   run_epilogue_row<EPI>(p, e, t, rc, taddr_row, nkb > 0, p.ksplit > 1);
 
   tc_fence_before();
@@ -567,7 +715,8 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_simt_kernel(const GemmProbl
   const bf16* Bb = p.B.base + t.model * p.B.model_stride;
   RowCtx rc;
   rc.model = t.model;
-  rc.row = t.m0 + threadIdx.x;
+  rc.row = t.m0 + (threadIdx.x & 127);
+  rc.cg = threadIdx.x >> 7;
   rc.valid = rc.row < t.Mrows;
   const int k_lo = t.kb_begin * GEMM_BK;
   const int k_hi = min(t.Kc, t.kb_end * GEMM_BK);
@@ -589,14 +738,14 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_simt_kernel(const GemmProbl
   };
   if (EPI == EPI_DECLOSS || EPI == EPI_DECOUT) {
     const int hb = p.BN >> 1;
-    for (int c = 0; c < hb; c += 16) {
+    for (int c = rc.cg * 16; c < hb; c += 16 * EPI_GROUPS) {
       float am[16], as[16];
       dot16(t.n0 + c, am);
       dot16(t.n0 + hb + c, as);
       epi_dec_chunk<EPI>(e, rc, t.tile_n * hb + c, t.n0 + c, t.n0 + hb + c, am, as);
     }
   } else {
-    for (int c = 0; c < p.BN; c += 16) {
+    for (int c = rc.cg * 16; c < p.BN; c += 16 * EPI_GROUPS) {
       float acc[16];
       dot16(t.n0 + c, acc);
       epi_chunk<EPI>(e, rc, t.n0 + c, acc, p.ksplit > 1);
@@ -646,6 +795,7 @@ inline cudaError_t gemm_launch(int epi, const GemmProblem& p, const EpiParams& e
     case EPI_LIN_C8: return gemm_launch_t<EPI_LIN_C8>(p, e, n_models, impl, st);
     case EPI_DACT_C8: return gemm_launch_t<EPI_DACT_C8>(p, e, n_models, impl, st);
     case EPI_GRAD: return gemm_launch_t<EPI_GRAD>(p, e, n_models, impl, st);
+    case EPI_GRAD_ADAM: return gemm_launch_t<EPI_GRAD_ADAM>(p, e, n_models, impl, st);
     case EPI_DECLOSS: return gemm_launch_t<EPI_DECLOSS>(p, e, n_models, impl, st);
     case EPI_DECOUT: return gemm_launch_t<EPI_DECOUT>(p, e, n_models, impl, st);
   }

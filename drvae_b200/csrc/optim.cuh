@@ -45,7 +45,7 @@ struct AdamArgs {
   const Seg* segs;
   int nseg;
   int P;  // parameters per model
-  float lr, beta1, beta2, eps, wd, bc1, bc2;
+  float lr_bc1, beta1, beta2, eps, wd, inv_sqrt_bc2;  // lr / (1 - beta1^t), 1 / sqrt(1 - beta2^t)
   int update;  // 0: only refresh the derived copies from the current parameters
 };
 
@@ -59,8 +59,8 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamArgs a) {
   bf16* sh = a.shadow.at(mdl);
   float* dv = a.derived.at(mdl);
   const int base = blockIdx.x * 1024 + threadIdx.x;
-  const float step_size = a.lr / a.bc1;
-  const float inv_sqrt_bc2 = rsqrtf(a.bc2);
+  const float step_size = a.lr_bc1;
+  const float inv_sqrt_bc2 = a.inv_sqrt_bc2;
   int si = -1;
 #pragma unroll
   for (int u = 0; u < 4; ++u) {

@@ -120,7 +120,8 @@ Shadow make_shadow(drvae_plan* pl, int ntens, const int* w_tid, const int* b_tid
   Shadow sh{};
   sh.ntens = ntens;
   sh.kin = kin;
-  sh.kc = round_up(kin, 16);
+  sh.kaug = kin + 1 + class_cols;
+  sh.kc = round_up(sh.kaug, 16);
   sh.BN = BN;
   sh.tiles_n = tiles_n;
   sh.rcap = BN * tiles_n;
@@ -146,6 +147,7 @@ Shadow make_shadow(drvae_plan* pl, int ntens, const int* w_tid, const int* b_tid
     sh.w_off[w] = wt.off;
     sh.b_off[w] = bt.off;
     sh.rows_each[w] = rows_each;
+    sh.bias_const[w] = bias_const ? bias_const[w] : 0.f;
     Seg s{};
     s.off = wt.off;
     s.rows = wt.rows;
@@ -192,7 +194,7 @@ void build_gauss_block(drvae_plan* pl, MlpBlock& blk, const std::string& prefix,
     const int cc = (i == 0) ? class_cols : 0;
     int w = add_tensor(pl, std::string(nm) + ".weight", widths[i], prev + cc);
     int b = add_tensor(pl, std::string(nm) + ".bias", widths[i], 0);
-    Tiling t = tile_cap(widths[i]);
+    Tiling t = tile_cap(widths[i] + 1);  // + the ones column the next layer's dW reads
     blk.hidden.push_back(make_shadow(pl, 1, &w, &b, widths[i], prev, cc, 1 << 30, 1 << 30, t.BN, t.tiles, nullptr));
     blk.widths.push_back(widths[i]);
     prev = widths[i];
@@ -322,8 +324,9 @@ extern "C" int drvae_plan_create(const drvae_arch_t* a, int n_models, drvae_plan
   const int Rdcap = round_up((pl->has_pair ? 3 : 1) * L * Ncap, 128) + 128;  // +1 tile: inference reads H at row offset N
   const int Flcap = pl->has_fprop ? Y * Ncap : 0;
   const int Fcap = round_up(std::max(1, L * Flcap), 128);
-  const int Xc = round_up(X, 16);
-  const int Zc = tile_cap(Z).cap, Z3c = tile_cap(Z3).cap;
+  // feature capacities of the GEMM input buffers: features + ones column (+ one-hot class columns)
+  const int Xc = round_up(X + 1, 16);
+  const int Zc = round_up(Z + 1 + (pl->has_fprop ? Y : 0), 16), Z3c = round_up(Z3 + 1 + Y, 16);
 
   ArenaBuilder ab;
   ab.E = E;
@@ -348,7 +351,7 @@ extern "C" int drvae_plan_create(const drvae_arch_t* a, int n_models, drvae_plan
   BufRec r_pair_of = I32("pair_of", Ncap), r_row_of_pair = I32("row_of_pair", Ncap), r_ebase = I32("ebase", Ncap);
   BufRec r_lab = I32("lab", Ncap), r_ycls = I32("ycls", Ncap), r_e_row = I32("e_row", std::max(1, Flcap));
   BufRec r_e_jj = I32("e_jj", std::max(1, Flcap)), r_e_cls = I32("e_cls_full", Fcap);
-  BufRec r_tgt = F32("tgt", (size_t)R0cap * X);
+  BufRec r_tgt = F32("tgt4", (size_t)R0cap * Xc);
   BufRec r_Ain = C8("Ain", R0cap, Xc);
   BufRec r_Q = F32("Q", (size_t)R0cap * 2 * Z), r_Z1f = F32("Z1f", (size_t)LNcap * Z);
   BufRec r_Zdec = C8("Zdec", Rdcap, Zc), r_Z1e = C8("Z1e", Fcap, Zc);
@@ -357,7 +360,7 @@ extern "C" int drvae_plan_create(const drvae_arch_t* a, int n_models, drvae_plan
   BufRec r_Z3b = C8("Z3b", Fcap, Z3c), r_PZ1 = F32("PZ1", (size_t)Fcap * 2 * Z);
   BufRec r_klq = F32("klq_row", R0cap), r_klz2 = F32("klz2_row", LNcap), r_yl = F32("yl_row", LNcap);
   BufRec r_ycat = F32("ycat_row", LNcap), r_kfp = F32("kfp_row", Fcap), r_kfpw = F32("kfpw_row", Fcap);
-  const int dec_tiles = pl->dec.head.tiles_n;
+  const int dec_tiles = pl->dec.head.tiles_n * EPI_GROUPS;
   BufRec r_part = F32("dec_part", (size_t)dec_tiles * Rdcap);
   BufRec r_dY5 = C8("dY5", Rdcap, pl->dec.head.rcap);
   BufRec r_dY9 = C8("dY9", Fcap, pl->has_fprop ? pl->dz1b.head.rcap : 16);
@@ -438,7 +441,7 @@ extern "C" int drvae_plan_create(const drvae_arch_t* a, int n_models, drvae_plan
   v.e_row = mbuf_of<int>(pl, r_e_row);
   v.e_jj = mbuf_of<int>(pl, r_e_jj);
   v.e_cls_full = mbuf_of<int>(pl, r_e_cls);
-  v.tgt = mbuf_of<float>(pl, r_tgt);
+  v.tgt4 = mbuf_of<float4>(pl, r_tgt);
   v.Ain = c8_of(pl, r_Ain);
   v.Q = mbuf_of<float>(pl, r_Q);
   v.Z1f = mbuf_of<float>(pl, r_Z1f);
@@ -569,6 +572,7 @@ struct Exec {
   cudaError_t err = cudaSuccess;
   const char* phase = "";
   std::string sub = "head";  // layer within the current block: h0, h1, ..., head
+  bool fused = false;        // Adam inside the gradient epilogues (drvae_train_step)
   bool ok() const { return err == cudaSuccess; }
   // event bracket around one launch when profiling is on
   void pre(const std::string& op) { prof_pre(pl, st, std::string(phase) + ":" + op); }
@@ -635,20 +639,21 @@ struct Exec {
     p.tiles_m = cdiv(row_bound, GEMM_BM);
     launch(epi, p, e, ("gemm_dx." + sub).c_str());
   }
-  // grad W[nout, kin] = dY[rows, nout]^T . Xin[rows, kin]
+  // grad W^T[kaug, nout] = Xin[rows, kaug]^T . dY[rows, nout]: weight, bias (ones column) and class-column
+  // gradients of one layer; with `fused` the epilogue applies Adam instead of storing the gradient.
   void gemm_dw(const C8Buf& dY, const C8Buf& Xin, int x_row0, const Shadow& W, int dyn_which, int row_bound) {
     GemmProblem p{};
-    p.A = op_c8(dY, 0);
-    p.B = op_c8(Xin, x_row0);
+    p.A = op_c8(Xin, x_row0);
+    p.B = op_c8(dY, 0);
     p.mode = GEMM_DW;
-    p.M = W.rcap;
-    p.N = W.kc;
+    p.M = W.kaug;
+    p.N = W.rcap;
     p.K = row_bound;
     p.dyn = cnt(dyn_which);
     p.dyn_stride = (int)v.counts.ms;
-    p.BN = W.BNx;
-    p.tiles_n = W.tiles_nx;
-    p.tiles_m = cdiv(W.rcap, GEMM_BM);
+    p.BN = W.BN;
+    p.tiles_n = W.tiles_n;
+    p.tiles_m = cdiv(W.kaug, GEMM_BM);
     p.ksplit = 1;
     EpiParams e = epi_base();
     e.grad = v.grads.p;
@@ -656,38 +661,35 @@ struct Exec {
     e.g_ntens = W.ntens;
     for (int w = 0; w < W.ntens; ++w) {
       e.g_off[w] = W.w_off[w];
+      e.g_boff[w] = W.b_off[w];
       e.g_rows[w] = W.rows_each[w];
+      e.bias_const[w] = W.bias_const[w];
     }
     e.g_ld = W.ld;
-    e.g_kvalid = W.kin;
+    e.g_kin = W.kin;
+    e.g_kaug = W.kaug;
     e.ilv_block = W.ilv_block;
     e.ilv_stride = W.ilv_stride;
-    launch(EPI_GRAD, p, e, ("gemm_dw." + sub).c_str());
-  }
-  void colsum(const C8Buf& dY, const Shadow& W, int dyn_which, bool class_cols) {
-    if (!ok()) return;
-    ColsumArgs a{};
-    a.src = dY;
-    a.dyn = cnt(dyn_which);
-    a.dyn_stride = (int)v.counts.ms;
-    a.grads = v.grads;
-    a.ntens = W.ntens;
-    for (int w = 0; w < W.ntens; ++w) {
-      a.b_off[w] = W.b_off[w];
-      a.rows_each[w] = W.rows_each[w];
+    if (fused) {
+      e.adam_p = v.params.p;
+      e.adam_m = v.adam_m.p;
+      e.adam_v = v.adam_v.p;
+      e.sh = pl->shadow.p + W.off;
+      e.sh_ms = pl->shadow.ms;
+      e.sh_rcap = W.rcap;
+      e.drv = pl->derived.p;
+      e.drv_ms = pl->derived.ms;
+      e.drv_bias_off = W.bias_off;
+      e.drv_clsb_off = W.clsb_off;
+      e.drv_clsb_ld = W.rcap;
+      e.lr_bc1 = v.s.lr_bc1;
+      e.beta1 = v.s.beta1;
+      e.beta2 = v.s.beta2;
+      e.adam_eps = v.s.eps;
+      e.wd = v.s.weight_decay;
+      e.inv_sqrt_bc2 = v.s.inv_sqrt_bc2;
     }
-    a.ilv_block = W.ilv_block;
-    a.ilv_stride = W.ilv_stride;
-    a.row_cls = class_cols ? v.e_cls_full.p : nullptr;
-    a.row_cls_ms = v.e_cls_full.ms;
-    a.Y = v.Y;
-    a.w_off = W.w_off[0];
-    a.ld = W.ld;
-    a.kmain = W.kin;
-    dim3 grid(cdiv(dY.fcap >> 3, 4), pl->E);
-    pre("colsum." + sub);
-    colsum_kernel<<<grid, 128, 0, st>>>(a);
-    chk();
+    launch(fused ? EPI_GRAD_ADAM : EPI_GRAD, p, e, ((fused ? "gemm_dw_adam." : "gemm_dw.") + sub).c_str());
   }
 
   EpiParams epi_elu(const Shadow& W, const C8Buf& out, int width, bool class_aug) const {
@@ -741,28 +743,43 @@ struct Exec {
     }
     sub = "head";
   }
-  // backward of a block given the head gradient rows dYh; optionally the input gradient as fp32
+  // backward of a block given the head gradient rows dYh; optionally the input gradient as fp32.
+  // Per layer the input gradient (which reads the layer's weight shadow) is launched BEFORE the
+  // weight gradient, because the fused-Adam epilogue of the latter overwrites that shadow.
   void block_bwd(MlpBlock& b, const C8Buf& dYh, const C8Buf& in, int in_row0, int in_feat, float* dx_out, long long dx_ms,
                  int dyn_which, int row_bound) {
     const int n = (int)b.hidden.size();
     sub = "head";
-    gemm_dw(dYh, b.H[n - 1], 0, b.head, dyn_which, row_bound);
-    colsum(dYh, b.head, dyn_which, false);
     gemm_dx(dYh, b.head, EPI_DACT_C8, epi_dact(b.H[n - 1], b.dPre[n - 1], b.widths[n - 1]), dyn_which, row_bound);
+    gemm_dw(dYh, b.H[n - 1], 0, b.head, dyn_which, row_bound);
     for (int i = n - 1; i >= 0; --i) {
       const C8Buf& src = (i == 0) ? in : b.H[i - 1];
       sub = "h" + std::to_string(i);
-      gemm_dw(b.dPre[i], src, i == 0 ? in_row0 : 0, b.hidden[i], dyn_which, row_bound);
-      colsum(b.dPre[i], b.hidden[i], dyn_which, b.class_aug && i == 0);
       if (i > 0) {
         gemm_dx(b.dPre[i], b.hidden[i], EPI_DACT_C8, epi_dact(b.H[i - 1], b.dPre[i - 1], b.widths[i - 1]), dyn_which, row_bound);
       } else if (dx_out) {
         gemm_dx(b.dPre[0], b.hidden[0], EPI_STORE_F32, epi_f32(dx_out, dx_ms, in_feat, in_feat, nullptr), dyn_which, row_bound);
       }
+      gemm_dw(b.dPre[i], src, i == 0 ? in_row0 : 0, b.hidden[i], dyn_which, row_bound);
     }
     sub = "head";
   }
 };
+
+// Step-dependent Adam scalars, computed once on the host so that the fused epilogue and the
+// stand-alone kernel apply bit-identical updates.
+struct AdamScalars {
+  float lr_bc1, inv_sqrt_bc2;
+};
+AdamScalars adam_scalars(const drvae_hparams_t* hp) {
+  const double t = (double)hp->step + 1.0;
+  const float bc1 = (float)(1.0 - pow((double)hp->beta1, t));
+  const float bc2 = (float)(1.0 - pow((double)hp->beta2, t));
+  AdamScalars a;
+  a.lr_bc1 = hp->lr / bc1;
+  a.inv_sqrt_bc2 = 1.0f / sqrtf(bc2);
+  return a;
+}
 
 int fill_view(drvae_plan* pl, Exec& ex, const drvae_batch_t* b, const drvae_noise_t* nz, const drvae_hparams_t* hp,
               bool need_grad) {
@@ -771,7 +788,7 @@ int fill_view(drvae_plan* pl, Exec& ex, const drvae_batch_t* b, const drvae_nois
   if (b->N < 1 || b->N > pl->Ncap) return set_error("drvae: batch.N exceeds the plan's max_batch");
   if (pl->has_pair && (!b->x2 || !b->has_x2)) return set_error("drvae: this model needs x2 and has_x2");
   if (pl->has_clf && (!b->y || !b->has_y)) return set_error("drvae: this model needs y and has_y");
-  if (need_grad && !pl->grads) return set_error("drvae: no gradient buffer bound");
+  if (need_grad && !ex.fused && !pl->grads) return set_error("drvae: no gradient buffer bound");
   DevView& v = ex.v;
   v = pl->view;
   const int N = b->N;
@@ -809,6 +826,14 @@ int fill_view(drvae_plan* pl, Exec& ex, const drvae_batch_t* b, const drvae_nois
   s.gNp = hp->global_Np;
   s.gNlab = hp->global_Nlab;
   for (int j = 0; j < 8; ++j) s.log_prior[j] = hp->log_prior_y[j];
+  AdamScalars as = adam_scalars(hp);
+  s.lr_bc1 = as.lr_bc1;
+  s.inv_sqrt_bc2 = as.inv_sqrt_bc2;
+  s.beta1 = hp->beta1;
+  s.beta2 = hp->beta2;
+  s.eps = hp->adam_eps;
+  s.weight_decay = hp->weight_decay;
+  s.fused_adam = 0;
   return 0;
 }
 
@@ -827,14 +852,13 @@ int run_adam(drvae_plan* pl, const drvae_hparams_t* hp, int update, cudaStream_t
   a.P = pl->P;
   a.update = update;
   if (update) {
-    const double t = (double)hp->step + 1.0;
-    a.lr = hp->lr;
+    AdamScalars as = adam_scalars(hp);
+    a.lr_bc1 = as.lr_bc1;
+    a.inv_sqrt_bc2 = as.inv_sqrt_bc2;
     a.beta1 = hp->beta1;
     a.beta2 = hp->beta2;
     a.eps = hp->adam_eps;
     a.wd = hp->weight_decay;
-    a.bc1 = (float)(1.0 - pow((double)hp->beta1, t));
-    a.bc2 = (float)(1.0 - pow((double)hp->beta2, t));
   }
   dim3 grid(cdiv(pl->P, 1024), pl->E);
   prof_pre(pl, st, update ? "opt:adam" : "opt:shadow_sync");
@@ -849,13 +873,16 @@ int run_adam(drvae_plan* pl, const drvae_hparams_t* hp, int update, cudaStream_t
 
 // forward (+ optional backward) of one minibatch per model
 int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, const drvae_hparams_t* hp, float* losses_out,
-             cudaStream_t st, bool backward) {
+             cudaStream_t st, bool backward, bool fused_adam) {
   if (!hp) return set_error("drvae: hparams is null");
+  if (fused_adam && (!pl->adam_m || !pl->adam_v)) return set_error("drvae: Adam needs bound moment buffers");
   Exec ex;
   ex.pl = pl;
   ex.st = st;
+  ex.fused = fused_adam;
   int rc = fill_view(pl, ex, b, nz, hp, backward);
   if (rc) return rc;
+  ex.v.s.fused_adam = fused_adam ? 1 : 0;
   if (!pl->shadows_valid) {
     rc = run_adam(pl, hp, 0, st);
     if (rc) return rc;
@@ -876,7 +903,7 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
   rowmap_kernel<<<E, 256, 0, st>>>(v);
   ex.chk();
   ex.pre("prep");
-  prep_kernel<<<dim3(round_up(R0b, 128), E), 128, 0, st>>>(v);
+  prep_kernel<<<dim3(round_up(R0b, 128) / PREP_ROWS, E), PREP_THREADS, 0, st>>>(v);
   ex.chk();
 
   // ---- encoder q(z1|x1), shared with q(z2|x2) (DrVAE.py:408,418) ----
@@ -905,9 +932,11 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
     e.out_c8_rcap = pl->dY5.rcap;
     e.bias = pl->derived.p + pl->dec.head.bias_off;
     e.bias_ms = pl->derived.ms;
-    e.tgt = v.tgt.p;
-    e.tgt_ms = v.tgt.ms;
+    e.tgt4 = v.tgt4.p;
+    e.tgt_ms = v.tgt4.ms;
+    e.tgt_rcap = pl->view.R0cap;
     e.X = pl->X;
+    e.Xc = pl->view.Xc;
     e.counts = v.counts.p;
     e.counts_stride = (int)v.counts.ms;
     e.coefs = v.coefs.p;
@@ -974,9 +1003,8 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
       ex.pre("T_back");
       T_back_kernel<<<rows_grid(N + PAD_ROWS), ROW_THREADS, 0, st>>>(v);
       ex.chk();
-      ex.gemm_dw(v.dYT, v.Zdec, 0, pl->Tsh, CNT_LN, LNb);
-      ex.colsum(v.dYT, pl->Tsh, CNT_LN, false);
       ex.gemm_dx(v.dYT, pl->Tsh, EPI_STORE_F32, ex.epi_f32(v.dZ1T.p, v.dZ1T.ms, pl->Z, pl->Z, nullptr), CNT_LN, LNb);
+      ex.gemm_dw(v.dYT, v.Zdec, 0, pl->Tsh, CNT_LN, LNb);
     }
     ex.phase = "enc.bwd";
     ex.pre("q_back");
@@ -999,21 +1027,21 @@ extern "C" int drvae_sync_shadows(drvae_plan_t* pl, void* stream) {
 extern "C" int drvae_train_step(drvae_plan_t* pl, const drvae_batch_t* b, const drvae_noise_t* nz, const drvae_hparams_t* hp,
                                 float* losses_out, void* stream) {
   if (!pl) return set_error("drvae_train_step: null plan");
-  int rc = run_step(pl, b, nz, hp, losses_out, (cudaStream_t)stream, true);
-  if (rc) return rc;
-  return run_adam(pl, hp, 1, (cudaStream_t)stream);
+  // forward + ELBO + backward with Adam fused into the gradient epilogues: no gradient buffer
+  // traffic and no separate optimizer pass (the bound gradient buffer is left untouched)
+  return run_step(pl, b, nz, hp, losses_out, (cudaStream_t)stream, true, true);
 }
 
 extern "C" int drvae_loss_forward(drvae_plan_t* pl, const drvae_batch_t* b, const drvae_noise_t* nz, const drvae_hparams_t* hp,
                                   float* losses_out, void* stream) {
   if (!pl) return set_error("drvae_loss_forward: null plan");
-  return run_step(pl, b, nz, hp, losses_out, (cudaStream_t)stream, false);
+  return run_step(pl, b, nz, hp, losses_out, (cudaStream_t)stream, false, false);
 }
 
 extern "C" int drvae_grad_step(drvae_plan_t* pl, const drvae_batch_t* b, const drvae_noise_t* nz, const drvae_hparams_t* hp,
                                float* losses_out, void* stream) {
   if (!pl) return set_error("drvae_grad_step: null plan");
-  return run_step(pl, b, nz, hp, losses_out, (cudaStream_t)stream, true);
+  return run_step(pl, b, nz, hp, losses_out, (cudaStream_t)stream, true, false);
 }
 
 extern "C" int drvae_adam_step(drvae_plan_t* pl, const drvae_hparams_t* hp, void* stream) {
@@ -1053,7 +1081,7 @@ extern "C" int drvae_infer(drvae_plan_t* pl, const float* x1, int N, const drvae
   infer_counts_kernel<<<E, 128, 0, st>>>(v, rows_dec);
   ex.chk();
   ex.pre("prep");
-  prep_kernel<<<dim3(round_up(N, 128), E), 128, 0, st>>>(v);
+  prep_kernel<<<dim3(round_up(N, 128) / PREP_ROWS, E), PREP_THREADS, 0, st>>>(v);
   ex.chk();
   ex.block_hidden_fwd(pl->enc, v.Ain, 0, CNT_R0, N);
   ex.gemm_nt(pl->enc.H.back(), 0, pl->enc.head, EPI_STORE_F32, ex.epi_f32(v.Q.p, v.Q.ms, 2 * pl->Z, 2 * pl->Z, &pl->enc.head),

@@ -64,7 +64,8 @@ struct Shadow {
   long long off;       // in the bf16 shadow arena (per model)
   int rcap;            // = tiles_n * BN  (output-feature capacity)
   int kin;             // true input features that go through the GEMM
-  int kc;              // round_up(kin, 16)
+  int kaug;            // kin + 1 (ones column -> bias gradient) + one-hot class columns
+  int kc;              // round_up(kaug, 16): K extent of the forward GEMM, M extent of the dW GEMM
   int nout_total;      // shadow rows in use
   int BN, tiles_n;     // forward N tiling
   int BNx, tiles_nx;   // tiling over input features (dX / dW output columns)
@@ -76,6 +77,7 @@ struct Shadow {
   int rows_each[2];
   int ld;         // leading dimension of the weight tensors (kin + class columns)
   int ilv_block, ilv_stride;
+  float bias_const[2];  // constant folded into the derived bias (logvar heads: -2)
 };
 
 struct MlpBlock {
@@ -95,8 +97,8 @@ struct StepScalars {
   float beta_pert, pertloss_rate, kl_qz2pz2_rate, yloss_rate;
   int training, add_noise;
   int gN, gNp, gNlab;  // global normalisers (0 = use local counts)
-  float lr, beta1, beta2, eps, weight_decay;
-  float bc1, bc2;  // 1 - beta^t
+  float lr_bc1, beta1, beta2, eps, weight_decay, inv_sqrt_bc2;  // Adam: lr / (1 - beta1^t), 1 / sqrt(1 - beta2^t)
+  int fused_adam;  // 1: the optimizer update happens inside the gradient kernels (drvae_train_step)
   float log_prior[8];  // log prior_y
 };
 
@@ -117,7 +119,7 @@ struct DevView {
   MBuf<float> coefs;  // COEF_*
   MBuf<int> pair_of, row_of_pair, ebase, lab, ycls, e_row, e_jj, e_cls_full;
   // activations
-  MBuf<float> tgt;  // [R0cap][X]
+  MBuf<float4> tgt4;  // fp32 targets, chunk4: [Xc/4][R0cap] float4
   C8Buf Ain;        // [Xc/8][R0cap][8]
   MBuf<float> Q;    // [R0cap][2Z]   (mu1 | lv1) rows < N, (mu2 | lv2) rows N + p
   MBuf<float> Z1f;  // [LNcap][Z]

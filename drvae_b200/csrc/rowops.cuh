@@ -136,45 +136,66 @@ __global__ void __launch_bounds__(256) rowmap_kernel(DevView v) {
 // prep: encoder input rows.  Row r < N is x1[r]; row N + p is x2 of the p-th pair.  With
 // --train-w-noise the noisy row is ALSO the reconstruction target (DrVAE.py:404-417 adds the
 // noise in place), so the fp32 target copy is written from the same value.
-// grid (R0cap, n_models), block 128
+// Reads are coalesced along features, writes along rows (the chunk8 bf16 GEMM operand with its
+// ones column at feature X, and the chunk4 fp32 target the decoder epilogue reads), through a
+// shared-memory transpose of 32 rows x 256 features.
+// grid (R0cap / 32, n_models), block 256
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) prep_kernel(DevView v) {
-  const int m = blockIdx.y, r = blockIdx.x;
+constexpr int PREP_ROWS = 32;
+constexpr int PREP_THREADS = 256;
+constexpr int PREP_SLAB = 256;
+
+__global__ void __launch_bounds__(PREP_THREADS) prep_kernel(DevView v) {
+  __shared__ float tile[PREP_ROWS][PREP_SLAB + 1];
+  const int m = blockIdx.y, r0 = blockIdx.x * PREP_ROWS;
   const int* cnt = v.counts.at(m);
   const int N = cnt[CNT_N], R0 = cnt[CNT_R0];
-  if (r >= pad128(R0)) return;
-  uint4* ain = reinterpret_cast<uint4*>(v.Ain.at(m));
-  const int nch = v.Xc >> 3;
-  if (r >= R0) {
-    for (int c = threadIdx.x; c < nch; c += 128) ain[(long long)c * v.Ain.rcap + r] = make_uint4(0, 0, 0, 0);
-    return;
-  }
-  const float* src;
-  const float* eps;
-  if (r < N) {
-    src = v.x1.at(m) + (long long)r * v.X;
-    eps = v.eps_x1.at(m) + (long long)r * v.X;
-  } else {
-    const int i = v.row_of_pair.at(m)[r - N];
-    src = v.x2.at(m) + (long long)i * v.X;
-    eps = v.eps_x2.at(m) + (long long)i * v.X;
-  }
+  if (r0 >= pad128(R0)) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool noisy = v.s.training && v.s.add_noise;
-  float* tg = v.tgt.at(m) + (long long)r * v.X;
-  for (int c = threadIdx.x; c < nch; c += 128) {
-    float a[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int f = c * 8 + k;
-      float x = 0.f;
-      if (f < v.X) {
-        x = src[f];
-        if (noisy) x += v.s.noise_std * eps[f];
-        tg[f] = x;
+  uint4* ain = reinterpret_cast<uint4*>(v.Ain.at(m));
+  float4* tg = v.tgt4.at(m);
+  for (int f0 = 0; f0 < v.Xc; f0 += PREP_SLAB) {
+    const int fw = min(PREP_SLAB, v.Xc - f0);  // multiple of 16
+    // phase 1: one warp per row, lanes along features
+    for (int rl = warp; rl < PREP_ROWS; rl += PREP_THREADS / 32) {
+      const int r = r0 + rl;
+      const float* src = nullptr;
+      const float* eps = nullptr;
+      if (r < N) {
+        src = v.x1.at(m) + (long long)r * v.X;
+        eps = v.eps_x1.at(m) + (long long)r * v.X;
+      } else if (r < R0) {
+        const int i = v.row_of_pair.at(m)[r - N];
+        src = v.x2.at(m) + (long long)i * v.X;
+        eps = v.eps_x2.at(m) + (long long)i * v.X;
       }
-      a[k] = x;
+      for (int j = lane; j < fw; j += 32) {
+        const int f = f0 + j;
+        float x = 0.f;
+        if (src && f < v.X) {
+          x = src[f];
+          if (noisy) x += v.s.noise_std * eps[f];
+        }
+        tile[rl][j] = x;
+      }
     }
-    ain[(long long)c * v.Ain.rcap + r] = pack_bf16x8(a);
+    __syncthreads();
+    // phase 2: lanes along rows, one 8-feature chunk per (warp, iteration)
+    const int r = r0 + lane;
+    for (int c = warp; c < (fw >> 3); c += PREP_THREADS / 32) {
+      float a[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a[k] = tile[lane][c * 8 + k];
+      const int fc = f0 + c * 8;
+      tg[(long long)(fc >> 2) * v.R0cap + r] = make_float4(a[0], a[1], a[2], a[3]);
+      tg[(long long)((fc >> 2) + 1) * v.R0cap + r] = make_float4(a[4], a[5], a[6], a[7]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (fc + k == v.X && r < R0) a[k] = 1.f;  // ones column (bias gradient of the first layer)
+      ain[(long long)(fc >> 3) * v.Ain.rcap + r] = pack_bf16x8(a);
+    }
+    __syncthreads();
   }
 }
 
@@ -269,12 +290,15 @@ __global__ void __launch_bounds__(ROW_THREADS) sample_q1_kernel(DevView v) {
   const int ecnt = v.has_fprop ? (v.lab.at(m)[i] ? 1 : v.Y) : 0;
   bf16* zdec = v.Zdec.at(m);
   bf16* z1e = v.has_fprop ? v.Z1e.at(m) : nullptr;
+  const int ycl = v.has_fprop ? v.ycls.at(m)[i] : 0;
   for (int l = 0; l < v.L; ++l) {
     const int r = l * N + i;
     const float* e1 = v.eps_z1.at(m) + ((long long)l * v.Ncap + i) * v.Z;
     const float* e2 = v.eps_z2.at(m) + ((long long)l * v.Ncap + i) * v.Z;
     for (int f = lane; f < v.Zc; f += 32) {
-      float z = 0.f, z2 = 0.f;
+      // feature Z is the ones column (bias gradients); features Z+1+j are the one-hot class
+      // columns of the [z1, onehot(y)] input of q(z_top | z1, y)
+      float z = (f == v.Z) ? 1.f : 0.f, z2 = z;
       if (f < v.Z) {
         const float mu = q[f], sd = expf(0.5f * q[v.Z + f]);
         z = mu + sd * e1[f];
@@ -283,7 +307,10 @@ __global__ void __launch_bounds__(ROW_THREADS) sample_q1_kernel(DevView v) {
       }
       st_c8(zdec, v.Zdec.rcap, r, f, z);
       if (p >= 0) st_c8(zdec, v.Zdec.rcap, LN + l * Np + p, f, z2);
-      for (int jj = 0; jj < ecnt; ++jj) st_c8(z1e, v.Z1e.rcap, l * Fl + eb + jj, f, z);
+      for (int jj = 0; jj < ecnt; ++jj) {
+        const int cls = ecnt == 1 ? ycl : jj;
+        st_c8(z1e, v.Z1e.rcap, l * Fl + eb + jj, f, (f == v.Z + 1 + cls) ? 1.f : z);
+      }
     }
     if (v.has_clf && !v.has_T) {
       __syncwarp();
@@ -330,7 +357,7 @@ __global__ void __launch_bounds__(ROW_THREADS) T_post_kernel(DevView v) {
     const float* ef = v.eps_z2f.at(m) + ((long long)l * v.Ncap + i) * v.Z;
     float kl = 0.f;
     for (int f = lane; f < v.Zc; f += 32) {
-      float z2f = 0.f;
+      float z2f = (f == v.Z) ? 1.f : 0.f;  // ones column
       if (f < v.Z) {
         const float pmu = pt[f] + z1[f];
         const float plv = pt[v.Z + f];
@@ -376,9 +403,10 @@ __global__ void __launch_bounds__(ROW_THREADS) z3_post_kernel(DevView v) {
   const float* q3 = v.Q3.at(m) + (long long)e * 2 * v.Z3;
   const float* ez = v.eps_z3.at(m) + (((long long)l * v.Ncap + i) * v.Y + jj) * v.Z3;
   bf16* z3b = v.Z3b.at(m);
+  const int cls = v.e_cls_full.at(m)[e];
   float kl = 0.f;
   for (int f = lane; f < v.Z3c; f += 32) {
-    float z = 0.f;
+    float z = (f == v.Z3 || f == v.Z3 + 1 + cls) ? 1.f : 0.f;  // ones column, one-hot class column
     if (f < v.Z3) {
       const float mu = q3[f], lv = q3[v.Z3 + f];
       z = mu + expf(0.5f * lv) * ez[f];
@@ -706,11 +734,22 @@ __global__ void __launch_bounds__(256) clf_grad_reduce_kernel(DevView v) {
     const int j = k / width, t = k - j * width;
     float s = 0.f;
     for (int sp = 0; sp < CLF_SPLITS; ++sp) s += v.clf_part.at(m)[((long long)sp * v.Y + j) * width + t];
-    float* g = v.grads.at(m);
-    if (t < v.clf_in)
-      g[v.clf_w_off + j * v.clf_in + t] = s;
-    else
-      g[v.clf_b_off + j] = s;
+    const int idx = (t < v.clf_in) ? v.clf_w_off + j * v.clf_in + t : v.clf_b_off + j;
+    if (!v.s.fused_adam) {
+      v.grads.at(m)[idx] = s;
+    } else {
+      // the classifier runs on the fp32 parameters directly: Adam here, no shadow to refresh
+      float* P = v.params.at(m);
+      float* M1 = v.adam_m.at(m);
+      float* V2 = v.adam_v.at(m);
+      const float pv = P[idx];
+      const float gr = s + v.s.weight_decay * pv;
+      const float m1 = v.s.beta1 * M1[idx] + (1.f - v.s.beta1) * gr;
+      const float v1 = v.s.beta2 * V2[idx] + (1.f - v.s.beta2) * gr * gr;
+      M1[idx] = m1;
+      V2[idx] = v1;
+      P[idx] = pv - v.s.lr_bc1 * (m1 / (sqrtf(v1) * v.s.inv_sqrt_bc2 + v.s.eps));
+    }
   }
 }
 

@@ -357,3 +357,37 @@ def test_model_class_surface():
                 assert torch.equal(v, before[k])
             ev2 = model.run_on_batch(train_mode=False, **kw)
             assert np.isfinite(float(ev2["CMPL"]))
+
+
+@pytest.mark.parametrize("case", ("tiny", "deep", "readme"))
+@pytest.mark.parametrize("kind", KINDS)
+def test_fused_adam_equals_grad_then_adam(kind, case):
+    """drvae_train_step applies Adam inside the weight-gradient epilogues (the gradient never reaches
+    HBM); drvae_grad_step + drvae_adam_step materialise it and run the stand-alone optimizer kernel.
+    Same gradients, same formula: parameters, moments and the refreshed bf16 shadows must agree."""
+    res = {}
+    for mode in ("fused", "split"):
+        arch, N, sd, batch, om, plan = setup(kind, case)
+        out = []
+        for it in range(2):
+            tape = orc.Tape(seed=SEED_TAPE + it)
+            om.iters = it
+            om.loss(batch, tape, train=True)
+            eps = eps_block_from_tape(plan, tape.log, batch["has_x2"], batch["has_y"], noisy=True)
+            hp = plan.hparams(step=it, beta_pert=anneal_coef(it, 1, 0))
+            if mode == "fused":
+                lo = plan.train_step(batch_fields(kind, batch), hp, eps=eps).cpu().clone()
+            else:
+                lo = plan.grad_step(batch_fields(kind, batch), hp, eps=eps).cpu().clone()
+                plan.adam_step(hp)
+            out.append(lo)
+        sh, _, _ = plan.debug_buffer("shadow", torch.bfloat16)
+        dv, _, _ = plan.debug_buffer("derived")
+        res[mode] = (out, plan.params.cpu().clone(), plan.adam_m.cpu().clone(), plan.adam_v.cpu().clone(),
+                     sh.float().cpu().clone(), dv.cpu().clone())
+    f, s = res["fused"], res["split"]
+    assert torch.equal(f[0][0], s[0][0]), "first-step losses differ"
+    for i, name in ((1, "params"), (2, "adam_m"), (3, "adam_v")):
+        assert torch.allclose(f[i], s[i], rtol=1e-6, atol=1e-9), name
+    assert rel_l2(f[4], s[4]) < 1e-4 and rel_l2(f[5], s[5]) < 1e-6, "shadow / derived copies differ"
+    assert torch.allclose(f[0][1], s[0][1], rtol=1e-5, atol=1e-6), "second-step losses differ"

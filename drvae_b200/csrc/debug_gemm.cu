@@ -1,6 +1,8 @@
 // Bring-up / validation entry point: run ONE grouped GEMM (tensor-core or SIMT mainloop) on
 // caller-provided chunk8 operands and return the fp32 accumulator tile matrix.  Used by
 // tests/test_gemm_gpu.py to pin the UMMA descriptor encodings against a torch matmul.
+#include <vector>
+
 #include "drvae_b200.h"
 #include "errors.h"
 #include "gemm.cuh"
@@ -43,15 +45,16 @@ extern "C" int drvae_debug_gemm(int impl, int mode, const void* A, int a_rcap, i
     epi = EPI_GRAD;
     e.grad = D;
     e.grad_ms = d_ms;
-    e.g_ntens = 1;
-    e.g_off[0] = 0;
-    e.g_boff[0] = 0;
-    e.g_rows[0] = N;
-    e.g_ld = M;
+    const int ncap = p.tiles_n * BN;
+    std::vector<int> tab(3 * (size_t)ncap, -1);
+    for (int s = 0; s < N; ++s) tab[s] = s * M;
+    int* d_tab = nullptr;  // test-only entry point: the table is leaked on purpose (a few KB)
+    if (cudaMalloc(&d_tab, tab.size() * sizeof(int)) != cudaSuccess) return set_error("cudaMalloc(table) failed");
+    cudaMemcpy(d_tab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice);
+    e.g_tab = d_tab;
+    e.g_tab_n = ncap;
     e.g_kin = M;
     e.g_kaug = M;
-    e.ilv_block = 1 << 30;
-    e.ilv_stride = 1 << 30;
   } else {
     e.out_f32 = D;
     e.out_f32_ms = d_ms;

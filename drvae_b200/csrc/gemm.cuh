@@ -99,18 +99,15 @@ struct EpiParams {
   int act_rcap;
   int act_row0;
   // EPI_GRAD / EPI_GRAD_ADAM: D row = input feature k (k == g_kin: ones column -> bias gradient,
-  // k > g_kin: one-hot class columns), D col = shadow row -> (tensor which, row n)
+  // k > g_kin: one-hot class columns), D col = shadow row s.  g_tab holds three int tables of
+  // g_tab_n entries each, indexed by s: flat offset of W[n(s)][0] (or -1: padding row), flat
+  // offset of b[n(s)], and the constant folded into the derived bias (float bits).
   float* grad;
   long long grad_ms;  // also the model stride of params / adam_m / adam_v
-  int g_ntens;
-  int g_off[2];   // flat offsets of the weight tensors
-  int g_boff[2];  // flat offsets of the bias tensors
-  int g_rows[2];
-  int g_ld;       // leading dimension of the weight tensors (g_kin + class columns)
+  const int* g_tab;
+  int g_tab_n;
   int g_kin;      // true input features
   int g_kaug;     // g_kin + 1 + class columns
-  int ilv_block;
-  int ilv_stride;
   // EPI_GRAD_ADAM
   float* adam_p;
   float* adam_m;
@@ -123,7 +120,6 @@ struct EpiParams {
   long long drv_bias_off;
   long long drv_clsb_off;
   int drv_clsb_ld;
-  float bias_const[2];
   float lr_bc1, beta1, beta2, adam_eps, wd, inv_sqrt_bc2;  // lr_bc1 = lr / (1 - beta1^t)
   // EPI_DECLOSS / EPI_DECOUT
   const float4* tgt4;  // fp32 targets, chunk4 layout [Xc/4][tgt_rcap] float4
@@ -205,12 +201,10 @@ __device__ __forceinline__ void epi_begin(const EpiParams& e, RowCtx& rc) {
   }
 }
 
-// shadow row -> (tensor, row) through the interleave map
-__device__ __forceinline__ void ilv_decode(const EpiParams& e, int srow, int& which, int& n) {
-  const int blk = srow / e.ilv_stride;
-  const int rem = srow - blk * e.ilv_stride;
-  which = rem / e.ilv_block;
-  n = blk * e.ilv_block + (rem - which * e.ilv_block);
+__device__ __forceinline__ float ld_global_f32(const float* p) {
+  float v;
+  asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
 }
 
 template <int EPI>
@@ -291,27 +285,21 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& e, RowCtx& rc, int co
   } else if (EPI == EPI_GRAD || EPI == EPI_GRAD_ADAM) {
     const int k = rc.row;  // input feature (or ones / class column)
     if (k >= e.g_kaug) return;
-    // flat parameter index of (column i): weight W[n][k], bias b[n] or class column W[n][kin + j]
+    // flat parameter index of column i: weight W[n][k], bias b[n] or class column W[n][kin + j]
+    // (tables are warp-uniform: broadcast loads)
+    const int4* tw = reinterpret_cast<const int4*>(e.g_tab + (k == e.g_kin ? e.g_tab_n : 0) + col0);
+    const int kofs = (k < e.g_kin) ? k : (k == e.g_kin ? 0 : k - 1);
     int idx[16];
-    bool ok[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      int which, n;
-      ilv_decode(e, col0 + i, which, n);
-      ok[i] = which < e.g_ntens && n < e.g_rows[which];
-      const int w = ok[i] ? which : 0;
-      if (k < e.g_kin)
-        idx[i] = e.g_off[w] + n * e.g_ld + k;
-      else if (k == e.g_kin)
-        idx[i] = e.g_boff[w] + n;
-      else
-        idx[i] = e.g_off[w] + n * e.g_ld + (k - 1);
+    for (int i = 0; i < 16; i += 4) {
+      const int4 t = tw[i >> 2];
+      idx[i] = t.x, idx[i + 1] = t.y, idx[i + 2] = t.z, idx[i + 3] = t.w;
     }
     if (EPI == EPI_GRAD) {
-      float* g = e.grad + rc.model * e.grad_ms;
+      float* g = e.grad + rc.model * e.grad_ms + kofs;
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        if (ok[i]) {
+        if (idx[i] >= 0) {
           if (atomic)
             atomicAdd(g + idx[i], acc[i]);
           else
@@ -319,16 +307,20 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& e, RowCtx& rc, int co
         }
       }
     } else {
-      // torch.optim.Adam, same expression order as adam_kernel
-      float* P = e.adam_p + rc.model * e.grad_ms;
-      float* M1 = e.adam_m + rc.model * e.grad_ms;
-      float* V2 = e.adam_v + rc.model * e.grad_ms;
+      // torch.optim.Adam, same expression order as adam_kernel.  All 48
+      // loads of the chunk are issued back to back (volatile asm keeps them ahead of the math).
+      float* P = e.adam_p + rc.model * e.grad_ms + kofs;
+      float* M1 = e.adam_m + rc.model * e.grad_ms + kofs;
+      float* V2 = e.adam_v + rc.model * e.grad_ms + kofs;
       float pv[16], mv[16], vv[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        pv[i] = ok[i] ? P[idx[i]] : 0.f;
-        mv[i] = ok[i] ? M1[idx[i]] : 0.f;
-        vv[i] = ok[i] ? V2[idx[i]] : 0.f;
+        pv[i] = mv[i] = vv[i] = 0.f;
+        if (idx[i] >= 0) {
+          pv[i] = ld_global_f32(P + idx[i]);
+          mv[i] = ld_global_f32(M1 + idx[i]);
+          vv[i] = ld_global_f32(V2 + idx[i]);
+        }
       }
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
@@ -341,7 +333,7 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& e, RowCtx& rc, int co
       }
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        if (ok[i]) {
+        if (idx[i] >= 0) {
           P[idx[i]] = pv[i];
           M1[idx[i]] = mv[i];
           V2[idx[i]] = vv[i];
@@ -349,25 +341,21 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& e, RowCtx& rc, int co
       }
       // kernel-facing copies
       if (k < e.g_kin) {
-        bf16* sh = e.sh + rc.model * e.sh_ms;
+        bf16* sh = e.sh + rc.model * e.sh_ms + ((long long)(k >> 3) * e.sh_rcap + col0) * 8 + (k & 7);
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-          if (ok[i]) sh[c8_index(col0 + i, k, e.sh_rcap)] = __float2bfloat16_rn(pv[i]);
+          if (idx[i] >= 0) sh[i * 8] = __float2bfloat16_rn(pv[i]);
       } else if (k == e.g_kin) {
-        float* d = e.drv + rc.model * e.drv_ms + e.drv_bias_off;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          if (ok[i]) {
-            int which, n;
-            ilv_decode(e, col0 + i, which, n);
-            d[col0 + i] = pv[i] + e.bias_const[which];
-          }
-        }
-      } else {
-        float* d = e.drv + rc.model * e.drv_ms + e.drv_clsb_off + (long long)(k - e.g_kin - 1) * e.drv_clsb_ld;
+        float* d = e.drv + rc.model * e.drv_ms + e.drv_bias_off + col0;
+        const float* bc = reinterpret_cast<const float*>(e.g_tab + 2 * e.g_tab_n + col0);
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-          if (ok[i]) d[col0 + i] = pv[i];
+          if (idx[i] >= 0) d[i] = pv[i] + bc[i];
+      } else {
+        float* d = e.drv + rc.model * e.drv_ms + e.drv_clsb_off + (long long)(k - e.g_kin - 1) * e.drv_clsb_ld + col0;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (idx[i] >= 0) d[i] = pv[i];
       }
     }
   }

@@ -184,12 +184,29 @@ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uin
   }
 }
 
-__global__ void __launch_bounds__(256) philox_normal_kernel(MBuf<float> out, long long n, unsigned long long seed,
-                                                            unsigned int step) {
-  const int m = blockIdx.y;
-  const long long i4 = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (i4 * 4 >= n) return;
-  uint32_t c[4] = {(uint32_t)i4, (uint32_t)(i4 >> 32), step, (uint32_t)m};
+// ε block generator.  Every normal is keyed by (seed, step, model, segment, MC sample, GLOBAL row,
+// position in the row) and never by its address, so a minibatch sharded over ranks
+// (row_offset = global index of the shard's first row) draws exactly the noise of the unsharded
+// run.  One thread = 4 consecutive normals of one row.  grid (blocks, n_models, 6 segments)
+struct EpsSegs {
+  long long off[6];  // segment offsets inside the per-model ε block (drvae_eps_layout_t order)
+  int outer[6];      // MC samples (1 for the input-noise segments)
+  int inner[6];      // floats per row
+};
+
+__global__ void __launch_bounds__(256) philox_normal_kernel(MBuf<float> out, EpsSegs sg, int N, int Ncap, long long row_offset,
+                                                            unsigned long long seed, unsigned int step) {
+  const int m = blockIdx.y, seg = blockIdx.z;
+  const int inner = sg.inner[seg], quads = (inner + 3) >> 2;
+  const long long total = (long long)sg.outer[seg] * N * quads;
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (inner <= 0 || t >= total) return;
+  const int q = (int)(t % quads);
+  const long long lr = t / quads;
+  const int r = (int)(lr % N), l = (int)(lr / N);
+  const unsigned long long grow = (unsigned long long)(row_offset + r);
+  uint32_t c[4] = {(uint32_t)q | ((uint32_t)(grow >> 32) << 24), (uint32_t)grow, step,
+                   (uint32_t)m | ((uint32_t)seg << 20) | ((uint32_t)l << 24)};
   philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
   const float k = 2.3283064365386963e-10f;  // 2^-32
   const float u0 = (c[0] + 1.0f) * k, u1 = c[1] * k, u2 = (c[2] + 1.0f) * k, u3 = c[3] * k;
@@ -197,11 +214,11 @@ __global__ void __launch_bounds__(256) philox_normal_kernel(MBuf<float> out, lon
   float s0, c0, s1, c1;
   sincospif(2.f * u1, &s0, &c0);
   sincospif(2.f * u3, &s1, &c1);
-  float z[4] = {r0 * c0, r0 * s0, r1 * c1, r1 * s1};
-  float* o = out.at(m);
+  const float z[4] = {r0 * c0, r0 * s0, r1 * c1, r1 * s1};
+  float* o = out.at(m) + sg.off[seg] + ((long long)l * Ncap + r) * inner + q * 4;
 #pragma unroll
   for (int j = 0; j < 4; ++j)
-    if (i4 * 4 + j < n) o[i4 * 4 + j] = z[j];
+    if (q * 4 + j < inner) o[j] = z[j];
 }
 
 }  // namespace drvae

@@ -54,6 +54,8 @@ struct drvae_plan {
   std::vector<ParamInfo> tensors;
   std::vector<Seg> segs;
   Seg* d_segs = nullptr;
+  std::vector<int> h_tabs;  // gradient-epilogue tables of every weight (see make_shadow)
+  int* d_tabs = nullptr;
   int P = 0;
   int clf_w_off = -1, clf_b_off = -1;
   // shadows
@@ -78,6 +80,13 @@ struct drvae_plan {
   int gemm_impl = GEMM_IMPL_TC;
   long long launches = 0;
   bool shadows_valid = false;
+  // side stream for the label-dependent branch (see run_step)
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_qy = nullptr, ev_side_fwd = nullptr, ev_side_bwd = nullptr;
+  bool overlap = true;
+  // gradient buckets (data-parallel overlap): contiguous parameter ranges in backward completion order
+  std::vector<std::pair<long long, long long>> buckets;  // (offset, count)
+  std::vector<cudaEvent_t> bucket_ev;
   // optional per-launch event timing (bench.py / profiles)
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;
@@ -180,6 +189,21 @@ Shadow make_shadow(drvae_plan* pl, int ntens, const int* w_tid, const int* b_tid
     if (srow > max_srow) max_srow = srow;
   }
   sh.nout_total = max_srow + 1;
+  // gradient-epilogue tables, indexed by shadow row s: flat offset of W[n(s)][0] (-1: padding),
+  // flat offset of b[n(s)], constant folded into the derived bias
+  sh.tab_off = (long long)pl->h_tabs.size();
+  pl->h_tabs.resize(pl->h_tabs.size() + 3 * (size_t)sh.rcap, -1);
+  int* tw = pl->h_tabs.data() + sh.tab_off;
+  for (int srow = 0; srow < sh.rcap; ++srow) {
+    const int blk = srow / ilv_stride, rem = srow % ilv_stride;
+    const int which = rem / ilv_block, n = blk * ilv_block + rem % ilv_block;
+    if (which < ntens && n < rows_each) {
+      tw[srow] = sh.w_off[which] + n * sh.ld;
+      tw[sh.rcap + srow] = sh.b_off[which] + n;
+      float c = sh.bias_const[which];
+      memcpy(&tw[2 * sh.rcap + srow], &c, sizeof(float));
+    }
+  }
   return sh;
 }
 
@@ -289,7 +313,10 @@ extern "C" int drvae_plan_create(const drvae_arch_t* a, int n_models, drvae_plan
   const int X = pl->X, Y = pl->Y, Z = pl->Z, Z3 = pl->Z3, L = pl->L, E = pl->E;
 
   // ---- parameters in the reference's state_dict order ----
+  int p0 = pl->P;
+  long long r_enc[2], r_T[2] = {0, 0}, r_clf[2] = {0, 0}, r_z3[2] = {0, 0}, r_dz1[2] = {0, 0}, r_dec[2];
   build_gauss_block(pl, pl->enc, "encoder_z1", X, 0, a->n_enc_z1, a->enc_z1, Z, false);
+  r_enc[0] = p0, r_enc[1] = pl->P - p0, p0 = pl->P;
   if (pl->has_T) {
     // DiagGaussianModuleLinear (blocks.py:304-361): W_mu, bias_mu are bare Parameters
     int wt[2], bt[2];
@@ -300,6 +327,7 @@ extern "C" int drvae_plan_create(const drvae_arch_t* a, int n_models, drvae_plan
     const float bc[2] = {0.f, -2.f};
     Tiling t = tile_cap(2 * Z);
     pl->Tsh = make_shadow(pl, 2, wt, bt, Z, Z, 0, Z, 2 * Z, t.BN, t.tiles, bc);
+    r_T[0] = p0, r_T[1] = pl->P - p0, p0 = pl->P;
   }
   if (pl->has_clf) {
     int w = add_tensor(pl, "encoder_y.decoder_p.linear_p.weight", Y, pl->clf_in);
@@ -308,13 +336,26 @@ extern "C" int drvae_plan_create(const drvae_arch_t* a, int n_models, drvae_plan
     pl->clf_b_off = pl->tensors[b].off;
     add_seg_plain(pl, w);
     add_seg_plain(pl, b);
+    r_clf[0] = p0, r_clf[1] = pl->P - p0, p0 = pl->P;
   }
   if (pl->has_fprop) {
     const char* top = (a->kind == DRVAE_KIND_DRVAE) ? "encoder_z3" : "encoder_z2";
     build_gauss_block(pl, pl->z3b, top, Z, Y, a->n_enc_z3, a->enc_z3, Z3, false);
+    r_z3[0] = p0, r_z3[1] = pl->P - p0, p0 = pl->P;
     build_gauss_block(pl, pl->dz1b, "decoder_z1", Z3, Y, a->n_dec_z1, a->dec_z1, Z, false);
+    r_dz1[0] = p0, r_dz1[1] = pl->P - p0, p0 = pl->P;
   }
   build_gauss_block(pl, pl->dec, "decoder_x", Z, 0, a->n_dec_x, a->dec_x, X, true);
+  r_dec[0] = p0, r_dec[1] = pl->P - p0;
+  // backward completes the blocks in this order (run_step)
+  if (pl->has_fprop) {
+    pl->buckets.push_back({r_dz1[0], r_dz1[1]});
+    pl->buckets.push_back({r_z3[0], r_z3[1]});
+  }
+  pl->buckets.push_back({r_dec[0], r_dec[1]});
+  if (pl->has_clf) pl->buckets.push_back({r_clf[0], r_clf[1]});
+  if (pl->has_T) pl->buckets.push_back({r_T[0], r_T[1]});
+  pl->buckets.push_back({r_enc[0], r_enc[1]});
   std::sort(pl->segs.begin(), pl->segs.end(), [](const Seg& x, const Seg& y) { return x.off < y.off; });
 
   // ---- workspace ----
@@ -398,8 +439,15 @@ extern "C" int drvae_plan_create(const drvae_arch_t* a, int n_models, drvae_plan
     return set_cuda_error("drvae_plan_create: cudaMalloc(workspace)", err);
   }
   cudaMemset(pl->arena, 0, pl->arena_bytes);
+  cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking);
+  for (cudaEvent_t* ev : {&pl->ev_fork, &pl->ev_qy, &pl->ev_side_fwd, &pl->ev_side_bwd})
+    cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
+  pl->bucket_ev.resize(pl->buckets.size());
+  for (auto& ev : pl->bucket_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
   cudaMalloc(&pl->dbg, sizeof(DebugWord));
   cudaMemset(pl->dbg, 0, sizeof(DebugWord));
+  cudaMalloc(&pl->d_tabs, pl->h_tabs.size() * sizeof(int));
+  cudaMemcpy(pl->d_tabs, pl->h_tabs.data(), pl->h_tabs.size() * sizeof(int), cudaMemcpyHostToDevice);
   cudaMalloc(&pl->d_segs, pl->segs.size() * sizeof(Seg));
   cudaMemcpy(pl->d_segs, pl->segs.data(), pl->segs.size() * sizeof(Seg), cudaMemcpyHostToDevice);
   for (auto& pr : pend) *pr.first = c8_of(pl, pr.second);
@@ -487,6 +535,11 @@ extern "C" int drvae_plan_destroy(drvae_plan_t* pl) {
   if (pl->arena) cudaFree(pl->arena);
   if (pl->dbg) cudaFree(pl->dbg);
   if (pl->d_segs) cudaFree(pl->d_segs);
+  if (pl->d_tabs) cudaFree(pl->d_tabs);
+  for (auto& ev : pl->bucket_ev) cudaEventDestroy(ev);
+  for (cudaEvent_t ev : {pl->ev_fork, pl->ev_qy, pl->ev_side_fwd, pl->ev_side_bwd})
+    if (ev) cudaEventDestroy(ev);
+  if (pl->side) cudaStreamDestroy(pl->side);
   delete pl;
   return 0;
 }
@@ -512,6 +565,19 @@ extern "C" int drvae_plan_eps_layout(const drvae_plan_t* pl, drvae_eps_layout_t*
   return 0;
 }
 extern "C" long long drvae_plan_workspace_bytes(const drvae_plan_t* pl) { return pl ? (long long)pl->arena_bytes : -1; }
+extern "C" int drvae_plan_num_buckets(const drvae_plan_t* pl) { return pl ? (int)pl->buckets.size() : -1; }
+extern "C" int drvae_plan_bucket_info(const drvae_plan_t* pl, int index, long long* offset, long long* count) {
+  if (!pl || index < 0 || index >= (int)pl->buckets.size()) return set_error("drvae_plan_bucket_info: bad index");
+  if (offset) *offset = pl->buckets[index].first;
+  if (count) *count = pl->buckets[index].second;
+  return 0;
+}
+extern "C" int drvae_stream_wait_bucket(drvae_plan_t* pl, int index, void* stream) {
+  if (!pl || index < 0 || index >= (int)pl->bucket_ev.size()) return set_error("drvae_stream_wait_bucket: bad index");
+  cudaError_t err = cudaStreamWaitEvent((cudaStream_t)stream, pl->bucket_ev[index], 0);
+  if (err != cudaSuccess) return set_cuda_error("drvae_stream_wait_bucket", err);
+  return 0;
+}
 extern "C" long long drvae_plan_launch_count(const drvae_plan_t* pl) { return pl ? pl->launches : -1; }
 extern "C" int drvae_set_gemm_impl(drvae_plan_t* pl, int impl) {
   if (!pl || (impl != GEMM_IMPL_TC && impl != GEMM_IMPL_SIMT)) return set_error("drvae_set_gemm_impl: bad argument");
@@ -592,7 +658,6 @@ struct Exec {
   EpiParams epi_base() const {
     EpiParams e;
     memset(&e, 0, sizeof(e));
-    e.ilv_block = e.ilv_stride = 1 << 30;
     return e;
   }
   void launch(int epi, GemmProblem& p, const EpiParams& e, const char* op) {
@@ -658,18 +723,10 @@ struct Exec {
     EpiParams e = epi_base();
     e.grad = v.grads.p;
     e.grad_ms = v.grads.ms;
-    e.g_ntens = W.ntens;
-    for (int w = 0; w < W.ntens; ++w) {
-      e.g_off[w] = W.w_off[w];
-      e.g_boff[w] = W.b_off[w];
-      e.g_rows[w] = W.rows_each[w];
-      e.bias_const[w] = W.bias_const[w];
-    }
-    e.g_ld = W.ld;
+    e.g_tab = pl->d_tabs + W.tab_off;
+    e.g_tab_n = W.rcap;
     e.g_kin = W.kin;
     e.g_kaug = W.kaug;
-    e.ilv_block = W.ilv_block;
-    e.ilv_stride = W.ilv_stride;
     if (fused) {
       e.adam_p = v.params.p;
       e.adam_m = v.adam_m.p;
@@ -894,9 +951,24 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
   auto rows_grid = [&](int rows) { return dim3(cdiv(rows, ROW_WARPS), E); };
 
   if (!(nz && nz->eps)) {
-    dim3 g(cdiv((int)cdiv((int)pl->epsl.total, 4), 256), E);
+    const drvae_eps_layout_t& el = pl->epsl;
+    EpsSegs sg{};
+    const long long offs[6] = {el.off_x1, el.off_x2, el.off_z1, el.off_z2, el.off_z2f, el.off_z3};
+    const int outer[6] = {1, 1, L, L, L, L};
+    const bool noisy = hp->training && hp->add_noise;
+    const int inner[6] = {noisy ? pl->X : 0, (noisy && pl->has_pair) ? pl->X : 0, pl->Z, pl->has_pair ? pl->Z : 0,
+                          pl->has_T ? pl->Z : 0, pl->has_fprop ? pl->Y * pl->Z3 : 0};
+    long long most = 0;
+    for (int i = 0; i < 6; ++i) {
+      sg.off[i] = offs[i];
+      sg.outer[i] = outer[i];
+      sg.inner[i] = inner[i];
+      most = std::max(most, (long long)outer[i] * N * ((inner[i] + 3) / 4));
+    }
+    dim3 g((unsigned)((most + 255) / 256), E, 6);
     ex.pre("philox_normal");
-    philox_normal_kernel<<<g, 256, 0, st>>>(pl->eps_own, pl->epsl.total, nz ? nz->seed : 0ULL, (unsigned)hp->step);
+    philox_normal_kernel<<<g, 256, 0, st>>>(pl->eps_own, sg, N, pl->Ncap, nz ? nz->row_offset : 0LL, nz ? nz->seed : 0ULL,
+                                            (unsigned)hp->step);
     ex.chk();
   }
   ex.pre("rowmap");
@@ -914,13 +986,68 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
   ex.pre("sample_q1");
   sample_q1_kernel<<<rows_grid(N + PAD_ROWS), ROW_THREADS, 0, st>>>(v);
   ex.chk();
+  // The label-dependent branch (q(z_top|z1,y) -> p(z1|z_top,y), forward and backward: ~14 small
+  // GEMMs + 4 row kernels that leave most SMs idle) is independent of the decoder branch, so it runs
+  // on the plan's side stream between a fork here and a join before the encoder backward.
+  const bool overlap = pl->has_fprop && pl->overlap && !pl->prof_on;
+  cudaStream_t side = overlap ? pl->side : st;
+  auto on = [&](cudaStream_t s) { ex.st = s; };
+  auto after = [&](cudaStream_t waiter, cudaEvent_t ev, cudaStream_t producer) {
+    if (!overlap || waiter == producer) return;
+    cudaEventRecord(ev, producer);
+    cudaStreamWaitEvent(waiter, ev, 0);
+  };
+  after(side, pl->ev_fork, st);
+
+  auto fprop_fwd_gemms = [&]() {
+    // ---- label-dependent part: q(z_top|z1,y), p(z1|z_top,y) per (row, class) evaluation ----
+    ex.phase = "z3.fwd";
+    ex.block_hidden_fwd(pl->z3b, v.Z1e, 0, CNT_F, Fb);
+    ex.gemm_nt(pl->z3b.H.back(), 0, pl->z3b.head, EPI_STORE_F32,
+               ex.epi_f32(v.Q3.p, v.Q3.ms, 2 * pl->Z3, 2 * pl->Z3, &pl->z3b.head), CNT_F, Fb);
+    ex.pre("z3_post");
+    z3_post_kernel<<<rows_grid(round_up(Fb, 128)), ROW_THREADS, 0, ex.st>>>(v);
+    ex.chk();
+    ex.phase = "dz1.fwd";
+    ex.block_hidden_fwd(pl->dz1b, v.Z3b, 0, CNT_F, Fb);
+    ex.gemm_nt(pl->dz1b.H.back(), 0, pl->dz1b.head, EPI_STORE_F32,
+               ex.epi_f32(v.PZ1.p, v.PZ1.ms, 2 * pl->Z, 2 * pl->Z, &pl->dz1b.head), CNT_F, Fb);
+  };
+  if (pl->has_fprop) {
+    on(side);
+    fprop_fwd_gemms();
+    on(st);
+  }
   // ---- p(z2|z1) ----
   ex.phase = "T.fwd";
   if (pl->has_T) {
     ex.gemm_nt(v.Zdec, 0, pl->Tsh, EPI_STORE_F32, ex.epi_f32(v.PT.p, v.PT.ms, 2 * pl->Z, 2 * pl->Z, &pl->Tsh), CNT_LN, LNb);
     ex.pre("T_post");
-    T_post_kernel<<<rows_grid(N + PAD_ROWS), ROW_THREADS, 0, st>>>(v);
+    T_post_kernel<<<rows_grid(N + PAD_ROWS), ROW_THREADS, 0, ex.st>>>(v);
     ex.chk();
+  }
+  if (pl->has_fprop) {
+    // pz1_post weighs unlabeled evaluations by q(y|.), which the classifier in T_post (DrVAE) or
+    // sample_q1 (VFAE) has just produced
+    after(side, pl->ev_qy, st);
+    on(side);
+    ex.pre("pz1_post");
+    pz1_post_kernel<<<rows_grid(round_up(Fb, 128)), ROW_THREADS, 0, ex.st>>>(v);
+    ex.chk();
+    if (overlap) cudaEventRecord(pl->ev_side_fwd, side);
+    if (backward) {
+      ex.phase = "dz1.bwd";
+      ex.block_bwd(pl->dz1b, v.dY9, v.Z3b, 0, pl->Z3, v.dZ3.p, v.dZ3.ms, CNT_F, Fb);
+      cudaEventRecord(pl->bucket_ev[0], ex.st);
+      ex.pre("z3_back");
+      z3_back_kernel<<<rows_grid(round_up(Fb, 128)), ROW_THREADS, 0, ex.st>>>(v);
+      ex.chk();
+      ex.phase = "z3.bwd";
+      ex.block_bwd(pl->z3b, v.dY7, v.Z1e, 0, pl->Z, v.dZ1e.p, v.dZ1e.ms, CNT_F, Fb);
+      cudaEventRecord(pl->bucket_ev[1], ex.st);
+      if (overlap) cudaEventRecord(pl->ev_side_bwd, side);
+    }
+    on(st);
   }
   // ---- decoder p(x|z) on the stacked rows [z1 | z2 | z2f], fused log-density + gradient ----
   ex.phase = "dec.fwd";
@@ -948,25 +1075,10 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
     e.write_dy = backward ? 1 : 0;
     ex.gemm_nt(pl->dec.H.back(), 0, pl->dec.head, EPI_DECLOSS, e, CNT_RD, Rdb);
   }
-  // ---- label-dependent part: q(z_top|z1,y), p(z1|z_top,y) per (row, class) evaluation ----
-  if (pl->has_fprop) {
-    ex.phase = "z3.fwd";
-    ex.block_hidden_fwd(pl->z3b, v.Z1e, 0, CNT_F, Fb);
-    ex.gemm_nt(pl->z3b.H.back(), 0, pl->z3b.head, EPI_STORE_F32,
-               ex.epi_f32(v.Q3.p, v.Q3.ms, 2 * pl->Z3, 2 * pl->Z3, &pl->z3b.head), CNT_F, Fb);
-    ex.pre("z3_post");
-    z3_post_kernel<<<rows_grid(round_up(Fb, 128)), ROW_THREADS, 0, st>>>(v);
-    ex.chk();
-    ex.phase = "dz1.fwd";
-    ex.block_hidden_fwd(pl->dz1b, v.Z3b, 0, CNT_F, Fb);
-    ex.gemm_nt(pl->dz1b.H.back(), 0, pl->dz1b.head, EPI_STORE_F32,
-               ex.epi_f32(v.PZ1.p, v.PZ1.ms, 2 * pl->Z, 2 * pl->Z, &pl->dz1b.head), CNT_F, Fb);
-    ex.pre("pz1_post");
-    pz1_post_kernel<<<rows_grid(round_up(Fb, 128)), ROW_THREADS, 0, st>>>(v);
-    ex.chk();
-  }
+  if (overlap) cudaStreamWaitEvent(st, pl->ev_side_fwd, 0);  // the loss reduction reads the side branch's KL rows
+  ex.phase = "";
   ex.pre("loss");
-  loss_kernel<<<E, 256, 0, st>>>(v);
+  loss_kernel<<<E, 256, 0, ex.st>>>(v);
   ex.chk();
   if (losses_out && ex.ok()) {
     // losses buffer per model is padded to 256 B in the arena; the caller's is dense [E][8]
@@ -975,42 +1087,40 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
   }
 
   if (backward && ex.ok()) {
-    if (pl->has_fprop) {
-      ex.phase = "dz1.bwd";
-      ex.block_bwd(pl->dz1b, v.dY9, v.Z3b, 0, pl->Z3, v.dZ3.p, v.dZ3.ms, CNT_F, Fb);
-      ex.pre("z3_back");
-      z3_back_kernel<<<rows_grid(round_up(Fb, 128)), ROW_THREADS, 0, st>>>(v);
-      ex.chk();
-      ex.phase = "z3.bwd";
-      ex.block_bwd(pl->z3b, v.dY7, v.Z1e, 0, pl->Z, v.dZ1e.p, v.dZ1e.ms, CNT_F, Fb);
-    }
+    size_t bk = pl->has_fprop ? 2 : 0;  // buckets 0, 1 (decoder_z1, encoder_z3) were recorded by the side branch
+    auto bucket_done = [&]() { cudaEventRecord(pl->bucket_ev[bk++], ex.st); };
     ex.phase = "dec.bwd";
     ex.block_bwd(pl->dec, pl->dY5, v.Zdec, 0, pl->Z, v.dZdec.p, v.dZdec.ms, CNT_RD, Rdb);
+    bucket_done();
     if (pl->has_clf) {
       ex.phase = "clf.bwd";
       ex.pre("clf_back");
-      clf_back_kernel<<<rows_grid(LNb), ROW_THREADS, 0, st>>>(v);
+      clf_back_kernel<<<rows_grid(LNb), ROW_THREADS, 0, ex.st>>>(v);
       ex.chk();
       ex.pre("clf_grad_partial");
-      clf_grad_partial_kernel<<<dim3(CLF_SPLITS, E), 256, 0, st>>>(v);
+      clf_grad_partial_kernel<<<dim3(CLF_SPLITS, E), 256, 0, ex.st>>>(v);
       ex.chk();
       ex.pre("clf_grad_reduce");
-      clf_grad_reduce_kernel<<<E, 256, 0, st>>>(v);
+      clf_grad_reduce_kernel<<<E, 256, 0, ex.st>>>(v);
       ex.chk();
+      bucket_done();
     }
     if (pl->has_T) {
       ex.phase = "T.bwd";
       ex.pre("T_back");
-      T_back_kernel<<<rows_grid(N + PAD_ROWS), ROW_THREADS, 0, st>>>(v);
+      T_back_kernel<<<rows_grid(N + PAD_ROWS), ROW_THREADS, 0, ex.st>>>(v);
       ex.chk();
       ex.gemm_dx(v.dYT, pl->Tsh, EPI_STORE_F32, ex.epi_f32(v.dZ1T.p, v.dZ1T.ms, pl->Z, pl->Z, nullptr), CNT_LN, LNb);
       ex.gemm_dw(v.dYT, v.Zdec, 0, pl->Tsh, CNT_LN, LNb);
+      bucket_done();
     }
+    if (overlap) cudaStreamWaitEvent(st, pl->ev_side_bwd, 0);  // join: q_back sums the side branch's gradients into q(z1|x1)
     ex.phase = "enc.bwd";
     ex.pre("q_back");
-    q_back_kernel<<<rows_grid(N + PAD_ROWS), ROW_THREADS, 0, st>>>(v);
+    q_back_kernel<<<rows_grid(N + PAD_ROWS), ROW_THREADS, 0, ex.st>>>(v);
     ex.chk();
     ex.block_bwd(pl->enc, v.dY2, v.Ain, 0, pl->X, nullptr, 0, CNT_R0, R0b);
+    bucket_done();
   }
   if (!ex.ok()) return set_cuda_error("drvae step launch", ex.err);
   return 0;

@@ -78,6 +78,7 @@ struct Shadow {
   int ld;         // leading dimension of the weight tensors (kin + class columns)
   int ilv_block, ilv_stride;
   float bias_const[2];  // constant folded into the derived bias (logvar heads: -2)
+  long long tab_off;    // offset of this weight's 3 x rcap gradient-epilogue tables (EpiParams::g_tab)
 };
 
 struct MlpBlock {

@@ -1,0 +1,117 @@
+"""Data-parallel training of ONE model on a large minibatch (BASELINE.json configs[3]).
+
+The reference has no distributed code; this is the B200 design for its large-batch case.  Rows of
+the minibatch are sharded over ranks.  Every loss term is a sum over rows divided by a batch-level
+count (DrVAE.py:612-616: N, max(1, Np), max(1, Nlab)), so a shard that is given the GLOBAL counts
+produces an additive share of every loss term and of the gradient:
+
+    counts   = all_reduce_sum([N_local, Np_local, Nlab_local])           (3 integers, before the step)
+    grads_r  = drvae_grad_step(shard_r, global counts, row_offset_r)     (flat fp32 [P], C ABI)
+    grads    = all_reduce_sum(grads_r)  — issued per parameter bucket on a side stream as soon as the
+               backward pass has produced that bucket, overlapping the rest of backward
+    drvae_adam_step(...)                                                 (replicated optimizer: 28 MB of state)
+
+ε is keyed by the global row index (drvae_noise_t.row_offset), so the result does not depend on
+the number of ranks.  The communication backend is torch.distributed (NCCL over NVLink on the
+GPU box; gloo in the CPU tests of the host logic, with the oracle as the compute backend).
+"""
+import torch
+import torch.distributed as dist
+
+from .plan import LOSS_KEYS
+
+
+def shard_rows(n_rows, world, rank):
+    """Contiguous, balanced row ranges: the first (n_rows % world) ranks get one extra row."""
+    base, extra = divmod(int(n_rows), int(world))
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def local_counts(n, has_x2=None, has_y=None):
+    np_ = int(has_x2.ne(0).sum()) if has_x2 is not None else 0
+    nl = int(has_y.ne(0).sum()) if has_y is not None else 0
+    return [int(n), np_, nl]
+
+
+def global_counts(counts, group=None, device="cpu"):
+    """Sum [N, Np, Nlab] over the ranks of `group`."""
+    t = torch.tensor(counts, dtype=torch.int64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return [int(v) for v in t.tolist()]
+
+
+class PlanBackend:
+    """Compute backend over the C ABI: one single-model Plan on this rank's GPU."""
+
+    def __init__(self, plan):
+        if plan.E != 1:
+            raise ValueError("data-parallel training shards ONE model; ensembles shard by model instead")
+        self.plan = plan
+        self.device = plan.device
+        self.comm_stream = torch.cuda.Stream(device=plan.device)
+
+    def flat_grads(self):
+        return self.plan.grads[0]
+
+    def buckets(self):
+        return self.plan.grad_buckets()
+
+    def grad_step(self, batch, hp_kwargs, counts, step, eps=None, seed=0, row_offset=0):
+        hp = self.plan.hparams(step=step, global_counts=counts, **hp_kwargs)
+        self._hp = hp
+        losses = self.plan.grad_step(batch, hp, eps=eps, seed=seed, row_offset=row_offset)
+        # drvae_grad_step records one CUDA event per bucket as its gradients complete
+        return losses[0], [lambda stream, k=k: self.plan.stream_wait_bucket(k, stream) for k in range(len(self.buckets()))]
+
+    def adam_step(self):
+        self.plan.adam_step(self._hp)
+
+
+class DataParallel:
+    """step(): one optimisation step of a row-sharded minibatch.  `backend` is a PlanBackend on the
+    GPU box; the CPU tests substitute an oracle-backed object with the same four methods."""
+
+    def __init__(self, backend, group=None):
+        self.backend = backend
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.finished_training_iters = 0
+
+    def _all_reduce(self, t):
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    def step(self, batch, hp_kwargs=None, eps=None, seed=0, row_offset=0):
+        """batch: this rank's shard (same fields as Plan.train_step).  Returns the GLOBAL losses as
+        an 8-vector (RECL, KLD, PERT, YL, MMD, ELBO, CMPL, 0) identical on every rank."""
+        be = self.backend
+        n = batch["x1"].shape[-2]
+        counts = global_counts(local_counts(n, batch.get("has_x2"), batch.get("has_y")), self.group,
+                               device=getattr(be, "device", "cpu"))
+        losses, events = be.grad_step(batch, dict(hp_kwargs or {}), counts, self.finished_training_iters, eps=eps, seed=seed,
+                                      row_offset=row_offset)
+        flat = be.flat_grads()
+        comm = getattr(be, "comm_stream", None)
+        if comm is None:  # CPU backend (tests): no streams, one reduce per bucket in the same order
+            for off, cnt in be.buckets():
+                self._all_reduce(flat[off:off + cnt])
+            self._all_reduce(losses)
+        else:
+            # bucket k is complete when events[k] fires; its all-reduce runs on the side stream while
+            # the compute stream is still inside the backward pass of the remaining blocks
+            with torch.cuda.stream(comm):
+                for (off, cnt), wait in zip(be.buckets(), events):
+                    wait(comm)
+                    self._all_reduce(flat[off:off + cnt])
+                self._all_reduce(losses)
+            torch.cuda.current_stream(be.device).wait_stream(comm)
+        be.adam_step()
+        self.finished_training_iters += 1
+        return losses
+
+    @staticmethod
+    def losses_dict(losses):
+        return {k: float(losses[i]) for i, k in enumerate(LOSS_KEYS)}

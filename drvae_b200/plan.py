@@ -171,29 +171,29 @@ class Plan:
         b = Batch(_ptr(keep[0]), _ptr(keep[1]), _ptr(keep[2]), _ptr(keep[3]), _ptr(keep[4]), int(N))
         return b, keep
 
-    def _noise(self, eps, seed):
+    def _noise(self, eps, seed, row_offset=0):
         if eps is not None:
             eps = eps.to(self.device, torch.float32).contiguous()
             if eps.numel() != self.E * self.eps_layout.total:
                 raise ValueError("eps block must have n_models * %d floats" % self.eps_layout.total)
-        return Noise(_ptr(eps), int(seed) & 0xFFFFFFFFFFFFFFFF), eps
+        return Noise(_ptr(eps), int(seed) & 0xFFFFFFFFFFFFFFFF, int(row_offset)), eps
 
-    def _run(self, fn, what, batch, hp, eps=None, seed=0):
+    def _run(self, fn, what, batch, hp, eps=None, seed=0, row_offset=0):
         b, keep = self._batch(**batch)
-        nz, keep_eps = self._noise(eps, seed)
+        nz, keep_eps = self._noise(eps, seed, row_offset)
         with torch.cuda.device(self.device):
             _lib.check(fn(self.h, ctypes.byref(b), ctypes.byref(nz), ctypes.byref(hp), _ptr(self.losses), self._stream()), what)
         del keep, keep_eps  # stream-ordered: torch's caching allocator keeps them alive for this stream
         return self.losses
 
-    def train_step(self, batch, hp, eps=None, seed=0):
-        return self._run(self.lib.drvae_train_step, "train_step", batch, hp, eps, seed)
+    def train_step(self, batch, hp, eps=None, seed=0, row_offset=0):
+        return self._run(self.lib.drvae_train_step, "train_step", batch, hp, eps, seed, row_offset)
 
-    def grad_step(self, batch, hp, eps=None, seed=0):
-        return self._run(self.lib.drvae_grad_step, "grad_step", batch, hp, eps, seed)
+    def grad_step(self, batch, hp, eps=None, seed=0, row_offset=0):
+        return self._run(self.lib.drvae_grad_step, "grad_step", batch, hp, eps, seed, row_offset)
 
-    def loss_forward(self, batch, hp, eps=None, seed=0):
-        return self._run(self.lib.drvae_loss_forward, "loss_forward", batch, hp, eps, seed)
+    def loss_forward(self, batch, hp, eps=None, seed=0, row_offset=0):
+        return self._run(self.lib.drvae_loss_forward, "loss_forward", batch, hp, eps, seed, row_offset)
 
     def adam_step(self, hp):
         with torch.cuda.device(self.device):
@@ -223,6 +223,18 @@ class Plan:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.drvae_infer(self.h, _ptr(x1), int(N), ctypes.byref(out), self._stream()), "infer")
         return res
+
+    def grad_buckets(self):
+        """[(offset, count)] of the flat gradient in the order drvae_grad_step completes them."""
+        out = []
+        for i in range(self.lib.drvae_plan_num_buckets(self.h)):
+            off, cnt = ctypes.c_longlong(), ctypes.c_longlong()
+            _lib.check(self.lib.drvae_plan_bucket_info(self.h, i, ctypes.byref(off), ctypes.byref(cnt)), "bucket_info")
+            out.append((off.value, cnt.value))
+        return out
+
+    def stream_wait_bucket(self, index, stream):
+        _lib.check(self.lib.drvae_stream_wait_bucket(self.h, int(index), ctypes.c_void_p(stream.cuda_stream)), "wait_bucket")
 
     # ---- introspection --------------------------------------------------------------------
     def set_gemm_impl(self, impl):

@@ -68,10 +68,12 @@ typedef struct {
 
 /* Noise.  eps != NULL: parity mode, a row-indexed block of standard normals per model laid out
  * as drvae_eps_layout() reports.  eps == NULL: the step draws its own with Philox4x32-10 keyed by
- * (seed, step, model). */
+ * (seed, step, model, draw kind, MC sample, row_offset + row, feature): a data-parallel shard that
+ * passes the global index of its first row draws the noise of the unsharded minibatch. */
 typedef struct {
   const float* eps;
   unsigned long long seed;
+  long long row_offset;
 } drvae_noise_t;
 
 /* Scalars of one step (reference: DrVAE.py:79-97 internals, run_drvae.py:173-185 ctor call). */
@@ -135,6 +137,14 @@ int drvae_loss_forward(drvae_plan_t* plan, const drvae_batch_t* batch, const drv
 int drvae_grad_step(drvae_plan_t* plan, const drvae_batch_t* batch, const drvae_noise_t* noise,
                     const drvae_hparams_t* hp, float* losses_out, void* stream);
 int drvae_adam_step(drvae_plan_t* plan, const drvae_hparams_t* hp, void* stream);
+
+/* Gradient buckets for data-parallel overlap.  drvae_grad_step completes the flat gradient in
+ * contiguous ranges ("buckets", one per network block, reported here in completion order) and
+ * records a CUDA event after each; drvae_stream_wait_bucket makes `stream` wait for bucket i of the
+ * most recent drvae_grad_step, so the caller can all-reduce it while backward is still running. */
+int drvae_plan_num_buckets(const drvae_plan_t* plan);
+int drvae_plan_bucket_info(const drvae_plan_t* plan, int index, long long* offset, long long* count);
+int drvae_stream_wait_bucket(drvae_plan_t* plan, int index, void* stream);
 int drvae_infer(drvae_plan_t* plan, const float* x1, int N, const drvae_infer_out_t* out, void* stream);
 
 /* Introspection for tests and bench.py */

@@ -146,6 +146,19 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 32 lanes x 8 consecutive fp32 columns.
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  __syncwarp();
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // Two 16-column loads in flight before one wait (decoder heads: mu and sigma halves of a tile).
 __device__ __forceinline__ void tmem_ld16x2(uint32_t taddr0, uint32_t taddr1, float (&v0)[16], float (&v1)[16]) {
   uint32_t r[16], q[16];
@@ -210,6 +223,24 @@ __device__ __forceinline__ float elu1_grad_from_out(float h) { return h > 0.f ? 
 // torch.nn.Softplus(beta=1, threshold=20)
 __device__ __forceinline__ float softplus20(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 __device__ __forceinline__ float sigmoid_sp(float x) { return x > 20.f ? 1.f : 1.f / (1.f + expf(-x)); }
+
+// torch.optim.Adam with coupled weight decay (reference DGMMixin.py:31-40):
+//   g <- g + wd p ; m <- b1 m + (1-b1) g ; v <- b2 v + (1-b2) g^2 ;
+//   p <- p - (lr / (1-b1^t)) * m / (sqrt(v) / sqrt(1-b2^t) + eps)
+// One definition for the stand-alone optimizer kernel and the fused gradient epilogues, so both
+// apply bit-identical updates.  sqrt / divide use the hardware approximations (<= 2 ulp): the
+// update is ~lr in magnitude, so the absolute effect is ~1e-10 per step.
+struct AdamHyper {
+  float lr_bc1, beta1, beta2, eps, wd, inv_sqrt_bc2;
+};
+__device__ __forceinline__ void adam_update(float g, float& p, float& m, float& v, const AdamHyper& h) {
+  const float gr = g + h.wd * p;
+  m = h.beta1 * m + (1.f - h.beta1) * gr;
+  v = h.beta2 * v + (1.f - h.beta2) * gr * gr;
+  float s;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(s) : "f"(v));
+  p = p - h.lr_bc1 * __fdividef(m, s * h.inv_sqrt_bc2 + h.eps);
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -120,7 +120,7 @@ struct EpiParams {
   long long drv_bias_off;
   long long drv_clsb_off;
   int drv_clsb_ld;
-  float lr_bc1, beta1, beta2, adam_eps, wd, inv_sqrt_bc2;  // lr_bc1 = lr / (1 - beta1^t)
+  AdamHyper adam;
   // EPI_DECLOSS / EPI_DECOUT
   const float4* tgt4;  // fp32 targets, chunk4 layout [Xc/4][tgt_rcap] float4
   long long tgt_ms;    // float4 elements between models
@@ -307,8 +307,8 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& e, RowCtx& rc, int co
         }
       }
     } else {
-      // torch.optim.Adam, same expression order as adam_kernel.  All 48
-      // loads of the chunk are issued back to back (volatile asm keeps them ahead of the math).
+      // generic (unpipelined) form, used by the SIMT validation kernel; the tensor-core kernel runs
+      // adam_epilogue_row below.  All 48 loads of the chunk are issued back to back.
       float* P = e.adam_p + rc.model * e.grad_ms + kofs;
       float* M1 = e.adam_m + rc.model * e.grad_ms + kofs;
       float* V2 = e.adam_v + rc.model * e.grad_ms + kofs;
@@ -323,14 +323,7 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& e, RowCtx& rc, int co
         }
       }
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const float gr = acc[i] + e.wd * pv[i];
-        const float m1 = e.beta1 * mv[i] + (1.f - e.beta1) * gr;
-        const float v1 = e.beta2 * vv[i] + (1.f - e.beta2) * gr * gr;
-        pv[i] = pv[i] - e.lr_bc1 * (m1 / (sqrtf(v1) * e.inv_sqrt_bc2 + e.adam_eps));
-        mv[i] = m1;
-        vv[i] = v1;
-      }
+      for (int i = 0; i < 16; ++i) adam_update(acc[i], pv[i], mv[i], vv[i], e.adam);
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         if (idx[i] >= 0) {
@@ -511,6 +504,103 @@ __device__ __forceinline__ void run_epilogue_row(const GemmProblem& p, const Epi
 }
 
 // ---------------------------------------------------------------------------------------------
+// Fused weight-gradient + Adam epilogue of the tensor-core kernel, software-pipelined.
+// A thread owns D row k (one input feature) and the columns of its group in half-chunks of 8
+// shadow rows.  For each half-chunk it streams p, m, v of 8 reference-weight elements W[n][k]
+// (lanes = consecutive k: 128-byte coalesced), applies Adam to the accumulator column and writes
+// p, m, v, the bf16 shadow and the derived bias back.  The loads of half-chunk h+1 are in flight
+// while h is computed and stored, and the first half-chunk is requested BEFORE the wait on the
+// accumulator barrier, i.e. while the MMA mainloop is still running.
+// ---------------------------------------------------------------------------------------------
+struct AdamBuf {
+  int idx[8];
+  float p[8], m[8], v[8];
+};
+
+__device__ __forceinline__ void adam_pipe_load(const EpiParams& e, int model, int k, int kofs, int col, AdamBuf& b) {
+  if (k >= e.g_kaug) return;
+  const int4* tw = reinterpret_cast<const int4*>(e.g_tab + (k == e.g_kin ? e.g_tab_n : 0) + col);
+  const int4 t0 = tw[0], t1 = tw[1];
+  b.idx[0] = t0.x, b.idx[1] = t0.y, b.idx[2] = t0.z, b.idx[3] = t0.w;
+  b.idx[4] = t1.x, b.idx[5] = t1.y, b.idx[6] = t1.z, b.idx[7] = t1.w;
+  const float* P = e.adam_p + model * e.grad_ms + kofs;
+  const float* M1 = e.adam_m + model * e.grad_ms + kofs;
+  const float* V2 = e.adam_v + model * e.grad_ms + kofs;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    b.p[i] = b.m[i] = b.v[i] = 0.f;
+    if (b.idx[i] >= 0) {
+      b.p[i] = ld_global_f32(P + b.idx[i]);
+      b.m[i] = ld_global_f32(M1 + b.idx[i]);
+      b.v[i] = ld_global_f32(V2 + b.idx[i]);
+    }
+  }
+}
+
+__device__ __forceinline__ void adam_pipe_apply(const EpiParams& e, int model, int k, int kofs, int col, uint32_t taddr,
+                                                bool have_acc, AdamBuf& b) {
+  float acc[8];
+  if (have_acc) {
+    tmem_ld8(taddr, acc);  // warp-collective: executed by every lane, including rows beyond kaug
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  }
+  if (k >= e.g_kaug) return;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) adam_update(acc[i], b.p[i], b.m[i], b.v[i], e.adam);
+  float* P = e.adam_p + model * e.grad_ms + kofs;
+  float* M1 = e.adam_m + model * e.grad_ms + kofs;
+  float* V2 = e.adam_v + model * e.grad_ms + kofs;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (b.idx[i] >= 0) {
+      P[b.idx[i]] = b.p[i];
+      M1[b.idx[i]] = b.m[i];
+      V2[b.idx[i]] = b.v[i];
+    }
+  }
+  if (k < e.g_kin) {
+    bf16* sh = e.sh + model * e.sh_ms + ((long long)(k >> 3) * e.sh_rcap + col) * 8 + (k & 7);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (b.idx[i] >= 0) sh[i * 8] = __float2bfloat16_rn(b.p[i]);
+  } else if (k == e.g_kin) {
+    float* d = e.drv + model * e.drv_ms + e.drv_bias_off + col;
+    const float* bc = reinterpret_cast<const float*>(e.g_tab + 2 * e.g_tab_n + col);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (b.idx[i] >= 0) d[i] = b.p[i] + bc[i];
+  } else {
+    float* d = e.drv + model * e.drv_ms + e.drv_clsb_off + (long long)(k - e.g_kin - 1) * e.drv_clsb_ld + col;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (b.idx[i] >= 0) d[i] = b.p[i];
+  }
+}
+
+__device__ __forceinline__ void adam_epilogue_row(const GemmProblem& p, const EpiParams& e, const TileInfo& t, int cg, int k,
+                                                  uint32_t taddr_row, bool have_acc, uint64_t* acc_bar) {
+  const int nchunks = p.BN >> 4;
+  const int nh = 2 * ((nchunks - cg + EPI_GROUPS - 1) / EPI_GROUPS);  // half-chunks of this column group (even)
+  const int kofs = (k < e.g_kin) ? k : (k == e.g_kin ? 0 : k - 1);
+  // tile-local column of half-chunk h
+  auto lcol = [&](int h) { return (cg + (h >> 1) * EPI_GROUPS) * 16 + (h & 1) * 8; };
+  AdamBuf A, B;
+  if (nh > 0) adam_pipe_load(e, t.model, k, kofs, t.n0 + lcol(0), A);
+  if (have_acc) {
+    mbar_wait(acc_bar, 0, p.dbg, 0xA0000000u);
+    tc_fence_after();
+  }
+  for (int h = 0; h < nh; h += 2) {
+    adam_pipe_load(e, t.model, k, kofs, t.n0 + lcol(h + 1), B);
+    adam_pipe_apply(e, t.model, k, kofs, t.n0 + lcol(h), taddr_row + lcol(h), have_acc, A);
+    if (h + 2 < nh) adam_pipe_load(e, t.model, k, kofs, t.n0 + lcol(h + 2), A);
+    adam_pipe_apply(e, t.model, k, kofs, t.n0 + lcol(h + 1), taddr_row + lcol(h + 1), have_acc, B);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Tensor-core kernel: warp 0 = bulk-copy producer, warp 1 lane 0 = UMMA issuer + TMEM owner,
 // all eight warps = epilogue (warp w reads TMEM lanes [32(w%4), 32(w%4)+32), columns of group w/4).
 // ---------------------------------------------------------------------------------------------
@@ -666,17 +756,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const GemmProb
   __syncwarp();
 
   // ===================== epilogue: TMEM -> registers -> fused math -> HBM =====================
-  if (nkb > 0) {
-    mbar_wait(&acc_bar, 0, p.dbg, 0xA0000000u);
-    tc_fence_after();
-  }
-  RowCtx rc;
-  rc.model = t.model;
-  rc.row = t.m0 + (warp & 3) * 32 + lane;
-  rc.cg = warp >> 2;
-  rc.valid = rc.row < t.Mrows;
   const uint32_t taddr_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-  run_epilogue_row<EPI>(p, e, t, rc, taddr_row, nkb > 0, p.ksplit > 1);
+  if (EPI == EPI_GRAD_ADAM) {
+    adam_epilogue_row(p, e, t, warp >> 2, t.m0 + (warp & 3) * 32 + lane, taddr_row, nkb > 0, &acc_bar);
+  } else {
+    if (nkb > 0) {
+      mbar_wait(&acc_bar, 0, p.dbg, 0xA0000000u);
+      tc_fence_after();
+    }
+    RowCtx rc;
+    rc.model = t.model;
+    rc.row = t.m0 + (warp & 3) * 32 + lane;
+    rc.cg = warp >> 2;
+    rc.valid = rc.row < t.Mrows;
+    run_epilogue_row<EPI>(p, e, t, rc, taddr_row, nkb > 0, p.ksplit > 1);
+  }
 
   tc_fence_before();
   __syncthreads();

@@ -45,7 +45,7 @@ struct AdamArgs {
   const Seg* segs;
   int nseg;
   int P;  // parameters per model
-  float lr_bc1, beta1, beta2, eps, wd, inv_sqrt_bc2;  // lr / (1 - beta1^t), 1 / sqrt(1 - beta2^t)
+  AdamHyper h;
   int update;  // 0: only refresh the derived copies from the current parameters
 };
 
@@ -59,8 +59,6 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamArgs a) {
   bf16* sh = a.shadow.at(mdl);
   float* dv = a.derived.at(mdl);
   const int base = blockIdx.x * 1024 + threadIdx.x;
-  const float step_size = a.lr_bc1;
-  const float inv_sqrt_bc2 = a.inv_sqrt_bc2;
   int si = -1;
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
@@ -68,14 +66,10 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamArgs a) {
     if (idx >= a.P) break;
     float pv = p[idx];
     if (a.update) {
-      // g <- g + wd p ; m <- b1 m + (1-b1) g ; v <- b2 v + (1-b2) g^2 ;
-      // p <- p - (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps)
-      const float gr = g[idx] + a.wd * pv;
-      const float m1 = a.beta1 * mm[idx] + (1.f - a.beta1) * gr;
-      const float v1 = a.beta2 * vv[idx] + (1.f - a.beta2) * gr * gr;
+      float m1 = mm[idx], v1 = vv[idx];
+      adam_update(g[idx], pv, m1, v1, a.h);
       mm[idx] = m1;
       vv[idx] = v1;
-      pv = pv - step_size * (m1 / (sqrtf(v1) * inv_sqrt_bc2 + a.eps));
       p[idx] = pv;
     }
     if (si < 0 || idx < a.segs[si].off || (si + 1 < a.nseg && idx >= a.segs[si + 1].off)) si = seg_find(a.segs, a.nseg, idx);
@@ -198,12 +192,12 @@ __global__ void __launch_bounds__(256) philox_normal_kernel(MBuf<float> out, Eps
                                                             unsigned long long seed, unsigned int step) {
   const int m = blockIdx.y, seg = blockIdx.z;
   const int inner = sg.inner[seg], quads = (inner + 3) >> 2;
-  const long long total = (long long)sg.outer[seg] * N * quads;
-  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  const unsigned total = (unsigned)sg.outer[seg] * (unsigned)N * (unsigned)quads;  // < 2^31 (checked on the host)
+  const unsigned t = blockIdx.x * 256u + threadIdx.x;
   if (inner <= 0 || t >= total) return;
-  const int q = (int)(t % quads);
-  const long long lr = t / quads;
-  const int r = (int)(lr % N), l = (int)(lr / N);
+  const unsigned lr = t / (unsigned)quads;
+  const int q = (int)(t - lr * (unsigned)quads);
+  const int l = (int)(lr / (unsigned)N), r = (int)(lr - (unsigned)l * (unsigned)N);
   const unsigned long long grow = (unsigned long long)(row_offset + r);
   uint32_t c[4] = {(uint32_t)q | ((uint32_t)(grow >> 32) << 24), (uint32_t)grow, step,
                    (uint32_t)m | ((uint32_t)seg << 20) | ((uint32_t)l << 24)};
@@ -216,9 +210,14 @@ __global__ void __launch_bounds__(256) philox_normal_kernel(MBuf<float> out, Eps
   sincospif(2.f * u3, &s1, &c1);
   const float z[4] = {r0 * c0, r0 * s0, r1 * c1, r1 * s1};
   float* o = out.at(m) + sg.off[seg] + ((long long)l * Ncap + r) * inner + q * 4;
+  if (!(inner & 1) && !(sg.off[seg] & 1)) {  // even rows: 8-byte aligned pairs
+    if (q * 4 + 1 < inner) *reinterpret_cast<float2*>(o) = make_float2(z[0], z[1]);
+    if (q * 4 + 3 < inner) *reinterpret_cast<float2*>(o + 2) = make_float2(z[2], z[3]);
+  } else {
 #pragma unroll
-  for (int j = 0; j < 4; ++j)
-    if (q * 4 + j < inner) o[j] = z[j];
+    for (int j = 0; j < 4; ++j)
+      if (q * 4 + j < inner) o[j] = z[j];
+  }
 }
 
 }  // namespace drvae

@@ -739,12 +739,7 @@ struct Exec {
       e.drv_bias_off = W.bias_off;
       e.drv_clsb_off = W.clsb_off;
       e.drv_clsb_ld = W.rcap;
-      e.lr_bc1 = v.s.lr_bc1;
-      e.beta1 = v.s.beta1;
-      e.beta2 = v.s.beta2;
-      e.adam_eps = v.s.eps;
-      e.wd = v.s.weight_decay;
-      e.inv_sqrt_bc2 = v.s.inv_sqrt_bc2;
+      e.adam = v.s.adam;
     }
     launch(fused ? EPI_GRAD_ADAM : EPI_GRAD, p, e, ((fused ? "gemm_dw_adam." : "gemm_dw.") + sub).c_str());
   }
@@ -825,16 +820,17 @@ struct Exec {
 
 // Step-dependent Adam scalars, computed once on the host so that the fused epilogue and the
 // stand-alone kernel apply bit-identical updates.
-struct AdamScalars {
-  float lr_bc1, inv_sqrt_bc2;
-};
-AdamScalars adam_scalars(const drvae_hparams_t* hp) {
+AdamHyper adam_scalars(const drvae_hparams_t* hp) {
   const double t = (double)hp->step + 1.0;
   const float bc1 = (float)(1.0 - pow((double)hp->beta1, t));
   const float bc2 = (float)(1.0 - pow((double)hp->beta2, t));
-  AdamScalars a;
+  AdamHyper a;
   a.lr_bc1 = hp->lr / bc1;
   a.inv_sqrt_bc2 = 1.0f / sqrtf(bc2);
+  a.beta1 = hp->beta1;
+  a.beta2 = hp->beta2;
+  a.eps = hp->adam_eps;
+  a.wd = hp->weight_decay;
   return a;
 }
 
@@ -883,13 +879,7 @@ int fill_view(drvae_plan* pl, Exec& ex, const drvae_batch_t* b, const drvae_nois
   s.gNp = hp->global_Np;
   s.gNlab = hp->global_Nlab;
   for (int j = 0; j < 8; ++j) s.log_prior[j] = hp->log_prior_y[j];
-  AdamScalars as = adam_scalars(hp);
-  s.lr_bc1 = as.lr_bc1;
-  s.inv_sqrt_bc2 = as.inv_sqrt_bc2;
-  s.beta1 = hp->beta1;
-  s.beta2 = hp->beta2;
-  s.eps = hp->adam_eps;
-  s.weight_decay = hp->weight_decay;
+  s.adam = adam_scalars(hp);
   s.fused_adam = 0;
   return 0;
 }
@@ -908,15 +898,7 @@ int run_adam(drvae_plan* pl, const drvae_hparams_t* hp, int update, cudaStream_t
   a.nseg = (int)pl->segs.size();
   a.P = pl->P;
   a.update = update;
-  if (update) {
-    AdamScalars as = adam_scalars(hp);
-    a.lr_bc1 = as.lr_bc1;
-    a.inv_sqrt_bc2 = as.inv_sqrt_bc2;
-    a.beta1 = hp->beta1;
-    a.beta2 = hp->beta2;
-    a.eps = hp->adam_eps;
-    a.wd = hp->weight_decay;
-  }
+  if (update) a.h = adam_scalars(hp);
   dim3 grid(cdiv(pl->P, 1024), pl->E);
   prof_pre(pl, st, update ? "opt:adam" : "opt:shadow_sync");
   adam_kernel<<<grid, 256, 0, st>>>(a);
@@ -965,6 +947,7 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
       sg.inner[i] = inner[i];
       most = std::max(most, (long long)outer[i] * N * ((inner[i] + 3) / 4));
     }
+    if (most >= (1LL << 31)) return set_error("drvae: minibatch too large for the noise generator");
     dim3 g((unsigned)((most + 255) / 256), E, 6);
     ex.pre("philox_normal");
     philox_normal_kernel<<<g, 256, 0, st>>>(pl->eps_own, sg, N, pl->Ncap, nz ? nz->row_offset : 0LL, nz ? nz->seed : 0ULL,
@@ -975,7 +958,7 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
   rowmap_kernel<<<E, 256, 0, st>>>(v);
   ex.chk();
   ex.pre("prep");
-  prep_kernel<<<dim3(round_up(R0b, 128) / PREP_ROWS, E), PREP_THREADS, 0, st>>>(v);
+  prep_kernel<<<dim3(round_up(R0b, 128) / PREP_ROWS, cdiv(pl->view.Xc, PREP_SLAB), E), PREP_THREADS, 0, st>>>(v);
   ex.chk();
 
   // ---- encoder q(z1|x1), shared with q(z2|x2) (DrVAE.py:408,418) ----
@@ -1191,7 +1174,7 @@ extern "C" int drvae_infer(drvae_plan_t* pl, const float* x1, int N, const drvae
   infer_counts_kernel<<<E, 128, 0, st>>>(v, rows_dec);
   ex.chk();
   ex.pre("prep");
-  prep_kernel<<<dim3(round_up(N, 128) / PREP_ROWS, E), PREP_THREADS, 0, st>>>(v);
+  prep_kernel<<<dim3(round_up(N, 128) / PREP_ROWS, cdiv(pl->view.Xc, PREP_SLAB), E), PREP_THREADS, 0, st>>>(v);
   ex.chk();
   ex.block_hidden_fwd(pl->enc, v.Ain, 0, CNT_R0, N);
   ex.gemm_nt(pl->enc.H.back(), 0, pl->enc.head, EPI_STORE_F32, ex.epi_f32(v.Q.p, v.Q.ms, 2 * pl->Z, 2 * pl->Z, &pl->enc.head),

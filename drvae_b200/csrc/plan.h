@@ -98,7 +98,7 @@ struct StepScalars {
   float beta_pert, pertloss_rate, kl_qz2pz2_rate, yloss_rate;
   int training, add_noise;
   int gN, gNp, gNlab;  // global normalisers (0 = use local counts)
-  float lr_bc1, beta1, beta2, eps, weight_decay, inv_sqrt_bc2;  // Adam: lr / (1 - beta1^t), 1 / sqrt(1 - beta2^t)
+  AdamHyper adam;
   int fused_adam;  // 1: the optimizer update happens inside the gradient kernels (drvae_train_step)
   float log_prior[8];  // log prior_y
 };

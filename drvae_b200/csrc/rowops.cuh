@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256) rowmap_kernel(DevView v) {
 // Reads are coalesced along features, writes along rows (the chunk8 bf16 GEMM operand with its
 // ones column at feature X, and the chunk4 fp32 target the decoder epilogue reads), through a
 // shared-memory transpose of 32 rows x 256 features.
-// grid (R0cap / 32, n_models), block 256
+// grid (R0cap / 32, ceil(Xc / 256), n_models), block 256
 // ---------------------------------------------------------------------------------------------
 constexpr int PREP_ROWS = 32;
 constexpr int PREP_THREADS = 256;
@@ -147,7 +147,7 @@ constexpr int PREP_SLAB = 256;
 
 __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(DevView v) {
   __shared__ float tile[PREP_ROWS][PREP_SLAB + 1];
-  const int m = blockIdx.y, r0 = blockIdx.x * PREP_ROWS;
+  const int m = blockIdx.z, r0 = blockIdx.x * PREP_ROWS;
   const int* cnt = v.counts.at(m);
   const int N = cnt[CNT_N], R0 = cnt[CNT_R0];
   if (r0 >= pad128(R0)) return;
@@ -155,7 +155,8 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(DevView v) {
   const bool noisy = v.s.training && v.s.add_noise;
   uint4* ain = reinterpret_cast<uint4*>(v.Ain.at(m));
   float4* tg = v.tgt4.at(m);
-  for (int f0 = 0; f0 < v.Xc; f0 += PREP_SLAB) {
+  {
+    const int f0 = blockIdx.y * PREP_SLAB;
     const int fw = min(PREP_SLAB, v.Xc - f0);  // multiple of 16
     // phase 1: one warp per row, lanes along features
     for (int rl = warp; rl < PREP_ROWS; rl += PREP_THREADS / 32) {
@@ -195,7 +196,6 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(DevView v) {
         if (fc + k == v.X && r < R0) a[k] = 1.f;  // ones column (bias gradient of the first layer)
       ain[(long long)(fc >> 3) * v.Ain.rcap + r] = pack_bf16x8(a);
     }
-    __syncthreads();
   }
 }
 
@@ -742,13 +742,11 @@ __global__ void __launch_bounds__(256) clf_grad_reduce_kernel(DevView v) {
       float* P = v.params.at(m);
       float* M1 = v.adam_m.at(m);
       float* V2 = v.adam_v.at(m);
-      const float pv = P[idx];
-      const float gr = s + v.s.weight_decay * pv;
-      const float m1 = v.s.beta1 * M1[idx] + (1.f - v.s.beta1) * gr;
-      const float v1 = v.s.beta2 * V2[idx] + (1.f - v.s.beta2) * gr * gr;
+      float pv = P[idx], m1 = M1[idx], v1 = V2[idx];
+      adam_update(s, pv, m1, v1, v.s.adam);
       M1[idx] = m1;
       V2[idx] = v1;
-      P[idx] = pv - v.s.lr_bc1 * (m1 / (sqrtf(v1) * v.s.inv_sqrt_bc2 + v.s.eps));
+      P[idx] = pv;
     }
   }
 }

@@ -5,6 +5,7 @@
 // watchdog that turns a would-be hang into a trapped, reported error.
 #pragma once
 
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -52,6 +53,9 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -69,6 +73,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, DebugW
   if (mbar_try_wait(bar, parity)) return;
   long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(40);  // back off: pollers must not starve the producer / MMA warps of issue slots
     if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
       if (dbg) {
         dbg->code = code;
@@ -93,6 +98,28 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
           smem_u32(smem_dst)),
       "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
+}
+
+// 4-D tiled TMA load (cp.async.bulk.tensor): one instruction moves a whole operand tile of a chunk8
+// buffer — box {8 features, rows, chunks, 1 model} — into shared memory in (chunk, row, 8) order,
+// which IS the no-swizzle UMMA canonical layout; out-of-bounds rows / chunks arrive as zeros and
+// count towards the transaction bytes.
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, int c2, int c3,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<unsigned long long>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<unsigned long long>(tmap)) : "memory");
+}
+
+// L2 prefetch of the cache line holding `p` (per-lane address, no destination register).  Used to
+// pull optimizer state towards L2 ahead of the fused Adam epilogue.
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------

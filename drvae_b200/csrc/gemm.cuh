@@ -22,6 +22,9 @@
 // validation reference for the tensor-core mainloop (tests only; never selected implicitly).
 #pragma once
 
+#include <map>
+#include <mutex>
+
 #include "common.cuh"
 
 namespace drvae {
@@ -42,10 +45,17 @@ enum {
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_MAX_STAGES = 6;
+constexpr int GEMM_MAX_STAGES = 8;
 constexpr int GEMM_A_STAGE_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
-constexpr int GEMM_THREADS = 256;
-constexpr int EPI_GROUPS = GEMM_THREADS / 128;  // column groups: warp w reads TMEM lanes 32*(w%4).., columns of group w/4
+constexpr int GEMM_EPI_WARPS = 16;                     // epilogue warps of the persistent kernel
+constexpr int EPI_GROUPS = GEMM_EPI_WARPS / 4;         // column groups: a warp reads TMEM lanes 32*(warp%4).., columns of its group
+constexpr int GEMM_PROD_WARPS = 3;                     // warp 0 = TMA producer; warps 1, 2 spare
+constexpr int GEMM_MMA_WARP = GEMM_PROD_WARPS;         // warp 3 MMA issuer, warps 4..19 epilogue
+constexpr int GEMM_EPI_WARP0 = GEMM_PROD_WARPS + 1;
+constexpr int GEMM_THREADS = (GEMM_PROD_WARPS + 1 + GEMM_EPI_WARPS) * 32;
+constexpr int GEMM_SIMT_THREADS = 128 * EPI_GROUPS;    // validation kernel: thread = (row, column group)
+constexpr int GEMM_ACC_STAGES = 2;                     // accumulator tiles in TMEM (epilogue of tile i overlaps mainloop of i+1)
+constexpr int GEMM_SMEM_BUDGET = 208 * 1024;           // operand ring per CTA (one CTA per SM)
 
 struct GemmOperand {
   const bf16* base;        // model 0
@@ -56,6 +66,10 @@ struct GemmOperand {
 };
 
 struct GemmProblem {
+  // TMA descriptors of the A and B operand buffers (box = one k-block tile of this problem); filled
+  // by gemm_launch_t from a per-process cache
+  alignas(64) CUtensorMap tmA;
+  alignas(64) CUtensorMap tmB;
   GemmOperand A, B;
   int mode;
   int M, N, K;      // static upper bounds of D rows / D cols / contraction length
@@ -65,7 +79,8 @@ struct GemmProblem {
   int tiles_n;
   int tiles_m;
   int nstages;
-  int ksplit;       // >1: contraction split across blockIdx.y (EPI_GRAD accumulates atomically)
+  int ksplit;       // >1: contraction split into ksplit tiles (EPI_GRAD accumulates atomically)
+  int n_models;
   int desc_variant; // debug knob for descriptor bring-up (0 = designed encoding)
   DebugWord* dbg;
 };
@@ -448,11 +463,23 @@ struct TileInfo {
   bool active;
 };
 
-__device__ __forceinline__ TileInfo gemm_tile_info(const GemmProblem& p) {
+// tile index -> (model, k-split slice, tile_m, tile_n).  tile = ((model * ksplit + ks) * tiles_mn) + mn
+__device__ __forceinline__ TileInfo gemm_tile_info(const GemmProblem& p, int tile) {
   TileInfo t;
-  t.model = blockIdx.z;
-  t.tile_n = blockIdx.x % p.tiles_n;
-  t.tile_m = blockIdx.x / p.tiles_n;
+  const int tiles_mn = p.tiles_m * p.tiles_n;
+  const int mn = tile % tiles_mn;
+  const int rest = tile / tiles_mn;
+  const int ks = rest % p.ksplit;
+  t.model = rest / p.ksplit;
+  if (p.mode == GEMM_DW) {
+    // weight-gradient tiles: consecutive tiles (running at the same time on neighbouring SMs) take
+    // consecutive 128-feature segments of the SAME reference-weight rows
+    t.tile_m = mn % p.tiles_m;
+    t.tile_n = mn / p.tiles_m;
+  } else {
+    t.tile_n = mn % p.tiles_n;
+    t.tile_m = mn / p.tiles_n;
+  }
   t.m0 = t.tile_m * GEMM_BM;
   t.n0 = t.tile_n * p.BN;
   int dyn = p.dyn ? p.dyn[(long long)t.model * p.dyn_stride] : -1;
@@ -466,9 +493,9 @@ __device__ __forceinline__ TileInfo gemm_tile_info(const GemmProblem& p) {
   }
   int nkb = (t.Kc + GEMM_BK - 1) / GEMM_BK;
   int per = (nkb + p.ksplit - 1) / p.ksplit;
-  t.kb_begin = min(nkb, (int)blockIdx.y * per);
+  t.kb_begin = min(nkb, ks * per);
   t.kb_end = min(nkb, t.kb_begin + per);
-  t.active = t.m0 < t.Mrows && (t.kb_end > t.kb_begin || blockIdx.y == 0);
+  t.active = t.m0 < t.Mrows && (t.kb_end > t.kb_begin || ks == 0);
   return t;
 }
 
@@ -579,133 +606,126 @@ __device__ __forceinline__ void adam_pipe_apply(const EpiParams& e, int model, i
   }
 }
 
+constexpr int ADAM_PREFETCH_DIST = 4;  // half-chunks of optimizer state requested into L2 ahead of their loads
+
 __device__ __forceinline__ void adam_epilogue_row(const GemmProblem& p, const EpiParams& e, const TileInfo& t, int cg, int k,
-                                                  uint32_t taddr_row, bool have_acc, uint64_t* acc_bar) {
+                                                  uint32_t taddr_row, bool have_acc, uint64_t* acc_bar, uint32_t acc_parity) {
   const int nchunks = p.BN >> 4;
   const int nh = 2 * ((nchunks - cg + EPI_GROUPS - 1) / EPI_GROUPS);  // half-chunks of this column group (even)
   const int kofs = (k < e.g_kin) ? k : (k == e.g_kin ? 0 : k - 1);
   // tile-local column of half-chunk h
   auto lcol = [&](int h) { return (cg + (h >> 1) * EPI_GROUPS) * 16 + (h & 1) * 8; };
+  // L2 prefetch of half-chunk h for the whole warp: lane j < 24 requests the warp's 32-feature
+  // (128-byte) segment of array j % 3 (p, m, v) in weight row j / 3 — first and last byte, the
+  // segment may straddle two lines — so the later per-thread loads find their lines in L2 instead
+  // of paying the loaded DRAM latency with registers held
+  const int lane = threadIdx.x & 31;
+  const int k0 = k - lane;  // first feature of this warp
+  auto prefetch = [&](int h) {
+    if (h >= nh || lane >= 24 || k0 >= e.g_kin) return;
+    const int widx = e.g_tab[t.n0 + lcol(h) + lane / 3];
+    if (widx < 0) return;
+    const int a = lane % 3;
+    const float* base = (a == 0 ? e.adam_p : (a == 1 ? e.adam_m : e.adam_v)) + t.model * e.grad_ms + widx + k0;
+    prefetch_l2(base);
+    prefetch_l2(base + min(32, e.g_kin - k0) - 1);
+  };
   AdamBuf A, B;
   if (nh > 0) adam_pipe_load(e, t.model, k, kofs, t.n0 + lcol(0), A);
-  if (have_acc) {
-    mbar_wait(acc_bar, 0, p.dbg, 0xA0000000u);
-    tc_fence_after();
-  }
+#pragma unroll
+  for (int d = 1; d <= ADAM_PREFETCH_DIST; ++d) prefetch(d);
+  if (lane == 0) mbar_wait(acc_bar, acc_parity, p.dbg, 0xA0000000u);  // one poller per warp
+  __syncwarp();
+  tc_fence_after();
   for (int h = 0; h < nh; h += 2) {
+    prefetch(h + 1 + ADAM_PREFETCH_DIST);
     adam_pipe_load(e, t.model, k, kofs, t.n0 + lcol(h + 1), B);
     adam_pipe_apply(e, t.model, k, kofs, t.n0 + lcol(h), taddr_row + lcol(h), have_acc, A);
+    prefetch(h + 2 + ADAM_PREFETCH_DIST);
     if (h + 2 < nh) adam_pipe_load(e, t.model, k, kofs, t.n0 + lcol(h + 2), A);
     adam_pipe_apply(e, t.model, k, kofs, t.n0 + lcol(h + 1), taddr_row + lcol(h + 1), have_acc, B);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// Tensor-core kernel: warp 0 = bulk-copy producer, warp 1 lane 0 = UMMA issuer + TMEM owner,
-// all eight warps = epilogue (warp w reads TMEM lanes [32(w%4), 32(w%4)+32), columns of group w/4).
+// Tensor-core kernel: persistent (one CTA per SM, tiles strided by gridDim.x) and warp-specialised.
+//   warp 0        TMA producer (lane 0): operand tiles -> shared-memory ring (full/empty mbarriers);
+//                 warps 1, 2 idle (keep the epilogue warps aligned to TMEM lane quarters)
+//   warp 3        lane 0 issues tcgen05.mma into one of two TMEM accumulator tiles; owns TMEM
+//   warps 4..19   epilogue: warp w reads TMEM lanes [32(w%4), +32), columns of group (w-4)/4
+// The accumulator is double-buffered (acc_full / acc_empty mbarriers), so the epilogue of tile i —
+// for the weight gradients a long HBM-bound Adam stream — overlaps the mainloop of tile i+1.
 // ---------------------------------------------------------------------------------------------
 template <int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const GemmProblem p, const EpiParams e) {
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmProblem p, const EpiParams e) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[GEMM_MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[GEMM_MAX_STAGES];
-  __shared__ __align__(8) uint64_t acc_bar;
+  __shared__ __align__(8) uint64_t acc_full[GEMM_ACC_STAGES];
+  __shared__ __align__(8) uint64_t acc_empty[GEMM_ACC_STAGES];
   __shared__ uint32_t tmem_base_s;
-
-  const TileInfo t = gemm_tile_info(p);
-  if (!t.active) return;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int nkb = t.kb_end - t.kb_begin;
   const int BN = p.BN;
   const int b_stage_bytes = BN * GEMM_BK * 2;
   const int stage_bytes = GEMM_A_STAGE_BYTES + b_stage_bytes;
   uint32_t ncols = 32;
   while ((int)ncols < BN) ncols <<= 1;
+  const int total_tiles = p.tiles_m * p.tiles_n * p.ksplit * p.n_models;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.nstages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(&acc_bar, 1);
+    for (int a = 0; a < GEMM_ACC_STAGES; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], GEMM_EPI_WARPS);
+    }
     mbar_fence_init();
   }
-  if (warp == 1 && nkb > 0) {
-    tmem_alloc(&tmem_base_s, ncols);
+  if (warp == GEMM_MMA_WARP) {
+    tmem_alloc(&tmem_base_s, GEMM_ACC_STAGES * ncols);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = nkb > 0 ? tmem_base_s : 0u;
+  const uint32_t tmem_base = tmem_base_s;
 
   const bool a_mn = (p.mode == GEMM_DW);
   const bool b_mn = (p.mode != GEMM_NT);
 
-  if (warp == 0 && nkb > 0) {
-    // ===================== producer: 1-D bulk copies of operand slabs =====================
-    const bf16* Ab = p.A.base + t.model * p.A.model_stride;
-    const bf16* Bb = p.B.base + t.model * p.B.model_stride;
-    for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
-      const int it = kb - t.kb_begin;
-      const int s = it % p.nstages;
-      const uint32_t ph = (it / p.nstages) & 1;
-      if (lane == 0) mbar_wait(&empty_bar[s], ph ^ 1, p.dbg, 0xE0000000u | kb);
-      __syncwarp();
-      const int kw = min(GEMM_BK, t.Kc - kb * GEMM_BK);  // multiple of 16
-      uint8_t* As = smem + (size_t)s * stage_bytes;
-      uint8_t* Bs = As + GEMM_A_STAGE_BYTES;
-      // --- copy descriptors ---
-      int nA, nB;
-      uint32_t bytesA, bytesB;
-      if (!a_mn) {
-        nA = kw >> 3;
-        bytesA = GEMM_BM * 16;
-      } else {
-        nA = min(GEMM_BM >> 3, p.A.nchunks - (t.m0 >> 3));
-        bytesA = kw * 16;
-      }
-      if (!b_mn) {
-        nB = kw >> 3;
-        bytesB = BN * 16;
-      } else {
-        nB = min(BN >> 3, p.B.nchunks - (t.n0 >> 3));
-        bytesB = kw * 16;
-      }
-      if (nA < 0) nA = 0;
-      if (nB < 0) nB = 0;
-      if (lane == 0) mbar_arrive_expect_tx(&full_bar[s], nA * bytesA + nB * bytesB);
-      __syncwarp();
-      for (int c = lane; c < nA + nB; c += 32) {
-        if (c < nA) {
-          const bf16* src;
-          uint8_t* dst;
-          if (!a_mn) {
-            src = Ab + ((long long)(kb * 8 + c) * p.A.rcap + p.A.row0 + t.m0) * 8;
-            dst = As + (size_t)c * (GEMM_BM * 16);
-          } else {
-            src = Ab + ((long long)((t.m0 >> 3) + c) * p.A.rcap + p.A.row0 + kb * GEMM_BK) * 8;
-            dst = As + (size_t)c * (GEMM_BK * 16);
-          }
-          bulk_g2s(dst, src, bytesA, &full_bar[s]);
-        } else {
-          const int cb = c - nA;
-          const bf16* src;
-          uint8_t* dst;
-          if (!b_mn) {
-            src = Bb + ((long long)(kb * 8 + cb) * p.B.rcap + p.B.row0 + t.n0) * 8;
-            dst = Bs + (size_t)cb * (BN * 16);
-          } else {
-            src = Bb + ((long long)((t.n0 >> 3) + cb) * p.B.rcap + p.B.row0 + kb * GEMM_BK) * 8;
-            dst = Bs + (size_t)cb * (GEMM_BK * 16);
-          }
-          bulk_g2s(dst, src, bytesB, &full_bar[s]);
+  if (warp == 0) {
+    // ===================== producer: one TMA tile load per operand and k-block =====================
+    if (lane == 0) {
+      tma_prefetch_desc(&p.tmA);
+      tma_prefetch_desc(&p.tmB);
+      const uint32_t tx_bytes = GEMM_A_STAGE_BYTES + b_stage_bytes;  // full boxes (out-of-bounds parts are zero-filled)
+      uint32_t it = 0;  // k-blocks issued by this CTA so far (ring position)
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileInfo t = gemm_tile_info(p, tile);
+        if (!t.active) continue;
+        for (int kb = t.kb_begin; kb < t.kb_end; ++kb, ++it) {
+          const int s = it % p.nstages;
+          const uint32_t ph = (it / p.nstages) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1, p.dbg, 0xE0000000u | kb);
+          uint8_t* As = smem + (size_t)s * stage_bytes;
+          uint8_t* Bs = As + GEMM_A_STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+          if (!a_mn)  // K-major: box {8, 128 rows, 8 feature chunks}
+            tma_load_4d(As, &p.tmA, 0, p.A.row0 + t.m0, kb * (GEMM_BK / 8), t.model, &full_bar[s]);
+          else        // MN-major: box {8, 64 contraction rows, 16 feature chunks}
+            tma_load_4d(As, &p.tmA, 0, p.A.row0 + kb * GEMM_BK, t.m0 >> 3, t.model, &full_bar[s]);
+          if (!b_mn)  // box {8, BN rows, 8 feature chunks}
+            tma_load_4d(Bs, &p.tmB, 0, p.B.row0 + t.n0, kb * (GEMM_BK / 8), t.model, &full_bar[s]);
+          else        // box {8, 64 contraction rows, BN / 8 feature chunks}
+            tma_load_4d(Bs, &p.tmB, 0, p.B.row0 + kb * GEMM_BK, t.n0 >> 3, t.model, &full_bar[s]);
         }
       }
     }
-  } else if (warp == 1 && lane == 0 && nkb > 0) {
+  } else if (warp == GEMM_MMA_WARP) {
     // ===================== UMMA issuer =====================
     const uint32_t idesc = umma_idesc_bf16(BN, a_mn ? 1 : 0, b_mn ? 1 : 0);
     uint32_t a_lbo, a_sbo, a_step, b_lbo, b_sbo, b_step;
@@ -735,46 +755,72 @@ __global__ void __launch_bounds__(GEMM_THREADS, 2) gemm_tc_kernel(const GemmProb
       b_lbo = b_sbo;
       b_sbo = x;
     }
-    for (int kb = t.kb_begin; kb < t.kb_end; ++kb) {
-      const int it = kb - t.kb_begin;
-      const int s = it % p.nstages;
-      const uint32_t ph = (it / p.nstages) & 1;
-      mbar_wait(&full_bar[s], ph, p.dbg, 0xF0000000u | kb);
-      tc_fence_after();
-      const int kw = min(GEMM_BK, t.Kc - kb * GEMM_BK);
-      const uint32_t As = smem_u32(smem + (size_t)s * stage_bytes);
-      const uint32_t Bs = As + GEMM_A_STAGE_BYTES;
-      for (int j = 0; j < (kw >> 4); ++j) {
-        uint64_t ad = umma_smem_desc(As + j * a_step, a_lbo, a_sbo);
-        uint64_t bd = umma_smem_desc(Bs + j * b_step, b_lbo, b_sbo);
-        umma_bf16(tmem_base, ad, bd, idesc, (it > 0 || j > 0) ? 1u : 0u);
+    uint32_t it = 0, j = 0;  // ring position, active tiles done
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileInfo t = gemm_tile_info(p, tile);
+      if (!t.active) continue;
+      const uint32_t a = j & 1, aph = (j >> 1) & 1;
+      if (lane == 0) {
+        mbar_wait(&acc_empty[a], aph ^ 1, p.dbg, 0xB0000000u | tile);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + a * ncols;
+        for (int kb = t.kb_begin; kb < t.kb_end; ++kb, ++it) {
+          const int s = it % p.nstages;
+          const uint32_t ph = (it / p.nstages) & 1;
+          mbar_wait(&full_bar[s], ph, p.dbg, 0xF0000000u | kb);
+          tc_fence_after();
+          const int kw = min(GEMM_BK, t.Kc - kb * GEMM_BK);
+          const uint32_t As = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t Bs = As + GEMM_A_STAGE_BYTES;
+          for (int q = 0; q < (kw >> 4); ++q) {
+            uint64_t ad = umma_smem_desc(As + q * a_step, a_lbo, a_sbo);
+            uint64_t bd = umma_smem_desc(Bs + q * b_step, b_lbo, b_sbo);
+            umma_bf16(tacc, ad, bd, idesc, (kb > t.kb_begin || q > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs retire
+        }
+        if (t.kb_end > t.kb_begin)
+          umma_commit(&acc_full[a]);  // accumulator complete
+        else
+          mbar_arrive(&acc_full[a]);  // empty contraction: the epilogue uses zeros
       }
-      umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs retire
+      __syncwarp();
+      ++j;
     }
-    umma_commit(&acc_bar);  // accumulator complete
-  }
-  __syncwarp();
-
-  // ===================== epilogue: TMEM -> registers -> fused math -> HBM =====================
-  const uint32_t taddr_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-  if (EPI == EPI_GRAD_ADAM) {
-    adam_epilogue_row(p, e, t, warp >> 2, t.m0 + (warp & 3) * 32 + lane, taddr_row, nkb > 0, &acc_bar);
   } else {
-    if (nkb > 0) {
-      mbar_wait(&acc_bar, 0, p.dbg, 0xA0000000u);
-      tc_fence_after();
+    // ===================== epilogue: TMEM -> registers -> fused math -> HBM =====================
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int cg = (warp - GEMM_EPI_WARP0) >> 2;  // column group
+    uint32_t j = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileInfo t = gemm_tile_info(p, tile);
+      if (!t.active) continue;
+      const uint32_t a = j & 1, aph = (j >> 1) & 1;
+      const bool have_acc = t.kb_end > t.kb_begin;
+      const uint32_t taddr_row = tmem_base + a * ncols + ((uint32_t)(q * 32) << 16);
+      if (EPI == EPI_GRAD_ADAM) {
+        adam_epilogue_row(p, e, t, cg, t.m0 + q * 32 + lane, taddr_row, have_acc, &acc_full[a], aph);
+      } else {
+        if (lane == 0) mbar_wait(&acc_full[a], aph, p.dbg, 0xA0000000u | tile);  // one poller per warp
+        __syncwarp();
+        tc_fence_after();
+        RowCtx rc;
+        rc.model = t.model;
+        rc.row = t.m0 + q * 32 + lane;
+        rc.cg = cg;
+        rc.valid = rc.row < t.Mrows;
+        run_epilogue_row<EPI>(p, e, t, rc, taddr_row, have_acc, p.ksplit > 1);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[a]);
+      ++j;
     }
-    RowCtx rc;
-    rc.model = t.model;
-    rc.row = t.m0 + (warp & 3) * 32 + lane;
-    rc.cg = warp >> 2;
-    rc.valid = rc.row < t.Mrows;
-    run_epilogue_row<EPI>(p, e, t, rc, taddr_row, nkb > 0, p.ksplit > 1);
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1 && nkb > 0) tmem_dealloc(tmem_base, ncols);
+  if (warp == GEMM_MMA_WARP) tmem_dealloc(tmem_base, GEMM_ACC_STAGES * ncols);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -790,8 +836,8 @@ __device__ __forceinline__ float simt_ldB(const GemmProblem& p, const bf16* B, i
 }
 
 template <int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS) gemm_simt_kernel(const GemmProblem p, const EpiParams e) {
-  const TileInfo t = gemm_tile_info(p);
+__global__ void __launch_bounds__(GEMM_SIMT_THREADS) gemm_simt_kernel(const GemmProblem p, const EpiParams e) {
+  const TileInfo t = gemm_tile_info(p, blockIdx.x);
   if (!t.active) return;
   const bf16* Ab = p.A.base + t.model * p.A.model_stride;
   const bf16* Bb = p.B.base + t.model * p.B.model_stride;
@@ -843,28 +889,107 @@ enum { GEMM_IMPL_TC = 0, GEMM_IMPL_SIMT = 1 };
 
 inline int gemm_pick_stages(int BN) {
   const int stage = GEMM_A_STAGE_BYTES + BN * GEMM_BK * 2;
-  int s = (100 * 1024) / stage;  // ~100 KB per CTA -> two CTAs per SM
+  int s = GEMM_SMEM_BUDGET / stage;
   if (s < 2) s = 2;
   if (s > GEMM_MAX_STAGES) s = GEMM_MAX_STAGES;
   return s;
 }
 
+// ---- TMA descriptors -------------------------------------------------------------------------
+// A chunk8 buffer [nchunks][rcap][8] bf16 per model is described to the TMA unit as a 4-D tensor
+// {8, rcap, nchunks, models}; the box is the k-block tile of the operand's role in this problem.
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled gemm_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+struct TmapKey {
+  const void* base;
+  long long ms;
+  int rcap, nchunks, models, box_rows, box_chunks;
+  bool operator<(const TmapKey& o) const {
+    if (base != o.base) return base < o.base;
+    if (ms != o.ms) return ms < o.ms;
+    if (rcap != o.rcap) return rcap < o.rcap;
+    if (nchunks != o.nchunks) return nchunks < o.nchunks;
+    if (models != o.models) return models < o.models;
+    if (box_rows != o.box_rows) return box_rows < o.box_rows;
+    return box_chunks < o.box_chunks;
+  }
+};
+
+inline cudaError_t gemm_get_tmap(const GemmOperand& op, int models, int box_rows, int box_chunks, CUtensorMap* out) {
+  static std::map<TmapKey, CUtensorMap> cache;
+  static std::mutex mu;
+  TmapKey key{op.base, op.model_stride, op.rcap, op.nchunks, models, box_rows, box_chunks};
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it == cache.end()) {
+    PFN_encodeTiled enc = gemm_encode_fn();
+    if (!enc) return cudaErrorNotSupported;
+    CUtensorMap m;
+    const cuuint64_t dims[4] = {8, (cuuint64_t)op.rcap, (cuuint64_t)op.nchunks, (cuuint64_t)models};
+    const cuuint64_t strides[3] = {16, (cuuint64_t)op.rcap * 16, (cuuint64_t)(models > 1 ? op.model_stride * 2 : (long long)op.rcap * 16 * op.nchunks)};
+    const cuuint32_t box[4] = {8, (cuuint32_t)box_rows, (cuuint32_t)box_chunks, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(op.base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    it = cache.emplace(key, m).first;
+  }
+  *out = it->second;
+  return cudaSuccess;
+}
+
+inline int gemm_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
 template <int EPI>
 inline cudaError_t gemm_launch_t(GemmProblem p, const EpiParams& e, int n_models, int impl, cudaStream_t st) {
-  dim3 grid(p.tiles_n * p.tiles_m, p.ksplit, n_models);
+  p.n_models = n_models;
+  const int total = p.tiles_n * p.tiles_m * p.ksplit * n_models;
   if (impl == GEMM_IMPL_SIMT) {
-    gemm_simt_kernel<EPI><<<grid, GEMM_THREADS, 0, st>>>(p, e);
+    gemm_simt_kernel<EPI><<<total, GEMM_SIMT_THREADS, 0, st>>>(p, e);
     return cudaGetLastError();
   }
   p.nstages = gemm_pick_stages(p.BN);
+  // weight-gradient tiles have short contractions (batch rows) and a long HBM-bound epilogue whose
+  // streaming loads/stores go through L1: a shallow operand ring leaves the rest of the 256 KB as L1
+  if (EPI == EPI_GRAD_ADAM && p.nstages > 3) p.nstages = 3;
   size_t smem = (size_t)p.nstages * (GEMM_A_STAGE_BYTES + p.BN * GEMM_BK * 2);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t err =
-        cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BUDGET + 4096);
     if (err != cudaSuccess) return err;
     attr_set = true;
   }
+  {
+    const bool a_mn = (p.mode == GEMM_DW), b_mn = (p.mode != GEMM_NT);
+    cudaError_t err = gemm_get_tmap(p.A, n_models, a_mn ? GEMM_BK : GEMM_BM, a_mn ? GEMM_BM / 8 : GEMM_BK / 8, &p.tmA);
+    if (err == cudaSuccess) err = gemm_get_tmap(p.B, n_models, b_mn ? GEMM_BK : p.BN, b_mn ? p.BN / 8 : GEMM_BK / 8, &p.tmB);
+    if (err != cudaSuccess) return err;
+  }
+  const int grid = total < gemm_num_sms() ? total : gemm_num_sms();  // persistent: one CTA per SM
   gemm_tc_kernel<EPI><<<grid, GEMM_THREADS, smem, st>>>(p, e);
   return cudaGetLastError();
 }

@@ -178,6 +178,64 @@ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uin
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// weight norm (layers.WeightNormLinear): one warp per output row of every normalised layer
+// grid (ceil(rows / 8), n_models), block 256
+// ---------------------------------------------------------------------------------------------
+struct WnArgs {
+  const WnRow* rows;
+  int nrows;
+  MBuf<float> params, grads;
+  MBuf<bf16> shadow;
+  MBuf<float> derived;
+};
+
+// effective rows -> bf16 shadow / class bias / classifier copy
+__global__ void __launch_bounds__(256) wn_refresh_kernel(WnArgs a) {
+  const int m = blockIdx.y, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= a.nrows) return;
+  const WnRow w = a.rows[r];
+  const float* vrow = a.params.at(m) + w.w_off;
+  float ss = 0.f;
+  for (int k = lane; k < w.ld; k += 32) ss += vrow[k] * vrow[k];
+  ss = warp_sum(ss);
+  const float scale = a.params.at(m)[w.g_idx] / sqrtf(ss);
+  if (w.sh_off >= 0) {
+    bf16* sh = a.shadow.at(m) + w.sh_off;
+    for (int k = lane; k < w.kin; k += 32) sh[c8_index(w.srow, k, w.sh_rcap)] = __float2bfloat16_rn(scale * vrow[k]);
+    float* cb = a.derived.at(m) + w.aux_off;
+    for (int k = w.kin + lane; k < w.ld; k += 32) cb[(long long)(k - w.kin) * w.aux_ld + w.srow] = scale * vrow[k];
+  } else {
+    float* eff = a.derived.at(m) + w.aux_off;
+    for (int k = lane; k < w.ld; k += 32) eff[k] = scale * vrow[k];
+  }
+}
+
+// in place: gradient wrt the effective row -> gradient wrt v (same slots) and g
+//   dg = <dW, v> / ||v|| ;  dv = (g / ||v||) dW - (g <dW, v> / ||v||^3) v
+__global__ void __launch_bounds__(256) wn_grad_kernel(WnArgs a) {
+  const int m = blockIdx.y, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= a.nrows) return;
+  const WnRow w = a.rows[r];
+  const float* vrow = a.params.at(m) + w.w_off;
+  float* grow = a.grads.at(m) + w.w_off;
+  float ss = 0.f, dot = 0.f;
+  for (int k = lane; k < w.ld; k += 32) {
+    const float vk = vrow[k];
+    ss += vk * vk;
+    dot += grow[k] * vk;
+  }
+  ss = warp_sum(ss);
+  dot = warp_sum(dot);
+  const float inv = 1.f / sqrtf(ss);
+  const float g = a.params.at(m)[w.g_idx];
+  const float c1 = g * inv, c2 = g * dot * inv * inv * inv;
+  for (int k = lane; k < w.ld; k += 32) grow[k] = c1 * grow[k] - c2 * vrow[k];
+  if (lane == 0) a.grads.at(m)[w.g_idx] = dot * inv;
+}
+
 // ε block generator.  Every normal is keyed by (seed, step, model, segment, MC sample, GLOBAL row,
 // position in the row) and never by its address, so a minibatch sharded over ranks
 // (row_offset = global index of the shard's first row) draws exactly the noise of the unsharded
@@ -191,8 +249,13 @@ struct EpsSegs {
 __global__ void __launch_bounds__(256) philox_normal_kernel(MBuf<float> out, EpsSegs sg, int N, int Ncap, long long row_offset,
                                                             unsigned long long seed, unsigned int step) {
   const int m = blockIdx.y, seg = blockIdx.z;
-  const int inner = sg.inner[seg], quads = (inner + 3) >> 2;
-  const unsigned total = (unsigned)sg.outer[seg] * (unsigned)N * (unsigned)quads;  // < 2^31 (checked on the host)
+  int inner = 0, outer = 0;
+  long long seg_off = 0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i)  // static indexing: a dynamic index would copy the struct to local memory
+    if (i == seg) inner = sg.inner[i], outer = sg.outer[i], seg_off = sg.off[i];
+  const int quads = (inner + 3) >> 2;
+  const unsigned total = (unsigned)outer * (unsigned)N * (unsigned)quads;  // < 2^31 (checked on the host)
   const unsigned t = blockIdx.x * 256u + threadIdx.x;
   if (inner <= 0 || t >= total) return;
   const unsigned lr = t / (unsigned)quads;
@@ -204,13 +267,17 @@ __global__ void __launch_bounds__(256) philox_normal_kernel(MBuf<float> out, Eps
   philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
   const float k = 2.3283064365386963e-10f;  // 2^-32
   const float u0 = (c[0] + 1.0f) * k, u1 = c[1] * k, u2 = (c[2] + 1.0f) * k, u3 = c[3] * k;
-  const float r0 = sqrtf(-2.f * logf(fminf(u0, 1.f))), r1 = sqrtf(-2.f * logf(fminf(u2, 1.f)));
+  // Box-Muller with the hardware approximations (noise: ~1e-6 absolute error is irrelevant); the clamp keeps
+  // -2 log(u) non-negative when u rounds to 1
+  float r0, r1;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r0) : "f"(fmaxf(-2.f * __logf(fminf(u0, 1.f)), 0.f)));
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r1) : "f"(fmaxf(-2.f * __logf(fminf(u2, 1.f)), 0.f)));
   float s0, c0, s1, c1;
-  sincospif(2.f * u1, &s0, &c0);
-  sincospif(2.f * u3, &s1, &c1);
+  __sincosf(6.283185307179586f * u1, &s0, &c0);
+  __sincosf(6.283185307179586f * u3, &s1, &c1);
   const float z[4] = {r0 * c0, r0 * s0, r1 * c1, r1 * s1};
-  float* o = out.at(m) + sg.off[seg] + ((long long)l * Ncap + r) * inner + q * 4;
-  if (!(inner & 1) && !(sg.off[seg] & 1)) {  // even rows: 8-byte aligned pairs
+  float* o = out.at(m) + seg_off + ((long long)l * Ncap + r) * inner + q * 4;
+  if (!(inner & 1) && !(seg_off & 1)) {  // even rows: 8-byte aligned pairs
     if (q * 4 + 1 < inner) *reinterpret_cast<float2*>(o) = make_float2(z[0], z[1]);
     if (q * 4 + 3 < inner) *reinterpret_cast<float2*>(o + 2) = make_float2(z[2], z[3]);
   } else {

@@ -56,6 +56,10 @@ struct drvae_plan {
   Seg* d_segs = nullptr;
   std::vector<int> h_tabs;  // gradient-epilogue tables of every weight (see make_shadow)
   int* d_tabs = nullptr;
+  bool wn = false;            // layers.WeightNormLinear instead of nn.Linear
+  std::vector<WnRow> wn_rows;
+  WnRow* d_wn_rows = nullptr;
+  long long clf_eff_off = -1;  // derived offset of the classifier's effective weights (weight norm only)
   int P = 0;
   int clf_w_off = -1, clf_b_off = -1;
   // shadows
@@ -125,8 +129,9 @@ void add_seg_plain(drvae_plan* pl, int tid) {
 
 // Allocate shadow storage + derived bias for a GEMM weight made of `ntens` reference tensors.
 Shadow make_shadow(drvae_plan* pl, int ntens, const int* w_tid, const int* b_tid, int rows_each, int kin, int class_cols,
-                   int ilv_block, int ilv_stride, int BN, int tiles_n, const float* bias_const) {
+                   int ilv_block, int ilv_stride, int BN, int tiles_n, const float* bias_const, const int* g_tid = nullptr) {
   Shadow sh{};
+  sh.g_off[0] = sh.g_off[1] = -1;
   sh.ntens = ntens;
   sh.kin = kin;
   sh.kaug = kin + 1 + class_cols;
@@ -171,6 +176,11 @@ Shadow make_shadow(drvae_plan* pl, int ntens, const int* w_tid, const int* b_tid
     s.clsb_off = sh.clsb_off;
     s.clsb_ld = sh.rcap;
     s.wn_g_off = -1;
+    if (g_tid) {
+      sh.g_off[w] = pl->tensors[g_tid[w]].off;
+      s.wn_g_off = sh.g_off[w];
+      add_seg_plain(pl, g_tid[w]);
+    }
     pl->segs.push_back(s);
     Seg b{};
     b.off = bt.off;
@@ -202,6 +212,19 @@ Shadow make_shadow(drvae_plan* pl, int ntens, const int* w_tid, const int* b_tid
       tw[sh.rcap + srow] = sh.b_off[which] + n;
       float c = sh.bias_const[which];
       memcpy(&tw[2 * sh.rcap + srow], &c, sizeof(float));
+      if (sh.g_off[which] >= 0) {
+        WnRow r{};
+        r.w_off = sh.w_off[which] + n * sh.ld;
+        r.g_idx = sh.g_off[which] + n;
+        r.ld = sh.ld;
+        r.kin = kin;
+        r.sh_off = sh.off;
+        r.sh_rcap = sh.rcap;
+        r.srow = srow;
+        r.aux_off = sh.clsb_off;
+        r.aux_ld = sh.rcap;
+        pl->wn_rows.push_back(r);
+      }
     }
   }
   return sh;
@@ -218,28 +241,29 @@ void build_gauss_block(drvae_plan* pl, MlpBlock& blk, const std::string& prefix,
     const int cc = (i == 0) ? class_cols : 0;
     int w = add_tensor(pl, std::string(nm) + ".weight", widths[i], prev + cc);
     int b = add_tensor(pl, std::string(nm) + ".bias", widths[i], 0);
+    int g = pl->wn ? add_tensor(pl, std::string(nm) + ".g", widths[i], 0) : -1;
     Tiling t = tile_cap(widths[i] + 1);  // + the ones column the next layer's dW reads
-    blk.hidden.push_back(make_shadow(pl, 1, &w, &b, widths[i], prev, cc, 1 << 30, 1 << 30, t.BN, t.tiles, nullptr));
+    blk.hidden.push_back(
+        make_shadow(pl, 1, &w, &b, widths[i], prev, cc, 1 << 30, 1 << 30, t.BN, t.tiles, nullptr, pl->wn ? &g : nullptr));
     blk.widths.push_back(widths[i]);
     prev = widths[i];
   }
-  int wt[2], bt[2];
+  int wt[2], bt[2], gt[2] = {-1, -1};
+  const char* second = sigma_heads ? "sg" : "lv";
+  const std::string heads[2] = {prefix + ".encoder_mu.linear_mu", prefix + ".encoder_" + second + ".linear_" + second};
+  for (int w = 0; w < 2; ++w) {
+    wt[w] = add_tensor(pl, heads[w] + ".weight", out_dim, prev);
+    bt[w] = add_tensor(pl, heads[w] + ".bias", out_dim, 0);
+    if (pl->wn) gt[w] = add_tensor(pl, heads[w] + ".g", out_dim, 0);
+  }
   if (!sigma_heads) {
-    wt[0] = add_tensor(pl, prefix + ".encoder_mu.linear_mu.weight", out_dim, prev);
-    bt[0] = add_tensor(pl, prefix + ".encoder_mu.linear_mu.bias", out_dim, 0);
-    wt[1] = add_tensor(pl, prefix + ".encoder_lv.linear_lv.weight", out_dim, prev);
-    bt[1] = add_tensor(pl, prefix + ".encoder_lv.linear_lv.bias", out_dim, 0);
     const float bc[2] = {0.f, -2.f};  // logvar = lin(h) - 2  (blocks.py:296)
     Tiling t = tile_cap(2 * out_dim);
-    blk.head = make_shadow(pl, 2, wt, bt, out_dim, prev, 0, out_dim, 2 * out_dim, t.BN, t.tiles, bc);
+    blk.head = make_shadow(pl, 2, wt, bt, out_dim, prev, 0, out_dim, 2 * out_dim, t.BN, t.tiles, bc, pl->wn ? gt : nullptr);
   } else {
-    wt[0] = add_tensor(pl, prefix + ".encoder_mu.linear_mu.weight", out_dim, prev);
-    bt[0] = add_tensor(pl, prefix + ".encoder_mu.linear_mu.bias", out_dim, 0);
-    wt[1] = add_tensor(pl, prefix + ".encoder_sg.linear_sg.weight", out_dim, prev);
-    bt[1] = add_tensor(pl, prefix + ".encoder_sg.linear_sg.bias", out_dim, 0);
     const int hb = std::min(128, round_up(out_dim, 16));
     pl->dec_hb = hb;
-    blk.head = make_shadow(pl, 2, wt, bt, out_dim, prev, 0, hb, 2 * hb, 2 * hb, cdiv(out_dim, hb), nullptr);
+    blk.head = make_shadow(pl, 2, wt, bt, out_dim, prev, 0, hb, 2 * hb, 2 * hb, cdiv(out_dim, hb), nullptr, pl->wn ? gt : nullptr);
   }
 }
 
@@ -285,7 +309,6 @@ extern "C" int drvae_plan_create(const drvae_arch_t* a, int n_models, drvae_plan
   if (!a || !out) return set_error("drvae_plan_create: null argument");
   if (n_models < 1) return set_error("drvae_plan_create: n_models must be >= 1");
   if (a->kind < 0 || a->kind > 2) return set_error("drvae_plan_create: unknown model kind");
-  if (a->weight_norm) return set_error("drvae_plan_create: weight_norm=True is not implemented yet (model.wn is False in every shipped configuration)");
   if (a->dim_x < 1 || a->dim_z1 < 1 || a->L < 1 || a->max_batch < 1) return set_error("drvae_plan_create: bad dimensions");
   if (a->dim_z1 > 32 * MAXJ) return set_error("drvae_plan_create: dim_z1 > 256 is not supported");
   if (a->kind != DRVAE_KIND_PVAE && (a->dim_y < 2 || a->dim_y > MAXY)) return set_error("drvae_plan_create: dim_y must be in [2, 8]");
@@ -298,6 +321,7 @@ extern "C" int drvae_plan_create(const drvae_arch_t* a, int n_models, drvae_plan
 
   drvae_plan* pl = new drvae_plan();
   pl->arch = *a;
+  pl->wn = a->weight_norm != 0;
   pl->E = n_models;
   pl->X = a->dim_x;
   pl->Y = (a->kind == DRVAE_KIND_PVAE) ? 1 : a->dim_y;
@@ -336,6 +360,21 @@ extern "C" int drvae_plan_create(const drvae_arch_t* a, int n_models, drvae_plan
     pl->clf_b_off = pl->tensors[b].off;
     add_seg_plain(pl, w);
     add_seg_plain(pl, b);
+    if (pl->wn) {
+      int g = add_tensor(pl, "encoder_y.decoder_p.linear_p.g", Y, 0);
+      add_seg_plain(pl, g);
+      pl->clf_eff_off = pl->derived_elems;
+      pl->derived_elems += round_up(Y * pl->clf_in, 64);
+      for (int n = 0; n < Y; ++n) {
+        WnRow r{};
+        r.w_off = pl->clf_w_off + n * pl->clf_in;
+        r.g_idx = pl->tensors[g].off + n;
+        r.ld = r.kin = pl->clf_in;
+        r.sh_off = -1;
+        r.aux_off = pl->clf_eff_off + (long long)n * pl->clf_in;
+        pl->wn_rows.push_back(r);
+      }
+    }
     r_clf[0] = p0, r_clf[1] = pl->P - p0, p0 = pl->P;
   }
   if (pl->has_fprop) {
@@ -448,6 +487,10 @@ extern "C" int drvae_plan_create(const drvae_arch_t* a, int n_models, drvae_plan
   cudaMemset(pl->dbg, 0, sizeof(DebugWord));
   cudaMalloc(&pl->d_tabs, pl->h_tabs.size() * sizeof(int));
   cudaMemcpy(pl->d_tabs, pl->h_tabs.data(), pl->h_tabs.size() * sizeof(int), cudaMemcpyHostToDevice);
+  if (!pl->wn_rows.empty()) {
+    cudaMalloc(&pl->d_wn_rows, pl->wn_rows.size() * sizeof(WnRow));
+    cudaMemcpy(pl->d_wn_rows, pl->wn_rows.data(), pl->wn_rows.size() * sizeof(WnRow), cudaMemcpyHostToDevice);
+  }
   cudaMalloc(&pl->d_segs, pl->segs.size() * sizeof(Seg));
   cudaMemcpy(pl->d_segs, pl->segs.data(), pl->segs.size() * sizeof(Seg), cudaMemcpyHostToDevice);
   for (auto& pr : pend) *pr.first = c8_of(pl, pr.second);
@@ -536,6 +579,7 @@ extern "C" int drvae_plan_destroy(drvae_plan_t* pl) {
   if (pl->dbg) cudaFree(pl->dbg);
   if (pl->d_segs) cudaFree(pl->d_segs);
   if (pl->d_tabs) cudaFree(pl->d_tabs);
+  if (pl->d_wn_rows) cudaFree(pl->d_wn_rows);
   for (auto& ev : pl->bucket_ev) cudaEventDestroy(ev);
   for (cudaEvent_t ev : {pl->ev_fork, pl->ev_qy, pl->ev_side_fwd, pl->ev_side_bwd})
     if (ev) cudaEventDestroy(ev);
@@ -863,6 +907,8 @@ int fill_view(drvae_plan* pl, Exec& ex, const drvae_batch_t* b, const drvae_nois
   v.eps_z2f = MBuf<const float>{eps + pl->epsl.off_z2f, ems};
   v.eps_z3 = MBuf<const float>{eps + pl->epsl.off_z3, ems};
   v.params = MBuf<float>{pl->params, pl->P};
+  v.clf_w = pl->wn ? MBuf<const float>{pl->derived.p + pl->clf_eff_off, pl->derived.ms}
+                   : MBuf<const float>{pl->params + pl->clf_w_off, pl->P};
   v.grads = MBuf<float>{pl->grads, pl->P};
   v.adam_m = MBuf<float>{pl->adam_m, pl->P};
   v.adam_v = MBuf<float>{pl->adam_v, pl->P};
@@ -906,7 +952,31 @@ int run_adam(drvae_plan* pl, const drvae_hparams_t* hp, int update, cudaStream_t
   pl->launches++;
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return set_cuda_error("adam_kernel", err);
+  if (pl->wn) {
+    // weight-normalised layers: the kernel-facing copies hold g v / ||v||, rebuilt row-wise
+    WnArgs w{pl->d_wn_rows, (int)pl->wn_rows.size(), a.params, a.grads, pl->shadow, pl->derived};
+    prof_pre(pl, st, "opt:wn_refresh");
+    wn_refresh_kernel<<<dim3(cdiv(w.nrows, 8), pl->E), 256, 0, st>>>(w);
+    prof_post(pl, st);
+    pl->launches++;
+    err = cudaGetLastError();
+    if (err != cudaSuccess) return set_cuda_error("wn_refresh_kernel", err);
+  }
   pl->shadows_valid = true;
+  return 0;
+}
+
+// weight norm: effective-weight gradients -> (dv, dg), in place in the gradient buffer
+int run_wn_grad(drvae_plan* pl, cudaStream_t st) {
+  if (!pl->wn) return 0;
+  WnArgs w{pl->d_wn_rows, (int)pl->wn_rows.size(), MBuf<float>{pl->params, pl->P}, MBuf<float>{pl->grads, pl->P}, pl->shadow,
+           pl->derived};
+  prof_pre(pl, st, "opt:wn_grad");
+  wn_grad_kernel<<<dim3(cdiv(w.nrows, 8), pl->E), 256, 0, st>>>(w);
+  prof_post(pl, st);
+  pl->launches++;
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return set_cuda_error("wn_grad_kernel", err);
   return 0;
 }
 
@@ -1017,7 +1087,6 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
     ex.pre("pz1_post");
     pz1_post_kernel<<<rows_grid(round_up(Fb, 128)), ROW_THREADS, 0, ex.st>>>(v);
     ex.chk();
-    if (overlap) cudaEventRecord(pl->ev_side_fwd, side);
     if (backward) {
       ex.phase = "dz1.bwd";
       ex.block_bwd(pl->dz1b, v.dY9, v.Z3b, 0, pl->Z3, v.dZ3.p, v.dZ3.ms, CNT_F, Fb);
@@ -1028,7 +1097,6 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
       ex.phase = "z3.bwd";
       ex.block_bwd(pl->z3b, v.dY7, v.Z1e, 0, pl->Z, v.dZ1e.p, v.dZ1e.ms, CNT_F, Fb);
       cudaEventRecord(pl->bucket_ev[1], ex.st);
-      if (overlap) cudaEventRecord(pl->ev_side_bwd, side);
     }
     on(st);
   }
@@ -1058,7 +1126,10 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
     e.write_dy = backward ? 1 : 0;
     ex.gemm_nt(pl->dec.H.back(), 0, pl->dec.head, EPI_DECLOSS, e, CNT_RD, Rdb);
   }
-  if (overlap) cudaStreamWaitEvent(st, pl->ev_side_fwd, 0);  // the loss reduction reads the side branch's KL rows
+  // The loss reduction is off the backward's critical path: it runs at the tail of the side stream
+  // (after that branch's backward), once the decoder log-density partials of the main stream exist.
+  after(side, pl->ev_side_fwd, st);
+  on(side);
   ex.phase = "";
   ex.pre("loss");
   loss_kernel<<<E, 256, 0, ex.st>>>(v);
@@ -1066,8 +1137,11 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
   if (losses_out && ex.ok()) {
     // losses buffer per model is padded to 256 B in the arena; the caller's is dense [E][8]
     ex.err = cudaMemcpy2DAsync(losses_out, 8 * sizeof(float), v.losses.p, v.losses.ms * sizeof(float), 8 * sizeof(float), E,
-                               cudaMemcpyDeviceToDevice, st);
+                               cudaMemcpyDeviceToDevice, ex.st);
   }
+  if (overlap) cudaEventRecord(pl->ev_side_bwd, side);  // everything the side stream does in this step
+  on(st);
+  if (overlap && !backward) cudaStreamWaitEvent(st, pl->ev_side_bwd, 0);
 
   if (backward && ex.ok()) {
     size_t bk = pl->has_fprop ? 2 : 0;  // buckets 0, 1 (decoder_z1, encoder_z3) were recorded by the side branch
@@ -1120,6 +1194,15 @@ extern "C" int drvae_sync_shadows(drvae_plan_t* pl, void* stream) {
 extern "C" int drvae_train_step(drvae_plan_t* pl, const drvae_batch_t* b, const drvae_noise_t* nz, const drvae_hparams_t* hp,
                                 float* losses_out, void* stream) {
   if (!pl) return set_error("drvae_train_step: null plan");
+  if (pl->wn) {
+    // weight norm: the update acts on (v, g), not on the effective weights the GEMMs produce
+    // gradients for -> materialise the gradient, convert, then run the stand-alone optimizer
+    int rc = run_step(pl, b, nz, hp, losses_out, (cudaStream_t)stream, true, false);
+    if (rc) return rc;
+    rc = run_wn_grad(pl, (cudaStream_t)stream);
+    if (rc) return rc;
+    return run_adam(pl, hp, 1, (cudaStream_t)stream);
+  }
   // forward + ELBO + backward with Adam fused into the gradient epilogues: no gradient buffer
   // traffic and no separate optimizer pass (the bound gradient buffer is left untouched)
   return run_step(pl, b, nz, hp, losses_out, (cudaStream_t)stream, true, true);
@@ -1134,7 +1217,12 @@ extern "C" int drvae_loss_forward(drvae_plan_t* pl, const drvae_batch_t* b, cons
 extern "C" int drvae_grad_step(drvae_plan_t* pl, const drvae_batch_t* b, const drvae_noise_t* nz, const drvae_hparams_t* hp,
                                float* losses_out, void* stream) {
   if (!pl) return set_error("drvae_grad_step: null plan");
-  return run_step(pl, b, nz, hp, losses_out, (cudaStream_t)stream, true, false);
+  int rc = run_step(pl, b, nz, hp, losses_out, (cudaStream_t)stream, true, false);
+  if (rc || !pl->wn) return rc;
+  rc = run_wn_grad(pl, (cudaStream_t)stream);
+  // the conversion rewrites every bucket: bucket events must not fire before it
+  for (auto& ev : pl->bucket_ev) cudaEventRecord(ev, (cudaStream_t)stream);
+  return rc;
 }
 
 extern "C" int drvae_adam_step(drvae_plan_t* pl, const drvae_hparams_t* hp, void* stream) {
@@ -1164,6 +1252,8 @@ extern "C" int drvae_infer(drvae_plan_t* pl, const float* x1, int N, const drvae
   v.eps_x1 = MBuf<const float>{pl->eps_own.p, pl->eps_own.ms};  // never read (training = 0)
   v.eps_x2 = v.eps_x1;
   v.params = MBuf<float>{pl->params, pl->P};
+  v.clf_w = pl->wn ? MBuf<const float>{pl->derived.p + pl->clf_eff_off, pl->derived.ms}
+                   : MBuf<const float>{pl->params + pl->clf_w_off, pl->P};
   v.s.training = 0;
   v.s.add_noise = 0;
   const int E = pl->E;

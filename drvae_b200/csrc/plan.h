@@ -79,6 +79,23 @@ struct Shadow {
   int ilv_block, ilv_stride;
   float bias_const[2];  // constant folded into the derived bias (logvar heads: -2)
   long long tab_off;    // offset of this weight's 3 x rcap gradient-epilogue tables (EpiParams::g_tab)
+  int g_off[2];         // weight norm: flat offsets of the `g` vectors (-1: plain nn.Linear)
+};
+
+// One output row of a weight-normalised layer (layers.WeightNormLinear, reference layers.py:25-41):
+// effective weight row = g[n] / ||v[n, :]|| * v[n, :].  The kernels never see v: the bf16 shadow (and
+// the class-bias / classifier copies) hold the effective row, refreshed by wn_refresh_kernel; the
+// backward converts the effective-weight gradient into (dv, dg) in wn_grad_kernel.
+struct WnRow {
+  int w_off;          // flat offset of v[n][0]
+  int g_idx;          // flat index of g[n]
+  int ld;             // row length (kin + class columns)
+  int kin;            // columns that go through the GEMM
+  long long sh_off;   // bf16 shadow of the layer (-1: classifier row, fp32 copy only)
+  int sh_rcap;
+  int srow;           // shadow row
+  long long aux_off;  // derived fp32: class-bias base of the layer, or the classifier's effective row
+  int aux_ld;
 };
 
 struct MlpBlock {
@@ -156,6 +173,8 @@ struct DevView {
   // parameters
   MBuf<float> params, grads, adam_m, adam_v;
   int clf_w_off, clf_b_off;
+  MBuf<const float> clf_w;  // classifier weights as the kernels read them: the parameters, or the
+                            // effective (weight-normalised) copy in the derived arena
   MBuf<float> losses;  // [8]
   StepScalars s;
 };

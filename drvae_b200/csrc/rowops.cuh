@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(DevView v) {
 // classifier q(y | u): u = [z1, z2f - z1] (DrVAE) or z1 (VFAE).  Warp-cooperative, fp32.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void classifier_row(const DevView& v, int m, int r, int i, int lane) {
-  const float* Wc = v.params.at(m) + v.clf_w_off;
+  const float* Wc = v.clf_w.at(m);
   const float* bc = v.params.at(m) + v.clf_b_off;
   const float* z1 = v.Z1f.at(m) + (long long)r * v.Z;
   const float* z2f = (v.clf_in > v.Z) ? v.Z2Ff.at(m) + (long long)r * v.Z : nullptr;
@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(ROW_THREADS) clf_back_kernel(DevView v) {
     dl[j] = (j < v.Y) ? q[j] * (g[j] - dot) : 0.f;
     if (j < v.Y && lane == 0) v.dlogit.at(m)[(long long)r * v.Y + j] = dl[j];
   }
-  const float* Wc = v.params.at(m) + v.clf_w_off;
+  const float* Wc = v.clf_w.at(m);
   const bool two = v.clf_in > v.Z;
   for (int f = lane; f < v.Z; f += 32) {
     float a = 0.f, b = 0.f;

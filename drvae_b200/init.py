@@ -11,14 +11,18 @@ from collections import OrderedDict
 import torch
 
 
-def init_state_dict(kind, dim_x, dim_y, dim_z1, dim_z3, enc_z1, dec_x, enc_z3=(), dec_z1=(), seed=12345):
+def init_state_dict(kind, dim_x, dim_y, dim_z1, dim_z3, enc_z1, dec_x, enc_z3=(), dec_z1=(), seed=12345, weight_norm=False):
+    """weight_norm=True: every layer except decoder_z2Fz1 is a layers.WeightNormLinear, which adds a `.g`
+    vector initialised to ones without consuming random numbers (reference layers.py:17-23)."""
     torch.manual_seed(seed)
     sd = OrderedDict()
 
-    def lin(name, i, o):
+    def lin(name, i, o, wn=None):
         m = torch.nn.Linear(i, o)
         sd[name + ".weight"] = m.weight.detach().clone()
         sd[name + ".bias"] = m.bias.detach().clone()
+        if weight_norm if wn is None else wn:
+            sd[name + ".g"] = torch.ones(o)
 
     def gauss(prefix, in_dim, hidden, out, second="lv"):
         prev = in_dim
@@ -29,7 +33,7 @@ def init_state_dict(kind, dim_x, dim_y, dim_z1, dim_z3, enc_z1, dec_x, enc_z3=()
         lin("%s.encoder_%s.linear_%s" % (prefix, second, second), prev, out)
 
     def gauss_linear(prefix, z):
-        lin(prefix + ".encoder_lv.linear_lv", z, z)
+        lin(prefix + ".encoder_lv.linear_lv", z, z, wn=False)
         sd[prefix + ".W_mu"] = torch.Tensor(z, z).uniform_(-0.0001, 0.0001)
         sd[prefix + ".bias_mu"] = torch.Tensor(z).uniform_(-0.0001, 0.0001)
 

@@ -26,7 +26,8 @@ TINY = dict(dim_x=40, dim_y=2, dim_z1=12, dim_z3=10, dim_z2=10, enc_z1=[24], dec
             dec_z1=[18])
 DEEP = dict(dim_x=40, dim_y=2, dim_z1=12, dim_z3=10, dim_z2=10, enc_z1=[24, 20], dec_x=[16, 28], enc_z3=[20, 12],
             enc_z2=[20, 12], dec_z1=[18, 14])
-CASES = [("tiny", TINY, 24), ("deep", DEEP, 24), ("readme", README, 150)]
+# (name, architecture, rows, weight_norm)
+CASES = [("tiny", TINY, 24, False), ("deep", DEEP, 24, False), ("readme", README, 150, False), ("tiny_wn", TINY, 24, True)]
 SEED_MODEL, SEED_TAPE, L = 123, 777, 2
 SAMPLE = 257
 
@@ -39,9 +40,20 @@ def main():
     out_dir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(out_dir, exist_ok=True)
     torch.set_num_threads(4)
-    for cname, arch, N in CASES:
+    only = sys.argv[1:]
+    for cname, arch, N, wn in CASES:
+        if only and cname not in only:
+            continue
         for kind in ("drvae", "pvae", "vfae"):
-            model = rh.build_reference_model(kind, arch, seed=SEED_MODEL, L=L)
+            model = rh.build_reference_model(kind, arch, seed=SEED_MODEL, L=L, weight_norm=wn)
+            if wn:
+                # g is initialised to exactly 1 (layers.py:22): perturb it reproducibly so the g/||v|| scale and its
+                # gradient are exercised away from the trivial point
+                gg = torch.Generator().manual_seed(99)
+                with torch.no_grad():
+                    for k, prm in model.named_parameters():
+                        if k.endswith(".g"):
+                            prm.mul_(1.0 + 0.2 * torch.randn(prm.shape, generator=gg))
             sd0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
             batch = orc.synthetic_batch(N, arch["dim_x"])
             cfg = orc.default_cfg(kind, L=L)

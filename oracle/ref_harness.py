@@ -65,8 +65,25 @@ def load_reference():
 
 # constructor arguments of the run_*.py drivers (run_drvae.py:173-185, run_pvae.py:169-179,
 # run_vfae.py:169-180) with the architecture left as parameters
-def build_reference_model(kind, arch, seed=123, L=2, noise=0.01, yloss_rate=1.0, batch_size=150):
+def build_reference_model(kind, arch, seed=123, L=2, noise=0.01, yloss_rate=1.0, batch_size=150, weight_norm=False):
+    """weight_norm=True builds the blocks from layers.WeightNormLinear.  The reference constructors
+    hard-code `self.wn = False` (DrVAE.py:80) before `_build_blocks`, so the flag is flipped by a
+    wrapper around `_build_blocks` for the duration of the construction; no reference code changes."""
     m = load_reference()
+    cls = m[{"drvae": "DrVAE", "pvae": "PVAE", "vfae": "VFAE"}[kind]]
+    orig_build = cls._build_blocks
+    if weight_norm:
+        def _build_wn(self):
+            self.wn = True
+            return orig_build(self)
+        cls._build_blocks = _build_wn
+    try:
+        return _build_reference_model(m, kind, arch, seed, L, noise, yloss_rate, batch_size)
+    finally:
+        cls._build_blocks = orig_build
+
+
+def _build_reference_model(m, kind, arch, seed, L, noise, yloss_rate, batch_size):
     common = dict(type_rec="diag_gaussian", epochs=1, batch_size=batch_size, nonlinearity="elu",
                   learning_rate=0.0005, optim_alg="adam", L=L, weight_decay=0.05, dropout_rate=0.,
                   input_x_dropout=0., add_noise_var=noise, use_MMD=False, kernel_MMD="rbf_fourier",

@@ -17,7 +17,8 @@ ARCH = dict(
     tiny=dict(dim_x=40, dim_y=2, dim_z1=12, dim_z3=10, enc_z1=[24], dec_x=[28], enc_z3=[20], dec_z1=[18]),
     deep=dict(dim_x=40, dim_y=2, dim_z1=12, dim_z3=10, enc_z1=[24, 20], dec_x=[16, 28], enc_z3=[20, 12], dec_z1=[18, 14]),
 )
-NROWS = dict(readme=150, tiny=24, deep=24)
+ARCH["tiny_wn"] = ARCH["tiny"]  # same dims, built from layers.WeightNormLinear (golden recorded with wn=True)
+NROWS = dict(readme=150, tiny=24, deep=24, tiny_wn=24)
 KINDS = ("drvae", "pvae", "vfae")
 SEED_MODEL, SEED_TAPE, L = 123, 777, 2
 

@@ -8,7 +8,7 @@ from helpers import ARCH, KINDS, L, NROWS, SEED_MODEL, SEED_TAPE, golden, orc
 
 from drvae_b200.init import init_state_dict
 
-CASES = ("tiny", "deep", "readme")
+CASES = ("tiny", "deep", "readme", "tiny_wn")
 
 
 def _sd(kind, case, g):

@@ -391,3 +391,53 @@ def test_fused_adam_equals_grad_then_adam(kind, case):
         assert torch.allclose(f[i], s[i], rtol=1e-6, atol=1e-9), name
     assert rel_l2(f[4], s[4]) < 1e-4 and rel_l2(f[5], s[5]) < 1e-6, "shadow / derived copies differ"
     assert torch.allclose(f[0][1], s[0][1], rtol=1e-5, atol=1e-6), "second-step losses differ"
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_weight_norm_parity(kind):
+    """layers.WeightNormLinear (reference layers.py:25-41): parameters (v, g, b), effective weight
+    g v / ||v||.  Golden recorded from the reference built with wn=True and perturbed g."""
+    case = "tiny_wn"
+    g = golden(kind, case)
+    arch, N = ARCH[case], NROWS[case]
+    sd = {k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd/")}
+    assert any(k.endswith(".g") for k in sd)
+    batch = orc.synthetic_batch(N, arch["dim_x"])
+    plan = Plan(kind, L=L, max_batch=N, n_models=1, weight_norm=True, **arch)
+    assert [t[0] for t in plan.tensors] == list(sd.keys())
+    plan.load_state_dict(sd)
+    om = orc.OracleModel(sd, orc.default_cfg(kind, L=L))
+    tape = orc.Tape(seed=SEED_TAPE)
+    lo_emu, g_emu = om.grads(batch, tape, emulate_bf16=True)
+    eps = eps_block_from_tape(plan, tape.log, batch["has_x2"], batch["has_y"], noisy=True)
+    hp = plan.hparams(step=0, beta_pert=anneal_coef(0, 1, 0))
+    got = loss_dict(kind, plan.grad_step(batch_fields(kind, batch), hp, eps=eps))
+    check_losses(got, lo_emu, TOL_EMU_LOSS, "wn vs emulating oracle")
+    ref = {k[len("loss_train0/"):]: float(g[k]) for k in g.files if k.startswith("loss_train0/")}
+    # this tiny model with randomly perturbed g is not a BASELINE config: its KL terms are more sensitive to the
+    # bf16 rounding of the (rescaled) weights than the 1e-3 budget of the shipped configs; the emulating oracle above
+    # holds the kernel logic to 2e-5
+    check_losses(got, ref, 5e-3, "wn vs reference golden")
+    gv = plan.tensor_views(plan.grads, 0)
+    for name, gr in g_emu.items():
+        assert rel_l2(gv[name], gr) <= 2e-2, "wn grad %s relL2 %.3e" % (name, rel_l2(gv[name], gr))
+        gn = float(g["gradnorm0/" + name])
+        assert abs(float(gv[name].double().norm()) - gn) <= 3e-2 * gn + 1e-9, name
+    # optimizer steps act on (v, g, b); the next forward must see the refreshed effective weights
+    for it in range(2):
+        cur = plan.state_dict()
+        o = orc.OracleModel({k: v.cpu() for k, v in cur.items()}, orc.default_cfg(kind, L=L))
+        o.iters = it
+        tape = orc.Tape(seed=SEED_TAPE + 10 + it)
+        lo = o.loss(batch, tape, train=True, emulate_bf16=True)
+        eps = eps_block_from_tape(plan, tape.log, batch["has_x2"], batch["has_y"], noisy=True)
+        got = loss_dict(kind, plan.train_step(batch_fields(kind, batch), plan.hparams(step=it, beta_pert=anneal_coef(it, 1, 0)), eps=eps))
+        check_losses(got, lo, TOL_EMU_LOSS, "wn step %d" % it)
+        new = plan.state_dict()
+        assert all(torch.isfinite(v).all() for v in new.values())
+        assert max((new[k] - cur[k]).abs().max().item() for k in new if k.endswith(".g")) > 0
+    res = plan.infer(batch["x1"])
+    fo = orc.OracleModel({k: v.cpu() for k, v in plan.state_dict().items()}, orc.default_cfg(kind, L=L)).forward(batch["x1"], emulate_bf16=True)
+    assert torch.allclose(res["z1_mu"][0].cpu(), fo["z1"], rtol=1e-3, atol=5e-4)
+    if kind != "pvae":
+        assert torch.allclose(res["proba"][0].cpu(), fo["proba"], rtol=1e-3, atol=2e-4)

@@ -1,0 +1,292 @@
+// Micro-benchmark: how fast can the Adam read-modify-write of p, m, v (fp32) + bf16 shadow stream
+// through HBM under different access patterns?  Informs the layout of the fused dW+Adam epilogue.
+//   nvcc -O3 -gencode arch=compute_100a,code=sm_100a tools/adam_pattern_bench.cu -o gpurun_out/adam_pattern_bench
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+struct H { float lr, b1, b2, eps, wd, isb; };
+__device__ __forceinline__ void upd(float g, float& p, float& m, float& v, const H& h) {
+  float gr = g + h.wd * p;
+  m = h.b1 * m + (1.f - h.b1) * gr;
+  v = h.b2 * v + (1.f - h.b2) * gr * gr;
+  float s;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(s) : "f"(v));
+  p = p - h.lr * __fdividef(m, s * h.isb + h.eps);
+}
+
+// P3: linear float4
+__global__ void k_linear(float4* P, float4* M, float4* V, __nv_bfloat162* S, long long n4, H h) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 p = P[i], m = M[i], v = V[i];
+    upd(1e-3f, p.x, m.x, v.x, h); upd(1e-3f, p.y, m.y, v.y, h); upd(1e-3f, p.z, m.z, v.z, h); upd(1e-3f, p.w, m.w, v.w, h);
+    P[i] = p; M[i] = m; V[i] = v;
+    S[2 * i] = __floats2bfloat162_rn(p.x, p.y); S[2 * i + 1] = __floats2bfloat162_rn(p.z, p.w);
+  }
+}
+
+// P1: tiles [128 k x BN n] of a [rows n][ld] matrix per model; CTA 256 threads: warp w: k quarter w&3, column group w>>2;
+// each thread batches NB columns (loads first, then math, then stores), like the GEMM epilogue.
+template <int NB>
+__global__ void k_tile(float* P, float* M, float* V, __nv_bfloat16* S, int rows, int ld, int BN, int tiles_m, int tiles_n, long long ms, H h,
+                       int m_fast) {
+  int tile_m, tile_n;
+  if (m_fast) { tile_m = blockIdx.x % tiles_m; tile_n = blockIdx.x / tiles_m; } else { tile_n = blockIdx.x % tiles_n; tile_m = blockIdx.x / tiles_n; }
+  const int model = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k = tile_m * 128 + (warp & 3) * 32 + lane;
+  const int cg = warp >> 2;
+  if (k >= ld) return;
+  float* p = P + model * ms + k; float* m = M + model * ms + k; float* v = V + model * ms + k;
+  __nv_bfloat16* s = S + model * ms + k;
+  for (int c = cg * NB; c < BN; c += 2 * NB) {
+    float pv[NB], mv[NB], vv[NB];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      int n = tile_n * BN + c + i;
+      pv[i] = mv[i] = vv[i] = 0.f;
+      if (n < rows) { long long idx = (long long)n * ld; pv[i] = p[idx]; mv[i] = m[idx]; vv[i] = v[idx]; }
+    }
+#pragma unroll
+    for (int i = 0; i < NB; ++i) upd(1e-3f, pv[i], mv[i], vv[i], h);
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+      int n = tile_n * BN + c + i;
+      if (n < rows) { long long idx = (long long)n * ld; p[idx] = pv[i]; m[idx] = mv[i]; v[idx] = vv[i]; s[idx] = __float2bfloat16_rn(pv[i]); }
+    }
+  }
+}
+
+// P1b: same tile pattern under the fused GEMM kernel's occupancy (2 CTAs/SM: 96 KB dynamic smem each), double-buffered
+// register prefetch of 8 columns (what the epilogue does today).
+__global__ void __launch_bounds__(256, 2) k_tile_occ2(float* P, float* M, float* V, __nv_bfloat16* S, int rows, int ld, int BN, int tiles_m,
+                                                      int tiles_n, long long ms, H h) {
+  extern __shared__ float sm[];
+  const int tile_m = blockIdx.x % tiles_m, tile_n = blockIdx.x / tiles_m;
+  const int model = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k = tile_m * 128 + (warp & 3) * 32 + lane;
+  const int cg = warp >> 2;
+  if (k >= ld) return;
+  if (sm[0] == 123.f) return;
+  float* p = P + model * ms + k; float* m = M + model * ms + k; float* v = V + model * ms + k;
+  __nv_bfloat16* s = S + model * ms + k;
+  for (int c = cg * 8; c < BN; c += 16) {
+    float pv[8], mv[8], vv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int n = tile_n * BN + c + i;
+      pv[i] = mv[i] = vv[i] = 0.f;
+      if (n < rows) { long long idx = (long long)n * ld; pv[i] = p[idx]; mv[i] = m[idx]; vv[i] = v[idx]; }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) upd(1e-3f, pv[i], mv[i], vv[i], h);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int n = tile_n * BN + c + i;
+      if (n < rows) { long long idx = (long long)n * ld; p[idx] = pv[i]; m[idx] = mv[i]; v[idx] = vv[i]; s[idx] = __float2bfloat16_rn(pv[i]); }
+    }
+  }
+}
+
+// P1d: persistent-kernel geometry: 1 CTA/SM (200 KB smem), 16 epilogue warps = 4 k-quarters x 4 column groups, NB=8 with
+// double buffering; SHADOW: 0 none, 1 linear bf16, 2 chunk8-scattered bf16 ([k/8][n][k%8], what the GEMMs read)
+template <int SHADOW>
+__global__ void __launch_bounds__(512) k_tile_p16(float* P, float* M, float* V, __nv_bfloat16* S, int rows, int ld, int BN, int tiles_m,
+                                                     int tiles_n, long long ms, H h, int total_tiles, int variant) {
+  extern __shared__ float sm[];
+  if (sm[0] == 123.f) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cg = warp >> 2;
+  for (int tile0 = blockIdx.x; tile0 < total_tiles; tile0 += gridDim.x) {
+    int tile = tile0;
+    if (variant == 2) {  // contiguous tile ranges per CTA instead of strided
+      const int per_cta = (total_tiles + gridDim.x - 1) / gridDim.x;
+      tile = blockIdx.x * per_cta + (tile0 / gridDim.x);
+      if (tile >= total_tiles || (tile0 / (int)gridDim.x) >= per_cta) continue;
+    }
+    const int per = tiles_m * tiles_n;
+    const int model = tile / per, mn = tile % per;
+    int tile_m = mn % tiles_m, tile_n = mn / tiles_m;
+    if (variant == 1) { tile_n = mn % tiles_n; tile_m = mn / tiles_n; }
+    const int k = tile_m * 128 + (warp & 3) * 32 + lane;
+    if (k >= ld) continue;
+    float* p = P + model * ms + k; float* m = M + model * ms + k; float* v = V + model * ms + k;
+    __nv_bfloat16* s = S + model * ms;
+    const int rcap = tiles_n * BN;
+    const int nb = BN / 32;
+    const int rot = (variant == 3) ? (int)(blockIdx.x * 5u) % nb : 0;  // per-CTA rotation of the batch order
+    for (int jb = 0; jb < nb; ++jb) {
+      const int c = cg * 8 + 32 * ((jb + rot) % nb);
+      float pv[8], mv[8], vv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        int n = tile_n * BN + c + i;
+        pv[i] = mv[i] = vv[i] = 0.f;
+        if (n < rows) { long long idx = (long long)n * ld; pv[i] = p[idx]; mv[i] = m[idx]; vv[i] = v[idx]; }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) upd(1e-3f, pv[i], mv[i], vv[i], h);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        int n = tile_n * BN + c + i;
+        if (n < rows) {
+          long long idx = (long long)n * ld; p[idx] = pv[i]; m[idx] = mv[i]; v[idx] = vv[i];
+          if (SHADOW == 1) s[idx + k] = __float2bfloat16_rn(pv[i]);
+          if (SHADOW == 2) s[((long long)(k >> 3) * rcap + n) * 8 + (k & 7)] = __float2bfloat16_rn(pv[i]);
+        }
+      }
+    }
+  }
+}
+
+// P1c: per-thread cp.async (4 B) ring in shared memory, depth R stages of 8 columns x 3 arrays; no registers hold data in
+// flight.  Same 2 CTAs/SM occupancy.
+template <int R>
+__global__ void __launch_bounds__(256, 2) k_tile_cpasync(float* P, float* M, float* V, __nv_bfloat16* S, int rows, int ld, int BN, int tiles_m,
+                                                         int tiles_n, long long ms, H h) {
+  extern __shared__ float sm[];  // [R][24][256]
+  const int tile_m = blockIdx.x % tiles_m, tile_n = blockIdx.x / tiles_m;
+  const int model = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k = tile_m * 128 + (warp & 3) * 32 + lane;
+  const int cg = warp >> 2;
+  if (k >= ld) return;
+  float* p = P + model * ms + k; float* m = M + model * ms + k; float* v = V + model * ms + k;
+  __nv_bfloat16* s = S + model * ms + k;
+  const int nh = (BN / 8 - cg + 1) / 2;  // half-chunks of this group: columns c = (cg + 2 j) * 8
+  auto issue = [&](int j) {
+    if (j < nh) {
+      const int c = (cg + 2 * j) * 8;
+      float* dst = sm + (size_t)(j % R) * 24 * 256 + threadIdx.x;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        int n = tile_n * BN + c + i;
+        if (n < rows) {
+          long long idx = (long long)n * ld;
+          unsigned d0 = (unsigned)__cvta_generic_to_shared(dst + (3 * i + 0) * 256);
+          unsigned d1 = (unsigned)__cvta_generic_to_shared(dst + (3 * i + 1) * 256);
+          unsigned d2 = (unsigned)__cvta_generic_to_shared(dst + (3 * i + 2) * 256);
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d0), "l"(p + idx) : "memory");
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d1), "l"(m + idx) : "memory");
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d2), "l"(v + idx) : "memory");
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  for (int j = 0; j < R - 1; ++j) issue(j);
+  for (int j = 0; j < nh; ++j) {
+    issue(j + R - 1);
+    asm volatile("cp.async.wait_group %0;" ::"n"(R - 1) : "memory");
+    const int c = (cg + 2 * j) * 8;
+    const float* src = sm + (size_t)(j % R) * 24 * 256 + threadIdx.x;
+    float pv[8], mv[8], vv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { pv[i] = src[(3 * i) * 256]; mv[i] = src[(3 * i + 1) * 256]; vv[i] = src[(3 * i + 2) * 256]; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) upd(1e-3f, pv[i], mv[i], vv[i], h);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int n = tile_n * BN + c + i;
+      if (n < rows) { long long idx = (long long)n * ld; p[idx] = pv[i]; m[idx] = mv[i]; v[idx] = vv[i]; s[idx] = __float2bfloat16_rn(pv[i]); }
+    }
+  }
+}
+
+// P2: row-linear: CTA handles RN consecutive rows n, all k; thread t handles k = t, t+256, ... for each row; NB rows batched.
+template <int NB>
+__global__ void k_rows(float* P, float* M, float* V, __nv_bfloat16* S, int rows, int ld, int RN, long long ms, H h) {
+  const int model = blockIdx.y;
+  const int n0 = blockIdx.x * RN;
+  float* p = P + model * ms; float* m = M + model * ms; float* v = V + model * ms;
+  __nv_bfloat16* s = S + model * ms;
+  for (int k = threadIdx.x; k < ld; k += blockDim.x) {
+    for (int c = 0; c < RN; c += NB) {
+      float pv[NB], mv[NB], vv[NB];
+#pragma unroll
+      for (int i = 0; i < NB; ++i) {
+        int n = n0 + c + i;
+        pv[i] = mv[i] = vv[i] = 0.f;
+        if (n < rows) { long long idx = (long long)n * ld + k; pv[i] = p[idx]; mv[i] = m[idx]; vv[i] = v[idx]; }
+      }
+#pragma unroll
+      for (int i = 0; i < NB; ++i) upd(1e-3f, pv[i], mv[i], vv[i], h);
+#pragma unroll
+      for (int i = 0; i < NB; ++i) {
+        int n = n0 + c + i;
+        if (n < rows) { long long idx = (long long)n * ld + k; p[idx] = pv[i]; m[idx] = mv[i]; v[idx] = vv[i]; s[idx] = __float2bfloat16_rn(pv[i]); }
+      }
+    }
+  }
+}
+
+int main() {
+  const int E = 32, rows = 1956, ld = 600;  // decoder heads
+  const long long ms = (long long)rows * ld, total = ms * E;
+  float *P, *M, *V; __nv_bfloat16* S;
+  cudaMalloc(&P, total * 4); cudaMalloc(&M, total * 4); cudaMalloc(&V, total * 4); cudaMalloc(&S, total * 2);
+  cudaMemset(P, 0, total * 4); cudaMemset(M, 0, total * 4); cudaMemset(V, 0, total * 4);
+  H h{5e-4f, 0.9f, 0.999f, 1e-8f, 0.05f, 1.f};
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  auto timeit = [&](const char* name, auto launch) {
+    for (int i = 0; i < 3; ++i) launch();
+    cudaEventRecord(e0);
+    const int R = 10;
+    for (int i = 0; i < R; ++i) launch();
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms_; cudaEventElapsedTime(&ms_, e0, e1); ms_ /= R;
+    cudaError_t err = cudaGetLastError();
+    printf("%-44s %8.1f us  %7.0f GB/s (26 B/param)  %s\n", name, ms_ * 1e3, 26.0 * total / (ms_ * 1e-3) / 1e9, err == cudaSuccess ? "" : cudaGetErrorString(err));
+  };
+  timeit("linear float4, 148*8 CTAs x 256", [&] { k_linear<<<148 * 8, 256>>>((float4*)P, (float4*)M, (float4*)V, (__nv_bfloat162*)S, total / 4, h); });
+  timeit("linear float4, 148*32 CTAs x 256", [&] { k_linear<<<148 * 32, 256>>>((float4*)P, (float4*)M, (float4*)V, (__nv_bfloat162*)S, total / 4, h); });
+  for (int BN : {256, 64}) {
+    int tiles_m = (ld + 127) / 128, tiles_n = (rows + BN - 1) / BN;
+    char nm[128];
+    for (int mf = 0; mf < 2; ++mf) {
+      snprintf(nm, sizeof(nm), "tile 128 x %d, NB=8, m_fast=%d", BN, mf);
+      timeit(nm, [&] { k_tile<8><<<dim3(tiles_m * tiles_n, E), 256>>>(P, M, V, S, rows, ld, BN, tiles_m, tiles_n, ms, h, mf); });
+      snprintf(nm, sizeof(nm), "tile 128 x %d, NB=16, m_fast=%d", BN, mf);
+      timeit(nm, [&] { k_tile<16><<<dim3(tiles_m * tiles_n, E), 256>>>(P, M, V, S, rows, ld, BN, tiles_m, tiles_n, ms, h, mf); });
+    }
+  }
+  {
+    const int BN = 256, tiles_m = (ld + 127) / 128, tiles_n = (rows + BN - 1) / BN;
+    cudaFuncSetAttribute(k_tile_occ2, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304);
+    cudaFuncSetAttribute(k_tile_cpasync<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304);
+    cudaFuncSetAttribute(k_tile_cpasync<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304);
+    cudaFuncSetAttribute(k_tile_cpasync<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304);
+    timeit("tile 128x256 regs NB=8, 2 CTA/SM (96KB smem)", [&] { k_tile_occ2<<<dim3(tiles_m * tiles_n, E), 256, 98304>>>(P, M, V, S, rows, ld, BN, tiles_m, tiles_n, ms, h); });
+    timeit("tile 128x256 cp.async ring R=2, 2 CTA/SM", [&] { k_tile_cpasync<2><<<dim3(tiles_m * tiles_n, E), 256, 98304>>>(P, M, V, S, rows, ld, BN, tiles_m, tiles_n, ms, h); });
+    timeit("tile 128x256 cp.async ring R=3, 2 CTA/SM", [&] { k_tile_cpasync<3><<<dim3(tiles_m * tiles_n, E), 256, 98304>>>(P, M, V, S, rows, ld, BN, tiles_m, tiles_n, ms, h); });
+    timeit("tile 128x256 cp.async ring R=4, 2 CTA/SM", [&] { k_tile_cpasync<4><<<dim3(tiles_m * tiles_n, E), 256, 98304>>>(P, M, V, S, rows, ld, BN, tiles_m, tiles_n, ms, h); });
+  }
+  {
+    const int BN = 256, tiles_m = (ld + 127) / 128, tiles_n = (rows + BN - 1) / BN;
+    const int total_tiles = tiles_m * tiles_n * E;
+    cudaFuncSetAttribute(k_tile_p16<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_tile_p16<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_tile_p16<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    for (int var = 0; var < 4; ++var) {
+      char nm[128];
+      snprintf(nm, sizeof(nm), "persistent 148x16 warps, no shadow, variant %d", var);
+      timeit(nm, [&] { k_tile_p16<0><<<148, 512, 200 * 1024>>>(P, M, V, S, rows, ld, BN, tiles_m, tiles_n, ms, h, total_tiles, var); });
+    }
+    timeit("persistent 148x16 warps, chunk8 shadow, v0", [&] { k_tile_p16<2><<<148, 512, 200 * 1024>>>(P, M, V, S, rows, ld, BN, tiles_m, tiles_n, ms, h, total_tiles, 0); });
+    timeit("p16: grid 1280 (one tile each), 512 thr, 200KB", [&] { k_tile_p16<0><<<1280, 512, 200 * 1024>>>(P, M, V, S, rows, ld, BN, tiles_m, tiles_n, ms, h, total_tiles, 0); });
+    timeit("p16: grid 1280 (one tile each), 512 thr, 96KB", [&] { k_tile_p16<0><<<1280, 512, 98304>>>(P, M, V, S, rows, ld, BN, tiles_m, tiles_n, ms, h, total_tiles, 0); });
+    timeit("p16: grid 296 persistent, 512 thr, 96KB (2/SM)", [&] { k_tile_p16<0><<<296, 512, 98304>>>(P, M, V, S, rows, ld, BN, tiles_m, tiles_n, ms, h, total_tiles, 0); });
+    timeit("p16: grid 148 persistent, 512 thr, 96KB", [&] { k_tile_p16<0><<<148, 512, 98304>>>(P, M, V, S, rows, ld, BN, tiles_m, tiles_n, ms, h, total_tiles, 0); });
+    timeit("p16: grid 640 persistent, 512 thr, 0KB", [&] { k_tile_p16<0><<<640, 512, 0>>>(P, M, V, S, rows, ld, BN, tiles_m, tiles_n, ms, h, total_tiles, 0); });
+  }
+  for (int RN : {16}) {
+    char nm[128];
+    snprintf(nm, sizeof(nm), "rows: %d full rows per CTA, NB=8", RN);
+    timeit(nm, [&] { k_rows<8><<<dim3((rows + RN - 1) / RN, E), 256>>>(P, M, V, S, rows, ld, RN, ms, h); });
+    snprintf(nm, sizeof(nm), "rows: %d full rows per CTA, NB=16", RN);
+    timeit(nm, [&] { k_rows<16><<<dim3((rows + RN - 1) / RN, E), 256>>>(P, M, V, S, rows, ld, RN, ms, h); });
+  }
+  return 0;
+}

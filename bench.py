@@ -42,6 +42,17 @@ def measured_peaks():
         return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, which="fallback")
 
 
+def ncu_traffic(kernel_tag):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel_tag`, from the committed
+    `ncu --set full` capture of this workload (profiles/ncu_traffic.json names the source report)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f)["kernels"].get(kernel_tag)
+        return None if t is None else {"bytes_per_launch": t["dram_read_bytes"] + t["dram_write_bytes"], "source": t["source"]}
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------
 # clocks
 # ------------------------------------------------------------------------------------------------
@@ -241,13 +252,28 @@ def main():
     launches = plan.launch_count() - l0
     samples = world * M * BATCH * args.steps
     value = samples / (ms / 1e3)
-    # ---- end-to-end through the public API: pinned host batch -> H2D -> step -> loss D2H ----
-    for _ in range(2):
-        float(plan.train_step(host, hp(), seed=rank).cpu()[0, 6])
+    # ---- end-to-end through the public API: pinned host batch -> H2D -> step -> loss D2H, every step ----
+    # The user-facing loop (drvae_b200.feed.DeviceFeeder + Plan.train_step): batch i+1 is copied from pinned
+    # memory on a copy stream while step i runs; every step ends with a device->host read of its losses.
+    from drvae_b200.feed import DeviceFeeder
+    feeder = DeviceFeeder(dev)
+
+    def e2e_loop(n):
+        feeder.put(host)
+        out = None
+        for i in range(n):
+            if i + 1 < n:
+                feeder.put(host)
+            b, slot = feeder.get()
+            res = plan.train_step(b, hp(), seed=rank)
+            feeder.done(slot)
+            out = res.cpu()  # D2H of the step's loss terms (synchronises the step)
+        return out
+
+    e2e_loop(3)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        losses = plan.train_step(host, hp(), seed=rank).cpu()
+    losses = e2e_loop(args.steps)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     sampler.stop_flag = True
@@ -293,7 +319,7 @@ def main():
     roofline = None
     if top is not None:
         roofline = {"kernel": top["kernel"], "bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"],
-                    "unit": top["unit"], "frac": top["frac"], "traffic": None, "share_of_step": top["share"],
+                    "unit": top["unit"], "frac": top["frac"], "traffic": ncu_traffic(top["kernel"]), "share_of_step": top["share"],
                     "peak_source": "%s (MEASURED_PEAKS.json %s)" % (peaks["which"], "hbm_gbs" if top["bound"] == "hbm" else "bf16_tflops_sustained")}
     step_flops = sum(2.0 * a * b * c for a, b, c in dims.values())
     line = {

@@ -5,7 +5,6 @@
 // watchdog that turns a would-be hang into a trapped, reported error.
 #pragma once
 
-#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -98,22 +97,6 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
           smem_u32(smem_dst)),
       "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
-}
-
-// 4-D tiled TMA load (cp.async.bulk.tensor): one instruction moves a whole operand tile of a chunk8
-// buffer — box {8 features, rows, chunks, 1 model} — into shared memory in (chunk, row, 8) order,
-// which IS the no-swizzle UMMA canonical layout; out-of-bounds rows / chunks arrive as zeros and
-// count towards the transaction bytes.
-__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, int c2, int c3,
-                                            uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
-          smem_u32(smem_dst)),
-      "l"(reinterpret_cast<unsigned long long>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
-      : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<unsigned long long>(tmap)) : "memory");
 }
 
 // L2 prefetch of the cache line holding `p` (per-lane address, no destination register).  Used to
@@ -267,6 +250,40 @@ __device__ __forceinline__ void adam_update(float g, float& p, float& m, float& 
   float s;
   asm("sqrt.approx.f32 %0, %1;" : "=f"(s) : "f"(v));
   p = p - h.lr_bc1 * __fdividef(m, s * h.inv_sqrt_bc2 + h.eps);
+}
+
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0;
+    c[1] = n1;
+    c[2] = n2;
+    c[3] = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+
+// Four standard normals keyed by (seed, step, model, draw kind `seg`, MC sample l, GLOBAL row, quad q of the
+// row): Philox4x32-10 + Box-Muller with the hardware approximations (noise: ~1e-6 absolute error is
+// irrelevant); the clamp keeps -2 log(u) non-negative when u rounds to 1.
+__device__ __forceinline__ void philox_normal4(unsigned long long seed, unsigned int step, int model, int seg, int l,
+                                               unsigned long long grow, int q, float (&z)[4]) {
+  uint32_t c[4] = {(uint32_t)q | ((uint32_t)(grow >> 32) << 24), (uint32_t)grow, step,
+                   (uint32_t)model | ((uint32_t)seg << 20) | ((uint32_t)l << 24)};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  const float k = 2.3283064365386963e-10f;  // 2^-32
+  const float u0 = (c[0] + 1.0f) * k, u1 = c[1] * k, u2 = (c[2] + 1.0f) * k, u3 = c[3] * k;
+  float r0, r1;
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r0) : "f"(fmaxf(-2.f * __logf(fminf(u0, 1.f)), 0.f)));
+  asm("sqrt.approx.f32 %0, %1;" : "=f"(r1) : "f"(fmaxf(-2.f * __logf(fminf(u2, 1.f)), 0.f)));
+  float s0, c0, s1, c1;
+  __sincosf(6.283185307179586f * u1, &s0, &c0);
+  __sincosf(6.283185307179586f * u3, &s1, &c1);
+  z[0] = r0 * c0, z[1] = r0 * s0, z[2] = r1 * c1, z[3] = r1 * s1;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

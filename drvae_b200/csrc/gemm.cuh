@@ -22,9 +22,6 @@
 // validation reference for the tensor-core mainloop (tests only; never selected implicitly).
 #pragma once
 
-#include <map>
-#include <mutex>
-
 #include "common.cuh"
 
 namespace drvae {
@@ -49,8 +46,9 @@ constexpr int GEMM_MAX_STAGES = 8;
 constexpr int GEMM_A_STAGE_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
 constexpr int GEMM_EPI_WARPS = 16;                     // epilogue warps of the persistent kernel
 constexpr int EPI_GROUPS = GEMM_EPI_WARPS / 4;         // column groups: a warp reads TMEM lanes 32*(warp%4).., columns of its group
-constexpr int GEMM_PROD_WARPS = 3;                     // warp 0 = TMA producer; warps 1, 2 spare
-constexpr int GEMM_MMA_WARP = GEMM_PROD_WARPS;         // warp 3 MMA issuer, warps 4..19 epilogue
+constexpr int GEMM_PROD_WARPS = 3;                     // producer warps: a bulk copy is issued from uniform registers, one
+                                                       // lane at a time, so the 16..48 copies of a k-block are spread over 3 warps
+constexpr int GEMM_MMA_WARP = GEMM_PROD_WARPS;         // warps 0..2 producers, warp 3 MMA issuer, warps 4..19 epilogue
 constexpr int GEMM_EPI_WARP0 = GEMM_PROD_WARPS + 1;
 constexpr int GEMM_THREADS = (GEMM_PROD_WARPS + 1 + GEMM_EPI_WARPS) * 32;
 constexpr int GEMM_SIMT_THREADS = 128 * EPI_GROUPS;    // validation kernel: thread = (row, column group)
@@ -66,10 +64,6 @@ struct GemmOperand {
 };
 
 struct GemmProblem {
-  // TMA descriptors of the A and B operand buffers (box = one k-block tile of this problem); filled
-  // by gemm_launch_t from a per-process cache
-  alignas(64) CUtensorMap tmA;
-  alignas(64) CUtensorMap tmB;
   GemmOperand A, B;
   int mode;
   int M, N, K;      // static upper bounds of D rows / D cols / contraction length
@@ -649,15 +643,14 @@ __device__ __forceinline__ void adam_epilogue_row(const GemmProblem& p, const Ep
 
 // ---------------------------------------------------------------------------------------------
 // Tensor-core kernel: persistent (one CTA per SM, tiles strided by gridDim.x) and warp-specialised.
-//   warp 0        TMA producer (lane 0): operand tiles -> shared-memory ring (full/empty mbarriers);
-//                 warps 1, 2 idle (keep the epilogue warps aligned to TMEM lane quarters)
+//   warps 0..2    bulk-copy producers: operand slabs -> shared-memory ring (full/empty mbarriers)
 //   warp 3        lane 0 issues tcgen05.mma into one of two TMEM accumulator tiles; owns TMEM
 //   warps 4..19   epilogue: warp w reads TMEM lanes [32(w%4), +32), columns of group (w-4)/4
 // The accumulator is double-buffered (acc_full / acc_empty mbarriers), so the epilogue of tile i —
 // for the weight gradients a long HBM-bound Adam stream — overlaps the mainloop of tile i+1.
 // ---------------------------------------------------------------------------------------------
 template <int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmProblem p, const EpiParams e) {
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmProblem p, const EpiParams e) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[GEMM_MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[GEMM_MAX_STAGES];
@@ -697,31 +690,72 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   const bool a_mn = (p.mode == GEMM_DW);
   const bool b_mn = (p.mode != GEMM_NT);
 
-  if (warp == 0) {
-    // ===================== producer: one TMA tile load per operand and k-block =====================
-    if (lane == 0) {
-      tma_prefetch_desc(&p.tmA);
-      tma_prefetch_desc(&p.tmB);
-      const uint32_t tx_bytes = GEMM_A_STAGE_BYTES + b_stage_bytes;  // full boxes (out-of-bounds parts are zero-filled)
-      uint32_t it = 0;  // k-blocks issued by this CTA so far (ring position)
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileInfo t = gemm_tile_info(p, tile);
-        if (!t.active) continue;
-        for (int kb = t.kb_begin; kb < t.kb_end; ++kb, ++it) {
-          const int s = it % p.nstages;
-          const uint32_t ph = (it / p.nstages) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1, p.dbg, 0xE0000000u | kb);
-          uint8_t* As = smem + (size_t)s * stage_bytes;
-          uint8_t* Bs = As + GEMM_A_STAGE_BYTES;
-          mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
-          if (!a_mn)  // K-major: box {8, 128 rows, 8 feature chunks}
-            tma_load_4d(As, &p.tmA, 0, p.A.row0 + t.m0, kb * (GEMM_BK / 8), t.model, &full_bar[s]);
-          else        // MN-major: box {8, 64 contraction rows, 16 feature chunks}
-            tma_load_4d(As, &p.tmA, 0, p.A.row0 + kb * GEMM_BK, t.m0 >> 3, t.model, &full_bar[s]);
-          if (!b_mn)  // box {8, BN rows, 8 feature chunks}
-            tma_load_4d(Bs, &p.tmB, 0, p.B.row0 + t.n0, kb * (GEMM_BK / 8), t.model, &full_bar[s]);
-          else        // box {8, 64 contraction rows, BN / 8 feature chunks}
-            tma_load_4d(Bs, &p.tmB, 0, p.B.row0 + kb * GEMM_BK, t.n0 >> 3, t.model, &full_bar[s]);
+  if (warp < GEMM_PROD_WARPS) {
+    // ===================== producers: 1-D bulk copies of operand slabs =====================
+    // Every producer warp walks the same ring; warp 0 posts the expected byte count, each warp
+    // issues its share of the copies (the transaction count may run ahead of the expectation:
+    // the phase cannot complete before warp 0's arrival).
+    uint32_t it = 0;  // k-blocks issued by this CTA so far (ring position)
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileInfo t = gemm_tile_info(p, tile);
+      if (!t.active) continue;
+      const bf16* Ab = p.A.base + t.model * p.A.model_stride;
+      const bf16* Bb = p.B.base + t.model * p.B.model_stride;
+      for (int kb = t.kb_begin; kb < t.kb_end; ++kb, ++it) {
+        const int s = it % p.nstages;
+        const uint32_t ph = (it / p.nstages) & 1;
+        if (lane == 0) mbar_wait(&empty_bar[s], ph ^ 1, p.dbg, 0xE0000000u | kb);
+        __syncwarp();
+        const int kw = min(GEMM_BK, t.Kc - kb * GEMM_BK);  // multiple of 16
+        uint8_t* As = smem + (size_t)s * stage_bytes;
+        uint8_t* Bs = As + GEMM_A_STAGE_BYTES;
+        // --- copy descriptors ---
+        int nA, nB;
+        uint32_t bytesA, bytesB;
+        if (!a_mn) {
+          nA = kw >> 3;
+          bytesA = GEMM_BM * 16;
+        } else {
+          nA = min(GEMM_BM >> 3, p.A.nchunks - (t.m0 >> 3));
+          bytesA = kw * 16;
+        }
+        if (!b_mn) {
+          nB = kw >> 3;
+          bytesB = BN * 16;
+        } else {
+          nB = min(BN >> 3, p.B.nchunks - (t.n0 >> 3));
+          bytesB = kw * 16;
+        }
+        if (nA < 0) nA = 0;
+        if (nB < 0) nB = 0;
+        if (warp == 0 && lane == 0) mbar_arrive_expect_tx(&full_bar[s], nA * bytesA + nB * bytesB);
+        __syncwarp();
+        // a bulk copy is issued from uniform registers, one lane at a time: spread the copies over the producer warps
+        for (int c = warp + GEMM_PROD_WARPS * lane; c < nA + nB; c += 32 * GEMM_PROD_WARPS) {
+          if (c < nA) {
+            const bf16* src;
+            uint8_t* dst;
+            if (!a_mn) {
+              src = Ab + ((long long)(kb * 8 + c) * p.A.rcap + p.A.row0 + t.m0) * 8;
+              dst = As + (size_t)c * (GEMM_BM * 16);
+            } else {
+              src = Ab + ((long long)((t.m0 >> 3) + c) * p.A.rcap + p.A.row0 + kb * GEMM_BK) * 8;
+              dst = As + (size_t)c * (GEMM_BK * 16);
+            }
+            bulk_g2s(dst, src, bytesA, &full_bar[s]);
+          } else {
+            const int cb = c - nA;
+            const bf16* src;
+            uint8_t* dst;
+            if (!b_mn) {
+              src = Bb + ((long long)(kb * 8 + cb) * p.B.rcap + p.B.row0 + t.n0) * 8;
+              dst = Bs + (size_t)cb * (BN * 16);
+            } else {
+              src = Bb + ((long long)((t.n0 >> 3) + cb) * p.B.rcap + p.B.row0 + kb * GEMM_BK) * 8;
+              dst = Bs + (size_t)cb * (GEMM_BK * 16);
+            }
+            bulk_g2s(dst, src, bytesB, &full_bar[s]);
+          }
         }
       }
     }
@@ -787,7 +821,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       __syncwarp();
       ++j;
     }
-  } else {
+  } else if (warp >= GEMM_EPI_WARP0) {
     // ===================== epilogue: TMEM -> registers -> fused math -> HBM =====================
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
     const int cg = (warp - GEMM_EPI_WARP0) >> 2;  // column group
@@ -895,64 +929,6 @@ inline int gemm_pick_stages(int BN) {
   return s;
 }
 
-// ---- TMA descriptors -------------------------------------------------------------------------
-// A chunk8 buffer [nchunks][rcap][8] bf16 per model is described to the TMA unit as a 4-D tensor
-// {8, rcap, nchunks, models}; the box is the k-block tile of the operand's role in this problem.
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-inline PFN_encodeTiled gemm_encode_fn() {
-  static PFN_encodeTiled fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = (PFN_encodeTiled)p;
-  }
-  return fn;
-}
-
-struct TmapKey {
-  const void* base;
-  long long ms;
-  int rcap, nchunks, models, box_rows, box_chunks;
-  bool operator<(const TmapKey& o) const {
-    if (base != o.base) return base < o.base;
-    if (ms != o.ms) return ms < o.ms;
-    if (rcap != o.rcap) return rcap < o.rcap;
-    if (nchunks != o.nchunks) return nchunks < o.nchunks;
-    if (models != o.models) return models < o.models;
-    if (box_rows != o.box_rows) return box_rows < o.box_rows;
-    return box_chunks < o.box_chunks;
-  }
-};
-
-inline cudaError_t gemm_get_tmap(const GemmOperand& op, int models, int box_rows, int box_chunks, CUtensorMap* out) {
-  static std::map<TmapKey, CUtensorMap> cache;
-  static std::mutex mu;
-  TmapKey key{op.base, op.model_stride, op.rcap, op.nchunks, models, box_rows, box_chunks};
-  std::lock_guard<std::mutex> lock(mu);
-  auto it = cache.find(key);
-  if (it == cache.end()) {
-    PFN_encodeTiled enc = gemm_encode_fn();
-    if (!enc) return cudaErrorNotSupported;
-    CUtensorMap m;
-    const cuuint64_t dims[4] = {8, (cuuint64_t)op.rcap, (cuuint64_t)op.nchunks, (cuuint64_t)models};
-    const cuuint64_t strides[3] = {16, (cuuint64_t)op.rcap * 16, (cuuint64_t)(models > 1 ? op.model_stride * 2 : (long long)op.rcap * 16 * op.nchunks)};
-    const cuuint32_t box[4] = {8, (cuuint32_t)box_rows, (cuuint32_t)box_chunks, 1};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<bf16*>(op.base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
-    it = cache.emplace(key, m).first;
-  }
-  *out = it->second;
-  return cudaSuccess;
-}
-
 inline int gemm_num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -982,12 +958,6 @@ inline cudaError_t gemm_launch_t(GemmProblem p, const EpiParams& e, int n_models
         cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BUDGET + 4096);
     if (err != cudaSuccess) return err;
     attr_set = true;
-  }
-  {
-    const bool a_mn = (p.mode == GEMM_DW), b_mn = (p.mode != GEMM_NT);
-    cudaError_t err = gemm_get_tmap(p.A, n_models, a_mn ? GEMM_BK : GEMM_BM, a_mn ? GEMM_BM / 8 : GEMM_BK / 8, &p.tmA);
-    if (err == cudaSuccess) err = gemm_get_tmap(p.B, n_models, b_mn ? GEMM_BK : p.BN, b_mn ? p.BN / 8 : GEMM_BK / 8, &p.tmB);
-    if (err != cudaSuccess) return err;
   }
   const int grid = total < gemm_num_sms() ? total : gemm_num_sms();  // persistent: one CTA per SM
   gemm_tc_kernel<EPI><<<grid, GEMM_THREADS, smem, st>>>(p, e);

@@ -1,7 +1,8 @@
-// Optimizer-side kernels: fused Adam over the flat parameter vector (torch.optim.Adam semantics,
-// SURVEY.md Appendix A.6 / reference DGMMixin.py:31-40, :123) that also refreshes the derived
-// kernel-facing copies (bf16 chunk8 weight shadows, fp32 bias / class-bias vectors), bias
-// gradients as column sums of the stored pre-activation gradients, and the Philox ε generator.
+// Optimizer-side kernels: the stand-alone Adam pass over the flat parameter vector (torch.optim.Adam
+// semantics, SURVEY.md Appendix A.6 / reference DGMMixin.py:31-40, :123; drvae_train_step fuses the
+// same update into the weight-gradient epilogues instead) that also refreshes the derived
+// kernel-facing copies (bf16 chunk8 weight shadows, fp32 bias / class-bias vectors), the
+// weight-norm row kernels, and the Philox ε generator.
 #pragma once
 
 #include "plan.h"
@@ -74,107 +75,6 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamArgs a) {
     }
     if (si < 0 || idx < a.segs[si].off || (si + 1 < a.nseg && idx >= a.segs[si + 1].off)) si = seg_find(a.segs, a.nseg, idx);
     write_derived(a.segs[si], idx, pv, sh, dv);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// bias gradients: column sums of a chunk8 gradient buffer over its valid rows, routed through the
-// shadow-row map to the reference bias tensors; optional per-class sums for the one-hot columns
-// of a class-augmented first layer (d W[:, kin + j] = sum over rows of class j).
-// grid (ceil(nchunks / 4), n_models), block 128 — one warp per 8-feature chunk
-// ---------------------------------------------------------------------------------------------
-struct ColsumArgs {
-  C8Buf src;
-  const int* dyn;
-  int dyn_stride;
-  MBuf<float> grads;
-  int ntens;
-  int b_off[2];
-  int rows_each[2];
-  int ilv_block, ilv_stride;
-  const int* row_cls;  // null: no class columns
-  long long row_cls_ms;
-  int Y;
-  int w_off, ld, kmain;
-};
-
-__global__ void __launch_bounds__(128) colsum_kernel(ColsumArgs a) {
-  const int m = blockIdx.y, lane = threadIdx.x & 31;
-  const int c = blockIdx.x * 4 + (threadIdx.x >> 5);
-  if (c >= (a.src.fcap >> 3)) return;
-  const int rows = a.dyn[(long long)m * a.dyn_stride];
-  const uint4* src = reinterpret_cast<const uint4*>(a.src.at(m)) + (long long)c * a.src.rcap;
-  const int* cls = a.row_cls ? a.row_cls + m * a.row_cls_ms : nullptr;
-  float tot[8];
-  float pc[MAXY][8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) tot[k] = 0.f;
-#pragma unroll
-  for (int j = 0; j < MAXY; ++j)
-#pragma unroll
-    for (int k = 0; k < 8; ++k) pc[j][k] = 0.f;
-  for (int r = lane; r < rows; r += 32) {
-    float f[8];
-    unpack_bf16x8(src[r], f);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) tot[k] += f[k];
-    if (cls) {
-      const int cj = cls[r];
-#pragma unroll
-      for (int j = 0; j < MAXY; ++j)
-        if (j == cj) {
-#pragma unroll
-          for (int k = 0; k < 8; ++k) pc[j][k] += f[k];
-        }
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < 8; ++k) tot[k] = warp_sum(tot[k]);
-  if (cls) {
-#pragma unroll
-    for (int j = 0; j < MAXY; ++j)
-      if (j < a.Y) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) pc[j][k] = warp_sum(pc[j][k]);
-      }
-  }
-  if (lane == 0) {
-    float* g = a.grads.at(m);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int srow = c * 8 + k;
-      const int blk = srow / a.ilv_stride;
-      const int rem = srow - blk * a.ilv_stride;
-      const int which = rem / a.ilv_block;
-      const int n = blk * a.ilv_block + (rem - which * a.ilv_block);
-      if (which < a.ntens && n < a.rows_each[which]) {
-        g[a.b_off[which] + n] = tot[k];
-        if (cls) {
-#pragma unroll
-          for (int j = 0; j < MAXY; ++j)
-            if (j < a.Y) g[a.w_off + (long long)n * a.ld + a.kmain + j] = pc[j][k];
-        }
-      }
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// ε generator: Philox4x32-10 + Box-Muller, 4 normals per thread.
-// counter = (i_lo, i_hi, step, model), key = seed.  grid (ceil(n/1024), n_models), block 256
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
-    const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
-    c[0] = n0;
-    c[1] = n1;
-    c[2] = n2;
-    c[3] = n3;
-    k0 += 0x9E3779B9u;
-    k1 += 0xBB67AE85u;
   }
 }
 
@@ -262,20 +162,8 @@ __global__ void __launch_bounds__(256) philox_normal_kernel(MBuf<float> out, Eps
   const int q = (int)(t - lr * (unsigned)quads);
   const int l = (int)(lr / (unsigned)N), r = (int)(lr - (unsigned)l * (unsigned)N);
   const unsigned long long grow = (unsigned long long)(row_offset + r);
-  uint32_t c[4] = {(uint32_t)q | ((uint32_t)(grow >> 32) << 24), (uint32_t)grow, step,
-                   (uint32_t)m | ((uint32_t)seg << 20) | ((uint32_t)l << 24)};
-  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-  const float k = 2.3283064365386963e-10f;  // 2^-32
-  const float u0 = (c[0] + 1.0f) * k, u1 = c[1] * k, u2 = (c[2] + 1.0f) * k, u3 = c[3] * k;
-  // Box-Muller with the hardware approximations (noise: ~1e-6 absolute error is irrelevant); the clamp keeps
-  // -2 log(u) non-negative when u rounds to 1
-  float r0, r1;
-  asm("sqrt.approx.f32 %0, %1;" : "=f"(r0) : "f"(fmaxf(-2.f * __logf(fminf(u0, 1.f)), 0.f)));
-  asm("sqrt.approx.f32 %0, %1;" : "=f"(r1) : "f"(fmaxf(-2.f * __logf(fminf(u2, 1.f)), 0.f)));
-  float s0, c0, s1, c1;
-  __sincosf(6.283185307179586f * u1, &s0, &c0);
-  __sincosf(6.283185307179586f * u3, &s1, &c1);
-  const float z[4] = {r0 * c0, r0 * s0, r1 * c1, r1 * s1};
+  float z[4];
+  philox_normal4(seed, step, m, seg, l, grow, q, z);
   float* o = out.at(m) + seg_off + ((long long)l * Ncap + r) * inner + q * 4;
   if (!(inner & 1) && !(seg_off & 1)) {  // even rows: 8-byte aligned pairs
     if (q * 4 + 1 < inner) *reinterpret_cast<float2*>(o) = make_float2(z[0], z[1]);

@@ -906,6 +906,10 @@ int fill_view(drvae_plan* pl, Exec& ex, const drvae_batch_t* b, const drvae_nois
   v.eps_z2 = MBuf<const float>{eps + pl->epsl.off_z2, ems};
   v.eps_z2f = MBuf<const float>{eps + pl->epsl.off_z2f, ems};
   v.eps_z3 = MBuf<const float>{eps + pl->epsl.off_z3, ems};
+  v.own_noise = (nz && nz->eps) ? 0 : 1;
+  v.noise_seed = nz ? nz->seed : 0ULL;
+  v.noise_step = (unsigned)hp->step;
+  v.row_offset = nz ? nz->row_offset : 0LL;
   v.params = MBuf<float>{pl->params, pl->P};
   v.clf_w = pl->wn ? MBuf<const float>{pl->derived.p + pl->clf_eff_off, pl->derived.ms}
                    : MBuf<const float>{pl->params + pl->clf_w_off, pl->P};
@@ -1008,7 +1012,8 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
     const long long offs[6] = {el.off_x1, el.off_x2, el.off_z1, el.off_z2, el.off_z2f, el.off_z3};
     const int outer[6] = {1, 1, L, L, L, L};
     const bool noisy = hp->training && hp->add_noise;
-    const int inner[6] = {noisy ? pl->X : 0, (noisy && pl->has_pair) ? pl->X : 0, pl->Z, pl->has_pair ? pl->Z : 0,
+    (void)noisy;  // the input noise (segments 0, 1) is drawn inside prep_kernel with the same keys
+    const int inner[6] = {0, 0, pl->Z, pl->has_pair ? pl->Z : 0,
                           pl->has_T ? pl->Z : 0, pl->has_fprop ? pl->Y * pl->Z3 : 0};
     long long most = 0;
     for (int i = 0; i < 6; ++i) {

@@ -132,6 +132,12 @@ struct DevView {
   MBuf<const int> y, has_x2, has_y;
   // ε (row indexed)
   MBuf<const float> eps_x1, eps_x2, eps_z1, eps_z2, eps_z2f, eps_z3;
+  // own_noise: the input noise of x1 / x2 is drawn inside prep_kernel (same Philox keys as the ε
+  // generator, segments 0 and 1) instead of being written to and read back from the ε block
+  int own_noise;
+  unsigned int noise_step;
+  unsigned long long noise_seed;
+  long long row_offset;
   // row maps
   MBuf<int> counts;   // CNT_*
   MBuf<float> coefs;  // COEF_*

@@ -158,27 +158,38 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(DevView v) {
   {
     const int f0 = blockIdx.y * PREP_SLAB;
     const int fw = min(PREP_SLAB, v.Xc - f0);  // multiple of 16
-    // phase 1: one warp per row, lanes along features
+    // phase 1: one warp per row, each lane 4 consecutive features (one Philox quad) at a time
     for (int rl = warp; rl < PREP_ROWS; rl += PREP_THREADS / 32) {
       const int r = r0 + rl;
       const float* src = nullptr;
       const float* eps = nullptr;
+      int seg = 0, nrow = 0;  // noise keys: draw kind and row inside this model's minibatch
       if (r < N) {
+        nrow = r;
         src = v.x1.at(m) + (long long)r * v.X;
         eps = v.eps_x1.at(m) + (long long)r * v.X;
       } else if (r < R0) {
-        const int i = v.row_of_pair.at(m)[r - N];
-        src = v.x2.at(m) + (long long)i * v.X;
-        eps = v.eps_x2.at(m) + (long long)i * v.X;
+        nrow = v.row_of_pair.at(m)[r - N];
+        seg = 1;
+        src = v.x2.at(m) + (long long)nrow * v.X;
+        eps = v.eps_x2.at(m) + (long long)nrow * v.X;
       }
-      for (int j = lane; j < fw; j += 32) {
-        const int f = f0 + j;
-        float x = 0.f;
+      for (int qd = lane; qd < (fw >> 2); qd += 32) {
+        const int f = f0 + qd * 4;
+        float x[4] = {0.f, 0.f, 0.f, 0.f};
         if (src && f < v.X) {
-          x = src[f];
-          if (noisy) x += v.s.noise_std * eps[f];
+          float z[4] = {0.f, 0.f, 0.f, 0.f};
+          if (noisy && v.own_noise) philox_normal4(v.noise_seed, v.noise_step, m, seg, 0, (unsigned long long)(v.row_offset + nrow), f >> 2, z);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (f + k < v.X) {
+              x[k] = src[f + k];
+              if (noisy) x[k] += v.s.noise_std * (v.own_noise ? z[k] : eps[f + k]);
+            }
+          }
         }
-        tile[rl][j] = x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tile[rl][qd * 4 + k] = x[k];
       }
     }
     __syncthreads();

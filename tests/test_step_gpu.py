@@ -288,7 +288,17 @@ def test_philox_noise_statistics_and_determinism():
     big = {k: torch.stack([v, v]) for k, v in batch_fields(kind, batch).items()}
     l1 = plan.loss_forward(big, plan.hparams(step=3), seed=99).cpu().clone()
     eps, _, _ = plan.debug_buffer("eps")
-    e = eps.cpu().clone()
+    # latent draws live in the eps block; the input noise of x1 / x2 is drawn inside prep_kernel (same generator, never
+    # stored) and is recovered here from the noisy fp32 targets: tgt = x + noise_std * eps
+    e_lat = eps[:, plan.eps_layout.off_z1:].cpu().clone()
+    tg, _, _ = plan.debug_buffer("tgt4")
+    Xc = (arch["dim_x"] + 1 + 15) // 16 * 16
+    R0cap = tg.shape[1] // Xc
+    t = tg.reshape(2, Xc // 4, R0cap, 4).permute(0, 2, 1, 3).reshape(2, R0cap, Xc)[:, :N, :arch["dim_x"]].cpu()
+    e_x = (t - batch["x1"][None]) / 0.01
+    assert not torch.equal(e_x[0], e_x[1])
+    assert abs(float(e_x.mean())) < 0.03 and abs(float(e_x.std()) - 1.0) < 0.03, (float(e_x.mean()), float(e_x.std()))
+    e = e_lat
     l2 = plan.loss_forward(big, plan.hparams(step=3), seed=99).cpu().clone()
     assert torch.equal(l1, l2), "same (seed, step) must give the same noise"
     l3 = plan.loss_forward(big, plan.hparams(step=4), seed=99).cpu().clone()
@@ -441,3 +451,33 @@ def test_weight_norm_parity(kind):
     assert torch.allclose(res["z1_mu"][0].cpu(), fo["z1"], rtol=1e-3, atol=5e-4)
     if kind != "pvae":
         assert torch.allclose(res["proba"][0].cpu(), fo["proba"], rtol=1e-3, atol=2e-4)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_row_shards_with_global_counts_add_up(kind):
+    """Data-parallel contract: a minibatch split into row shards, each given the GLOBAL
+    normalisers and the global index of its first row (Philox noise is keyed by global row), produces additive
+    shares of every loss term and of the gradient — independent of how many shards there are."""
+    from drvae_b200.dp import local_counts, shard_rows
+    arch, N = ARCH["tiny"], 48
+    sd = init_state_dict(kind, seed=SEED_MODEL, **arch)
+    batch = orc.synthetic_batch(N, arch["dim_x"], seed=3)
+    fields = batch_fields(kind, batch)
+    full = Plan(kind, L=L, max_batch=N, n_models=1, **arch)
+    full.load_state_dict(sd)
+    lf = full.grad_step(fields, full.hparams(step=2), seed=1234).cpu().clone()
+    gf = full.grads[0].cpu().clone()
+    counts = local_counts(N, batch.get("has_x2") if kind != "vfae" else None, batch.get("has_y") if kind != "pvae" else None)
+    for world in (2, 3):
+        lsum, gsum = torch.zeros(8), torch.zeros_like(gf)
+        for r in range(world):
+            lo, hi = shard_rows(N, world, r)
+            shard = {k: v[lo:hi].contiguous() for k, v in fields.items()}
+            p = Plan(kind, L=L, max_batch=hi - lo, n_models=1, **arch)
+            p.load_state_dict(sd)
+            l = p.grad_step(shard, p.hparams(step=2, global_counts=counts), seed=1234, row_offset=lo).cpu()
+            lsum += l[0]
+            gsum += p.grads[0].cpu()
+        for i, k in enumerate(LOSS_KEYS):
+            assert abs(float(lsum[i]) - float(lf[0, i])) <= 2e-5 * abs(float(lf[0, i])) + 1e-5, (world, k, float(lsum[i]), float(lf[0, i]))
+        assert rel_l2(gsum, gf) < 2e-3, (world, rel_l2(gsum, gf))

@@ -6,3 +6,4 @@ C ABI in include/drvae_b200.h; there is no CPU fallback.
 """
 from .models import DrVAE, PVAE, VFAE  # noqa: F401
 from .plan import Plan  # noqa: F401
+from .training import DrVAEDataset, VFAEDataset, wrap_in_DrVAEDataset, wrap_in_VFAEDataset  # noqa: F401,E402

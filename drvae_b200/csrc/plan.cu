@@ -683,6 +683,7 @@ struct Exec {
   const char* phase = "";
   std::string sub = "head";  // layer within the current block: h0, h1, ..., head
   bool fused = false;        // Adam inside the gradient epilogues (drvae_train_step)
+  bool splitk = false;       // split-K weight gradients (large minibatches, unfused path)
   bool ok() const { return err == cudaSuccess; }
   // event bracket around one launch when profiling is on
   void pre(const std::string& op) { prof_pre(pl, st, std::string(phase) + ":" + op); }
@@ -764,6 +765,14 @@ struct Exec {
     p.tiles_n = W.tiles_n;
     p.tiles_m = cdiv(W.kaug, GEMM_BM);
     p.ksplit = 1;
+    if (splitk && !fused) {
+      // large minibatch, few weight tiles: split the contraction (rows) so the persistent grid is filled;
+      // partial tiles accumulate with red.global.add into the gradient buffer zeroed at the start of the step
+      const int nkb = cdiv(row_bound, GEMM_BK);
+      const int tiles = p.tiles_m * p.tiles_n * pl->E;
+      int ks = std::min(cdiv(2 * gemm_num_sms(), tiles), nkb / 4);
+      p.ksplit = std::max(1, std::min(ks, 64));
+    }
     EpiParams e = epi_base();
     e.grad = v.grads.p;
     e.grad_ms = v.grads.ms;
@@ -1003,6 +1012,11 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
   DevView& v = ex.v;
   const int E = pl->E, N = ex.N, L = pl->L;
   const int R0b = (pl->has_pair ? 2 : 1) * N, LNb = L * N, Rdb = (pl->has_pair ? 3 : 1) * L * N;
+  ex.splitk = backward && !fused_adam && Rdb >= 2048;
+  if (ex.splitk) {
+    cudaError_t e0 = cudaMemsetAsync(pl->grads, 0, sizeof(float) * (size_t)pl->P * E, st);
+    if (e0 != cudaSuccess) return set_cuda_error("drvae: zeroing the gradient buffer", e0);
+  }
   const int Fb = std::max(1, L * pl->Y * N);
   auto rows_grid = [&](int rows) { return dim3(cdiv(rows, ROW_WARPS), E); };
 
@@ -1205,6 +1219,13 @@ extern "C" int drvae_train_step(drvae_plan_t* pl, const drvae_batch_t* b, const 
     int rc = run_step(pl, b, nz, hp, losses_out, (cudaStream_t)stream, true, false);
     if (rc) return rc;
     rc = run_wn_grad(pl, (cudaStream_t)stream);
+    if (rc) return rc;
+    return run_adam(pl, hp, 1, (cudaStream_t)stream);
+  }
+  if (b && (long long)b->N * pl->L >= 1024 && pl->E < 8) {
+    // one (or a few) models on a large minibatch: the weight gradients need split-K to fill the GPU, which
+    // the fused epilogue cannot do (it needs the complete sum) -> gradient buffer + stand-alone optimizer
+    int rc = run_step(pl, b, nz, hp, losses_out, (cudaStream_t)stream, true, false);
     if (rc) return rc;
     return run_adam(pl, hp, 1, (cudaStream_t)stream);
   }

@@ -223,9 +223,10 @@ class _B200Model(nn.Module):
         self._eps_tape = None
         return eps
 
-    def _losses(self, fn, batch, training):
+    def _losses(self, fn_name, batch, training):
         n = batch['x1'].shape[0]
-        self._ensure_capacity(n)
+        self._ensure_capacity(n)  # may replace self.plan: resolve the entry point afterwards
+        fn = getattr(self.plan, fn_name)
         eps = self._eps_for(batch, training)
         seed = (int(self.random_seed) << 20) ^ 0x5DEECE66D
         out = fn(batch, self._hparams(training), eps=eps, seed=seed)
@@ -238,16 +239,40 @@ class _B200Model(nn.Module):
         batch = self._batch_kwargs(**kwargs)
         if train_mode:
             self.train()
-            losses = self._losses(self.plan.train_step, batch, True)
+            losses = self._losses('train_step', batch, True)
             self.finished_training_iters += 1
         else:
             self.eval()
-            losses = self._losses(self.plan.loss_forward, batch, False)
+            losses = self._losses('loss_forward', batch, False)
         return losses
 
     def _loss_function(self, **kwargs):
         kwargs.pop('s', None)
-        return self._losses(self.plan.loss_forward, self._batch_kwargs(**kwargs), bool(self.training))
+        return self._losses('loss_forward', self._batch_kwargs(**kwargs), bool(self.training))
+
+    # ------------------------------------------------------------------------------------------
+    # training-loop surface (reference fit / evaluate_performance*; see drvae_b200/training.py)
+    def fit(self, train_loader, valid_loader, add_noise=False, verbose=False, early_stop=False,
+            model_filename='best_model.pth'):
+        from . import training
+        return training.fit(self, train_loader, valid_loader, add_noise=add_noise, verbose=verbose,
+                            early_stop=early_stop, model_filename=model_filename)
+
+    def evaluate_performance(self, return_full_data=False, **batch):
+        from . import training
+        return training.evaluate_performance(self, return_full_data=return_full_data, **batch)
+
+    def evaluate_performance_on_dataset(self, ds, return_full_data=False):
+        from . import training
+        return training.evaluate_performance_on_dataset(self, ds, return_full_data=return_full_data)
+
+    def eval_x_reconstruction(self, x, x_rec, x_rec_sigma=None):
+        from . import training
+        return training.eval_x_reconstruction(x, x_rec, x_rec_sigma)
+
+    def eval_y_prediction(self, pred, proba, ylab):
+        from . import training
+        return training.eval_y_prediction(pred, proba, ylab, self.dim_y)
 
     # ------------------------------------------------------------------------------------------
     def _infer(self, x1):

@@ -29,7 +29,7 @@ def test_struct_sizes_match_header_layout():
     # ints/floats only: natural alignment, no padding surprises between C and ctypes
     assert ctypes.sizeof(_lib.Arch) == 4 * (5 + 4 * (1 + _lib.MAX_HIDDEN) + 3)
     assert ctypes.sizeof(_lib.Batch) == 5 * 8 + 8
-    assert ctypes.sizeof(_lib.Noise) == 16
+    assert ctypes.sizeof(_lib.Noise) == 24  # eps pointer, seed, row_offset
     assert ctypes.sizeof(_lib.HParams) == 4 * 17 + 4 * 8
     assert ctypes.sizeof(_lib.EpsLayout) == 7 * 8
     assert ctypes.sizeof(_lib.InferOut) == 10 * 8
@@ -92,3 +92,61 @@ def test_group_indices_partition_rows():
     for kind in KINDS:
         idx = torch.cat([g[0] for g in group_indices(kind, b["has_x2"], b["has_y"])])
         assert sorted(idx.tolist()) == list(range(31))
+
+
+def test_cli_flags_and_defaults_match_the_reference_drivers():
+    """run_drvae.py:248-283 / run_pvae.py:238-266 / run_vfae.py:243-277."""
+    from drvae_b200.cli import build_parser
+    base = ["--modelid", "auto", "--datafile", "synthetic"]
+    a = build_parser("drvae").parse_args(base)
+    assert (a.batch_size, a.L, a.rseed, a.yloss_rate, a.noise_var, a.dim_z1, a.dim_z3) == (200, 1, 12345, 50., 0.01, 50, 50)
+    assert (a.enc_z1, a.dec_x, a.enc_z3, a.dec_z1, a.enc_z2Fz1, a.class_y) == ([200, 200], [200, 200], [200], [200], [], [])
+    assert a.semi_supervised and not a.stopearly and not a.train_w_noise and a.drug == "26" and a.data_mode == "strictC2C"
+    # the README command line (workspace/example-cmd.sh)
+    a = build_parser("drvae").parse_args(base + "--dim-z1 100 --dim-z3 100 --enc-z1 800 --dec-x 600 --enc-z3 200 --dec-z1 200 "
+                                         "--L 2 --batch-size 150 --train-w-noise --stopearly --yloss-rate 1".split())
+    assert (a.dim_z1, a.enc_z1, a.dec_x, a.L, a.batch_size, a.train_w_noise, a.stopearly, a.yloss_rate) == (100, [800], [600], 2, 150, True, True, 1.0)
+    p = build_parser("pvae").parse_args(base)
+    assert p.kl_z2_rate == 1. and not p.with_pairdata_test and not hasattr(p, "yloss_rate")
+    v = build_parser("vfae").parse_args(base)
+    assert (v.dim_z2, v.enc_z2, v.alldata) == (50, [200], False) and not hasattr(v, "pair_data_only")
+
+
+def test_dataset_wrappers_follow_the_reference_layout():
+    """wrap_in_DrVAEDataset (DrVAE.py:907-963): singletons first with a zero x2 and has_x2 = 0, then pairs."""
+    import numpy as np
+    from drvae_b200.training import wrap_in_DrVAEDataset, wrap_in_VFAEDataset
+    sing = dict(x1=np.ones((3, 5), np.float32), y=np.array([0, 1, 0]), has_y=np.array([1, 0, 1]), s=np.zeros(3), cid=np.arange(3))
+    pair = dict(x1=2 * np.ones((2, 5), np.float32), x2=3 * np.ones((2, 5), np.float32), y=np.array([1, 1]), has_y=np.array([1, 1]),
+                s=np.zeros(2), cid=np.arange(3, 5))
+    ds, d = wrap_in_DrVAEDataset(sing, pair)
+    assert len(ds) == 5 and ds.has_x2.tolist() == [0, 0, 0, 1, 1] and ds.has_x2.dtype == torch.int32
+    assert float(ds.x2[:3].abs().sum()) == 0 and float(ds.x2[3:].mean()) == 3
+    x1, x2, s, y, hx, hy = ds[4]
+    assert float(x1[0]) == 2 and int(hx) == 1 and int(hy) == 1
+    ds2, _ = wrap_in_DrVAEDataset(sing, pair, remove_unlabeled=True)
+    assert len(ds2) == 4
+    ds3, _ = wrap_in_DrVAEDataset(sing, pair, concat="pair_only")
+    assert len(ds3) == 2 and ds3.has_x2.tolist() == [1, 1]
+    dv, _ = wrap_in_VFAEDataset(sing, pair, concat="both")
+    assert len(dv) == 5 and len(dv[0]) == 4
+
+
+def test_reconstruction_metrics_match_scipy_and_sklearn():
+    """eval_x_reconstruction (DGMMixin.py:128-158) computed as batched reductions."""
+    import numpy as np
+    import scipy.stats
+    import sklearn.metrics
+    from drvae_b200.training import eval_x_reconstruction
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(17, 40, generator=g)
+    r = x + 0.5 * torch.randn(17, 40, generator=g)
+    sg = 0.3 + torch.rand(17, 40, generator=g)
+    m = eval_x_reconstruction(x, r, sg)
+    xn, rn = x.double().numpy(), r.double().numpy()
+    assert abs(m["rmse"] - np.sqrt(((xn - rn) ** 2).mean())) < 1e-12
+    assert abs(m["r2"] - sklearn.metrics.r2_score(xn, rn, multioutput="variance_weighted")) < 1e-10
+    assert abs(m["pearr"] - np.mean([scipy.stats.pearsonr(xn[i], rn[i])[0] for i in range(17)])) < 1e-10
+    sgn = sg.double().numpy()
+    ll = (-0.5 * (np.log(2 * np.pi) + np.log(sgn ** 2) + (xn - rn) ** 2 / sgn ** 2)).sum(1).mean()
+    assert abs(m["ll"] - ll) < 1e-9

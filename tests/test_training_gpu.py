@@ -1,0 +1,55 @@
+"""GPU: the training-loop surface around the step (reference fit / evaluate_performance / run_*.py drivers)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("kind", ("drvae", "pvae", "vfae"))
+def test_cli_trains_snapshots_reloads_and_reports(kind, tmp_path):
+    from drvae_b200 import cli
+    argv = [kind, "--modelid", "auto", "--datafile", "synthetic:400", "--outdir", str(tmp_path), "--epochs", "3", "--batch-size", "40",
+            "--L", "2", "--dim-z1", "12", "--enc-z1", "24", "--dec-x", "28", "--train-w-noise", "--stopearly", "--rseed", "7"]
+    if kind == "drvae":
+        argv += ["--dim-z3", "10", "--enc-z3", "20", "--dec-z1", "18", "--yloss-rate", "1"]
+    if kind == "vfae":
+        argv += ["--dim-z2", "10", "--enc-z2", "20", "--dec-z1", "18", "--yloss-rate", "1"]
+    res = cli.main(argv)
+    for split in ("train", "valid", "test"):
+        r = res[split]
+        assert np.isfinite(r["x1_rmse"]) and np.isfinite(r["x1_pearr"]) and r["losses"] is not None
+        assert np.isfinite(r["losses"]["CMPL"])
+        if kind != "pvae":
+            assert 0.0 <= r["y_acc"] <= 1.0
+    files = os.listdir(os.path.join(str(tmp_path), "results"))
+    assert len(files) == 1
+    with open(os.path.join(str(tmp_path), "results", files[0])) as f:
+        assert "26" in json.load(f)
+    assert len(os.listdir(os.path.join(str(tmp_path), "models"))) == 1
+
+
+def test_fit_reduces_the_training_loss_and_learns_the_labels():
+    """A few epochs on separable synthetic data: CMPL falls and the classifier beats chance."""
+    from drvae_b200 import DrVAE, wrap_in_DrVAEDataset
+    from drvae_b200.cli import synthetic_data, split
+    sing, pair = synthetic_data(600, dim_x=60, seed=1)
+    tr_s, va_s, _ = split(sing, 1)
+    tr_p, va_p, _ = split(pair, 1)
+    train_ds, _ = wrap_in_DrVAEDataset(tr_s, tr_p)
+    valid_ds, _ = wrap_in_DrVAEDataset(va_s, va_p)
+    model = DrVAE(dim_x=60, dim_s=1, dim_y=2, dim_h_en_z1=[32], dim_h_de_z1=[16], dim_h_en_z2Fz1=[], dim_h_en_z3=[16], dim_h_de_x=[32],
+                  dim_h_clf=[], dim_z1=8, dim_z3=6, type_rec="diag_gaussian", epochs=30, batch_size=60, nonlinearity="elu",
+                  learning_rate=5e-3, L=1, weight_decay=0.0, add_noise_var=0.01, yloss_rate=50., use_MMD=False, pertloss_rate=0.05,
+                  random_seed=3)
+    before, _ = model.evaluate_performance_on_dataset(valid_ds)
+    loader = torch.utils.data.DataLoader(train_ds, batch_size=60, shuffle=True, drop_last=True)
+    vloader = torch.utils.data.DataLoader(valid_ds, batch_size=60)
+    model.fit(loader, vloader, add_noise=True)
+    after, _ = model.evaluate_performance_on_dataset(valid_ds)
+    assert float(after["losses"]["RECL"]) > float(before["losses"]["RECL"]), (float(before["losses"]["RECL"]), float(after["losses"]["RECL"]))
+    assert after["y_auroc"] > 0.65 and after["y_auroc"] > before["y_auroc"], (before["y_auroc"], after["y_auroc"])
+    assert model.finished_training_iters == 30 * len(loader)

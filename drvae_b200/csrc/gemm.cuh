@@ -950,7 +950,7 @@ inline cudaError_t gemm_launch_t(GemmProblem p, const EpiParams& e, int n_models
   p.nstages = gemm_pick_stages(p.BN);
   // weight-gradient tiles have short contractions (batch rows) and a long HBM-bound epilogue whose
   // streaming loads/stores go through L1: a shallow operand ring leaves the rest of the 256 KB as L1
-  if (EPI == EPI_GRAD_ADAM && p.nstages > 3) p.nstages = 3;
+  if (EPI == EPI_GRAD_ADAM && p.nstages > 2) p.nstages = 2;
   size_t smem = (size_t)p.nstages * (GEMM_A_STAGE_BYTES + p.BN * GEMM_BK * 2);
   static bool attr_set = false;
   if (!attr_set) {

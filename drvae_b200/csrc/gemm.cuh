@@ -51,6 +51,8 @@ constexpr int GEMM_PROD_WARPS = 3;                     // producer warps: a bulk
 constexpr int GEMM_MMA_WARP = GEMM_PROD_WARPS;         // warps 0..2 producers, warp 3 MMA issuer, warps 4..19 epilogue
 constexpr int GEMM_EPI_WARP0 = GEMM_PROD_WARPS + 1;
 constexpr int GEMM_THREADS = (GEMM_PROD_WARPS + 1 + GEMM_EPI_WARPS) * 32;
+constexpr int GEMM_ADAM_EPI_WARPS = 24;                // the fused dW+Adam epilogue is an HBM stream whose bandwidth scales with
+                                                       // resident warps (profiles/r01_experiments.md): 24 warps at <= 72 registers
 constexpr int GEMM_SIMT_THREADS = 128 * EPI_GROUPS;    // validation kernel: thread = (row, column group)
 constexpr int GEMM_ACC_STAGES = 2;                     // accumulator tiles in TMEM (epilogue of tile i overlaps mainloop of i+1)
 constexpr int GEMM_SMEM_BUDGET = 208 * 1024;           // operand ring per CTA (one CTA per SM)
@@ -602,13 +604,17 @@ __device__ __forceinline__ void adam_pipe_apply(const EpiParams& e, int model, i
 
 constexpr int ADAM_PREFETCH_DIST = 4;  // half-chunks of optimizer state requested into L2 ahead of their loads
 
+// GROUPS column groups share the tile's half-chunks (8 shadow rows each) round-robin.  With 4 groups
+// (16 epilogue warps, 96 registers) the loads are double-buffered in registers; with more groups
+// (24 warps, 72 registers) each warp keeps one half-chunk in flight and the extra warps provide the
+// memory-level parallelism.
+template <int GROUPS>
 __device__ __forceinline__ void adam_epilogue_row(const GemmProblem& p, const EpiParams& e, const TileInfo& t, int cg, int k,
                                                   uint32_t taddr_row, bool have_acc, uint64_t* acc_bar, uint32_t acc_parity) {
-  const int nchunks = p.BN >> 4;
-  const int nh = 2 * ((nchunks - cg + EPI_GROUPS - 1) / EPI_GROUPS);  // half-chunks of this column group (even)
+  const int nhc = p.BN >> 3;                        // half-chunks in the tile
+  const int nh = (nhc - cg + GROUPS - 1) / GROUPS;  // half-chunks of this column group
   const int kofs = (k < e.g_kin) ? k : (k == e.g_kin ? 0 : k - 1);
-  // tile-local column of half-chunk h
-  auto lcol = [&](int h) { return (cg + (h >> 1) * EPI_GROUPS) * 16 + (h & 1) * 8; };
+  auto lcol = [&](int h) { return (cg + h * GROUPS) * 8; };  // tile-local column of this group's h-th half-chunk
   // L2 prefetch of half-chunk h for the whole warp: lane j < 24 requests the warp's 32-feature
   // (128-byte) segment of array j % 3 (p, m, v) in weight row j / 3 — first and last byte, the
   // segment may straddle two lines — so the later per-thread loads find their lines in L2 instead
@@ -624,20 +630,35 @@ __device__ __forceinline__ void adam_epilogue_row(const GemmProblem& p, const Ep
     prefetch_l2(base);
     prefetch_l2(base + min(32, e.g_kin - k0) - 1);
   };
-  AdamBuf A, B;
-  if (nh > 0) adam_pipe_load(e, t.model, k, kofs, t.n0 + lcol(0), A);
+  if (GROUPS == EPI_GROUPS) {
+    AdamBuf A, B;
+    if (nh > 0) adam_pipe_load(e, t.model, k, kofs, t.n0 + lcol(0), A);
 #pragma unroll
-  for (int d = 1; d <= ADAM_PREFETCH_DIST; ++d) prefetch(d);
-  if (lane == 0) mbar_wait(acc_bar, acc_parity, p.dbg, 0xA0000000u);  // one poller per warp
-  __syncwarp();
-  tc_fence_after();
-  for (int h = 0; h < nh; h += 2) {
-    prefetch(h + 1 + ADAM_PREFETCH_DIST);
-    adam_pipe_load(e, t.model, k, kofs, t.n0 + lcol(h + 1), B);
-    adam_pipe_apply(e, t.model, k, kofs, t.n0 + lcol(h), taddr_row + lcol(h), have_acc, A);
-    prefetch(h + 2 + ADAM_PREFETCH_DIST);
-    if (h + 2 < nh) adam_pipe_load(e, t.model, k, kofs, t.n0 + lcol(h + 2), A);
-    adam_pipe_apply(e, t.model, k, kofs, t.n0 + lcol(h + 1), taddr_row + lcol(h + 1), have_acc, B);
+    for (int d = 1; d <= ADAM_PREFETCH_DIST; ++d) prefetch(d);
+    if (lane == 0) mbar_wait(acc_bar, acc_parity, p.dbg, 0xA0000000u);  // one poller per warp
+    __syncwarp();
+    tc_fence_after();
+    for (int h = 0; h < nh; h += 2) {
+      prefetch(h + 1 + ADAM_PREFETCH_DIST);
+      if (h + 1 < nh) adam_pipe_load(e, t.model, k, kofs, t.n0 + lcol(h + 1), B);
+      adam_pipe_apply(e, t.model, k, kofs, t.n0 + lcol(h), taddr_row + lcol(h), have_acc, A);
+      prefetch(h + 2 + ADAM_PREFETCH_DIST);
+      if (h + 2 < nh) adam_pipe_load(e, t.model, k, kofs, t.n0 + lcol(h + 2), A);
+      if (h + 1 < nh) adam_pipe_apply(e, t.model, k, kofs, t.n0 + lcol(h + 1), taddr_row + lcol(h + 1), have_acc, B);
+    }
+  } else {
+    AdamBuf A;
+    if (nh > 0) adam_pipe_load(e, t.model, k, kofs, t.n0 + lcol(0), A);
+#pragma unroll
+    for (int d = 1; d <= ADAM_PREFETCH_DIST; ++d) prefetch(d);
+    if (lane == 0) mbar_wait(acc_bar, acc_parity, p.dbg, 0xA0000000u);
+    __syncwarp();
+    tc_fence_after();
+    for (int h = 0; h < nh; ++h) {
+      prefetch(h + 1 + ADAM_PREFETCH_DIST);
+      adam_pipe_apply(e, t.model, k, kofs, t.n0 + lcol(h), taddr_row + lcol(h), have_acc, A);
+      if (h + 1 < nh) adam_pipe_load(e, t.model, k, kofs, t.n0 + lcol(h + 1), A);
+    }
   }
 }
 
@@ -649,8 +670,8 @@ __device__ __forceinline__ void adam_epilogue_row(const GemmProblem& p, const Ep
 // The accumulator is double-buffered (acc_full / acc_empty mbarriers), so the epilogue of tile i —
 // for the weight gradients a long HBM-bound Adam stream — overlaps the mainloop of tile i+1.
 // ---------------------------------------------------------------------------------------------
-template <int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmProblem p, const EpiParams e) {
+template <int EPI, int EW>
+__global__ void __launch_bounds__((GEMM_PROD_WARPS + 1 + EW) * 32, 1) gemm_tc_kernel(const GemmProblem p, const EpiParams e) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[GEMM_MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[GEMM_MAX_STAGES];
@@ -674,7 +695,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmProb
     }
     for (int a = 0; a < GEMM_ACC_STAGES; ++a) {
       mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], GEMM_EPI_WARPS);
+      mbar_init(&acc_empty[a], EW);
     }
     mbar_fence_init();
   }
@@ -833,7 +854,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmProb
       const bool have_acc = t.kb_end > t.kb_begin;
       const uint32_t taddr_row = tmem_base + a * ncols + ((uint32_t)(q * 32) << 16);
       if (EPI == EPI_GRAD_ADAM) {
-        adam_epilogue_row(p, e, t, cg, t.m0 + q * 32 + lane, taddr_row, have_acc, &acc_full[a], aph);
+        adam_epilogue_row<EW / 4>(p, e, t, cg, t.m0 + q * 32 + lane, taddr_row, have_acc, &acc_full[a], aph);
       } else {
         if (lane == 0) mbar_wait(&acc_full[a], aph, p.dbg, 0xA0000000u | tile);  // one poller per warp
         __syncwarp();
@@ -952,15 +973,16 @@ inline cudaError_t gemm_launch_t(GemmProblem p, const EpiParams& e, int n_models
   // streaming loads/stores go through L1: a shallow operand ring leaves the rest of the 256 KB as L1
   if (EPI == EPI_GRAD_ADAM && p.nstages > 2) p.nstages = 2;
   size_t smem = (size_t)p.nstages * (GEMM_A_STAGE_BYTES + p.BN * GEMM_BK * 2);
+  constexpr int EW = (EPI == EPI_GRAD_ADAM) ? GEMM_ADAM_EPI_WARPS : GEMM_EPI_WARPS;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t err =
-        cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BUDGET + 4096);
+        cudaFuncSetAttribute(gemm_tc_kernel<EPI, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BUDGET + 4096);
     if (err != cudaSuccess) return err;
     attr_set = true;
   }
   const int grid = total < gemm_num_sms() ? total : gemm_num_sms();  // persistent: one CTA per SM
-  gemm_tc_kernel<EPI><<<grid, GEMM_THREADS, smem, st>>>(p, e);
+  gemm_tc_kernel<EPI, EW><<<grid, (GEMM_PROD_WARPS + 1 + EW) * 32, smem, st>>>(p, e);
   return cudaGetLastError();
 }
 

@@ -92,6 +92,46 @@ __global__ void __launch_bounds__(256, 2) k_tile_occ2(float* P, float* M, float*
 
 // P1d: persistent-kernel geometry: 1 CTA/SM (200 KB smem), 16 epilogue warps = 4 k-quarters x 4 column groups, NB=8 with
 // double buffering; SHADOW: 0 none, 1 linear bf16, 2 chunk8-scattered bf16 ([k/8][n][k%8], what the GEMMs read)
+// P1e: persistent, EW epilogue warps per CTA (EW/4 column groups), register budget set by the thread count
+template <int EW, int NB>
+__global__ void __launch_bounds__(EW * 32 + 128, 1) k_tile_pw(float* P, float* M, float* V, __nv_bfloat16* S, int rows, int ld, int BN,
+                                                              int tiles_m, int tiles_n, long long ms, H h, int total_tiles) {
+  extern __shared__ float sm[];
+  if (sm[0] == 123.f) return;
+  const int warp = (threadIdx.x >> 5) - 4, lane = threadIdx.x & 31;
+  if (warp < 0) return;  // the producer / MMA warps of the real kernel
+  const int cg = warp >> 2, ngroups = EW / 4;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int per = tiles_m * tiles_n;
+    const int model = tile / per, mn = tile % per;
+    const int tile_m = mn % tiles_m, tile_n = mn / tiles_m;
+    const int k = tile_m * 128 + (warp & 3) * 32 + lane;
+    if (k >= ld) continue;
+    float* p = P + model * ms + k; float* m = M + model * ms + k; float* v = V + model * ms + k;
+    __nv_bfloat16* s = S + model * ms;
+    const int rcap = tiles_n * BN;
+    for (int c = cg * NB; c < BN; c += ngroups * NB) {
+      float pv[NB], mv[NB], vv[NB];
+#pragma unroll
+      for (int i = 0; i < NB; ++i) {
+        int n = tile_n * BN + c + i;
+        pv[i] = mv[i] = vv[i] = 0.f;
+        if (n < rows && c + i < BN) { long long idx = (long long)n * ld; pv[i] = p[idx]; mv[i] = m[idx]; vv[i] = v[idx]; }
+      }
+#pragma unroll
+      for (int i = 0; i < NB; ++i) upd(1e-3f, pv[i], mv[i], vv[i], h);
+#pragma unroll
+      for (int i = 0; i < NB; ++i) {
+        int n = tile_n * BN + c + i;
+        if (n < rows && c + i < BN) {
+          long long idx = (long long)n * ld; p[idx] = pv[i]; m[idx] = mv[i]; v[idx] = vv[i];
+          s[((long long)(k >> 3) * rcap + n) * 8 + (k & 7)] = __float2bfloat16_rn(pv[i]);
+        }
+      }
+    }
+  }
+}
+
 template <int SHADOW>
 __global__ void __launch_bounds__(512) k_tile_p16(float* P, float* M, float* V, __nv_bfloat16* S, int rows, int ld, int BN, int tiles_m,
                                                      int tiles_n, long long ms, H h, int total_tiles, int variant) {
@@ -275,6 +315,14 @@ int main() {
       timeit(nm, [&] { k_tile_p16<0><<<148, 512, 200 * 1024>>>(P, M, V, S, rows, ld, BN, tiles_m, tiles_n, ms, h, total_tiles, var); });
     }
     timeit("persistent 148x16 warps, chunk8 shadow, v0", [&] { k_tile_p16<2><<<148, 512, 200 * 1024>>>(P, M, V, S, rows, ld, BN, tiles_m, tiles_n, ms, h, total_tiles, 0); });
+#define PW(EW, NB, SM)                                                                                                  \
+    {                                                                                                                    \
+      cudaFuncSetAttribute(k_tile_pw<EW, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM * 1024);                   \
+      char nm[128];                                                                                                      \
+      snprintf(nm, sizeof(nm), "persistent 148 CTA, %d epi warps, NB=%d, %d KB smem", EW, NB, SM);                       \
+      timeit(nm, [&] { k_tile_pw<EW, NB><<<148, EW * 32 + 128, SM * 1024>>>(P, M, V, S, rows, ld, BN, tiles_m, tiles_n, ms, h, total_tiles); }); \
+    }
+    PW(16, 8, 200) PW(16, 8, 100) PW(20, 8, 100) PW(24, 8, 100) PW(28, 8, 100) PW(28, 4, 100) PW(28, 8, 200) PW(24, 4, 100) PW(16, 16, 100)
     timeit("p16: grid 1280 (one tile each), 512 thr, 200KB", [&] { k_tile_p16<0><<<1280, 512, 200 * 1024>>>(P, M, V, S, rows, ld, BN, tiles_m, tiles_n, ms, h, total_tiles, 0); });
     timeit("p16: grid 1280 (one tile each), 512 thr, 96KB", [&] { k_tile_p16<0><<<1280, 512, 98304>>>(P, M, V, S, rows, ld, BN, tiles_m, tiles_n, ms, h, total_tiles, 0); });
     timeit("p16: grid 296 persistent, 512 thr, 96KB (2/SM)", [&] { k_tile_p16<0><<<296, 512, 98304>>>(P, M, V, S, rows, ld, BN, tiles_m, tiles_n, ms, h, total_tiles, 0); });

@@ -253,6 +253,17 @@ def run_dp8192(args):
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     sampler.stop_flag = True
     sampler.join(timeout=2)
+    dump = os.environ.get("BENCH_BREAKDOWN")
+    if dump and rank == 0:
+        plan.profile_begin()
+        for _ in range(3):
+            runner.step(devb, seed=1, row_offset=lo)
+        prof = plan.profile_end()
+        tot = sum(v[1] for v in prof.values())
+        with open(dump, "w") as f:
+            json.dump({"ms_per_step": ms / args.steps, "profiled_ms_per_step": tot / 3,
+                       "kernels": sorted(({"kernel": k, "ms_per_launch": v[1] / v[0], "share": v[1] / tot} for k, v in prof.items()),
+                                         key=lambda r: -r["share"])}, f, indent=1)
     peaks = measured_peaks()
     flops = 3.106e11  # GEMM FLOPs of one N=8192 DrVAE step (fwd + dX + dW)
     tf = flops / (ms / args.steps * 1e-3) / 1e12

@@ -452,7 +452,8 @@ extern "C" int drvae_plan_create(const drvae_arch_t* a, int n_models, drvae_plan
   BufRec r_dZdec = F32("dZdec", (size_t)Rdcap * Z), r_dZ1T = F32("dZ1T", (size_t)LNcap * Z);
   BufRec r_DZ1 = F32("DZ1", (size_t)LNcap * Z), r_DZ2F = F32("DZ2F", (size_t)LNcap * Z);
   BufRec r_dlogit = F32("dlogit", (size_t)LNcap * Y);
-  BufRec r_clfp = F32("clf_part", (size_t)CLF_SPLITS * Y * (pl->clf_in + 1));
+  BufRec r_clfp = F32("clf_part", (size_t)CLF_SPLITS_MAX * Y * (pl->clf_in + 1));
+  BufRec r_lossp = F32("loss_part", (size_t)LOSS_SLICES_MAX * 8);
   BufRec r_losses = F32("losses", 8);
   // per-block activations
   struct BlkAlloc {
@@ -566,6 +567,7 @@ extern "C" int drvae_plan_create(const drvae_arch_t* a, int n_models, drvae_plan
   v.DZ2F = mbuf_of<float>(pl, r_DZ2F);
   v.dlogit = mbuf_of<float>(pl, r_dlogit);
   v.clf_part = mbuf_of<float>(pl, r_clfp);
+  v.loss_part = mbuf_of<float>(pl, r_lossp);
   v.losses = mbuf_of<float>(pl, r_losses);
   v.clf_w_off = pl->clf_w_off;
   v.clf_b_off = pl->clf_b_off;
@@ -1012,6 +1014,11 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
   DevView& v = ex.v;
   const int E = pl->E, N = ex.N, L = pl->L;
   const int R0b = (pl->has_pair ? 2 : 1) * N, LNb = L * N, Rdb = (pl->has_pair ? 3 : 1) * L * N;
+  // row parallelism of the fixed-order reductions: sized for one wave at ensemble scale, widened for a single
+  // model on a large minibatch
+  // (functions of the row counts only, so an ensemble member sums in the same order as a single-model plan)
+  v.clf_splits = std::max(CLF_SPLITS, std::min(CLF_SPLITS_MAX, cdiv(LNb, 64)));
+  v.loss_slices = std::max(1, std::min(LOSS_SLICES_MAX, cdiv(Rdb, 512)));
   ex.splitk = backward && !fused_adam && Rdb >= 2048;
   if (ex.splitk) {
     cudaError_t e0 = cudaMemsetAsync(pl->grads, 0, sizeof(float) * (size_t)pl->P * E, st);
@@ -1151,7 +1158,10 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
   on(side);
   ex.phase = "";
   ex.pre("loss");
-  loss_kernel<<<E, 256, 0, ex.st>>>(v);
+  loss_partial_kernel<<<dim3(v.loss_slices, E), 256, 0, ex.st>>>(v);
+  ex.chk();
+  ex.pre("loss_final");
+  loss_final_kernel<<<E, 32, 0, ex.st>>>(v);
   ex.chk();
   if (losses_out && ex.ok()) {
     // losses buffer per model is padded to 256 B in the arena; the caller's is dense [E][8]
@@ -1174,7 +1184,7 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
       clf_back_kernel<<<rows_grid(LNb), ROW_THREADS, 0, ex.st>>>(v);
       ex.chk();
       ex.pre("clf_grad_partial");
-      clf_grad_partial_kernel<<<dim3(CLF_SPLITS, E), 256, 0, ex.st>>>(v);
+      clf_grad_partial_kernel<<<dim3(v.clf_splits, E), 256, 0, ex.st>>>(v);
       ex.chk();
       ex.pre("clf_grad_reduce");
       clf_grad_reduce_kernel<<<E, 256, 0, ex.st>>>(v);

@@ -175,7 +175,10 @@ struct DevView {
   MBuf<float> DZ1;     // [LNcap][Z]
   MBuf<float> DZ2F;    // [LNcap][Z]
   MBuf<float> dlogit;  // [LNcap][Y]
-  MBuf<float> clf_part; // [CLF_SPLITS][Y][clf_in + 1]
+  MBuf<float> clf_part; // [clf_splits][Y][clf_in + 1]
+  int clf_splits;
+  MBuf<float> loss_part;  // [loss_slices][8] partial sums of the loss terms
+  int loss_slices;
   // parameters
   MBuf<float> params, grads, adam_m, adam_v;
   int clf_w_off, clf_b_off;
@@ -185,7 +188,9 @@ struct DevView {
   StepScalars s;
 };
 
-constexpr int CLF_SPLITS = 32;
+constexpr int CLF_SPLITS = 32;       // row splits of the classifier weight gradient (ensemble-sized batches)
+constexpr int CLF_SPLITS_MAX = 512;  // ... for large single-model minibatches
+constexpr int LOSS_SLICES_MAX = 64;  // row slices of the loss reduction
 constexpr int MAXY = 8;   // classes
 constexpr int MAXJ = 8;   // latent dim <= 32 * MAXJ
 

@@ -719,7 +719,7 @@ __global__ void __launch_bounds__(256) clf_grad_partial_kernel(DevView v) {
     float acc[MAXY];
 #pragma unroll
     for (int j = 0; j < MAXY; ++j) acc[j] = 0.f;
-    for (int r = split; r < LN; r += CLF_SPLITS) {
+    for (int r = split; r < LN; r += v.clf_splits) {
       float u;
       if (t < v.Z)
         u = v.Z1f.at(m)[(long long)r * v.Z + t];
@@ -744,7 +744,7 @@ __global__ void __launch_bounds__(256) clf_grad_reduce_kernel(DevView v) {
   for (int k = threadIdx.x; k < v.Y * width; k += 256) {
     const int j = k / width, t = k - j * width;
     float s = 0.f;
-    for (int sp = 0; sp < CLF_SPLITS; ++sp) s += v.clf_part.at(m)[((long long)sp * v.Y + j) * width + t];
+    for (int sp = 0; sp < v.clf_splits; ++sp) s += v.clf_part.at(m)[((long long)sp * v.Y + j) * width + t];
     const int idx = (t < v.clf_in) ? v.clf_w_off + j * v.clf_in + t : v.clf_b_off + j;
     if (!v.s.fused_adam) {
       v.grads.at(m)[idx] = s;
@@ -878,14 +878,15 @@ __device__ __forceinline__ float block_sum_256(float x, float* sm) {
   return r;
 }
 
-__global__ void __launch_bounds__(256) loss_kernel(DevView v) {
+// grid (loss_slices, n_models): slice s reduces rows s, s + slices, ... of every per-row term in a fixed order
+__global__ void __launch_bounds__(256) loss_partial_kernel(DevView v) {
   __shared__ float sm[256];
-  const int m = blockIdx.x, t = threadIdx.x;
+  const int m = blockIdx.y, t = threadIdx.x;
+  const int stride = 256 * gridDim.x, first = blockIdx.x * 256 + t;
   const int* cnt = v.counts.at(m);
   const int LN = cnt[CNT_LN], LNp = cnt[CNT_LNP], Rd = cnt[CNT_RD], F = cnt[CNT_F], R0 = cnt[CNT_R0];
-  const float* cf = v.coefs.at(m);
   float a_recl = 0.f, a_pert = 0.f;
-  for (int r = t; r < Rd; r += 256) {
+  for (int r = first; r < Rd; r += stride) {
     float s = 0.f;
     for (int k = 0; k < v.dec_tiles; ++k) s += v.dec_part.at(m)[(long long)k * v.Rdcap + r];
     if (r < LN + LNp)
@@ -894,7 +895,7 @@ __global__ void __launch_bounds__(256) loss_kernel(DevView v) {
       a_pert += s;
   }
   float a_klz2 = 0.f, a_yl = 0.f, a_ycat = 0.f, a_kfp = 0.f, a_klq = 0.f;
-  for (int r = t; r < LN; r += 256) {
+  for (int r = first; r < LN; r += stride) {
     if (v.has_T) a_klz2 += v.klz2_row.at(m)[r];
     if (v.has_clf) {
       a_yl += v.yl_row.at(m)[r];
@@ -902,9 +903,9 @@ __global__ void __launch_bounds__(256) loss_kernel(DevView v) {
     }
   }
   if (v.has_fprop)
-    for (int e = t; e < F; e += 256) a_kfp += v.kfpw_row.at(m)[e];
+    for (int e = first; e < F; e += stride) a_kfp += v.kfpw_row.at(m)[e];
   if (v.kind == KIND_PVAE)
-    for (int r = t; r < R0; r += 256) a_klq += v.klq_row.at(m)[r];
+    for (int r = first; r < R0; r += stride) a_klq += v.klq_row.at(m)[r];
   a_recl = block_sum_256(a_recl, sm);
   a_pert = block_sum_256(a_pert, sm);
   a_klz2 = block_sum_256(a_klz2, sm);
@@ -913,22 +914,34 @@ __global__ void __launch_bounds__(256) loss_kernel(DevView v) {
   a_kfp = block_sum_256(a_kfp, sm);
   a_klq = block_sum_256(a_klq, sm);
   if (t == 0) {
-    const float RECL = cf[COEF_RECL] * a_recl;
-    const float PERT = cf[COEF_PERT_PLAIN] * a_pert;
-    const float KLD = cf[COEF_KLZ2] * a_klz2 + cf[COEF_KLD] * (a_kfp + a_ycat) + cf[COEF_INV_N] * a_klq;
-    const float YL = cf[COEF_YL_PLAIN] * a_yl;
-    const float ELBO = RECL + v.s.beta_pert * v.s.pertloss_rate * PERT - KLD;
-    const float CMPL = -ELBO - v.s.yloss_rate * YL;
-    float* o = v.losses.at(m);
-    o[0] = RECL;
-    o[1] = KLD;
-    o[2] = PERT;
-    o[3] = YL;
-    o[4] = 0.f;
-    o[5] = ELBO;
-    o[6] = CMPL;
-    o[7] = 0.f;
+    float* o = v.loss_part.at(m) + blockIdx.x * 8;
+    o[0] = a_recl, o[1] = a_pert, o[2] = a_klz2, o[3] = a_yl, o[4] = a_ycat, o[5] = a_kfp, o[6] = a_klq, o[7] = 0.f;
   }
+}
+
+// grid n_models, one warp: fixed-order sum of the slices, then the reference's normalisation
+__global__ void __launch_bounds__(32) loss_final_kernel(DevView v) {
+  const int m = blockIdx.x;
+  if (threadIdx.x != 0) return;
+  float a[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int s = 0; s < v.loss_slices; ++s)
+    for (int k = 0; k < 7; ++k) a[k] += v.loss_part.at(m)[s * 8 + k];
+  const float* cf = v.coefs.at(m);
+  const float RECL = cf[COEF_RECL] * a[0];
+  const float PERT = cf[COEF_PERT_PLAIN] * a[1];
+  const float KLD = cf[COEF_KLZ2] * a[2] + cf[COEF_KLD] * (a[5] + a[4]) + cf[COEF_INV_N] * a[6];
+  const float YL = cf[COEF_YL_PLAIN] * a[3];
+  const float ELBO = RECL + v.s.beta_pert * v.s.pertloss_rate * PERT - KLD;
+  const float CMPL = -ELBO - v.s.yloss_rate * YL;
+  float* o = v.losses.at(m);
+  o[0] = RECL;
+  o[1] = KLD;
+  o[2] = PERT;
+  o[3] = YL;
+  o[4] = 0.f;
+  o[5] = ELBO;
+  o[6] = CMPL;
+  o[7] = 0.f;
 }
 
 }  // namespace drvae

@@ -1051,7 +1051,7 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
     ex.chk();
   }
   ex.pre("rowmap");
-  rowmap_kernel<<<E, 256, 0, st>>>(v);
+  rowmap_kernel<<<E, ROWMAP_THREADS, 0, st>>>(v);
   ex.chk();
   ex.pre("prep");
   prep_kernel<<<dim3(round_up(R0b, 128) / PREP_ROWS, cdiv(pl->view.Xc, PREP_SLAB), E), PREP_THREADS, 0, st>>>(v);
@@ -1063,7 +1063,7 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
   ex.gemm_nt(pl->enc.H.back(), 0, pl->enc.head, EPI_STORE_F32, ex.epi_f32(v.Q.p, v.Q.ms, 2 * pl->Z, 2 * pl->Z, &pl->enc.head),
              CNT_R0, R0b);
   ex.pre("sample_q1");
-  sample_q1_kernel<<<rows_grid(N + PAD_ROWS), ROW_THREADS, 0, st>>>(v);
+  sample_q1_kernel<<<rows_grid(N + PAD_WARPS), ROW_THREADS, 0, st>>>(v);
   ex.chk();
   // The label-dependent branch (q(z_top|z1,y) -> p(z1|z_top,y), forward and backward: ~14 small
   // GEMMs + 4 row kernels that leave most SMs idle) is independent of the decoder branch, so it runs
@@ -1102,7 +1102,7 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
   if (pl->has_T) {
     ex.gemm_nt(v.Zdec, 0, pl->Tsh, EPI_STORE_F32, ex.epi_f32(v.PT.p, v.PT.ms, 2 * pl->Z, 2 * pl->Z, &pl->Tsh), CNT_LN, LNb);
     ex.pre("T_post");
-    T_post_kernel<<<rows_grid(N + PAD_ROWS), ROW_THREADS, 0, ex.st>>>(v);
+    T_post_kernel<<<rows_grid(N + PAD_WARPS), ROW_THREADS, 0, ex.st>>>(v);
     ex.chk();
   }
   if (pl->has_fprop) {
@@ -1187,14 +1187,14 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
       clf_grad_partial_kernel<<<dim3(v.clf_splits, E), 256, 0, ex.st>>>(v);
       ex.chk();
       ex.pre("clf_grad_reduce");
-      clf_grad_reduce_kernel<<<E, 256, 0, ex.st>>>(v);
+      clf_grad_reduce_kernel<<<dim3(cdiv(pl->Y * (pl->clf_in + 1), 8), E), 256, 0, ex.st>>>(v);
       ex.chk();
       bucket_done();
     }
     if (pl->has_T) {
       ex.phase = "T.bwd";
       ex.pre("T_back");
-      T_back_kernel<<<rows_grid(N + PAD_ROWS), ROW_THREADS, 0, ex.st>>>(v);
+      T_back_kernel<<<rows_grid(N + PAD_WARPS), ROW_THREADS, 0, ex.st>>>(v);
       ex.chk();
       ex.gemm_dx(v.dYT, pl->Tsh, EPI_STORE_F32, ex.epi_f32(v.dZ1T.p, v.dZ1T.ms, pl->Z, pl->Z, nullptr), CNT_LN, LNb);
       ex.gemm_dw(v.dYT, v.Zdec, 0, pl->Tsh, CNT_LN, LNb);
@@ -1203,7 +1203,7 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
     if (overlap) cudaStreamWaitEvent(st, pl->ev_side_bwd, 0);  // join: q_back sums the side branch's gradients into q(z1|x1)
     ex.phase = "enc.bwd";
     ex.pre("q_back");
-    q_back_kernel<<<rows_grid(N + PAD_ROWS), ROW_THREADS, 0, ex.st>>>(v);
+    q_back_kernel<<<rows_grid(N + PAD_WARPS), ROW_THREADS, 0, ex.st>>>(v);
     ex.chk();
     ex.block_bwd(pl->enc, v.dY2, v.Ain, 0, pl->X, nullptr, 0, CNT_R0, R0b);
     bucket_done();
@@ -1306,7 +1306,7 @@ extern "C" int drvae_infer(drvae_plan_t* pl, const float* x1, int N, const drvae
   ex.gemm_nt(pl->enc.H.back(), 0, pl->enc.head, EPI_STORE_F32, ex.epi_f32(v.Q.p, v.Q.ms, 2 * pl->Z, 2 * pl->Z, &pl->enc.head),
              CNT_R0, N);
   ex.pre("infer_z1");
-  infer_z1_kernel<<<rows_grid(N + PAD_ROWS), ROW_THREADS, 0, st>>>(v, o, rows_dec);
+  infer_z1_kernel<<<rows_grid(N + PAD_WARPS), ROW_THREADS, 0, st>>>(v, o, rows_dec);
   ex.chk();
   if (pl->has_T) {
     ex.gemm_nt(v.Zdec, 0, pl->Tsh, EPI_STORE_F32, ex.epi_f32(v.PT.p, v.PT.ms, 2 * pl->Z, 2 * pl->Z, &pl->Tsh), CNT_LN, N);

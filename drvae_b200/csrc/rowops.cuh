@@ -18,7 +18,8 @@ namespace drvae {
 
 constexpr int ROW_WARPS = 8;            // warps per block in the row kernels
 constexpr int ROW_THREADS = ROW_WARPS * 32;
-constexpr int PAD_ROWS = 128;           // extra "pad duty" warps per launch
+constexpr int PAD_ROWS = 128;           // rows of zero padding kept after the valid rows of a GEMM operand
+constexpr int PAD_WARPS = 16;           // extra "pad duty" warps per launch, each zeroing PAD_ROWS / PAD_WARPS rows
 
 __device__ __forceinline__ void st_c8(bf16* base, int rcap, int row, int f, float v) {
   base[c8_index(row, f, rcap)] = __float2bfloat16_rn(v);
@@ -36,13 +37,44 @@ __device__ __forceinline__ int pad128(int n) { return (n + 127) & ~127; }
 // place and we only record, per row, its pair index, its evaluation slots for _fprop
 // (1 for a labeled row, dim_y for an unlabeled one) and the batch-level normalisers.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) rowmap_kernel(DevView v) {
+constexpr int ROWMAP_THREADS = 1024;
+
+// exclusive prefix sum of one int per thread over the block (warp shuffles + one smem pass); returns the block total in `total`
+__device__ __forceinline__ int block_exclusive_scan(int x, int* warp_tot, int& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  int incl = x;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = lane < nw ? warp_tot[lane] : 0;
+    int wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += y;
+    }
+    warp_tot[lane] = wi - w;  // exclusive prefix of the warp totals
+    if (lane == 31) warp_tot[32] = wi;
+  }
+  __syncthreads();
+  const int res = warp_tot[warp] + incl - x;
+  total = warp_tot[32];
+  __syncthreads();
+  return res;
+}
+
+__global__ void __launch_bounds__(ROWMAP_THREADS) rowmap_kernel(DevView v) {
   const int m = blockIdx.x, t = threadIdx.x, N = v.N;
-  __shared__ int s_np[256], s_ne[256], s_nl[256];
+  __shared__ int s_tot[33];
   const int* hx = v.has_pair ? v.has_x2.at(m) : nullptr;
   const int* hy = (v.has_clf && v.has_y.p) ? v.has_y.at(m) : nullptr;
   const int* yy = (v.has_clf && v.y.p) ? v.y.at(m) : nullptr;
-  const int seg = (N + 255) / 256;
+  const int seg = (N + ROWMAP_THREADS - 1) / ROWMAP_THREADS;
   const int i0 = min(N, t * seg), i1 = min(N, i0 + seg);
   int np = 0, ne = 0, nl = 0;
   for (int i = i0; i < i1; ++i) {
@@ -52,22 +84,11 @@ __global__ void __launch_bounds__(256) rowmap_kernel(DevView v) {
     nl += lb;
     ne += v.has_fprop ? (lb ? 1 : v.Y) : 0;
   }
-  s_np[t] = np;
-  s_ne[t] = ne;
-  s_nl[t] = nl;
-  __syncthreads();
+  int Np, Fl, Nlab;
+  int p = block_exclusive_scan(np, s_tot, Np);
+  int e = block_exclusive_scan(ne, s_tot, Fl);
+  (void)block_exclusive_scan(nl, s_tot, Nlab);
   if (t == 0) {
-    int a = 0, b = 0, c = 0;
-    for (int k = 0; k < 256; ++k) {
-      int x = s_np[k];
-      s_np[k] = a;
-      a += x;
-      x = s_ne[k];
-      s_ne[k] = b;
-      b += x;
-      c += s_nl[k];
-    }
-    const int Np = a, Fl = b, Nlab = c;
     int* cnt = v.counts.at(m);
     cnt[CNT_N] = N;
     cnt[CNT_NP] = Np;
@@ -92,8 +113,6 @@ __global__ void __launch_bounds__(256) rowmap_kernel(DevView v) {
     cf[COEF_PERT_PLAIN] = 1.f / (Lf * gNp);
     cf[COEF_YL_PLAIN] = 1.f / (Lf * gNl);
   }
-  __syncthreads();
-  int p = s_np[t], e = s_ne[t];
   int* pair_of = v.pair_of.at(m);
   int* row_of_pair = v.row_of_pair.at(m);
   int* ebase = v.ebase.at(m);
@@ -122,9 +141,8 @@ __global__ void __launch_bounds__(256) rowmap_kernel(DevView v) {
   }
   __syncthreads();
   if (v.has_fprop) {
-    const int Fl = v.counts.at(m)[CNT_FL];
     int* full = v.e_cls_full.at(m);
-    for (int k = t; k < v.L * Fl; k += 256) {
+    for (int k = t; k < v.L * Fl; k += ROWMAP_THREADS) {
       const int el = k % Fl;
       const int i = e_row[el];
       full[k] = lab[i] ? ycls[i] : e_jj[el];
@@ -280,18 +298,20 @@ __device__ __forceinline__ float kl_term(float muq, float lvq, float mup, float 
 // ---------------------------------------------------------------------------------------------
 // sample_q1: after the encoder heads.  Draw z1 (and z2 — from q(z1|x1), as the reference does,
 // DrVAE.py:427) for every MC sample and scatter them to the stacked decoder rows.
-// grid (ceil((Ncap + PAD_ROWS) / ROW_WARPS), n_models)
+// grid (ceil((N + PAD_WARPS) / ROW_WARPS), n_models)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ROW_THREADS) sample_q1_kernel(DevView v) {
+__global__ void __launch_bounds__(ROW_THREADS, 5) sample_q1_kernel(DevView v) {
   const int m = blockIdx.y, lane = threadIdx.x & 31;
   const int i = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int* cnt = v.counts.at(m);
   const int N = cnt[CNT_N], Np = cnt[CNT_NP], LN = cnt[CNT_LN], Fl = cnt[CNT_FL], F = cnt[CNT_F], Rd = cnt[CNT_RD];
   if (i >= N) {
     const int j = i - N;  // pad duty
-    if (j < PAD_ROWS) {
-      if (v.has_fprop && F + j < pad128(F)) zero_c8_row(v.Z1e, m, F + j, lane);
-      if (!v.has_T && Rd + j < pad128(Rd)) zero_c8_row(v.Zdec, m, Rd + j, lane);
+    if (j < PAD_WARPS) {
+      for (int jj = j; jj < PAD_ROWS; jj += PAD_WARPS) {
+        if (v.has_fprop && F + jj < pad128(F)) zero_c8_row(v.Z1e, m, F + jj, lane);
+        if (!v.has_T && Rd + jj < pad128(Rd)) zero_c8_row(v.Zdec, m, Rd + jj, lane);
+      }
     }
     return;
   }
@@ -348,14 +368,16 @@ __global__ void __launch_bounds__(ROW_THREADS) sample_q1_kernel(DevView v) {
 // T_post: after the p(z2|z1) GEMM.  Residual mean, sample z2f, KL(q(z2|x2) || p(z2|z1)) with free
 // bits for pair rows, and the classifier.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ROW_THREADS) T_post_kernel(DevView v) {
+__global__ void __launch_bounds__(ROW_THREADS, 5) T_post_kernel(DevView v) {
   const int m = blockIdx.y, lane = threadIdx.x & 31;
   const int i = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int* cnt = v.counts.at(m);
   const int N = cnt[CNT_N], Np = cnt[CNT_NP], LN = cnt[CNT_LN], LNp = cnt[CNT_LNP], Rd = cnt[CNT_RD];
   if (i >= N) {
     const int j = i - N;
-    if (j < PAD_ROWS && Rd + j < pad128(Rd)) zero_c8_row(v.Zdec, m, Rd + j, lane);
+    if (j < PAD_WARPS)
+      for (int jj = j; jj < PAD_ROWS; jj += PAD_WARPS)
+        if (Rd + jj < pad128(Rd)) zero_c8_row(v.Zdec, m, Rd + jj, lane);
     return;
   }
   const int p = v.pair_of.at(m)[i];
@@ -575,14 +597,16 @@ __global__ void __launch_bounds__(ROW_THREADS) clf_back_kernel(DevView v) {
 // T_back: gradient rows of the p(z2|z1) heads (dYT = [d p_mu | d p_lv]), the KL(q2||p) gradient
 // towards q2 (dQ2) and the residual / classifier contributions to d z1 (DZ1).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ROW_THREADS) T_back_kernel(DevView v) {
+__global__ void __launch_bounds__(ROW_THREADS, 5) T_back_kernel(DevView v) {
   const int m = blockIdx.y, lane = threadIdx.x & 31;
   const int i = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int* cnt = v.counts.at(m);
   const int N = cnt[CNT_N], Np = cnt[CNT_NP], LN = cnt[CNT_LN], LNp = cnt[CNT_LNP];
   if (i >= N) {
     const int j = i - N;
-    if (j < PAD_ROWS && LN + j < pad128(LN)) zero_c8_row(v.dYT, m, LN + j, lane);
+    if (j < PAD_WARPS)
+      for (int jj = j; jj < PAD_ROWS; jj += PAD_WARPS)
+        if (LN + jj < pad128(LN)) zero_c8_row(v.dYT, m, LN + jj, lane);
     return;
   }
   const int p = v.pair_of.at(m)[i];
@@ -640,14 +664,16 @@ __global__ void __launch_bounds__(ROW_THREADS) T_back_kernel(DevView v) {
 // q_back: gradient rows of the encoder heads, dY2 = [d mu | d lv] for q(z1|x1) rows and for
 // q(z2|x2) rows.  Collects every path into z1 / z2 samples and the direct KL gradients.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ROW_THREADS) q_back_kernel(DevView v) {
+__global__ void __launch_bounds__(ROW_THREADS, 5) q_back_kernel(DevView v) {
   const int m = blockIdx.y, lane = threadIdx.x & 31;
   const int i = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int* cnt = v.counts.at(m);
   const int N = cnt[CNT_N], Np = cnt[CNT_NP], LN = cnt[CNT_LN], R0 = cnt[CNT_R0], Fl = cnt[CNT_FL];
   if (i >= N) {
     const int j = i - N;
-    if (j < PAD_ROWS && R0 + j < pad128(R0)) zero_c8_row(v.dY2, m, R0 + j, lane);
+    if (j < PAD_WARPS)
+      for (int jj = j; jj < PAD_ROWS; jj += PAD_WARPS)
+        if (R0 + jj < pad128(R0)) zero_c8_row(v.dY2, m, R0 + jj, lane);
     return;
   }
   const float* q = v.Q.at(m) + (long long)i * 2 * v.Z;
@@ -657,10 +683,7 @@ __global__ void __launch_bounds__(ROW_THREADS) q_back_kernel(DevView v) {
   const bool have_dz1 = v.has_clf || v.has_T;
   bf16* dy = v.dY2.at(m);
   const float cN = v.coefs.at(m)[COEF_INV_N];
-#pragma unroll
-  for (int k = 0; k < MAXJ; ++k) {
-    const int f = lane + 32 * k;
-    if (f >= v.Z) continue;
+  for (int f = lane; f < v.Z; f += 32) {
     const float mu = q[f], lv = q[v.Z + f];
     const float hs = 0.5f * expf(0.5f * lv);
     float amu = 0.f, alv = 0.f;
@@ -738,27 +761,31 @@ __global__ void __launch_bounds__(256) clf_grad_partial_kernel(DevView v) {
   }
 }
 
+// grid (ceil(Y * (clf_in + 1) / 8), n_models), block 256: one warp per gradient element, lanes over the row splits
+// (lane l sums splits l, l + 32, ... in order, then a fixed shuffle tree -> deterministic)
 __global__ void __launch_bounds__(256) clf_grad_reduce_kernel(DevView v) {
-  const int m = blockIdx.x;
+  const int m = blockIdx.y, lane = threadIdx.x & 31;
   const int width = v.clf_in + 1;
-  for (int k = threadIdx.x; k < v.Y * width; k += 256) {
-    const int j = k / width, t = k - j * width;
-    float s = 0.f;
-    for (int sp = 0; sp < v.clf_splits; ++sp) s += v.clf_part.at(m)[((long long)sp * v.Y + j) * width + t];
-    const int idx = (t < v.clf_in) ? v.clf_w_off + j * v.clf_in + t : v.clf_b_off + j;
-    if (!v.s.fused_adam) {
-      v.grads.at(m)[idx] = s;
-    } else {
-      // the classifier runs on the fp32 parameters directly: Adam here, no shadow to refresh
-      float* P = v.params.at(m);
-      float* M1 = v.adam_m.at(m);
-      float* V2 = v.adam_v.at(m);
-      float pv = P[idx], m1 = M1[idx], v1 = V2[idx];
-      adam_update(s, pv, m1, v1, v.s.adam);
-      M1[idx] = m1;
-      V2[idx] = v1;
-      P[idx] = pv;
-    }
+  const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (k >= v.Y * width) return;
+  const int j = k / width, t = k - j * width;
+  float s = 0.f;
+  for (int sp = lane; sp < v.clf_splits; sp += 32) s += v.clf_part.at(m)[((long long)sp * v.Y + j) * width + t];
+  s = warp_sum(s);
+  if (lane != 0) return;
+  const int idx = (t < v.clf_in) ? v.clf_w_off + j * v.clf_in + t : v.clf_b_off + j;
+  if (!v.s.fused_adam) {
+    v.grads.at(m)[idx] = s;
+  } else {
+    // the classifier runs on the fp32 parameters directly: Adam here, no shadow to refresh
+    float* P = v.params.at(m);
+    float* M1 = v.adam_m.at(m);
+    float* V2 = v.adam_v.at(m);
+    float pv = P[idx], m1 = M1[idx], v1 = V2[idx];
+    adam_update(s, pv, m1, v1, v.s.adam);
+    M1[idx] = m1;
+    V2[idx] = v1;
+    P[idx] = pv;
   }
 }
 
@@ -810,7 +837,9 @@ __global__ void __launch_bounds__(ROW_THREADS) infer_z1_kernel(DevView v, InferV
   const int N = v.N;
   if (r >= N) {
     const int j = r - N;
-    if (j < PAD_ROWS && rows_dec + j < pad128(rows_dec)) zero_c8_row(v.Zdec, m, rows_dec + j, lane);
+    if (j < PAD_WARPS)
+      for (int jj = j; jj < PAD_ROWS; jj += PAD_WARPS)
+        if (rows_dec + jj < pad128(rows_dec)) zero_c8_row(v.Zdec, m, rows_dec + jj, lane);
     return;
   }
   const float* q = v.Q.at(m) + (long long)r * 2 * v.Z;

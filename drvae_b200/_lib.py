@@ -62,7 +62,7 @@ EXPORTS = ["drvae_last_error", "drvae_plan_create", "drvae_plan_destroy", "drvae
            "drvae_plan_workspace_bytes", "drvae_plan_bind", "drvae_sync_shadows", "drvae_train_step",
            "drvae_loss_forward", "drvae_grad_step", "drvae_adam_step", "drvae_infer", "drvae_set_gemm_impl",
            "drvae_plan_launch_count", "drvae_debug_buffer", "drvae_debug_gemm", "drvae_profile_begin",
-           "drvae_profile_end", "drvae_plan_num_buckets", "drvae_plan_bucket_info", "drvae_stream_wait_bucket"]
+           "drvae_profile_end", "drvae_plan_num_buckets", "drvae_plan_bucket_info", "drvae_stream_wait_bucket", "drvae_set_graph", "drvae_plan_graph_replays"]
 
 
 def load():
@@ -108,6 +108,10 @@ def load():
     lib.drvae_plan_bucket_info.argtypes = [c_void_p, c_int, P(c_ll), P(c_ll)]
     lib.drvae_stream_wait_bucket.restype = c_int
     lib.drvae_stream_wait_bucket.argtypes = [c_void_p, c_int, c_void_p]
+    lib.drvae_set_graph.restype = c_int
+    lib.drvae_set_graph.argtypes = [c_void_p, c_int]
+    lib.drvae_plan_graph_replays.restype = c_ll
+    lib.drvae_plan_graph_replays.argtypes = [c_void_p]
     lib.drvae_infer.restype = c_int
     lib.drvae_infer.argtypes = [c_void_p, c_void_p, c_int, P(InferOut), c_void_p]
     lib.drvae_set_gemm_impl.restype = c_int

@@ -131,7 +131,7 @@ struct EpiParams {
   long long drv_bias_off;
   long long drv_clsb_off;
   int drv_clsb_ld;
-  AdamHyper adam;
+  const AdamHyper* adam;  // device memory (StepDyn): changes every step
   // EPI_DECLOSS / EPI_DECOUT
   const float4* tgt4;  // fp32 targets, chunk4 layout [Xc/4][tgt_rcap] float4
   long long tgt_ms;    // float4 elements between models
@@ -323,6 +323,7 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& e, RowCtx& rc, int co
       float* P = e.adam_p + rc.model * e.grad_ms + kofs;
       float* M1 = e.adam_m + rc.model * e.grad_ms + kofs;
       float* V2 = e.adam_v + rc.model * e.grad_ms + kofs;
+      const AdamHyper h = *e.adam;
       float pv[16], mv[16], vv[16];
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
@@ -334,7 +335,7 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& e, RowCtx& rc, int co
         }
       }
 #pragma unroll
-      for (int i = 0; i < 16; ++i) adam_update(acc[i], pv[i], mv[i], vv[i], e.adam);
+      for (int i = 0; i < 16; ++i) adam_update(acc[i], pv[i], mv[i], vv[i], h);
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         if (idx[i] >= 0) {
@@ -570,8 +571,9 @@ __device__ __forceinline__ void adam_pipe_apply(const EpiParams& e, int model, i
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
   }
   if (k >= e.g_kaug) return;
+  const AdamHyper h = *e.adam;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) adam_update(acc[i], b.p[i], b.m[i], b.v[i], e.adam);
+  for (int i = 0; i < 8; ++i) adam_update(acc[i], b.p[i], b.m[i], b.v[i], h);
   float* P = e.adam_p + model * e.grad_ms + kofs;
   float* M1 = e.adam_m + model * e.grad_ms + kofs;
   float* V2 = e.adam_v + model * e.grad_ms + kofs;

@@ -46,7 +46,7 @@ struct AdamArgs {
   const Seg* segs;
   int nseg;
   int P;  // parameters per model
-  AdamHyper h;
+  const AdamHyper* h;  // device memory (StepDyn)
   int update;  // 0: only refresh the derived copies from the current parameters
 };
 
@@ -60,6 +60,8 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamArgs a) {
   bf16* sh = a.shadow.at(mdl);
   float* dv = a.derived.at(mdl);
   const int base = blockIdx.x * 1024 + threadIdx.x;
+  AdamHyper hyper{};
+  if (a.update) hyper = *a.h;
   int si = -1;
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
@@ -68,7 +70,7 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamArgs a) {
     float pv = p[idx];
     if (a.update) {
       float m1 = mm[idx], v1 = vv[idx];
-      adam_update(g[idx], pv, m1, v1, a.h);
+      adam_update(g[idx], pv, m1, v1, hyper);
       mm[idx] = m1;
       vv[idx] = v1;
       p[idx] = pv;
@@ -136,6 +138,9 @@ __global__ void __launch_bounds__(256) wn_grad_kernel(WnArgs a) {
   if (lane == 0) a.grads.at(m)[w.g_idx] = dot * inv;
 }
 
+// writes the per-step scalars; the only kernel whose arguments differ between two steps of the same shape
+__global__ void set_dyn_kernel(StepDyn value, StepDyn* dst) { *dst = value; }
+
 // ε block generator.  Every normal is keyed by (seed, step, model, segment, MC sample, GLOBAL row,
 // position in the row) and never by its address, so a minibatch sharded over ranks
 // (row_offset = global index of the shard's first row) draws exactly the noise of the unsharded
@@ -146,8 +151,10 @@ struct EpsSegs {
   int inner[6];      // floats per row
 };
 
-__global__ void __launch_bounds__(256) philox_normal_kernel(MBuf<float> out, EpsSegs sg, int N, int Ncap, long long row_offset,
-                                                            unsigned long long seed, unsigned int step) {
+__global__ void __launch_bounds__(256) philox_normal_kernel(MBuf<float> out, EpsSegs sg, int N, int Ncap, const StepDyn* dyn) {
+  const long long row_offset = dyn->row_offset;
+  const unsigned long long seed = dyn->noise_seed;
+  const unsigned int step = dyn->noise_step;
   const int m = blockIdx.y, seg = blockIdx.z;
   int inner = 0, outer = 0;
   long long seg_off = 0;

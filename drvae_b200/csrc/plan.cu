@@ -84,6 +84,21 @@ struct drvae_plan {
   int gemm_impl = GEMM_IMPL_TC;
   long long launches = 0;
   bool shadows_valid = false;
+  // per-step scalars in device memory + CUDA-graph replay of the launch sequence (see step_entry)
+  StepDyn* d_dyn = nullptr;
+  bool graph_enabled = true;
+  struct GraphEntry {
+    int seen = 0;
+    cudaGraph_t graph = nullptr;  // kept alive: node handles used for parameter updates belong to it
+    cudaGraphExec_t exec = nullptr;
+    cudaGraphNode_t dyn_node = nullptr;
+    cudaKernelNodeParams dyn_params{};
+    long long launches = 0;
+    long long last_use = 0;
+  };
+  std::map<std::vector<long long>, GraphEntry> graphs;
+  long long graph_clock = 0;
+  long long graph_replays = 0;
   // side stream for the label-dependent branch (see run_step)
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_qy = nullptr, ev_side_fwd = nullptr, ev_side_bwd = nullptr;
@@ -479,6 +494,8 @@ extern "C" int drvae_plan_create(const drvae_arch_t* a, int n_models, drvae_plan
     return set_cuda_error("drvae_plan_create: cudaMalloc(workspace)", err);
   }
   cudaMemset(pl->arena, 0, pl->arena_bytes);
+  cudaMalloc(&pl->d_dyn, sizeof(StepDyn));
+  cudaMemset(pl->d_dyn, 0, sizeof(StepDyn));
   cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking);
   for (cudaEvent_t* ev : {&pl->ev_fork, &pl->ev_qy, &pl->ev_side_fwd, &pl->ev_side_bwd})
     cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
@@ -575,8 +592,20 @@ extern "C" int drvae_plan_create(const drvae_arch_t* a, int n_models, drvae_plan
   return 0;
 }
 
+namespace {
+void drop_graphs(drvae_plan* pl) {
+  for (auto& kv : pl->graphs) {
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    if (kv.second.graph) cudaGraphDestroy(kv.second.graph);
+  }
+  pl->graphs.clear();
+}
+}  // namespace
+
 extern "C" int drvae_plan_destroy(drvae_plan_t* pl) {
   if (!pl) return 0;
+  drop_graphs(pl);
+  if (pl->d_dyn) cudaFree(pl->d_dyn);
   if (pl->arena) cudaFree(pl->arena);
   if (pl->dbg) cudaFree(pl->dbg);
   if (pl->d_segs) cudaFree(pl->d_segs);
@@ -638,6 +667,7 @@ extern "C" int drvae_plan_bind(drvae_plan_t* pl, float* params, float* adam_m, f
   pl->adam_v = adam_v;
   pl->grads = grads;
   pl->shadows_valid = false;
+  drop_graphs(pl);  // captured sequences hold the old pointers
   return 0;
 }
 
@@ -794,7 +824,7 @@ struct Exec {
       e.drv_bias_off = W.bias_off;
       e.drv_clsb_off = W.clsb_off;
       e.drv_clsb_ld = W.rcap;
-      e.adam = v.s.adam;
+      e.adam = &pl->d_dyn->s.adam;
     }
     launch(fused ? EPI_GRAD_ADAM : EPI_GRAD, p, e, ((fused ? "gemm_dw_adam." : "gemm_dw.") + sub).c_str());
   }
@@ -918,16 +948,20 @@ int fill_view(drvae_plan* pl, Exec& ex, const drvae_batch_t* b, const drvae_nois
   v.eps_z2f = MBuf<const float>{eps + pl->epsl.off_z2f, ems};
   v.eps_z3 = MBuf<const float>{eps + pl->epsl.off_z3, ems};
   v.own_noise = (nz && nz->eps) ? 0 : 1;
-  v.noise_seed = nz ? nz->seed : 0ULL;
-  v.noise_step = (unsigned)hp->step;
-  v.row_offset = nz ? nz->row_offset : 0LL;
+  v.dyn = pl->d_dyn;
   v.params = MBuf<float>{pl->params, pl->P};
   v.clf_w = pl->wn ? MBuf<const float>{pl->derived.p + pl->clf_eff_off, pl->derived.ms}
                    : MBuf<const float>{pl->params + pl->clf_w_off, pl->P};
   v.grads = MBuf<float>{pl->grads, pl->P};
   v.adam_m = MBuf<float>{pl->adam_m, pl->P};
   v.adam_v = MBuf<float>{pl->adam_v, pl->P};
-  StepScalars& s = v.s;
+  return 0;
+}
+
+// per-step scalars of one call (written to device memory by set_dyn_kernel)
+StepDyn make_dyn(const drvae_noise_t* nz, const drvae_hparams_t* hp, bool fused_adam) {
+  StepDyn d{};
+  StepScalars& s = d.s;
   s.kl_min = hp->kl_min;
   s.noise_std = hp->noise_std;
   s.beta_pert = hp->beta_pert;
@@ -941,7 +975,20 @@ int fill_view(drvae_plan* pl, Exec& ex, const drvae_batch_t* b, const drvae_nois
   s.gNlab = hp->global_Nlab;
   for (int j = 0; j < 8; ++j) s.log_prior[j] = hp->log_prior_y[j];
   s.adam = adam_scalars(hp);
-  s.fused_adam = 0;
+  s.fused_adam = fused_adam ? 1 : 0;
+  d.noise_step = (unsigned)hp->step;
+  d.noise_seed = nz ? nz->seed : 0ULL;
+  d.row_offset = nz ? nz->row_offset : 0LL;
+  return d;
+}
+
+int push_dyn(drvae_plan* pl, const StepDyn& d, cudaStream_t st) {
+  prof_pre(pl, st, ":set_dyn");
+  set_dyn_kernel<<<1, 1, 0, st>>>(d, pl->d_dyn);
+  prof_post(pl, st);
+  pl->launches++;
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return set_cuda_error("set_dyn_kernel", err);
   return 0;
 }
 
@@ -959,7 +1006,7 @@ int run_adam(drvae_plan* pl, const drvae_hparams_t* hp, int update, cudaStream_t
   a.nseg = (int)pl->segs.size();
   a.P = pl->P;
   a.update = update;
-  if (update) a.h = adam_scalars(hp);
+  a.h = &pl->d_dyn->s.adam;  // the caller has pushed this step's scalars
   dim3 grid(cdiv(pl->P, 1024), pl->E);
   prof_pre(pl, st, update ? "opt:adam" : "opt:shadow_sync");
   adam_kernel<<<grid, 256, 0, st>>>(a);
@@ -1006,7 +1053,6 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
   ex.fused = fused_adam;
   int rc = fill_view(pl, ex, b, nz, hp, backward);
   if (rc) return rc;
-  ex.v.s.fused_adam = fused_adam ? 1 : 0;
   if (!pl->shadows_valid) {
     rc = run_adam(pl, hp, 0, st);
     if (rc) return rc;
@@ -1046,8 +1092,7 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
     if (most >= (1LL << 31)) return set_error("drvae: minibatch too large for the noise generator");
     dim3 g((unsigned)((most + 255) / 256), E, 6);
     ex.pre("philox_normal");
-    philox_normal_kernel<<<g, 256, 0, st>>>(pl->eps_own, sg, N, pl->Ncap, nz ? nz->row_offset : 0LL, nz ? nz->seed : 0ULL,
-                                            (unsigned)hp->step);
+    philox_normal_kernel<<<g, 256, 0, st>>>(pl->eps_own, sg, N, pl->Ncap, pl->d_dyn);
     ex.chk();
   }
   ex.pre("rowmap");
@@ -1214,6 +1259,139 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
 
 }  // namespace
 
+namespace {
+
+enum { SEQ_TRAIN = 0, SEQ_LOSS = 1, SEQ_GRAD = 2 };
+
+// does this train step run with Adam fused into the weight-gradient epilogues?
+bool train_is_fused(const drvae_plan* pl, const drvae_batch_t* b) {
+  // weight norm: the update acts on (v, g), not on the effective weights the GEMMs produce gradients for.
+  // One (or a few) models on a large minibatch: the weight gradients need split-K to fill the GPU, which the
+  // fused epilogue cannot do (it needs the complete sum).  Both -> gradient buffer + stand-alone optimizer.
+  if (pl->wn) return false;
+  if (b && (long long)b->N * pl->L >= 1024 && pl->E < 8) return false;
+  return true;
+}
+
+// Enqueue the whole launch sequence of one call on `st` (everything after the per-step scalars).
+int enqueue_sequence(drvae_plan* pl, int seq, const drvae_batch_t* b, const drvae_noise_t* nz, const drvae_hparams_t* hp,
+                     float* losses_out, cudaStream_t st, bool fused) {
+  if (seq == SEQ_LOSS) return run_step(pl, b, nz, hp, losses_out, st, false, false);
+  if (seq == SEQ_GRAD) {
+    int rc = run_step(pl, b, nz, hp, losses_out, st, true, false);
+    if (rc || !pl->wn) return rc;
+    rc = run_wn_grad(pl, st);
+    // the conversion rewrites every bucket: bucket events must not fire before it
+    for (auto& ev : pl->bucket_ev) cudaEventRecord(ev, st);
+    return rc;
+  }
+  if (fused) {
+    // forward + ELBO + backward with Adam fused into the gradient epilogues: no gradient buffer traffic and
+    // no separate optimizer pass (the bound gradient buffer is left untouched)
+    return run_step(pl, b, nz, hp, losses_out, st, true, true);
+  }
+  int rc = run_step(pl, b, nz, hp, losses_out, st, true, false);
+  if (rc) return rc;
+  rc = run_wn_grad(pl, st);
+  if (rc) return rc;
+  return run_adam(pl, hp, 1, st);
+}
+
+// One call = [set_dyn_kernel(per-step scalars)] + a launch sequence that is identical for every step of the same
+// shape and the same buffers.  The second time a (sequence, N, buffers, stream) combination is seen, the sequence is
+// captured into a CUDA graph (the side-stream fork/join becomes graph edges); afterwards a step is one graph launch
+// with the arguments of the set_dyn node updated.  Not captured: parity runs with a caller-provided eps block,
+// drvae_grad_step (its bucket events are consumed outside), profiling passes, and the legacy default stream.
+int step_entry(drvae_plan* pl, int seq, const drvae_batch_t* b, const drvae_noise_t* nz, const drvae_hparams_t* hp,
+               float* losses_out, cudaStream_t st) {
+  if (!hp) return set_error("drvae: hparams is null");
+  if (!b) return set_error("drvae: batch is null");
+  const bool fused = seq == SEQ_TRAIN && train_is_fused(pl, b);
+  const StepDyn dyn = make_dyn(nz, hp, fused);
+  const bool graphable = pl->graph_enabled && !pl->prof_on && !(nz && nz->eps) && seq != SEQ_GRAD && pl->shadows_valid &&
+                         st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;
+  if (graphable) {
+    std::vector<long long> key = {seq, b->N, (long long)(size_t)b->x1, (long long)(size_t)b->x2, (long long)(size_t)b->y,
+                                  (long long)(size_t)b->has_x2, (long long)(size_t)b->has_y, (long long)(size_t)losses_out,
+                                  (long long)(size_t)st, hp->training, hp->add_noise};
+    drvae_plan::GraphEntry& ge = pl->graphs[key];
+    ge.last_use = ++pl->graph_clock;
+    if (!ge.exec && ge.seen >= 1) {
+      // capture (nothing executes during capture)
+      const long long l0 = pl->launches;
+      cudaError_t err = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+      if (err == cudaSuccess) {
+        int rc = push_dyn(pl, dyn, st);
+        if (!rc) rc = enqueue_sequence(pl, seq, b, nz, hp, losses_out, st, fused);
+        cudaGraph_t graph = nullptr;
+        err = cudaStreamEndCapture(st, &graph);
+        if (rc || err != cudaSuccess || !graph) {
+          if (graph) cudaGraphDestroy(graph);
+          cudaGetLastError();
+          pl->graph_enabled = false;  // fall back to plain launches for the rest of this plan's life
+          if (rc) return rc;
+        } else {
+          size_t n = 0;
+          cudaGraphGetNodes(graph, nullptr, &n);
+          std::vector<cudaGraphNode_t> nodes(n);
+          cudaGraphGetNodes(graph, nodes.data(), &n);
+          for (size_t i = 0; i < n && !ge.dyn_node; ++i) {
+            cudaGraphNodeType ty;
+            if (cudaGraphNodeGetType(nodes[i], &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) continue;
+            cudaKernelNodeParams np{};
+            if (cudaGraphKernelNodeGetParams(nodes[i], &np) == cudaSuccess && np.func == (void*)set_dyn_kernel) {
+              ge.dyn_node = nodes[i];
+              ge.dyn_params = np;
+            }
+          }
+          if (ge.dyn_node && cudaGraphInstantiate(&ge.exec, graph, 0) == cudaSuccess) {
+            ge.launches = pl->launches - l0;
+            ge.graph = graph;
+          } else {
+            ge.exec = nullptr;
+            pl->graph_enabled = false;
+            cudaGraphDestroy(graph);
+          }
+          pl->launches = l0;
+        }
+      } else {
+        cudaGetLastError();
+        pl->graph_enabled = false;
+      }
+      if (pl->graphs.size() > 16) {  // bound the cache: drop the least recently used entry
+        auto victim = pl->graphs.end();
+        for (auto it = pl->graphs.begin(); it != pl->graphs.end(); ++it)
+          if (&it->second != &ge && (victim == pl->graphs.end() || it->second.last_use < victim->second.last_use)) victim = it;
+        if (victim != pl->graphs.end()) {
+          if (victim->second.exec) cudaGraphExecDestroy(victim->second.exec);
+          if (victim->second.graph) cudaGraphDestroy(victim->second.graph);
+          pl->graphs.erase(victim);
+        }
+      }
+    }
+    if (ge.exec) {
+      StepDyn value = dyn;
+      StepDyn* dst = pl->d_dyn;
+      void* args[2] = {&value, &dst};
+      cudaKernelNodeParams np = ge.dyn_params;
+      np.kernelParams = args;
+      np.extra = nullptr;
+      cudaError_t err = cudaGraphExecKernelNodeSetParams(ge.exec, ge.dyn_node, &np);
+      if (err == cudaSuccess) err = cudaGraphLaunch(ge.exec, st);
+      if (err != cudaSuccess) return set_cuda_error("drvae: graph replay", err);
+      pl->launches += ge.launches;
+      pl->graph_replays++;
+      return 0;
+    }
+    ge.seen++;
+  }
+  int rc = push_dyn(pl, dyn, st);
+  if (rc) return rc;
+  return enqueue_sequence(pl, seq, b, nz, hp, losses_out, st, fused);
+}
+
+}  // namespace
+
 extern "C" int drvae_sync_shadows(drvae_plan_t* pl, void* stream) {
   if (!pl) return set_error("drvae_sync_shadows: null plan");
   drvae_hparams_t hp{};
@@ -1223,48 +1401,35 @@ extern "C" int drvae_sync_shadows(drvae_plan_t* pl, void* stream) {
 extern "C" int drvae_train_step(drvae_plan_t* pl, const drvae_batch_t* b, const drvae_noise_t* nz, const drvae_hparams_t* hp,
                                 float* losses_out, void* stream) {
   if (!pl) return set_error("drvae_train_step: null plan");
-  if (pl->wn) {
-    // weight norm: the update acts on (v, g), not on the effective weights the GEMMs produce
-    // gradients for -> materialise the gradient, convert, then run the stand-alone optimizer
-    int rc = run_step(pl, b, nz, hp, losses_out, (cudaStream_t)stream, true, false);
-    if (rc) return rc;
-    rc = run_wn_grad(pl, (cudaStream_t)stream);
-    if (rc) return rc;
-    return run_adam(pl, hp, 1, (cudaStream_t)stream);
-  }
-  if (b && (long long)b->N * pl->L >= 1024 && pl->E < 8) {
-    // one (or a few) models on a large minibatch: the weight gradients need split-K to fill the GPU, which
-    // the fused epilogue cannot do (it needs the complete sum) -> gradient buffer + stand-alone optimizer
-    int rc = run_step(pl, b, nz, hp, losses_out, (cudaStream_t)stream, true, false);
-    if (rc) return rc;
-    return run_adam(pl, hp, 1, (cudaStream_t)stream);
-  }
-  // forward + ELBO + backward with Adam fused into the gradient epilogues: no gradient buffer
-  // traffic and no separate optimizer pass (the bound gradient buffer is left untouched)
-  return run_step(pl, b, nz, hp, losses_out, (cudaStream_t)stream, true, true);
+  return step_entry(pl, SEQ_TRAIN, b, nz, hp, losses_out, (cudaStream_t)stream);
 }
 
 extern "C" int drvae_loss_forward(drvae_plan_t* pl, const drvae_batch_t* b, const drvae_noise_t* nz, const drvae_hparams_t* hp,
                                   float* losses_out, void* stream) {
   if (!pl) return set_error("drvae_loss_forward: null plan");
-  return run_step(pl, b, nz, hp, losses_out, (cudaStream_t)stream, false, false);
+  return step_entry(pl, SEQ_LOSS, b, nz, hp, losses_out, (cudaStream_t)stream);
 }
 
 extern "C" int drvae_grad_step(drvae_plan_t* pl, const drvae_batch_t* b, const drvae_noise_t* nz, const drvae_hparams_t* hp,
                                float* losses_out, void* stream) {
   if (!pl) return set_error("drvae_grad_step: null plan");
-  int rc = run_step(pl, b, nz, hp, losses_out, (cudaStream_t)stream, true, false);
-  if (rc || !pl->wn) return rc;
-  rc = run_wn_grad(pl, (cudaStream_t)stream);
-  // the conversion rewrites every bucket: bucket events must not fire before it
-  for (auto& ev : pl->bucket_ev) cudaEventRecord(ev, (cudaStream_t)stream);
-  return rc;
+  return step_entry(pl, SEQ_GRAD, b, nz, hp, losses_out, (cudaStream_t)stream);
 }
 
 extern "C" int drvae_adam_step(drvae_plan_t* pl, const drvae_hparams_t* hp, void* stream) {
   if (!pl || !hp) return set_error("drvae_adam_step: null argument");
+  int rc = push_dyn(pl, make_dyn(nullptr, hp, false), (cudaStream_t)stream);
+  if (rc) return rc;
   return run_adam(pl, hp, 1, (cudaStream_t)stream);
 }
+
+extern "C" int drvae_set_graph(drvae_plan_t* pl, int enable) {
+  if (!pl) return set_error("drvae_set_graph: null plan");
+  pl->graph_enabled = enable != 0;
+  if (!enable) drop_graphs(pl);
+  return 0;
+}
+extern "C" long long drvae_plan_graph_replays(const drvae_plan_t* pl) { return pl ? pl->graph_replays : -1; }
 
 extern "C" int drvae_infer(drvae_plan_t* pl, const float* x1, int N, const drvae_infer_out_t* out, void* stream) {
   if (!pl || !x1 || !out) return set_error("drvae_infer: null argument");
@@ -1290,8 +1455,14 @@ extern "C" int drvae_infer(drvae_plan_t* pl, const float* x1, int N, const drvae
   v.params = MBuf<float>{pl->params, pl->P};
   v.clf_w = pl->wn ? MBuf<const float>{pl->derived.p + pl->clf_eff_off, pl->derived.ms}
                    : MBuf<const float>{pl->params + pl->clf_w_off, pl->P};
-  v.s.training = 0;
-  v.s.add_noise = 0;
+  v.dyn = pl->d_dyn;
+  v.own_noise = 0;
+  {
+    drvae_hparams_t ihp{};  // eval mode: training = 0, add_noise = 0
+    ihp.beta1 = 0.9f, ihp.beta2 = 0.999f;
+    int rc = push_dyn(pl, make_dyn(nullptr, &ihp, false), st);
+    if (rc) return rc;
+  }
   const int E = pl->E;
   const int rows_dec = pl->has_T ? 2 * N : N;
   InferView o{out->z1_mu, out->z1_lv, out->z2_mu, out->z2_lv, out->proba, out->pred};

@@ -120,6 +120,17 @@ struct StepScalars {
   float log_prior[8];  // log prior_y
 };
 
+// Everything that changes from step to step.  Lives in device memory (one block per plan), written by
+// set_dyn_kernel at the head of every launch sequence: kernels read it through DevView::dyn, so the
+// sequence itself — grids, pointers, kernel arguments — is identical from step to step and can be
+// replayed as a CUDA graph with only that one kernel node's arguments updated.
+struct StepDyn {
+  StepScalars s;
+  unsigned int noise_step;
+  unsigned long long noise_seed;
+  long long row_offset;
+};
+
 struct DevView {
   int kind, X, Y, Z, Z3, L, N, Ncap;
   int Xc;            // round_up(X, 16)
@@ -135,9 +146,6 @@ struct DevView {
   // own_noise: the input noise of x1 / x2 is drawn inside prep_kernel (same Philox keys as the ε
   // generator, segments 0 and 1) instead of being written to and read back from the ε block
   int own_noise;
-  unsigned int noise_step;
-  unsigned long long noise_seed;
-  long long row_offset;
   // row maps
   MBuf<int> counts;   // CNT_*
   MBuf<float> coefs;  // COEF_*
@@ -185,7 +193,7 @@ struct DevView {
   MBuf<const float> clf_w;  // classifier weights as the kernels read them: the parameters, or the
                             // effective (weight-normalised) copy in the derived arena
   MBuf<float> losses;  // [8]
-  StepScalars s;
+  const StepDyn* dyn;  // per-step scalars (device memory)
 };
 
 constexpr int CLF_SPLITS = 32;       // row splits of the classifier weight gradient (ensemble-sized batches)

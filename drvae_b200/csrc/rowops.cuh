@@ -99,16 +99,16 @@ __global__ void __launch_bounds__(ROWMAP_THREADS) rowmap_kernel(DevView v) {
     cnt[CNT_RD] = v.L * (N + 2 * Np);
     cnt[CNT_FL] = Fl;
     cnt[CNT_F] = v.L * Fl;
-    const float gN = v.s.gN > 0 ? v.s.gN : N;
-    const float gNp = fmaxf(1.f, v.s.gN > 0 ? v.s.gNp : Np);
-    const float gNl = fmaxf(1.f, v.s.gN > 0 ? v.s.gNlab : Nlab);
+    const float gN = v.dyn->s.gN > 0 ? v.dyn->s.gN : N;
+    const float gNp = fmaxf(1.f, v.dyn->s.gN > 0 ? v.dyn->s.gNp : Np);
+    const float gNl = fmaxf(1.f, v.dyn->s.gN > 0 ? v.dyn->s.gNlab : Nlab);
     const float Lf = v.L;
     float* cf = v.coefs.at(m);
     cf[COEF_RECL] = 1.f / (Lf * gN);
-    cf[COEF_PERT] = v.s.beta_pert * v.s.pertloss_rate / (Lf * gNp);
-    cf[COEF_KLZ2] = v.s.beta_pert * v.s.kl_qz2pz2_rate / (Lf * gN);
+    cf[COEF_PERT] = v.dyn->s.beta_pert * v.dyn->s.pertloss_rate / (Lf * gNp);
+    cf[COEF_KLZ2] = v.dyn->s.beta_pert * v.dyn->s.kl_qz2pz2_rate / (Lf * gN);
     cf[COEF_KLD] = 1.f / (Lf * gN);
-    cf[COEF_YL] = v.s.yloss_rate / (Lf * gNl);
+    cf[COEF_YL] = v.dyn->s.yloss_rate / (Lf * gNl);
     cf[COEF_INV_N] = 1.f / gN;
     cf[COEF_PERT_PLAIN] = 1.f / (Lf * gNp);
     cf[COEF_YL_PLAIN] = 1.f / (Lf * gNl);
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(DevView v) {
   const int N = cnt[CNT_N], R0 = cnt[CNT_R0];
   if (r0 >= pad128(R0)) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool noisy = v.s.training && v.s.add_noise;
+  const bool noisy = v.dyn->s.training && v.dyn->s.add_noise;
   uint4* ain = reinterpret_cast<uint4*>(v.Ain.at(m));
   float4* tg = v.tgt4.at(m);
   {
@@ -197,12 +197,12 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(DevView v) {
         float x[4] = {0.f, 0.f, 0.f, 0.f};
         if (src && f < v.X) {
           float z[4] = {0.f, 0.f, 0.f, 0.f};
-          if (noisy && v.own_noise) philox_normal4(v.noise_seed, v.noise_step, m, seg, 0, (unsigned long long)(v.row_offset + nrow), f >> 2, z);
+          if (noisy && v.own_noise) philox_normal4(v.dyn->noise_seed, v.dyn->noise_step, m, seg, 0, (unsigned long long)(v.dyn->row_offset + nrow), f >> 2, z);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             if (f + k < v.X) {
               x[k] = src[f + k];
-              if (noisy) x[k] += v.s.noise_std * (v.own_noise ? z[k] : eps[f + k]);
+              if (noisy) x[k] += v.dyn->s.noise_std * (v.own_noise ? z[k] : eps[f + k]);
             }
           }
         }
@@ -279,7 +279,7 @@ __device__ __forceinline__ void classifier_row(const DevView& v, int m, int r, i
       if (lb) {
         if (j == yi) yl = lq;
       } else {
-        ycat += -q * (v.s.log_prior[j] - lq);
+        ycat += -q * (v.dyn->s.log_prior[j] - lq);
       }
     }
   }
@@ -358,8 +358,8 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) sample_q1_kernel(DevView v) {
     k1 = warp_sum(k1);
     k2 = warp_sum(k2);
     if (lane == 0) {
-      v.klq_row.at(m)[i] = fmaxf(k1, v.s.kl_min);
-      if (p >= 0) v.klq_row.at(m)[N + p] = fmaxf(k2, v.s.kl_min);
+      v.klq_row.at(m)[i] = fmaxf(k1, v.dyn->s.kl_min);
+      if (p >= 0) v.klq_row.at(m)[N + p] = fmaxf(k2, v.dyn->s.kl_min);
     }
   }
 }
@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) T_post_kernel(DevView v) {
       if (p >= 0) st_c8(zdec, v.Zdec.rcap, LN + LNp + l * Np + p, f, z2f);
     }
     kl = warp_sum(kl);
-    if (lane == 0) v.klz2_row.at(m)[r] = q2 ? fmaxf(kl, v.s.kl_min) : 0.f;
+    if (lane == 0) v.klz2_row.at(m)[r] = q2 ? fmaxf(kl, v.dyn->s.kl_min) : 0.f;
     if (v.has_clf) {
       __syncwarp();
       classifier_row(v, m, r, i, lane);
@@ -448,7 +448,7 @@ __global__ void __launch_bounds__(ROW_THREADS) z3_post_kernel(DevView v) {
     st_c8(z3b, v.Z3b.rcap, e, f, z);
   }
   kl = warp_sum(kl);
-  if (lane == 0) v.kfp_row.at(m)[e] = fmaxf(kl, v.s.kl_min);
+  if (lane == 0) v.kfp_row.at(m)[e] = fmaxf(kl, v.dyn->s.kl_min);
 }
 
 // weight of evaluation e in the batch KLD: 1 for the true class of a labeled row, q(y=j) otherwise
@@ -478,9 +478,9 @@ __global__ void __launch_bounds__(ROW_THREADS) pz1_post_kernel(DevView v) {
   float kl = 0.f;
   for (int f = lane; f < v.Z; f += 32) kl += kl_term(q1[f], q1[v.Z + f], pz[f], pz[v.Z + f]);
   kl = warp_sum(kl);
-  const bool act = kl > v.s.kl_min;
+  const bool act = kl > v.dyn->s.kl_min;
   const float w = eval_weight(v, m, l, i, jj, N);
-  const float ke = v.kfp_row.at(m)[e] + fmaxf(kl, v.s.kl_min);
+  const float ke = v.kfp_row.at(m)[e] + fmaxf(kl, v.dyn->s.kl_min);
   __syncwarp();
   if (lane == 0) {
     v.kfp_row.at(m)[e] = ke;
@@ -524,7 +524,7 @@ __global__ void __launch_bounds__(ROW_THREADS) z3_back_kernel(DevView v) {
   for (int f = lane; f < v.Z3; f += 32) kl += kl_prior_term(q3[f], q3[v.Z3 + f]);
   kl = warp_sum(kl);
   const float w = eval_weight(v, m, l, i, jj, N);
-  const float cw = kl > v.s.kl_min ? v.coefs.at(m)[COEF_KLD] * w : 0.f;
+  const float cw = kl > v.dyn->s.kl_min ? v.coefs.at(m)[COEF_KLD] * w : 0.f;
   bf16* dy = v.dY7.at(m);
   for (int f = lane; f < v.Z3; f += 32) {
     const float mu = q3[f], lv = q3[v.Z3 + f];
@@ -565,7 +565,7 @@ __global__ void __launch_bounds__(ROW_THREADS) clf_back_kernel(DevView v) {
         g[j] = (j == yi) ? -cf[COEF_YL] / q[j] : 0.f;
       } else {
         const float ke = v.has_fprop ? v.kfp_row.at(m)[l * Fl + v.ebase.at(m)[i] + j] : 0.f;
-        g[j] = cf[COEF_KLD] * (ke + logf(q[j]) - v.s.log_prior[j] + 1.f);
+        g[j] = cf[COEF_KLD] * (ke + logf(q[j]) - v.dyn->s.log_prior[j] + 1.f);
       }
       if (clamped) g[j] = 0.f;
       dot += q[j] * g[j];
@@ -621,7 +621,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) T_back_kernel(DevView v) {
     const float* pt = v.PT.at(m) + (long long)r * 2 * v.Z;
     const float* ef = v.eps_z2f.at(m) + ((long long)l * v.Ncap + i) * v.Z;
     const float* dzd = p >= 0 ? v.dZdec.at(m) + (long long)(LN + LNp + l * Np + p) * v.Z : nullptr;
-    const bool act = q2 && v.klz2_row.at(m)[r] > v.s.kl_min;
+    const bool act = q2 && v.klz2_row.at(m)[r] > v.dyn->s.kl_min;
     float* dz1 = v.DZ1.at(m) + (long long)r * v.Z;
     const float* dz2f_c = v.has_clf ? v.DZ2F.at(m) + (long long)r * v.Z : nullptr;
 #pragma unroll
@@ -706,7 +706,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) q_back_kernel(DevView v) {
         alv += g2 * hs * v.eps_z2.at(m)[((long long)l * v.Ncap + i) * v.Z + f];
       }
     }
-    if (v.kind == KIND_PVAE && v.klq_row.at(m)[i] > v.s.kl_min) {
+    if (v.kind == KIND_PVAE && v.klq_row.at(m)[i] > v.dyn->s.kl_min) {
       amu += cN * mu;
       alv += cN * 0.5f * (expf(lv) - 1.f);
     }
@@ -716,7 +716,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) q_back_kernel(DevView v) {
       const float* q2 = v.Q.at(m) + (long long)(N + p) * 2 * v.Z;
       float bmu = v.has_T ? v.dQ2.at(m)[(long long)p * 2 * v.Z + f] : 0.f;
       float blv = v.has_T ? v.dQ2.at(m)[(long long)p * 2 * v.Z + v.Z + f] : 0.f;
-      if (v.kind == KIND_PVAE && v.klq_row.at(m)[N + p] > v.s.kl_min) {
+      if (v.kind == KIND_PVAE && v.klq_row.at(m)[N + p] > v.dyn->s.kl_min) {
         bmu += cN * q2[f];
         blv += cN * 0.5f * (expf(q2[v.Z + f]) - 1.f);
       }
@@ -774,7 +774,7 @@ __global__ void __launch_bounds__(256) clf_grad_reduce_kernel(DevView v) {
   s = warp_sum(s);
   if (lane != 0) return;
   const int idx = (t < v.clf_in) ? v.clf_w_off + j * v.clf_in + t : v.clf_b_off + j;
-  if (!v.s.fused_adam) {
+  if (!v.dyn->s.fused_adam) {
     v.grads.at(m)[idx] = s;
   } else {
     // the classifier runs on the fp32 parameters directly: Adam here, no shadow to refresh
@@ -782,7 +782,7 @@ __global__ void __launch_bounds__(256) clf_grad_reduce_kernel(DevView v) {
     float* M1 = v.adam_m.at(m);
     float* V2 = v.adam_v.at(m);
     float pv = P[idx], m1 = M1[idx], v1 = V2[idx];
-    adam_update(s, pv, m1, v1, v.s.adam);
+    adam_update(s, pv, m1, v1, v.dyn->s.adam);
     M1[idx] = m1;
     V2[idx] = v1;
     P[idx] = pv;
@@ -960,8 +960,8 @@ __global__ void __launch_bounds__(32) loss_final_kernel(DevView v) {
   const float PERT = cf[COEF_PERT_PLAIN] * a[1];
   const float KLD = cf[COEF_KLZ2] * a[2] + cf[COEF_KLD] * (a[5] + a[4]) + cf[COEF_INV_N] * a[6];
   const float YL = cf[COEF_YL_PLAIN] * a[3];
-  const float ELBO = RECL + v.s.beta_pert * v.s.pertloss_rate * PERT - KLD;
-  const float CMPL = -ELBO - v.s.yloss_rate * YL;
+  const float ELBO = RECL + v.dyn->s.beta_pert * v.dyn->s.pertloss_rate * PERT - KLD;
+  const float CMPL = -ELBO - v.dyn->s.yloss_rate * YL;
   float* o = v.losses.at(m);
   o[0] = RECL;
   o[1] = KLD;

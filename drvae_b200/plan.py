@@ -6,6 +6,7 @@ the shared library.  CUDA-only: there is no CPU fallback.
 """
 import ctypes
 import math
+import os
 from collections import OrderedDict
 
 import torch
@@ -78,7 +79,12 @@ class Plan:
         self.adam_v = torch.zeros(self.E, self.P, **kw)
         self.grads = torch.zeros(self.E, self.P, **kw)
         self.losses = torch.zeros(self.E, 8, **kw)
+        # CUDA graphs cannot be captured on the legacy default stream: calls made while torch's current stream is
+        # the default one run on this stream instead, ordered after / before the caller's stream with events
+        self._own_stream = torch.cuda.Stream(device=self.device)
         _lib.check(self.lib.drvae_plan_bind(h, _ptr(self.params), _ptr(self.adam_m), _ptr(self.adam_v), _ptr(self.grads)))
+        if os.environ.get("DRVAE_B200_GRAPH", "1") == "0":  # measurement knob: launch kernel by kernel
+            self.set_graph(False)
 
     def __del__(self):
         try:
@@ -182,7 +188,15 @@ class Plan:
         b, keep = self._batch(**batch)
         nz, keep_eps = self._noise(eps, seed, row_offset)
         with torch.cuda.device(self.device):
-            _lib.check(fn(self.h, ctypes.byref(b), ctypes.byref(nz), ctypes.byref(hp), _ptr(self.losses), self._stream()), what)
+            cur = torch.cuda.current_stream(self.device)
+            if cur.cuda_stream == 0:
+                own = self._own_stream
+                own.wait_stream(cur)
+                _lib.check(fn(self.h, ctypes.byref(b), ctypes.byref(nz), ctypes.byref(hp), _ptr(self.losses),
+                              ctypes.c_void_p(own.cuda_stream)), what)
+                cur.wait_stream(own)  # later work on the caller's stream (incl. reuse of freed batch memory) is ordered after the step
+            else:
+                _lib.check(fn(self.h, ctypes.byref(b), ctypes.byref(nz), ctypes.byref(hp), _ptr(self.losses), self._stream()), what)
         del keep, keep_eps  # stream-ordered: torch's caching allocator keeps them alive for this stream
         return self.losses
 
@@ -237,6 +251,12 @@ class Plan:
         _lib.check(self.lib.drvae_stream_wait_bucket(self.h, int(index), ctypes.c_void_p(stream.cuda_stream)), "wait_bucket")
 
     # ---- introspection --------------------------------------------------------------------
+    def set_graph(self, enable):
+        _lib.check(self.lib.drvae_set_graph(self.h, int(bool(enable))), "set_graph")
+
+    def graph_replays(self):
+        return int(self.lib.drvae_plan_graph_replays(self.h))
+
     def set_gemm_impl(self, impl):
         _lib.check(self.lib.drvae_set_gemm_impl(self.h, {"tc": 0, "simt": 1}[impl]))
 

@@ -147,6 +147,13 @@ int drvae_plan_bucket_info(const drvae_plan_t* plan, int index, long long* offse
 int drvae_stream_wait_bucket(drvae_plan_t* plan, int index, void* stream);
 int drvae_infer(drvae_plan_t* plan, const float* x1, int N, const drvae_infer_out_t* out, void* stream);
 
+/* Launch mechanism.  With graphs enabled (default) drvae_train_step / drvae_loss_forward replay their launch
+ * sequence as a CUDA graph from the third call with the same (N, batch buffers, output buffer, stream) on;
+ * per-step scalars live in device memory, so only one kernel node's arguments change between steps.  Calls on
+ * the legacy default stream, with a caller-provided eps block, or under profiling are launched kernel by kernel. */
+int drvae_set_graph(drvae_plan_t* plan, int enable);
+long long drvae_plan_graph_replays(const drvae_plan_t* plan);
+
 /* Introspection for tests and bench.py */
 int drvae_set_gemm_impl(drvae_plan_t* plan, int impl);   /* 0 tcgen05 (default), 1 SIMT validation kernel */
 long long drvae_plan_launch_count(const drvae_plan_t* plan); /* kernels launched by this plan so far */

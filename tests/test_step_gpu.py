@@ -512,3 +512,80 @@ def test_large_batch_split_k_matches_oracle(kind):
     check_losses(out, lo_emu, 5e-5, "large batch train_step")
     moved = (plan.params - before).abs().max().item()
     assert 0 < moved <= 2.5 * 5e-4
+
+
+@pytest.mark.parametrize("kind,dim_y,Lmc", [("drvae", 3, 1), ("vfae", 4, 3), ("drvae", 2, 3), ("pvae", 2, 1)])
+def test_other_class_counts_and_sample_counts(kind, dim_y, Lmc):
+    """dim_y > 2 (unlabeled rows are marginalised over every class, DrVAE.py:516-526) and L != 2."""
+    arch = dict(ARCH["tiny"], dim_y=dim_y)
+    N = 30
+    sd = init_state_dict(kind, seed=SEED_MODEL, **arch)
+    batch = orc.synthetic_batch(N, arch["dim_x"], seed=11, dim_y=dim_y)
+    cfg = orc.default_cfg(kind, L=Lmc, dim_y=dim_y)
+    om = orc.OracleModel(sd, cfg)
+    om.iters = 1
+    tape = orc.Tape(seed=31)
+    lo_emu, g_emu = om.grads(batch, tape, emulate_bf16=True)
+    plan = Plan(kind, L=Lmc, max_batch=N, n_models=1, **arch)
+    plan.load_state_dict(sd)
+    eps = eps_block_from_tape(plan, tape.log, batch["has_x2"], batch["has_y"], noisy=True)
+    got = loss_dict(kind, plan.grad_step(batch_fields(kind, batch), plan.hparams(step=1), eps=eps))
+    check_losses(got, lo_emu, 5e-5, "dim_y=%d L=%d" % (dim_y, Lmc))
+    gv = plan.tensor_views(plan.grads, 0)
+    for name, g in g_emu.items():
+        assert rel_l2(gv[name], g) <= 2e-2, "grad %s relL2 %.3e" % (name, rel_l2(gv[name], g))
+    if kind != "pvae":
+        res = plan.infer(batch["x1"])
+        fo = om.forward(batch["x1"], emulate_bf16=True)
+        assert res["proba"].shape[-1] == dim_y
+        assert torch.allclose(res["proba"][0].cpu(), fo["proba"], rtol=1e-3, atol=3e-4)
+
+
+def test_argument_errors_are_reported_not_crashed():
+    """Error convention of the C ABI: non-zero status + message, surfaced as RuntimeError / ValueError."""
+    arch, N = ARCH["tiny"], 8
+    plan = Plan("drvae", L=1, max_batch=N, n_models=1, **arch)
+    b = orc.synthetic_batch(N + 1, arch["dim_x"])
+    with pytest.raises(RuntimeError, match="max_batch"):
+        plan.grad_step(batch_fields("drvae", b), plan.hparams(step=0))
+    b = orc.synthetic_batch(N, arch["dim_x"] + 1)
+    with pytest.raises(ValueError):
+        plan.grad_step(batch_fields("drvae", b), plan.hparams(step=0))
+    with pytest.raises(RuntimeError):
+        Plan("drvae", L=1, max_batch=N, n_models=1, **dict(arch, dim_y=9))
+    from drvae_b200 import DrVAE
+    with pytest.raises(ValueError, match="use_s"):
+        DrVAE(dim_x=10, dim_s=1, dim_y=2, type_rec="diag_gaussian", nonlinearity="elu", use_s=True)
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_graph_replay_equals_plain_launches(kind):
+    """drvae_train_step replays its launch sequence as a CUDA graph from the third call on (per-step scalars live
+    in device memory).  Same seeds, same batches: parameters after 6 steps must be identical to the plan that
+    launches kernel by kernel, and both must equal the oracle-tracked behaviour checked elsewhere."""
+    arch, N = ARCH["tiny"], 40
+    sd = init_state_dict(kind, seed=SEED_MODEL, **arch)
+    batch = {k: v.cuda() for k, v in batch_fields(kind, orc.synthetic_batch(N, arch["dim_x"], seed=2)).items()}
+    res = {}
+    for mode in ("graph", "plain"):
+        plan = Plan(kind, L=L, max_batch=N, n_models=2, **arch)
+        plan.set_graph(mode == "graph")
+        for m in range(2):
+            plan.load_state_dict(sd, model=m)
+        big = {k: torch.stack([v, v]).contiguous() for k, v in batch.items()}
+        losses = []
+        for it in range(6):
+            out = plan.train_step(big, plan.hparams(step=it, beta_pert=anneal_coef(it, 1, 0)), seed=5)
+            losses.append(out.cpu().clone())
+        ev = plan.loss_forward(big, plan.hparams(step=6, training=False), seed=5).cpu().clone()
+        ev2 = plan.loss_forward(big, plan.hparams(step=7, training=False), seed=5).cpu().clone()
+        ev3 = plan.loss_forward(big, plan.hparams(step=7, training=False), seed=5).cpu().clone()
+        assert torch.equal(ev2, ev3)
+        res[mode] = (losses, plan.params.cpu().clone(), ev, plan.graph_replays())
+    assert res["graph"][3] >= 4 and res["plain"][3] == 0, (res["graph"][3], res["plain"][3])
+    for a, b in zip(res["graph"][0], res["plain"][0]):
+        assert torch.equal(a, b)
+    assert torch.equal(res["graph"][1], res["plain"][1])
+    assert torch.equal(res["graph"][2], res["plain"][2])
+    # steps differ (noise, Adam bias correction): the dynamic scalars really are updated under replay
+    assert not torch.equal(res["graph"][0][3], res["graph"][0][4])

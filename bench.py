@@ -213,7 +213,7 @@ def run_dp8192(args):
         return float(t.item())
 
     for _ in range(args.warmup):
-        runner.step(devb, seed=1, row_offset=lo)
+        runner.step(devb, seed=1, row_offset=lo, host_flags=host)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -223,7 +223,7 @@ def run_dp8192(args):
     barrier()
     e0.record()
     for _ in range(args.steps):
-        losses = runner.step(devb, seed=1, row_offset=lo)
+        losses = runner.step(devb, seed=1, row_offset=lo, host_flags=host)
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
@@ -233,17 +233,24 @@ def run_dp8192(args):
     from drvae_b200.feed import DeviceFeeder
     feeder = DeviceFeeder(dev)
 
+    loss_host = [torch.empty(8).pin_memory() for _ in range(2)]
+    loss_ready = [torch.cuda.Event() for _ in range(2)]
+
     def e2e_loop(n):
+        # H2D of the shard and D2H of the loss terms every step; the host reads step i's losses after enqueueing step i+1
         feeder.put(host)
-        out = None
         for i in range(n):
             if i + 1 < n:
                 feeder.put(host)
             b, slot = feeder.get()
-            res = runner.step(b, seed=1, row_offset=lo)
+            res = runner.step(b, seed=1, row_offset=lo, host_flags=host)
             feeder.done(slot)
-            out = res.cpu()
-        return out
+            loss_host[i % 2].copy_(res, non_blocking=True)
+            loss_ready[i % 2].record()
+            if i > 0:
+                loss_ready[(i - 1) % 2].synchronize()
+        loss_ready[(n - 1) % 2].synchronize()
+        return loss_host[(n - 1) % 2].clone()
 
     e2e_loop(2)
     barrier()
@@ -257,7 +264,7 @@ def run_dp8192(args):
     if dump and rank == 0:
         plan.profile_begin()
         for _ in range(3):
-            runner.step(devb, seed=1, row_offset=lo)
+            runner.step(devb, seed=1, row_offset=lo, host_flags=host)
         prof = plan.profile_end()
         tot = sum(v[1] for v in prof.values())
         with open(dump, "w") as f:
@@ -382,7 +389,13 @@ def main():
     from drvae_b200.feed import DeviceFeeder
     feeder = DeviceFeeder(dev)
 
+    loss_host = [torch.empty(M, 8).pin_memory() for _ in range(2)]
+    loss_ready = [torch.cuda.Event() for _ in range(2)]
+
     def e2e_loop(n):
+        """Every step: H2D of its batch (pinned -> device, on the feeder's copy stream while the previous step runs)
+        and a D2H read of its loss terms into pinned memory; the host reads step i's losses right after it has
+        enqueued step i+1, so the GPU never waits for the host between steps."""
         feeder.put(host)
         out = None
         for i in range(n):
@@ -391,8 +404,13 @@ def main():
             b, slot = feeder.get()
             res = plan.train_step(b, hp(), seed=rank)
             feeder.done(slot)
-            out = res.cpu()  # D2H of the step's loss terms (synchronises the step)
-        return out
+            loss_host[i % 2].copy_(res, non_blocking=True)
+            loss_ready[i % 2].record()
+            if i > 0:
+                loss_ready[(i - 1) % 2].synchronize()
+                out = loss_host[(i - 1) % 2].clone()
+        loss_ready[(n - 1) % 2].synchronize()
+        return loss_host[(n - 1) % 2].clone() if n > 0 else out
 
     e2e_loop(3)
     barrier()

@@ -36,9 +36,10 @@ def local_counts(n, has_x2=None, has_y=None):
 
 def global_counts(counts, group=None, device="cpu"):
     """Sum [N, Np, Nlab] over the ranks of `group`."""
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+        return [int(c) for c in counts]
     t = torch.tensor(counts, dtype=torch.int64, device=device)
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return [int(v) for v in t.tolist()]
 
 
@@ -84,12 +85,15 @@ class DataParallel:
         if self.world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
 
-    def step(self, batch, hp_kwargs=None, eps=None, seed=0, row_offset=0):
+    def step(self, batch, hp_kwargs=None, eps=None, seed=0, row_offset=0, host_flags=None):
         """batch: this rank's shard (same fields as Plan.train_step).  Returns the GLOBAL losses as
-        an 8-vector (RECL, KLD, PERT, YL, MMD, ELBO, CMPL, 0) identical on every rank."""
+        an 8-vector (RECL, KLD, PERT, YL, MMD, ELBO, CMPL, 0) identical on every rank.
+        host_flags: optional dict with the CPU copies of has_x2 / has_y (what a DataLoader yields), so the local
+        counts are taken on the host without a device synchronisation."""
         be = self.backend
         n = batch["x1"].shape[-2]
-        counts = global_counts(local_counts(n, batch.get("has_x2"), batch.get("has_y")), self.group,
+        flags = host_flags if host_flags is not None else batch
+        counts = global_counts(local_counts(n, flags.get("has_x2"), flags.get("has_y")), self.group,
                                device=getattr(be, "device", "cpu"))
         losses, events = be.grad_step(batch, dict(hp_kwargs or {}), counts, self.finished_training_iters, eps=eps, seed=seed,
                                       row_offset=row_offset)

@@ -589,3 +589,33 @@ def test_graph_replay_equals_plain_launches(kind):
     assert torch.equal(res["graph"][2], res["plain"][2])
     # steps differ (noise, Adam bias correction): the dynamic scalars really are updated under replay
     assert not torch.equal(res["graph"][0][3], res["graph"][0][4])
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_odd_dimensions(kind):
+    """Nothing in the layouts may assume even / multiple-of-4 feature counts (978 = 2 * 489 is even, but the
+    reference accepts any --dim-z1 / --enc-z1 ...): odd sizes everywhere, Philox noise and tape noise."""
+    arch = dict(dim_x=37, dim_y=3, dim_z1=13, dim_z3=7, enc_z1=[23], dec_x=[19, 21], enc_z3=[11], dec_z1=[9])
+    N = 29
+    sd = init_state_dict(kind, seed=SEED_MODEL, **arch)
+    batch = orc.synthetic_batch(N, arch["dim_x"], seed=13, dim_y=3)
+    om = orc.OracleModel(sd, orc.default_cfg(kind, L=L, dim_y=3))
+    om.iters = 1
+    tape = orc.Tape(seed=41)
+    lo_emu, g_emu = om.grads(batch, tape, emulate_bf16=True)
+    plan = Plan(kind, L=L, max_batch=N + 3, n_models=1, **arch)
+    plan.load_state_dict(sd)
+    eps = eps_block_from_tape(plan, tape.log, batch["has_x2"], batch["has_y"], noisy=True)
+    got = loss_dict(kind, plan.grad_step(batch_fields(kind, batch), plan.hparams(step=1), eps=eps))
+    check_losses(got, lo_emu, 5e-5, "odd dims")
+    gv = plan.tensor_views(plan.grads, 0)
+    for name, g in g_emu.items():
+        assert rel_l2(gv[name], g) <= 2e-2, "grad %s relL2 %.3e" % (name, rel_l2(gv[name], g))
+    # Philox path: finite, deterministic, and training moves the loss
+    fields = {k: v.cuda() for k, v in batch_fields(kind, batch).items()}
+    first = None
+    for it in range(8):
+        out = plan.train_step(fields, plan.hparams(step=it, beta_pert=anneal_coef(it, 1, 0), lr=2e-3), seed=3).cpu()
+        assert torch.isfinite(out).all()
+        first = out.clone() if it == 1 else first
+    assert float(out[0, 6]) < float(first[0, 6])

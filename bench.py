@@ -48,7 +48,7 @@ def ncu_traffic(kernel_tag):
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             t = json.load(f)["kernels"].get(kernel_tag)
-        return None if t is None else {"bytes_per_launch": t["dram_read_bytes"] + t["dram_write_bytes"], "source": t["source"]}
+        return None if t is None else t["dram_read_bytes"] + t["dram_write_bytes"]
     except Exception:
         return None
 
@@ -444,7 +444,7 @@ def main():
             # optimizer state (read p, m, v; write p, m, v: 24 B/param) -> HBM-bound
             mm, nn, kk = dims[base]
             by = 24.0 * (mm * nn + mm) * M  # weights + biases of the layer
-            r.update(bound="hbm", achieved=by / (per * 1e-3) / 1e9, peak=peaks["hbm"], unit="GB/s",
+            r.update(bound="hbm", achieved=by / (per * 1e-3) / 1e9, peak=peaks["hbm"], unit="GB/s", algorithmic_bytes=by,
                      gemm_tflops=2.0 * mm * nn * kk * M / (per * 1e-3) / 1e12)
         elif tag in dims:
             mm, nn, kk = dims[tag]
@@ -461,7 +461,10 @@ def main():
     roofline = None
     if top is not None:
         roofline = {"kernel": top["kernel"], "bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"],
-                    "unit": top["unit"], "frac": top["frac"], "traffic": ncu_traffic(top["kernel"]), "share_of_step": top["share"],
+                    "unit": top["unit"], "frac": top["frac"], "traffic": ncu_traffic(top["kernel"]),
+                    "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full (profiles/ncu_traffic.json); "
+                                    "algorithmic bytes per launch = 24 B x parameters of the layer x models",
+                    "algorithmic_bytes": top.get("algorithmic_bytes"), "share_of_step": top["share"],
                     "peak_source": "%s (MEASURED_PEAKS.json %s)" % (peaks["which"], "hbm_gbs" if top["bound"] == "hbm" else "bf16_tflops_sustained")}
     step_flops = sum(2.0 * a * b * c for a, b, c in dims.values())
     line = {

@@ -34,9 +34,12 @@ def _newer(src_files, target):
     return any(os.path.getmtime(f) > t for f in src_files)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, extra_flags=(), variant=""):
+    """variant: suffix of an instrumented build (own object directory and library name), e.g. "waits" with
+    extra_flags=["-DGEMM_PROFILE_WAITS"] -> lib/libdrvae_b200_waits.so."""
     os.makedirs(LIBDIR, exist_ok=True)
-    objdir = os.path.join(LIBDIR, "obj")
+    objdir = os.path.join(LIBDIR, "obj" + ("_" + variant if variant else ""))
+    lib = LIB if not variant else os.path.join(LIBDIR, "libdrvae_b200_%s.so" % variant)
     os.makedirs(objdir, exist_ok=True)
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(ROOT, "include", "drvae_b200.h"))
@@ -47,7 +50,7 @@ def build(force=False, verbose=False):
         obj = os.path.join(objdir, s[:-3] + ".o")
         objs.append(obj)
         if force or _newer([src] + headers, obj):
-            cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+            cmd = ["nvcc"] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
             jobs.append(cmd)
 
     def run(cmd):
@@ -61,10 +64,13 @@ def build(force=False, verbose=False):
             for out in ex.map(run, jobs):
                 if verbose and out:
                     print(out)
-    if jobs or not os.path.exists(LIB):
-        run(["nvcc", "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
-    return LIB
+    if jobs or not os.path.exists(lib):
+        run(["nvcc", "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--waits" in sys.argv:  # instrumented variant for tools/wait_profile.py
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, extra_flags=["-DGEMM_PROFILE_WAITS"], variant="waits"))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -99,6 +99,16 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
       : "memory");
 }
 
+// Tensor load global -> shared of one 3-D box (TMA unit, SASS UTMALDG), completion on an mbarrier.  `map` must
+// live in parameter (__grid_constant__), constant or global memory.
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"((unsigned long long)map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+
 // L2 prefetch of the cache line holding `p` (per-lane address, no destination register).  Used to
 // pull optimizer state towards L2 ahead of the fused Adam epilogue.
 __device__ __forceinline__ void prefetch_l2(const void* p) {
@@ -125,20 +135,59 @@ __device__ __forceinline__ void tc_fence_before() {
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem], kind::f16 (bf16 in, fp32 accumulate), issued by ONE thread.
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
+// One lane of a CONVERGED warp (elect.sync picks the same lane every time for a full mask).  The single-thread
+// instructions below (tcgen05.mma / commit, TMA loads) are issued from warp-uniform code under this predicate:
+// with uniform control flow and operands ptxas keeps descriptors and addresses in uniform registers, whereas the
+// same instructions under `if (lane == 0)` are wrapped in a per-lane ELECT / R2UR.BROADCAST loop (~50 SASS
+// instructions per MMA on the one thread the whole tile waits for).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// D[tmem] (+)= A[smem] * B[smem], kind::f16 (bf16 in, fp32 accumulate): called by the whole (converged) warp, issued
+// by its elected lane.
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  if (elect_one()) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// Single-thread forms for an issue loop that already runs on one elected lane: descriptors as 32-bit halves (only
+// the low word, which holds the shared-memory address, changes between MMAs), no election per instruction.  The
+// issuing thread is the critical path of a tile: tools/umma_rate_bench.cu measures 128 cycles per N=256 MMA (the
+// hardware floor) for back-to-back issue and 133-275 cycles when every MMA carries its own election and
+// descriptor arithmetic.
+__device__ __forceinline__ void umma_issue(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                           uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// Arrive on an mbarrier once all previously issued UMMAs of this thread have completed.
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+__device__ __forceinline__ void umma_commit_1t(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+// Arrive on an mbarrier once all UMMAs previously issued by the elected lane have completed (whole warp calls).
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  if (elect_one()) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+  }
 }
 // 32 lanes x 16 consecutive fp32 columns: thread t of the warp reads TMEM lane (lane_base + t).
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {

@@ -13,14 +13,22 @@
 // variant, the whole Adam read-modify-write of p, m, v — are 128-byte coalesced.  Every GEMM
 // input carries a ones column (and the one-hot class columns of [z, onehot(y)] inputs) after its
 // last real feature, so the bias and class-column gradients are rows of the same D tile.
-// Operand tiles are moved global->shared with 1-D bulk copies (TMA engine) into the no-swizzle
-// UMMA canonical layout, multiplied with tcgen05.mma (bf16 in, fp32 accumulate in TMEM) by one
-// elected thread, and the accumulator tile is read back with tcgen05.ld by four epilogue warps
-// that apply the layer's epilogue (bias/ELU, ELU', Gaussian log-density + its gradient, ...).
+// Operand tiles are moved global->shared by TMA tensor loads (one box per operand tile and
+// k-block: a chunk8 buffer is described as a 3-D tensor {row x 16 B, feature chunk, model} of
+// 8-byte elements, so a box lands in shared memory as the no-swizzle UMMA canonical layout),
+// multiplied with tcgen05.mma (bf16 in, fp32 accumulate in TMEM) by one elected thread, and the
+// accumulator tile is read back with tcgen05.ld by the epilogue warps that apply the layer's
+// epilogue (bias/ELU, ELU', Gaussian log-density + its gradient, Adam, ...).
 //
 // A slow SIMT kernel with the *same* operand format and the *same* epilogue code is kept as a
 // validation reference for the tensor-core mainloop (tests only; never selected implicitly).
 #pragma once
+
+#include <cuda.h>  // CUtensorMap (types only: the encoder is resolved through cudaGetDriverEntryPoint)
+
+#include <map>
+#include <mutex>
+#include <tuple>
 
 #include "common.cuh"
 
@@ -56,6 +64,20 @@ constexpr int GEMM_ADAM_EPI_WARPS = 24;                // the fused dW+Adam epil
 constexpr int GEMM_SIMT_THREADS = 128 * EPI_GROUPS;    // validation kernel: thread = (row, column group)
 constexpr int GEMM_ACC_STAGES = 2;                     // accumulator tiles in TMEM (epilogue of tile i overlaps mainloop of i+1)
 constexpr int GEMM_SMEM_BUDGET = 208 * 1024;           // operand ring per CTA (one CTA per SM)
+
+// Optional instrumentation (-DGEMM_PROFILE_WAITS, tools/wait_profile.py): cycles the producer / MMA / epilogue roles
+// spend blocked on each mbarrier, summed per (mode, epilogue) over CTAs and launches.  Compiled out by default.
+#ifdef GEMM_PROFILE_WAITS
+static __device__ unsigned long long g_wait_stats[3 * 8 * 8];
+#define WS_T0() const long long ws_t0 = clock64()
+#define WS_ADD(c) atomicAdd(&g_wait_stats[(p.mode * 8 + EPI) * 8 + (c)], (unsigned long long)(clock64() - ws_t0))
+#define WS_INC(c, v) atomicAdd(&g_wait_stats[(p.mode * 8 + EPI) * 8 + (c)], (unsigned long long)(v))
+#else
+#define WS_T0()
+#define WS_ADD(c)
+#define WS_INC(c, v)
+#endif
+enum { WS_PROD_EMPTY = 0, WS_MMA_FULL, WS_MMA_ACC_EMPTY, WS_EPI_ACC_FULL, WS_EPI_BUSY, WS_CTA_TOTAL, WS_TILES, WS_KBLOCKS };
 
 struct GemmOperand {
   const bf16* base;        // model 0
@@ -119,6 +141,7 @@ struct EpiParams {
   int g_tab_n;
   int g_kin;      // true input features
   int g_kaug;     // g_kin + 1 + class columns
+  int g_vec;      // EPI_GRAD_ADAM: 4 / 2 = weight rows are 16- / 8-byte aligned (vector epilogue), 1 = scalar epilogue
   // EPI_GRAD_ADAM
   float* adam_p;
   float* adam_m;
@@ -665,6 +688,206 @@ __device__ __forceinline__ void adam_epilogue_row(const GemmProblem& p, const Ep
 }
 
 // ---------------------------------------------------------------------------------------------
+// Vectorised form of the fused weight-gradient + Adam epilogue (the default; the scalar form above
+// remains for layers whose weight rows are not even 8-byte aligned).  After tcgen05.ld a thread
+// holds 8 columns (weight rows) of ONE input feature k; a 4x4 transpose inside each lane quad
+// (4 shuffles per 4 columns) turns that into 4 CONSECUTIVE k of 2 weight rows, so the optimizer
+// state streams as 16-byte accesses: 6 LDG.128 + 6 STG.128 (+ 2 x 8-byte bf16 shadow stores) per
+// thread and half-chunk instead of 24 + 24 (+ 8) scalar ones for the same bytes.  Memory-level
+// parallelism per resident warp is 4x that of the scalar form, which is what the HBM stream of
+// this kernel is limited by (tools/adam_pattern_bench.cu: 3.6-4.2 -> 4.8 TB/s in this geometry).
+// Used when the weight rows are 16-byte aligned (ld % 4 == 0, VEC = 4).  Measured on B200 (32 models,
+// profiles/r01_experiments.md): decoder heads 261 -> 226 us; with 8-byte aligned rows (ld = 978 or
+// 102, two float2 per row, VEC = 2) the vector form is slower than the scalar one (166 -> 183 us),
+// so those layers keep the scalar epilogue.  The ragged end of the feature range (k4 + 3 >= kin:
+// last partial quad, the bias row k == kin and the class columns k > kin) is loaded / stored
+// element-wise into the same registers.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void quad_transpose4(const float (&x)[4], float (&y)[4], int lane) {
+  const bool hi2 = lane & 2, hi1 = lane & 1;
+  const float r0 = __shfl_xor_sync(0xffffffffu, hi2 ? x[0] : x[2], 2);
+  const float r1 = __shfl_xor_sync(0xffffffffu, hi2 ? x[1] : x[3], 2);
+  const float z0 = hi2 ? r0 : x[0], z1 = hi2 ? r1 : x[1], z2 = hi2 ? x[2] : r0, z3 = hi2 ? x[3] : r1;
+  const float u0 = __shfl_xor_sync(0xffffffffu, hi1 ? z0 : z1, 1);
+  const float u1 = __shfl_xor_sync(0xffffffffu, hi1 ? z2 : z3, 1);
+  const float k0 = hi1 ? z1 : z0, k1 = hi1 ? z3 : z2;
+  y[0] = hi1 ? u0 : k0;
+  y[1] = hi1 ? k0 : u0;
+  y[2] = hi1 ? u1 : k1;
+  y[3] = hi1 ? k1 : u1;
+}
+
+struct AdamVecBuf {
+  int idx[2];  // flat offset of W[n][0] for this thread's two weight rows (or -1)
+  float4 p[2], m[2], v[2];
+};
+
+template <int VEC>
+__device__ __forceinline__ float4 ld_state(const float* a) {
+  if (VEC == 4) return *reinterpret_cast<const float4*>(a);
+  const float2 lo = *reinterpret_cast<const float2*>(a), hi = *reinterpret_cast<const float2*>(a + 2);
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+template <int VEC>
+__device__ __forceinline__ void st_state(float* a, const float4& x) {
+  if (VEC == 4) {
+    *reinterpret_cast<float4*>(a) = x;
+  } else {
+    *reinterpret_cast<float2*>(a) = make_float2(x.x, x.y);
+    *reinterpret_cast<float2*>(a + 2) = make_float2(x.z, x.w);
+  }
+}
+
+// Ragged end of the feature range (quads with k4 + 3 >= kin: last weights, the bias row k == kin, class columns
+// k > kin): element offset inside the flat per-model vector, or -1.  s = shadow row.
+__device__ __forceinline__ int adam_edge_off(const EpiParams& e, int k, int s) {
+  if (k >= e.g_kaug) return -1;
+  const int idx = e.g_tab[(k == e.g_kin ? e.g_tab_n : 0) + s];
+  if (idx < 0) return -1;
+  return idx + ((k < e.g_kin) ? k : (k == e.g_kin ? 0 : k - 1));
+}
+__device__ __forceinline__ float& f4c(float4& x, int r) { return r == 0 ? x.x : (r == 1 ? x.y : (r == 2 ? x.z : x.w)); }
+
+// request p, m, v of this thread's two weight rows, features [k4, k4 + 4); col = first shadow row of the half-chunk.
+// Ragged quads fill the same registers with scalar loads, so they are pipelined like the vector path.
+template <int VEC>
+__device__ __forceinline__ void adam_vec_load(const EpiParams& e, int model, int k4, int col, int ci, AdamVecBuf& b) {
+  const float* P = e.adam_p + model * e.grad_ms;
+  const float* M1 = e.adam_m + model * e.grad_ms;
+  const float* V2 = e.adam_v + model * e.grad_ms;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) b.p[j] = b.m[j] = b.v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (k4 + 3 < e.g_kin) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      b.idx[j] = e.g_tab[col + 4 * j + ci];
+      if (b.idx[j] >= 0) {
+        const int o = b.idx[j] + k4;
+        b.p[j] = ld_state<VEC>(P + o);
+        b.m[j] = ld_state<VEC>(M1 + o);
+        b.v[j] = ld_state<VEC>(V2 + o);
+      }
+    }
+  } else if (k4 < e.g_kaug) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int o = adam_edge_off(e, k4 + r, col + 4 * j + ci);
+        if (o >= 0) {
+          f4c(b.p[j], r) = ld_global_f32(P + o);
+          f4c(b.m[j], r) = ld_global_f32(M1 + o);
+          f4c(b.v[j], r) = ld_global_f32(V2 + o);
+        }
+      }
+    }
+  }
+}
+
+template <int VEC>
+__device__ __forceinline__ void adam_vec_apply(const EpiParams& e, int model, int k4, int col, int ci, int lane, uint32_t taddr,
+                                               bool have_acc, AdamVecBuf& b) {
+  float acc[8];
+  if (have_acc) {
+    tmem_ld8(taddr, acc);  // warp-collective
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  }
+  float g[2][4];
+  {
+    const float x0[4] = {acc[0], acc[1], acc[2], acc[3]}, x1[4] = {acc[4], acc[5], acc[6], acc[7]};
+    quad_transpose4(x0, g[0], lane);
+    quad_transpose4(x1, g[1], lane);
+  }
+  if (k4 >= e.g_kaug) return;
+  const AdamHyper h = *e.adam;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    adam_update(g[j][0], b.p[j].x, b.m[j].x, b.v[j].x, h);
+    adam_update(g[j][1], b.p[j].y, b.m[j].y, b.v[j].y, h);
+    adam_update(g[j][2], b.p[j].z, b.m[j].z, b.v[j].z, h);
+    adam_update(g[j][3], b.p[j].w, b.m[j].w, b.v[j].w, h);
+  }
+  float* P = e.adam_p + model * e.grad_ms;
+  float* M1 = e.adam_m + model * e.grad_ms;
+  float* V2 = e.adam_v + model * e.grad_ms;
+  if (k4 + 3 < e.g_kin) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      if (b.idx[j] < 0) continue;
+      const int o = b.idx[j] + k4;
+      st_state<VEC>(P + o, b.p[j]);
+      st_state<VEC>(M1 + o, b.m[j]);
+      st_state<VEC>(V2 + o, b.v[j]);
+      const int s = col + 4 * j + ci;
+      uint2 pk;
+      pk.x = pack_bf16x2(b.p[j].x, b.p[j].y);
+      pk.y = pack_bf16x2(b.p[j].z, b.p[j].w);
+      *reinterpret_cast<uint2*>(e.sh + model * e.sh_ms + ((long long)(k4 >> 3) * e.sh_rcap + s) * 8 + (k4 & 7)) = pk;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int s = col + 4 * j + ci;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int k = k4 + r;
+        const int o = adam_edge_off(e, k, s);
+        if (o < 0) continue;
+        const float pv = f4c(b.p[j], r);
+        P[o] = pv;
+        M1[o] = f4c(b.m[j], r);
+        V2[o] = f4c(b.v[j], r);
+        if (k < e.g_kin) {
+          e.sh[model * e.sh_ms + ((long long)(k >> 3) * e.sh_rcap + s) * 8 + (k & 7)] = __float2bfloat16_rn(pv);
+        } else if (k == e.g_kin) {
+          e.drv[model * e.drv_ms + e.drv_bias_off + s] = pv + reinterpret_cast<const float*>(e.g_tab + 2 * e.g_tab_n)[s];
+        } else {
+          e.drv[model * e.drv_ms + e.drv_clsb_off + (long long)(k - e.g_kin - 1) * e.drv_clsb_ld + s] = pv;
+        }
+      }
+    }
+  }
+}
+
+template <int GROUPS, int VEC>
+__device__ __forceinline__ void adam_epilogue_vec(const GemmProblem& p, const EpiParams& e, const TileInfo& t, int cg, int kbase,
+                                                  uint32_t taddr_row, bool have_acc, uint64_t* acc_bar, uint32_t acc_parity) {
+  const int lane = threadIdx.x & 31;
+  const int ci = lane & 3, k4 = kbase + (lane >> 2) * 4;
+  const int nhc = p.BN >> 3;
+  const int nh = (nhc - cg + GROUPS - 1) / GROUPS;
+  auto lcol = [&](int h) { return (cg + h * GROUPS) * 8; };
+  AdamVecBuf A;
+  if (nh > 0) adam_vec_load<VEC>(e, t.model, k4, t.n0 + lcol(0), ci, A);
+  if (lane == 0) {
+    constexpr int EPI = EPI_GRAD_ADAM;
+    (void)EPI;
+    WS_T0();
+    mbar_wait(acc_bar, acc_parity, p.dbg, 0xA0000000u);
+    if ((threadIdx.x >> 5) == GEMM_EPI_WARP0) WS_ADD(WS_EPI_ACC_FULL);
+  }
+  __syncwarp();
+  tc_fence_after();
+  if (GROUPS <= 4) {
+    // 16 epilogue warps, 96 registers: the loads of the next half-chunk are in flight during the math of this one
+    AdamVecBuf B;
+    for (int h = 0; h < nh; h += 2) {
+      if (h + 1 < nh) adam_vec_load<VEC>(e, t.model, k4, t.n0 + lcol(h + 1), ci, B);
+      adam_vec_apply<VEC>(e, t.model, k4, t.n0 + lcol(h), ci, lane, taddr_row + lcol(h), have_acc, A);
+      if (h + 2 < nh) adam_vec_load<VEC>(e, t.model, k4, t.n0 + lcol(h + 2), ci, A);
+      if (h + 1 < nh) adam_vec_apply<VEC>(e, t.model, k4, t.n0 + lcol(h + 1), ci, lane, taddr_row + lcol(h + 1), have_acc, B);
+    }
+  } else {
+    for (int h = 0; h < nh; ++h) {
+      adam_vec_apply<VEC>(e, t.model, k4, t.n0 + lcol(h), ci, lane, taddr_row + lcol(h), have_acc, A);
+      if (h + 1 < nh) adam_vec_load<VEC>(e, t.model, k4, t.n0 + lcol(h + 1), ci, A);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Tensor-core kernel: persistent (one CTA per SM, tiles strided by gridDim.x) and warp-specialised.
 //   warps 0..2    bulk-copy producers: operand slabs -> shared-memory ring (full/empty mbarriers)
 //   warp 3        lane 0 issues tcgen05.mma into one of two TMEM accumulator tiles; owns TMEM
@@ -672,8 +895,12 @@ __device__ __forceinline__ void adam_epilogue_row(const GemmProblem& p, const Ep
 // The accumulator is double-buffered (acc_full / acc_empty mbarriers), so the epilogue of tile i —
 // for the weight gradients a long HBM-bound Adam stream — overlaps the mainloop of tile i+1.
 // ---------------------------------------------------------------------------------------------
-template <int EPI, int EW>
-__global__ void __launch_bounds__((GEMM_PROD_WARPS + 1 + EW) * 32, 1) gemm_tc_kernel(const GemmProblem p, const EpiParams e) {
+// VEC (EPI_GRAD_ADAM only): vector width of the optimizer-state accesses, 4 / 2 (adam_epilogue_vec) or 1 (adam_epilogue_row)
+template <int EPI, int EW, int VEC>
+__global__ void __launch_bounds__((GEMM_PROD_WARPS + 1 + EW) * 32, 1) gemm_tc_kernel(const GemmProblem p, const EpiParams e,
+                                                                                     const __grid_constant__ CUtensorMap tmA,
+                                                                                     const __grid_constant__ CUtensorMap tmB,
+                                                                                     const __grid_constant__ CUtensorMap tmB2) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t full_bar[GEMM_MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[GEMM_MAX_STAGES];
@@ -709,82 +936,62 @@ __global__ void __launch_bounds__((GEMM_PROD_WARPS + 1 + EW) * 32, 1) gemm_tc_ke
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+#ifdef GEMM_PROFILE_WAITS
+  const long long ws_cta_t0 = clock64();
+#endif
 
   const bool a_mn = (p.mode == GEMM_DW);
   const bool b_mn = (p.mode != GEMM_NT);
 
-  if (warp < GEMM_PROD_WARPS) {
-    // ===================== producers: 1-D bulk copies of operand slabs =====================
-    // Every producer warp walks the same ring; warp 0 posts the expected byte count, each warp
-    // issues its share of the copies (the transaction count may run ahead of the expectation:
-    // the phase cannot complete before warp 0's arrival).
-    uint32_t it = 0;  // k-blocks issued by this CTA so far (ring position)
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileInfo t = gemm_tile_info(p, tile);
-      if (!t.active) continue;
-      const bf16* Ab = p.A.base + t.model * p.A.model_stride;
-      const bf16* Bb = p.B.base + t.model * p.B.model_stride;
-      for (int kb = t.kb_begin; kb < t.kb_end; ++kb, ++it) {
-        const int s = it % p.nstages;
-        const uint32_t ph = (it / p.nstages) & 1;
-        if (lane == 0) mbar_wait(&empty_bar[s], ph ^ 1, p.dbg, 0xE0000000u | kb);
-        __syncwarp();
-        const int kw = min(GEMM_BK, t.Kc - kb * GEMM_BK);  // multiple of 16
-        uint8_t* As = smem + (size_t)s * stage_bytes;
-        uint8_t* Bs = As + GEMM_A_STAGE_BYTES;
-        // --- copy descriptors ---
-        int nA, nB;
-        uint32_t bytesA, bytesB;
-        if (!a_mn) {
-          nA = kw >> 3;
-          bytesA = GEMM_BM * 16;
-        } else {
-          nA = min(GEMM_BM >> 3, p.A.nchunks - (t.m0 >> 3));
-          bytesA = kw * 16;
-        }
-        if (!b_mn) {
-          nB = kw >> 3;
-          bytesB = BN * 16;
-        } else {
-          nB = min(BN >> 3, p.B.nchunks - (t.n0 >> 3));
-          bytesB = kw * 16;
-        }
-        if (nA < 0) nA = 0;
-        if (nB < 0) nB = 0;
-        if (warp == 0 && lane == 0) mbar_arrive_expect_tx(&full_bar[s], nA * bytesA + nB * bytesB);
-        __syncwarp();
-        // a bulk copy is issued from uniform registers, one lane at a time: spread the copies over the producer warps
-        for (int c = warp + GEMM_PROD_WARPS * lane; c < nA + nB; c += 32 * GEMM_PROD_WARPS) {
-          if (c < nA) {
-            const bf16* src;
-            uint8_t* dst;
-            if (!a_mn) {
-              src = Ab + ((long long)(kb * 8 + c) * p.A.rcap + p.A.row0 + t.m0) * 8;
-              dst = As + (size_t)c * (GEMM_BM * 16);
-            } else {
-              src = Ab + ((long long)((t.m0 >> 3) + c) * p.A.rcap + p.A.row0 + kb * GEMM_BK) * 8;
-              dst = As + (size_t)c * (GEMM_BK * 16);
-            }
-            bulk_g2s(dst, src, bytesA, &full_bar[s]);
-          } else {
-            const int cb = c - nA;
-            const bf16* src;
-            uint8_t* dst;
-            if (!b_mn) {
-              src = Bb + ((long long)(kb * 8 + cb) * p.B.rcap + p.B.row0 + t.n0) * 8;
-              dst = Bs + (size_t)cb * (BN * 16);
-            } else {
-              src = Bb + ((long long)((t.n0 >> 3) + cb) * p.B.rcap + p.B.row0 + kb * GEMM_BK) * 8;
-              dst = Bs + (size_t)cb * (GEMM_BK * 16);
-            }
-            bulk_g2s(dst, src, bytesB, &full_bar[s]);
+  if (warp == 0) {
+    // ===================== producer: TMA tensor loads of operand tiles =====================
+    // A chunk8 buffer is the tensor {rcap x 16 B, chunks, models}; a K-major tile is the box
+    // {rows, 8 chunks} at (row, k-chunk), an MN-major tile the box {64 contraction rows, MN chunks}
+    // at (contraction row, feature chunk).  Boxes are dense in shared memory, which is exactly the
+    // [chunk][row][16 B] slab layout of the UMMA descriptors below; rows / chunks beyond the buffer
+    // are zero-filled by the TMA unit.  A K-major B tile wider than 128 rows takes two boxes
+    // (box extents are limited to 256 elements), multiplied as two N halves.
+    // The whole warp walks the ring (uniform control flow), one elected lane issues.
+    {
+      const uint32_t stage_tx = GEMM_A_STAGE_BYTES + b_stage_bytes;
+      const bool b_split = !b_mn && BN > 128;
+      uint32_t it = 0;  // k-blocks issued by this CTA so far (ring position)
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileInfo t = gemm_tile_info(p, tile);
+        if (!t.active) continue;
+        for (int kb = t.kb_begin; kb < t.kb_end; ++kb, ++it) {
+          const int s = it % p.nstages;
+          const uint32_t ph = (it / p.nstages) & 1;
+          {
+            WS_T0();
+            mbar_wait(&empty_bar[s], ph ^ 1, p.dbg, 0xE0000000u | kb);
+            if (lane == 0) WS_ADD(WS_PROD_EMPTY);
           }
+          uint8_t* As = smem + (size_t)s * stage_bytes;
+          uint8_t* Bs = As + GEMM_A_STAGE_BYTES;
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full_bar[s], stage_tx);
+            if (!a_mn)
+              tma_load_3d(As, &tmA, (p.A.row0 + t.m0) * 2, kb * 8, t.model, &full_bar[s]);
+            else
+              tma_load_3d(As, &tmA, (p.A.row0 + kb * GEMM_BK) * 2, t.m0 >> 3, t.model, &full_bar[s]);
+            if (!b_mn) {
+              tma_load_3d(Bs, &tmB, (p.B.row0 + t.n0) * 2, kb * 8, t.model, &full_bar[s]);
+              if (b_split) tma_load_3d(Bs + 128 * GEMM_BK * 2, &tmB2, (p.B.row0 + t.n0 + 128) * 2, kb * 8, t.model, &full_bar[s]);
+            } else {
+              tma_load_3d(Bs, &tmB, (p.B.row0 + kb * GEMM_BK) * 2, t.n0 >> 3, t.model, &full_bar[s]);
+            }
+          }
+          __syncwarp();
         }
       }
     }
   } else if (warp == GEMM_MMA_WARP) {
     // ===================== UMMA issuer =====================
-    const uint32_t idesc = umma_idesc_bf16(BN, a_mn ? 1 : 0, b_mn ? 1 : 0);
+    const bool b_split = !b_mn && BN > 128;  // K-major B wider than one TMA box: two N halves
+    const int bn0 = b_split ? 128 : BN, bn1 = BN - 128;
+    const uint32_t idesc = umma_idesc_bf16(bn0, a_mn ? 1 : 0, b_mn ? 1 : 0);
+    const uint32_t idesc1 = b_split ? umma_idesc_bf16(bn1, a_mn ? 1 : 0, 0) : 0u;
     uint32_t a_lbo, a_sbo, a_step, b_lbo, b_sbo, b_step;
     if (!a_mn) {
       a_lbo = GEMM_BM * 16;  // next 8-wide K chunk
@@ -796,14 +1003,15 @@ __global__ void __launch_bounds__((GEMM_PROD_WARPS + 1 + EW) * 32, 1) gemm_tc_ke
       a_step = 16 * 16;
     }
     if (!b_mn) {
-      b_lbo = BN * 16;
+      b_lbo = bn0 * 16;
       b_sbo = 128;
-      b_step = 2 * BN * 16;
+      b_step = 2 * bn0 * 16;
     } else {
       b_lbo = 128;
       b_sbo = GEMM_BK * 16;
       b_step = 16 * 16;
     }
+    const uint32_t b1_lbo = bn1 * 16, b1_step = 2 * bn1 * 16;
     if (p.desc_variant & 1) {  // bring-up knob: swapped LBO/SBO meaning
       uint32_t x = a_lbo;
       a_lbo = a_sbo;
@@ -812,38 +1020,75 @@ __global__ void __launch_bounds__((GEMM_PROD_WARPS + 1 + EW) * 32, 1) gemm_tc_ke
       b_lbo = b_sbo;
       b_sbo = x;
     }
-    uint32_t it = 0, j = 0;  // ring position, active tiles done
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileInfo t = gemm_tile_info(p, tile);
-      if (!t.active) continue;
-      const uint32_t a = j & 1, aph = (j >> 1) & 1;
-      if (lane == 0) {
-        mbar_wait(&acc_empty[a], aph ^ 1, p.dbg, 0xB0000000u | tile);  // epilogue has drained this accumulator
+    // One elected lane runs the whole issue loop (the other lanes go to the final barrier).  It is the critical
+    // path of every tile, so a k-block is: one barrier wait, the shared-memory address folded into the low
+    // descriptor words once, then the MMAs back to back with constant increments (see umma_issue).
+    if (elect_one()) {
+      const uint64_t a_desc0 = umma_smem_desc(0, a_lbo, a_sbo), b_desc0 = umma_smem_desc(0, b_lbo, b_sbo);
+      const uint64_t b1_desc0 = umma_smem_desc(0, b1_lbo, 128);
+      const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), b_hi = (uint32_t)(b_desc0 >> 32), b1_hi = (uint32_t)(b1_desc0 >> 32);
+      const uint32_t a_lo0 = (uint32_t)a_desc0, b_lo0 = (uint32_t)b_desc0, b1_lo0 = (uint32_t)b1_desc0;
+      const uint32_t da = a_step >> 4, db = b_step >> 4, db1 = b1_step >> 4;
+      const uint32_t smem0 = smem_u32(smem) >> 4, stage16 = (uint32_t)stage_bytes >> 4;
+      uint32_t it = 0, j = 0;  // ring position, active tiles done
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileInfo t = gemm_tile_info(p, tile);
+        if (!t.active) continue;
+        const uint32_t a = j & 1, aph = (j >> 1) & 1;
+        {
+          WS_T0();
+          mbar_wait(&acc_empty[a], aph ^ 1, p.dbg, 0xB0000000u | tile);  // epilogue has drained this accumulator
+          WS_ADD(WS_MMA_ACC_EMPTY);
+          WS_INC(WS_TILES, 1);
+          WS_INC(WS_KBLOCKS, t.kb_end - t.kb_begin);
+        }
         tc_fence_after();
         const uint32_t tacc = tmem_base + a * ncols;
+        uint32_t s = it % p.nstages, ph = (it / p.nstages) & 1;
         for (int kb = t.kb_begin; kb < t.kb_end; ++kb, ++it) {
-          const int s = it % p.nstages;
-          const uint32_t ph = (it / p.nstages) & 1;
-          mbar_wait(&full_bar[s], ph, p.dbg, 0xF0000000u | kb);
-          tc_fence_after();
-          const int kw = min(GEMM_BK, t.Kc - kb * GEMM_BK);
-          const uint32_t As = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint32_t Bs = As + GEMM_A_STAGE_BYTES;
-          for (int q = 0; q < (kw >> 4); ++q) {
-            uint64_t ad = umma_smem_desc(As + q * a_step, a_lbo, a_sbo);
-            uint64_t bd = umma_smem_desc(Bs + q * b_step, b_lbo, b_sbo);
-            umma_bf16(tacc, ad, bd, idesc, (kb > t.kb_begin || q > 0) ? 1u : 0u);
+          {
+            WS_T0();
+            mbar_wait(&full_bar[s], ph, p.dbg, 0xF0000000u | kb);
+            WS_ADD(WS_MMA_FULL);
           }
-          umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs retire
+          tc_fence_after();
+          const int nq = min(GEMM_BK, t.Kc - kb * GEMM_BK) >> 4;
+          const uint32_t sa = smem0 + s * stage16;  // (shared address of the stage) >> 4
+          const uint32_t alo = a_lo0 + sa, blo = b_lo0 + sa + (GEMM_A_STAGE_BYTES >> 4);
+          const uint32_t b1lo = b1_lo0 + sa + ((GEMM_A_STAGE_BYTES + 128 * GEMM_BK * 2) >> 4);
+          const uint32_t first = kb > t.kb_begin ? 1u : 0u;
+          if (nq == 4 && !b_split) {
+            umma_issue(tacc, alo, a_hi, blo, b_hi, idesc, first);
+            umma_issue(tacc, alo + da, a_hi, blo + db, b_hi, idesc, 1u);
+            umma_issue(tacc, alo + 2 * da, a_hi, blo + 2 * db, b_hi, idesc, 1u);
+            umma_issue(tacc, alo + 3 * da, a_hi, blo + 3 * db, b_hi, idesc, 1u);
+          } else if (nq == 4) {
+            umma_issue(tacc, alo, a_hi, blo, b_hi, idesc, first);
+            umma_issue(tacc + 128, alo, a_hi, b1lo, b1_hi, idesc1, first);
+            umma_issue(tacc, alo + da, a_hi, blo + db, b_hi, idesc, 1u);
+            umma_issue(tacc + 128, alo + da, a_hi, b1lo + db1, b1_hi, idesc1, 1u);
+            umma_issue(tacc, alo + 2 * da, a_hi, blo + 2 * db, b_hi, idesc, 1u);
+            umma_issue(tacc + 128, alo + 2 * da, a_hi, b1lo + 2 * db1, b1_hi, idesc1, 1u);
+            umma_issue(tacc, alo + 3 * da, a_hi, blo + 3 * db, b_hi, idesc, 1u);
+            umma_issue(tacc + 128, alo + 3 * da, a_hi, b1lo + 3 * db1, b1_hi, idesc1, 1u);
+          } else {
+            for (int q = 0; q < nq; ++q) {
+              const uint32_t accum = (first | (uint32_t)q) ? 1u : 0u;
+              umma_issue(tacc, alo + q * da, a_hi, blo + q * db, b_hi, idesc, accum);
+              if (b_split) umma_issue(tacc + 128, alo + q * da, a_hi, b1lo + q * db1, b1_hi, idesc1, accum);
+            }
+          }
+          umma_commit_1t(&empty_bar[s]);  // frees the smem slot once these MMAs retire
+          if (++s == (uint32_t)p.nstages) s = 0, ph ^= 1;
         }
         if (t.kb_end > t.kb_begin)
-          umma_commit(&acc_full[a]);  // accumulator complete
+          umma_commit_1t(&acc_full[a]);  // accumulator complete
         else
           mbar_arrive(&acc_full[a]);  // empty contraction: the epilogue uses zeros
+        ++j;
       }
-      __syncwarp();
-      ++j;
     }
+    __syncwarp();
   } else if (warp >= GEMM_EPI_WARP0) {
     // ===================== epilogue: TMEM -> registers -> fused math -> HBM =====================
     const int q = warp & 3;                       // TMEM lane quarter this warp may access
@@ -856,9 +1101,16 @@ __global__ void __launch_bounds__((GEMM_PROD_WARPS + 1 + EW) * 32, 1) gemm_tc_ke
       const bool have_acc = t.kb_end > t.kb_begin;
       const uint32_t taddr_row = tmem_base + a * ncols + ((uint32_t)(q * 32) << 16);
       if (EPI == EPI_GRAD_ADAM) {
-        adam_epilogue_row<EW / 4>(p, e, t, cg, t.m0 + q * 32 + lane, taddr_row, have_acc, &acc_full[a], aph);
+        if (VEC >= 2)
+          adam_epilogue_vec<EW / 4, (VEC >= 2 ? VEC : 2)>(p, e, t, cg, t.m0 + q * 32, taddr_row, have_acc, &acc_full[a], aph);
+        else
+          adam_epilogue_row<EW / 4>(p, e, t, cg, t.m0 + q * 32 + lane, taddr_row, have_acc, &acc_full[a], aph);
       } else {
-        if (lane == 0) mbar_wait(&acc_full[a], aph, p.dbg, 0xA0000000u | tile);  // one poller per warp
+        if (lane == 0) {
+          WS_T0();
+          mbar_wait(&acc_full[a], aph, p.dbg, 0xA0000000u | tile);  // one poller per warp
+          if (warp == GEMM_EPI_WARP0) WS_ADD(WS_EPI_ACC_FULL);
+        }
         __syncwarp();
         tc_fence_after();
         RowCtx rc;
@@ -875,8 +1127,14 @@ __global__ void __launch_bounds__((GEMM_PROD_WARPS + 1 + EW) * 32, 1) gemm_tc_ke
     }
   }
 
+#ifdef GEMM_PROFILE_WAITS
+  if (lane == 0 && warp == GEMM_EPI_WARP0) WS_INC(WS_EPI_BUSY, clock64() - ws_cta_t0);  // epilogue warp: loop time incl. waits
+#endif
   tc_fence_before();
   __syncthreads();
+#ifdef GEMM_PROFILE_WAITS
+  if (threadIdx.x == 0) WS_INC(WS_CTA_TOTAL, clock64() - ws_cta_t0);
+#endif
   if (warp == GEMM_MMA_WARP) tmem_dealloc(tmem_base, GEMM_ACC_STAGES * ncols);
 }
 
@@ -962,7 +1220,55 @@ inline int gemm_num_sms() {
   return n;
 }
 
-template <int EPI>
+// Tensor map of a chunk8 operand buffer: {rcap rows x 16 B (as 2 x 8-byte elements), chunks, models}, box =
+// {box_rows, box_chunks, 1}.  Encoded on the host (driver entry point resolved at run time, no libcuda link) and
+// cached: a plan launches the same few dozen (buffer, box) combinations every step.
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline cudaError_t gemm_c8_map(CUtensorMap* out, const GemmOperand& op, int n_models, int box_rows, int box_chunks) {
+  static TmapEncodeFn encode = nullptr;
+  static std::mutex mu;
+  typedef std::tuple<const void*, long long, int, int, int, int, int> Key;
+  static std::map<Key, CUtensorMap> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!encode) {
+    void* fp = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t err = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q);
+    if (err != cudaSuccess) return err;
+    if (!fp || q != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
+    encode = (TmapEncodeFn)fp;
+  }
+  const Key key(op.base, op.model_stride, op.rcap, op.nchunks, n_models, box_rows, box_chunks);
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return cudaSuccess;
+  }
+  const cuuint64_t chunk_bytes = (cuuint64_t)op.rcap * 16;
+  cuuint64_t model_bytes = (cuuint64_t)op.model_stride * 2;
+  if (n_models <= 1 || model_bytes == 0) model_bytes = chunk_bytes * (cuuint64_t)op.nchunks;
+  if ((model_bytes & 15) || (reinterpret_cast<uintptr_t>(op.base) & 15) || op.rcap < 1 || op.nchunks < 1 || box_rows < 1 ||
+      box_rows > 128 || box_chunks < 1 || box_chunks > 256)
+    return cudaErrorInvalidValue;
+  const cuuint64_t dims[3] = {(cuuint64_t)op.rcap * 2, (cuuint64_t)op.nchunks, (cuuint64_t)(n_models < 1 ? 1 : n_models)};
+  const cuuint64_t strides[2] = {chunk_bytes, model_bytes};
+  const cuuint32_t box[3] = {(cuuint32_t)box_rows * 2, (cuuint32_t)box_chunks, 1};
+  const cuuint32_t es[3] = {1, 1, 1};
+  CUtensorMap m;
+  CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<bf16*>(op.base), dims, strides, box, es,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+  if (cache.size() > 4096) cache.clear();  // plans come and go (tests): bound the cache
+  cache[key] = m;
+  *out = m;
+  return cudaSuccess;
+}
+
+template <int EPI, int VEC = 1>
 inline cudaError_t gemm_launch_t(GemmProblem p, const EpiParams& e, int n_models, int impl, cudaStream_t st) {
   p.n_models = n_models;
   const int total = p.tiles_n * p.tiles_m * p.ksplit * n_models;
@@ -975,16 +1281,31 @@ inline cudaError_t gemm_launch_t(GemmProblem p, const EpiParams& e, int n_models
   // streaming loads/stores go through L1: a shallow operand ring leaves the rest of the 256 KB as L1
   if (EPI == EPI_GRAD_ADAM && p.nstages > 2) p.nstages = 2;
   size_t smem = (size_t)p.nstages * (GEMM_A_STAGE_BYTES + p.BN * GEMM_BK * 2);
+  // fused Adam epilogue (scalar and vector form): 24 warps x 72 registers, its HBM stream scales with resident warps
   constexpr int EW = (EPI == EPI_GRAD_ADAM) ? GEMM_ADAM_EPI_WARPS : GEMM_EPI_WARPS;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t err =
-        cudaFuncSetAttribute(gemm_tc_kernel<EPI, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BUDGET + 4096);
+        cudaFuncSetAttribute(gemm_tc_kernel<EPI, EW, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BUDGET + 4096);
     if (err != cudaSuccess) return err;
     attr_set = true;
   }
+  // operand tensor maps (see the producer warp of gemm_tc_kernel)
+  CUtensorMap tmA, tmB, tmB2;
+  const bool a_mn = p.mode == GEMM_DW, b_mn = p.mode != GEMM_NT;
+  cudaError_t err = a_mn ? gemm_c8_map(&tmA, p.A, n_models, GEMM_BK, GEMM_BM / 8) : gemm_c8_map(&tmA, p.A, n_models, GEMM_BM, GEMM_BK / 8);
+  if (err != cudaSuccess) return err;
+  if (b_mn) {
+    err = gemm_c8_map(&tmB, p.B, n_models, GEMM_BK, p.BN / 8);
+    tmB2 = tmB;
+  } else {
+    err = gemm_c8_map(&tmB, p.B, n_models, p.BN > 128 ? 128 : p.BN, GEMM_BK / 8);
+    if (err == cudaSuccess && p.BN > 128) err = gemm_c8_map(&tmB2, p.B, n_models, p.BN - 128, GEMM_BK / 8);
+    if (p.BN <= 128) tmB2 = tmB;
+  }
+  if (err != cudaSuccess) return err;
   const int grid = total < gemm_num_sms() ? total : gemm_num_sms();  // persistent: one CTA per SM
-  gemm_tc_kernel<EPI, EW><<<grid, (GEMM_PROD_WARPS + 1 + EW) * 32, smem, st>>>(p, e);
+  gemm_tc_kernel<EPI, EW, VEC><<<grid, (GEMM_PROD_WARPS + 1 + EW) * 32, smem, st>>>(p, e, tmA, tmB, tmB2);
   return cudaGetLastError();
 }
 
@@ -996,7 +1317,9 @@ inline cudaError_t gemm_launch(int epi, const GemmProblem& p, const EpiParams& e
     case EPI_LIN_C8: return gemm_launch_t<EPI_LIN_C8>(p, e, n_models, impl, st);
     case EPI_DACT_C8: return gemm_launch_t<EPI_DACT_C8>(p, e, n_models, impl, st);
     case EPI_GRAD: return gemm_launch_t<EPI_GRAD>(p, e, n_models, impl, st);
-    case EPI_GRAD_ADAM: return gemm_launch_t<EPI_GRAD_ADAM>(p, e, n_models, impl, st);
+    case EPI_GRAD_ADAM:
+      if (impl != GEMM_IMPL_SIMT && e.g_vec == 4) return gemm_launch_t<EPI_GRAD_ADAM, 4>(p, e, n_models, impl, st);
+      return gemm_launch_t<EPI_GRAD_ADAM>(p, e, n_models, impl, st);
     case EPI_DECLOSS: return gemm_launch_t<EPI_DECLOSS>(p, e, n_models, impl, st);
     case EPI_DECOUT: return gemm_launch_t<EPI_DECOUT>(p, e, n_models, impl, st);
   }

@@ -76,7 +76,8 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamArgs a) {
       p[idx] = pv;
     }
     if (si < 0 || idx < a.segs[si].off || (si + 1 < a.nseg && idx >= a.segs[si + 1].off)) si = seg_find(a.segs, a.nseg, idx);
-    write_derived(a.segs[si], idx, pv, sh, dv);
+    // tensors start on 16-byte boundaries: an index in the padding after a segment belongs to no tensor
+    if (idx - a.segs[si].off < a.segs[si].rows * a.segs[si].cols) write_derived(a.segs[si], idx, pv, sh, dv);
   }
 }
 

@@ -56,6 +56,7 @@ struct drvae_plan {
   Seg* d_segs = nullptr;
   std::vector<int> h_tabs;  // gradient-epilogue tables of every weight (see make_shadow)
   int* d_tabs = nullptr;
+  int adam_vec_max = 4;       // debug knob (DRVAE_B200_ADAM_VEC): cap on the vector width of the fused Adam epilogue
   bool wn = false;            // layers.WeightNormLinear instead of nn.Linear
   std::vector<WnRow> wn_rows;
   WnRow* d_wn_rows = nullptr;
@@ -124,6 +125,9 @@ int add_tensor(drvae_plan* pl, const std::string& name, int rows, int cols) {
   t.name = name;
   t.rows = rows;
   t.cols = cols;
+  // every tensor starts on a 16-byte boundary of the flat vector (vector accesses of the fused Adam epilogue); the
+  // padding elements are zero parameters with zero gradients and stay zero
+  pl->P = round_up(pl->P, 4);
   t.off = pl->P;
   pl->P += rows * (cols > 0 ? cols : 1);
   pl->tensors.push_back(t);
@@ -400,6 +404,7 @@ extern "C" int drvae_plan_create(const drvae_arch_t* a, int n_models, drvae_plan
     r_dz1[0] = p0, r_dz1[1] = pl->P - p0, p0 = pl->P;
   }
   build_gauss_block(pl, pl->dec, "decoder_x", Z, 0, a->n_dec_x, a->dec_x, X, true);
+  pl->P = round_up(pl->P, 4);  // model stride of the flat vectors: 16-byte aligned
   r_dec[0] = p0, r_dec[1] = pl->P - p0;
   // backward completes the blocks in this order (run_step)
   if (pl->has_fprop) {
@@ -496,6 +501,7 @@ extern "C" int drvae_plan_create(const drvae_arch_t* a, int n_models, drvae_plan
   cudaMemset(pl->arena, 0, pl->arena_bytes);
   cudaMalloc(&pl->d_dyn, sizeof(StepDyn));
   cudaMemset(pl->d_dyn, 0, sizeof(StepDyn));
+  if (const char* knob = getenv("DRVAE_B200_ADAM_VEC")) pl->adam_vec_max = atoi(knob);  // measurement knob
   cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking);
   for (cudaEvent_t* ev : {&pl->ev_fork, &pl->ev_qy, &pl->ev_side_fwd, &pl->ev_side_bwd})
     cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
@@ -813,6 +819,11 @@ struct Exec {
     e.g_kin = W.kin;
     e.g_kaug = W.kaug;
     if (fused) {
+      // vector width of the optimizer-state accesses: weight rows W[n][:] start at w_off + n * ld floats
+      // (16-byte accesses when every row is 16-byte aligned, else the scalar epilogue: gemm.cuh, adam_epilogue_vec)
+      bool al4 = W.ld % 4 == 0 && v.params.ms % 4 == 0;
+      for (int w = 0; w < W.ntens; ++w) al4 = al4 && W.w_off[w] % 4 == 0;
+      e.g_vec = (al4 && pl->adam_vec_max >= 4) ? 4 : 1;
       e.adam_p = v.params.p;
       e.adam_m = v.adam_m.p;
       e.adam_v = v.adam_v.p;
@@ -1421,6 +1432,25 @@ extern "C" int drvae_adam_step(drvae_plan_t* pl, const drvae_hparams_t* hp, void
   int rc = push_dyn(pl, make_dyn(nullptr, hp, false), (cudaStream_t)stream);
   if (rc) return rc;
   return run_adam(pl, hp, 1, (cudaStream_t)stream);
+}
+
+// Instrumented builds only (-DGEMM_PROFILE_WAITS): copy out (and optionally clear) the per-(mode, epilogue) barrier
+// wait counters of gemm.cuh; a normal build reports that the counters are not compiled in.
+extern "C" int drvae_debug_wait_stats(unsigned long long* out, int reset) {
+#ifdef GEMM_PROFILE_WAITS
+  cudaError_t err = cudaDeviceSynchronize();
+  if (err == cudaSuccess && out) err = cudaMemcpyFromSymbol(out, g_wait_stats, sizeof(unsigned long long) * 3 * 8 * 8);
+  if (err == cudaSuccess && reset) {
+    static unsigned long long zeros[3 * 8 * 8];
+    err = cudaMemcpyToSymbol(g_wait_stats, zeros, sizeof(zeros));
+  }
+  if (err != cudaSuccess) return set_cuda_error("drvae_debug_wait_stats", err);
+  return 0;
+#else
+  (void)out;
+  (void)reset;
+  return set_error("drvae_debug_wait_stats: library built without -DGEMM_PROFILE_WAITS");
+#endif
 }
 
 extern "C" int drvae_set_graph(drvae_plan_t* pl, int enable) {

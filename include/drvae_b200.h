@@ -161,6 +161,9 @@ long long drvae_plan_launch_count(const drvae_plan_t* plan); /* kernels launched
  * receives lines "phase:kernel launches total_ms". */
 int drvae_profile_begin(drvae_plan_t* plan);
 int drvae_profile_end(drvae_plan_t* plan, char* out, int cap);
+/* Barrier-wait cycle counters of the GEMM kernel roles, [3 modes][8 epilogues][8 counters]; only in libraries built
+ * with -DGEMM_PROFILE_WAITS (tools/wait_profile.py), otherwise an error status. */
+int drvae_debug_wait_stats(unsigned long long* out, int reset);
 int drvae_debug_buffer(drvae_plan_t* plan, const char* name, void** ptr, long long* model_stride_bytes,
                        long long* bytes, int* rcap, int* fcap);
 int drvae_debug_gemm(int impl, int mode, const void* A, int a_rcap, int a_nchunks, long long a_ms,

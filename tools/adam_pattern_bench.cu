@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 struct H { float lr, b1, b2, eps, wd, isb; };
 __device__ __forceinline__ void upd(float g, float& p, float& m, float& v, const H& h) {
@@ -235,6 +236,230 @@ __global__ void __launch_bounds__(256, 2) k_tile_cpasync(float* P, float* M, flo
   }
 }
 
+
+// P4: persistent geometry, optimizer state staged through shared memory by the bulk-copy (TMA) engine: producer warps
+// issue one 512-byte copy per (array, weight row) of a half-chunk (8 weight rows x 128 k) into a ring of NST stages,
+// 4 quarter-warps of a column group consume a stage.  In-flight bytes are set by the ring, not by registers x warps.
+// BULK_ST: results go back into the stage and a store warp writes them out with bulk shared->global copies.
+__device__ __forceinline__ unsigned s32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mb_init(unsigned long long* b, unsigned c) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(b)), "r"(c)); }
+__device__ __forceinline__ void mb_expect(unsigned long long* b, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(b)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mb_arrive(unsigned long long* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(b)) : "memory"); }
+__device__ __forceinline__ void mb_wait(unsigned long long* b, unsigned par, int tag = 0) {
+  for (unsigned spin = 0;; ++spin) {
+    unsigned ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(s32(b)), "r"(par) : "memory");
+    if (ok) return;
+    if (spin > (1u << 22)) {  // watchdog: a protocol bug must not hang the box
+      printf("mb_wait timeout: block %d warp %d tag %d parity %u\n", blockIdx.x, threadIdx.x >> 5, tag, par);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(dst)), "l"(src), "r"(bytes), "r"(s32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(s32(src)), "r"(bytes) : "memory");
+}
+
+template <int EW, int NST, int PW, int BULK_ST>
+__global__ void __launch_bounds__((EW + 4) * 32, 1) k_tile_bulk(float* P, float* M, float* V, __nv_bfloat16* S, int rows, int ld, int BN, int tiles_m,
+                                                                 int tiles_n, long long ms, H h, int total_tiles, int reserve_bytes) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  __shared__ __align__(8) unsigned long long full[NST], empty[NST], done[NST];
+  constexpr int PITCH = 132;  // floats per staged weight-row segment (128 + one 16-byte slot for misaligned rows)
+  constexpr int STAGE = 3 * 8 * PITCH;
+  constexpr int GROUPS = EW / 4;
+  float* ring = reinterpret_cast<float*>(smraw + reserve_bytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NST; ++s) { mb_init(&full[s], 1); mb_init(&empty[s], BULK_ST ? 1 : 4); mb_init(&done[s], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int nhc = BN >> 3, per = tiles_m * tiles_n;
+  if (warp < PW) {
+    unsigned g = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int model = tile / per, mn = tile % per, tile_m = mn % tiles_m, tile_n = mn / tiles_m;
+      const int k0 = tile_m * 128;
+      const unsigned kbytes = (unsigned)min(128, ld - k0) * 4u;
+      for (int hc = 0; hc < nhc; ++hc, ++g) {
+        const int slot = g % NST;
+        const unsigned ph = (g / NST) & 1;
+        if (lane == 0) mb_wait(&empty[slot], ph ^ 1, 100 + slot);
+        __syncwarp();
+        const int n0 = tile_n * BN + hc * 8;
+        const int nr = max(0, min(8, rows - n0));
+        if (warp == 0 && lane == 0) {
+          if (nr > 0) mb_expect(&full[slot], 3u * nr * kbytes); else mb_arrive(&full[slot]);
+        }
+        __syncwarp();
+        const int c = warp + PW * lane;
+        if (c < 24) {
+          const int a = c >> 3, i = c & 7;
+          if (i < nr) {
+            const float* src = (a == 0 ? P : (a == 1 ? M : V)) + model * ms + (long long)(n0 + i) * ld + k0;
+            bulk_g2s(ring + (size_t)slot * STAGE + (a * 8 + i) * PITCH, src, kbytes, &full[slot]);
+          }
+        }
+      }
+    }
+  } else if (BULK_ST && warp == 3) {
+    unsigned g = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int model = tile / per, mn = tile % per, tile_m = mn % tiles_m, tile_n = mn / tiles_m;
+      const int k0 = tile_m * 128;
+      const unsigned kbytes = (unsigned)min(128, ld - k0) * 4u;
+      for (int hc = 0; hc < nhc; ++hc, ++g) {
+        const int slot = g % NST;
+        const unsigned ph = (g / NST) & 1;
+        if (lane == 0) mb_wait(&done[slot], ph, 200 + slot);
+        __syncwarp();
+        const int n0 = tile_n * BN + hc * 8;
+        const int nr = max(0, min(8, rows - n0));
+        if (lane < 24) {
+          const int a = lane >> 3, i = lane & 7;
+          if (i < nr) {
+            float* dst = (a == 0 ? P : (a == 1 ? M : V)) + model * ms + (long long)(n0 + i) * ld + k0;
+            bulk_s2g(dst, ring + (size_t)slot * STAGE + (a * 8 + i) * PITCH, kbytes);
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        __syncwarp();
+        if (lane == 0) mb_arrive(&empty[slot]);
+      }
+    }
+    if (lane < 24) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  } else if (warp >= 4) {
+    const int q = warp & 3, cg = (warp - 4) >> 2;
+    unsigned j = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
+      const int model = tile / per, mn = tile % per, tile_m = mn % tiles_m, tile_n = mn / tiles_m;
+      const int kk = q * 32 + lane, k = tile_m * 128 + kk;
+      const bool kok = k < ld;
+      const int rcap = tiles_n * BN;
+      float* p = P + model * ms + k; float* m = M + model * ms + k; float* v = V + model * ms + k;
+      __nv_bfloat16* s = S + model * ms;
+      for (int hc = cg; hc < nhc; hc += GROUPS) {
+        const unsigned g = j * nhc + hc;
+        const int slot = g % NST;
+        const unsigned ph = (g / NST) & 1;
+        if (lane == 0) mb_wait(&full[slot], ph, 300 + slot);
+        __syncwarp();
+        float* st = ring + (size_t)slot * STAGE + kk;
+        const int n0 = tile_n * BN + hc * 8;
+        float pv[8], mv[8], vv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { pv[i] = st[i * PITCH]; mv[i] = st[(8 + i) * PITCH]; vv[i] = st[(16 + i) * PITCH]; }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) upd(1e-3f, pv[i], mv[i], vv[i], h);
+        if (kok) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int n = n0 + i;
+            if (n < rows) {
+              long long idx = (long long)n * ld;
+              if (BULK_ST) { st[i * PITCH] = pv[i]; st[(8 + i) * PITCH] = mv[i]; st[(16 + i) * PITCH] = vv[i]; }
+              else { p[idx] = pv[i]; m[idx] = mv[i]; v[idx] = vv[i]; }
+              s[((long long)(k >> 3) * rcap + n) * 8 + (k & 7)] = __float2bfloat16_rn(pv[i]);
+            }
+          }
+        }
+        if (BULK_ST) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mb_arrive(BULK_ST ? &done[slot] : &empty[slot]);
+      }
+    }
+  }
+}
+
+
+// P5: persistent geometry, 16-byte accesses: after a 4x4 lane-quad transpose of the accumulators (not modelled here) a
+// thread owns 4 consecutive k of 2 of the 8 weight rows of a half-chunk: 6 x LDG.128 / STG.128 instead of 24 scalar
+// accesses for the same bytes.  VEC = 4: float4 (rows 16-byte aligned), VEC = 2: two float2 per row (8-byte aligned
+// rows, e.g. ld = 978).  DB = 1: the loads of the next half-chunk are issued before the math of the current one.
+template <int EW, int VEC, int DB>
+__global__ void __launch_bounds__(EW * 32 + 128, 1) k_tile_v4(float* P, float* M, float* V, __nv_bfloat16* S, int rows, int ld, int BN, int tiles_m,
+                                                              int tiles_n, long long ms, H h, int total_tiles) {
+  extern __shared__ float sm[];
+  if (sm[0] == 123.f) return;
+  const int warp = (threadIdx.x >> 5) - 4, lane = threadIdx.x & 31;
+  if (warp < 0) return;
+  const int cg = warp >> 2, ngroups = EW / 4, q = warp & 3;
+  const int ci = lane & 3, kg = lane >> 2;
+  const int nhc = BN >> 3;
+  struct Buf { float4 p[2], m[2], v[2]; };
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int per = tiles_m * tiles_n;
+    const int model = tile / per, mn = tile % per;
+    const int tile_m = mn % tiles_m, tile_n = mn / tiles_m;
+    const int k4 = tile_m * 128 + q * 32 + kg * 4;
+    const bool kok = k4 + 3 < ld;
+    float* p = P + model * ms + k4; float* m = M + model * ms + k4; float* v = V + model * ms + k4;
+    __nv_bfloat16* s = S + model * ms;
+    const int rcap = tiles_n * BN;
+    auto load = [&](int hc, Buf& b) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int n = tile_n * BN + hc * 8 + j * 4 + ci;
+        b.p[j] = b.m[j] = b.v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n < rows && kok) {
+          const long long idx = (long long)n * ld;
+          if (VEC == 4) {
+            b.p[j] = *reinterpret_cast<const float4*>(p + idx); b.m[j] = *reinterpret_cast<const float4*>(m + idx); b.v[j] = *reinterpret_cast<const float4*>(v + idx);
+          } else {
+            float2 a0 = *reinterpret_cast<const float2*>(p + idx), a1 = *reinterpret_cast<const float2*>(p + idx + 2);
+            float2 b0 = *reinterpret_cast<const float2*>(m + idx), b1 = *reinterpret_cast<const float2*>(m + idx + 2);
+            float2 c0 = *reinterpret_cast<const float2*>(v + idx), c1 = *reinterpret_cast<const float2*>(v + idx + 2);
+            b.p[j] = make_float4(a0.x, a0.y, a1.x, a1.y); b.m[j] = make_float4(b0.x, b0.y, b1.x, b1.y); b.v[j] = make_float4(c0.x, c0.y, c1.x, c1.y);
+          }
+        }
+      }
+    };
+    auto apply = [&](int hc, Buf& b) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        upd(1e-3f, b.p[j].x, b.m[j].x, b.v[j].x, h); upd(1e-3f, b.p[j].y, b.m[j].y, b.v[j].y, h);
+        upd(1e-3f, b.p[j].z, b.m[j].z, b.v[j].z, h); upd(1e-3f, b.p[j].w, b.m[j].w, b.v[j].w, h);
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int n = tile_n * BN + hc * 8 + j * 4 + ci;
+        if (n < rows && kok) {
+          const long long idx = (long long)n * ld;
+          if (VEC == 4) {
+            *reinterpret_cast<float4*>(p + idx) = b.p[j]; *reinterpret_cast<float4*>(m + idx) = b.m[j]; *reinterpret_cast<float4*>(v + idx) = b.v[j];
+          } else {
+            *reinterpret_cast<float2*>(p + idx) = make_float2(b.p[j].x, b.p[j].y); *reinterpret_cast<float2*>(p + idx + 2) = make_float2(b.p[j].z, b.p[j].w);
+            *reinterpret_cast<float2*>(m + idx) = make_float2(b.m[j].x, b.m[j].y); *reinterpret_cast<float2*>(m + idx + 2) = make_float2(b.m[j].z, b.m[j].w);
+            *reinterpret_cast<float2*>(v + idx) = make_float2(b.v[j].x, b.v[j].y); *reinterpret_cast<float2*>(v + idx + 2) = make_float2(b.v[j].z, b.v[j].w);
+          }
+          __nv_bfloat162 lo = __floats2bfloat162_rn(b.p[j].x, b.p[j].y), hi = __floats2bfloat162_rn(b.p[j].z, b.p[j].w);
+          uint2 pk = make_uint2(*reinterpret_cast<unsigned*>(&lo), *reinterpret_cast<unsigned*>(&hi));
+          *reinterpret_cast<uint2*>(s + ((long long)(k4 >> 3) * rcap + n) * 8 + (k4 & 7)) = pk;
+        }
+      }
+    };
+    if (DB) {
+      Buf A, B;
+      int hc = cg;
+      if (hc < nhc) load(hc, A);
+      for (; hc < nhc; hc += 2 * ngroups) {
+        if (hc + ngroups < nhc) load(hc + ngroups, B);
+        apply(hc, A);
+        if (hc + 2 * ngroups < nhc) load(hc + 2 * ngroups, A);
+        if (hc + ngroups < nhc) apply(hc + ngroups, B);
+      }
+    } else {
+      Buf A;
+      for (int hc = cg; hc < nhc; hc += ngroups) { load(hc, A); apply(hc, A); }
+    }
+  }
+}
+
 // P2: row-linear: CTA handles RN consecutive rows n, all k; thread t handles k = t, t+256, ... for each row; NB rows batched.
 template <int NB>
 __global__ void k_rows(float* P, float* M, float* V, __nv_bfloat16* S, int rows, int ld, int RN, long long ms, H h) {
@@ -262,7 +487,9 @@ __global__ void k_rows(float* P, float* M, float* V, __nv_bfloat16* S, int rows,
   }
 }
 
-int main() {
+int main(int argc, char** argv) {
+  setvbuf(stdout, NULL, _IONBF, 0);
+  const bool only_bulk = argc > 1;
   const int E = 32, rows = 1956, ld = 600;  // decoder heads
   const long long ms = (long long)rows * ld, total = ms * E;
   float *P, *M, *V; __nv_bfloat16* S;
@@ -271,6 +498,7 @@ int main() {
   H h{5e-4f, 0.9f, 0.999f, 1e-8f, 0.05f, 1.f};
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   auto timeit = [&](const char* name, auto launch) {
+    if (only_bulk && strncmp(name, "bulk", 4) != 0 && strncmp(name, "linear", 6) != 0 && strncmp(name, "persistent 148 CTA", 18) != 0) return;
     for (int i = 0; i < 3; ++i) launch();
     cudaEventRecord(e0);
     const int R = 10;
@@ -323,6 +551,26 @@ int main() {
       timeit(nm, [&] { k_tile_pw<EW, NB><<<148, EW * 32 + 128, SM * 1024>>>(P, M, V, S, rows, ld, BN, tiles_m, tiles_n, ms, h, total_tiles); }); \
     }
     PW(16, 8, 200) PW(16, 8, 100) PW(20, 8, 100) PW(24, 8, 100) PW(28, 8, 100) PW(28, 4, 100) PW(28, 8, 200) PW(24, 4, 100) PW(16, 16, 100)
+
+#define BK_(EW, NST, PW, BST, RES)                                                                                        \
+    {                                                                                                                    \
+      const int smem = RES * 1024 + NST * 3 * 8 * 132 * 4;                                                                \
+      cudaFuncSetAttribute(k_tile_bulk<EW, NST, PW, BST>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);             \
+      char nm[128];                                                                                                      \
+      snprintf(nm, sizeof(nm), "bulk-staged: %d epi warps, %d stages, %d prod, st=%d, +%dKB", EW, NST, PW, BST, RES);     \
+      timeit(nm, [&] { k_tile_bulk<EW, NST, PW, BST><<<148, (EW + 4) * 32, smem>>>(P, M, V, S, rows, ld, BN, tiles_m, tiles_n, ms, h, total_tiles, RES * 1024); }); \
+    }
+
+#define V4_(EW, VEC, DB, SM)                                                                                              \
+    {                                                                                                                    \
+      cudaFuncSetAttribute(k_tile_v4<EW, VEC, DB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM * 1024);               \
+      char nm[128];                                                                                                      \
+      snprintf(nm, sizeof(nm), "bulk-alt vec%d: persistent, %d epi warps, db=%d, %d KB smem", VEC, EW, DB, SM);           \
+      timeit(nm, [&] { k_tile_v4<EW, VEC, DB><<<148, EW * 32 + 128, SM * 1024>>>(P, M, V, S, rows, ld, BN, tiles_m, tiles_n, ms, h, total_tiles); }); \
+    }
+    V4_(16, 4, 0, 100) V4_(16, 4, 1, 100) V4_(24, 4, 0, 100) V4_(24, 4, 1, 100) V4_(16, 4, 1, 200) V4_(16, 2, 1, 100) V4_(24, 2, 0, 100) V4_(24, 2, 1, 100) V4_(12, 4, 1, 100) V4_(8, 4, 1, 100)
+    PW(16, 8, 100) PW(24, 8, 100)
+    BK_(16, 4, 3, 0, 96) BK_(16, 8, 3, 0, 96) BK_(16, 8, 1, 0, 96) BK_(16, 8, 3, 0, 0) BK_(16, 12, 3, 0, 0) BK_(16, 8, 3, 1, 96)
     timeit("p16: grid 1280 (one tile each), 512 thr, 200KB", [&] { k_tile_p16<0><<<1280, 512, 200 * 1024>>>(P, M, V, S, rows, ld, BN, tiles_m, tiles_n, ms, h, total_tiles, 0); });
     timeit("p16: grid 1280 (one tile each), 512 thr, 96KB", [&] { k_tile_p16<0><<<1280, 512, 98304>>>(P, M, V, S, rows, ld, BN, tiles_m, tiles_n, ms, h, total_tiles, 0); });
     timeit("p16: grid 296 persistent, 512 thr, 96KB (2/SM)", [&] { k_tile_p16<0><<<296, 512, 98304>>>(P, M, V, S, rows, ld, BN, tiles_m, tiles_n, ms, h, total_tiles, 0); });

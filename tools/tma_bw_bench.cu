@@ -22,7 +22,8 @@ __device__ __forceinline__ void tma3(void* dst, const CUtensorMap* m, int c0, in
 
 // operand: chunk8 buffer [nchunks][rcap][8] bf16; a "stage" = A tile (128 rows x 8 chunks = 16 KB) + B tile (256 rows x 8 chunks = 32 KB)
 template <int MODE>  // 0: 1-D bulk copies from one thread; 1: 1-D bulk copies from 3 warps; 2: TMA tensor (2 KB inner boxes)
-__global__ void __launch_bounds__(128) k(const uint8_t* base, const CUtensorMap* tm, int rcap, int nchunks, int iters, int S) {
+                     // 3: dX pattern (B operand MN-major: 32 copies of 1 KB) from 3 warps; 4: dX pattern, TMA tensor (1 KB inner box x 32 chunks)
+__global__ void __launch_bounds__(128) k(const uint8_t* base, const CUtensorMap* tm, const CUtensorMap* tm2, int rcap, int nchunks, int iters, int S) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full[8];
   const int stage_bytes = 48 * 1024;
@@ -50,6 +51,21 @@ __global__ void __launch_bounds__(128) k(const uint8_t* base, const CUtensorMap*
         if (warp < 3) for (int c = warp + 3 * lane; c < 16; c += 96) {
           if (c < 8) bulk(dst + c * 2048, base + ((size_t)(kb * 8 + c) * rcap + row0) * 16, 2048, &full[s]);
           else bulk(dst + 16384 + (c - 8) * 4096, base + ((size_t)(kb * 8 + c - 8) * rcap + row0 + 128) * 16, 4096, &full[s]);
+        }
+      } else if (MODE == 3) {
+        if (threadIdx.x == 0) expect(&full[s], stage_bytes);
+        __syncwarp();
+        const int r64 = row0 + (it % 4) * 64;
+        if (warp < 3) for (int c = warp + 3 * lane; c < 40; c += 96) {
+          if (c < 8) bulk(dst + c * 2048, base + ((size_t)(kb * 8 + c) * rcap + row0) * 16, 2048, &full[s]);
+          else bulk(dst + 16384 + (c - 8) * 1024, base + ((size_t)(c - 8) * rcap + r64) * 16, 1024, &full[s]);
+        }
+      } else if (MODE == 4) {
+        if (threadIdx.x == 0) {
+          const int r64 = row0 + (it % 4) * 64;
+          expect(&full[s], stage_bytes);
+          tma3(dst, tm, row0 * 2, kb * 8, 0, &full[s]);   // A: 128 rows x 8 chunks
+          tma3(dst + 16384, tm2, r64 * 2, 0, 0, &full[s]);  // B: 64 contraction rows x 32 feature chunks
         }
       } else {
         if (threadIdx.x == 0) {
@@ -80,13 +96,19 @@ int main() {
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   printf("encode: %d\n", (int)r);
   CUtensorMap* dm; cudaMalloc(&dm, sizeof(m)); cudaMemcpy(dm, &m, sizeof(m), cudaMemcpyHostToDevice);
+  CUtensorMap m2;
+  cuuint32_t box2[3] = {128, 32, 1};
+  r = ((PFN)fp)(&m2, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, buf, dims, strides, box2, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  printf("encode2: %d\n", (int)r);
+  CUtensorMap* dm2; cudaMalloc(&dm2, sizeof(m2)); cudaMemcpy(dm2, &m2, sizeof(m2), cudaMemcpyHostToDevice);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   const int iters = 2000;
   auto run = [&](const char* name, auto kern, int S, int grid) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    kern<<<grid, 128, S * 48 * 1024>>>(buf, dm, rcap, nchunks, 200, S);
+    kern<<<grid, 128, S * 48 * 1024>>>(buf, dm, dm2, rcap, nchunks, 200, S);
     cudaEventRecord(e0);
-    kern<<<grid, 128, S * 48 * 1024>>>(buf, dm, rcap, nchunks, iters, S);
+    kern<<<grid, 128, S * 48 * 1024>>>(buf, dm, dm2, rcap, nchunks, iters, S);
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     cudaError_t err = cudaGetLastError();
@@ -98,6 +120,8 @@ int main() {
     run("1-D bulk copies, one thread", k<0>, S, grid);
     run("1-D bulk copies, 3 warps", k<1>, S, grid);
     run("TMA tensor 3-D (2 KB inner box)", k<2>, S, grid);
+    run("dX pattern: 1-D bulk 8x2KB+32x1KB, 3 warps", k<3>, S, grid);
+    run("dX pattern: TMA tensor 2 instr", k<4>, S, grid);
   }
   return 0;
 }

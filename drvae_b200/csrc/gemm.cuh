@@ -318,7 +318,7 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& e, RowCtx& rc, int co
     o[e.out_c8_rcap] = pack_bf16x8(v + 8);
   } else if (EPI == EPI_GRAD || EPI == EPI_GRAD_ADAM) {
     const int k = rc.row;  // input feature (or ones / class column)
-    if (k >= e.g_kaug) return;
+    if (k >= e.g_kaug || col0 >= e.g_tab_n) return;  // (weight-gradient tiles need not divide the shadow rows)
     // flat parameter index of column i: weight W[n][k], bias b[n] or class column W[n][kin + j]
     // (tables are warp-uniform: broadcast loads)
     const int4* tw = reinterpret_cast<const int4*>(e.g_tab + (k == e.g_kin ? e.g_tab_n : 0) + col0);
@@ -636,8 +636,8 @@ constexpr int ADAM_PREFETCH_DIST = 4;  // half-chunks of optimizer state request
 template <int GROUPS>
 __device__ __forceinline__ void adam_epilogue_row(const GemmProblem& p, const EpiParams& e, const TileInfo& t, int cg, int k,
                                                   uint32_t taddr_row, bool have_acc, uint64_t* acc_bar, uint32_t acc_parity) {
-  const int nhc = p.BN >> 3;                        // half-chunks in the tile
-  const int nh = (nhc - cg + GROUPS - 1) / GROUPS;  // half-chunks of this column group
+  const int nhc = min(p.BN, e.g_tab_n - t.n0) >> 3;                // half-chunks of shadow rows that exist in the tile
+  const int nh = nhc > cg ? (nhc - cg + GROUPS - 1) / GROUPS : 0;  // half-chunks of this column group
   const int kofs = (k < e.g_kin) ? k : (k == e.g_kin ? 0 : k - 1);
   auto lcol = [&](int h) { return (cg + h * GROUPS) * 8; };  // tile-local column of this group's h-th half-chunk
   // L2 prefetch of half-chunk h for the whole warp: lane j < 24 requests the warp's 32-feature
@@ -856,8 +856,8 @@ __device__ __forceinline__ void adam_epilogue_vec(const GemmProblem& p, const Ep
                                                   uint32_t taddr_row, bool have_acc, uint64_t* acc_bar, uint32_t acc_parity) {
   const int lane = threadIdx.x & 31;
   const int ci = lane & 3, k4 = kbase + (lane >> 2) * 4;
-  const int nhc = p.BN >> 3;
-  const int nh = (nhc - cg + GROUPS - 1) / GROUPS;
+  const int nhc = min(p.BN, e.g_tab_n - t.n0) >> 3;  // half-chunks of shadow rows that exist (the last tile may be ragged)
+  const int nh = nhc > cg ? (nhc - cg + GROUPS - 1) / GROUPS : 0;
   auto lcol = [&](int h) { return (cg + h * GROUPS) * 8; };
   AdamVecBuf A;
   if (nh > 0) adam_vec_load<VEC>(e, t.model, k4, t.n0 + lcol(0), ci, A);

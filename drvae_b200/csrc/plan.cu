@@ -56,6 +56,7 @@ struct drvae_plan {
   Seg* d_segs = nullptr;
   std::vector<int> h_tabs;  // gradient-epilogue tables of every weight (see make_shadow)
   int* d_tabs = nullptr;
+  int sched = 1;              // measurement knob (DRVAE_B200_SCHED): bit 0 = noise generator, bit 1 = classifier backward on the side stream (measured: 1.037 / 1.027 / 1.048 / 1.048 ms for 0 / 1 / 2 / 3)
   int adam_vec_max = 4;       // debug knob (DRVAE_B200_ADAM_VEC): cap on the vector width of the fused Adam epilogue
   bool wn = false;            // layers.WeightNormLinear instead of nn.Linear
   std::vector<WnRow> wn_rows;
@@ -102,7 +103,8 @@ struct drvae_plan {
   long long graph_replays = 0;
   // side stream for the label-dependent branch (see run_step)
   cudaStream_t side = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_qy = nullptr, ev_side_fwd = nullptr, ev_side_bwd = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_qy = nullptr, ev_side_fwd = nullptr, ev_side_bwd = nullptr, ev_begin = nullptr, ev_eps = nullptr,
+              ev_clf = nullptr;
   bool overlap = true;
   // gradient buckets (data-parallel overlap): contiguous parameter ranges in backward completion order
   std::vector<std::pair<long long, long long>> buckets;  // (offset, count)
@@ -502,8 +504,9 @@ extern "C" int drvae_plan_create(const drvae_arch_t* a, int n_models, drvae_plan
   cudaMalloc(&pl->d_dyn, sizeof(StepDyn));
   cudaMemset(pl->d_dyn, 0, sizeof(StepDyn));
   if (const char* knob = getenv("DRVAE_B200_ADAM_VEC")) pl->adam_vec_max = atoi(knob);  // measurement knob
+  if (const char* knob = getenv("DRVAE_B200_SCHED")) pl->sched = atoi(knob);
   cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking);
-  for (cudaEvent_t* ev : {&pl->ev_fork, &pl->ev_qy, &pl->ev_side_fwd, &pl->ev_side_bwd})
+  for (cudaEvent_t* ev : {&pl->ev_fork, &pl->ev_qy, &pl->ev_side_fwd, &pl->ev_side_bwd, &pl->ev_begin, &pl->ev_eps, &pl->ev_clf})
     cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
   pl->bucket_ev.resize(pl->buckets.size());
   for (auto& ev : pl->bucket_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
@@ -618,7 +621,7 @@ extern "C" int drvae_plan_destroy(drvae_plan_t* pl) {
   if (pl->d_tabs) cudaFree(pl->d_tabs);
   if (pl->d_wn_rows) cudaFree(pl->d_wn_rows);
   for (auto& ev : pl->bucket_ev) cudaEventDestroy(ev);
-  for (cudaEvent_t ev : {pl->ev_fork, pl->ev_qy, pl->ev_side_fwd, pl->ev_side_bwd})
+  for (cudaEvent_t ev : {pl->ev_fork, pl->ev_qy, pl->ev_side_fwd, pl->ev_side_bwd, pl->ev_begin, pl->ev_eps, pl->ev_clf})
     if (ev) cudaEventDestroy(ev);
   if (pl->side) cudaStreamDestroy(pl->side);
   delete pl;
@@ -803,13 +806,22 @@ struct Exec {
     p.tiles_n = W.tiles_n;
     p.tiles_m = cdiv(W.kaug, GEMM_BM);
     p.ksplit = 1;
-    if (splitk && !fused) {
-      // large minibatch, few weight tiles: split the contraction (rows) so the persistent grid is filled;
-      // partial tiles accumulate with red.global.add into the gradient buffer zeroed at the start of the step
-      const int nkb = cdiv(row_bound, GEMM_BK);
-      const int tiles = p.tiles_m * p.tiles_n * pl->E;
-      int ks = std::min(cdiv(2 * gemm_num_sms(), tiles), nkb / 4);
-      p.ksplit = std::max(1, std::min(ks, 64));
+    if (fused) {
+      // Small layers: a 128 x 208 tile per model leaves most SMs idle and makes every epilogue warp walk its
+      // half-chunks one HBM round trip at a time.  Pick the tile width that minimises (waves of the persistent
+      // grid) x (time of one tile ~ fixed mainloop / latency part + epilogue part proportional to the width);
+      // constants from the measured 25 us of a full 128 x 256 tile.
+      const int nsm = gemm_num_sms();
+      int best_bn = p.BN;
+      float best = 1e30f;
+      for (int bn : {W.BN, 128, 64}) {
+        if (bn > W.BN) continue;
+        const int tiles = p.tiles_m * cdiv(W.rcap, bn) * pl->E;
+        const float cost = (float)cdiv(tiles, nsm) * (6.f + 20.f * (float)bn / 256.f);
+        if (cost < best * 0.97f) best = cost, best_bn = bn;
+      }
+      p.BN = best_bn;
+      p.tiles_n = cdiv(W.rcap, best_bn);
     }
     EpiParams e = epi_base();
     e.grad = v.grads.p;
@@ -1084,6 +1096,17 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
   const int Fb = std::max(1, L * pl->Y * N);
   auto rows_grid = [&](int rows) { return dim3(cdiv(rows, ROW_WARPS), E); };
 
+  // Two-stream schedule (captured as graph edges): everything that is not on the longest dependency chain runs on
+  // the plan's side stream — the latent-noise generator (next to rowmap / prep / the encoder), the label-dependent
+  // branch, the classifier backward and the loss reduction.
+  const bool overlap = pl->has_fprop && pl->overlap && !pl->prof_on;
+  cudaStream_t side = overlap ? pl->side : st;
+  auto on = [&](cudaStream_t s) { ex.st = s; };
+  auto after = [&](cudaStream_t waiter, cudaEvent_t ev, cudaStream_t producer) {
+    if (!overlap || waiter == producer) return;
+    cudaEventRecord(ev, producer);
+    cudaStreamWaitEvent(waiter, ev, 0);
+  };
   if (!(nz && nz->eps)) {
     const drvae_eps_layout_t& el = pl->epsl;
     EpsSegs sg{};
@@ -1102,9 +1125,14 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
     }
     if (most >= (1LL << 31)) return set_error("drvae: minibatch too large for the noise generator");
     dim3 g((unsigned)((most + 255) / 256), E, 6);
+    if (pl->sched & 1) {
+      after(side, pl->ev_begin, st);  // after this step's scalars (set_dyn) and everything before them
+      on(side);
+    }
     ex.pre("philox_normal");
-    philox_normal_kernel<<<g, 256, 0, st>>>(pl->eps_own, sg, N, pl->Ncap, pl->d_dyn);
+    philox_normal_kernel<<<g, 256, 0, ex.st>>>(pl->eps_own, sg, N, pl->Ncap, pl->d_dyn);
     ex.chk();
+    on(st);
   }
   ex.pre("rowmap");
   rowmap_kernel<<<E, ROWMAP_THREADS, 0, st>>>(v);
@@ -1118,20 +1146,13 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
   ex.block_hidden_fwd(pl->enc, v.Ain, 0, CNT_R0, R0b);
   ex.gemm_nt(pl->enc.H.back(), 0, pl->enc.head, EPI_STORE_F32, ex.epi_f32(v.Q.p, v.Q.ms, 2 * pl->Z, 2 * pl->Z, &pl->enc.head),
              CNT_R0, R0b);
+  if (!(nz && nz->eps) && (pl->sched & 1)) after(st, pl->ev_eps, side);  // latent noise of this step
   ex.pre("sample_q1");
   sample_q1_kernel<<<rows_grid(N + PAD_WARPS), ROW_THREADS, 0, st>>>(v);
   ex.chk();
   // The label-dependent branch (q(z_top|z1,y) -> p(z1|z_top,y), forward and backward: ~14 small
   // GEMMs + 4 row kernels that leave most SMs idle) is independent of the decoder branch, so it runs
   // on the plan's side stream between a fork here and a join before the encoder backward.
-  const bool overlap = pl->has_fprop && pl->overlap && !pl->prof_on;
-  cudaStream_t side = overlap ? pl->side : st;
-  auto on = [&](cudaStream_t s) { ex.st = s; };
-  auto after = [&](cudaStream_t waiter, cudaEvent_t ev, cudaStream_t producer) {
-    if (!overlap || waiter == producer) return;
-    cudaEventRecord(ev, producer);
-    cudaStreamWaitEvent(waiter, ev, 0);
-  };
   after(side, pl->ev_fork, st);
 
   auto fprop_fwd_gemms = [&]() {
@@ -1147,6 +1168,18 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
     ex.block_hidden_fwd(pl->dz1b, v.Z3b, 0, CNT_F, Fb);
     ex.gemm_nt(pl->dz1b.H.back(), 0, pl->dz1b.head, EPI_STORE_F32,
                ex.epi_f32(v.PZ1.p, v.PZ1.ms, 2 * pl->Z, 2 * pl->Z, &pl->dz1b.head), CNT_F, Fb);
+  };
+  auto clf_bwd = [&]() {
+    ex.phase = "clf.bwd";
+    ex.pre("clf_back");
+    clf_back_kernel<<<rows_grid(LNb), ROW_THREADS, 0, ex.st>>>(v);
+    ex.chk();
+    ex.pre("clf_grad_partial");
+    clf_grad_partial_kernel<<<dim3(v.clf_splits, E), 256, 0, ex.st>>>(v);
+    ex.chk();
+    ex.pre("clf_grad_reduce");
+    clf_grad_reduce_kernel<<<dim3(cdiv(pl->Y * (pl->clf_in + 1), 8), E), 256, 0, ex.st>>>(v);
+    ex.chk();
   };
   if (pl->has_fprop) {
     on(side);
@@ -1170,6 +1203,13 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
     pz1_post_kernel<<<rows_grid(round_up(Fb, 128)), ROW_THREADS, 0, ex.st>>>(v);
     ex.chk();
     if (backward) {
+      if (pl->has_clf && (pl->sched & 2)) {
+        // classifier backward: needs only q(y|.) (T_post / sample_q1) and the per-class terms pz1_post has just
+        // written, so it leaves the main stream's chain; T_back / q_back wait for ev_clf
+        clf_bwd();
+        cudaEventRecord(pl->bucket_ev[3], ex.st);  // buckets: dz1, z3 (this stream), dec, clf, ...
+        if (overlap) cudaEventRecord(pl->ev_clf, ex.st);
+      }
       ex.phase = "dz1.bwd";
       ex.block_bwd(pl->dz1b, v.dY9, v.Z3b, 0, pl->Z3, v.dZ3.p, v.dZ3.ms, CNT_F, Fb);
       cudaEventRecord(pl->bucket_ev[0], ex.st);
@@ -1235,17 +1275,13 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
     ex.block_bwd(pl->dec, pl->dY5, v.Zdec, 0, pl->Z, v.dZdec.p, v.dZdec.ms, CNT_RD, Rdb);
     bucket_done();
     if (pl->has_clf) {
-      ex.phase = "clf.bwd";
-      ex.pre("clf_back");
-      clf_back_kernel<<<rows_grid(LNb), ROW_THREADS, 0, ex.st>>>(v);
-      ex.chk();
-      ex.pre("clf_grad_partial");
-      clf_grad_partial_kernel<<<dim3(v.clf_splits, E), 256, 0, ex.st>>>(v);
-      ex.chk();
-      ex.pre("clf_grad_reduce");
-      clf_grad_reduce_kernel<<<dim3(cdiv(pl->Y * (pl->clf_in + 1), 8), E), 256, 0, ex.st>>>(v);
-      ex.chk();
-      bucket_done();
+      if (pl->has_fprop && (pl->sched & 2)) {
+        ++bk;  // ran on the side stream right after pz1_post (bucket event recorded there)
+        if (overlap) cudaStreamWaitEvent(st, pl->ev_clf, 0);
+      } else {
+        clf_bwd();
+        bucket_done();
+      }
     }
     if (pl->has_T) {
       ex.phase = "T.bwd";

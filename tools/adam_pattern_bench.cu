@@ -460,6 +460,128 @@ __global__ void __launch_bounds__(EW * 32 + 128, 1) k_tile_v4(float* P, float* M
   }
 }
 
+
+// P6: as P5 (16-byte accesses, persistent geometry, 16 epilogue warps) but with the tile's k-span KS as a parameter:
+// KS = 128 reads 512-byte pieces of each weight row (the GEMM epilogue's pattern), 256 / 512 read 1 / 2 KB pieces
+// (tile = KS x 32768/KS).  Tests whether DRAM page locality limits the tile pattern.
+template <int KS>
+__global__ void __launch_bounds__(16 * 32 + 128, 1) k_tile_ks(float* P, float* M, float* V, __nv_bfloat16* S, int rows, int ld, long long ms, H h,
+                                                             int n_models) {
+  extern __shared__ float sm[];
+  if (sm[0] == 123.f) return;
+  const int warp = (threadIdx.x >> 5) - 4, lane = threadIdx.x & 31;
+  if (warp < 0) return;
+  constexpr int NS = 32768 / KS, KSLOTS = KS / 32, GROUPS = 16 / KSLOTS, NHC = NS / 8;
+  const int ks = warp % KSLOTS, cg = warp / KSLOTS;
+  const int ci = lane & 3, kg = lane >> 2;
+  const int tiles_m = (ld + KS - 1) / KS, tiles_n = (rows + NS - 1) / NS;
+  const int total_tiles = tiles_m * tiles_n * n_models;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int per = tiles_m * tiles_n;
+    const int model = tile / per, mn = tile % per;
+    const int tile_m = mn % tiles_m, tile_n = mn / tiles_m;
+    const int k4 = tile_m * KS + ks * 32 + kg * 4;
+    const bool kok = k4 + 3 < ld;
+    float* p = P + model * ms + k4; float* m = M + model * ms + k4; float* v = V + model * ms + k4;
+    for (int hc = cg; hc < NHC; hc += GROUPS) {
+      float4 bp[2], bm[2], bv[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int n = tile_n * NS + hc * 8 + j * 4 + ci;
+        bp[j] = bm[j] = bv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n < rows && kok) {
+          const long long idx = (long long)n * ld;
+          bp[j] = *reinterpret_cast<const float4*>(p + idx); bm[j] = *reinterpret_cast<const float4*>(m + idx); bv[j] = *reinterpret_cast<const float4*>(v + idx);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        upd(1e-3f, bp[j].x, bm[j].x, bv[j].x, h); upd(1e-3f, bp[j].y, bm[j].y, bv[j].y, h);
+        upd(1e-3f, bp[j].z, bm[j].z, bv[j].z, h); upd(1e-3f, bp[j].w, bm[j].w, bv[j].w, h);
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int n = tile_n * NS + hc * 8 + j * 4 + ci;
+        if (n < rows && kok) {
+          const long long idx = (long long)n * ld;
+          *reinterpret_cast<float4*>(p + idx) = bp[j]; *reinterpret_cast<float4*>(m + idx) = bm[j]; *reinterpret_cast<float4*>(v + idx) = bv[j];
+          __nv_bfloat162 lo = __floats2bfloat162_rn(bp[j].x, bp[j].y), hi = __floats2bfloat162_rn(bp[j].z, bp[j].w);
+          uint2 pk = make_uint2(*reinterpret_cast<unsigned*>(&lo), *reinterpret_cast<unsigned*>(&hi));
+          *reinterpret_cast<uint2*>(S + model * ms + ((long long)(k4 >> 3) * 2048 + n) * 8 + (k4 & 7)) = pk;
+        }
+      }
+    }
+  }
+}
+
+
+// P7: as P5 (vec4, persistent geometry) but the optimizer state is fetched with per-thread 16-byte cp.async.cg
+// (LDGSTS.128, L1 bypass) into a private shared-memory ring of D half-chunks per warp: data in flight is bounded by
+// shared memory, not by registers.  The thread that issued a copy is the one that reads it back (no cross-thread sync).
+template <int EW, int D>
+__global__ void __launch_bounds__(EW * 32 + 128, 1) k_tile_cpa16(float* P, float* M, float* V, __nv_bfloat16* S, int rows, int ld, int BN, int tiles_m,
+                                                                 int tiles_n, long long ms, H h, int total_tiles, int reserve) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  const int warp = (threadIdx.x >> 5) - 4, lane = threadIdx.x & 31;
+  if (warp < 0) return;
+  float4* ring = reinterpret_cast<float4*>(smraw + reserve) + (size_t)warp * D * 6 * 32;  // [D][6][32 lanes] float4
+  const int cg = warp >> 2, ngroups = EW / 4, q = warp & 3;
+  const int ci = lane & 3, kg = lane >> 2;
+  const int nhc = BN >> 3;
+  const int nh = (nhc - cg + ngroups - 1) / ngroups;           // half-chunks of this warp per tile
+  const int my_tiles = (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int total = my_tiles * nh;                              // work items of this warp
+  auto item = [&](int w, int& model, int& k4, int& n0, bool& kok) {
+    const int tile = blockIdx.x + (w / nh) * gridDim.x, hc = cg + (w % nh) * ngroups;
+    const int per = tiles_m * tiles_n;
+    model = tile / per;
+    const int mn = tile % per, tile_m = mn % tiles_m, tile_n = mn / tiles_m;
+    k4 = tile_m * 128 + q * 32 + kg * 4;
+    kok = k4 + 3 < ld;
+    n0 = tile_n * BN + hc * 8;
+  };
+  auto issue = [&](int w) {
+    if (w < total) {
+      int model, k4, n0; bool kok;
+      item(w, model, k4, n0, kok);
+      float4* dst = ring + (size_t)(w % D) * 6 * 32 + lane;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int n = n0 + j * 4 + ci;
+        if (n < rows && kok) {
+          const long long idx = model * ms + (long long)n * ld + k4;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst + (3 * j + 0) * 32)), "l"(P + idx) : "memory");
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst + (3 * j + 1) * 32)), "l"(M + idx) : "memory");
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst + (3 * j + 2) * 32)), "l"(V + idx) : "memory");
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  for (int w = 0; w < D - 1; ++w) issue(w);
+  for (int w = 0; w < total; ++w) {
+    issue(w + D - 1);
+    asm volatile("cp.async.wait_group %0;" ::"n"(D - 1) : "memory");
+    int model, k4, n0; bool kok;
+    item(w, model, k4, n0, kok);
+    const float4* src = ring + (size_t)(w % D) * 6 * 32 + lane;
+    const int rcap = tiles_n * BN;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int n = n0 + j * 4 + ci;
+      if (n < rows && kok) {
+        float4 bp = src[(3 * j + 0) * 32], bm = src[(3 * j + 1) * 32], bv = src[(3 * j + 2) * 32];
+        upd(1e-3f, bp.x, bm.x, bv.x, h); upd(1e-3f, bp.y, bm.y, bv.y, h); upd(1e-3f, bp.z, bm.z, bv.z, h); upd(1e-3f, bp.w, bm.w, bv.w, h);
+        const long long idx = model * ms + (long long)n * ld + k4;
+        *reinterpret_cast<float4*>(P + idx) = bp; *reinterpret_cast<float4*>(M + idx) = bm; *reinterpret_cast<float4*>(V + idx) = bv;
+        __nv_bfloat162 lo = __floats2bfloat162_rn(bp.x, bp.y), hi = __floats2bfloat162_rn(bp.z, bp.w);
+        uint2 pk = make_uint2(*reinterpret_cast<unsigned*>(&lo), *reinterpret_cast<unsigned*>(&hi));
+        *reinterpret_cast<uint2*>(S + model * ms + ((long long)(k4 >> 3) * rcap + n) * 8 + (k4 & 7)) = pk;
+      }
+    }
+  }
+}
+
 // P2: row-linear: CTA handles RN consecutive rows n, all k; thread t handles k = t, t+256, ... for each row; NB rows batched.
 template <int NB>
 __global__ void k_rows(float* P, float* M, float* V, __nv_bfloat16* S, int rows, int ld, int RN, long long ms, H h) {
@@ -568,6 +690,27 @@ int main(int argc, char** argv) {
       snprintf(nm, sizeof(nm), "bulk-alt vec%d: persistent, %d epi warps, db=%d, %d KB smem", VEC, EW, DB, SM);           \
       timeit(nm, [&] { k_tile_v4<EW, VEC, DB><<<148, EW * 32 + 128, SM * 1024>>>(P, M, V, S, rows, ld, BN, tiles_m, tiles_n, ms, h, total_tiles); }); \
     }
+
+#define KS_(KS)                                                                                                           \
+    {                                                                                                                    \
+      cudaFuncSetAttribute(k_tile_ks<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);                       \
+      char nm[128];                                                                                                      \
+      snprintf(nm, sizeof(nm), "bulk-alt k-span %d: persistent vec4, 16 epi warps, 100 KB smem", KS);                     \
+      timeit(nm, [&] { k_tile_ks<KS><<<148, 16 * 32 + 128, 100 * 1024>>>(P, M, V, S, rows, ld, ms, h, E); });             \
+    }
+    KS_(128)
+    V4_(24, 4, 0, 1) V4_(24, 4, 0, 32) V4_(24, 4, 0, 64) V4_(24, 4, 0, 100) V4_(24, 4, 0, 132) V4_(24, 4, 0, 164) V4_(16, 4, 1, 1) V4_(16, 4, 1, 32) V4_(16, 4, 1, 64) V4_(28, 4, 0, 32)
+
+#define CPA_(EW, D, RES)                                                                                                  \
+    {                                                                                                                    \
+      const int smem = RES * 1024 + EW * D * 6 * 32 * 16;                                                                 \
+      cudaFuncSetAttribute(k_tile_cpa16<EW, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);                       \
+      char nm[128];                                                                                                      \
+      snprintf(nm, sizeof(nm), "bulk-alt cp.async.cg 16B: %d epi warps, depth %d, +%d KB (%d KB smem)", EW, D, RES, smem / 1024); \
+      timeit(nm, [&] { k_tile_cpa16<EW, D><<<148, EW * 32 + 128, smem>>>(P, M, V, S, rows, ld, BN, tiles_m, tiles_n, ms, h, total_tiles, RES * 1024); }); \
+    }
+    CPA_(16, 2, 0) CPA_(8, 2, 0) CPA_(16, 4, 0)
+
     V4_(16, 4, 0, 100) V4_(16, 4, 1, 100) V4_(24, 4, 0, 100) V4_(24, 4, 1, 100) V4_(16, 4, 1, 200) V4_(16, 2, 1, 100) V4_(24, 2, 0, 100) V4_(24, 2, 1, 100) V4_(12, 4, 1, 100) V4_(8, 4, 1, 100)
     PW(16, 8, 100) PW(24, 8, 100)
     BK_(16, 4, 3, 0, 96) BK_(16, 8, 3, 0, 96) BK_(16, 8, 1, 0, 96) BK_(16, 8, 3, 0, 0) BK_(16, 12, 3, 0, 0) BK_(16, 8, 3, 1, 96)

@@ -908,6 +908,7 @@ __global__ void __launch_bounds__((GEMM_PROD_WARPS + 1 + EW) * 32, 1) gemm_tc_ke
   __shared__ __align__(8) uint64_t acc_empty[GEMM_ACC_STAGES];
   __shared__ uint32_t tmem_base_s;
 
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int BN = p.BN;
@@ -936,6 +937,7 @@ __global__ void __launch_bounds__((GEMM_PROD_WARPS + 1 + EW) * 32, 1) gemm_tc_ke
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  pdl_wait();  // everything above (barriers, TMEM) overlapped the previous kernel's tail; global memory from here on
 #ifdef GEMM_PROFILE_WAITS
   const long long ws_cta_t0 = clock64();
 #endif
@@ -1305,8 +1307,7 @@ inline cudaError_t gemm_launch_t(GemmProblem p, const EpiParams& e, int n_models
   }
   if (err != cudaSuccess) return err;
   const int grid = total < gemm_num_sms() ? total : gemm_num_sms();  // persistent: one CTA per SM
-  gemm_tc_kernel<EPI, EW, VEC><<<grid, (GEMM_PROD_WARPS + 1 + EW) * 32, smem, st>>>(p, e, tmA, tmB, tmB2);
-  return cudaGetLastError();
+  return launch_k(gemm_tc_kernel<EPI, EW, VEC>, dim3(grid), dim3((GEMM_PROD_WARPS + 1 + EW) * 32), smem, st, 1, p, e, tmA, tmB, tmB2);
 }
 
 inline cudaError_t gemm_launch(int epi, const GemmProblem& p, const EpiParams& e, int n_models, int impl,

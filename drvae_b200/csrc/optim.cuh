@@ -140,7 +140,11 @@ __global__ void __launch_bounds__(256) wn_grad_kernel(WnArgs a) {
 }
 
 // writes the per-step scalars; the only kernel whose arguments differ between two steps of the same shape
-__global__ void set_dyn_kernel(StepDyn value, StepDyn* dst) { *dst = value; }
+__global__ void set_dyn_kernel(StepDyn value, StepDyn* dst) {
+  pdl_launch_dependents();
+  pdl_wait();
+  *dst = value;
+}
 
 // ε block generator.  Every normal is keyed by (seed, step, model, segment, MC sample, GLOBAL row,
 // position in the row) and never by its address, so a minibatch sharded over ranks
@@ -153,6 +157,8 @@ struct EpsSegs {
 };
 
 __global__ void __launch_bounds__(256) philox_normal_kernel(MBuf<float> out, EpsSegs sg, int N, int Ncap, const StepDyn* dyn) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long row_offset = dyn->row_offset;
   const unsigned long long seed = dyn->noise_seed;
   const unsigned int step = dyn->noise_step;

@@ -505,6 +505,7 @@ extern "C" int drvae_plan_create(const drvae_arch_t* a, int n_models, drvae_plan
   cudaMemset(pl->d_dyn, 0, sizeof(StepDyn));
   if (const char* knob = getenv("DRVAE_B200_ADAM_VEC")) pl->adam_vec_max = atoi(knob);  // measurement knob
   if (const char* knob = getenv("DRVAE_B200_SCHED")) pl->sched = atoi(knob);
+  if (const char* knob = getenv("DRVAE_B200_PDL")) pdl_mask() = atoi(knob);  // measurement knob: programmatic dependent launch
   cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking);
   for (cudaEvent_t* ev : {&pl->ev_fork, &pl->ev_qy, &pl->ev_side_fwd, &pl->ev_side_bwd, &pl->ev_begin, &pl->ev_eps, &pl->ev_clf})
     cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
@@ -1007,7 +1008,7 @@ StepDyn make_dyn(const drvae_noise_t* nz, const drvae_hparams_t* hp, bool fused_
 
 int push_dyn(drvae_plan* pl, const StepDyn& d, cudaStream_t st) {
   prof_pre(pl, st, ":set_dyn");
-  set_dyn_kernel<<<1, 1, 0, st>>>(d, pl->d_dyn);
+  launch_k(set_dyn_kernel, dim3(1), dim3(1), 0, st, 2, d, pl->d_dyn);
   prof_post(pl, st);
   pl->launches++;
   cudaError_t err = cudaGetLastError();
@@ -1130,15 +1131,15 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
       on(side);
     }
     ex.pre("philox_normal");
-    philox_normal_kernel<<<g, 256, 0, ex.st>>>(pl->eps_own, sg, N, pl->Ncap, pl->d_dyn);
+    launch_k(philox_normal_kernel, g, dim3(256), 0, ex.st, 2, pl->eps_own, sg, N, pl->Ncap, pl->d_dyn);
     ex.chk();
     on(st);
   }
   ex.pre("rowmap");
-  rowmap_kernel<<<E, ROWMAP_THREADS, 0, st>>>(v);
+  launch_k(rowmap_kernel, dim3(E), dim3(ROWMAP_THREADS), 0, st, 2, v);
   ex.chk();
   ex.pre("prep");
-  prep_kernel<<<dim3(round_up(R0b, 128) / PREP_ROWS, cdiv(pl->view.Xc, PREP_SLAB), E), PREP_THREADS, 0, st>>>(v);
+  launch_k(prep_kernel, dim3(round_up(R0b, 128) / PREP_ROWS, cdiv(pl->view.Xc, PREP_SLAB), E), dim3(PREP_THREADS), 0, st, 2, v);
   ex.chk();
 
   // ---- encoder q(z1|x1), shared with q(z2|x2) (DrVAE.py:408,418) ----
@@ -1148,7 +1149,7 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
              CNT_R0, R0b);
   if (!(nz && nz->eps) && (pl->sched & 1)) after(st, pl->ev_eps, side);  // latent noise of this step
   ex.pre("sample_q1");
-  sample_q1_kernel<<<rows_grid(N + PAD_WARPS), ROW_THREADS, 0, st>>>(v);
+  launch_k(sample_q1_kernel, rows_grid(N + PAD_WARPS), dim3(ROW_THREADS), 0, st, 2, v);
   ex.chk();
   // The label-dependent branch (q(z_top|z1,y) -> p(z1|z_top,y), forward and backward: ~14 small
   // GEMMs + 4 row kernels that leave most SMs idle) is independent of the decoder branch, so it runs
@@ -1162,7 +1163,7 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
     ex.gemm_nt(pl->z3b.H.back(), 0, pl->z3b.head, EPI_STORE_F32,
                ex.epi_f32(v.Q3.p, v.Q3.ms, 2 * pl->Z3, 2 * pl->Z3, &pl->z3b.head), CNT_F, Fb);
     ex.pre("z3_post");
-    z3_post_kernel<<<rows_grid(round_up(Fb, 128)), ROW_THREADS, 0, ex.st>>>(v);
+    launch_k(z3_post_kernel, rows_grid(round_up(Fb, 128)), dim3(ROW_THREADS), 0, ex.st, 2, v);
     ex.chk();
     ex.phase = "dz1.fwd";
     ex.block_hidden_fwd(pl->dz1b, v.Z3b, 0, CNT_F, Fb);
@@ -1172,13 +1173,13 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
   auto clf_bwd = [&]() {
     ex.phase = "clf.bwd";
     ex.pre("clf_back");
-    clf_back_kernel<<<rows_grid(LNb), ROW_THREADS, 0, ex.st>>>(v);
+    launch_k(clf_back_kernel, rows_grid(LNb), dim3(ROW_THREADS), 0, ex.st, 2, v);
     ex.chk();
     ex.pre("clf_grad_partial");
-    clf_grad_partial_kernel<<<dim3(v.clf_splits, E), 256, 0, ex.st>>>(v);
+    launch_k(clf_grad_partial_kernel, dim3(v.clf_splits, E), dim3(256), 0, ex.st, 2, v);
     ex.chk();
     ex.pre("clf_grad_reduce");
-    clf_grad_reduce_kernel<<<dim3(cdiv(pl->Y * (pl->clf_in + 1), 8), E), 256, 0, ex.st>>>(v);
+    launch_k(clf_grad_reduce_kernel, dim3(cdiv(pl->Y * (pl->clf_in + 1), 8), E), dim3(256), 0, ex.st, 2, v);
     ex.chk();
   };
   if (pl->has_fprop) {
@@ -1191,7 +1192,7 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
   if (pl->has_T) {
     ex.gemm_nt(v.Zdec, 0, pl->Tsh, EPI_STORE_F32, ex.epi_f32(v.PT.p, v.PT.ms, 2 * pl->Z, 2 * pl->Z, &pl->Tsh), CNT_LN, LNb);
     ex.pre("T_post");
-    T_post_kernel<<<rows_grid(N + PAD_WARPS), ROW_THREADS, 0, ex.st>>>(v);
+    launch_k(T_post_kernel, rows_grid(N + PAD_WARPS), dim3(ROW_THREADS), 0, ex.st, 2, v);
     ex.chk();
   }
   if (pl->has_fprop) {
@@ -1200,7 +1201,7 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
     after(side, pl->ev_qy, st);
     on(side);
     ex.pre("pz1_post");
-    pz1_post_kernel<<<rows_grid(round_up(Fb, 128)), ROW_THREADS, 0, ex.st>>>(v);
+    launch_k(pz1_post_kernel, rows_grid(round_up(Fb, 128)), dim3(ROW_THREADS), 0, ex.st, 2, v);
     ex.chk();
     if (backward) {
       if (pl->has_clf && (pl->sched & 2)) {
@@ -1214,7 +1215,7 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
       ex.block_bwd(pl->dz1b, v.dY9, v.Z3b, 0, pl->Z3, v.dZ3.p, v.dZ3.ms, CNT_F, Fb);
       cudaEventRecord(pl->bucket_ev[0], ex.st);
       ex.pre("z3_back");
-      z3_back_kernel<<<rows_grid(round_up(Fb, 128)), ROW_THREADS, 0, ex.st>>>(v);
+      launch_k(z3_back_kernel, rows_grid(round_up(Fb, 128)), dim3(ROW_THREADS), 0, ex.st, 2, v);
       ex.chk();
       ex.phase = "z3.bwd";
       ex.block_bwd(pl->z3b, v.dY7, v.Z1e, 0, pl->Z, v.dZ1e.p, v.dZ1e.ms, CNT_F, Fb);
@@ -1254,10 +1255,10 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
   on(side);
   ex.phase = "";
   ex.pre("loss");
-  loss_partial_kernel<<<dim3(v.loss_slices, E), 256, 0, ex.st>>>(v);
+  launch_k(loss_partial_kernel, dim3(v.loss_slices, E), dim3(256), 0, ex.st, 2, v);
   ex.chk();
   ex.pre("loss_final");
-  loss_final_kernel<<<E, 32, 0, ex.st>>>(v);
+  launch_k(loss_final_kernel, dim3(E), dim3(32), 0, ex.st, 2, v);
   ex.chk();
   if (losses_out && ex.ok()) {
     // losses buffer per model is padded to 256 B in the arena; the caller's is dense [E][8]
@@ -1286,7 +1287,7 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
     if (pl->has_T) {
       ex.phase = "T.bwd";
       ex.pre("T_back");
-      T_back_kernel<<<rows_grid(N + PAD_WARPS), ROW_THREADS, 0, ex.st>>>(v);
+      launch_k(T_back_kernel, rows_grid(N + PAD_WARPS), dim3(ROW_THREADS), 0, ex.st, 2, v);
       ex.chk();
       ex.gemm_dx(v.dYT, pl->Tsh, EPI_STORE_F32, ex.epi_f32(v.dZ1T.p, v.dZ1T.ms, pl->Z, pl->Z, nullptr), CNT_LN, LNb);
       ex.gemm_dw(v.dYT, v.Zdec, 0, pl->Tsh, CNT_LN, LNb);
@@ -1295,7 +1296,7 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
     if (overlap) cudaStreamWaitEvent(st, pl->ev_side_bwd, 0);  // join: q_back sums the side branch's gradients into q(z1|x1)
     ex.phase = "enc.bwd";
     ex.pre("q_back");
-    q_back_kernel<<<rows_grid(N + PAD_WARPS), ROW_THREADS, 0, ex.st>>>(v);
+    launch_k(q_back_kernel, rows_grid(N + PAD_WARPS), dim3(ROW_THREADS), 0, ex.st, 2, v);
     ex.chk();
     ex.block_bwd(pl->enc, v.dY2, v.Ain, 0, pl->X, nullptr, 0, CNT_R0, R0b);
     bucket_done();
@@ -1325,7 +1326,7 @@ int enqueue_sequence(drvae_plan* pl, int seq, const drvae_batch_t* b, const drva
                      float* losses_out, cudaStream_t st, bool fused) {
   if (seq == SEQ_LOSS) return run_step(pl, b, nz, hp, losses_out, st, false, false);
   if (seq == SEQ_GRAD) {
-    int rc = run_step(pl, b, nz, hp, losses_out, st, true, false);
+    int rc = run_step(pl, b, nz, hp, losses_out, st, 2, false);
     if (rc || !pl->wn) return rc;
     rc = run_wn_grad(pl, st);
     // the conversion rewrites every bucket: bucket events must not fire before it
@@ -1335,9 +1336,9 @@ int enqueue_sequence(drvae_plan* pl, int seq, const drvae_batch_t* b, const drva
   if (fused) {
     // forward + ELBO + backward with Adam fused into the gradient epilogues: no gradient buffer traffic and
     // no separate optimizer pass (the bound gradient buffer is left untouched)
-    return run_step(pl, b, nz, hp, losses_out, st, true, true);
+    return run_step(pl, b, nz, hp, losses_out, st, 2, true);
   }
-  int rc = run_step(pl, b, nz, hp, losses_out, st, true, false);
+  int rc = run_step(pl, b, nz, hp, losses_out, st, 2, false);
   if (rc) return rc;
   rc = run_wn_grad(pl, st);
   if (rc) return rc;

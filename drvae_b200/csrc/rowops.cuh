@@ -69,6 +69,8 @@ __device__ __forceinline__ int block_exclusive_scan(int x, int* warp_tot, int& t
 }
 
 __global__ void __launch_bounds__(ROWMAP_THREADS) rowmap_kernel(DevView v) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int m = blockIdx.x, t = threadIdx.x, N = v.N;
   __shared__ int s_tot[33];
   const int* hx = v.has_pair ? v.has_x2.at(m) : nullptr;
@@ -164,6 +166,8 @@ constexpr int PREP_THREADS = 256;
 constexpr int PREP_SLAB = 256;
 
 __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(DevView v) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float tile[PREP_ROWS][PREP_SLAB + 1];
   const int m = blockIdx.z, r0 = blockIdx.x * PREP_ROWS;
   const int* cnt = v.counts.at(m);
@@ -301,6 +305,8 @@ __device__ __forceinline__ float kl_term(float muq, float lvq, float mup, float 
 // grid (ceil((N + PAD_WARPS) / ROW_WARPS), n_models)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(ROW_THREADS, 5) sample_q1_kernel(DevView v) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int m = blockIdx.y, lane = threadIdx.x & 31;
   const int i = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int* cnt = v.counts.at(m);
@@ -369,6 +375,8 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) sample_q1_kernel(DevView v) {
 // bits for pair rows, and the classifier.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(ROW_THREADS, 5) T_post_kernel(DevView v) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int m = blockIdx.y, lane = threadIdx.x & 31;
   const int i = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int* cnt = v.counts.at(m);
@@ -422,6 +430,8 @@ __device__ __forceinline__ void eval_decode(const DevView& v, int m, int e, int 
 }
 
 __global__ void __launch_bounds__(ROW_THREADS) z3_post_kernel(DevView v) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int m = blockIdx.y, lane = threadIdx.x & 31;
   const int e = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int* cnt = v.counts.at(m);
@@ -462,6 +472,8 @@ __device__ __forceinline__ float eval_weight(const DevView& v, int m, int l, int
 // decoder_z1 heads (dY9) and towards q1 (dQ1e).  DrVAE.py:352-355, VFAE.py:253-256.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(ROW_THREADS) pz1_post_kernel(DevView v) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int m = blockIdx.y, lane = threadIdx.x & 31;
   const int e = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int* cnt = v.counts.at(m);
@@ -506,6 +518,8 @@ __global__ void __launch_bounds__(ROW_THREADS) pz1_post_kernel(DevView v) {
 // decoder_z1 input gradient) + the direct prior-KL gradient.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(ROW_THREADS) z3_back_kernel(DevView v) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int m = blockIdx.y, lane = threadIdx.x & 31;
   const int e = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int* cnt = v.counts.at(m);
@@ -542,6 +556,8 @@ __global__ void __launch_bounds__(ROW_THREADS) z3_back_kernel(DevView v) {
 // grid (ceil(LNcap / ROW_WARPS), n_models), one warp per stacked row r = l*N + i
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(ROW_THREADS) clf_back_kernel(DevView v) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int m = blockIdx.y, lane = threadIdx.x & 31;
   const int r = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int* cnt = v.counts.at(m);
@@ -598,6 +614,8 @@ __global__ void __launch_bounds__(ROW_THREADS) clf_back_kernel(DevView v) {
 // towards q2 (dQ2) and the residual / classifier contributions to d z1 (DZ1).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(ROW_THREADS, 5) T_back_kernel(DevView v) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int m = blockIdx.y, lane = threadIdx.x & 31;
   const int i = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int* cnt = v.counts.at(m);
@@ -665,6 +683,8 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) T_back_kernel(DevView v) {
 // q(z2|x2) rows.  Collects every path into z1 / z2 samples and the direct KL gradients.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(ROW_THREADS, 5) q_back_kernel(DevView v) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int m = blockIdx.y, lane = threadIdx.x & 31;
   const int i = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int* cnt = v.counts.at(m);
@@ -735,6 +755,8 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) q_back_kernel(DevView v) {
 // two stages (row-split partials, then a fixed-order reduction) -> deterministic
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) clf_grad_partial_kernel(DevView v) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int m = blockIdx.y, split = blockIdx.x;
   const int LN = v.counts.at(m)[CNT_LN];
   const int width = v.clf_in + 1;
@@ -764,6 +786,8 @@ __global__ void __launch_bounds__(256) clf_grad_partial_kernel(DevView v) {
 // grid (ceil(Y * (clf_in + 1) / 8), n_models), block 256: one warp per gradient element, lanes over the row splits
 // (lane l sums splits l, l + 32, ... in order, then a fixed shuffle tree -> deterministic)
 __global__ void __launch_bounds__(256) clf_grad_reduce_kernel(DevView v) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int m = blockIdx.y, lane = threadIdx.x & 31;
   const int width = v.clf_in + 1;
   const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -909,6 +933,8 @@ __device__ __forceinline__ float block_sum_256(float x, float* sm) {
 
 // grid (loss_slices, n_models): slice s reduces rows s, s + slices, ... of every per-row term in a fixed order
 __global__ void __launch_bounds__(256) loss_partial_kernel(DevView v) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float sm[256];
   const int m = blockIdx.y, t = threadIdx.x;
   const int stride = 256 * gridDim.x, first = blockIdx.x * 256 + t;
@@ -950,6 +976,8 @@ __global__ void __launch_bounds__(256) loss_partial_kernel(DevView v) {
 
 // grid n_models, one warp: fixed-order sum of the slices, then the reference's normalisation
 __global__ void __launch_bounds__(32) loss_final_kernel(DevView v) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int m = blockIdx.x;
   if (threadIdx.x != 0) return;
   float a[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};

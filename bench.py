@@ -312,6 +312,8 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    # stdout carries exactly one JSON line: NCCL's debug output (the version banner at NCCL_DEBUG >= VERSION) goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if args.impl == "reference":
         return run_reference(args)
     if args.workload == "dp8192":

@@ -824,6 +824,14 @@ struct Exec {
       p.BN = best_bn;
       p.tiles_n = cdiv(W.rcap, best_bn);
     }
+    if (splitk && !fused) {
+      // large minibatch, few weight tiles: split the contraction (rows) so the persistent grid is filled;
+      // partial tiles accumulate with red.global.add into the gradient buffer zeroed at the start of the step
+      const int nkb = cdiv(row_bound, GEMM_BK);
+      const int tiles = p.tiles_m * p.tiles_n * pl->E;
+      int ks = std::min(cdiv(2 * gemm_num_sms(), tiles), nkb / 4);
+      p.ksplit = std::max(1, std::min(ks, 64));
+    }
     EpiParams e = epi_base();
     e.grad = v.grads.p;
     e.grad_ms = v.grads.ms;

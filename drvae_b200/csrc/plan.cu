@@ -1157,7 +1157,7 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
              CNT_R0, R0b);
   if (!(nz && nz->eps) && (pl->sched & 1)) after(st, pl->ev_eps, side);  // latent noise of this step
   ex.pre("sample_q1");
-  launch_k(sample_q1_kernel, rows_grid(N + PAD_WARPS), dim3(ROW_THREADS), 0, st, 2, v);
+  launch_k(pl->view.Zc <= 128 ? sample_q1_kernel<4> : sample_q1_kernel<MAXJ>, rows_grid(N + PAD_WARPS), dim3(ROW_THREADS), 0, st, 2, v);
   ex.chk();
   // The label-dependent branch (q(z_top|z1,y) -> p(z1|z_top,y), forward and backward: ~14 small
   // GEMMs + 4 row kernels that leave most SMs idle) is independent of the decoder branch, so it runs
@@ -1200,7 +1200,7 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
   if (pl->has_T) {
     ex.gemm_nt(v.Zdec, 0, pl->Tsh, EPI_STORE_F32, ex.epi_f32(v.PT.p, v.PT.ms, 2 * pl->Z, 2 * pl->Z, &pl->Tsh), CNT_LN, LNb);
     ex.pre("T_post");
-    launch_k(T_post_kernel, rows_grid(N + PAD_WARPS), dim3(ROW_THREADS), 0, ex.st, 2, v);
+    launch_k(pl->view.Zc <= 128 ? T_post_kernel<4> : T_post_kernel<MAXJ>, rows_grid(N + PAD_WARPS), dim3(ROW_THREADS), 0, ex.st, 2, v);
     ex.chk();
   }
   if (pl->has_fprop) {

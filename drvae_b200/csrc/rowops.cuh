@@ -304,6 +304,9 @@ __device__ __forceinline__ float kl_term(float muq, float lvq, float mup, float 
 // DrVAE.py:427) for every MC sample and scatter them to the stacked decoder rows.
 // grid (ceil((N + PAD_WARPS) / ROW_WARPS), n_models)
 // ---------------------------------------------------------------------------------------------
+// J: feature slots per lane held in registers (latent dim <= 32 J); 4 covers the README's 100-dim latents within the
+// 48-register budget of 5 blocks per SM, MAXJ is the general case
+template <int J>
 __global__ void __launch_bounds__(ROW_THREADS, 5) sample_q1_kernel(DevView v) {
   pdl_launch_dependents();
   pdl_wait();
@@ -328,19 +331,36 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) sample_q1_kernel(DevView v) {
   bf16* zdec = v.Zdec.at(m);
   bf16* z1e = v.has_fprop ? v.Z1e.at(m) : nullptr;
   const int ycl = v.has_fprop ? v.ycls.at(m)[i] : 0;
+  // q(z1|x1) statistics of this row, staged in registers: feature f = lane + 32 k
+  float mu[J], sd[J];
+#pragma unroll
+  for (int k = 0; k < J; ++k) {
+    const int f = lane + 32 * k;
+    mu[k] = f < v.Z ? q[f] : 0.f;
+    sd[k] = f < v.Z ? expf(0.5f * q[v.Z + f]) : 0.f;
+  }
   for (int l = 0; l < v.L; ++l) {
     const int r = l * N + i;
     const float* e1 = v.eps_z1.at(m) + ((long long)l * v.Ncap + i) * v.Z;
     const float* e2 = v.eps_z2.at(m) + ((long long)l * v.Ncap + i) * v.Z;
-    for (int f = lane; f < v.Zc; f += 32) {
+    float n1[J], n2[J];
+#pragma unroll
+    for (int k = 0; k < J; ++k) {  // all noise loads of this sample before the first store
+      const int f = lane + 32 * k;
+      n1[k] = f < v.Z ? e1[f] : 0.f;
+      n2[k] = (f < v.Z && p >= 0) ? e2[f] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < J; ++k) {
+      const int f = lane + 32 * k;
+      if (f >= v.Zc) continue;
       // feature Z is the ones column (bias gradients); features Z+1+j are the one-hot class
       // columns of the [z1, onehot(y)] input of q(z_top | z1, y)
       float z = (f == v.Z) ? 1.f : 0.f, z2 = z;
       if (f < v.Z) {
-        const float mu = q[f], sd = expf(0.5f * q[v.Z + f]);
-        z = mu + sd * e1[f];
+        z = mu[k] + sd[k] * n1[k];
         v.Z1f.at(m)[(long long)r * v.Z + f] = z;
-        if (p >= 0) z2 = mu + sd * e2[f];
+        if (p >= 0) z2 = mu[k] + sd[k] * n2[k];
       }
       st_c8(zdec, v.Zdec.rcap, r, f, z);
       if (p >= 0) st_c8(zdec, v.Zdec.rcap, LN + l * Np + p, f, z2);
@@ -374,6 +394,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) sample_q1_kernel(DevView v) {
 // T_post: after the p(z2|z1) GEMM.  Residual mean, sample z2f, KL(q(z2|x2) || p(z2|z1)) with free
 // bits for pair rows, and the classifier.
 // ---------------------------------------------------------------------------------------------
+template <int J>
 __global__ void __launch_bounds__(ROW_THREADS, 5) T_post_kernel(DevView v) {
   pdl_launch_dependents();
   pdl_wait();
@@ -397,15 +418,30 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) T_post_kernel(DevView v) {
     const float* z1 = v.Z1f.at(m) + (long long)r * v.Z;
     const float* ef = v.eps_z2f.at(m) + ((long long)l * v.Ncap + i) * v.Z;
     float kl = 0.f;
-    for (int f = lane; f < v.Zc; f += 32) {
+    float a_pmu[J], a_plv[J], a_z1[J], a_ef[J], a_q2m[J], a_q2l[J];
+#pragma unroll
+    for (int k = 0; k < J; ++k) {  // every load of this sample before the first store
+      const int f = lane + 32 * k;
+      const bool in = f < v.Z;
+      a_pmu[k] = in ? pt[f] : 0.f;
+      a_plv[k] = in ? pt[v.Z + f] : 0.f;
+      a_z1[k] = in ? z1[f] : 0.f;
+      a_ef[k] = in ? ef[f] : 0.f;
+      a_q2m[k] = (in && q2) ? q2[f] : 0.f;
+      a_q2l[k] = (in && q2) ? q2[v.Z + f] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < J; ++k) {
+      const int f = lane + 32 * k;
+      if (f >= v.Zc) continue;
       float z2f = (f == v.Z) ? 1.f : 0.f;  // ones column
       if (f < v.Z) {
-        const float pmu = pt[f] + z1[f];
-        const float plv = pt[v.Z + f];
+        const float pmu = a_pmu[k] + a_z1[k];
+        const float plv = a_plv[k];
         pt[f] = pmu;
-        z2f = pmu + expf(0.5f * plv) * ef[f];
+        z2f = pmu + expf(0.5f * plv) * a_ef[k];
         v.Z2Ff.at(m)[(long long)r * v.Z + f] = z2f;
-        if (q2) kl += kl_term(q2[f], q2[v.Z + f], pmu, plv);
+        if (q2) kl += kl_term(a_q2m[k], a_q2l[k], pmu, plv);
       }
       if (p >= 0) st_c8(zdec, v.Zdec.rcap, LN + LNp + l * Np + p, f, z2f);
     }

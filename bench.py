@@ -33,6 +33,26 @@ METRIC = "DrVAE train samples/sec (fwd+bwd+Adam)"
 UNIT = "samples/s"
 
 
+_STDOUT_FD = None
+
+
+def quiet_stdout():
+    """stdout carries exactly one JSON line: native libraries that print there (NCCL's version banner at communicator
+    creation) are pointed at stderr for the duration of the run; emit() restores the real stdout for the result."""
+    global _STDOUT_FD
+    if _STDOUT_FD is None:
+        sys.stdout.flush()
+        _STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _STDOUT_FD is not None:
+        os.dup2(_STDOUT_FD, 1)
+    print(json.dumps(line), flush=True)
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -128,7 +148,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args):
@@ -292,7 +312,7 @@ def run_dp8192(args):
         "losses": {k: float(out[i]) for i, k in enumerate(("RECL", "KLD", "PERT", "YL", "MMD", "ELBO", "CMPL"))},
     }
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -312,8 +332,7 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    # stdout carries exactly one JSON line: NCCL's debug output (the version banner at NCCL_DEBUG >= VERSION) goes to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
     if args.workload == "dp8192":
@@ -495,7 +514,7 @@ def main():
         if dump:
             with open(dump, "w") as f:
                 json.dump({"ms_per_step": ms / args.steps, "profiled_ms_per_step": total_prof / PSTEPS, "kernels": rows}, f, indent=1)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 

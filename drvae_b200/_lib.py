@@ -45,7 +45,7 @@ class HParams(ctypes.Structure):
                 ("yloss_rate", c_float), ("kl_min", c_float), ("lr", c_float), ("beta1", c_float),
                 ("beta2", c_float), ("adam_eps", c_float), ("weight_decay", c_float),
                 ("global_N", c_int), ("global_Np", c_int), ("global_Nlab", c_int),
-                ("log_prior_y", c_float * 8)]
+                ("log_prior_y", c_float * 8), ("global_counts_dev", c_void_p)]
 
 
 class EpsLayout(ctypes.Structure):

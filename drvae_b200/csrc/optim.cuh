@@ -143,6 +143,11 @@ __global__ void __launch_bounds__(256) wn_grad_kernel(WnArgs a) {
 __global__ void set_dyn_kernel(StepDyn value, StepDyn* dst) {
   pdl_launch_dependents();
   pdl_wait();
+  if (value.counts_dev) {  // batch-global normalisers left in device memory by the caller's all-reduce
+    value.s.gN = (int)value.counts_dev[0];
+    value.s.gNp = (int)value.counts_dev[1];
+    value.s.gNlab = (int)value.counts_dev[2];
+  }
   *dst = value;
 }
 

@@ -1011,6 +1011,7 @@ StepDyn make_dyn(const drvae_noise_t* nz, const drvae_hparams_t* hp, bool fused_
   d.noise_step = (unsigned)hp->step;
   d.noise_seed = nz ? nz->seed : 0ULL;
   d.row_offset = nz ? nz->row_offset : 0LL;
+  d.counts_dev = hp->global_counts_dev;
   return d;
 }
 

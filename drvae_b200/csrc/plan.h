@@ -129,6 +129,7 @@ struct StepDyn {
   unsigned int noise_step;
   unsigned long long noise_seed;
   long long row_offset;
+  const long long* counts_dev;  // optional device {N, Np, Nlab} summed over the shards: overrides s.gN / gNp / gNlab
 };
 
 struct DevView {

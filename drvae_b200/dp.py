@@ -43,6 +43,14 @@ def global_counts(counts, group=None, device="cpu"):
     return [int(v) for v in t.tolist()]
 
 
+def global_counts_device(counts, device, group=None):
+    """As global_counts, but the sum stays on the device (int64 [3]): the host does not wait for the all-reduce and
+    can keep enqueueing the step (drvae_hparams_t.global_counts_dev)."""
+    t = torch.tensor(counts, dtype=torch.int64).pin_memory().to(device, non_blocking=True)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
 class PlanBackend:
     """Compute backend over the C ABI: one single-model Plan on this rank's GPU."""
 
@@ -93,8 +101,11 @@ class DataParallel:
         be = self.backend
         n = batch["x1"].shape[-2]
         flags = host_flags if host_flags is not None else batch
-        counts = global_counts(local_counts(n, flags.get("has_x2"), flags.get("has_y")), self.group,
-                               device=getattr(be, "device", "cpu"))
+        local = local_counts(n, flags.get("has_x2"), flags.get("has_y"))
+        if self.world > 1 and getattr(be, "comm_stream", None) is not None:
+            counts = global_counts_device(local, be.device, self.group)  # GPU backend: no host round trip
+        else:
+            counts = global_counts(local, self.group, device=getattr(be, "device", "cpu"))
         losses, events = be.grad_step(batch, dict(hp_kwargs or {}), counts, self.finished_training_iters, eps=eps, seed=seed,
                                       row_offset=row_offset)
         flat = be.flat_grads()

@@ -137,7 +137,13 @@ class Plan:
         hp.noise_std, hp.beta_pert, hp.pertloss_rate = noise_std, beta_pert, pertloss_rate
         hp.kl_qz2pz2_rate, hp.yloss_rate, hp.kl_min = kl_qz2pz2_rate, yloss_rate, kl_min
         hp.lr, hp.beta1, hp.beta2, hp.adam_eps, hp.weight_decay = lr, beta1, beta2, adam_eps, weight_decay
-        if global_counts is not None:
+        if isinstance(global_counts, torch.Tensor) and global_counts.is_cuda:
+            # device-resident [N, Np, Nlab] (int64), e.g. straight out of an all-reduce: no host round trip
+            if global_counts.dtype != torch.int64 or global_counts.numel() != 3 or not global_counts.is_contiguous():
+                raise ValueError("device global_counts must be a contiguous int64 tensor of 3 elements")
+            hp.global_counts_dev = global_counts.data_ptr()
+            hp._keep = global_counts
+        elif global_counts is not None:
             hp.global_N, hp.global_Np, hp.global_Nlab = [int(c) for c in global_counts]
         ny = max(1, self.dim_y)
         for j in range(8):

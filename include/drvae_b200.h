@@ -88,6 +88,10 @@ typedef struct {
   float lr, beta1, beta2, adam_eps, weight_decay;
   int global_N, global_Np, global_Nlab;  /* >0: batch-global normalisers (data-parallel shards) */
   float log_prior_y[8];   /* log prior over classes ('uniform' -> log(1/dim_y)) */
+  /* optional: DEVICE pointer to {N, Np, Nlab} as int64, already summed over the shards (e.g. by an NCCL all-reduce
+   * enqueued on the same stream).  Overrides global_* when non-NULL, so a data-parallel step needs no host round
+   * trip for its normalisers. */
+  const long long* global_counts_dev;
 } drvae_hparams_t;
 
 /* Layout of the row-indexed eps block (floats, per model; Ncap = max_batch):

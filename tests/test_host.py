@@ -30,7 +30,7 @@ def test_struct_sizes_match_header_layout():
     assert ctypes.sizeof(_lib.Arch) == 4 * (5 + 4 * (1 + _lib.MAX_HIDDEN) + 3)
     assert ctypes.sizeof(_lib.Batch) == 5 * 8 + 8
     assert ctypes.sizeof(_lib.Noise) == 24  # eps pointer, seed, row_offset
-    assert ctypes.sizeof(_lib.HParams) == 4 * 17 + 4 * 8
+    assert ctypes.sizeof(_lib.HParams) == 4 * 17 + 4 * 8 + 4 + 8  # ... + padding + global_counts_dev pointer
     assert ctypes.sizeof(_lib.EpsLayout) == 7 * 8
     assert ctypes.sizeof(_lib.InferOut) == 10 * 8
 

@@ -478,6 +478,12 @@ def test_row_shards_with_global_counts_add_up(kind):
             l = p.grad_step(shard, p.hparams(step=2, global_counts=counts), seed=1234, row_offset=lo).cpu()
             lsum += l[0]
             gsum += p.grads[0].cpu()
+            if r == 0:
+                # the same normalisers handed over in device memory (what dp.py's all-reduce leaves behind): bit-identical
+                dev_counts = torch.tensor(counts, dtype=torch.int64, device="cuda")
+                l2 = p.grad_step(shard, p.hparams(step=2, global_counts=dev_counts), seed=1234, row_offset=lo).cpu()
+                assert torch.equal(l2, l)
+                assert torch.equal(p.grads[0].cpu(), gsum)
         for i, k in enumerate(LOSS_KEYS):
             assert abs(float(lsum[i]) - float(lf[0, i])) <= 2e-5 * abs(float(lf[0, i])) + 1e-5, (world, k, float(lsum[i]), float(lf[0, i]))
         assert rel_l2(gsum, gf) < 2e-3, (world, rel_l2(gsum, gf))

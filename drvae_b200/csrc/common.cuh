@@ -144,6 +144,11 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* map, int
       : "memory");
 }
 
+// Fetch a tensor map (kernel parameter) into the TMA unit's descriptor cache ahead of its first use.
+__device__ __forceinline__ void tma_prefetch_map(const void* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"((unsigned long long)map) : "memory");
+}
+
 // L2 prefetch of the cache line holding `p` (per-lane address, no destination register).  Used to
 // pull optimizer state towards L2 ahead of the fused Adam epilogue.
 __device__ __forceinline__ void prefetch_l2(const void* p) {

@@ -919,6 +919,9 @@ __global__ void __launch_bounds__((GEMM_PROD_WARPS + 1 + EW) * 32, 1) gemm_tc_ke
   const int total_tiles = p.tiles_m * p.tiles_n * p.ksplit * p.n_models;
 
   if (threadIdx.x == 0) {
+    tma_prefetch_map(&tmA);
+    tma_prefetch_map(&tmB);
+    tma_prefetch_map(&tmB2);
     for (int s = 0; s < p.nstages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -1280,8 +1283,10 @@ inline cudaError_t gemm_launch_t(GemmProblem p, const EpiParams& e, int n_models
   }
   p.nstages = gemm_pick_stages(p.BN);
   // weight-gradient tiles have short contractions (batch rows) and a long HBM-bound epilogue whose
-  // streaming loads/stores go through L1: a shallow operand ring leaves the rest of the 256 KB as L1
-  if (EPI == EPI_GRAD_ADAM && p.nstages > 2) p.nstages = 2;
+  // streaming loads/stores go through L1: a shallow operand ring leaves the rest of the 256 KB as L1.
+  // Only when a CTA runs several tiles, though: with at most one tile per CTA (small layers) nothing hides the
+  // mainloop, and a deeper ring shortens its exposed TMA latency chain.
+  if (EPI == EPI_GRAD_ADAM && p.nstages > 2 && total > gemm_num_sms()) p.nstages = 2;
   size_t smem = (size_t)p.nstages * (GEMM_A_STAGE_BYTES + p.BN * GEMM_BK * 2);
   // fused Adam epilogue (scalar and vector form): 24 warps x 72 registers, its HBM stream scales with resident warps
   constexpr int EW = (EPI == EPI_GRAD_ADAM) ? GEMM_ADAM_EPI_WARPS : GEMM_EPI_WARPS;

@@ -64,7 +64,8 @@ EXPORTS = ["drvae_last_error", "drvae_plan_create", "drvae_plan_destroy", "drvae
            "drvae_plan_workspace_bytes", "drvae_plan_bind", "drvae_sync_shadows", "drvae_train_step",
            "drvae_loss_forward", "drvae_grad_step", "drvae_adam_step", "drvae_infer", "drvae_set_gemm_impl",
            "drvae_plan_launch_count", "drvae_debug_buffer", "drvae_debug_gemm", "drvae_profile_begin",
-           "drvae_profile_end", "drvae_plan_num_buckets", "drvae_plan_bucket_info", "drvae_stream_wait_bucket", "drvae_set_graph", "drvae_plan_graph_replays", "drvae_debug_wait_stats"]
+           "drvae_profile_end", "drvae_plan_num_buckets", "drvae_plan_bucket_info", "drvae_stream_wait_bucket", "drvae_set_graph", "drvae_plan_graph_replays", "drvae_debug_wait_stats",
+           "drvae_push_scalars", "drvae_set_external_scalars"]
 
 
 def load():
@@ -116,6 +117,10 @@ def load():
     lib.drvae_plan_graph_replays.argtypes = [c_void_p]
     lib.drvae_infer.restype = c_int
     lib.drvae_infer.argtypes = [c_void_p, c_void_p, c_int, P(InferOut), c_void_p]
+    lib.drvae_push_scalars.restype = c_int
+    lib.drvae_push_scalars.argtypes = [c_void_p, P(Noise), P(HParams), c_int, c_void_p]
+    lib.drvae_set_external_scalars.restype = c_int
+    lib.drvae_set_external_scalars.argtypes = [c_void_p, c_int]
     lib.drvae_debug_wait_stats.restype = c_int
     lib.drvae_debug_wait_stats.argtypes = [c_void_p, c_int]
     lib.drvae_set_gemm_impl.restype = c_int

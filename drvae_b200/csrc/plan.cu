@@ -89,6 +89,7 @@ struct drvae_plan {
   // per-step scalars in device memory + CUDA-graph replay of the launch sequence (see step_entry)
   StepDyn* d_dyn = nullptr;
   bool graph_enabled = true;
+  bool external_dyn = false;  // the caller pushes the per-step scalars (drvae_push_scalars) and captures the sequence itself
   struct GraphEntry {
     int seen = 0;
     cudaGraph_t graph = nullptr;  // kept alive: node handles used for parameter updates belong to it
@@ -1365,6 +1366,7 @@ int step_entry(drvae_plan* pl, int seq, const drvae_batch_t* b, const drvae_nois
   if (!b) return set_error("drvae: batch is null");
   const bool fused = seq == SEQ_TRAIN && train_is_fused(pl, b);
   const StepDyn dyn = make_dyn(nz, hp, fused);
+  if (pl->external_dyn) return enqueue_sequence(pl, seq, b, nz, hp, losses_out, st, fused);
   const bool graphable = pl->graph_enabled && !pl->prof_on && !(nz && nz->eps) && seq != SEQ_GRAD && pl->shadows_valid &&
                          st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;
   if (graphable) {
@@ -1475,9 +1477,22 @@ extern "C" int drvae_grad_step(drvae_plan_t* pl, const drvae_batch_t* b, const d
 
 extern "C" int drvae_adam_step(drvae_plan_t* pl, const drvae_hparams_t* hp, void* stream) {
   if (!pl || !hp) return set_error("drvae_adam_step: null argument");
-  int rc = push_dyn(pl, make_dyn(nullptr, hp, false), (cudaStream_t)stream);
-  if (rc) return rc;
+  if (!pl->external_dyn) {
+    int rc = push_dyn(pl, make_dyn(nullptr, hp, false), (cudaStream_t)stream);
+    if (rc) return rc;
+  }
   return run_adam(pl, hp, 1, (cudaStream_t)stream);
+}
+
+extern "C" int drvae_push_scalars(drvae_plan_t* pl, const drvae_noise_t* nz, const drvae_hparams_t* hp, int fused_adam,
+                                  void* stream) {
+  if (!pl || !hp) return set_error("drvae_push_scalars: null argument");
+  return push_dyn(pl, make_dyn(nz, hp, fused_adam != 0), (cudaStream_t)stream);
+}
+extern "C" int drvae_set_external_scalars(drvae_plan_t* pl, int enable) {
+  if (!pl) return set_error("drvae_set_external_scalars: null plan");
+  pl->external_dyn = enable != 0;
+  return 0;
 }
 
 // Instrumented builds only (-DGEMM_PROFILE_WAITS): copy out (and optionally clear) the per-(mode, epilogue) barrier

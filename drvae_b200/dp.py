@@ -15,6 +15,8 @@ produces an additive share of every loss term and of the gradient:
 the number of ranks.  The communication backend is torch.distributed (NCCL over NVLink on the
 GPU box; gloo in the CPU tests of the host logic, with the oracle as the compute backend).
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -52,14 +54,26 @@ def global_counts_device(counts, device, group=None):
 
 
 class PlanBackend:
-    """Compute backend over the C ABI: one single-model Plan on this rank's GPU."""
+    """Compute backend over the C ABI: one single-model Plan on this rank's GPU.
 
-    def __init__(self, plan):
+    graph=True (default; DRVAE_B200_DP_GRAPH=0 disables): DataParallel.step captures the whole step — gradient
+    kernels, the optimizer — as ONE CUDA graph per set of batch buffers and replays it; only the per-step scalars
+    (drvae_push_scalars) stay outside (1 GPU, batch 8192: 1.03 -> 0.96 ms).  Used on a single rank only for now:
+    capturing the per-bucket NCCL all-reduces as well is what a multi-rank step needs (a shard of a few hundred rows
+    finishes faster than the host can enqueue ~50 launches and 7 collectives), but that capture deadlocked when
+    tried and is left for the next round."""
+
+    def __init__(self, plan, graph=None):
         if plan.E != 1:
             raise ValueError("data-parallel training shards ONE model; ensembles shard by model instead")
         self.plan = plan
         self.device = plan.device
         self.comm_stream = torch.cuda.Stream(device=plan.device)
+        self.graph = (os.environ.get("DRVAE_B200_DP_GRAPH", "1") != "0") if graph is None else bool(graph)
+        self.graphs = {}  # batch buffers -> (CUDAGraph, static losses)
+        self.seen = {}
+        self.counts_pin = torch.zeros(3, dtype=torch.int64).pin_memory()
+        self.counts_dev = torch.zeros(3, dtype=torch.int64, device=plan.device)
 
     def flat_grads(self):
         return self.plan.grads[0]
@@ -93,6 +107,61 @@ class DataParallel:
         if self.world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
 
+    def _enqueue(self, be, batch, hp_kwargs, counts, eps, seed, row_offset):
+        """grad_step -> per-bucket all-reduce on the communication stream -> optimizer, on the current stream."""
+        losses, events = be.grad_step(batch, hp_kwargs, counts, self.finished_training_iters, eps=eps, seed=seed,
+                                      row_offset=row_offset)
+        flat = be.flat_grads()
+        comm = be.comm_stream
+        # bucket k is complete when events[k] fires; its all-reduce runs on the side stream while
+        # the compute stream is still inside the backward pass of the remaining blocks
+        with torch.cuda.stream(comm):
+            for (off, cnt), wait in zip(be.buckets(), events):
+                wait(comm)
+                self._all_reduce(flat[off:off + cnt])
+            self._all_reduce(losses)
+        torch.cuda.current_stream(be.device).wait_stream(comm)
+        be.adam_step()
+        return losses
+
+    def _step_graph(self, be, batch, hp_kwargs, local, seed, row_offset):
+        """Replay (or, the third time a set of batch buffers is seen, capture) the step as one CUDA graph."""
+        plan = be.plan
+        # a graph bakes in the addresses (and dtypes) of the caller's batch buffers
+        key = (int(batch["x1"].shape[-2]),) + tuple((k, v.data_ptr(), str(v.dtype)) for k, v in sorted(batch.items()))
+        # batch-global normalisers: summed on the device, read by set_dyn (no host round trip)
+        if self.world > 1:
+            be.counts_pin.copy_(torch.tensor(local, dtype=torch.int64))
+            be.counts_dev.copy_(be.counts_pin, non_blocking=True)
+            dist.all_reduce(be.counts_dev, op=dist.ReduceOp.SUM, group=self.group)
+            counts = be.counts_dev
+        else:
+            counts = local
+        entry = be.graphs.get(key)
+        if entry is None:
+            if len(be.seen) > 64:  # callers that allocate a new batch every step never reach a capture
+                be.seen.clear()
+            be.seen[key] = be.seen.get(key, 0) + 1
+            if be.seen[key] < 3:  # warm-up: communicators, function attributes, tensor maps
+                return self._enqueue(be, batch, hp_kwargs, counts, None, seed, row_offset)
+            cur = torch.cuda.current_stream(be.device)
+            cur.synchronize()
+            plan.set_external_scalars(True)
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    losses = self._enqueue(be, batch, hp_kwargs, counts, None, seed, row_offset)
+            finally:
+                plan.set_external_scalars(False)
+            if len(be.graphs) >= 8:
+                be.graphs.clear()
+            entry = be.graphs[key] = (g, losses, dict(batch))  # keep the captured buffers alive
+        g, losses, _ = entry
+        hp = plan.hparams(step=self.finished_training_iters, global_counts=counts, **hp_kwargs)
+        plan.push_scalars(hp, seed=seed, row_offset=row_offset, fused=False)
+        g.replay()
+        return losses
+
     def step(self, batch, hp_kwargs=None, eps=None, seed=0, row_offset=0, host_flags=None):
         """batch: this rank's shard (same fields as Plan.train_step).  Returns the GLOBAL losses as
         an 8-vector (RECL, KLD, PERT, YL, MMD, ELBO, CMPL, 0) identical on every rank.
@@ -102,6 +171,13 @@ class DataParallel:
         n = batch["x1"].shape[-2]
         flags = host_flags if host_flags is not None else batch
         local = local_counts(n, flags.get("has_x2"), flags.get("has_y"))
+        # (single rank only: with NCCL collectives inside the capture the one 2-rank attempt of this round deadlocked,
+        #  so ranks > 1 keep the eager, event-overlapped path below)
+        if getattr(be, "graph", False) and self.world == 1 and eps is None and \
+                all(torch.is_tensor(v) and v.is_cuda for v in batch.values()):
+            losses = self._step_graph(be, batch, dict(hp_kwargs or {}), local, seed, row_offset)
+            self.finished_training_iters += 1
+            return losses
         if self.world > 1 and getattr(be, "comm_stream", None) is not None:
             counts = global_counts_device(local, be.device, self.group)  # GPU backend: no host round trip
         else:

@@ -215,6 +215,17 @@ class Plan:
     def loss_forward(self, batch, hp, eps=None, seed=0, row_offset=0):
         return self._run(self.lib.drvae_loss_forward, "loss_forward", batch, hp, eps, seed, row_offset)
 
+    def push_scalars(self, hp, seed=0, row_offset=0, fused=False):
+        """Write one call's per-step scalars to the plan's device block without running a step (caller-side graph
+        capture: see drvae_b200/dp.py)."""
+        nz, _ = self._noise(None, seed, row_offset)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.drvae_push_scalars(self.h, ctypes.byref(nz), ctypes.byref(hp), int(bool(fused)), self._stream()),
+                       "push_scalars")
+
+    def set_external_scalars(self, enable):
+        _lib.check(self.lib.drvae_set_external_scalars(self.h, int(bool(enable))), "set_external_scalars")
+
     def adam_step(self, hp):
         with torch.cuda.device(self.device):
             _lib.check(self.lib.drvae_adam_step(self.h, ctypes.byref(hp), self._stream()), "adam_step")

@@ -156,6 +156,14 @@ int drvae_infer(drvae_plan_t* plan, const float* x1, int N, const drvae_infer_ou
  * per-step scalars live in device memory, so only one kernel node's arguments change between steps.  Calls on
  * the legacy default stream, with a caller-provided eps block, or under profiling are launched kernel by kernel. */
 int drvae_set_graph(drvae_plan_t* plan, int enable);
+/* Caller-side graph capture (drvae_b200/dp.py captures grad_step + its NCCL all-reduces + adam_step as one CUDA
+ * graph): drvae_push_scalars writes a call's per-step scalars (step number, Adam bias corrections, beta_pert, noise
+ * seed / row offset, global counts) to the plan's device block WITHOUT running a step; while external scalars are
+ * enabled the step entry points do not write that block themselves, so a captured launch sequence can be replayed
+ * with fresh scalars pushed before each replay. */
+int drvae_push_scalars(drvae_plan_t* plan, const drvae_noise_t* noise, const drvae_hparams_t* hp, int fused_adam,
+                       void* stream);
+int drvae_set_external_scalars(drvae_plan_t* plan, int enable);
 long long drvae_plan_graph_replays(const drvae_plan_t* plan);
 
 /* Introspection for tests and bench.py */

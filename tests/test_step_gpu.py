@@ -625,3 +625,30 @@ def test_odd_dimensions(kind):
         assert torch.isfinite(out).all()
         first = out.clone() if it == 1 else first
     assert float(out[0, 6]) < float(first[0, 6])
+
+
+@pytest.mark.gpu
+def test_data_parallel_step_graph_replay_equals_eager():
+    """drvae_b200.dp captures grad_step + (all-reduces) + adam_step as one CUDA graph and replays it with the per-step
+    scalars pushed from outside (drvae_push_scalars / drvae_set_external_scalars).  Same trajectory as the eager path."""
+    from drvae_b200 import dp as dpm
+    arch, N = ARCH["tiny"], 64
+    sd = init_state_dict("drvae", seed=SEED_MODEL, **arch)
+    batch = orc.synthetic_batch(N, arch["dim_x"], seed=9)
+    fields = {k: v.cuda() for k, v in batch_fields("drvae", batch).items()}
+    host = {k: batch[k] for k in ("has_x2", "has_y")}
+    out = {}
+    for mode in (False, True):
+        plan = Plan("drvae", L=L, max_batch=N, n_models=1, **arch)
+        plan.load_state_dict(sd)
+        runner = dpm.DataParallel(dpm.PlanBackend(plan, graph=mode))
+        losses = []
+        for it in range(7):
+            res = runner.step(fields, hp_kwargs=dict(beta_pert=anneal_coef(it, 1, 0)), seed=5, host_flags=host)
+            losses.append(res.detach().cpu().clone())
+        out[mode] = (torch.stack(losses), plan.params.cpu().clone())
+        if mode:
+            assert len(runner.backend.graphs) == 1  # captured on the third step, replayed afterwards
+    assert torch.equal(out[False][0], out[True][0])
+    assert torch.equal(out[False][1], out[True][1])
+    assert not torch.equal(out[True][0][3], out[True][0][4])  # the pushed scalars really change between replays

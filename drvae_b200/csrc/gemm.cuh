@@ -689,17 +689,17 @@ __device__ __forceinline__ void adam_epilogue_row(const GemmProblem& p, const Ep
 
 // ---------------------------------------------------------------------------------------------
 // Vectorised form of the fused weight-gradient + Adam epilogue (the default; the scalar form above
-// remains for layers whose weight rows are not even 8-byte aligned).  After tcgen05.ld a thread
+// remains for layers whose weight rows are not 16-byte aligned).  After tcgen05.ld a thread
 // holds 8 columns (weight rows) of ONE input feature k; a 4x4 transpose inside each lane quad
 // (4 shuffles per 4 columns) turns that into 4 CONSECUTIVE k of 2 weight rows, so the optimizer
 // state streams as 16-byte accesses: 6 LDG.128 + 6 STG.128 (+ 2 x 8-byte bf16 shadow stores) per
 // thread and half-chunk instead of 24 + 24 (+ 8) scalar ones for the same bytes.  Memory-level
 // parallelism per resident warp is 4x that of the scalar form, which is what the HBM stream of
 // this kernel is limited by (tools/adam_pattern_bench.cu: 3.6-4.2 -> 4.8 TB/s in this geometry).
-// Used when the weight rows are 16-byte aligned (ld % 4 == 0, VEC = 4).  Measured on B200 (32 models,
+// Used when the weight rows are 16-byte aligned (ld % 4 == 0).  Measured on B200 (32 models,
 // profiles/r01_experiments.md): decoder heads 261 -> 226 us; with 8-byte aligned rows (ld = 978 or
-// 102, two float2 per row, VEC = 2) the vector form is slower than the scalar one (166 -> 183 us),
-// so those layers keep the scalar epilogue.  The ragged end of the feature range (k4 + 3 >= kin:
+// 102) an 8-byte variant of this epilogue was slower than the scalar one (166 -> 183 us), so those
+// layers keep the scalar epilogue.  The ragged end of the feature range (k4 + 3 >= kin:
 // last partial quad, the bias row k == kin and the class columns k > kin) is loaded / stored
 // element-wise into the same registers.
 // ---------------------------------------------------------------------------------------------
@@ -722,21 +722,8 @@ struct AdamVecBuf {
   float4 p[2], m[2], v[2];
 };
 
-template <int VEC>
-__device__ __forceinline__ float4 ld_state(const float* a) {
-  if (VEC == 4) return *reinterpret_cast<const float4*>(a);
-  const float2 lo = *reinterpret_cast<const float2*>(a), hi = *reinterpret_cast<const float2*>(a + 2);
-  return make_float4(lo.x, lo.y, hi.x, hi.y);
-}
-template <int VEC>
-__device__ __forceinline__ void st_state(float* a, const float4& x) {
-  if (VEC == 4) {
-    *reinterpret_cast<float4*>(a) = x;
-  } else {
-    *reinterpret_cast<float2*>(a) = make_float2(x.x, x.y);
-    *reinterpret_cast<float2*>(a + 2) = make_float2(x.z, x.w);
-  }
-}
+__device__ __forceinline__ float4 ld_state(const float* a) { return *reinterpret_cast<const float4*>(a); }
+__device__ __forceinline__ void st_state(float* a, const float4& x) { *reinterpret_cast<float4*>(a) = x; }
 
 // Ragged end of the feature range (quads with k4 + 3 >= kin: last weights, the bias row k == kin, class columns
 // k > kin): element offset inside the flat per-model vector, or -1.  s = shadow row.
@@ -750,7 +737,6 @@ __device__ __forceinline__ float& f4c(float4& x, int r) { return r == 0 ? x.x : 
 
 // request p, m, v of this thread's two weight rows, features [k4, k4 + 4); col = first shadow row of the half-chunk.
 // Ragged quads fill the same registers with scalar loads, so they are pipelined like the vector path.
-template <int VEC>
 __device__ __forceinline__ void adam_vec_load(const EpiParams& e, int model, int k4, int col, int ci, AdamVecBuf& b) {
   const float* P = e.adam_p + model * e.grad_ms;
   const float* M1 = e.adam_m + model * e.grad_ms;
@@ -763,9 +749,9 @@ __device__ __forceinline__ void adam_vec_load(const EpiParams& e, int model, int
       b.idx[j] = e.g_tab[col + 4 * j + ci];
       if (b.idx[j] >= 0) {
         const int o = b.idx[j] + k4;
-        b.p[j] = ld_state<VEC>(P + o);
-        b.m[j] = ld_state<VEC>(M1 + o);
-        b.v[j] = ld_state<VEC>(V2 + o);
+        b.p[j] = ld_state(P + o);
+        b.m[j] = ld_state(M1 + o);
+        b.v[j] = ld_state(V2 + o);
       }
     }
   } else if (k4 < e.g_kaug) {
@@ -784,7 +770,6 @@ __device__ __forceinline__ void adam_vec_load(const EpiParams& e, int model, int
   }
 }
 
-template <int VEC>
 __device__ __forceinline__ void adam_vec_apply(const EpiParams& e, int model, int k4, int col, int ci, int lane, uint32_t taddr,
                                                bool have_acc, AdamVecBuf& b) {
   float acc[8];
@@ -817,9 +802,9 @@ __device__ __forceinline__ void adam_vec_apply(const EpiParams& e, int model, in
     for (int j = 0; j < 2; ++j) {
       if (b.idx[j] < 0) continue;
       const int o = b.idx[j] + k4;
-      st_state<VEC>(P + o, b.p[j]);
-      st_state<VEC>(M1 + o, b.m[j]);
-      st_state<VEC>(V2 + o, b.v[j]);
+      st_state(P + o, b.p[j]);
+      st_state(M1 + o, b.m[j]);
+      st_state(V2 + o, b.v[j]);
       const int s = col + 4 * j + ci;
       uint2 pk;
       pk.x = pack_bf16x2(b.p[j].x, b.p[j].y);
@@ -851,7 +836,7 @@ __device__ __forceinline__ void adam_vec_apply(const EpiParams& e, int model, in
   }
 }
 
-template <int GROUPS, int VEC>
+template <int GROUPS>
 __device__ __forceinline__ void adam_epilogue_vec(const GemmProblem& p, const EpiParams& e, const TileInfo& t, int cg, int kbase,
                                                   uint32_t taddr_row, bool have_acc, uint64_t* acc_bar, uint32_t acc_parity) {
   const int lane = threadIdx.x & 31;
@@ -860,7 +845,7 @@ __device__ __forceinline__ void adam_epilogue_vec(const GemmProblem& p, const Ep
   const int nh = nhc > cg ? (nhc - cg + GROUPS - 1) / GROUPS : 0;
   auto lcol = [&](int h) { return (cg + h * GROUPS) * 8; };
   AdamVecBuf A;
-  if (nh > 0) adam_vec_load<VEC>(e, t.model, k4, t.n0 + lcol(0), ci, A);
+  if (nh > 0) adam_vec_load(e, t.model, k4, t.n0 + lcol(0), ci, A);
   if (lane == 0) {
     constexpr int EPI = EPI_GRAD_ADAM;
     (void)EPI;
@@ -870,20 +855,11 @@ __device__ __forceinline__ void adam_epilogue_vec(const GemmProblem& p, const Ep
   }
   __syncwarp();
   tc_fence_after();
-  if (GROUPS <= 4) {
-    // 16 epilogue warps, 96 registers: the loads of the next half-chunk are in flight during the math of this one
-    AdamVecBuf B;
-    for (int h = 0; h < nh; h += 2) {
-      if (h + 1 < nh) adam_vec_load<VEC>(e, t.model, k4, t.n0 + lcol(h + 1), ci, B);
-      adam_vec_apply<VEC>(e, t.model, k4, t.n0 + lcol(h), ci, lane, taddr_row + lcol(h), have_acc, A);
-      if (h + 2 < nh) adam_vec_load<VEC>(e, t.model, k4, t.n0 + lcol(h + 2), ci, A);
-      if (h + 1 < nh) adam_vec_apply<VEC>(e, t.model, k4, t.n0 + lcol(h + 1), ci, lane, taddr_row + lcol(h + 1), have_acc, B);
-    }
-  } else {
-    for (int h = 0; h < nh; ++h) {
-      adam_vec_apply<VEC>(e, t.model, k4, t.n0 + lcol(h), ci, lane, taddr_row + lcol(h), have_acc, A);
-      if (h + 1 < nh) adam_vec_load<VEC>(e, t.model, k4, t.n0 + lcol(h + 1), ci, A);
-    }
+  // one half-chunk in flight per warp: 24 warps x 72 registers provide the memory-level parallelism (a 16-warp,
+  // 96-register variant with double-buffered loads measured slower: 254 vs 226 us on the decoder heads)
+  for (int h = 0; h < nh; ++h) {
+    adam_vec_apply(e, t.model, k4, t.n0 + lcol(h), ci, lane, taddr_row + lcol(h), have_acc, A);
+    if (h + 1 < nh) adam_vec_load(e, t.model, k4, t.n0 + lcol(h + 1), ci, A);
   }
 }
 
@@ -895,7 +871,7 @@ __device__ __forceinline__ void adam_epilogue_vec(const GemmProblem& p, const Ep
 // The accumulator is double-buffered (acc_full / acc_empty mbarriers), so the epilogue of tile i —
 // for the weight gradients a long HBM-bound Adam stream — overlaps the mainloop of tile i+1.
 // ---------------------------------------------------------------------------------------------
-// VEC (EPI_GRAD_ADAM only): vector width of the optimizer-state accesses, 4 / 2 (adam_epilogue_vec) or 1 (adam_epilogue_row)
+// VEC (EPI_GRAD_ADAM only): vector width of the optimizer-state accesses, 4 (adam_epilogue_vec) or 1 (adam_epilogue_row)
 template <int EPI, int EW, int VEC>
 __global__ void __launch_bounds__((GEMM_PROD_WARPS + 1 + EW) * 32, 1) gemm_tc_kernel(const GemmProblem p, const EpiParams e,
                                                                                      const __grid_constant__ CUtensorMap tmA,
@@ -1106,8 +1082,8 @@ __global__ void __launch_bounds__((GEMM_PROD_WARPS + 1 + EW) * 32, 1) gemm_tc_ke
       const bool have_acc = t.kb_end > t.kb_begin;
       const uint32_t taddr_row = tmem_base + a * ncols + ((uint32_t)(q * 32) << 16);
       if (EPI == EPI_GRAD_ADAM) {
-        if (VEC >= 2)
-          adam_epilogue_vec<EW / 4, (VEC >= 2 ? VEC : 2)>(p, e, t, cg, t.m0 + q * 32, taddr_row, have_acc, &acc_full[a], aph);
+        if (VEC == 4)
+          adam_epilogue_vec<EW / 4>(p, e, t, cg, t.m0 + q * 32, taddr_row, have_acc, &acc_full[a], aph);
         else
           adam_epilogue_row<EW / 4>(p, e, t, cg, t.m0 + q * 32 + lane, taddr_row, have_acc, &acc_full[a], aph);
       } else {

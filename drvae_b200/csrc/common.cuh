@@ -25,7 +25,8 @@ typedef __nv_bfloat16 bf16;
 // (row, 8-feature chunk), rows contiguous inside a chunk.  `rcap` is the row capacity (row
 // stride between chunks).  A [rows x 8k] slab of this buffer is already the no-swizzle UMMA
 // canonical layout, K-major when the contraction runs over features and MN-major when it runs
-// over rows, so one storage format feeds forward, dX and dW GEMMs with plain 1-D bulk copies.
+// over rows, so one storage format feeds forward, dX and dW GEMMs: a tile is one TMA box of a 3-D tensor map over
+// {row x 16 B, feature chunk, model} (gemm.cuh, gemm_c8_map).
 // ---------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ long long c8_index(int row, int feat, int rcap) {
   return ((long long)(feat >> 3) * rcap + row) * 8 + (feat & 7);
@@ -124,16 +125,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, DebugW
 }
 
 // ---------------------------------------------------------------------------------------------
-// 1-D bulk copy global -> shared (TMA engine, SASS UBLKCP), completion on an mbarrier.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-          smem_u32(smem_dst)),
-      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
-
 // Tensor load global -> shared of one 3-D box (TMA unit, SASS UTMALDG), completion on an mbarrier.  `map` must
 // live in parameter (__grid_constant__), constant or global memory.
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* map, int c0, int c1, int c2, uint64_t* bar) {

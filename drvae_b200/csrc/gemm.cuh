@@ -54,9 +54,10 @@ constexpr int GEMM_MAX_STAGES = 8;
 constexpr int GEMM_A_STAGE_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
 constexpr int GEMM_EPI_WARPS = 16;                     // epilogue warps of the persistent kernel
 constexpr int EPI_GROUPS = GEMM_EPI_WARPS / 4;         // column groups: a warp reads TMEM lanes 32*(warp%4).., columns of its group
-constexpr int GEMM_PROD_WARPS = 3;                     // producer warps: a bulk copy is issued from uniform registers, one
-                                                       // lane at a time, so the 16..48 copies of a k-block are spread over 3 warps
-constexpr int GEMM_MMA_WARP = GEMM_PROD_WARPS;         // warps 0..2 producers, warp 3 MMA issuer, warps 4..19 epilogue
+constexpr int GEMM_PROD_WARPS = 3;                     // warps before the MMA warp: warp 0 is the TMA producer, warps 1-2 are idle
+                                                       // (they issued bulk copies before the operands moved to tensor loads; the
+                                                       // count keeps epilogue warp w on TMEM lane quarter w % 4)
+constexpr int GEMM_MMA_WARP = GEMM_PROD_WARPS;         // warp 3: MMA issuer; warps 4.. epilogue
 constexpr int GEMM_EPI_WARP0 = GEMM_PROD_WARPS + 1;
 constexpr int GEMM_THREADS = (GEMM_PROD_WARPS + 1 + GEMM_EPI_WARPS) * 32;
 constexpr int GEMM_ADAM_EPI_WARPS = 24;                // the fused dW+Adam epilogue is an HBM stream whose bandwidth scales with
@@ -865,9 +866,10 @@ __device__ __forceinline__ void adam_epilogue_vec(const GemmProblem& p, const Ep
 
 // ---------------------------------------------------------------------------------------------
 // Tensor-core kernel: persistent (one CTA per SM, tiles strided by gridDim.x) and warp-specialised.
-//   warps 0..2    bulk-copy producers: operand slabs -> shared-memory ring (full/empty mbarriers)
-//   warp 3        lane 0 issues tcgen05.mma into one of two TMEM accumulator tiles; owns TMEM
-//   warps 4..19   epilogue: warp w reads TMEM lanes [32(w%4), +32), columns of group (w-4)/4
+//   warp 0        producer: TMA tensor loads of the operand tiles -> shared-memory ring (full/empty mbarriers)
+//   warps 1..2    idle
+//   warp 3        one elected lane issues tcgen05.mma into one of two TMEM accumulator tiles; owns TMEM
+//   warps 4..     epilogue (16, or 24 for the fused Adam): warp w reads TMEM lanes [32(w%4), +32), columns of group (w-4)/4
 // The accumulator is double-buffered (acc_full / acc_empty mbarriers), so the epilogue of tile i —
 // for the weight gradients a long HBM-bound Adam stream — overlaps the mainloop of tile i+1.
 // ---------------------------------------------------------------------------------------------

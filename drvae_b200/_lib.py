@@ -65,7 +65,7 @@ EXPORTS = ["drvae_last_error", "drvae_plan_create", "drvae_plan_destroy", "drvae
            "drvae_loss_forward", "drvae_grad_step", "drvae_adam_step", "drvae_infer", "drvae_set_gemm_impl",
            "drvae_plan_launch_count", "drvae_debug_buffer", "drvae_debug_gemm", "drvae_profile_begin",
            "drvae_profile_end", "drvae_plan_num_buckets", "drvae_plan_bucket_info", "drvae_stream_wait_bucket", "drvae_set_graph", "drvae_plan_graph_replays", "drvae_debug_wait_stats",
-           "drvae_push_scalars", "drvae_set_external_scalars"]
+           "drvae_push_scalars", "drvae_set_external_scalars", "drvae_debug_side_delay", "drvae_plan_tensor_ld"]
 
 
 def load():
@@ -89,6 +89,8 @@ def load():
     lib.drvae_plan_num_tensors.argtypes = [c_void_p]
     lib.drvae_plan_tensor_info.restype = c_int
     lib.drvae_plan_tensor_info.argtypes = [c_void_p, c_int, ctypes.c_char_p, c_int, P(c_int), P(c_int), P(c_ll)]
+    lib.drvae_plan_tensor_ld.restype = c_int
+    lib.drvae_plan_tensor_ld.argtypes = [c_void_p, c_int]
     lib.drvae_plan_eps_layout.restype = c_int
     lib.drvae_plan_eps_layout.argtypes = [c_void_p, P(EpsLayout)]
     lib.drvae_plan_workspace_bytes.restype = c_ll
@@ -123,6 +125,8 @@ def load():
     lib.drvae_set_external_scalars.argtypes = [c_void_p, c_int]
     lib.drvae_debug_wait_stats.restype = c_int
     lib.drvae_debug_wait_stats.argtypes = [c_void_p, c_int]
+    lib.drvae_debug_side_delay.restype = c_int
+    lib.drvae_debug_side_delay.argtypes = [c_void_p, c_ll]
     lib.drvae_set_gemm_impl.restype = c_int
     lib.drvae_set_gemm_impl.argtypes = [c_void_p, c_int]
     lib.drvae_profile_begin.restype = c_int

@@ -26,7 +26,8 @@ __device__ __forceinline__ void write_derived(const Seg& s, int idx, float pv, b
   if (s.kind == SEG_W) {
     if (s.wn_g_off >= 0) return;  // weight-normalised layers: shadow = g v / ||v||, written row-wise
     const int local = idx - s.off;
-    const int n = local / s.cols, k = local - n * s.cols;
+    const int n = local / s.ld, k = local - n * s.ld;
+    if (k >= s.cols) return;  // row padding
     const int srow = (n / s.ilv_block) * s.ilv_stride + s.which * s.ilv_block + (n % s.ilv_block);
     if (k < s.kmain)
       shadow[s.sh_off + c8_index(srow, k, s.sh_rcap)] = __float2bfloat16_rn(pv);
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamArgs a) {
     }
     if (si < 0 || idx < a.segs[si].off || (si + 1 < a.nseg && idx >= a.segs[si + 1].off)) si = seg_find(a.segs, a.nseg, idx);
     // tensors start on 16-byte boundaries: an index in the padding after a segment belongs to no tensor
-    if (idx - a.segs[si].off < a.segs[si].rows * a.segs[si].cols) write_derived(a.segs[si], idx, pv, sh, dv);
+    if (idx - a.segs[si].off < a.segs[si].rows * a.segs[si].ld) write_derived(a.segs[si], idx, pv, sh, dv);
   }
 }
 
@@ -101,17 +102,17 @@ __global__ void __launch_bounds__(256) wn_refresh_kernel(WnArgs a) {
   const WnRow w = a.rows[r];
   const float* vrow = a.params.at(m) + w.w_off;
   float ss = 0.f;
-  for (int k = lane; k < w.ld; k += 32) ss += vrow[k] * vrow[k];
+  for (int k = lane; k < w.len; k += 32) ss += vrow[k] * vrow[k];
   ss = warp_sum(ss);
   const float scale = a.params.at(m)[w.g_idx] / sqrtf(ss);
   if (w.sh_off >= 0) {
     bf16* sh = a.shadow.at(m) + w.sh_off;
     for (int k = lane; k < w.kin; k += 32) sh[c8_index(w.srow, k, w.sh_rcap)] = __float2bfloat16_rn(scale * vrow[k]);
     float* cb = a.derived.at(m) + w.aux_off;
-    for (int k = w.kin + lane; k < w.ld; k += 32) cb[(long long)(k - w.kin) * w.aux_ld + w.srow] = scale * vrow[k];
+    for (int k = w.kin + lane; k < w.len; k += 32) cb[(long long)(k - w.kin) * w.aux_ld + w.srow] = scale * vrow[k];
   } else {
     float* eff = a.derived.at(m) + w.aux_off;
-    for (int k = lane; k < w.ld; k += 32) eff[k] = scale * vrow[k];
+    for (int k = lane; k < w.len; k += 32) eff[k] = scale * vrow[k];
   }
 }
 
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(256) wn_grad_kernel(WnArgs a) {
   const float* vrow = a.params.at(m) + w.w_off;
   float* grow = a.grads.at(m) + w.w_off;
   float ss = 0.f, dot = 0.f;
-  for (int k = lane; k < w.ld; k += 32) {
+  for (int k = lane; k < w.len; k += 32) {
     const float vk = vrow[k];
     ss += vk * vk;
     dot += grow[k] * vk;
@@ -135,8 +136,15 @@ __global__ void __launch_bounds__(256) wn_grad_kernel(WnArgs a) {
   const float inv = 1.f / sqrtf(ss);
   const float g = a.params.at(m)[w.g_idx];
   const float c1 = g * inv, c2 = g * dot * inv * inv * inv;
-  for (int k = lane; k < w.ld; k += 32) grow[k] = c1 * grow[k] - c2 * vrow[k];
+  for (int k = lane; k < w.len; k += 32) grow[k] = c1 * grow[k] - c2 * vrow[k];
   if (lane == 0) a.grads.at(m)[w.g_idx] = dot * inv;
+}
+
+// test knob (drvae_debug_side_delay): holds a stream for `cycles` clocks so that a missing cross-stream dependency
+// shows up as a wrong result instead of passing by timing luck
+__global__ void spin_kernel(long long cycles) {
+  const long long t0 = clock64();
+  while (clock64() - t0 < cycles) __nanosleep(64);
 }
 
 // writes the per-step scalars; the only kernel whose arguments differ between two steps of the same shape

@@ -105,8 +105,9 @@ struct drvae_plan {
   // side stream for the label-dependent branch (see run_step)
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_qy = nullptr, ev_side_fwd = nullptr, ev_side_bwd = nullptr, ev_begin = nullptr, ev_eps = nullptr,
-              ev_clf = nullptr;
+              ev_clf = nullptr, ev_kfp = nullptr;
   bool overlap = true;
+  long long side_delay_cycles = 0;  // test knob (drvae_debug_side_delay): spin on the side stream before pz1_post
   // gradient buckets (data-parallel overlap): contiguous parameter ranges in backward completion order
   std::vector<std::pair<long long, long long>> buckets;  // (offset, count)
   std::vector<cudaEvent_t> bucket_ev;
@@ -132,7 +133,11 @@ int add_tensor(drvae_plan* pl, const std::string& name, int rows, int cols) {
   // padding elements are zero parameters with zero gradients and stay zero
   pl->P = round_up(pl->P, 4);
   t.off = pl->P;
-  pl->P += rows * (cols > 0 ? cols : 1);
+  // matrix rows are 16-byte aligned as well (row stride = cols rounded up to 4 floats): the optimizer state of a
+  // weight tile can then be moved by TMA tensor loads / stores (global strides must be multiples of 16 bytes) and
+  // every layer takes the 16-byte epilogue paths.  Padding elements behave like the padding between tensors.
+  t.ld = cols > 0 ? round_up(cols, 4) : 1;
+  pl->P += rows * t.ld;
   pl->tensors.push_back(t);
   return (int)pl->tensors.size() - 1;
 }
@@ -143,6 +148,7 @@ void add_seg_plain(drvae_plan* pl, int tid) {
   s.off = t.off;
   s.rows = t.rows;
   s.cols = t.cols > 0 ? t.cols : 1;
+  s.ld = t.ld;
   s.kind = SEG_PLAIN;
   s.wn_g_off = -1;
   s.ilv_block = s.ilv_stride = 1 << 30;
@@ -166,7 +172,7 @@ Shadow make_shadow(drvae_plan* pl, int ntens, const int* w_tid, const int* b_tid
   sh.tiles_nx = tx.tiles;
   sh.ilv_block = ilv_block;
   sh.ilv_stride = ilv_stride;
-  sh.ld = kin + class_cols;
+  sh.ld = round_up(kin + class_cols, 4);
   sh.off = pl->shadow_elems;
   pl->shadow_elems += (long long)(sh.kc / 8) * sh.rcap * 8;
   sh.bias_off = pl->derived_elems;
@@ -188,6 +194,7 @@ Shadow make_shadow(drvae_plan* pl, int ntens, const int* w_tid, const int* b_tid
     s.off = wt.off;
     s.rows = wt.rows;
     s.cols = wt.cols;
+    s.ld = wt.ld;
     s.kind = SEG_W;
     s.sh_off = sh.off;
     s.sh_rcap = sh.rcap;
@@ -208,6 +215,7 @@ Shadow make_shadow(drvae_plan* pl, int ntens, const int* w_tid, const int* b_tid
     b.off = bt.off;
     b.rows = bt.rows;
     b.cols = 1;
+    b.ld = 1;
     b.kind = SEG_B;
     b.which = w;
     b.ilv_block = ilv_block;
@@ -239,6 +247,7 @@ Shadow make_shadow(drvae_plan* pl, int ntens, const int* w_tid, const int* b_tid
         r.w_off = sh.w_off[which] + n * sh.ld;
         r.g_idx = sh.g_off[which] + n;
         r.ld = sh.ld;
+        r.len = kin + class_cols;
         r.kin = kin;
         r.sh_off = sh.off;
         r.sh_rcap = sh.rcap;
@@ -280,8 +289,9 @@ void build_gauss_block(drvae_plan* pl, MlpBlock& blk, const std::string& prefix,
   }
   if (!sigma_heads) {
     const float bc[2] = {0.f, -2.f};  // logvar = lin(h) - 2  (blocks.py:296)
-    Tiling t = tile_cap(2 * out_dim);
-    blk.head = make_shadow(pl, 2, wt, bt, out_dim, prev, 0, out_dim, 2 * out_dim, t.BN, t.tiles, bc, pl->wn ? gt : nullptr);
+    const int os = round_up(out_dim, 16);  // (mu | logvar) stacked in 16-aligned blocks (DevView::Zs)
+    Tiling t = tile_cap(2 * os);
+    blk.head = make_shadow(pl, 2, wt, bt, out_dim, prev, 0, os, 2 * os, t.BN, t.tiles, bc, pl->wn ? gt : nullptr);
   } else {
     const int hb = std::min(128, round_up(out_dim, 16));
     pl->dec_hb = hb;
@@ -322,6 +332,16 @@ C8Buf c8_of(drvae_plan* pl, const BufRec& r) {
   return b;
 }
 
+}  // namespace
+
+namespace {
+void drop_graphs(drvae_plan* pl) {
+  for (auto& kv : pl->graphs) {
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    if (kv.second.graph) cudaGraphDestroy(kv.second.graph);
+  }
+  pl->graphs.clear();
+}
 }  // namespace
 
 // =============================================================================================
@@ -371,8 +391,9 @@ extern "C" int drvae_plan_create(const drvae_arch_t* a, int n_models, drvae_plan
     wt[1] = add_tensor(pl, "decoder_z2Fz1.encoder_lv.linear_lv.weight", Z, Z);
     bt[1] = add_tensor(pl, "decoder_z2Fz1.encoder_lv.linear_lv.bias", Z, 0);
     const float bc[2] = {0.f, -2.f};
-    Tiling t = tile_cap(2 * Z);
-    pl->Tsh = make_shadow(pl, 2, wt, bt, Z, Z, 0, Z, 2 * Z, t.BN, t.tiles, bc);
+    const int Zs = round_up(Z, 16);
+    Tiling t = tile_cap(2 * Zs);
+    pl->Tsh = make_shadow(pl, 2, wt, bt, Z, Z, 0, Zs, 2 * Zs, t.BN, t.tiles, bc);
     r_T[0] = p0, r_T[1] = pl->P - p0, p0 = pl->P;
   }
   if (pl->has_clf) {
@@ -386,14 +407,15 @@ extern "C" int drvae_plan_create(const drvae_arch_t* a, int n_models, drvae_plan
       int g = add_tensor(pl, "encoder_y.decoder_p.linear_p.g", Y, 0);
       add_seg_plain(pl, g);
       pl->clf_eff_off = pl->derived_elems;
-      pl->derived_elems += round_up(Y * pl->clf_in, 64);
+      pl->derived_elems += round_up(Y * pl->tensors[w].ld, 64);
       for (int n = 0; n < Y; ++n) {
         WnRow r{};
-        r.w_off = pl->clf_w_off + n * pl->clf_in;
+        r.w_off = pl->clf_w_off + n * pl->tensors[w].ld;
         r.g_idx = pl->tensors[g].off + n;
-        r.ld = r.kin = pl->clf_in;
+        r.ld = pl->tensors[w].ld;
+        r.len = r.kin = pl->clf_in;
         r.sh_off = -1;
-        r.aux_off = pl->clf_eff_off + (long long)n * pl->clf_in;
+        r.aux_off = pl->clf_eff_off + (long long)n * pl->tensors[w].ld;
         pl->wn_rows.push_back(r);
       }
     }
@@ -430,6 +452,7 @@ extern "C" int drvae_plan_create(const drvae_arch_t* a, int n_models, drvae_plan
   // feature capacities of the GEMM input buffers: features + ones column (+ one-hot class columns)
   const int Xc = round_up(X + 1, 16);
   const int Zc = round_up(Z + 1 + (pl->has_fprop ? Y : 0), 16), Z3c = round_up(Z3 + 1 + Y, 16);
+  const int Zs = round_up(Z, 16), Z3s = round_up(Z3, 16);
 
   ArenaBuilder ab;
   ab.E = E;
@@ -456,11 +479,11 @@ extern "C" int drvae_plan_create(const drvae_arch_t* a, int n_models, drvae_plan
   BufRec r_e_jj = I32("e_jj", std::max(1, Flcap)), r_e_cls = I32("e_cls_full", Fcap);
   BufRec r_tgt = F32("tgt4", (size_t)R0cap * Xc);
   BufRec r_Ain = C8("Ain", R0cap, Xc);
-  BufRec r_Q = F32("Q", (size_t)R0cap * 2 * Z), r_Z1f = F32("Z1f", (size_t)LNcap * Z);
+  BufRec r_Q = F32("Q", (size_t)R0cap * 2 * Zs), r_Z1f = F32("Z1f", (size_t)LNcap * Z);
   BufRec r_Zdec = C8("Zdec", Rdcap, Zc), r_Z1e = C8("Z1e", Fcap, Zc);
-  BufRec r_PT = F32("PT", (size_t)LNcap * 2 * Z), r_Z2Ff = F32("Z2Ff", (size_t)LNcap * Z);
-  BufRec r_QY = F32("QY", (size_t)LNcap * Y), r_Q3 = F32("Q3", (size_t)Fcap * 2 * Z3);
-  BufRec r_Z3b = C8("Z3b", Fcap, Z3c), r_PZ1 = F32("PZ1", (size_t)Fcap * 2 * Z);
+  BufRec r_PT = F32("PT", (size_t)LNcap * 2 * Zs), r_Z2Ff = F32("Z2Ff", (size_t)LNcap * Z);
+  BufRec r_QY = F32("QY", (size_t)LNcap * Y), r_Q3 = F32("Q3", (size_t)Fcap * 2 * Z3s);
+  BufRec r_Z3b = C8("Z3b", Fcap, Z3c), r_PZ1 = F32("PZ1", (size_t)Fcap * 2 * Zs);
   BufRec r_klq = F32("klq_row", R0cap), r_klz2 = F32("klz2_row", LNcap), r_yl = F32("yl_row", LNcap);
   BufRec r_ycat = F32("ycat_row", LNcap), r_kfp = F32("kfp_row", Fcap), r_kfpw = F32("kfpw_row", Fcap);
   const int dec_tiles = pl->dec.head.tiles_n * EPI_GROUPS;
@@ -470,7 +493,7 @@ extern "C" int drvae_plan_create(const drvae_arch_t* a, int n_models, drvae_plan
   BufRec r_dY7 = C8("dY7", Fcap, pl->has_fprop ? pl->z3b.head.rcap : 16);
   BufRec r_dYT = C8("dYT", LNcap, pl->has_T ? pl->Tsh.rcap : 16);
   BufRec r_dY2 = C8("dY2", R0cap, pl->enc.head.rcap);
-  BufRec r_dQ1e = F32("dQ1e", (size_t)Fcap * 2 * Z), r_dQ2 = F32("dQ2", (size_t)Ncap * 2 * Z);
+  BufRec r_dQ1e = F32("dQ1e", (size_t)Fcap * 2 * Zs), r_dQ2 = F32("dQ2", (size_t)Ncap * 2 * Zs);
   BufRec r_dZ3 = F32("dZ3", (size_t)Fcap * Z3), r_dZ1e = F32("dZ1e", (size_t)Fcap * Z);
   BufRec r_dZdec = F32("dZdec", (size_t)Rdcap * Z), r_dZ1T = F32("dZ1T", (size_t)LNcap * Z);
   BufRec r_DZ1 = F32("DZ1", (size_t)LNcap * Z), r_DZ2F = F32("DZ2F", (size_t)LNcap * Z);
@@ -508,7 +531,7 @@ extern "C" int drvae_plan_create(const drvae_arch_t* a, int n_models, drvae_plan
   if (const char* knob = getenv("DRVAE_B200_SCHED")) pl->sched = atoi(knob);
   if (const char* knob = getenv("DRVAE_B200_PDL")) pdl_mask() = atoi(knob);  // measurement knob: programmatic dependent launch
   cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking);
-  for (cudaEvent_t* ev : {&pl->ev_fork, &pl->ev_qy, &pl->ev_side_fwd, &pl->ev_side_bwd, &pl->ev_begin, &pl->ev_eps, &pl->ev_clf})
+  for (cudaEvent_t* ev : {&pl->ev_fork, &pl->ev_qy, &pl->ev_side_fwd, &pl->ev_side_bwd, &pl->ev_begin, &pl->ev_eps, &pl->ev_clf, &pl->ev_kfp})
     cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
   pl->bucket_ev.resize(pl->buckets.size());
   for (auto& ev : pl->bucket_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
@@ -541,6 +564,9 @@ extern "C" int drvae_plan_create(const drvae_arch_t* a, int n_models, drvae_plan
   v.Xc = Xc;
   v.Zc = Zc;
   v.Z3c = Z3c;
+  v.Zs = Zs;
+  v.Z3s = Z3s;
+  v.clf_ld = round_up(pl->clf_in, 4);
   v.R0cap = R0cap;
   v.LNcap = LNcap;
   v.Rdcap = Rdcap;
@@ -603,16 +629,6 @@ extern "C" int drvae_plan_create(const drvae_arch_t* a, int n_models, drvae_plan
   return 0;
 }
 
-namespace {
-void drop_graphs(drvae_plan* pl) {
-  for (auto& kv : pl->graphs) {
-    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
-    if (kv.second.graph) cudaGraphDestroy(kv.second.graph);
-  }
-  pl->graphs.clear();
-}
-}  // namespace
-
 extern "C" int drvae_plan_destroy(drvae_plan_t* pl) {
   if (!pl) return 0;
   drop_graphs(pl);
@@ -623,7 +639,7 @@ extern "C" int drvae_plan_destroy(drvae_plan_t* pl) {
   if (pl->d_tabs) cudaFree(pl->d_tabs);
   if (pl->d_wn_rows) cudaFree(pl->d_wn_rows);
   for (auto& ev : pl->bucket_ev) cudaEventDestroy(ev);
-  for (cudaEvent_t ev : {pl->ev_fork, pl->ev_qy, pl->ev_side_fwd, pl->ev_side_bwd, pl->ev_begin, pl->ev_eps, pl->ev_clf})
+  for (cudaEvent_t ev : {pl->ev_fork, pl->ev_qy, pl->ev_side_fwd, pl->ev_side_bwd, pl->ev_begin, pl->ev_eps, pl->ev_clf, pl->ev_kfp})
     if (ev) cudaEventDestroy(ev);
   if (pl->side) cudaStreamDestroy(pl->side);
   delete pl;
@@ -644,6 +660,10 @@ extern "C" int drvae_plan_tensor_info(const drvae_plan_t* pl, int index, char* n
   if (cols) *cols = t.cols;
   if (offset) *offset = t.off;
   return 0;
+}
+extern "C" int drvae_plan_tensor_ld(const drvae_plan_t* pl, int index) {
+  if (!pl || index < 0 || index >= (int)pl->tensors.size()) return -1;
+  return pl->tensors[index].ld;
 }
 extern "C" int drvae_plan_eps_layout(const drvae_plan_t* pl, drvae_eps_layout_t* out) {
   if (!pl || !out) return set_error("drvae_plan_eps_layout: null argument");
@@ -667,7 +687,14 @@ extern "C" int drvae_stream_wait_bucket(drvae_plan_t* pl, int index, void* strea
 extern "C" long long drvae_plan_launch_count(const drvae_plan_t* pl) { return pl ? pl->launches : -1; }
 extern "C" int drvae_set_gemm_impl(drvae_plan_t* pl, int impl) {
   if (!pl || (impl != GEMM_IMPL_TC && impl != GEMM_IMPL_SIMT)) return set_error("drvae_set_gemm_impl: bad argument");
+  if (pl->gemm_impl != impl) drop_graphs(pl);  // captured sequences replay the kernels of the old implementation
   pl->gemm_impl = impl;
+  return 0;
+}
+extern "C" int drvae_debug_side_delay(drvae_plan_t* pl, long long cycles) {
+  if (!pl || cycles < 0) return set_error("drvae_debug_side_delay: bad argument");
+  pl->side_delay_cycles = cycles;
+  drop_graphs(pl);
   return 0;
 }
 
@@ -1155,7 +1182,7 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
   // ---- encoder q(z1|x1), shared with q(z2|x2) (DrVAE.py:408,418) ----
   ex.phase = "enc.fwd";
   ex.block_hidden_fwd(pl->enc, v.Ain, 0, CNT_R0, R0b);
-  ex.gemm_nt(pl->enc.H.back(), 0, pl->enc.head, EPI_STORE_F32, ex.epi_f32(v.Q.p, v.Q.ms, 2 * pl->Z, 2 * pl->Z, &pl->enc.head),
+  ex.gemm_nt(pl->enc.H.back(), 0, pl->enc.head, EPI_STORE_F32, ex.epi_f32(v.Q.p, v.Q.ms, 2 * pl->view.Zs, 2 * pl->view.Zs, &pl->enc.head),
              CNT_R0, R0b);
   if (!(nz && nz->eps) && (pl->sched & 1)) after(st, pl->ev_eps, side);  // latent noise of this step
   ex.pre("sample_q1");
@@ -1171,14 +1198,14 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
     ex.phase = "z3.fwd";
     ex.block_hidden_fwd(pl->z3b, v.Z1e, 0, CNT_F, Fb);
     ex.gemm_nt(pl->z3b.H.back(), 0, pl->z3b.head, EPI_STORE_F32,
-               ex.epi_f32(v.Q3.p, v.Q3.ms, 2 * pl->Z3, 2 * pl->Z3, &pl->z3b.head), CNT_F, Fb);
+               ex.epi_f32(v.Q3.p, v.Q3.ms, 2 * pl->view.Z3s, 2 * pl->view.Z3s, &pl->z3b.head), CNT_F, Fb);
     ex.pre("z3_post");
     launch_k(z3_post_kernel, rows_grid(round_up(Fb, 128)), dim3(ROW_THREADS), 0, ex.st, 2, v);
     ex.chk();
     ex.phase = "dz1.fwd";
     ex.block_hidden_fwd(pl->dz1b, v.Z3b, 0, CNT_F, Fb);
     ex.gemm_nt(pl->dz1b.H.back(), 0, pl->dz1b.head, EPI_STORE_F32,
-               ex.epi_f32(v.PZ1.p, v.PZ1.ms, 2 * pl->Z, 2 * pl->Z, &pl->dz1b.head), CNT_F, Fb);
+               ex.epi_f32(v.PZ1.p, v.PZ1.ms, 2 * pl->view.Zs, 2 * pl->view.Zs, &pl->dz1b.head), CNT_F, Fb);
   };
   auto clf_bwd = [&]() {
     ex.phase = "clf.bwd";
@@ -1200,7 +1227,7 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
   // ---- p(z2|z1) ----
   ex.phase = "T.fwd";
   if (pl->has_T) {
-    ex.gemm_nt(v.Zdec, 0, pl->Tsh, EPI_STORE_F32, ex.epi_f32(v.PT.p, v.PT.ms, 2 * pl->Z, 2 * pl->Z, &pl->Tsh), CNT_LN, LNb);
+    ex.gemm_nt(v.Zdec, 0, pl->Tsh, EPI_STORE_F32, ex.epi_f32(v.PT.p, v.PT.ms, 2 * pl->view.Zs, 2 * pl->view.Zs, &pl->Tsh), CNT_LN, LNb);
     ex.pre("T_post");
     launch_k(pl->view.Zc <= 128 ? T_post_kernel<4> : T_post_kernel<MAXJ>, rows_grid(N + PAD_WARPS), dim3(ROW_THREADS), 0, ex.st, 2, v);
     ex.chk();
@@ -1210,9 +1237,12 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
     // sample_q1 (VFAE) has just produced
     after(side, pl->ev_qy, st);
     on(side);
+    if (pl->side_delay_cycles > 0) spin_kernel<<<1, 1, 0, ex.st>>>(pl->side_delay_cycles);
     ex.pre("pz1_post");
     launch_k(pz1_post_kernel, rows_grid(round_up(Fb, 128)), dim3(ROW_THREADS), 0, ex.st, 2, v);
     ex.chk();
+    // clf_back (main stream) reads the per-class KL terms pz1_post has just written (kfp_row)
+    if (overlap && backward && pl->has_clf && !(pl->sched & 2)) cudaEventRecord(pl->ev_kfp, ex.st);
     if (backward) {
       if (pl->has_clf && (pl->sched & 2)) {
         // classifier backward: needs only q(y|.) (T_post / sample_q1) and the per-class terms pz1_post has just
@@ -1290,6 +1320,7 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
         ++bk;  // ran on the side stream right after pz1_post (bucket event recorded there)
         if (overlap) cudaStreamWaitEvent(st, pl->ev_clf, 0);
       } else {
+        if (overlap && pl->has_fprop) cudaStreamWaitEvent(st, pl->ev_kfp, 0);
         clf_bwd();
         bucket_done();
       }
@@ -1565,13 +1596,13 @@ extern "C" int drvae_infer(drvae_plan_t* pl, const float* x1, int N, const drvae
   prep_kernel<<<dim3(round_up(N, 128) / PREP_ROWS, cdiv(pl->view.Xc, PREP_SLAB), E), PREP_THREADS, 0, st>>>(v);
   ex.chk();
   ex.block_hidden_fwd(pl->enc, v.Ain, 0, CNT_R0, N);
-  ex.gemm_nt(pl->enc.H.back(), 0, pl->enc.head, EPI_STORE_F32, ex.epi_f32(v.Q.p, v.Q.ms, 2 * pl->Z, 2 * pl->Z, &pl->enc.head),
+  ex.gemm_nt(pl->enc.H.back(), 0, pl->enc.head, EPI_STORE_F32, ex.epi_f32(v.Q.p, v.Q.ms, 2 * pl->view.Zs, 2 * pl->view.Zs, &pl->enc.head),
              CNT_R0, N);
   ex.pre("infer_z1");
   infer_z1_kernel<<<rows_grid(N + PAD_WARPS), ROW_THREADS, 0, st>>>(v, o, rows_dec);
   ex.chk();
   if (pl->has_T) {
-    ex.gemm_nt(v.Zdec, 0, pl->Tsh, EPI_STORE_F32, ex.epi_f32(v.PT.p, v.PT.ms, 2 * pl->Z, 2 * pl->Z, &pl->Tsh), CNT_LN, N);
+    ex.gemm_nt(v.Zdec, 0, pl->Tsh, EPI_STORE_F32, ex.epi_f32(v.PT.p, v.PT.ms, 2 * pl->view.Zs, 2 * pl->view.Zs, &pl->Tsh), CNT_LN, N);
     ex.pre("infer_z2");
     infer_z2_kernel<<<rows_grid(N), ROW_THREADS, 0, st>>>(v, o);
     ex.chk();

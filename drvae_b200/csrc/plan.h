@@ -39,6 +39,7 @@ struct Seg {
   int off;   // offset in the flat per-model parameter vector
   int rows;  // out features (or vector length)
   int cols;  // in features (1 for vectors)
+  int ld;    // floats between rows: cols rounded up to 4 (16-byte aligned rows; the padding stays zero)
   int kind;
   // SEG_W: bf16 chunk8 shadow [Kc/8][sh_rcap][8]; columns >= kmain are one-hot class columns
   long long sh_off;
@@ -57,6 +58,7 @@ struct ParamInfo {
   std::string name;
   int rows, cols;  // cols == 0: vector
   int off;
+  int ld;  // floats between rows (cols rounded up to a multiple of 4); 1 for vectors
 };
 
 // One weight matrix as the GEMMs see it (possibly two stacked / interleaved reference tensors).
@@ -75,7 +77,7 @@ struct Shadow {
   int w_off[2];   // flat offsets of the weight tensors
   int b_off[2];   // flat offsets of the bias tensors
   int rows_each[2];
-  int ld;         // leading dimension of the weight tensors (kin + class columns)
+  int ld;         // leading dimension of the weight tensors: kin + class columns, rounded up to 4 (16-byte rows)
   int ilv_block, ilv_stride;
   float bias_const[2];  // constant folded into the derived bias (logvar heads: -2)
   long long tab_off;    // offset of this weight's 3 x rcap gradient-epilogue tables (EpiParams::g_tab)
@@ -89,7 +91,8 @@ struct Shadow {
 struct WnRow {
   int w_off;          // flat offset of v[n][0]
   int g_idx;          // flat index of g[n]
-  int ld;             // row length (kin + class columns)
+  int ld;             // floats between rows of v
+  int len;            // row length (kin + class columns)
   int kin;            // columns that go through the GEMM
   long long sh_off;   // bf16 shadow of the layer (-1: classifier row, fp32 copy only)
   int sh_rcap;
@@ -136,6 +139,10 @@ struct DevView {
   int kind, X, Y, Z, Z3, L, N, Ncap;
   int Xc;            // round_up(X, 16)
   int Zc, Z3c;       // chunk8 feature capacities of the latent buffers
+  int Zs, Z3s;       // column of the logvar half in (mu | logvar) rows: round_up(Z, 16) / round_up(Z3, 16).  The two
+                     // heads of a block are stacked in blocks of 16-aligned width, so an epilogue chunk or a 16-row
+                     // stage of optimizer state never straddles the two weight tensors
+  int clf_ld;        // floats between rows of the classifier weight
   int R0cap, LNcap, Rdcap, Fcap, Flcap;
   int has_pair, has_T, has_clf, has_fprop, clf_in;
   int need_grad;
@@ -154,16 +161,16 @@ struct DevView {
   // activations
   MBuf<float4> tgt4;  // fp32 targets, chunk4: [Xc/4][R0cap] float4
   C8Buf Ain;        // [Xc/8][R0cap][8]
-  MBuf<float> Q;    // [R0cap][2Z]   (mu1 | lv1) rows < N, (mu2 | lv2) rows N + p
+  MBuf<float> Q;    // [R0cap][2 Zs] (mu1 | lv1) rows < N, (mu2 | lv2) rows N + p; logvar at column Zs
   MBuf<float> Z1f;  // [LNcap][Z]
   C8Buf Zdec;       // rows: z1 (L*N) | z2 (L*Np) | z2f (L*Np)
   C8Buf Z1e;        // eval-ordered copies of z1
-  MBuf<float> PT;   // [LNcap][2Z]   (p_mu | p_lv) of p(z2|z1)
+  MBuf<float> PT;   // [LNcap][2 Zs] (p_mu | p_lv) of p(z2|z1)
   MBuf<float> Z2Ff; // [LNcap][Z]
   MBuf<float> QY;   // [LNcap][Y]
-  MBuf<float> Q3;   // [Fcap][2*Z3]
+  MBuf<float> Q3;   // [Fcap][2 Z3s]
   C8Buf Z3b;        // [Z3c/8][Fcap][8]
-  MBuf<float> PZ1;  // [Fcap][2Z]
+  MBuf<float> PZ1;  // [Fcap][2 Zs]
   // per-row loss terms
   MBuf<float> klq_row;   // [R0cap]  PVAE prior KLs
   MBuf<float> klz2_row;  // [LNcap]
@@ -175,8 +182,8 @@ struct DevView {
   int dec_tiles;
   // backward
   C8Buf dY9, dY7, dYT, dY2;
-  MBuf<float> dQ1e;    // [Fcap][2Z]
-  MBuf<float> dQ2;     // [Ncap][2Z]
+  MBuf<float> dQ1e;    // [Fcap][2 Zs]
+  MBuf<float> dQ2;     // [Ncap][2 Zs]
   MBuf<float> dZ3;     // [Fcap][Z3]
   MBuf<float> dZ1e;    // [Fcap][Z]
   MBuf<float> dZdec;   // [Rdcap][Z]

@@ -30,6 +30,11 @@ __device__ __forceinline__ void zero_c8_row(const C8Buf& b, int model, int row, 
   for (int c = lane; c < (b.fcap >> 3); c += 32) p[(long long)c * b.rcap + row] = z;
 }
 __device__ __forceinline__ int pad128(int n) { return (n + 127) & ~127; }
+// zero the columns of a (d mu | d logvar) gradient row that hold neither half: [Z, Zs) and [Zs + Z, fcap)
+__device__ __forceinline__ void zero_c8_gaps(const C8Buf& b, bf16* base, int row, int Z, int Zs, int lane) {
+  for (int f = Z + lane; f < Zs; f += 32) st_c8(base, b.rcap, row, f, 0.f);
+  for (int f = Zs + Z + lane; f < b.fcap; f += 32) st_c8(base, b.rcap, row, f, 0.f);
+}
 
 // ---------------------------------------------------------------------------------------------
 // rowmap: split the minibatch into the reference's row groups without moving rows.
@@ -249,8 +254,8 @@ __device__ __forceinline__ void classifier_row(const DevView& v, int m, int r, i
 #pragma unroll
     for (int j = 0; j < MAXY; ++j) {
       if (j < v.Y) {
-        acc[j] = fmaf(Wc[j * v.clf_in + f], a, acc[j]);
-        if (z2f) acc[j] = fmaf(Wc[j * v.clf_in + v.Z + f], d, acc[j]);
+        acc[j] = fmaf(Wc[j * v.clf_ld + f], a, acc[j]);
+        if (z2f) acc[j] = fmaf(Wc[j * v.clf_ld + v.Z + f], d, acc[j]);
       }
     }
   }
@@ -324,7 +329,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) sample_q1_kernel(DevView v) {
     }
     return;
   }
-  const float* q = v.Q.at(m) + (long long)i * 2 * v.Z;
+  const float* q = v.Q.at(m) + (long long)i * 2 * v.Zs;
   const int p = v.pair_of.at(m)[i];
   const int eb = v.has_fprop ? v.ebase.at(m)[i] : 0;
   const int ecnt = v.has_fprop ? (v.lab.at(m)[i] ? 1 : v.Y) : 0;
@@ -337,7 +342,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) sample_q1_kernel(DevView v) {
   for (int k = 0; k < J; ++k) {
     const int f = lane + 32 * k;
     mu[k] = f < v.Z ? q[f] : 0.f;
-    sd[k] = f < v.Z ? expf(0.5f * q[v.Z + f]) : 0.f;
+    sd[k] = f < v.Z ? expf(0.5f * q[v.Zs + f]) : 0.f;
   }
   for (int l = 0; l < v.L; ++l) {
     const int r = l * N + i;
@@ -376,10 +381,10 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) sample_q1_kernel(DevView v) {
   }
   if (v.kind == KIND_PVAE) {  // KL(q1 || N(0,I)) and KL(q2 || N(0,I)) with free bits (PVAE.py:330-372)
     float k1 = 0.f, k2 = 0.f;
-    const float* q2 = p >= 0 ? v.Q.at(m) + (long long)(N + p) * 2 * v.Z : nullptr;
+    const float* q2 = p >= 0 ? v.Q.at(m) + (long long)(N + p) * 2 * v.Zs : nullptr;
     for (int f = lane; f < v.Z; f += 32) {
-      k1 += kl_prior_term(q[f], q[v.Z + f]);
-      if (q2) k2 += kl_prior_term(q2[f], q2[v.Z + f]);
+      k1 += kl_prior_term(q[f], q[v.Zs + f]);
+      if (q2) k2 += kl_prior_term(q2[f], q2[v.Zs + f]);
     }
     k1 = warp_sum(k1);
     k2 = warp_sum(k2);
@@ -410,11 +415,11 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) T_post_kernel(DevView v) {
     return;
   }
   const int p = v.pair_of.at(m)[i];
-  const float* q2 = p >= 0 ? v.Q.at(m) + (long long)(N + p) * 2 * v.Z : nullptr;
+  const float* q2 = p >= 0 ? v.Q.at(m) + (long long)(N + p) * 2 * v.Zs : nullptr;
   bf16* zdec = v.Zdec.at(m);
   for (int l = 0; l < v.L; ++l) {
     const int r = l * N + i;
-    float* pt = v.PT.at(m) + (long long)r * 2 * v.Z;
+    float* pt = v.PT.at(m) + (long long)r * 2 * v.Zs;
     const float* z1 = v.Z1f.at(m) + (long long)r * v.Z;
     const float* ef = v.eps_z2f.at(m) + ((long long)l * v.Ncap + i) * v.Z;
     float kl = 0.f;
@@ -424,11 +429,11 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) T_post_kernel(DevView v) {
       const int f = lane + 32 * k;
       const bool in = f < v.Z;
       a_pmu[k] = in ? pt[f] : 0.f;
-      a_plv[k] = in ? pt[v.Z + f] : 0.f;
+      a_plv[k] = in ? pt[v.Zs + f] : 0.f;
       a_z1[k] = in ? z1[f] : 0.f;
       a_ef[k] = in ? ef[f] : 0.f;
       a_q2m[k] = (in && q2) ? q2[f] : 0.f;
-      a_q2l[k] = (in && q2) ? q2[v.Z + f] : 0.f;
+      a_q2l[k] = (in && q2) ? q2[v.Zs + f] : 0.f;
     }
 #pragma unroll
     for (int k = 0; k < J; ++k) {
@@ -479,7 +484,7 @@ __global__ void __launch_bounds__(ROW_THREADS) z3_post_kernel(DevView v) {
   }
   int l, i, jj;
   eval_decode(v, m, e, Fl, l, i, jj);
-  const float* q3 = v.Q3.at(m) + (long long)e * 2 * v.Z3;
+  const float* q3 = v.Q3.at(m) + (long long)e * 2 * v.Z3s;
   const float* ez = v.eps_z3.at(m) + (((long long)l * v.Ncap + i) * v.Y + jj) * v.Z3;
   bf16* z3b = v.Z3b.at(m);
   const int cls = v.e_cls_full.at(m)[e];
@@ -487,7 +492,7 @@ __global__ void __launch_bounds__(ROW_THREADS) z3_post_kernel(DevView v) {
   for (int f = lane; f < v.Z3c; f += 32) {
     float z = (f == v.Z3 || f == v.Z3 + 1 + cls) ? 1.f : 0.f;  // ones column, one-hot class column
     if (f < v.Z3) {
-      const float mu = q3[f], lv = q3[v.Z3 + f];
+      const float mu = q3[f], lv = q3[v.Z3s + f];
       z = mu + expf(0.5f * lv) * ez[f];
       kl += kl_prior_term(mu, lv);
     }
@@ -521,10 +526,10 @@ __global__ void __launch_bounds__(ROW_THREADS) pz1_post_kernel(DevView v) {
   }
   int l, i, jj;
   eval_decode(v, m, e, Fl, l, i, jj);
-  const float* q1 = v.Q.at(m) + (long long)i * 2 * v.Z;
-  const float* pz = v.PZ1.at(m) + (long long)e * 2 * v.Z;
+  const float* q1 = v.Q.at(m) + (long long)i * 2 * v.Zs;
+  const float* pz = v.PZ1.at(m) + (long long)e * 2 * v.Zs;
   float kl = 0.f;
-  for (int f = lane; f < v.Z; f += 32) kl += kl_term(q1[f], q1[v.Z + f], pz[f], pz[v.Z + f]);
+  for (int f = lane; f < v.Z; f += 32) kl += kl_term(q1[f], q1[v.Zs + f], pz[f], pz[v.Zs + f]);
   kl = warp_sum(kl);
   const bool act = kl > v.dyn->s.kl_min;
   const float w = eval_weight(v, m, l, i, jj, N);
@@ -537,16 +542,16 @@ __global__ void __launch_bounds__(ROW_THREADS) pz1_post_kernel(DevView v) {
   if (!v.need_grad) return;
   const float cw = act ? v.coefs.at(m)[COEF_KLD] * w : 0.f;
   bf16* dy = v.dY9.at(m);
-  float* dq = v.dQ1e.at(m) + (long long)e * 2 * v.Z;
+  float* dq = v.dQ1e.at(m) + (long long)e * 2 * v.Zs;
   for (int f = lane; f < v.Z; f += 32) {
-    const float mu1 = q1[f], lv1 = q1[v.Z + f], mup = pz[f], lvp = pz[v.Z + f];
+    const float mu1 = q1[f], lv1 = q1[v.Zs + f], mup = pz[f], lvp = pz[v.Zs + f];
     const float d = mu1 - mup, ie = expf(-lvp), ev = expf(lv1);
     st_c8(dy, v.dY9.rcap, e, f, -cw * d * ie);
-    st_c8(dy, v.dY9.rcap, e, v.Z + f, cw * 0.5f * (1.f - (d * d + ev) * ie));
+    st_c8(dy, v.dY9.rcap, e, v.Zs + f, cw * 0.5f * (1.f - (d * d + ev) * ie));
     dq[f] = cw * d * ie;
-    dq[v.Z + f] = cw * 0.5f * (ev * ie - 1.f);
+    dq[v.Zs + f] = cw * 0.5f * (ev * ie - 1.f);
   }
-  for (int f = 2 * v.Z + lane; f < v.dY9.fcap; f += 32) st_c8(dy, v.dY9.rcap, e, f, 0.f);
+  zero_c8_gaps(v.dY9, dy, e, v.Z, v.Zs, lane);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -567,22 +572,22 @@ __global__ void __launch_bounds__(ROW_THREADS) z3_back_kernel(DevView v) {
   }
   int l, i, jj;
   eval_decode(v, m, e, Fl, l, i, jj);
-  const float* q3 = v.Q3.at(m) + (long long)e * 2 * v.Z3;
+  const float* q3 = v.Q3.at(m) + (long long)e * 2 * v.Z3s;
   const float* ez = v.eps_z3.at(m) + (((long long)l * v.Ncap + i) * v.Y + jj) * v.Z3;
   const float* dz = v.dZ3.at(m) + (long long)e * v.Z3;
   float kl = 0.f;
-  for (int f = lane; f < v.Z3; f += 32) kl += kl_prior_term(q3[f], q3[v.Z3 + f]);
+  for (int f = lane; f < v.Z3; f += 32) kl += kl_prior_term(q3[f], q3[v.Z3s + f]);
   kl = warp_sum(kl);
   const float w = eval_weight(v, m, l, i, jj, N);
   const float cw = kl > v.dyn->s.kl_min ? v.coefs.at(m)[COEF_KLD] * w : 0.f;
   bf16* dy = v.dY7.at(m);
   for (int f = lane; f < v.Z3; f += 32) {
-    const float mu = q3[f], lv = q3[v.Z3 + f];
+    const float mu = q3[f], lv = q3[v.Z3s + f];
     const float g = dz[f];
     st_c8(dy, v.dY7.rcap, e, f, g + cw * mu);
-    st_c8(dy, v.dY7.rcap, e, v.Z3 + f, g * 0.5f * expf(0.5f * lv) * ez[f] + cw * 0.5f * (expf(lv) - 1.f));
+    st_c8(dy, v.dY7.rcap, e, v.Z3s + f, g * 0.5f * expf(0.5f * lv) * ez[f] + cw * 0.5f * (expf(lv) - 1.f));
   }
-  for (int f = 2 * v.Z3 + lane; f < v.dY7.fcap; f += 32) st_c8(dy, v.dY7.rcap, e, f, 0.f);
+  zero_c8_gaps(v.dY7, dy, e, v.Z3, v.Z3s, lane);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -636,8 +641,8 @@ __global__ void __launch_bounds__(ROW_THREADS) clf_back_kernel(DevView v) {
 #pragma unroll
     for (int j = 0; j < MAXY; ++j) {
       if (j < v.Y) {
-        a = fmaf(dl[j], Wc[j * v.clf_in + f], a);
-        if (two) b = fmaf(dl[j], Wc[j * v.clf_in + v.Z + f], b);
+        a = fmaf(dl[j], Wc[j * v.clf_ld + f], a);
+        if (two) b = fmaf(dl[j], Wc[j * v.clf_ld + v.Z + f], b);
       }
     }
     v.DZ1.at(m)[(long long)r * v.Z + f] = a - b;
@@ -664,7 +669,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) T_back_kernel(DevView v) {
     return;
   }
   const int p = v.pair_of.at(m)[i];
-  const float* q2 = p >= 0 ? v.Q.at(m) + (long long)(N + p) * 2 * v.Z : nullptr;
+  const float* q2 = p >= 0 ? v.Q.at(m) + (long long)(N + p) * 2 * v.Zs : nullptr;
   const float ckl = v.coefs.at(m)[COEF_KLZ2];
   bf16* dy = v.dYT.at(m);
   float a_mu[MAXJ], a_lv[MAXJ];
@@ -672,7 +677,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) T_back_kernel(DevView v) {
   for (int k = 0; k < MAXJ; ++k) a_mu[k] = a_lv[k] = 0.f;
   for (int l = 0; l < v.L; ++l) {
     const int r = l * N + i;
-    const float* pt = v.PT.at(m) + (long long)r * 2 * v.Z;
+    const float* pt = v.PT.at(m) + (long long)r * 2 * v.Zs;
     const float* ef = v.eps_z2f.at(m) + ((long long)l * v.Ncap + i) * v.Z;
     const float* dzd = p >= 0 ? v.dZdec.at(m) + (long long)(LN + LNp + l * Np + p) * v.Z : nullptr;
     const bool act = q2 && v.klz2_row.at(m)[r] > v.dyn->s.kl_min;
@@ -682,12 +687,12 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) T_back_kernel(DevView v) {
     for (int k = 0; k < MAXJ; ++k) {
       const int f = lane + 32 * k;
       if (f < v.Z) {
-        const float pmu = pt[f], plv = pt[v.Z + f];
+        const float pmu = pt[f], plv = pt[v.Zs + f];
         float g = (dzd ? dzd[f] : 0.f) + (dz2f_c ? dz2f_c[f] : 0.f);
         float dpmu = g;
         float dplv = g * 0.5f * expf(0.5f * plv) * ef[f];
         if (act) {
-          const float mu2 = q2[f], lv2 = q2[v.Z + f];
+          const float mu2 = q2[f], lv2 = q2[v.Zs + f];
           const float d = mu2 - pmu, ie = expf(-plv), ev = expf(lv2);
           dpmu += -ckl * d * ie;
           dplv += ckl * 0.5f * (1.f - (d * d + ev) * ie);
@@ -696,19 +701,19 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) T_back_kernel(DevView v) {
         }
         dz1[f] = (v.has_clf ? dz1[f] : 0.f) + dpmu;  // residual path mu = z1 + ...
         st_c8(dy, v.dYT.rcap, r, f, dpmu);
-        st_c8(dy, v.dYT.rcap, r, v.Z + f, dplv);
+        st_c8(dy, v.dYT.rcap, r, v.Zs + f, dplv);
       }
     }
-    for (int f = 2 * v.Z + lane; f < v.dYT.fcap; f += 32) st_c8(dy, v.dYT.rcap, r, f, 0.f);
+    zero_c8_gaps(v.dYT, dy, r, v.Z, v.Zs, lane);
   }
   if (p >= 0) {
-    float* dq2 = v.dQ2.at(m) + (long long)p * 2 * v.Z;
+    float* dq2 = v.dQ2.at(m) + (long long)p * 2 * v.Zs;
 #pragma unroll
     for (int k = 0; k < MAXJ; ++k) {
       const int f = lane + 32 * k;
       if (f < v.Z) {
         dq2[f] = a_mu[k];
-        dq2[v.Z + f] = a_lv[k];
+        dq2[v.Zs + f] = a_lv[k];
       }
     }
   }
@@ -732,7 +737,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) q_back_kernel(DevView v) {
         if (R0 + jj < pad128(R0)) zero_c8_row(v.dY2, m, R0 + jj, lane);
     return;
   }
-  const float* q = v.Q.at(m) + (long long)i * 2 * v.Z;
+  const float* q = v.Q.at(m) + (long long)i * 2 * v.Zs;
   const int p = v.pair_of.at(m)[i];
   const int eb = v.has_fprop ? v.ebase.at(m)[i] : 0;
   const int ecnt = v.has_fprop ? (v.lab.at(m)[i] ? 1 : v.Y) : 0;
@@ -740,7 +745,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) q_back_kernel(DevView v) {
   bf16* dy = v.dY2.at(m);
   const float cN = v.coefs.at(m)[COEF_INV_N];
   for (int f = lane; f < v.Z; f += 32) {
-    const float mu = q[f], lv = q[v.Z + f];
+    const float mu = q[f], lv = q[v.Zs + f];
     const float hs = 0.5f * expf(0.5f * lv);
     float amu = 0.f, alv = 0.f;
     for (int l = 0; l < v.L; ++l) {
@@ -751,8 +756,8 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) q_back_kernel(DevView v) {
       for (int jj = 0; jj < ecnt; ++jj) {
         const long long e = (long long)l * Fl + eb + jj;
         g += v.dZ1e.at(m)[e * v.Z + f];
-        amu += v.dQ1e.at(m)[e * 2 * v.Z + f];
-        alv += v.dQ1e.at(m)[e * 2 * v.Z + v.Z + f];
+        amu += v.dQ1e.at(m)[e * 2 * v.Zs + f];
+        alv += v.dQ1e.at(m)[e * 2 * v.Zs + v.Zs + f];
       }
       amu += g;
       alv += g * hs * v.eps_z1.at(m)[((long long)l * v.Ncap + i) * v.Z + f];
@@ -767,23 +772,21 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) q_back_kernel(DevView v) {
       alv += cN * 0.5f * (expf(lv) - 1.f);
     }
     st_c8(dy, v.dY2.rcap, i, f, amu);
-    st_c8(dy, v.dY2.rcap, i, v.Z + f, alv);
+    st_c8(dy, v.dY2.rcap, i, v.Zs + f, alv);
     if (p >= 0) {
-      const float* q2 = v.Q.at(m) + (long long)(N + p) * 2 * v.Z;
-      float bmu = v.has_T ? v.dQ2.at(m)[(long long)p * 2 * v.Z + f] : 0.f;
-      float blv = v.has_T ? v.dQ2.at(m)[(long long)p * 2 * v.Z + v.Z + f] : 0.f;
+      const float* q2 = v.Q.at(m) + (long long)(N + p) * 2 * v.Zs;
+      float bmu = v.has_T ? v.dQ2.at(m)[(long long)p * 2 * v.Zs + f] : 0.f;
+      float blv = v.has_T ? v.dQ2.at(m)[(long long)p * 2 * v.Zs + v.Zs + f] : 0.f;
       if (v.kind == KIND_PVAE && v.klq_row.at(m)[N + p] > v.dyn->s.kl_min) {
         bmu += cN * q2[f];
-        blv += cN * 0.5f * (expf(q2[v.Z + f]) - 1.f);
+        blv += cN * 0.5f * (expf(q2[v.Zs + f]) - 1.f);
       }
       st_c8(dy, v.dY2.rcap, N + p, f, bmu);
-      st_c8(dy, v.dY2.rcap, N + p, v.Z + f, blv);
+      st_c8(dy, v.dY2.rcap, N + p, v.Zs + f, blv);
     }
   }
-  for (int f = 2 * v.Z + lane; f < v.dY2.fcap; f += 32) {
-    st_c8(dy, v.dY2.rcap, i, f, 0.f);
-    if (p >= 0) st_c8(dy, v.dY2.rcap, N + p, f, 0.f);
-  }
+  zero_c8_gaps(v.dY2, dy, i, v.Z, v.Zs, lane);
+  if (p >= 0) zero_c8_gaps(v.dY2, dy, N + p, v.Z, v.Zs, lane);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -833,7 +836,7 @@ __global__ void __launch_bounds__(256) clf_grad_reduce_kernel(DevView v) {
   for (int sp = lane; sp < v.clf_splits; sp += 32) s += v.clf_part.at(m)[((long long)sp * v.Y + j) * width + t];
   s = warp_sum(s);
   if (lane != 0) return;
-  const int idx = (t < v.clf_in) ? v.clf_w_off + j * v.clf_in + t : v.clf_b_off + j;
+  const int idx = (t < v.clf_in) ? v.clf_w_off + j * v.clf_ld + t : v.clf_b_off + j;
   if (!v.dyn->s.fused_adam) {
     v.grads.at(m)[idx] = s;
   } else {
@@ -902,7 +905,7 @@ __global__ void __launch_bounds__(ROW_THREADS) infer_z1_kernel(DevView v, InferV
         if (rows_dec + jj < pad128(rows_dec)) zero_c8_row(v.Zdec, m, rows_dec + jj, lane);
     return;
   }
-  const float* q = v.Q.at(m) + (long long)r * 2 * v.Z;
+  const float* q = v.Q.at(m) + (long long)r * 2 * v.Zs;
   bf16* zdec = v.Zdec.at(m);
   for (int f = lane; f < v.Zc; f += 32) {
     float z = 0.f;
@@ -910,7 +913,7 @@ __global__ void __launch_bounds__(ROW_THREADS) infer_z1_kernel(DevView v, InferV
       z = q[f];
       v.Z1f.at(m)[(long long)r * v.Z + f] = z;
       if (o.z1_mu) o.z1_mu[((long long)m * N + r) * v.Z + f] = z;
-      if (o.z1_lv) o.z1_lv[((long long)m * N + r) * v.Z + f] = q[v.Z + f];
+      if (o.z1_lv) o.z1_lv[((long long)m * N + r) * v.Z + f] = q[v.Zs + f];
     }
     st_c8(zdec, v.Zdec.rcap, r, f, z);
   }
@@ -928,7 +931,7 @@ __global__ void __launch_bounds__(ROW_THREADS) infer_z2_kernel(DevView v, InferV
   const int r = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int N = v.N;
   if (r >= N) return;
-  const float* pt = v.PT.at(m) + (long long)r * 2 * v.Z;
+  const float* pt = v.PT.at(m) + (long long)r * 2 * v.Zs;
   const float* z1 = v.Z1f.at(m) + (long long)r * v.Z;
   bf16* zdec = v.Zdec.at(m);
   for (int f = lane; f < v.Zc; f += 32) {
@@ -937,7 +940,7 @@ __global__ void __launch_bounds__(ROW_THREADS) infer_z2_kernel(DevView v, InferV
       z = z1[f] + pt[f];
       v.Z2Ff.at(m)[(long long)r * v.Z + f] = z;
       if (o.z2_mu) o.z2_mu[((long long)m * N + r) * v.Z + f] = z;
-      if (o.z2_lv) o.z2_lv[((long long)m * N + r) * v.Z + f] = pt[v.Z + f];
+      if (o.z2_lv) o.z2_lv[((long long)m * N + r) * v.Z + f] = pt[v.Zs + f];
     }
     st_c8(zdec, v.Zdec.rcap, N + r, f, z);
   }

@@ -46,7 +46,9 @@ class _B200Model(nn.Module):
         for arg, val in values.items():
             setattr(self, arg, val)
         # fixed internals of the reference constructors (DrVAE.py:79-97)
-        self.wn = False
+        # the reference hard-codes wn = False before _build_blocks (DrVAE.py:79); layers.WeightNormLinear is reachable
+        # there only by editing that line.  Here: a class attribute, e.g. `class DrVAEwn(DrVAE): WN = True`
+        self.wn = bool(getattr(type(self), 'WN', False))
         self.bn = False
         self.prior_mu = 0.
         self.prior_sg = 1.
@@ -107,7 +109,7 @@ class _B200Model(nn.Module):
         self.plan = Plan(self.kind, L=self.L, max_batch=max(int(self.batch_size), 1), n_models=1,
                          weight_norm=self.wn, **arch)
         self._max_batch = self.plan.Ncap
-        sd = init_state_dict(self.kind, seed=self.random_seed, **arch)
+        sd = init_state_dict(self.kind, seed=self.random_seed, weight_norm=self.wn, **arch)
         self.plan.load_state_dict(sd)
         for name, view in self.plan.tensor_views(self.plan.params, 0).items():
             parts = name.split('.')
@@ -171,7 +173,8 @@ class _B200Model(nn.Module):
         self.plan.sync_shadows()
 
     def save_to_file(self, filename):
-        torch.save(OrderedDict((k, v.detach().cpu()) for k, v in self.state_dict().items()), filename)
+        # parameters alias the kernels' flat vector (16-byte aligned rows): save compact copies, reference shapes
+        torch.save(OrderedDict((k, v.detach().contiguous().cpu()) for k, v in self.state_dict().items()), filename)
 
     def load_params_from_file(self, filename):
         self.load_state_dict(torch.load(filename))
@@ -184,6 +187,12 @@ class _B200Model(nn.Module):
         return 1.
 
     def _hparams(self, training):
+        # the reference honours these attributes inside run_on_batch / loss_function (DGMMixin.py:100-104,
+        # DrVAE.py:549-557); no shipped driver sets them and the kernels do not implement them: refuse rather than
+        # train differently in silence
+        for flag in ('anneal_learning_rate', 'anneal_kl', 'anneal_yloss'):
+            if getattr(self, flag, False):
+                raise ValueError("%s: %s=True is not supported by the B200 hot path" % (type(self).__name__, flag))
         prior = None
         if self.kind != 'pvae' and not isinstance(self.prior_y, str) and self.prior_y is not None:
             prior = [float(p) for p in self.prior_y]
@@ -276,7 +285,7 @@ class _B200Model(nn.Module):
 
     # ------------------------------------------------------------------------------------------
     def _infer(self, x1):
-        self.eval()
+        self.eval()  # as the reference's forward() does (DrVAE.py:262, PVAE.py:214, VFAE.py:186)
         self._ensure_capacity(x1.shape[0])
         r = self.plan.infer(x1)
         return {k: v[0] for k, v in r.items()}

@@ -70,6 +70,8 @@ class Plan:
             r, c, off = ctypes.c_int(), ctypes.c_int(), ctypes.c_longlong()
             _lib.check(self.lib.drvae_plan_tensor_info(h, i, nm, 256, ctypes.byref(r), ctypes.byref(c), ctypes.byref(off)))
             self.tensors.append((nm.value.decode(), r.value, c.value, off.value))
+        # floats between matrix rows (cols rounded up to 4: 16-byte aligned rows, see include/drvae_b200.h)
+        self.tensor_ld = [int(self.lib.drvae_plan_tensor_ld(h, i)) for i in range(len(self.tensors))]
         el = EpsLayout()
         _lib.check(self.lib.drvae_plan_eps_layout(h, ctypes.byref(el)))
         self.eps_layout = el
@@ -96,16 +98,18 @@ class Plan:
 
     # ---- parameters -----------------------------------------------------------------------
     def tensor_views(self, buf, model=0):
-        """name -> zero-copy view (reference shapes) into buf[model]."""
+        """name -> zero-copy view (reference shapes) into buf[model].  Matrix rows are
+        16-byte aligned in the flat vector, so a matrix whose width is not a multiple of 4 is a strided view."""
         out = OrderedDict()
-        for name, r, c, off in self.tensors:
-            n = r * (c if c > 0 else 1)
-            v = buf[model, off:off + n]
-            out[name] = v.view(r, c) if c > 0 else v
+        for (name, r, c, off), ld in zip(self.tensors, self.tensor_ld):
+            if c > 0:
+                out[name] = buf[model, off:off + r * ld].view(r, ld)[:, :c]
+            else:
+                out[name] = buf[model, off:off + r]
         return out
 
     def state_dict(self, model=0):
-        return OrderedDict((k, v.detach().clone()) for k, v in self.tensor_views(self.params, model).items())
+        return OrderedDict((k, v.detach().clone(memory_format=torch.contiguous_format)) for k, v in self.tensor_views(self.params, model).items())
 
     def load_state_dict(self, sd, model=0, strict=True):
         views = self.tensor_views(self.params, model)
@@ -276,6 +280,9 @@ class Plan:
 
     def set_gemm_impl(self, impl):
         _lib.check(self.lib.drvae_set_gemm_impl(self.h, {"tc": 0, "simt": 1}[impl]))
+
+    def debug_side_delay(self, cycles):
+        _lib.check(self.lib.drvae_debug_side_delay(self.h, int(cycles)), "debug_side_delay")
 
     def launch_count(self):
         return int(self.lib.drvae_plan_launch_count(self.h))

@@ -120,12 +120,16 @@ const char* drvae_last_error(void);
 int drvae_plan_create(const drvae_arch_t* arch, int n_models, drvae_plan_t** out);
 int drvae_plan_destroy(drvae_plan_t* plan);
 
-/* Parameter layout: tensors in the reference's state_dict order, each
- * row-major at `offset` floats inside the flat per-model vector of drvae_plan_param_count(). */
+/* Parameter layout: tensors in the reference's state_dict order, each row-major at `offset`
+ * floats inside the flat per-model vector of drvae_plan_param_count().  Every tensor and every matrix ROW starts on
+ * a 16-byte boundary: element (r, c) of tensor i lives at offset + r * drvae_plan_tensor_ld(i) + c, with
+ * ld = cols rounded up to a multiple of 4 (1 for vectors).  The padding floats are zero parameters with zero
+ * gradients and stay zero; Adam moments and gradients use the same layout. */
 long long drvae_plan_param_count(const drvae_plan_t* plan);
 int drvae_plan_num_tensors(const drvae_plan_t* plan);
 int drvae_plan_tensor_info(const drvae_plan_t* plan, int index, char* name, int name_cap, int* rows, int* cols,
                            long long* offset);
+int drvae_plan_tensor_ld(const drvae_plan_t* plan, int index);   /* floats between rows; -1: bad index */
 int drvae_plan_eps_layout(const drvae_plan_t* plan, drvae_eps_layout_t* out);
 long long drvae_plan_workspace_bytes(const drvae_plan_t* plan);
 
@@ -176,6 +180,10 @@ int drvae_profile_end(drvae_plan_t* plan, char* out, int cap);
 /* Barrier-wait cycle counters of the GEMM kernel roles, [3 modes][8 epilogues][8 counters]; only in libraries built
  * with -DGEMM_PROFILE_WAITS (tools/wait_profile.py), otherwise an error status. */
 int drvae_debug_wait_stats(unsigned long long* out, int reset);
+/* Test knob: hold the plan's side stream for `cycles` SM clocks in front of the kernel whose output the main stream
+ * consumes next (pz1_post -> clf_back), so that a missing cross-stream dependency produces a wrong result instead of
+ * passing by timing luck (tests/test_step_gpu.py::test_side_stream_delay_does_not_change_results).  0 = off. */
+int drvae_debug_side_delay(drvae_plan_t* plan, long long cycles);
 int drvae_debug_buffer(drvae_plan_t* plan, const char* name, void** ptr, long long* model_stride_bytes,
                        long long* bytes, int* rcap, int* fcap);
 int drvae_debug_gemm(int impl, int mode, const void* A, int a_rcap, int a_nchunks, long long a_ms,

@@ -652,3 +652,26 @@ def test_data_parallel_step_graph_replay_equals_eager():
     assert torch.equal(out[False][0], out[True][0])
     assert torch.equal(out[False][1], out[True][1])
     assert not torch.equal(out[True][0][3], out[True][0][4])  # the pushed scalars really change between replays
+
+
+@pytest.mark.parametrize("kind", ("drvae", "vfae"))
+def test_side_stream_delay_does_not_change_results(kind):
+    """The label-dependent branch runs on the plan's side stream.  clf_back (main stream) consumes the per-class KL
+    terms pz1_post (side stream) writes; holding the side stream for ~1.5 ms in front of pz1_post must not change a
+    single bit of the result — a missing cross-stream dependency would (round-1 ADVICE, plan.cu clf_bwd)."""
+    arch, N = ARCH["tiny"], 40
+    sd = init_state_dict(kind, seed=SEED_MODEL, **arch)
+    batch = {k: v.cuda() for k, v in batch_fields(kind, orc.synthetic_batch(N, arch["dim_x"], seed=4)).items()}
+    res = {}
+    for delay in (0, 3_000_000):
+        plan = Plan(kind, L=L, max_batch=N, n_models=2, **arch)
+        plan.debug_side_delay(delay)
+        for m in range(2):
+            plan.load_state_dict(sd, model=m)
+        big = {k: torch.stack([v, v]).contiguous() for k, v in batch.items()}
+        out = []
+        for it in range(4):  # plain launches, then (from the third call) the captured graph
+            out.append(plan.train_step(big, plan.hparams(step=it, beta_pert=anneal_coef(it, 1, 0)), seed=7).cpu().clone())
+        res[delay] = (torch.stack(out), plan.params.cpu().clone())
+    assert torch.equal(res[0][0], res[3_000_000][0])
+    assert torch.equal(res[0][1], res[3_000_000][1])

@@ -94,6 +94,7 @@ struct GemmProblem {
   int M, N, K;      // static upper bounds of D rows / D cols / contraction length
   const int* dyn;   // per-model dynamic extent: rows of D (NT, DX) or contraction rows (DW); may be null
   int dyn_stride;   // ints between models in `dyn`
+  const int* skip;  // optional per-model count (same stride): when it is zero the model's tiles do nothing at all
   int BN;           // N tile (multiple of 16, <= 256)
   int tiles_n;
   int tiles_m;
@@ -517,6 +518,7 @@ __device__ __forceinline__ TileInfo gemm_tile_info(const GemmProblem& p, int til
   t.kb_begin = min(nkb, ks * per);
   t.kb_end = min(nkb, t.kb_begin + per);
   t.active = t.m0 < t.Mrows && (t.kb_end > t.kb_begin || ks == 0);
+  if (p.skip && p.skip[(long long)t.model * p.dyn_stride] == 0) t.active = false;
   return t;
 }
 

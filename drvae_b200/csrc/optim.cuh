@@ -49,6 +49,11 @@ struct AdamArgs {
   int P;  // parameters per model
   const AdamHyper* h;  // device memory (StepDyn)
   int update;  // 0: only refresh the derived copies from the current parameters
+  // parameters [skip_lo, skip_hi) are left untouched when the batch (global counts if given) has no pair rows
+  int skip_lo, skip_hi;
+  const StepDyn* dyn;
+  const int* counts;
+  int counts_stride;
 };
 
 // grid (ceil(P / 1024), n_models), block 256, 4 elements per thread
@@ -63,13 +68,18 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamArgs a) {
   const int base = blockIdx.x * 1024 + threadIdx.x;
   AdamHyper hyper{};
   if (a.update) hyper = *a.h;
+  bool skip_range = false;
+  if (a.update && a.skip_hi > a.skip_lo) {
+    const int np = a.dyn->s.gN > 0 ? a.dyn->s.gNp : a.counts[(long long)mdl * a.counts_stride + CNT_NP];
+    skip_range = np == 0;
+  }
   int si = -1;
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     const int idx = base + u * 256;
     if (idx >= a.P) break;
     float pv = p[idx];
-    if (a.update) {
+    if (a.update && !(skip_range && idx >= a.skip_lo && idx < a.skip_hi)) {
       float m1 = mm[idx], v1 = vv[idx];
       adam_update(g[idx], pv, m1, v1, hyper);
       mm[idx] = m1;

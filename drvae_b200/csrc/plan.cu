@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "errors.h"
+#include "dwadam.cuh"
 #include "gemm.cuh"
 #include "optim.cuh"
 #include "plan.h"
@@ -63,6 +64,7 @@ struct drvae_plan {
   WnRow* d_wn_rows = nullptr;
   long long clf_eff_off = -1;  // derived offset of the classifier's effective weights (weight norm only)
   int P = 0;
+  long long T_range[2] = {0, 0};  // (offset, count) of the decoder_z2Fz1 parameters
   int clf_w_off = -1, clf_b_off = -1;
   // shadows
   long long shadow_elems = 0;   // bf16 per model
@@ -111,6 +113,13 @@ struct drvae_plan {
   // gradient buckets (data-parallel overlap): contiguous parameter ranges in backward completion order
   std::vector<std::pair<long long, long long>> buckets;  // (offset, count)
   std::vector<cudaEvent_t> bucket_ev;
+  // grouped weight-gradient + Adam launch (dwadam.cuh): layer table and tensor maps in device memory, rebuilt by bind
+  std::vector<DwaLayer> dwa_layers;
+  DwaLayer* d_dwa_layers = nullptr;
+  DwaMaps* d_dwa_maps = nullptr;
+  int dwa_tiles = 0;
+  bool dwa_ok = false;       // every layer fits the kernel's layout conditions and the state is bound
+  bool dwa_enabled = true;   // measurement knob (DRVAE_B200_DWADAM=0: per-layer fused kernels of round 1)
   // optional per-launch event timing (bench.py / profiles)
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;
@@ -395,6 +404,7 @@ extern "C" int drvae_plan_create(const drvae_arch_t* a, int n_models, drvae_plan
     Tiling t = tile_cap(2 * Zs);
     pl->Tsh = make_shadow(pl, 2, wt, bt, Z, Z, 0, Zs, 2 * Zs, t.BN, t.tiles, bc);
     r_T[0] = p0, r_T[1] = pl->P - p0, p0 = pl->P;
+    pl->T_range[0] = r_T[0], pl->T_range[1] = r_T[1];
   }
   if (pl->has_clf) {
     int w = add_tensor(pl, "encoder_y.decoder_p.linear_p.weight", Y, pl->clf_in);
@@ -529,6 +539,7 @@ extern "C" int drvae_plan_create(const drvae_arch_t* a, int n_models, drvae_plan
   cudaMemset(pl->d_dyn, 0, sizeof(StepDyn));
   if (const char* knob = getenv("DRVAE_B200_ADAM_VEC")) pl->adam_vec_max = atoi(knob);  // measurement knob
   if (const char* knob = getenv("DRVAE_B200_SCHED")) pl->sched = atoi(knob);
+  if (const char* knob = getenv("DRVAE_B200_DWADAM")) pl->dwa_enabled = atoi(knob) != 0;
   if (const char* knob = getenv("DRVAE_B200_PDL")) pdl_mask() = atoi(knob);  // measurement knob: programmatic dependent launch
   cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking);
   for (cudaEvent_t* ev : {&pl->ev_fork, &pl->ev_qy, &pl->ev_side_fwd, &pl->ev_side_bwd, &pl->ev_begin, &pl->ev_eps, &pl->ev_clf, &pl->ev_kfp})
@@ -638,6 +649,8 @@ extern "C" int drvae_plan_destroy(drvae_plan_t* pl) {
   if (pl->d_segs) cudaFree(pl->d_segs);
   if (pl->d_tabs) cudaFree(pl->d_tabs);
   if (pl->d_wn_rows) cudaFree(pl->d_wn_rows);
+  if (pl->d_dwa_layers) cudaFree(pl->d_dwa_layers);
+  if (pl->d_dwa_maps) cudaFree(pl->d_dwa_maps);
   for (auto& ev : pl->bucket_ev) cudaEventDestroy(ev);
   for (cudaEvent_t ev : {pl->ev_fork, pl->ev_qy, pl->ev_side_fwd, pl->ev_side_bwd, pl->ev_begin, pl->ev_eps, pl->ev_clf, pl->ev_kfp})
     if (ev) cudaEventDestroy(ev);
@@ -698,6 +711,97 @@ extern "C" int drvae_debug_side_delay(drvae_plan_t* pl, long long cycles) {
   return 0;
 }
 
+namespace {
+
+// Layer table + tensor maps of the grouped dW+Adam launch.  Leaves pl->dwa_ok false (-> per-layer kernels) when the
+// optimizer state is not bound, with weight norm (the update acts on (v, g)), or when a layer does not meet the
+// kernel's layout conditions (class columns must share the 128-feature tile of the ones column).
+int build_dwa(drvae_plan* pl) {
+  pl->dwa_ok = false;
+  pl->dwa_layers.clear();
+  if (!pl->params || !pl->adam_m || !pl->adam_v || pl->wn) return 0;
+  struct Ref {
+    const Shadow* W;
+    const C8Buf* dY;
+    const C8Buf* X;
+    int cnt, skip;
+  };
+  std::vector<Ref> refs;
+  const DevView& v = pl->view;
+  auto add_block = [&](MlpBlock& b, const C8Buf* dYh, const C8Buf* in, int cnt) {
+    const int n = (int)b.hidden.size();
+    refs.push_back({&b.head, dYh, &b.H[n - 1], cnt, -1});
+    for (int i = 0; i < n; ++i) refs.push_back({&b.hidden[i], &b.dPre[i], i == 0 ? in : &b.H[i - 1], cnt, -1});
+  };
+  add_block(pl->dec, &pl->dY5, &v.Zdec, CNT_RD);
+  add_block(pl->enc, &v.dY2, &v.Ain, CNT_R0);
+  if (pl->has_fprop) {
+    add_block(pl->z3b, &v.dY7, &v.Z1e, CNT_F);
+    add_block(pl->dz1b, &v.dY9, &v.Z3b, CNT_F);
+  }
+  if (pl->has_T) refs.push_back({&pl->Tsh, &v.dYT, &v.Zdec, CNT_LN, pl->arch.kind == DRVAE_KIND_PVAE ? CNT_NP : -1});
+  if ((int)refs.size() > DWA_MAX_LAYERS) return 0;
+  // heaviest layers first: the strided persistent grid then ends on the small ones
+  std::stable_sort(refs.begin(), refs.end(), [](const Ref& a, const Ref& b) {
+    return (long long)a.W->kc * a.W->rcap > (long long)b.W->kc * b.W->rcap;
+  });
+  std::vector<DwaMaps> maps(refs.size());
+  int tile = 0;
+  for (size_t i = 0; i < refs.size(); ++i) {
+    const Shadow& W = *refs[i].W;
+    const int cc = W.kaug - W.kin - 1;
+    if (cc > 0 && (W.kin % GEMM_BM) + 1 + cc > GEMM_BM) return 0;
+    if (W.BN % DWA_R || W.BN > 256 || W.rcap != W.BN * W.tiles_n || W.ntens > 2 || (W.ld & 3)) return 0;
+    if (W.ntens == 2 && (W.ilv_block % DWA_R)) return 0;
+    DwaLayer y{};
+    y.tile_begin = tile;
+    y.tiles_m = cdiv(W.kaug, GEMM_BM);
+    y.tiles_n = W.tiles_n;
+    y.BN = W.BN;
+    tile += y.tiles_m * y.tiles_n * pl->E;
+    y.tile_end = tile;
+    y.kin = W.kin;
+    y.kaug = W.kaug;
+    y.cnt_which = refs[i].cnt;
+    y.a_row0 = 0;
+    y.ntens = W.ntens;
+    y.rows_each = W.rows_each[0];
+    y.ilv_block = W.ilv_block;
+    y.ilv_stride = W.ilv_stride;
+    y.rcap = W.rcap;
+    y.skip_which = refs[i].skip;
+    y.tab_off = W.tab_off;
+    y.drv_bias_off = W.bias_off;
+    y.drv_clsb_off = W.clsb_off;
+    y.drv_clsb_ld = W.rcap;
+    pl->dwa_layers.push_back(y);
+    DwaMaps& m = maps[i];
+    const C8Buf& X = *refs[i].X;
+    const C8Buf& dY = *refs[i].dY;
+    cudaError_t err = gemm_c8_map(&m.A, GemmOperand{X.p, X.ms, X.rcap, X.fcap >> 3, 0}, pl->E, GEMM_BK, GEMM_BM / 8);
+    if (err == cudaSuccess) err = gemm_c8_map(&m.B, GemmOperand{dY.p, dY.ms, dY.rcap, dY.fcap >> 3, 0}, pl->E, GEMM_BK, W.BN / 8);
+    if (err == cudaSuccess)
+      err = gemm_c8_map(&m.S, GemmOperand{pl->shadow.p + W.off, pl->shadow.ms, W.rcap, W.kc >> 3, 0}, pl->E, DWA_R, GEMM_BM / 8);
+    for (int w = 0; w < 2 && err == cudaSuccess; ++w) {
+      const int ww = w < W.ntens ? w : 0;
+      err = dwa_state_map(&m.P[w], pl->params + W.w_off[ww], W.ld, W.rows_each[ww], pl->P, pl->E);
+      if (err == cudaSuccess) err = dwa_state_map(&m.M[w], pl->adam_m + W.w_off[ww], W.ld, W.rows_each[ww], pl->P, pl->E);
+      if (err == cudaSuccess) err = dwa_state_map(&m.V[w], pl->adam_v + W.w_off[ww], W.ld, W.rows_each[ww], pl->P, pl->E);
+    }
+    if (err != cudaSuccess) return set_cuda_error("drvae_plan_bind: tensor maps of the grouped weight-gradient launch", err);
+  }
+  if (!pl->d_dwa_layers) cudaMalloc(&pl->d_dwa_layers, sizeof(DwaLayer) * DWA_MAX_LAYERS);
+  if (!pl->d_dwa_maps) cudaMalloc(&pl->d_dwa_maps, sizeof(DwaMaps) * DWA_MAX_LAYERS);
+  cudaError_t err = cudaMemcpy(pl->d_dwa_layers, pl->dwa_layers.data(), sizeof(DwaLayer) * pl->dwa_layers.size(), cudaMemcpyHostToDevice);
+  if (err == cudaSuccess) err = cudaMemcpy(pl->d_dwa_maps, maps.data(), sizeof(DwaMaps) * maps.size(), cudaMemcpyHostToDevice);
+  if (err != cudaSuccess) return set_cuda_error("drvae_plan_bind: uploading the grouped weight-gradient tables", err);
+  pl->dwa_tiles = tile;
+  pl->dwa_ok = true;
+  return 0;
+}
+
+}  // namespace
+
 extern "C" int drvae_plan_bind(drvae_plan_t* pl, float* params, float* adam_m, float* adam_v, float* grads) {
   if (!pl || !params) return set_error("drvae_plan_bind: params must not be null");
   pl->params = params;
@@ -706,7 +810,7 @@ extern "C" int drvae_plan_bind(drvae_plan_t* pl, float* params, float* adam_m, f
   pl->grads = grads;
   pl->shadows_valid = false;
   drop_graphs(pl);  // captured sequences hold the old pointers
-  return 0;
+  return build_dwa(pl);
 }
 
 extern "C" int drvae_debug_buffer(drvae_plan_t* pl, const char* name, void** ptr, long long* ms_bytes, long long* bytes,
@@ -754,6 +858,7 @@ struct Exec {
   std::string sub = "head";  // layer within the current block: h0, h1, ..., head
   bool fused = false;        // Adam inside the gradient epilogues (drvae_train_step)
   bool splitk = false;       // split-K weight gradients (large minibatches, unfused path)
+  bool defer_dw = false;     // weight gradients + Adam of every layer in ONE launch at the end of backward (dwadam.cuh)
   bool ok() const { return err == cudaSuccess; }
   // event bracket around one launch when profiling is on
   void pre(const std::string& op) { prof_pre(pl, st, std::string(phase) + ":" + op); }
@@ -821,8 +926,10 @@ struct Exec {
   }
   // grad W^T[kaug, nout] = Xin[rows, kaug]^T . dY[rows, nout]: weight, bias (ones column) and class-column
   // gradients of one layer; with `fused` the epilogue applies Adam instead of storing the gradient.
-  void gemm_dw(const C8Buf& dY, const C8Buf& Xin, int x_row0, const Shadow& W, int dyn_which, int row_bound) {
+  void gemm_dw(const C8Buf& dY, const C8Buf& Xin, int x_row0, const Shadow& W, int dyn_which, int row_bound, int skip_which = -1) {
+    if (defer_dw) return;
     GemmProblem p{};
+    if (skip_which >= 0 && fused) p.skip = cnt(skip_which);  // (unfused: the zero gradient is stored, adam_kernel skips)
     p.A = op_c8(Xin, x_row0);
     p.B = op_c8(dY, 0);
     p.mode = GEMM_DW;
@@ -1068,6 +1175,13 @@ int run_adam(drvae_plan* pl, const drvae_hparams_t* hp, int update, cudaStream_t
   a.P = pl->P;
   a.update = update;
   a.h = &pl->d_dyn->s.adam;  // the caller has pushed this step's scalars
+  // PVAE: p(z2|z1) takes part in the loss only through pair rows (PVAE.py:313-330); without pairs the reference's
+  // gradient is None and torch.optim.Adam leaves the tensors (and their moments) untouched
+  a.skip_lo = a.skip_hi = 0;
+  if (pl->arch.kind == DRVAE_KIND_PVAE && pl->has_T) a.skip_lo = (int)pl->T_range[0], a.skip_hi = (int)(pl->T_range[0] + pl->T_range[1]);
+  a.dyn = pl->d_dyn;
+  a.counts = pl->view.counts.p;
+  a.counts_stride = (int)pl->view.counts.ms;
   dim3 grid(cdiv(pl->P, 1024), pl->E);
   prof_pre(pl, st, update ? "opt:adam" : "opt:shadow_sync");
   adam_kernel<<<grid, 256, 0, st>>>(a);
@@ -1127,6 +1241,7 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
   v.clf_splits = std::max(CLF_SPLITS, std::min(CLF_SPLITS_MAX, cdiv(LNb, 64)));
   v.loss_slices = std::max(1, std::min(LOSS_SLICES_MAX, cdiv(Rdb, 512)));
   ex.splitk = backward && !fused_adam && Rdb >= 2048;
+  ex.defer_dw = backward && fused_adam && pl->dwa_ok && pl->dwa_enabled;
   if (ex.splitk) {
     cudaError_t e0 = cudaMemsetAsync(pl->grads, 0, sizeof(float) * (size_t)pl->P * E, st);
     if (e0 != cudaSuccess) return set_cuda_error("drvae: zeroing the gradient buffer", e0);
@@ -1331,7 +1446,7 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
       launch_k(T_back_kernel, rows_grid(N + PAD_WARPS), dim3(ROW_THREADS), 0, ex.st, 2, v);
       ex.chk();
       ex.gemm_dx(v.dYT, pl->Tsh, EPI_STORE_F32, ex.epi_f32(v.dZ1T.p, v.dZ1T.ms, pl->Z, pl->Z, nullptr), CNT_LN, LNb);
-      ex.gemm_dw(v.dYT, v.Zdec, 0, pl->Tsh, CNT_LN, LNb);
+      ex.gemm_dw(v.dYT, v.Zdec, 0, pl->Tsh, CNT_LN, LNb, pl->arch.kind == DRVAE_KIND_PVAE ? CNT_NP : -1);
       bucket_done();
     }
     if (overlap) cudaStreamWaitEvent(st, pl->ev_side_bwd, 0);  // join: q_back sums the side branch's gradients into q(z1|x1)
@@ -1341,6 +1456,31 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
     ex.chk();
     ex.block_bwd(pl->enc, v.dY2, v.Ain, 0, pl->X, nullptr, 0, CNT_R0, R0b);
     bucket_done();
+    if (ex.defer_dw && ex.ok()) {
+      DwaParams dp{};
+      dp.n_layers = (int)pl->dwa_layers.size();
+      dp.n_models = E;
+      dp.total_tiles = pl->dwa_tiles;
+      dp.layers = pl->d_dwa_layers;
+      dp.maps = pl->d_dwa_maps;
+      dp.tabs = pl->d_tabs;
+      dp.counts = v.counts.p;
+      dp.counts_stride = (int)v.counts.ms;
+      dp.adam_p = pl->params;
+      dp.adam_m = pl->adam_m;
+      dp.adam_v = pl->adam_v;
+      dp.state_ms = pl->P;
+      dp.drv = pl->derived.p;
+      dp.drv_ms = pl->derived.ms;
+      dp.adam = &pl->d_dyn->s.adam;
+      dp.dbg = pl->dbg;
+      ex.phase = "bwd";
+      ex.pre("dw_adam_all");
+      cudaError_t r = dwadam_launch(dp, ex.st);
+      ex.post();
+      if (r != cudaSuccess) ex.err = r;
+      pl->launches++;
+    }
   }
   if (!ex.ok()) return set_cuda_error("drvae step launch", ex.err);
   return 0;

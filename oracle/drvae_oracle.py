@@ -447,9 +447,6 @@ class OracleModel:
         self.opt.zero_grad()
         losses = loss_function(self.sd, batch, tape, self.cfg, self.iters, train=True, emulate_bf16=emulate_bf16)
         losses["CMPL"].backward()
-        for p in self.sd.values():  # parameters untouched by this batch still get wd + Adam in the
-            if p.grad is None:       # CUDA path; torch.optim.Adam would skip them
-                p.grad = torch.zeros_like(p)
         if grad_hook is not None:
             grad_hook(self.sd)
         self.opt.step()

@@ -675,3 +675,38 @@ def test_side_stream_delay_does_not_change_results(kind):
         res[delay] = (torch.stack(out), plan.params.cpu().clone())
     assert torch.equal(res[0][0], res[3_000_000][0])
     assert torch.equal(res[0][1], res[3_000_000][1])
+
+
+@pytest.mark.parametrize("path", ("fused", "split"))
+def test_pvae_without_pairs_leaves_the_perturbation_block_untouched(path):
+    """PVAE uses p(z2|z1) only for pair rows (PVAE.py:313-330).  On a batch without pairs the reference's gradient of
+    decoder_z2Fz1 is None, so torch.optim.Adam skips those tensors entirely (no weight decay, no moment update);
+    every other tensor takes a normal step.  Both optimizer paths must do the same."""
+    kind, arch, N = "pvae", ARCH["tiny"], 20
+    sd = init_state_dict(kind, seed=SEED_MODEL, **arch)
+    batch = orc.synthetic_batch(N, arch["dim_x"], seed=6)
+    batch["has_x2"].zero_()
+    batch["x2"].zero_()
+    plan = Plan(kind, L=L, max_batch=N, n_models=1, **arch)
+    plan.load_state_dict(sd)
+    om = orc.OracleModel(sd, orc.default_cfg(kind, L=L))
+    for it in range(2):
+        tape = orc.Tape(seed=60 + it)
+        om.step(batch, tape)
+        eps = eps_block_from_tape(plan, tape.log, batch["has_x2"], None, noisy=True)
+        hp = plan.hparams(step=it, beta_pert=anneal_coef(it, 1, 0))
+        if path == "fused":
+            plan.train_step(batch_fields(kind, batch), hp, eps=eps)
+        else:
+            plan.grad_step(batch_fields(kind, batch), hp, eps=eps)
+            plan.adam_step(hp)
+    new, ref = plan.state_dict(), om.state_dict()
+    mv, vv = plan.tensor_views(plan.adam_m, 0), plan.tensor_views(plan.adam_v, 0)
+    for k in new:
+        if k.startswith("decoder_z2Fz1"):
+            assert torch.equal(ref[k], sd[k]), "oracle moved %s" % k
+            assert torch.equal(new[k].cpu(), sd[k]), k
+            assert float(mv[k].abs().max()) == 0 and float(vv[k].abs().max()) == 0, k
+        else:
+            assert not torch.equal(new[k].cpu(), sd[k]), k
+            assert (new[k].cpu() - ref[k]).abs().max() <= 2.2 * 5e-4, k  # two Adam steps of lr 5e-4, signs may differ

@@ -76,6 +76,27 @@ inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_
 }
 
 // ---------------------------------------------------------------------------------------------
+// Kernel trace (drvae_trace_begin / _end): every kernel of the step stamps %globaltimer when its first CTA starts and
+// when its last CTA leaves, into slot `id` of a device buffer.  The host turns the slots into a timeline of the step
+// as it really ran (streams overlapping, launch gaps), which per-launch event brackets cannot show.  Off (null
+// buffer) it costs one predictable branch per CTA.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+struct TraceScope {
+  unsigned long long* slot;
+  __device__ __forceinline__ TraceScope(unsigned long long* buf, int id) : slot(buf ? buf + 2 * (long long)id : nullptr) {
+    if (slot && threadIdx.x == 0) atomicMin(slot, global_ns());
+  }
+  __device__ __forceinline__ ~TraceScope() {
+    if (slot && threadIdx.x == 0) atomicMax(slot + 1, global_ns());
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -101,6 +122,36 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
   return ok != 0;
+}
+// try_wait with a suspend-time hint: the thread may sleep in hardware up to `ns` nanoseconds waiting for the phase,
+// instead of returning to a software polling loop after the (short) default time
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait for long-running producers/consumers of a persistent kernel: hardware-suspended polling (few issued
+// instructions while waiting), trap with a code after ~2 s.
+__device__ __forceinline__ void mbar_wait_sleepy(uint64_t* bar, uint32_t parity, DebugWord* dbg, uint32_t code) {
+  if (mbar_try_wait(bar, parity)) return;
+  for (int spins = 0; !mbar_try_wait_hint(bar, parity, 2000u); ++spins) {
+    if (spins > 1000000) {  // >= 2 s of suspended waiting
+      if (dbg) {
+        dbg->code = code;
+        dbg->info[0] = blockIdx.x;
+        dbg->info[3] = threadIdx.x;
+        dbg->info[4] = parity;
+        __threadfence_system();
+      }
+      __trap();
+    }
+  }
 }
 // Bounded wait: a barrier that never completes (wrong tx byte count, lost commit) becomes a
 // trapped kernel with a code in the debug word instead of a hung GPU.

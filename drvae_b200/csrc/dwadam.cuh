@@ -77,6 +77,9 @@ struct DwaParams {
   long long drv_ms;
   const AdamHyper* adam;
   DebugWord* dbg;
+  unsigned long long* trace;
+  int trace_id;
+  unsigned long long* stats;  // optional [8] cycle counters of the roles' barrier waits (drvae_debug_dwa_stats)
 };
 
 __device__ __forceinline__ void tma_store_3d(const void* map, const void* src, int c0, int c1, int c2) {
@@ -101,6 +104,25 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+enum { DWS_EPI_ACC = 0, DWS_EPI_STATE, DWS_LOADER_EMPTY, DWS_STORER_DONE, DWS_STORER_READ, DWS_PROD_EMPTY, DWS_MMA_FULL, DWS_CTA_TOTAL };
+#define DWS_T0() const long long dws_t0 = p.stats ? clock64() : 0
+#define DWS_ADD(acc) \
+  if (p.stats) acc += clock64() - dws_t0
+
+// issue / complete halves of a 4-column TMEM load (the load is in flight across a barrier wait)
+__device__ __forceinline__ void tmem_ld4_issue(uint32_t taddr, uint32_t (&r)[4]) {
+  __syncwarp();
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld4_wait(bool have, uint32_t (&r)[4], float (&v)[4]) {
+  if (have) asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3])::"memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = have ? __uint_as_float(r[i]) : 0.f;
 }
 
 struct DwaTile {
@@ -144,12 +166,15 @@ __global__ void __launch_bounds__(DWA_THREADS, 1) dwadam_kernel(const DwaParams 
   __shared__ uint32_t tmem_base_s;
   __shared__ DwaLayer L[DWA_MAX_LAYERS];
 
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1 KB alignment by pointer arithmetic on the __shared__ array itself: a round trip through an integer makes the
+  // compiler lose the address space and emit generic LD/ST (seen in the SASS of the first version) instead of LDS/STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* op_ring = smem;
   uint8_t* st_ring = smem + DWA_OPS * DWA_OP_STAGE;
   float* bst = reinterpret_cast<float*>(st_ring + DWA_NST * DWA_ST_STAGE);  // [3][256] b, m, v
   int* bidx = reinterpret_cast<int*>(bst + 3 * 256);                         // [256] flat offset of b[n] or -1
 
+  TraceScope trace_scope(p.trace, p.trace_id);
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -179,6 +204,8 @@ __global__ void __launch_bounds__(DWA_THREADS, 1) dwadam_kernel(const DwaParams 
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   pdl_wait();
+  long long w_a = 0, w_b = 0;  // wait-cycle counters of this thread's role (p.stats)
+  const long long cta_t0 = p.stats ? clock64() : 0;
 
   if (warp == 0) {
     // ===================== operand producer =====================
@@ -191,7 +218,11 @@ __global__ void __launch_bounds__(DWA_THREADS, 1) dwadam_kernel(const DwaParams 
       const uint32_t tx = GEMM_A_STAGE_BYTES + t.BN * GEMM_BK * 2;
       for (int kb = 0; kb < t.nkb; ++kb, ++it) {
         const int s = it % DWA_OPS;
-        mbar_wait(&op_empty[s], ((it / DWA_OPS) & 1) ^ 1, p.dbg, 0xE1000000u | kb);
+        {
+          DWS_T0();
+          mbar_wait_sleepy(&op_empty[s], ((it / DWA_OPS) & 1) ^ 1, p.dbg, 0xE1000000u | kb);
+          DWS_ADD(w_a);
+        }
         if (elect_one()) {
           uint8_t* As = op_ring + (size_t)s * DWA_OP_STAGE;
           mbar_arrive_expect_tx(&op_full[s], tx);
@@ -211,7 +242,11 @@ __global__ void __launch_bounds__(DWA_THREADS, 1) dwadam_kernel(const DwaParams 
       const DwaMaps* mp = p.maps + t.layer;
       for (int sub = 0; sub < t.BN / DWA_R; ++sub, ++it) {
         const int s = it % DWA_NST;
-        mbar_wait(&st_empty[s], ((it / DWA_NST) & 1) ^ 1, p.dbg, 0xE2000000u | sub);
+        {
+          DWS_T0();
+          mbar_wait_sleepy(&st_empty[s], ((it / DWA_NST) & 1) ^ 1, p.dbg, 0xE2000000u | sub);
+          DWS_ADD(w_a);
+        }
         int which, n;
         const bool has = dwa_stage_rows(y, t.n0 + sub * DWA_R, which, n);
         if (elect_one()) {
@@ -238,7 +273,11 @@ __global__ void __launch_bounds__(DWA_THREADS, 1) dwadam_kernel(const DwaParams 
       const DwaMaps* mp = p.maps + t.layer;
       for (int sub = 0; sub < t.BN / DWA_R; ++sub, ++it) {
         const int s = it % DWA_NST;
-        mbar_wait(&st_done[s], (it / DWA_NST) & 1, p.dbg, 0xE3000000u | sub);
+        {
+          DWS_T0();
+          mbar_wait_sleepy(&st_done[s], (it / DWA_NST) & 1, p.dbg, 0xE3000000u | sub);
+          DWS_ADD(w_a);
+        }
         int which, n;
         const int s0 = t.n0 + sub * DWA_R;
         const bool has = dwa_stage_rows(y, s0, which, n);
@@ -250,7 +289,9 @@ __global__ void __launch_bounds__(DWA_THREADS, 1) dwadam_kernel(const DwaParams 
             tma_store_3d(&mp->V[which], st + 2 * DWA_ARR, t.m0, n, t.model);
             tma_store_3d(&mp->S, st + 3 * DWA_ARR, s0 * 2, t.m0 >> 3, t.model);
             tma_commit_group();
+            DWS_T0();
             tma_wait_group_read0();  // the TMA unit has read this stage's shared memory
+            DWS_ADD(w_b);
           }
           mbar_arrive(&st_empty[s]);
         }
@@ -271,12 +312,16 @@ __global__ void __launch_bounds__(DWA_THREADS, 1) dwadam_kernel(const DwaParams 
         if (!t.active) continue;
         const uint32_t idesc = umma_idesc_bf16(t.BN, 1, 1);
         const uint32_t a = j & 1, aph = (j >> 1) & 1;
-        mbar_wait(&acc_empty[a], aph ^ 1, p.dbg, 0xB1000000u | tile);
+        mbar_wait_sleepy(&acc_empty[a], aph ^ 1, p.dbg, 0xB1000000u | tile);
         tc_fence_after();
         const uint32_t tacc = tmem_base + a * 256;
         for (int kb = 0; kb < t.nkb; ++kb, ++it) {
           const uint32_t s = it % DWA_OPS;
-          mbar_wait(&op_full[s], (it / DWA_OPS) & 1, p.dbg, 0xF1000000u | kb);
+          {
+            DWS_T0();
+            mbar_wait_sleepy(&op_full[s], (it / DWA_OPS) & 1, p.dbg, 0xF1000000u | kb);
+            DWS_ADD(w_a);
+          }
           tc_fence_after();
           const int nq = min(GEMM_BK, t.Kc - kb * GEMM_BK) >> 4;
           const uint32_t alo = lo0 + smem0 + s * stage16, blo = alo + (GEMM_A_STAGE_BYTES >> 4);
@@ -296,6 +341,7 @@ __global__ void __launch_bounds__(DWA_THREADS, 1) dwadam_kernel(const DwaParams 
     const int w = warp - 4, q = w & 3, g = w >> 2;
     const int kl = q * 32 + lane;          // tile-local input feature = TMEM lane
     const int et = threadIdx.x - 128;      // 0 .. 511
+    const AdamHyper h = *p.adam;
     uint32_t it = 0, j = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const DwaTile t = dwa_tile(p, L, tile);
@@ -321,49 +367,63 @@ __global__ void __launch_bounds__(DWA_THREADS, 1) dwadam_kernel(const DwaParams 
         }
         epi_bar_sync();
       }
-      const AdamHyper h = *p.adam;
       const bool have_acc = t.nkb > 0;
-      if (lane == 0) mbar_wait(&acc_full[a], aph, p.dbg, 0xA1000000u | tile);
+      if (lane == 0) {
+        DWS_T0();
+        mbar_wait_sleepy(&acc_full[a], aph, p.dbg, 0xA1000000u | tile);
+        DWS_ADD(w_a);
+      }
       __syncwarp();
       tc_fence_after();
       const uint32_t taddr = tmem_base + a * 256 + ((uint32_t)(q * 32) << 16) + g * 4;
-      for (int sub = 0; sub < t.BN / DWA_R; ++sub, ++it) {
+      // All 16 warps work on the same stage (4 weight rows each): a stage is occupied for the shortest possible time,
+      // which is what the 4-slot ring needs.  Measured alternatives (profiles/r02_experiments.md): column group g owning
+      // slot g and all 16 rows of its stages (fewer barrier operations per parameter, but no overlap of a slot's load
+      // and its update): 443 -> 503 us; writing p, m, v straight from registers instead of tensor stores: 443 -> 475 us.
+      //
+      // (tensor, row) of a stage's first weight row, tracked incrementally: stages advance by 16 shadow rows and the
+      // stacking blocks are multiples of 16
+      int blk = t.n0 / y.ilv_stride, rem = t.n0 - blk * y.ilv_stride;
+      const int my_off = (g * 4) * 128 + scol;  // this thread's first element inside a stage array
+      const bool wc = is_w || is_c;
+      const int rot = lane >> 3;  // shadow rows are written rotated by the lane's chunk: conflict-free 2-byte stores
+      for (int sub = 0; sub < t.BN / DWA_R; ++sub, ++it, rem += DWA_R) {
+        if (rem >= y.ilv_stride) rem -= y.ilv_stride, ++blk;
+        const int which = rem >= y.ilv_block ? 1 : 0;
+        const int n = blk * y.ilv_block + rem - which * y.ilv_block;
+        const bool has = which < y.ntens && n < y.rows_each;
         const int s = it % DWA_NST;
-        if (lane == 0) mbar_wait(&st_full[s], (it / DWA_NST) & 1, p.dbg, 0xA2000000u | sub);
-        __syncwarp();
-        float acc[4];
-        if (have_acc) {
-          tmem_ld4(taddr + sub * DWA_R, acc);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) acc[i] = 0.f;
+        uint32_t accr[4];
+        if (have_acc) tmem_ld4_issue(taddr + sub * DWA_R, accr);  // in flight while this warp waits for the stage
+        if (lane == 0) {
+          DWS_T0();
+          mbar_wait_sleepy(&st_full[s], (it / DWA_NST) & 1, p.dbg, 0xA2000000u | sub);
+          DWS_ADD(w_b);
         }
+        __syncwarp();
         uint8_t* st = st_ring + (size_t)s * DWA_ST_STAGE;
-        float* sp = reinterpret_cast<float*>(st);
-        float* sm = reinterpret_cast<float*>(st + DWA_ARR);
-        float* sv = reinterpret_cast<float*>(st + 2 * DWA_ARR);
-        bf16* ss = reinterpret_cast<bf16*>(st + 3 * DWA_ARR);
-        int which, n;
-        const int s0 = t.n0 + sub * DWA_R;
-        const bool has = dwa_stage_rows(y, s0, which, n);
+        float* sp = reinterpret_cast<float*>(st) + my_off;
+        float* sm = reinterpret_cast<float*>(st + DWA_ARR) + my_off;
+        float* sv = reinterpret_cast<float*>(st + 2 * DWA_ARR) + my_off;
+        bf16* ss = reinterpret_cast<bf16*>(st + 3 * DWA_ARR) + ((kl >> 3) * DWA_R + g * 4) * 8 + (kl & 7);
         float shv[4] = {0.f, 0.f, 0.f, 0.f};
-        if (has && (is_w || is_c)) {
-          float pv[4], mv[4], vv[4];
+        float pv[4], mv[4], vv[4], acc[4];
+        const bool upd = has && wc;
+        if (upd) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int r = g * 4 + i;
-            pv[i] = sp[r * 128 + scol], mv[i] = sm[r * 128 + scol], vv[i] = sv[r * 128 + scol];
-          }
+          for (int i = 0; i < 4; ++i) pv[i] = sp[i * 128], mv[i] = sm[i * 128], vv[i] = sv[i * 128];
+        }
+        tmem_ld4_wait(have_acc, accr, acc);  // warp-collective: outside the lane-dependent branches
+        if (upd) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) adam_update(acc[i], pv[i], mv[i], vv[i], h);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int r = g * 4 + i;
-            sp[r * 128 + scol] = pv[i], sm[r * 128 + scol] = mv[i], sv[r * 128 + scol] = vv[i];
-            if (is_w) shv[i] = pv[i];
-          }
-          if (is_c) {  // class columns: the forward reads them as fp32 per-class bias rows
-            float* d = p.drv + t.model * p.drv_ms + y.drv_clsb_off + (long long)(kk - y.kin - 1) * y.drv_clsb_ld + s0 + g * 4;
+          for (int i = 0; i < 4; ++i) sp[i * 128] = pv[i], sm[i * 128] = mv[i], sv[i * 128] = vv[i];
+          if (is_w) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) shv[i] = pv[i];
+          } else {  // class columns: the forward reads them as fp32 per-class bias rows
+            float* d = p.drv + t.model * p.drv_ms + y.drv_clsb_off + (long long)(kk - y.kin - 1) * y.drv_clsb_ld + t.n0 + sub * DWA_R + g * 4;
 #pragma unroll
             for (int i = 0; i < 4; ++i)
               if (n + g * 4 + i < y.rows_each) d[i] = pv[i];
@@ -372,14 +432,20 @@ __global__ void __launch_bounds__(DWA_THREADS, 1) dwadam_kernel(const DwaParams 
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int c = sub * DWA_R + g * 4 + i;  // tile-local weight row
-            float pv = bst[c], mv = bst[256 + c], vv = bst[512 + c];
-            adam_update(acc[i], pv, mv, vv, h);
-            bst[c] = pv, bst[256 + c] = mv, bst[512 + c] = vv;
+            float pb = bst[c], mb = bst[256 + c], vb = bst[512 + c];
+            adam_update(acc[i], pb, mb, vb, h);
+            bst[c] = pb, bst[256 + c] = mb, bst[512 + c] = vb;
           }
         }
-        // shadow stage [16 chunks][R rows][8]: columns >= kin (ones / class columns, padding) stay zero
+        // shadow stage [16 chunks][R rows][8]: columns >= kin (ones / class columns, padding) stay zero.  The four
+        // 8-lane groups of a warp write four different chunks whose rows are 256 bytes (= all 32 banks x 2) apart: row
+        // order rotated by the group index so that they hit different banks
 #pragma unroll
-        for (int i = 0; i < 4; ++i) ss[((kl >> 3) * DWA_R + g * 4 + i) * 8 + (kl & 7)] = __float2bfloat16_rn(shv[i]);
+        for (int i = 0; i < 4; ++i) {
+          const int r = (i + rot) & 3;
+          const float x = r == 0 ? shv[0] : (r == 1 ? shv[1] : (r == 2 ? shv[2] : shv[3]));
+          ss[r * 8] = __float2bfloat16_rn(x);
+        }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(&st_done[s]);
@@ -404,8 +470,15 @@ __global__ void __launch_bounds__(DWA_THREADS, 1) dwadam_kernel(const DwaParams 
       ++j;
     }
   }
+  if (p.stats && lane == 0) {
+    if (warp == 0) atomicAdd(p.stats + DWS_PROD_EMPTY, (unsigned long long)w_a);
+    if (warp == 1) atomicAdd(p.stats + DWS_LOADER_EMPTY, (unsigned long long)w_a);
+    if (warp == 2) atomicAdd(p.stats + DWS_STORER_DONE, (unsigned long long)w_a), atomicAdd(p.stats + DWS_STORER_READ, (unsigned long long)w_b);
+    if (warp == 4) atomicAdd(p.stats + DWS_EPI_ACC, (unsigned long long)w_a), atomicAdd(p.stats + DWS_EPI_STATE, (unsigned long long)w_b);
+  }
   tc_fence_before();
   __syncthreads();
+  if (p.stats && threadIdx.x == 0) atomicAdd(p.stats + DWS_CTA_TOTAL, (unsigned long long)(clock64() - cta_t0));
   if (warp == 3) tmem_dealloc(tmem_base, 512);
 }
 

@@ -100,9 +100,13 @@ struct GemmProblem {
   int tiles_m;
   int nstages;
   int ksplit;       // >1: contraction split into ksplit tiles (EPI_GRAD accumulates atomically)
-  int n_models;
+  int n_models;     // models of this launch ...
+  int model0;       // ... starting at this ensemble member
+  int ens;          // ensemble members the operand buffers hold (extent of the tensor maps); 0: n_models
   int desc_variant; // debug knob for descriptor bring-up (0 = designed encoding)
   DebugWord* dbg;
+  unsigned long long* trace;  // kernel trace (common.cuh TraceScope)
+  int trace_id;
 };
 
 struct EpiParams {
@@ -492,7 +496,7 @@ __device__ __forceinline__ TileInfo gemm_tile_info(const GemmProblem& p, int til
   const int mn = tile % tiles_mn;
   const int rest = tile / tiles_mn;
   const int ks = rest % p.ksplit;
-  t.model = rest / p.ksplit;
+  t.model = p.model0 + rest / p.ksplit;
   if (p.mode == GEMM_DW) {
     // weight-gradient tiles: consecutive tiles (running at the same time on neighbouring SMs) take
     // consecutive 128-feature segments of the SAME reference-weight rows
@@ -888,6 +892,7 @@ __global__ void __launch_bounds__((GEMM_PROD_WARPS + 1 + EW) * 32, 1) gemm_tc_ke
   __shared__ __align__(8) uint64_t acc_empty[GEMM_ACC_STAGES];
   __shared__ uint32_t tmem_base_s;
 
+  TraceScope trace_scope(p.trace, p.trace_id);
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -1279,15 +1284,16 @@ inline cudaError_t gemm_launch_t(GemmProblem p, const EpiParams& e, int n_models
   }
   // operand tensor maps (see the producer warp of gemm_tc_kernel)
   CUtensorMap tmA, tmB, tmB2;
+  const int ens = p.ens > 0 ? p.ens : n_models;
   const bool a_mn = p.mode == GEMM_DW, b_mn = p.mode != GEMM_NT;
-  cudaError_t err = a_mn ? gemm_c8_map(&tmA, p.A, n_models, GEMM_BK, GEMM_BM / 8) : gemm_c8_map(&tmA, p.A, n_models, GEMM_BM, GEMM_BK / 8);
+  cudaError_t err = a_mn ? gemm_c8_map(&tmA, p.A, ens, GEMM_BK, GEMM_BM / 8) : gemm_c8_map(&tmA, p.A, ens, GEMM_BM, GEMM_BK / 8);
   if (err != cudaSuccess) return err;
   if (b_mn) {
-    err = gemm_c8_map(&tmB, p.B, n_models, GEMM_BK, p.BN / 8);
+    err = gemm_c8_map(&tmB, p.B, ens, GEMM_BK, p.BN / 8);
     tmB2 = tmB;
   } else {
-    err = gemm_c8_map(&tmB, p.B, n_models, p.BN > 128 ? 128 : p.BN, GEMM_BK / 8);
-    if (err == cudaSuccess && p.BN > 128) err = gemm_c8_map(&tmB2, p.B, n_models, p.BN - 128, GEMM_BK / 8);
+    err = gemm_c8_map(&tmB, p.B, ens, p.BN > 128 ? 128 : p.BN, GEMM_BK / 8);
+    if (err == cudaSuccess && p.BN > 128) err = gemm_c8_map(&tmB2, p.B, ens, p.BN - 128, GEMM_BK / 8);
     if (p.BN <= 128) tmB2 = tmB;
   }
   if (err != cudaSuccess) return err;

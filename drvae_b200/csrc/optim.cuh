@@ -179,13 +179,15 @@ struct EpsSegs {
   int inner[6];      // floats per row
 };
 
-__global__ void __launch_bounds__(256) philox_normal_kernel(MBuf<float> out, EpsSegs sg, int N, int Ncap, const StepDyn* dyn) {
+__global__ void __launch_bounds__(256) philox_normal_kernel(MBuf<float> out, EpsSegs sg, int N, int Ncap, const StepDyn* dyn, int model0,
+                                                            unsigned long long* trace, int trace_id) {
+  TraceScope trace_scope(trace, trace_id);
   pdl_launch_dependents();
   pdl_wait();
   const long long row_offset = dyn->row_offset;
   const unsigned long long seed = dyn->noise_seed;
   const unsigned int step = dyn->noise_step;
-  const int m = blockIdx.y, seg = blockIdx.z;
+  const int m = model0 + blockIdx.y, seg = blockIdx.z;
   int inner = 0, outer = 0;
   long long seg_off = 0;
 #pragma unroll

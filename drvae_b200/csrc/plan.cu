@@ -104,10 +104,18 @@ struct drvae_plan {
   std::map<std::vector<long long>, GraphEntry> graphs;
   long long graph_clock = 0;
   long long graph_replays = 0;
-  // side stream for the label-dependent branch (see run_step)
-  cudaStream_t side = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_qy = nullptr, ev_side_fwd = nullptr, ev_side_bwd = nullptr, ev_begin = nullptr, ev_eps = nullptr,
-              ev_clf = nullptr, ev_kfp = nullptr;
+  // streams of the step schedule (see run_step): per model range a main stream (range 0 uses the caller's) and a side
+  // stream for the label-dependent branch
+  static constexpr int MAX_CHAINS = 8;
+  struct Chain {
+    cudaStream_t main = nullptr, side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_qy = nullptr, ev_side_fwd = nullptr, ev_side_bwd = nullptr, ev_begin = nullptr, ev_eps = nullptr,
+                ev_clf = nullptr, ev_kfp = nullptr, ev_end = nullptr;
+    cudaEvent_t* all() { return &ev_fork; }  // 9 consecutive events
+  };
+  Chain chain[MAX_CHAINS];
+  int chains = 1;             // model ranges per step (DRVAE_B200_CHAINS; default chosen from n_models at creation)
+  cudaEvent_t ev_begin = nullptr;
   bool overlap = true;
   long long side_delay_cycles = 0;  // test knob (drvae_debug_side_delay): spin on the side stream before pz1_post
   // gradient buckets (data-parallel overlap): contiguous parameter ranges in backward completion order
@@ -119,7 +127,13 @@ struct drvae_plan {
   DwaMaps* d_dwa_maps = nullptr;
   int dwa_tiles = 0;
   bool dwa_ok = false;       // every layer fits the kernel's layout conditions and the state is bound
+  unsigned long long* d_dwa_stats = nullptr;  // drvae_debug_dwa_stats
   bool dwa_enabled = true;   // measurement knob (DRVAE_B200_DWADAM=0: per-layer fused kernels of round 1)
+  // kernel trace (drvae_trace_begin / _end): device slots {first CTA start, last CTA end} per launch, tags on the host
+  unsigned long long* d_trace = nullptr;
+  int trace_cap = 0, trace_next = 0;
+  bool trace_on = false, trace_saved_graph = true;
+  std::vector<std::string> trace_tags;
   // optional per-launch event timing (bench.py / profiles)
   bool prof_on = false;
   std::vector<cudaEvent_t> prof_ev;
@@ -541,9 +555,15 @@ extern "C" int drvae_plan_create(const drvae_arch_t* a, int n_models, drvae_plan
   if (const char* knob = getenv("DRVAE_B200_SCHED")) pl->sched = atoi(knob);
   if (const char* knob = getenv("DRVAE_B200_DWADAM")) pl->dwa_enabled = atoi(knob) != 0;
   if (const char* knob = getenv("DRVAE_B200_PDL")) pdl_mask() = atoi(knob);  // measurement knob: programmatic dependent launch
-  cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking);
-  for (cudaEvent_t* ev : {&pl->ev_fork, &pl->ev_qy, &pl->ev_side_fwd, &pl->ev_side_bwd, &pl->ev_begin, &pl->ev_eps, &pl->ev_clf, &pl->ev_kfp})
-    cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
+  pl->chains = 1;  // measured (32 models): 0.970 / 1.002 / 1.020 / 1.054 ms for 1 / 2 / 4 / 8 ranges
+  if (const char* knob = getenv("DRVAE_B200_CHAINS")) pl->chains = std::max(1, atoi(knob));
+  if (const char* knob = getenv("DRVAE_B200_OVERLAP")) pl->overlap = atoi(knob) != 0;
+  for (auto& ch : pl->chain) {
+    cudaStreamCreateWithFlags(&ch.main, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ch.side, cudaStreamNonBlocking);
+    for (int i = 0; i < 9; ++i) cudaEventCreateWithFlags(ch.all() + i, cudaEventDisableTiming);
+  }
+  cudaEventCreateWithFlags(&pl->ev_begin, cudaEventDisableTiming);
   pl->bucket_ev.resize(pl->buckets.size());
   for (auto& ev : pl->bucket_ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
   cudaMalloc(&pl->dbg, sizeof(DebugWord));
@@ -651,10 +671,16 @@ extern "C" int drvae_plan_destroy(drvae_plan_t* pl) {
   if (pl->d_wn_rows) cudaFree(pl->d_wn_rows);
   if (pl->d_dwa_layers) cudaFree(pl->d_dwa_layers);
   if (pl->d_dwa_maps) cudaFree(pl->d_dwa_maps);
+  if (pl->d_trace) cudaFree(pl->d_trace);
+  if (pl->d_dwa_stats) cudaFree(pl->d_dwa_stats);
   for (auto& ev : pl->bucket_ev) cudaEventDestroy(ev);
-  for (cudaEvent_t ev : {pl->ev_fork, pl->ev_qy, pl->ev_side_fwd, pl->ev_side_bwd, pl->ev_begin, pl->ev_eps, pl->ev_clf, pl->ev_kfp})
-    if (ev) cudaEventDestroy(ev);
-  if (pl->side) cudaStreamDestroy(pl->side);
+  for (auto& ch : pl->chain) {
+    for (int i = 0; i < 9; ++i)
+      if (ch.all()[i]) cudaEventDestroy(ch.all()[i]);
+    if (ch.main) cudaStreamDestroy(ch.main);
+    if (ch.side) cudaStreamDestroy(ch.side);
+  }
+  if (pl->ev_begin) cudaEventDestroy(pl->ev_begin);
   delete pl;
   return 0;
 }
@@ -702,6 +728,12 @@ extern "C" int drvae_set_gemm_impl(drvae_plan_t* pl, int impl) {
   if (!pl || (impl != GEMM_IMPL_TC && impl != GEMM_IMPL_SIMT)) return set_error("drvae_set_gemm_impl: bad argument");
   if (pl->gemm_impl != impl) drop_graphs(pl);  // captured sequences replay the kernels of the old implementation
   pl->gemm_impl = impl;
+  return 0;
+}
+extern "C" int drvae_set_chains(drvae_plan_t* pl, int chains) {
+  if (!pl || chains < 1) return set_error("drvae_set_chains: bad argument");
+  pl->chains = std::min(chains, (int)drvae_plan::MAX_CHAINS);
+  drop_graphs(pl);
   return 0;
 }
 extern "C" int drvae_debug_side_delay(drvae_plan_t* pl, long long cycles) {
@@ -858,10 +890,19 @@ struct Exec {
   std::string sub = "head";  // layer within the current block: h0, h1, ..., head
   bool fused = false;        // Adam inside the gradient epilogues (drvae_train_step)
   bool splitk = false;       // split-K weight gradients (large minibatches, unfused path)
+  int model0 = 0, Ec = 0;    // model range of the launches being enqueued (Ec = 0: the whole ensemble)
   bool defer_dw = false;     // weight gradients + Adam of every layer in ONE launch at the end of backward (dwadam.cuh)
   bool ok() const { return err == cudaSuccess; }
   // event bracket around one launch when profiling is on
-  void pre(const std::string& op) { prof_pre(pl, st, std::string(phase) + ":" + op); }
+  void pre(const std::string& op) {
+    prof_pre(pl, st, std::string(phase) + ":" + op);
+    v.trace = nullptr;
+    if (pl->trace_on && pl->trace_next < pl->trace_cap) {
+      v.trace = pl->d_trace;
+      v.trace_id = pl->trace_next++;
+      pl->trace_tags.push_back(std::string(phase) + ":" + op);
+    }
+  }
   void post() { prof_post(pl, st); }
   void chk() {
     post();
@@ -886,7 +927,11 @@ struct Exec {
     p.desc_variant = 0;
     if (p.ksplit < 1) p.ksplit = 1;
     pre(op);
-    cudaError_t r = gemm_launch(epi, p, e, pl->E, pl->gemm_impl, st);
+    p.model0 = model0;
+    p.ens = pl->E;
+    p.trace = v.trace;
+    p.trace_id = v.trace_id;
+    cudaError_t r = gemm_launch(epi, p, e, Ec > 0 ? Ec : pl->E, pl->gemm_impl, st);
     post();
     if (r != cudaSuccess) err = r;
     pl->launches++;
@@ -1218,6 +1263,12 @@ int run_wn_grad(drvae_plan* pl, cudaStream_t st) {
 }
 
 // forward (+ optional backward) of one minibatch per model
+//
+// Schedule.  The ensemble is cut into `chains` contiguous model ranges; each range runs its whole forward + dX chain
+// on its own pair of streams (main + side, the side stream taking the label-dependent branch as before), so the
+// latency-bound small kernels of one range overlap those of the others.  The ranges fork from the caller's stream
+// after the per-step scalars and join before the grouped dW+Adam launch, which covers every model and layer at once.
+// Captured into a CUDA graph the forks and joins become graph edges.
 int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, const drvae_hparams_t* hp, float* losses_out,
              cudaStream_t st, bool backward, bool fused_adam) {
   if (!hp) return set_error("drvae: hparams is null");
@@ -1247,240 +1298,270 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
     if (e0 != cudaSuccess) return set_cuda_error("drvae: zeroing the gradient buffer", e0);
   }
   const int Fb = std::max(1, L * pl->Y * N);
-  auto rows_grid = [&](int rows) { return dim3(cdiv(rows, ROW_WARPS), E); };
-
-  // Two-stream schedule (captured as graph edges): everything that is not on the longest dependency chain runs on
-  // the plan's side stream — the latent-noise generator (next to rowmap / prep / the encoder), the label-dependent
-  // branch, the classifier backward and the loss reduction.
-  const bool overlap = pl->has_fprop && pl->overlap && !pl->prof_on;
-  cudaStream_t side = overlap ? pl->side : st;
-  auto on = [&](cudaStream_t s) { ex.st = s; };
-  auto after = [&](cudaStream_t waiter, cudaEvent_t ev, cudaStream_t producer) {
-    if (!overlap || waiter == producer) return;
-    cudaEventRecord(ev, producer);
-    cudaStreamWaitEvent(waiter, ev, 0);
-  };
-  if (!(nz && nz->eps)) {
-    const drvae_eps_layout_t& el = pl->epsl;
-    EpsSegs sg{};
-    const long long offs[6] = {el.off_x1, el.off_x2, el.off_z1, el.off_z2, el.off_z2f, el.off_z3};
-    const int outer[6] = {1, 1, L, L, L, L};
-    const bool noisy = hp->training && hp->add_noise;
-    (void)noisy;  // the input noise (segments 0, 1) is drawn inside prep_kernel with the same keys
-    const int inner[6] = {0, 0, pl->Z, pl->has_pair ? pl->Z : 0,
-                          pl->has_T ? pl->Z : 0, pl->has_fprop ? pl->Y * pl->Z3 : 0};
+  const bool own_eps = !(nz && nz->eps);
+  if (own_eps) {
     long long most = 0;
-    for (int i = 0; i < 6; ++i) {
-      sg.off[i] = offs[i];
-      sg.outer[i] = outer[i];
-      sg.inner[i] = inner[i];
-      most = std::max(most, (long long)outer[i] * N * ((inner[i] + 3) / 4));
-    }
+    for (int inner : {pl->Z, pl->Y * pl->Z3}) most = std::max(most, (long long)L * N * ((inner + 3) / 4));
     if (most >= (1LL << 31)) return set_error("drvae: minibatch too large for the noise generator");
-    dim3 g((unsigned)((most + 255) / 256), E, 6);
-    if (pl->sched & 1) {
-      after(side, pl->ev_begin, st);  // after this step's scalars (set_dyn) and everything before them
-      on(side);
-    }
-    ex.pre("philox_normal");
-    launch_k(philox_normal_kernel, g, dim3(256), 0, ex.st, 2, pl->eps_own, sg, N, pl->Ncap, pl->d_dyn);
-    ex.chk();
-    on(st);
   }
-  ex.pre("rowmap");
-  launch_k(rowmap_kernel, dim3(E), dim3(ROWMAP_THREADS), 0, st, 2, v);
-  ex.chk();
-  ex.pre("prep");
-  launch_k(prep_kernel, dim3(round_up(R0b, 128) / PREP_ROWS, cdiv(pl->view.Xc, PREP_SLAB), E), dim3(PREP_THREADS), 0, st, 2, v);
-  ex.chk();
 
-  // ---- encoder q(z1|x1), shared with q(z2|x2) (DrVAE.py:408,418) ----
-  ex.phase = "enc.fwd";
-  ex.block_hidden_fwd(pl->enc, v.Ain, 0, CNT_R0, R0b);
-  ex.gemm_nt(pl->enc.H.back(), 0, pl->enc.head, EPI_STORE_F32, ex.epi_f32(v.Q.p, v.Q.ms, 2 * pl->view.Zs, 2 * pl->view.Zs, &pl->enc.head),
-             CNT_R0, R0b);
-  if (!(nz && nz->eps) && (pl->sched & 1)) after(st, pl->ev_eps, side);  // latent noise of this step
-  ex.pre("sample_q1");
-  launch_k(pl->view.Zc <= 128 ? sample_q1_kernel<4> : sample_q1_kernel<MAXJ>, rows_grid(N + PAD_WARPS), dim3(ROW_THREADS), 0, st, 2, v);
-  ex.chk();
-  // The label-dependent branch (q(z_top|z1,y) -> p(z1|z_top,y), forward and backward: ~14 small
-  // GEMMs + 4 row kernels that leave most SMs idle) is independent of the decoder branch, so it runs
-  // on the plan's side stream between a fork here and a join before the encoder backward.
-  after(side, pl->ev_fork, st);
+  // model ranges: separate chains only where the gradient buckets are not consumed outside (drvae_grad_step records
+  // one event per bucket on ONE stream) and not under per-launch profiling
+  int K = 1;
+  if (!pl->prof_on && !(backward && !fused_adam)) K = std::max(1, std::min({pl->chains, E, (int)drvae_plan::MAX_CHAINS}));
+  if (K > 1) cudaEventRecord(pl->ev_begin, st);
 
-  auto fprop_fwd_gemms = [&]() {
-    // ---- label-dependent part: q(z_top|z1,y), p(z1|z_top,y) per (row, class) evaluation ----
-    ex.phase = "z3.fwd";
-    ex.block_hidden_fwd(pl->z3b, v.Z1e, 0, CNT_F, Fb);
-    ex.gemm_nt(pl->z3b.H.back(), 0, pl->z3b.head, EPI_STORE_F32,
-               ex.epi_f32(v.Q3.p, v.Q3.ms, 2 * pl->view.Z3s, 2 * pl->view.Z3s, &pl->z3b.head), CNT_F, Fb);
-    ex.pre("z3_post");
-    launch_k(z3_post_kernel, rows_grid(round_up(Fb, 128)), dim3(ROW_THREADS), 0, ex.st, 2, v);
-    ex.chk();
-    ex.phase = "dz1.fwd";
-    ex.block_hidden_fwd(pl->dz1b, v.Z3b, 0, CNT_F, Fb);
-    ex.gemm_nt(pl->dz1b.H.back(), 0, pl->dz1b.head, EPI_STORE_F32,
-               ex.epi_f32(v.PZ1.p, v.PZ1.ms, 2 * pl->view.Zs, 2 * pl->view.Zs, &pl->dz1b.head), CNT_F, Fb);
-  };
-  auto clf_bwd = [&]() {
-    ex.phase = "clf.bwd";
-    ex.pre("clf_back");
-    launch_k(clf_back_kernel, rows_grid(LNb), dim3(ROW_THREADS), 0, ex.st, 2, v);
-    ex.chk();
-    ex.pre("clf_grad_partial");
-    launch_k(clf_grad_partial_kernel, dim3(v.clf_splits, E), dim3(256), 0, ex.st, 2, v);
-    ex.chk();
-    ex.pre("clf_grad_reduce");
-    launch_k(clf_grad_reduce_kernel, dim3(cdiv(pl->Y * (pl->clf_in + 1), 8), E), dim3(256), 0, ex.st, 2, v);
-    ex.chk();
-  };
-  if (pl->has_fprop) {
-    on(side);
-    fprop_fwd_gemms();
-    on(st);
-  }
-  // ---- p(z2|z1) ----
-  ex.phase = "T.fwd";
-  if (pl->has_T) {
-    ex.gemm_nt(v.Zdec, 0, pl->Tsh, EPI_STORE_F32, ex.epi_f32(v.PT.p, v.PT.ms, 2 * pl->view.Zs, 2 * pl->view.Zs, &pl->Tsh), CNT_LN, LNb);
-    ex.pre("T_post");
-    launch_k(pl->view.Zc <= 128 ? T_post_kernel<4> : T_post_kernel<MAXJ>, rows_grid(N + PAD_WARPS), dim3(ROW_THREADS), 0, ex.st, 2, v);
-    ex.chk();
-  }
-  if (pl->has_fprop) {
-    // pz1_post weighs unlabeled evaluations by q(y|.), which the classifier in T_post (DrVAE) or
-    // sample_q1 (VFAE) has just produced
-    after(side, pl->ev_qy, st);
-    on(side);
-    if (pl->side_delay_cycles > 0) spin_kernel<<<1, 1, 0, ex.st>>>(pl->side_delay_cycles);
-    ex.pre("pz1_post");
-    launch_k(pz1_post_kernel, rows_grid(round_up(Fb, 128)), dim3(ROW_THREADS), 0, ex.st, 2, v);
-    ex.chk();
-    // clf_back (main stream) reads the per-class KL terms pz1_post has just written (kfp_row)
-    if (overlap && backward && pl->has_clf && !(pl->sched & 2)) cudaEventRecord(pl->ev_kfp, ex.st);
-    if (backward) {
-      if (pl->has_clf && (pl->sched & 2)) {
-        // classifier backward: needs only q(y|.) (T_post / sample_q1) and the per-class terms pz1_post has just
-        // written, so it leaves the main stream's chain; T_back / q_back wait for ev_clf
-        clf_bwd();
-        cudaEventRecord(pl->bucket_ev[3], ex.st);  // buckets: dz1, z3 (this stream), dec, clf, ...
-        if (overlap) cudaEventRecord(pl->ev_clf, ex.st);
+  for (int c = 0; c < K && ex.ok(); ++c) {
+    drvae_plan::Chain& ch = pl->chain[c];
+    const int m0 = (int)((long long)E * c / K), Ec = (int)((long long)E * (c + 1) / K) - m0;
+    cudaStream_t cm = (c == 0) ? st : ch.main;  // range 0 stays on the caller's stream
+    if (c > 0) cudaStreamWaitEvent(cm, pl->ev_begin, 0);
+    v.model0 = m0;
+    ex.phase = "";
+    ex.model0 = m0;
+    ex.Ec = Ec;
+    ex.st = cm;
+    auto rows_grid = [&](int rows) { return dim3(cdiv(rows, ROW_WARPS), Ec); };
+    // Two-stream schedule inside a range: everything that is not on the longest dependency chain runs on the range's
+    // side stream — the latent-noise generator (next to rowmap / prep / the encoder), the label-dependent branch and
+    // the loss reduction.
+    const bool overlap = pl->has_fprop && pl->overlap && !pl->prof_on;
+    cudaStream_t side = overlap ? ch.side : cm;
+    auto on = [&](cudaStream_t s) { ex.st = s; };
+    auto after = [&](cudaStream_t waiter, cudaEvent_t ev, cudaStream_t producer) {
+      if (!overlap || waiter == producer) return;
+      cudaEventRecord(ev, producer);
+      cudaStreamWaitEvent(waiter, ev, 0);
+    };
+    if (own_eps) {
+      const drvae_eps_layout_t& el = pl->epsl;
+      EpsSegs sg{};
+      const long long offs[6] = {el.off_x1, el.off_x2, el.off_z1, el.off_z2, el.off_z2f, el.off_z3};
+      const int outer[6] = {1, 1, L, L, L, L};
+      // the input noise (segments 0, 1) is drawn inside prep_kernel with the same keys
+      const int inner[6] = {0, 0, pl->Z, pl->has_pair ? pl->Z : 0, pl->has_T ? pl->Z : 0, pl->has_fprop ? pl->Y * pl->Z3 : 0};
+      long long most = 0;
+      for (int i = 0; i < 6; ++i) {
+        sg.off[i] = offs[i];
+        sg.outer[i] = outer[i];
+        sg.inner[i] = inner[i];
+        most = std::max(most, (long long)outer[i] * N * ((inner[i] + 3) / 4));
       }
-      ex.phase = "dz1.bwd";
-      ex.block_bwd(pl->dz1b, v.dY9, v.Z3b, 0, pl->Z3, v.dZ3.p, v.dZ3.ms, CNT_F, Fb);
-      cudaEventRecord(pl->bucket_ev[0], ex.st);
-      ex.pre("z3_back");
-      launch_k(z3_back_kernel, rows_grid(round_up(Fb, 128)), dim3(ROW_THREADS), 0, ex.st, 2, v);
+      dim3 g((unsigned)((most + 255) / 256), Ec, 6);
+      if (pl->sched & 1) {
+        after(side, ch.ev_begin, cm);  // after this step's scalars (set_dyn) and everything before them
+        on(side);
+      }
+      ex.pre("philox_normal");
+      launch_k(philox_normal_kernel, g, dim3(256), 0, ex.st, 2, pl->eps_own, sg, N, pl->Ncap, pl->d_dyn, m0, v.trace, v.trace_id);
       ex.chk();
-      ex.phase = "z3.bwd";
-      ex.block_bwd(pl->z3b, v.dY7, v.Z1e, 0, pl->Z, v.dZ1e.p, v.dZ1e.ms, CNT_F, Fb);
-      cudaEventRecord(pl->bucket_ev[1], ex.st);
+      on(cm);
     }
-    on(st);
-  }
-  // ---- decoder p(x|z) on the stacked rows [z1 | z2 | z2f], fused log-density + gradient ----
-  ex.phase = "dec.fwd";
-  ex.block_hidden_fwd(pl->dec, v.Zdec, 0, CNT_RD, Rdb);
-  {
-    EpiParams e = ex.epi_base();
-    e.out_c8 = pl->dY5.p;
-    e.out_c8_ms = pl->dY5.ms;
-    e.out_c8_rcap = pl->dY5.rcap;
-    e.bias = pl->derived.p + pl->dec.head.bias_off;
-    e.bias_ms = pl->derived.ms;
-    e.tgt4 = v.tgt4.p;
-    e.tgt_ms = v.tgt4.ms;
-    e.tgt_rcap = pl->view.R0cap;
-    e.X = pl->X;
-    e.Xc = pl->view.Xc;
-    e.counts = v.counts.p;
-    e.counts_stride = (int)v.counts.ms;
-    e.coefs = v.coefs.p;
-    e.coefs_stride = (int)v.coefs.ms;
-    e.L = L;
-    e.part = v.dec_part.p;
-    e.part_ms = v.dec_part.ms;
-    e.part_rcap = pl->view.Rdcap;
-    e.write_dy = backward ? 1 : 0;
-    ex.gemm_nt(pl->dec.H.back(), 0, pl->dec.head, EPI_DECLOSS, e, CNT_RD, Rdb);
-  }
-  // The loss reduction is off the backward's critical path: it runs at the tail of the side stream
-  // (after that branch's backward), once the decoder log-density partials of the main stream exist.
-  after(side, pl->ev_side_fwd, st);
-  on(side);
-  ex.phase = "";
-  ex.pre("loss");
-  launch_k(loss_partial_kernel, dim3(v.loss_slices, E), dim3(256), 0, ex.st, 2, v);
-  ex.chk();
-  ex.pre("loss_final");
-  launch_k(loss_final_kernel, dim3(E), dim3(32), 0, ex.st, 2, v);
-  ex.chk();
-  if (losses_out && ex.ok()) {
-    // losses buffer per model is padded to 256 B in the arena; the caller's is dense [E][8]
-    ex.err = cudaMemcpy2DAsync(losses_out, 8 * sizeof(float), v.losses.p, v.losses.ms * sizeof(float), 8 * sizeof(float), E,
-                               cudaMemcpyDeviceToDevice, ex.st);
-  }
-  if (overlap) cudaEventRecord(pl->ev_side_bwd, side);  // everything the side stream does in this step
-  on(st);
-  if (overlap && !backward) cudaStreamWaitEvent(st, pl->ev_side_bwd, 0);
+    ex.pre("rowmap");
+    launch_k(rowmap_kernel, dim3(Ec), dim3(ROWMAP_THREADS), 0, cm, 2, v);
+    ex.chk();
+    ex.pre("prep");
+    launch_k(prep_kernel, dim3(round_up(R0b, 128) / PREP_ROWS, cdiv(pl->view.Xc, PREP_SLAB), Ec), dim3(PREP_THREADS), 0, cm, 2, v);
+    ex.chk();
 
-  if (backward && ex.ok()) {
-    size_t bk = pl->has_fprop ? 2 : 0;  // buckets 0, 1 (decoder_z1, encoder_z3) were recorded by the side branch
-    auto bucket_done = [&]() { cudaEventRecord(pl->bucket_ev[bk++], ex.st); };
-    ex.phase = "dec.bwd";
-    ex.block_bwd(pl->dec, pl->dY5, v.Zdec, 0, pl->Z, v.dZdec.p, v.dZdec.ms, CNT_RD, Rdb);
-    bucket_done();
-    if (pl->has_clf) {
-      if (pl->has_fprop && (pl->sched & 2)) {
-        ++bk;  // ran on the side stream right after pz1_post (bucket event recorded there)
-        if (overlap) cudaStreamWaitEvent(st, pl->ev_clf, 0);
-      } else {
-        if (overlap && pl->has_fprop) cudaStreamWaitEvent(st, pl->ev_kfp, 0);
-        clf_bwd();
+    // ---- encoder q(z1|x1), shared with q(z2|x2) (DrVAE.py:408,418) ----
+    ex.phase = "enc.fwd";
+    ex.block_hidden_fwd(pl->enc, v.Ain, 0, CNT_R0, R0b);
+    ex.gemm_nt(pl->enc.H.back(), 0, pl->enc.head, EPI_STORE_F32,
+               ex.epi_f32(v.Q.p, v.Q.ms, 2 * pl->view.Zs, 2 * pl->view.Zs, &pl->enc.head), CNT_R0, R0b);
+    if (own_eps && (pl->sched & 1)) after(cm, ch.ev_eps, side);  // latent noise of this step
+    ex.pre("sample_q1");
+    launch_k(pl->view.Zc <= 128 ? sample_q1_kernel<4> : sample_q1_kernel<MAXJ>, rows_grid(N + PAD_WARPS), dim3(ROW_THREADS), 0, cm, 2, v);
+    ex.chk();
+    // The label-dependent branch (q(z_top|z1,y) -> p(z1|z_top,y), forward and backward dX: small GEMMs + row kernels
+    // that leave most SMs idle) is independent of the decoder branch: side stream between a fork here and a join
+    // before the encoder backward.
+    after(side, ch.ev_fork, cm);
+
+    auto fprop_fwd_gemms = [&]() {
+      // ---- label-dependent part: q(z_top|z1,y), p(z1|z_top,y) per (row, class) evaluation ----
+      ex.phase = "z3.fwd";
+      ex.block_hidden_fwd(pl->z3b, v.Z1e, 0, CNT_F, Fb);
+      ex.gemm_nt(pl->z3b.H.back(), 0, pl->z3b.head, EPI_STORE_F32,
+                 ex.epi_f32(v.Q3.p, v.Q3.ms, 2 * pl->view.Z3s, 2 * pl->view.Z3s, &pl->z3b.head), CNT_F, Fb);
+      ex.pre("z3_post");
+      launch_k(z3_post_kernel, rows_grid(round_up(Fb, 128)), dim3(ROW_THREADS), 0, ex.st, 2, v);
+      ex.chk();
+      ex.phase = "dz1.fwd";
+      ex.block_hidden_fwd(pl->dz1b, v.Z3b, 0, CNT_F, Fb);
+      ex.gemm_nt(pl->dz1b.H.back(), 0, pl->dz1b.head, EPI_STORE_F32,
+                 ex.epi_f32(v.PZ1.p, v.PZ1.ms, 2 * pl->view.Zs, 2 * pl->view.Zs, &pl->dz1b.head), CNT_F, Fb);
+    };
+    auto clf_bwd = [&]() {
+      ex.phase = "clf.bwd";
+      ex.pre("clf_back");
+      launch_k(clf_back_kernel, rows_grid(LNb), dim3(ROW_THREADS), 0, ex.st, 2, v);
+      ex.chk();
+      ex.pre("clf_grad_partial");
+      launch_k(clf_grad_partial_kernel, dim3(v.clf_splits, Ec), dim3(256), 0, ex.st, 2, v);
+      ex.chk();
+      ex.pre("clf_grad_reduce");
+      launch_k(clf_grad_reduce_kernel, dim3(cdiv(pl->Y * (pl->clf_in + 1), 8), Ec), dim3(256), 0, ex.st, 2, v);
+      ex.chk();
+    };
+    if (pl->has_fprop) {
+      on(side);
+      fprop_fwd_gemms();
+      on(cm);
+    }
+    // ---- p(z2|z1) ----
+    ex.phase = "T.fwd";
+    if (pl->has_T) {
+      ex.gemm_nt(v.Zdec, 0, pl->Tsh, EPI_STORE_F32, ex.epi_f32(v.PT.p, v.PT.ms, 2 * pl->view.Zs, 2 * pl->view.Zs, &pl->Tsh), CNT_LN, LNb);
+      ex.pre("T_post");
+      launch_k(pl->view.Zc <= 128 ? T_post_kernel<4> : T_post_kernel<MAXJ>, rows_grid(N + PAD_WARPS), dim3(ROW_THREADS), 0, ex.st, 2, v);
+      ex.chk();
+    }
+    if (pl->has_fprop) {
+      // pz1_post weighs unlabeled evaluations by q(y|.), which the classifier in T_post (DrVAE) or
+      // sample_q1 (VFAE) has just produced
+      after(side, ch.ev_qy, cm);
+      on(side);
+      if (pl->side_delay_cycles > 0) spin_kernel<<<1, 1, 0, ex.st>>>(pl->side_delay_cycles);
+      ex.pre("pz1_post");
+      launch_k(pz1_post_kernel, rows_grid(round_up(Fb, 128)), dim3(ROW_THREADS), 0, ex.st, 2, v);
+      ex.chk();
+      // clf_back (main stream) reads the per-class KL terms pz1_post has just written (kfp_row)
+      if (overlap && backward && pl->has_clf && !(pl->sched & 2)) cudaEventRecord(ch.ev_kfp, ex.st);
+      if (backward) {
+        if (pl->has_clf && (pl->sched & 2)) {
+          // classifier backward: needs only q(y|.) (T_post / sample_q1) and the per-class terms pz1_post has just
+          // written, so it leaves the main stream's chain; T_back / q_back wait for ev_clf
+          clf_bwd();
+          cudaEventRecord(pl->bucket_ev[3], ex.st);  // buckets: dz1, z3 (this stream), dec, clf, ...
+          if (overlap) cudaEventRecord(ch.ev_clf, ex.st);
+        }
+        ex.phase = "dz1.bwd";
+        ex.block_bwd(pl->dz1b, v.dY9, v.Z3b, 0, pl->Z3, v.dZ3.p, v.dZ3.ms, CNT_F, Fb);
+        cudaEventRecord(pl->bucket_ev[0], ex.st);
+        ex.pre("z3_back");
+        launch_k(z3_back_kernel, rows_grid(round_up(Fb, 128)), dim3(ROW_THREADS), 0, ex.st, 2, v);
+        ex.chk();
+        ex.phase = "z3.bwd";
+        ex.block_bwd(pl->z3b, v.dY7, v.Z1e, 0, pl->Z, v.dZ1e.p, v.dZ1e.ms, CNT_F, Fb);
+        cudaEventRecord(pl->bucket_ev[1], ex.st);
+      }
+      on(cm);
+    }
+    // ---- decoder p(x|z) on the stacked rows [z1 | z2 | z2f], fused log-density + gradient ----
+    ex.phase = "dec.fwd";
+    ex.block_hidden_fwd(pl->dec, v.Zdec, 0, CNT_RD, Rdb);
+    {
+      EpiParams e = ex.epi_base();
+      e.out_c8 = pl->dY5.p;
+      e.out_c8_ms = pl->dY5.ms;
+      e.out_c8_rcap = pl->dY5.rcap;
+      e.bias = pl->derived.p + pl->dec.head.bias_off;
+      e.bias_ms = pl->derived.ms;
+      e.tgt4 = v.tgt4.p;
+      e.tgt_ms = v.tgt4.ms;
+      e.tgt_rcap = pl->view.R0cap;
+      e.X = pl->X;
+      e.Xc = pl->view.Xc;
+      e.counts = v.counts.p;
+      e.counts_stride = (int)v.counts.ms;
+      e.coefs = v.coefs.p;
+      e.coefs_stride = (int)v.coefs.ms;
+      e.L = L;
+      e.part = v.dec_part.p;
+      e.part_ms = v.dec_part.ms;
+      e.part_rcap = pl->view.Rdcap;
+      e.write_dy = backward ? 1 : 0;
+      ex.gemm_nt(pl->dec.H.back(), 0, pl->dec.head, EPI_DECLOSS, e, CNT_RD, Rdb);
+    }
+    // The loss reduction is off the backward's critical path: it runs at the tail of the side stream
+    // (after that branch's backward), once the decoder log-density partials of the main stream exist.
+    after(side, ch.ev_side_fwd, cm);
+    on(side);
+    ex.phase = "";
+    ex.pre("loss");
+    launch_k(loss_partial_kernel, dim3(v.loss_slices, Ec), dim3(256), 0, ex.st, 2, v);
+    ex.chk();
+    ex.pre("loss_final");
+    launch_k(loss_final_kernel, dim3(Ec), dim3(32), 0, ex.st, 2, v);
+    ex.chk();
+    if (losses_out && ex.ok()) {
+      // losses buffer per model is padded to 256 B in the arena; the caller's is dense [E][8]
+      ex.err = cudaMemcpy2DAsync(losses_out + 8 * (size_t)m0, 8 * sizeof(float), v.losses.at(m0), v.losses.ms * sizeof(float),
+                                 8 * sizeof(float), Ec, cudaMemcpyDeviceToDevice, ex.st);
+    }
+    if (overlap) cudaEventRecord(ch.ev_side_bwd, side);  // everything the side stream does in this step
+    on(cm);
+    if (overlap && !backward) cudaStreamWaitEvent(cm, ch.ev_side_bwd, 0);
+
+    if (backward && ex.ok()) {
+      size_t bk = pl->has_fprop ? 2 : 0;  // buckets 0, 1 (decoder_z1, encoder_z3) were recorded by the side branch
+      auto bucket_done = [&]() { cudaEventRecord(pl->bucket_ev[bk++], ex.st); };
+      ex.phase = "dec.bwd";
+      ex.block_bwd(pl->dec, pl->dY5, v.Zdec, 0, pl->Z, v.dZdec.p, v.dZdec.ms, CNT_RD, Rdb);
+      bucket_done();
+      if (pl->has_clf) {
+        if (pl->has_fprop && (pl->sched & 2)) {
+          ++bk;  // ran on the side stream right after pz1_post (bucket event recorded there)
+          if (overlap) cudaStreamWaitEvent(cm, ch.ev_clf, 0);
+        } else {
+          if (overlap && pl->has_fprop) cudaStreamWaitEvent(cm, ch.ev_kfp, 0);
+          clf_bwd();
+          bucket_done();
+        }
+      }
+      if (pl->has_T) {
+        ex.phase = "T.bwd";
+        ex.pre("T_back");
+        launch_k(T_back_kernel, rows_grid(N + PAD_WARPS), dim3(ROW_THREADS), 0, ex.st, 2, v);
+        ex.chk();
+        ex.gemm_dx(v.dYT, pl->Tsh, EPI_STORE_F32, ex.epi_f32(v.dZ1T.p, v.dZ1T.ms, pl->Z, pl->Z, nullptr), CNT_LN, LNb);
+        ex.gemm_dw(v.dYT, v.Zdec, 0, pl->Tsh, CNT_LN, LNb, pl->arch.kind == DRVAE_KIND_PVAE ? CNT_NP : -1);
         bucket_done();
       }
-    }
-    if (pl->has_T) {
-      ex.phase = "T.bwd";
-      ex.pre("T_back");
-      launch_k(T_back_kernel, rows_grid(N + PAD_WARPS), dim3(ROW_THREADS), 0, ex.st, 2, v);
+      if (overlap) cudaStreamWaitEvent(cm, ch.ev_side_bwd, 0);  // join: q_back sums the side branch's gradients into q(z1|x1)
+      ex.phase = "enc.bwd";
+      ex.pre("q_back");
+      launch_k(q_back_kernel, rows_grid(N + PAD_WARPS), dim3(ROW_THREADS), 0, ex.st, 2, v);
       ex.chk();
-      ex.gemm_dx(v.dYT, pl->Tsh, EPI_STORE_F32, ex.epi_f32(v.dZ1T.p, v.dZ1T.ms, pl->Z, pl->Z, nullptr), CNT_LN, LNb);
-      ex.gemm_dw(v.dYT, v.Zdec, 0, pl->Tsh, CNT_LN, LNb, pl->arch.kind == DRVAE_KIND_PVAE ? CNT_NP : -1);
+      ex.block_bwd(pl->enc, v.dY2, v.Ain, 0, pl->X, nullptr, 0, CNT_R0, R0b);
       bucket_done();
     }
-    if (overlap) cudaStreamWaitEvent(st, pl->ev_side_bwd, 0);  // join: q_back sums the side branch's gradients into q(z1|x1)
-    ex.phase = "enc.bwd";
-    ex.pre("q_back");
-    launch_k(q_back_kernel, rows_grid(N + PAD_WARPS), dim3(ROW_THREADS), 0, ex.st, 2, v);
-    ex.chk();
-    ex.block_bwd(pl->enc, v.dY2, v.Ain, 0, pl->X, nullptr, 0, CNT_R0, R0b);
-    bucket_done();
-    if (ex.defer_dw && ex.ok()) {
-      DwaParams dp{};
-      dp.n_layers = (int)pl->dwa_layers.size();
-      dp.n_models = E;
-      dp.total_tiles = pl->dwa_tiles;
-      dp.layers = pl->d_dwa_layers;
-      dp.maps = pl->d_dwa_maps;
-      dp.tabs = pl->d_tabs;
-      dp.counts = v.counts.p;
-      dp.counts_stride = (int)v.counts.ms;
-      dp.adam_p = pl->params;
-      dp.adam_m = pl->adam_m;
-      dp.adam_v = pl->adam_v;
-      dp.state_ms = pl->P;
-      dp.drv = pl->derived.p;
-      dp.drv_ms = pl->derived.ms;
-      dp.adam = &pl->d_dyn->s.adam;
-      dp.dbg = pl->dbg;
-      ex.phase = "bwd";
-      ex.pre("dw_adam_all");
-      cudaError_t r = dwadam_launch(dp, ex.st);
-      ex.post();
-      if (r != cudaSuccess) ex.err = r;
-      pl->launches++;
+    if (c > 0) {  // join this range into the caller's stream
+      cudaEventRecord(ch.ev_end, cm);
+      cudaStreamWaitEvent(st, ch.ev_end, 0);
     }
+  }
+  ex.st = st;
+  ex.model0 = 0;
+  ex.Ec = E;
+  if (backward && ex.defer_dw && ex.ok()) {
+    DwaParams dp{};
+    dp.n_layers = (int)pl->dwa_layers.size();
+    dp.n_models = E;
+    dp.total_tiles = pl->dwa_tiles;
+    dp.layers = pl->d_dwa_layers;
+    dp.maps = pl->d_dwa_maps;
+    dp.tabs = pl->d_tabs;
+    dp.counts = v.counts.p;
+    dp.counts_stride = (int)v.counts.ms;
+    dp.adam_p = pl->params;
+    dp.adam_m = pl->adam_m;
+    dp.adam_v = pl->adam_v;
+    dp.state_ms = pl->P;
+    dp.drv = pl->derived.p;
+    dp.drv_ms = pl->derived.ms;
+    dp.adam = &pl->d_dyn->s.adam;
+    dp.dbg = pl->dbg;
+    ex.phase = "bwd";
+    ex.pre("dw_adam_all");
+    dp.trace = v.trace;
+    dp.trace_id = v.trace_id;
+    dp.stats = pl->d_dwa_stats;
+    cudaError_t r = dwadam_launch(dp, st);
+    ex.post();
+    if (r != cudaSuccess) ex.err = r;
+    pl->launches++;
   }
   if (!ex.ok()) return set_cuda_error("drvae step launch", ex.err);
   return 0;
@@ -1765,6 +1846,69 @@ extern "C" int drvae_infer(drvae_plan_t* pl, const float* x1, int N, const drvae
     }
   }
   if (!ex.ok()) return set_cuda_error("drvae_infer launch", ex.err);
+  return 0;
+}
+
+// Wait-cycle counters of the grouped dW+Adam kernel's roles (summed over CTAs and launches since the last reset):
+// out[8] = epilogue waits for the accumulator / for a state stage, loader waits for a free stage, storer waits for an
+// updated stage / for the TMA unit to read it, operand producer waits for a free slot, MMA waits for operands,
+// total CTA cycles.  enable != 0 switches the counters on (drops captured graphs), 0 reads them and switches off.
+extern "C" int drvae_debug_dwa_stats(drvae_plan_t* pl, int enable, unsigned long long* out) {
+  if (!pl) return set_error("drvae_debug_dwa_stats: null plan");
+  cudaError_t err = cudaDeviceSynchronize();
+  if (enable) {
+    if (!pl->d_dwa_stats && err == cudaSuccess) err = cudaMalloc(&pl->d_dwa_stats, 8 * sizeof(unsigned long long));
+    if (err == cudaSuccess) err = cudaMemset(pl->d_dwa_stats, 0, 8 * sizeof(unsigned long long));
+  } else if (pl->d_dwa_stats) {
+    if (out && err == cudaSuccess) err = cudaMemcpy(out, pl->d_dwa_stats, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaFree(pl->d_dwa_stats);
+    pl->d_dwa_stats = nullptr;
+  }
+  drop_graphs(pl);
+  if (err != cudaSuccess) return set_cuda_error("drvae_debug_dwa_stats", err);
+  return 0;
+}
+
+// ---- kernel trace: what really ran when (first CTA start / last CTA end of every launch, %globaltimer) ----
+extern "C" int drvae_trace_begin(drvae_plan_t* pl, int max_launches) {
+  if (!pl || max_launches < 1) return set_error("drvae_trace_begin: bad argument");
+  if (pl->d_trace) cudaFree(pl->d_trace);
+  if (pl->d_dwa_stats) cudaFree(pl->d_dwa_stats);
+  std::vector<unsigned long long> init(2 * (size_t)max_launches);
+  for (int i = 0; i < max_launches; ++i) init[2 * i] = ~0ULL, init[2 * i + 1] = 0ULL;
+  cudaError_t err = cudaMalloc(&pl->d_trace, sizeof(unsigned long long) * init.size());
+  if (err == cudaSuccess) err = cudaMemcpy(pl->d_trace, init.data(), sizeof(unsigned long long) * init.size(), cudaMemcpyHostToDevice);
+  if (err != cudaSuccess) return set_cuda_error("drvae_trace_begin", err);
+  pl->trace_cap = max_launches;
+  pl->trace_next = 0;
+  pl->trace_tags.clear();
+  pl->trace_on = true;
+  pl->trace_saved_graph = pl->graph_enabled;  // slots are per launch: replayed graphs would reuse them
+  pl->graph_enabled = false;
+  return 0;
+}
+// out: lines "index tag start_ns end_ns" (nanoseconds of the GPU's global timer)
+extern "C" int drvae_trace_end(drvae_plan_t* pl, char* out, int cap) {
+  if (!pl || !pl->trace_on) return set_error("drvae_trace_end: no trace in progress");
+  pl->trace_on = false;
+  pl->graph_enabled = pl->trace_saved_graph;
+  cudaError_t err = cudaDeviceSynchronize();
+  std::vector<unsigned long long> h(2 * (size_t)pl->trace_next);
+  if (err == cudaSuccess && !h.empty())
+    err = cudaMemcpy(h.data(), pl->d_trace, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost);
+  cudaFree(pl->d_trace);
+  pl->d_trace = nullptr;
+  if (err != cudaSuccess) return set_cuda_error("drvae_trace_end", err);
+  std::string txt;
+  char line[320];
+  for (int i = 0; i < pl->trace_next; ++i) {
+    snprintf(line, sizeof(line), "%d %s %llu %llu\n", i, pl->trace_tags[i].c_str(), h[2 * i], h[2 * i + 1]);
+    txt += line;
+  }
+  if (out && cap > 0) {
+    strncpy(out, txt.c_str(), cap - 1);
+    out[cap - 1] = 0;
+  }
   return 0;
 }
 

@@ -137,6 +137,7 @@ struct StepDyn {
 
 struct DevView {
   int kind, X, Y, Z, Z3, L, N, Ncap;
+  int model0;        // first ensemble member of this launch (a step may run sub-ranges of the ensemble as separate chains)
   int Xc;            // round_up(X, 16)
   int Zc, Z3c;       // chunk8 feature capacities of the latent buffers
   int Zs, Z3s;       // column of the logvar half in (mu | logvar) rows: round_up(Z, 16) / round_up(Z3, 16).  The two
@@ -202,6 +203,8 @@ struct DevView {
                             // effective (weight-normalised) copy in the derived arena
   MBuf<float> losses;  // [8]
   const StepDyn* dyn;  // per-step scalars (device memory)
+  unsigned long long* trace;  // kernel trace buffer (null: off) and this launch's slot
+  int trace_id;
 };
 
 constexpr int CLF_SPLITS = 32;       // row splits of the classifier weight gradient (ensemble-sized batches)

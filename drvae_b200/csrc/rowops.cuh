@@ -74,9 +74,10 @@ __device__ __forceinline__ int block_exclusive_scan(int x, int* warp_tot, int& t
 }
 
 __global__ void __launch_bounds__(ROWMAP_THREADS) rowmap_kernel(DevView v) {
+  TraceScope trace_scope(v.trace, v.trace_id);
   pdl_launch_dependents();
   pdl_wait();
-  const int m = blockIdx.x, t = threadIdx.x, N = v.N;
+  const int m = v.model0 + blockIdx.x, t = threadIdx.x, N = v.N;
   __shared__ int s_tot[33];
   const int* hx = v.has_pair ? v.has_x2.at(m) : nullptr;
   const int* hy = (v.has_clf && v.has_y.p) ? v.has_y.at(m) : nullptr;
@@ -171,10 +172,11 @@ constexpr int PREP_THREADS = 256;
 constexpr int PREP_SLAB = 256;
 
 __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(DevView v) {
+  TraceScope trace_scope(v.trace, v.trace_id);
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float tile[PREP_ROWS][PREP_SLAB + 1];
-  const int m = blockIdx.z, r0 = blockIdx.x * PREP_ROWS;
+  const int m = v.model0 + blockIdx.z, r0 = blockIdx.x * PREP_ROWS;
   const int* cnt = v.counts.at(m);
   const int N = cnt[CNT_N], R0 = cnt[CNT_R0];
   if (r0 >= pad128(R0)) return;
@@ -313,9 +315,10 @@ __device__ __forceinline__ float kl_term(float muq, float lvq, float mup, float 
 // 48-register budget of 5 blocks per SM, MAXJ is the general case
 template <int J>
 __global__ void __launch_bounds__(ROW_THREADS, 5) sample_q1_kernel(DevView v) {
+  TraceScope trace_scope(v.trace, v.trace_id);
   pdl_launch_dependents();
   pdl_wait();
-  const int m = blockIdx.y, lane = threadIdx.x & 31;
+  const int m = v.model0 + blockIdx.y, lane = threadIdx.x & 31;
   const int i = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int* cnt = v.counts.at(m);
   const int N = cnt[CNT_N], Np = cnt[CNT_NP], LN = cnt[CNT_LN], Fl = cnt[CNT_FL], F = cnt[CNT_F], Rd = cnt[CNT_RD];
@@ -401,9 +404,10 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) sample_q1_kernel(DevView v) {
 // ---------------------------------------------------------------------------------------------
 template <int J>
 __global__ void __launch_bounds__(ROW_THREADS, 5) T_post_kernel(DevView v) {
+  TraceScope trace_scope(v.trace, v.trace_id);
   pdl_launch_dependents();
   pdl_wait();
-  const int m = blockIdx.y, lane = threadIdx.x & 31;
+  const int m = v.model0 + blockIdx.y, lane = threadIdx.x & 31;
   const int i = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int* cnt = v.counts.at(m);
   const int N = cnt[CNT_N], Np = cnt[CNT_NP], LN = cnt[CNT_LN], LNp = cnt[CNT_LNP], Rd = cnt[CNT_RD];
@@ -471,9 +475,10 @@ __device__ __forceinline__ void eval_decode(const DevView& v, int m, int e, int 
 }
 
 __global__ void __launch_bounds__(ROW_THREADS) z3_post_kernel(DevView v) {
+  TraceScope trace_scope(v.trace, v.trace_id);
   pdl_launch_dependents();
   pdl_wait();
-  const int m = blockIdx.y, lane = threadIdx.x & 31;
+  const int m = v.model0 + blockIdx.y, lane = threadIdx.x & 31;
   const int e = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int* cnt = v.counts.at(m);
   const int F = cnt[CNT_F], Fl = cnt[CNT_FL];
@@ -513,9 +518,10 @@ __device__ __forceinline__ float eval_weight(const DevView& v, int m, int l, int
 // decoder_z1 heads (dY9) and towards q1 (dQ1e).  DrVAE.py:352-355, VFAE.py:253-256.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(ROW_THREADS) pz1_post_kernel(DevView v) {
+  TraceScope trace_scope(v.trace, v.trace_id);
   pdl_launch_dependents();
   pdl_wait();
-  const int m = blockIdx.y, lane = threadIdx.x & 31;
+  const int m = v.model0 + blockIdx.y, lane = threadIdx.x & 31;
   const int e = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int* cnt = v.counts.at(m);
   const int N = cnt[CNT_N], F = cnt[CNT_F], Fl = cnt[CNT_FL];
@@ -559,9 +565,10 @@ __global__ void __launch_bounds__(ROW_THREADS) pz1_post_kernel(DevView v) {
 // decoder_z1 input gradient) + the direct prior-KL gradient.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(ROW_THREADS) z3_back_kernel(DevView v) {
+  TraceScope trace_scope(v.trace, v.trace_id);
   pdl_launch_dependents();
   pdl_wait();
-  const int m = blockIdx.y, lane = threadIdx.x & 31;
+  const int m = v.model0 + blockIdx.y, lane = threadIdx.x & 31;
   const int e = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int* cnt = v.counts.at(m);
   const int N = cnt[CNT_N], F = cnt[CNT_F], Fl = cnt[CNT_FL];
@@ -597,9 +604,10 @@ __global__ void __launch_bounds__(ROW_THREADS) z3_back_kernel(DevView v) {
 // grid (ceil(LNcap / ROW_WARPS), n_models), one warp per stacked row r = l*N + i
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(ROW_THREADS) clf_back_kernel(DevView v) {
+  TraceScope trace_scope(v.trace, v.trace_id);
   pdl_launch_dependents();
   pdl_wait();
-  const int m = blockIdx.y, lane = threadIdx.x & 31;
+  const int m = v.model0 + blockIdx.y, lane = threadIdx.x & 31;
   const int r = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int* cnt = v.counts.at(m);
   const int N = cnt[CNT_N], LN = cnt[CNT_LN], Fl = cnt[CNT_FL];
@@ -655,9 +663,10 @@ __global__ void __launch_bounds__(ROW_THREADS) clf_back_kernel(DevView v) {
 // towards q2 (dQ2) and the residual / classifier contributions to d z1 (DZ1).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(ROW_THREADS, 5) T_back_kernel(DevView v) {
+  TraceScope trace_scope(v.trace, v.trace_id);
   pdl_launch_dependents();
   pdl_wait();
-  const int m = blockIdx.y, lane = threadIdx.x & 31;
+  const int m = v.model0 + blockIdx.y, lane = threadIdx.x & 31;
   const int i = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int* cnt = v.counts.at(m);
   const int N = cnt[CNT_N], Np = cnt[CNT_NP], LN = cnt[CNT_LN], LNp = cnt[CNT_LNP];
@@ -724,9 +733,10 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) T_back_kernel(DevView v) {
 // q(z2|x2) rows.  Collects every path into z1 / z2 samples and the direct KL gradients.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(ROW_THREADS, 5) q_back_kernel(DevView v) {
+  TraceScope trace_scope(v.trace, v.trace_id);
   pdl_launch_dependents();
   pdl_wait();
-  const int m = blockIdx.y, lane = threadIdx.x & 31;
+  const int m = v.model0 + blockIdx.y, lane = threadIdx.x & 31;
   const int i = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int* cnt = v.counts.at(m);
   const int N = cnt[CNT_N], Np = cnt[CNT_NP], LN = cnt[CNT_LN], R0 = cnt[CNT_R0], Fl = cnt[CNT_FL];
@@ -794,9 +804,10 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) q_back_kernel(DevView v) {
 // two stages (row-split partials, then a fixed-order reduction) -> deterministic
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) clf_grad_partial_kernel(DevView v) {
+  TraceScope trace_scope(v.trace, v.trace_id);
   pdl_launch_dependents();
   pdl_wait();
-  const int m = blockIdx.y, split = blockIdx.x;
+  const int m = v.model0 + blockIdx.y, split = blockIdx.x;
   const int LN = v.counts.at(m)[CNT_LN];
   const int width = v.clf_in + 1;
   for (int t = threadIdx.x; t < width; t += 256) {
@@ -825,9 +836,10 @@ __global__ void __launch_bounds__(256) clf_grad_partial_kernel(DevView v) {
 // grid (ceil(Y * (clf_in + 1) / 8), n_models), block 256: one warp per gradient element, lanes over the row splits
 // (lane l sums splits l, l + 32, ... in order, then a fixed shuffle tree -> deterministic)
 __global__ void __launch_bounds__(256) clf_grad_reduce_kernel(DevView v) {
+  TraceScope trace_scope(v.trace, v.trace_id);
   pdl_launch_dependents();
   pdl_wait();
-  const int m = blockIdx.y, lane = threadIdx.x & 31;
+  const int m = v.model0 + blockIdx.y, lane = threadIdx.x & 31;
   const int width = v.clf_in + 1;
   const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (k >= v.Y * width) return;
@@ -895,7 +907,7 @@ __device__ __forceinline__ void infer_emit_proba(const DevView& v, const InferVi
 
 // z1 = mu(q(z1|x1)); stage it for the p(z2|z1) and decoder GEMMs.  One warp per row.
 __global__ void __launch_bounds__(ROW_THREADS) infer_z1_kernel(DevView v, InferView o, int rows_dec) {
-  const int m = blockIdx.y, lane = threadIdx.x & 31;
+  const int m = v.model0 + blockIdx.y, lane = threadIdx.x & 31;
   const int r = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int N = v.N;
   if (r >= N) {
@@ -927,7 +939,7 @@ __global__ void __launch_bounds__(ROW_THREADS) infer_z1_kernel(DevView v, InferV
 
 // z2 = mu(p(z2|z1)) = z1 + z1 W^T + b; classifier on [z1, z2 - z1].
 __global__ void __launch_bounds__(ROW_THREADS) infer_z2_kernel(DevView v, InferView o) {
-  const int m = blockIdx.y, lane = threadIdx.x & 31;
+  const int m = v.model0 + blockIdx.y, lane = threadIdx.x & 31;
   const int r = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
   const int N = v.N;
   if (r >= N) return;
@@ -972,10 +984,11 @@ __device__ __forceinline__ float block_sum_256(float x, float* sm) {
 
 // grid (loss_slices, n_models): slice s reduces rows s, s + slices, ... of every per-row term in a fixed order
 __global__ void __launch_bounds__(256) loss_partial_kernel(DevView v) {
+  TraceScope trace_scope(v.trace, v.trace_id);
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float sm[256];
-  const int m = blockIdx.y, t = threadIdx.x;
+  const int m = v.model0 + blockIdx.y, t = threadIdx.x;
   const int stride = 256 * gridDim.x, first = blockIdx.x * 256 + t;
   const int* cnt = v.counts.at(m);
   const int LN = cnt[CNT_LN], LNp = cnt[CNT_LNP], Rd = cnt[CNT_RD], F = cnt[CNT_F], R0 = cnt[CNT_R0];
@@ -1015,9 +1028,10 @@ __global__ void __launch_bounds__(256) loss_partial_kernel(DevView v) {
 
 // grid n_models, one warp: fixed-order sum of the slices, then the reference's normalisation
 __global__ void __launch_bounds__(32) loss_final_kernel(DevView v) {
+  TraceScope trace_scope(v.trace, v.trace_id);
   pdl_launch_dependents();
   pdl_wait();
-  const int m = blockIdx.x;
+  const int m = v.model0 + blockIdx.x;
   if (threadIdx.x != 0) return;
   float a[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int s = 0; s < v.loss_slices; ++s)

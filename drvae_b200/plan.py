@@ -281,6 +281,9 @@ class Plan:
     def set_gemm_impl(self, impl):
         _lib.check(self.lib.drvae_set_gemm_impl(self.h, {"tc": 0, "simt": 1}[impl]))
 
+    def set_chains(self, chains):
+        _lib.check(self.lib.drvae_set_chains(self.h, int(chains)), "set_chains")
+
     def debug_side_delay(self, cycles):
         _lib.check(self.lib.drvae_debug_side_delay(self.h, int(cycles)), "debug_side_delay")
 
@@ -298,6 +301,27 @@ class Plan:
         for line in buf.value.decode().splitlines():
             tag, n, ms = line.rsplit(" ", 2)
             out[tag] = (int(n), float(ms))
+        return out
+
+    def dwa_stats(self, enable):
+        """enable=True: start counting; False: -> dict of the grouped dW+Adam kernel's role wait cycles."""
+        out = (ctypes.c_ulonglong * 8)()
+        _lib.check(self.lib.drvae_debug_dwa_stats(self.h, int(bool(enable)), out), "dwa_stats")
+        names = ("epi_wait_acc", "epi_wait_state", "loader_wait_empty", "storer_wait_done", "storer_wait_read",
+                 "producer_wait_empty", "mma_wait_full", "cta_total")
+        return None if enable else dict(zip(names, [int(x) for x in out]))
+
+    def trace_begin(self, max_launches=4096):
+        _lib.check(self.lib.drvae_trace_begin(self.h, int(max_launches)), "trace_begin")
+
+    def trace_end(self):
+        """-> [(index, tag, start_ns, end_ns)] for every kernel launched since trace_begin()."""
+        buf = ctypes.create_string_buffer(1 << 20)
+        _lib.check(self.lib.drvae_trace_end(self.h, buf, len(buf)), "trace_end")
+        out = []
+        for line in buf.value.decode().splitlines():
+            i, tag, a, b = line.rsplit(" ", 3)
+            out.append((int(i), tag, int(a), int(b)))
         return out
 
     def workspace_bytes(self):

@@ -169,6 +169,10 @@ int drvae_push_scalars(drvae_plan_t* plan, const drvae_noise_t* noise, const drv
                        void* stream);
 int drvae_set_external_scalars(drvae_plan_t* plan, int enable);
 long long drvae_plan_graph_replays(const drvae_plan_t* plan);
+/* Step schedule: the ensemble is cut into `chains` contiguous model ranges whose forward + input-gradient chains run on
+ * separate streams (their latency-bound kernels overlap); the grouped weight-gradient + Adam launch at the end covers
+ * all of them.  Default 1.  Results do not depend on it (bit-identical). */
+int drvae_set_chains(drvae_plan_t* plan, int chains);
 
 /* Introspection for tests and bench.py */
 int drvae_set_gemm_impl(drvae_plan_t* plan, int impl);   /* 0 tcgen05 (default), 1 SIMT validation kernel */
@@ -177,6 +181,16 @@ long long drvae_plan_launch_count(const drvae_plan_t* plan); /* kernels launched
  * receives lines "phase:kernel launches total_ms". */
 int drvae_profile_begin(drvae_plan_t* plan);
 int drvae_profile_end(drvae_plan_t* plan, char* out, int cap);
+/* Kernel trace: between begin and end every kernel the plan launches stamps the GPU's global timer when its first
+ * CTA starts and when its last CTA leaves (graphs are off meanwhile: slots are per launch).  `out` receives lines
+ * "index phase:kernel start_ns end_ns": the step as it really ran, streams overlapping (tools/trace_step.py). */
+int drvae_trace_begin(drvae_plan_t* plan, int max_launches);
+int drvae_trace_end(drvae_plan_t* plan, char* out, int cap);
+/* Wait-cycle counters of the grouped weight-gradient + Adam kernel's roles: enable != 0 starts counting; enable == 0
+ * copies out[8] = {epilogue waits for accumulator, epilogue waits for a state stage, state loader waits for a free
+ * stage, storer waits for an updated stage, storer waits for the TMA unit to read it, operand producer waits for a
+ * free slot, MMA waits for operands, total CTA cycles} (host memory) and stops. */
+int drvae_debug_dwa_stats(drvae_plan_t* plan, int enable, unsigned long long* out);
 /* Barrier-wait cycle counters of the GEMM kernel roles, [3 modes][8 epilogues][8 counters]; only in libraries built
  * with -DGEMM_PROFILE_WAITS (tools/wait_profile.py), otherwise an error status. */
 int drvae_debug_wait_stats(unsigned long long* out, int reset);

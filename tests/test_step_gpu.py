@@ -710,3 +710,28 @@ def test_pvae_without_pairs_leaves_the_perturbation_block_untouched(path):
         else:
             assert not torch.equal(new[k].cpu(), sd[k]), k
             assert (new[k].cpu() - ref[k]).abs().max() <= 2.2 * 5e-4, k  # two Adam steps of lr 5e-4, signs may differ
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_model_range_chains_do_not_change_results(kind):
+    """The step may run sub-ranges of the ensemble as separate stream chains (drvae_set_chains); the grouped
+    weight-gradient + Adam launch at the end covers all models.  1, 2 and 3 ranges over 6 models (distinct weights and
+    batches), plain launches and graph replays: losses and parameters are bit-identical."""
+    arch, N, E = ARCH["tiny"], 36, 6
+    sds = [init_state_dict(kind, seed=SEED_MODEL + m, **arch) for m in range(E)]
+    batches = [batch_fields(kind, orc.synthetic_batch(N, arch["dim_x"], seed=20 + m)) for m in range(E)]
+    big = {k: torch.stack([b[k] for b in batches]).contiguous().cuda() for k in batches[0]}
+    res = {}
+    for chains in (1, 2, 3):
+        plan = Plan(kind, L=L, max_batch=N, n_models=E, **arch)
+        plan.set_chains(chains)
+        for m in range(E):
+            plan.load_state_dict(sds[m], model=m)
+        out = [plan.train_step(big, plan.hparams(step=it, beta_pert=anneal_coef(it, 1, 0)), seed=11).cpu().clone() for it in range(5)]
+        ev = plan.loss_forward(big, plan.hparams(step=5, training=False), seed=11).cpu().clone()
+        res[chains] = (torch.stack(out), plan.params.cpu().clone(), ev)
+        assert plan.graph_replays() >= 2
+    for chains in (2, 3):
+        for a, b in zip(res[1], res[chains]):
+            assert torch.equal(a, b), chains
+    assert not torch.equal(res[1][0][0, 0], res[1][0][0, 1])  # members really differ

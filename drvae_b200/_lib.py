@@ -65,7 +65,7 @@ EXPORTS = ["drvae_last_error", "drvae_plan_create", "drvae_plan_destroy", "drvae
            "drvae_loss_forward", "drvae_grad_step", "drvae_adam_step", "drvae_infer", "drvae_set_gemm_impl",
            "drvae_plan_launch_count", "drvae_debug_buffer", "drvae_debug_gemm", "drvae_profile_begin",
            "drvae_profile_end", "drvae_plan_num_buckets", "drvae_plan_bucket_info", "drvae_stream_wait_bucket", "drvae_set_graph", "drvae_plan_graph_replays", "drvae_debug_wait_stats",
-           "drvae_push_scalars", "drvae_set_external_scalars", "drvae_debug_side_delay", "drvae_plan_tensor_ld", "drvae_set_chains", "drvae_trace_begin", "drvae_trace_end", "drvae_debug_dwa_stats"]
+           "drvae_push_scalars", "drvae_set_external_scalars", "drvae_debug_side_delay", "drvae_plan_tensor_ld", "drvae_set_chains", "drvae_trace_begin", "drvae_trace_end", "drvae_debug_dwa_stats", "drvae_set_infer_precision"]
 
 
 def load():
@@ -127,6 +127,8 @@ def load():
     lib.drvae_debug_wait_stats.argtypes = [c_void_p, c_int]
     lib.drvae_debug_dwa_stats.restype = c_int
     lib.drvae_debug_dwa_stats.argtypes = [c_void_p, c_int, c_void_p]
+    lib.drvae_set_infer_precision.restype = c_int
+    lib.drvae_set_infer_precision.argtypes = [c_void_p, c_int]
     lib.drvae_trace_begin.restype = c_int
     lib.drvae_trace_begin.argtypes = [c_void_p, c_int]
     lib.drvae_trace_end.restype = c_int

@@ -13,6 +13,7 @@
 #include "errors.h"
 #include "dwadam.cuh"
 #include "gemm.cuh"
+#include "infer_f32.cuh"
 #include "optim.cuh"
 #include "plan.h"
 #include "rowops.cuh"
@@ -110,8 +111,8 @@ struct drvae_plan {
   struct Chain {
     cudaStream_t main = nullptr, side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_qy = nullptr, ev_side_fwd = nullptr, ev_side_bwd = nullptr, ev_begin = nullptr, ev_eps = nullptr,
-                ev_clf = nullptr, ev_kfp = nullptr, ev_end = nullptr;
-    cudaEvent_t* all() { return &ev_fork; }  // 9 consecutive events
+                ev_clf = nullptr, ev_kfp = nullptr, ev_end = nullptr, ev_side_end = nullptr;
+    cudaEvent_t* all() { return &ev_fork; }  // 10 consecutive events
   };
   Chain chain[MAX_CHAINS];
   int chains = 1;             // model ranges per step (DRVAE_B200_CHAINS; default chosen from n_models at creation)
@@ -129,6 +130,10 @@ struct drvae_plan {
   bool dwa_ok = false;       // every layer fits the kernel's layout conditions and the state is bound
   unsigned long long* d_dwa_stats = nullptr;  // drvae_debug_dwa_stats
   bool dwa_enabled = true;   // measurement knob (DRVAE_B200_DWADAM=0: per-layer fused kernels of round 1)
+  // fp32 inference path (infer_f32.cuh): on by default (exact thresholded predictions); scratch allocated on first use
+  bool infer_fp32 = true;
+  float* f32ws = nullptr;
+  size_t f32ws_floats = 0;
   // kernel trace (drvae_trace_begin / _end): device slots {first CTA start, last CTA end} per launch, tags on the host
   unsigned long long* d_trace = nullptr;
   int trace_cap = 0, trace_next = 0;
@@ -561,7 +566,7 @@ extern "C" int drvae_plan_create(const drvae_arch_t* a, int n_models, drvae_plan
   for (auto& ch : pl->chain) {
     cudaStreamCreateWithFlags(&ch.main, cudaStreamNonBlocking);
     cudaStreamCreateWithFlags(&ch.side, cudaStreamNonBlocking);
-    for (int i = 0; i < 9; ++i) cudaEventCreateWithFlags(ch.all() + i, cudaEventDisableTiming);
+    for (int i = 0; i < 10; ++i) cudaEventCreateWithFlags(ch.all() + i, cudaEventDisableTiming);
   }
   cudaEventCreateWithFlags(&pl->ev_begin, cudaEventDisableTiming);
   pl->bucket_ev.resize(pl->buckets.size());
@@ -671,11 +676,12 @@ extern "C" int drvae_plan_destroy(drvae_plan_t* pl) {
   if (pl->d_wn_rows) cudaFree(pl->d_wn_rows);
   if (pl->d_dwa_layers) cudaFree(pl->d_dwa_layers);
   if (pl->d_dwa_maps) cudaFree(pl->d_dwa_maps);
+  if (pl->f32ws) cudaFree(pl->f32ws);
   if (pl->d_trace) cudaFree(pl->d_trace);
   if (pl->d_dwa_stats) cudaFree(pl->d_dwa_stats);
   for (auto& ev : pl->bucket_ev) cudaEventDestroy(ev);
   for (auto& ch : pl->chain) {
-    for (int i = 0; i < 9; ++i)
+    for (int i = 0; i < 10; ++i)
       if (ch.all()[i]) cudaEventDestroy(ch.all()[i]);
     if (ch.main) cudaStreamDestroy(ch.main);
     if (ch.side) cudaStreamDestroy(ch.side);
@@ -1445,6 +1451,8 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
         ex.phase = "z3.bwd";
         ex.block_bwd(pl->z3b, v.dY7, v.Z1e, 0, pl->Z, v.dZ1e.p, v.dZ1e.ms, CNT_F, Fb);
         cudaEventRecord(pl->bucket_ev[1], ex.st);
+        // what q_back needs from this stream; the loss reduction that follows here is joined at the end of the step only
+        if (overlap) cudaEventRecord(ch.ev_side_bwd, ex.st);
       }
       on(cm);
     }
@@ -1490,9 +1498,8 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
       ex.err = cudaMemcpy2DAsync(losses_out + 8 * (size_t)m0, 8 * sizeof(float), v.losses.at(m0), v.losses.ms * sizeof(float),
                                  8 * sizeof(float), Ec, cudaMemcpyDeviceToDevice, ex.st);
     }
-    if (overlap) cudaEventRecord(ch.ev_side_bwd, side);  // everything the side stream does in this step
+    if (overlap) cudaEventRecord(ch.ev_side_end, side);  // everything the side stream does in this step
     on(cm);
-    if (overlap && !backward) cudaStreamWaitEvent(cm, ch.ev_side_bwd, 0);
 
     if (backward && ex.ok()) {
       size_t bk = pl->has_fprop ? 2 : 0;  // buckets 0, 1 (decoder_z1, encoder_z3) were recorded by the side branch
@@ -1527,6 +1534,7 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
       ex.block_bwd(pl->enc, v.dY2, v.Ain, 0, pl->X, nullptr, 0, CNT_R0, R0b);
       bucket_done();
     }
+    if (overlap) cudaStreamWaitEvent(cm, ch.ev_side_end, 0);
     if (c > 0) {  // join this range into the caller's stream
       cudaEventRecord(ch.ev_end, cm);
       cudaStreamWaitEvent(st, ch.ev_end, 0);
@@ -1774,11 +1782,108 @@ extern "C" int drvae_set_graph(drvae_plan_t* pl, int enable) {
 }
 extern "C" long long drvae_plan_graph_replays(const drvae_plan_t* pl) { return pl ? pl->graph_replays : -1; }
 
+namespace {
+
+// deterministic mu-path in fp32 from the master parameters (see infer_f32.cuh)
+int run_infer_fp32(drvae_plan* pl, const float* x1, int N, const drvae_infer_out_t* out, cudaStream_t st) {
+  const int E = pl->E, X = pl->X, Z = pl->Z, Y = pl->Y;
+  int maxw = Z;
+  for (const MlpBlock* b : {&pl->enc, &pl->dec})
+    for (int w : b->widths) maxw = std::max(maxw, w);
+  // scratch per model: two activation buffers [N][maxw], z1 / z2 / one spare [N][Z]
+  const size_t per = (size_t)pl->Ncap * (2 * (size_t)maxw + 3 * (size_t)Z);
+  if (pl->f32ws_floats < per * E) {
+    if (pl->f32ws) cudaFree(pl->f32ws);
+    pl->f32ws = nullptr;
+    cudaError_t err = cudaMalloc(&pl->f32ws, per * E * sizeof(float));
+    if (err != cudaSuccess) return set_cuda_error("drvae_infer: fp32 scratch", err);
+    pl->f32ws_floats = per * E;
+  }
+  float* Ha = pl->f32ws;
+  float* Hb = Ha + (size_t)pl->Ncap * maxw;
+  float* z1s = Hb + (size_t)pl->Ncap * maxw;
+  float* z2s = z1s + (size_t)pl->Ncap * Z;
+  const long long ws_ms = (long long)per;
+  cudaError_t lerr = cudaSuccess;
+  auto lin = [&](const float* Xp, long long x_ms, int ldx, int w_off, int b_off, int ldw, int nout, int K, float bconst, int act,
+                 const float* resid, long long r_ms, int ldr, float* o, long long o_ms, int ldo) {
+    LinF32 a{};
+    a.X = Xp, a.x_ms = x_ms, a.ldx = ldx;
+    a.W = pl->params + w_off, a.b = pl->params + b_off, a.p_ms = pl->P, a.ldw = ldw;
+    a.bconst = bconst, a.resid = resid, a.r_ms = r_ms, a.ldr = ldr;
+    a.out = o, a.o_ms = o_ms, a.ldo = ldo;
+    a.rows = N, a.nout = nout, a.K = K, a.act = act;
+    linear_f32_kernel<<<dim3(cdiv(nout, 64), cdiv(N, 64), E), 256, 0, st>>>(a);
+    pl->launches++;
+    if (lerr == cudaSuccess) lerr = cudaGetLastError();
+  };
+  // hidden layers of a block: leaves (h, h_ms, h_ld) on the last activation
+  auto hidden = [&](const MlpBlock& b, const float* in, long long in_ms, int in_ld, const float*& h, long long& h_ms, int& h_ld) {
+    h = in, h_ms = in_ms, h_ld = in_ld;
+    for (size_t i = 0; i < b.hidden.size(); ++i) {
+      const Shadow& W = b.hidden[i];
+      float* dst = (h == Ha) ? Hb : Ha;
+      lin(h, h_ms, h_ld, W.w_off[0], W.b_off[0], W.ld, b.widths[i], W.kin, 0.f, ACT_ELU, nullptr, 0, 0, dst, ws_ms, maxw);
+      h = dst, h_ms = ws_ms, h_ld = maxw;
+    }
+  };
+  const long long outZ = (long long)N * Z, outX = (long long)N * X;
+  const float* h;
+  long long h_ms;
+  int h_ld;
+  hidden(pl->enc, x1, (long long)N * X, X, h, h_ms, h_ld);
+  const Shadow& eh = pl->enc.head;
+  float* z1 = out->z1_mu ? out->z1_mu : z1s;
+  const long long z1_ms = out->z1_mu ? outZ : ws_ms;
+  lin(h, h_ms, h_ld, eh.w_off[0], eh.b_off[0], eh.ld, Z, eh.kin, 0.f, ACT_NONE, nullptr, 0, 0, z1, z1_ms, Z);
+  if (out->z1_lv) lin(h, h_ms, h_ld, eh.w_off[1], eh.b_off[1], eh.ld, Z, eh.kin, -2.f, ACT_NONE, nullptr, 0, 0, out->z1_lv, outZ, Z);
+  float* z2 = nullptr;
+  long long z2_ms = 0;
+  if (pl->has_T) {
+    const Shadow& T = pl->Tsh;  // blocks.py:349-361: mu = z + z W_mu^T + bias_mu, logvar = lin(z) - 2
+    z2 = out->z2_mu ? out->z2_mu : z2s;
+    z2_ms = out->z2_mu ? outZ : ws_ms;
+    lin(z1, z1_ms, Z, T.w_off[0], T.b_off[0], T.ld, Z, Z, 0.f, ACT_NONE, z1, z1_ms, Z, z2, z2_ms, Z);
+    if (out->z2_lv) lin(z1, z1_ms, Z, T.w_off[1], T.b_off[1], T.ld, Z, Z, -2.f, ACT_NONE, nullptr, 0, 0, out->z2_lv, outZ, Z);
+  }
+  if (pl->has_clf && (out->proba || out->pred)) {
+    if (pl->has_T && z2_ms != z1_ms) return set_error("drvae_infer: z1_mu and z2_mu must both be given or both be null");
+    ClfF32 c{};
+    c.z1 = z1, c.z2 = pl->has_T ? z2 : nullptr, c.z_ms = z1_ms;
+    c.W = pl->params + pl->clf_w_off, c.b = pl->params + pl->clf_b_off, c.p_ms = pl->P;
+    c.ldw = pl->view.clf_ld, c.Z = Z, c.Y = Y, c.N = N;
+    c.proba = out->proba, c.pred = out->pred;
+    clf_f32_kernel<<<dim3(cdiv(N, 8), E), 256, 0, st>>>(c);
+    pl->launches++;
+    if (lerr == cudaSuccess) lerr = cudaGetLastError();
+  }
+  const Shadow& dh = pl->dec.head;
+  for (int half = 0; half < (pl->has_T ? 2 : 1); ++half) {
+    float* mu = half == 0 ? out->px1_mu : out->px2_mu;
+    float* sg = half == 0 ? out->px1_sg : out->px2_sg;
+    if (!mu && !sg) continue;
+    hidden(pl->dec, half == 0 ? z1 : z2, half == 0 ? z1_ms : z2_ms, Z, h, h_ms, h_ld);
+    if (mu) lin(h, h_ms, h_ld, dh.w_off[0], dh.b_off[0], dh.ld, X, dh.kin, 0.f, ACT_NONE, nullptr, 0, 0, mu, outX, X);
+    if (sg) lin(h, h_ms, h_ld, dh.w_off[1], dh.b_off[1], dh.ld, X, dh.kin, 0.f, ACT_SOFTPLUS_EPS, nullptr, 0, 0, sg, outX, X);
+  }
+  if (lerr != cudaSuccess) return set_cuda_error("drvae_infer (fp32) launch", lerr);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int drvae_set_infer_precision(drvae_plan_t* pl, int fp32) {
+  if (!pl) return set_error("drvae_set_infer_precision: null plan");
+  pl->infer_fp32 = fp32 != 0;
+  return 0;
+}
+
 extern "C" int drvae_infer(drvae_plan_t* pl, const float* x1, int N, const drvae_infer_out_t* out, void* stream) {
   if (!pl || !x1 || !out) return set_error("drvae_infer: null argument");
   if (!pl->params) return set_error("drvae_infer: plan has no bound parameters");
   if (N < 1 || N > pl->Ncap) return set_error("drvae_infer: N exceeds the plan's max_batch");
   cudaStream_t st = (cudaStream_t)stream;
+  if (pl->infer_fp32 && !pl->wn) return run_infer_fp32(pl, x1, N, out, st);
   drvae_hparams_t hp{};
   if (!pl->shadows_valid) {
     int rc = run_adam(pl, &hp, 0, st);
@@ -1873,7 +1978,6 @@ extern "C" int drvae_debug_dwa_stats(drvae_plan_t* pl, int enable, unsigned long
 extern "C" int drvae_trace_begin(drvae_plan_t* pl, int max_launches) {
   if (!pl || max_launches < 1) return set_error("drvae_trace_begin: bad argument");
   if (pl->d_trace) cudaFree(pl->d_trace);
-  if (pl->d_dwa_stats) cudaFree(pl->d_dwa_stats);
   std::vector<unsigned long long> init(2 * (size_t)max_launches);
   for (int i = 0; i < max_launches; ++i) init[2 * i] = ~0ULL, init[2 * i + 1] = 0ULL;
   cudaError_t err = cudaMalloc(&pl->d_trace, sizeof(unsigned long long) * init.size());

@@ -259,6 +259,10 @@ class Plan:
             _lib.check(self.lib.drvae_infer(self.h, _ptr(x1), int(N), ctypes.byref(out), self._stream()), "infer")
         return res
 
+    def set_infer_precision(self, fp32=True):
+        """fp32 (default): exact thresholded predictions; False: bf16 tensor-core inference."""
+        _lib.check(self.lib.drvae_set_infer_precision(self.h, int(bool(fp32))), "set_infer_precision")
+
     def grad_buckets(self):
         """[(offset, count)] of the flat gradient in the order drvae_grad_step completes them."""
         out = []

@@ -154,6 +154,11 @@ int drvae_plan_num_buckets(const drvae_plan_t* plan);
 int drvae_plan_bucket_info(const drvae_plan_t* plan, int index, long long* offset, long long* count);
 int drvae_stream_wait_bucket(drvae_plan_t* plan, int index, void* stream);
 int drvae_infer(drvae_plan_t* plan, const float* x1, int N, const drvae_infer_out_t* out, void* stream);
+/* Inference arithmetic.  fp32 != 0 (default): the mu-path is evaluated with fp32 operands and fp32 accumulation from
+ * the master parameters, so that class probabilities agree with the reference to ~1e-6 and thresholded predictions
+ * match it exactly; 0: the bf16 tensor-core GEMMs of the training step (faster, probabilities within ~1e-3).  Plans
+ * with weight norm always use the tensor-core path. */
+int drvae_set_infer_precision(drvae_plan_t* plan, int fp32);
 
 /* Launch mechanism.  With graphs enabled (default) drvae_train_step / drvae_loss_forward replay their launch
  * sequence as a CUDA graph from the third call with the same (N, batch buffers, output buffer, stream) on;

@@ -26,8 +26,12 @@ TINY = dict(dim_x=40, dim_y=2, dim_z1=12, dim_z3=10, dim_z2=10, enc_z1=[24], dec
             dec_z1=[18])
 DEEP = dict(dim_x=40, dim_y=2, dim_z1=12, dim_z3=10, dim_z2=10, enc_z1=[24, 20], dec_x=[16, 28], enc_z3=[20, 12],
             enc_z2=[20, 12], dec_z1=[18, 14])
-# (name, architecture, rows, weight_norm)
-CASES = [("tiny", TINY, 24, False), ("deep", DEEP, 24, False), ("readme", README, 150, False), ("tiny_wn", TINY, 24, True)]
+# (name, architecture, rows, weight_norm, model kinds)
+ALL = ("drvae", "pvae", "vfae")
+CASES = [("tiny", TINY, 24, False, ALL), ("deep", DEEP, 24, False, ALL), ("readme", README, 150, False, ALL),
+         ("tiny_wn", TINY, 24, True, ALL),
+         # the shapes bench.py times: README architecture with weight norm, and the 8192-row minibatch of BASELINE configs[3]
+         ("readme_wn", README, 150, True, ALL), ("readme8192", README, 8192, False, ("drvae", "vfae"))]
 SEED_MODEL, SEED_TAPE, L = 123, 777, 2
 SAMPLE = 257
 
@@ -41,10 +45,10 @@ def main():
     os.makedirs(out_dir, exist_ok=True)
     torch.set_num_threads(4)
     only = sys.argv[1:]
-    for cname, arch, N, wn in CASES:
+    for cname, arch, N, wn, kinds in CASES:
         if only and cname not in only:
             continue
-        for kind in ("drvae", "pvae", "vfae"):
+        for kind in kinds:
             model = rh.build_reference_model(kind, arch, seed=SEED_MODEL, L=L, weight_norm=wn)
             if wn:
                 # g is initialised to exactly 1 (layers.py:22): perturb it reproducibly so the g/||v|| scale and its
@@ -58,14 +62,14 @@ def main():
             batch = orc.synthetic_batch(N, arch["dim_x"])
             cfg = orc.default_cfg(kind, L=L)
             om = orc.OracleModel(sd0, cfg)
-            full = cname != "readme"
+            full = not cname.startswith("readme")
             rec = {}
             rec["meta/N"] = np.array(N)
             rec["meta/L"] = np.array(L)
             for k, v in sd0.items():
                 a = v.numpy()
                 rec["sdsum/" + k] = np.array([a.sum(dtype=np.float64), np.abs(a).sum(dtype=np.float64)])
-                if full:
+                if full or k.endswith(".g"):  # (the perturbed g vectors are small: kept so that tests can rebuild the weights)
                     rec["sd/" + k] = a
             # inference on the initial weights
             fw = rh.reference_forward(model, batch["x1"])

@@ -32,7 +32,7 @@ class Arch(ctypes.Structure):
 
 class Batch(ctypes.Structure):
     _fields_ = [("x1", c_void_p), ("x2", c_void_p), ("y", c_void_p), ("has_x2", c_void_p), ("has_y", c_void_p),
-                ("N", c_int)]
+                ("N", c_int), ("row_index", c_void_p), ("dataset_rows", c_int)]
 
 
 class Noise(ctypes.Structure):

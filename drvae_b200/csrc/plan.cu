@@ -1151,12 +1151,15 @@ int fill_view(drvae_plan* pl, Exec& ex, const drvae_batch_t* b, const drvae_nois
   ex.N = N;
   v.N = N;
   v.need_grad = need_grad;
-  const long long rowsX = (long long)N * pl->X;
+  if (b->row_index && b->dataset_rows < 1) return set_error("drvae: batch.row_index needs dataset_rows >= 1");
+  const long long drows = b->row_index ? b->dataset_rows : N;  // rows per model in the caller's arrays
+  const long long rowsX = drows * pl->X;
   v.x1 = MBuf<const float>{b->x1, rowsX};
   v.x2 = MBuf<const float>{b->x2, rowsX};
-  v.y = MBuf<const int>{b->y, N};
-  v.has_x2 = MBuf<const int>{b->has_x2, N};
-  v.has_y = MBuf<const int>{b->has_y, N};
+  v.y = MBuf<const int>{b->y, drows};
+  v.has_x2 = MBuf<const int>{b->has_x2, drows};
+  v.has_y = MBuf<const int>{b->has_y, drows};
+  v.row_index = MBuf<const int>{b->row_index, N};
   const float* eps = (nz && nz->eps) ? nz->eps : pl->eps_own.p;
   const long long ems = (nz && nz->eps) ? pl->epsl.total : pl->eps_own.ms;
   v.eps_x1 = MBuf<const float>{eps + pl->epsl.off_x1, ems};
@@ -1631,7 +1634,8 @@ int step_entry(drvae_plan* pl, int seq, const drvae_batch_t* b, const drvae_nois
                          st != nullptr && st != cudaStreamLegacy && st != cudaStreamPerThread;
   if (graphable) {
     std::vector<long long> key = {seq, b->N, (long long)(size_t)b->x1, (long long)(size_t)b->x2, (long long)(size_t)b->y,
-                                  (long long)(size_t)b->has_x2, (long long)(size_t)b->has_y, (long long)(size_t)losses_out,
+                                  (long long)(size_t)b->has_x2, (long long)(size_t)b->has_y, (long long)(size_t)b->row_index,
+                                  (long long)b->dataset_rows, (long long)(size_t)losses_out,
                                   (long long)(size_t)st, hp->training, hp->add_noise};
     drvae_plan::GraphEntry& ge = pl->graphs[key];
     ge.last_use = ++pl->graph_clock;

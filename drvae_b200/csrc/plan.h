@@ -150,6 +150,7 @@ struct DevView {
   // batch (caller memory)
   MBuf<const float> x1, x2;
   MBuf<const int> y, has_x2, has_y;
+  MBuf<const int> row_index;  // optional [N] per model: the batch is rows row_index[i] of a device-resident dataset
   // ε (row indexed)
   MBuf<const float> eps_x1, eps_x2, eps_z1, eps_z2, eps_z2f, eps_z3;
   // own_noise: the input noise of x1 / x2 is drawn inside prep_kernel (same Philox keys as the ε

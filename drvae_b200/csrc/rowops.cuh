@@ -82,12 +82,14 @@ __global__ void __launch_bounds__(ROWMAP_THREADS) rowmap_kernel(DevView v) {
   const int* hx = v.has_pair ? v.has_x2.at(m) : nullptr;
   const int* hy = (v.has_clf && v.has_y.p) ? v.has_y.at(m) : nullptr;
   const int* yy = (v.has_clf && v.y.p) ? v.y.at(m) : nullptr;
+  const int* ri = v.row_index.p ? v.row_index.at(m) : nullptr;  // batch row -> dataset row (device-resident dataset)
   const int seg = (N + ROWMAP_THREADS - 1) / ROWMAP_THREADS;
   const int i0 = min(N, t * seg), i1 = min(N, i0 + seg);
   int np = 0, ne = 0, nl = 0;
   for (int i = i0; i < i1; ++i) {
-    const bool pr = hx && hx[i] != 0;
-    const bool lb = hy && hy[i] != 0;
+    const int di = ri ? ri[i] : i;
+    const bool pr = hx && hx[di] != 0;
+    const bool lb = hy && hy[di] != 0;
     np += pr;
     nl += lb;
     ne += v.has_fprop ? (lb ? 1 : v.Y) : 0;
@@ -129,9 +131,10 @@ __global__ void __launch_bounds__(ROWMAP_THREADS) rowmap_kernel(DevView v) {
   int* e_row = v.e_row.at(m);
   int* e_jj = v.e_jj.at(m);
   for (int i = i0; i < i1; ++i) {
-    const bool pr = hx && hx[i] != 0;
-    const bool lb = hy && hy[i] != 0;
-    int yi = yy ? yy[i] : 0;
+    const int di = ri ? ri[i] : i;
+    const bool pr = hx && hx[di] != 0;
+    const bool lb = hy && hy[di] != 0;
+    int yi = yy ? yy[di] : 0;
     yi = min(max(yi, 0), v.Y - 1);
     pair_of[i] = pr ? p : -1;
     if (pr) row_of_pair[p++] = i;
@@ -195,12 +198,12 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_kernel(DevView v) {
       int seg = 0, nrow = 0;  // noise keys: draw kind and row inside this model's minibatch
       if (r < N) {
         nrow = r;
-        src = v.x1.at(m) + (long long)r * v.X;
+        src = v.x1.at(m) + (long long)(v.row_index.p ? v.row_index.at(m)[r] : r) * v.X;
         eps = v.eps_x1.at(m) + (long long)r * v.X;
       } else if (r < R0) {
         nrow = v.row_of_pair.at(m)[r - N];
         seg = 1;
-        src = v.x2.at(m) + (long long)nrow * v.X;
+        src = v.x2.at(m) + (long long)(v.row_index.p ? v.row_index.at(m)[nrow] : nrow) * v.X;
         eps = v.eps_x2.at(m) + (long long)nrow * v.X;
       }
       for (int qd = lane; qd < (fw >> 2); qd += 32) {

@@ -157,7 +157,10 @@ class Plan:
                 hp.log_prior_y[j] = math.log(float(prior_y[j])) if j < len(prior_y) else 0.0
         return hp
 
-    def _batch(self, x1, x2=None, y=None, has_x2=None, has_y=None):
+    def _batch(self, x1, x2=None, y=None, has_x2=None, has_y=None, row_index=None):
+        """Marshal one minibatch per model.  With row_index ([n_models, N] or [N] int32) the other fields are whole
+        device-resident datasets ([n_models, D, ...]) and the minibatch is rows row_index of them — the step reads the
+        dataset through the indices (drvae_batch_t.row_index), nothing is gathered."""
         def f32(t):
             if t is None:
                 return None
@@ -173,18 +176,25 @@ class Plan:
         if x1.dim() == 2:
             if self.E != 1:
                 raise ValueError("ensemble plans take batches shaped [n_models, N, dim_x]")
-            N = x1.shape[0]
+            rows = x1.shape[0]
         else:
             if x1.shape[0] != self.E:
                 raise ValueError("first batch dimension must be n_models")
-            N = x1.shape[1]
+            rows = x1.shape[1]
         if x1.shape[-1] != self.dim_x:
             raise ValueError("x1 has %d features, the model has dim_x=%d" % (x1.shape[-1], self.dim_x))
-        keep = [x1, f32(x2), i32(y), i32(has_x2), i32(has_y)]
-        for t in keep[1:]:
-            if t is not None and t.numel() not in (self.E * N, self.E * N * self.dim_x):
+        ridx = i32(row_index)
+        N = rows
+        if ridx is not None:
+            if ridx.numel() % self.E != 0:
+                raise ValueError("row_index must be shaped [n_models, N]")
+            N = ridx.numel() // self.E
+        keep = [x1, f32(x2), i32(y), i32(has_x2), i32(has_y), ridx]
+        for t in keep[1:5]:
+            if t is not None and t.numel() not in (self.E * rows, self.E * rows * self.dim_x):
                 raise ValueError("batch field has an unexpected number of elements")
-        b = Batch(_ptr(keep[0]), _ptr(keep[1]), _ptr(keep[2]), _ptr(keep[3]), _ptr(keep[4]), int(N))
+        b = Batch(_ptr(keep[0]), _ptr(keep[1]), _ptr(keep[2]), _ptr(keep[3]), _ptr(keep[4]), int(N), _ptr(ridx),
+                  int(rows) if ridx is not None else 0)
         return b, keep
 
     def _noise(self, eps, seed, row_offset=0):

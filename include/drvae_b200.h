@@ -56,7 +56,8 @@ typedef struct {
 
 /* One minibatch per model, reference layout (DrVAE.py:956-961): x1, x2 float32 [n_models][N][dim_x]
  * row-major; y, has_x2, has_y int32 [n_models][N].  Unused fields may be NULL (x2/has_x2 for
- * VFAE, y/has_y for PVAE).  s is not consumed (use_s=False). */
+ * VFAE, y/has_y for PVAE).  s is not consumed (use_s=False).  Zero-initialise the struct: optional fields added
+ * at its end must be NULL / 0 when unused. */
 typedef struct {
   const float* x1;
   const float* x2;
@@ -64,6 +65,12 @@ typedef struct {
   const int* has_x2;
   const int* has_y;
   int N;
+  /* Device-resident dataset (the reference's fit() draws minibatches from an in-memory dataset through a sampler,
+   * src/DrVAE.py:743-781, src/utils.py:292-327): when row_index is non-NULL the arrays above hold dataset_rows rows per
+   * model and the minibatch is rows row_index[model][0..N) of them (int32, device).  The step reads the dataset
+   * through the indices; nothing is gathered or copied.  NULL: the arrays are the minibatch itself. */
+  const int* row_index;
+  int dataset_rows;
 } drvae_batch_t;
 
 /* Noise.  eps != NULL: parity mode, a row-indexed block of standard normals per model laid out

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_sizes_match_header_layout():
     # ints/floats only: natural alignment, no padding surprises between C and ctypes
     assert ctypes.sizeof(_lib.Arch) == 4 * (5 + 4 * (1 + _lib.MAX_HIDDEN) + 3)
-    assert ctypes.sizeof(_lib.Batch) == 5 * 8 + 8
+    assert ctypes.sizeof(_lib.Batch) == 5 * 8 + 8 + 8 + 8  # 5 pointers, N (+pad), row_index, dataset_rows (+pad)
     assert ctypes.sizeof(_lib.Noise) == 24  # eps pointer, seed, row_offset
     assert ctypes.sizeof(_lib.HParams) == 4 * 17 + 4 * 8 + 4 + 8  # ... + padding + global_counts_dev pointer
     assert ctypes.sizeof(_lib.EpsLayout) == 7 * 8

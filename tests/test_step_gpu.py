@@ -752,3 +752,36 @@ def test_model_range_chains_do_not_change_results(kind):
         for a, b in zip(res[1], res[chains]):
             assert torch.equal(a, b), chains
     assert not torch.equal(res[1][0][0, 0], res[1][0][0, 1])  # members really differ
+
+
+@pytest.mark.parametrize("kind", KINDS)
+def test_device_resident_dataset_indexing_equals_gathered_batches(kind):
+    """drvae_batch_t.row_index: the minibatch as indices into datasets that stay on the device (what the reference's
+    fit() does on the host with a sampler + DataLoader) gives bit-identical steps to passing the gathered rows."""
+    arch, D, N, E = ARCH["tiny"], 90, 24, 2
+    sd = init_state_dict(kind, seed=SEED_MODEL, **arch)
+    data = [batch_fields(kind, orc.synthetic_batch(D, arch["dim_x"], seed=30 + m)) for m in range(E)]
+    dataset = {k: torch.stack([d[k] for d in data]).contiguous().cuda() for k in data[0]}
+    gen = torch.Generator().manual_seed(1)
+    res = {}
+    for mode in ("indexed", "gathered"):
+        plan = Plan(kind, L=L, max_batch=N, n_models=E, **arch)
+        for m in range(E):
+            plan.load_state_dict(sd, model=m)
+        gen.manual_seed(1)
+        idx_buf = torch.zeros(E, N, dtype=torch.int32, device="cuda")
+        out = []
+        for it in range(5):
+            idx = torch.stack([torch.randperm(D, generator=gen)[:N] for _ in range(E)]).int()
+            hp = plan.hparams(step=it, beta_pert=anneal_coef(it, 1, 0))
+            if mode == "indexed":
+                idx_buf.copy_(idx)  # same device buffer every step: the captured graph is replayed
+                out.append(plan.train_step(dict(dataset, row_index=idx_buf), hp, seed=3).cpu().clone())
+            else:
+                b = {k: torch.stack([v[m][idx[m].long().cuda()] for m in range(E)]).contiguous() for k, v in dataset.items()}
+                out.append(plan.train_step(b, hp, seed=3).cpu().clone())
+        res[mode] = (torch.stack(out), plan.params.cpu().clone())
+        if mode == "indexed":
+            assert plan.graph_replays() >= 2
+    assert torch.equal(res["indexed"][0], res["gathered"][0])
+    assert torch.equal(res["indexed"][1], res["gathered"][1])

@@ -380,7 +380,15 @@ def dp8192_result(ranks, steps, warmup):
     full = synthetic_batch(GLOBAL_N, README["dim_x"], seed=0)
     host = {k: full[k][lo:hi].contiguous().pin_memory() for k in FIELDS["drvae"]}
     devb = {k: v.to(dev) for k, v in host.items()}
-    runner = dpm.DataParallel(dpm.PlanBackend(plan))
+    backend = None
+    if world > 1 and os.environ.get("DRVAE_B200_DP_BACKEND", "peer") == "peer":
+        try:
+            backend = dpm.PeerBackend(plan)  # gradients summed over NVLink peer memory inside the optimizer kernel
+        except Exception as e:  # symmetric memory unavailable: NCCL all-reduce per bucket
+            print("PeerBackend unavailable (%s): falling back to NCCL" % e, file=sys.stderr)
+    if backend is None:
+        backend = dpm.PlanBackend(plan)
+    runner = dpm.DataParallel(backend)
     for _ in range(max(warmup, 4)):
         runner.step(devb, seed=1, row_offset=lo, host_flags=host)
     ranks.barrier()
@@ -398,9 +406,11 @@ def dp8192_result(ranks, steps, warmup):
     tf = flops / (ms / steps * 1e-3) / 1e12
     out = losses.detach().cpu()
     return {"workload": "DrVAE README config, single model, global batch 8192 (BASELINE configs[3]), rows sharded over %d rank(s); "
-                        "gradient all-reduce (NCCL over NVLink) overlapped with backward; Philox noise keyed by global row" % world,
+                        "gradients summed over NVLink; Philox noise keyed by global row" % world,
             "value": GLOBAL_N * steps / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / steps, "scaling": "strong", "n_gpus": world,
             "rows_per_rank": hi - lo, "gpu_launches": launches, "graph": bool(getattr(runner.backend, "graphs", None)),
+            "exchange": ("NVLink peer memory, all-reduce fused into the Adam kernel" + (" (NVLS multicast)" if getattr(backend, "multicast", False) else ""))
+                        if getattr(backend, "peer", False) else ("NCCL all-reduce per bucket" if world > 1 else "none (1 rank)"),
             "gemm_tflops_per_gpu": tf / world, "frac_of_bf16_sustained_per_gpu": tf / world / peaks["bf16_sustained"],
             "losses": {k: float(out[i]) for i, k in enumerate(("RECL", "KLD", "PERT", "YL", "MMD", "ELBO", "CMPL"))}}
 

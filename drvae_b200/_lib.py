@@ -53,6 +53,11 @@ class EpsLayout(ctypes.Structure):
                 ("off_z3", c_ll), ("total", c_ll)]
 
 
+class DpPeers(ctypes.Structure):
+    _fields_ = [("rank", c_int), ("world", c_int), ("grad_ptrs", ctypes.POINTER(c_void_p)), ("ctl_ptrs", ctypes.POINTER(c_void_p)),
+                ("grads_multicast", c_void_p)]
+
+
 class InferOut(ctypes.Structure):
     _fields_ = [(n, c_void_p) for n in ("z1_mu", "z1_lv", "z2_mu", "z2_lv", "proba", "pred", "px1_mu", "px1_sg",
                                         "px2_mu", "px2_sg")]
@@ -65,7 +70,8 @@ EXPORTS = ["drvae_last_error", "drvae_plan_create", "drvae_plan_destroy", "drvae
            "drvae_loss_forward", "drvae_grad_step", "drvae_adam_step", "drvae_infer", "drvae_set_gemm_impl",
            "drvae_plan_launch_count", "drvae_debug_buffer", "drvae_debug_gemm", "drvae_profile_begin",
            "drvae_profile_end", "drvae_plan_num_buckets", "drvae_plan_bucket_info", "drvae_stream_wait_bucket", "drvae_set_graph", "drvae_plan_graph_replays", "drvae_debug_wait_stats",
-           "drvae_push_scalars", "drvae_set_external_scalars", "drvae_debug_side_delay", "drvae_plan_tensor_ld", "drvae_set_chains", "drvae_trace_begin", "drvae_trace_end", "drvae_debug_dwa_stats", "drvae_set_infer_precision"]
+           "drvae_push_scalars", "drvae_set_external_scalars", "drvae_debug_side_delay", "drvae_plan_tensor_ld", "drvae_set_chains", "drvae_trace_begin", "drvae_trace_end", "drvae_debug_dwa_stats", "drvae_set_infer_precision", "drvae_dp_attach", "drvae_dp_grad_floats",
+           "drvae_dp_counts_ptr", "drvae_dp_exchange_counts", "drvae_dp_adam_step"]
 
 
 def load():
@@ -127,6 +133,16 @@ def load():
     lib.drvae_debug_wait_stats.argtypes = [c_void_p, c_int]
     lib.drvae_debug_dwa_stats.restype = c_int
     lib.drvae_debug_dwa_stats.argtypes = [c_void_p, c_int, c_void_p]
+    lib.drvae_dp_attach.restype = c_int
+    lib.drvae_dp_attach.argtypes = [c_void_p, P(DpPeers)]
+    lib.drvae_dp_grad_floats.restype = c_ll
+    lib.drvae_dp_grad_floats.argtypes = [c_void_p]
+    lib.drvae_dp_counts_ptr.restype = c_void_p
+    lib.drvae_dp_counts_ptr.argtypes = [c_void_p]
+    lib.drvae_dp_exchange_counts.restype = c_int
+    lib.drvae_dp_exchange_counts.argtypes = [c_void_p, c_ll, c_ll, c_ll, c_ll, c_void_p]
+    lib.drvae_dp_adam_step.restype = c_int
+    lib.drvae_dp_adam_step.argtypes = [c_void_p, P(HParams), c_void_p, c_void_p]
     lib.drvae_set_infer_precision.restype = c_int
     lib.drvae_set_infer_precision.argtypes = [c_void_p, c_int]
     lib.drvae_trace_begin.restype = c_int

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "errors.h"
+#include "dp_peer.cuh"
 #include "dwadam.cuh"
 #include "gemm.cuh"
 #include "infer_f32.cuh"
@@ -130,6 +131,10 @@ struct drvae_plan {
   bool dwa_ok = false;       // every layer fits the kernel's layout conditions and the state is bound
   unsigned long long* d_dwa_stats = nullptr;  // drvae_debug_dwa_stats
   bool dwa_enabled = true;   // measurement knob (DRVAE_B200_DWADAM=0: per-layer fused kernels of round 1)
+  // data-parallel exchange over peer memory (dp_peer.cuh): attached by drvae_dp_attach
+  bool dp_on = false;
+  DpPeers dp{};
+  long long* dp_counts = nullptr;  // int64 [3]: batch-global {N, Np, Nlab} of the current step
   // fp32 inference path (infer_f32.cuh): on by default (exact thresholded predictions); scratch allocated on first use
   bool infer_fp32 = true;
   float* f32ws = nullptr;
@@ -676,6 +681,7 @@ extern "C" int drvae_plan_destroy(drvae_plan_t* pl) {
   if (pl->d_wn_rows) cudaFree(pl->d_wn_rows);
   if (pl->d_dwa_layers) cudaFree(pl->d_dwa_layers);
   if (pl->d_dwa_maps) cudaFree(pl->d_dwa_maps);
+  if (pl->dp_counts) cudaFree(pl->dp_counts);
   if (pl->f32ws) cudaFree(pl->f32ws);
   if (pl->d_trace) cudaFree(pl->d_trace);
   if (pl->d_dwa_stats) cudaFree(pl->d_dwa_stats);
@@ -1746,6 +1752,88 @@ extern "C" int drvae_adam_step(drvae_plan_t* pl, const drvae_hparams_t* hp, void
     if (rc) return rc;
   }
   return run_adam(pl, hp, 1, (cudaStream_t)stream);
+}
+
+// ---- data parallelism over NVLink peer memory (dp_peer.cuh) ----
+extern "C" int drvae_dp_attach(drvae_plan_t* pl, const drvae_dp_peers_t* peers) {
+  if (!pl || !peers) return set_error("drvae_dp_attach: null argument");
+  if (pl->E != 1) return set_error("drvae_dp_attach: data-parallel training shards ONE model (ensembles shard by model)");
+  if (peers->world < 1 || peers->world > DP_MAX_RANKS || peers->rank < 0 || peers->rank >= peers->world)
+    return set_error("drvae_dp_attach: bad rank / world size");
+  if (!pl->params || !pl->adam_m || !pl->adam_v) return set_error("drvae_dp_attach: bind parameters and Adam moments first");
+  DpPeers d{};
+  d.rank = peers->rank;
+  d.world = peers->world;
+  for (int r = 0; r < peers->world; ++r) {
+    if (!peers->grad_ptrs[r] || !peers->ctl_ptrs[r]) return set_error("drvae_dp_attach: null peer pointer");
+    d.grads[r] = peers->grad_ptrs[r];
+    d.ctl[r] = peers->ctl_ptrs[r];
+  }
+  d.grads_mc = peers->grads_multicast;
+  pl->dp = d;
+  pl->dp_on = true;
+  pl->grads = peers->grad_ptrs[peers->rank];  // the gradient kernels write this rank's symmetric vector
+  if (!pl->dp_counts) {
+    cudaError_t err = cudaMalloc(&pl->dp_counts, 3 * sizeof(long long));
+    if (err != cudaSuccess) return set_cuda_error("drvae_dp_attach", err);
+  }
+  drop_graphs(pl);
+  return 0;
+}
+extern "C" const long long* drvae_dp_counts_ptr(const drvae_plan_t* pl) { return pl ? pl->dp_counts : nullptr; }
+extern "C" long long drvae_dp_grad_floats(const drvae_plan_t* pl) { return pl ? (long long)pl->P + 64 : -1; }
+extern "C" int drvae_dp_exchange_counts(drvae_plan_t* pl, long long N, long long Np, long long Nlab, long long tag, void* stream) {
+  if (!pl || !pl->dp_on) return set_error("drvae_dp_exchange_counts: no peers attached");
+  dp_counts_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pl->dp, N, Np, Nlab, tag, pl->dp_counts, pl->dbg);
+  pl->launches++;
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return set_cuda_error("dp_counts_kernel", err);
+  return 0;
+}
+extern "C" int drvae_dp_adam_step(drvae_plan_t* pl, const drvae_hparams_t* hp, float* losses_out, void* stream) {
+  if (!pl || !hp || !losses_out) return set_error("drvae_dp_adam_step: null argument");
+  if (!pl->dp_on) return set_error("drvae_dp_adam_step: no peers attached");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!pl->external_dyn) {
+    int rc = push_dyn(pl, make_dyn(nullptr, hp, false), st);
+    if (rc) return rc;
+  }
+  prof_pre(pl, st, "opt:dp_barrier");
+  dp_barrier_kernel<<<1, 32, 0, st>>>(pl->dp, pl->d_dyn, pl->dbg);
+  prof_post(pl, st);
+  AdamArgs a{};
+  a.params = MBuf<float>{pl->params, pl->P};
+  a.grads = MBuf<float>{pl->grads, pl->P};
+  a.m = MBuf<float>{pl->adam_m, pl->P};
+  a.v = MBuf<float>{pl->adam_v, pl->P};
+  a.shadow = pl->shadow;
+  a.derived = pl->derived;
+  a.segs = pl->d_segs;
+  a.nseg = (int)pl->segs.size();
+  a.P = pl->P;
+  a.update = 1;
+  a.h = &pl->d_dyn->s.adam;
+  a.skip_lo = a.skip_hi = 0;
+  if (pl->arch.kind == DRVAE_KIND_PVAE && pl->has_T) a.skip_lo = (int)pl->T_range[0], a.skip_hi = (int)(pl->T_range[0] + pl->T_range[1]);
+  a.dyn = pl->d_dyn;
+  a.counts = pl->view.counts.p;
+  a.counts_stride = (int)pl->view.counts.ms;
+  const int nred = pl->P + 8;
+  prof_pre(pl, st, "opt:adam_peer");
+  adam_peer_kernel<<<cdiv(nred, 1024), 256, 0, st>>>(a, pl->dp, nred, losses_out);
+  prof_post(pl, st);
+  pl->launches += 2;
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return set_cuda_error("adam_peer_kernel", err);
+  if (pl->wn) {
+    WnArgs w{pl->d_wn_rows, (int)pl->wn_rows.size(), a.params, a.grads, pl->shadow, pl->derived};
+    wn_refresh_kernel<<<dim3(cdiv(w.nrows, 8), pl->E), 256, 0, st>>>(w);
+    pl->launches++;
+    err = cudaGetLastError();
+    if (err != cudaSuccess) return set_cuda_error("wn_refresh_kernel", err);
+  }
+  pl->shadows_valid = true;
+  return 0;
 }
 
 extern "C" int drvae_push_scalars(drvae_plan_t* pl, const drvae_noise_t* nz, const drvae_hparams_t* hp, int fused_adam,

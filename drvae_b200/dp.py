@@ -92,6 +92,43 @@ class PlanBackend:
         self.plan.adam_step(self._hp)
 
 
+class PeerBackend(PlanBackend):
+    """GPU backend without NCCL on the data path: every rank's flat gradient lives in symmetric memory all ranks have
+    mapped (torch.distributed._symmetric_memory is used for the allocation and the pointer exchange only), and the
+    all-reduce is fused into the optimizer kernel (csrc/dp_peer.cuh): cross-GPU flag barrier + ONE kernel that sums the
+    ranks' gradients over NVLink in rank order and applies Adam.  The whole step — gradient kernels, barrier, optimizer —
+    is one CUDA graph per set of batch buffers on every rank; per step the host launches the counts exchange, the
+    per-step scalars and the graph."""
+
+    def __init__(self, plan, group=None, graph=None, multicast=None):
+        super().__init__(plan, graph=graph)
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        dev = plan.device
+        n = plan.dp_grad_floats()
+        self.gbuf = symm_mem.empty(n, dtype=torch.float32, device=dev)
+        self.ctl = symm_mem.empty(128, dtype=torch.int64, device=dev)
+        self.gbuf.zero_()
+        self.ctl.zero_()
+        gh = symm_mem.rendezvous(self.gbuf, self.group)
+        ch = symm_mem.rendezvous(self.ctl, self.group)
+        torch.cuda.synchronize(dev)
+        dist.barrier(self.group)  # every control block is zero before anybody posts a flag
+        if multicast is None:
+            multicast = os.environ.get("DRVAE_B200_DP_MULTICAST", "0") != "0"
+        mc = int(getattr(gh, "multicast_ptr", 0) or 0) if multicast else 0
+        self.multicast = bool(mc)
+        plan.dp_attach(self.rank, self.world, list(gh.buffer_ptrs), list(ch.buffer_ptrs), mc)
+        self._handles = (gh, ch)
+        self.loss_share = self.gbuf[plan.P:plan.P + 8]  # this rank's additive loss shares, reduced with the gradient
+        self.global_losses = torch.zeros(8, dtype=torch.float32, device=dev)
+        self.peer = True
+
+    def flat_grads(self):
+        return self.gbuf[:self.plan.P]
+
+
 class DataParallel:
     """step(): one optimisation step of a row-sharded minibatch.  `backend` is a PlanBackend on the
     GPU box; the CPU tests substitute an oracle-backed object with the same four methods."""
@@ -162,6 +199,47 @@ class DataParallel:
         g.replay()
         return losses
 
+    def _step_peer(self, be, batch, hp_kwargs, local, eps, seed, row_offset):
+        """PeerBackend: counts exchange (doubles as the cross-step barrier) -> [graph: gradient kernels -> peer barrier ->
+        fused all-reduce + Adam]."""
+        plan = be.plan
+        it = self.finished_training_iters
+        plan.dp_exchange_counts(local, it + 1)
+        hp = plan.hparams(step=it, global_counts_ptr=plan.dp_counts_ptr, **hp_kwargs)
+
+        def enqueue():
+            plan.grad_step(batch, hp, eps=eps, seed=seed, row_offset=row_offset, losses_out=be.loss_share)
+            plan.dp_adam_step(hp, be.global_losses)
+
+        graphable = be.graph and eps is None and all(torch.is_tensor(v) and v.is_cuda for v in batch.values())
+        if not graphable:
+            enqueue()
+            return be.global_losses
+        key = (int(batch["x1"].shape[-2]),) + tuple((k, v.data_ptr(), str(v.dtype)) for k, v in sorted(batch.items()))
+        entry = be.graphs.get(key)
+        if entry is None:
+            if len(be.seen) > 64:
+                be.seen.clear()
+            be.seen[key] = be.seen.get(key, 0) + 1
+            if be.seen[key] < 3:  # warm-up: function attributes, tensor maps
+                enqueue()
+                return be.global_losses
+            cur = torch.cuda.current_stream(be.device)
+            cur.synchronize()
+            plan.set_external_scalars(True)
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    enqueue()
+            finally:
+                plan.set_external_scalars(False)
+            if len(be.graphs) >= 8:
+                be.graphs.clear()
+            entry = be.graphs[key] = (g, dict(batch))
+        plan.push_scalars(hp, seed=seed, row_offset=row_offset, fused=False)
+        entry[0].replay()
+        return be.global_losses
+
     def step(self, batch, hp_kwargs=None, eps=None, seed=0, row_offset=0, host_flags=None):
         """batch: this rank's shard (same fields as Plan.train_step).  Returns the GLOBAL losses as
         an 8-vector (RECL, KLD, PERT, YL, MMD, ELBO, CMPL, 0) identical on every rank.
@@ -171,6 +249,10 @@ class DataParallel:
         n = batch["x1"].shape[-2]
         flags = host_flags if host_flags is not None else batch
         local = local_counts(n, flags.get("has_x2"), flags.get("has_y"))
+        if getattr(be, "peer", False):
+            losses = self._step_peer(be, batch, dict(hp_kwargs or {}), local, eps, seed, row_offset)
+            self.finished_training_iters += 1
+            return losses
         # (single rank only: with NCCL collectives inside the capture the one 2-rank attempt of this round deadlocked,
         #  so ranks > 1 keep the eager, event-overlapped path below)
         if getattr(be, "graph", False) and self.world == 1 and eps is None and \

@@ -135,7 +135,7 @@ class Plan:
     # ---- marshalling ----------------------------------------------------------------------
     def hparams(self, step, training=True, add_noise=True, noise_std=0.01, beta_pert=1.0, pertloss_rate=0.05,
                 kl_qz2pz2_rate=1.0, yloss_rate=1.0, kl_min=2.0, lr=5e-4, beta1=0.9, beta2=0.999, adam_eps=1e-8,
-                weight_decay=0.05, global_counts=None, prior_y=None):
+                weight_decay=0.05, global_counts=None, prior_y=None, global_counts_ptr=None):
         hp = HParams()
         hp.step, hp.training, hp.add_noise = int(step), int(training), int(add_noise)
         hp.noise_std, hp.beta_pert, hp.pertloss_rate = noise_std, beta_pert, pertloss_rate
@@ -149,6 +149,8 @@ class Plan:
             hp._keep = global_counts
         elif global_counts is not None:
             hp.global_N, hp.global_Np, hp.global_Nlab = [int(c) for c in global_counts]
+        if global_counts_ptr:  # raw device pointer to int64 {N, Np, Nlab} (drvae_dp_counts_ptr)
+            hp.global_counts_dev = int(global_counts_ptr)
         ny = max(1, self.dim_y)
         for j in range(8):
             if prior_y is None:
@@ -204,27 +206,28 @@ class Plan:
                 raise ValueError("eps block must have n_models * %d floats" % self.eps_layout.total)
         return Noise(_ptr(eps), int(seed) & 0xFFFFFFFFFFFFFFFF, int(row_offset)), eps
 
-    def _run(self, fn, what, batch, hp, eps=None, seed=0, row_offset=0):
+    def _run(self, fn, what, batch, hp, eps=None, seed=0, row_offset=0, losses_out=None):
         b, keep = self._batch(**batch)
         nz, keep_eps = self._noise(eps, seed, row_offset)
+        lo = _ptr(self.losses) if losses_out is None else _ptr(losses_out)
         with torch.cuda.device(self.device):
             cur = torch.cuda.current_stream(self.device)
             if cur.cuda_stream == 0:
                 own = self._own_stream
                 own.wait_stream(cur)
-                _lib.check(fn(self.h, ctypes.byref(b), ctypes.byref(nz), ctypes.byref(hp), _ptr(self.losses),
+                _lib.check(fn(self.h, ctypes.byref(b), ctypes.byref(nz), ctypes.byref(hp), lo,
                               ctypes.c_void_p(own.cuda_stream)), what)
                 cur.wait_stream(own)  # later work on the caller's stream (incl. reuse of freed batch memory) is ordered after the step
             else:
-                _lib.check(fn(self.h, ctypes.byref(b), ctypes.byref(nz), ctypes.byref(hp), _ptr(self.losses), self._stream()), what)
+                _lib.check(fn(self.h, ctypes.byref(b), ctypes.byref(nz), ctypes.byref(hp), lo, self._stream()), what)
         del keep, keep_eps  # stream-ordered: torch's caching allocator keeps them alive for this stream
-        return self.losses
+        return self.losses if losses_out is None else losses_out
 
     def train_step(self, batch, hp, eps=None, seed=0, row_offset=0):
         return self._run(self.lib.drvae_train_step, "train_step", batch, hp, eps, seed, row_offset)
 
-    def grad_step(self, batch, hp, eps=None, seed=0, row_offset=0):
-        return self._run(self.lib.drvae_grad_step, "grad_step", batch, hp, eps, seed, row_offset)
+    def grad_step(self, batch, hp, eps=None, seed=0, row_offset=0, losses_out=None):
+        return self._run(self.lib.drvae_grad_step, "grad_step", batch, hp, eps, seed, row_offset, losses_out)
 
     def loss_forward(self, batch, hp, eps=None, seed=0, row_offset=0):
         return self._run(self.lib.drvae_loss_forward, "loss_forward", batch, hp, eps, seed, row_offset)
@@ -243,6 +246,29 @@ class Plan:
     def adam_step(self, hp):
         with torch.cuda.device(self.device):
             _lib.check(self.lib.drvae_adam_step(self.h, ctypes.byref(hp), self._stream()), "adam_step")
+
+    # ---- data parallelism over NVLink peer memory (include/drvae_b200.h, drvae_dp_*) ----
+    def dp_grad_floats(self):
+        return int(self.lib.drvae_dp_grad_floats(self.h))
+
+    def dp_attach(self, rank, world, grad_ptrs, ctl_ptrs, multicast_ptr=0):
+        pe = _lib.DpPeers()
+        pe.rank, pe.world = int(rank), int(world)
+        ga = (ctypes.c_void_p * world)(*[int(p) for p in grad_ptrs])
+        ca = (ctypes.c_void_p * world)(*[int(p) for p in ctl_ptrs])
+        pe.grad_ptrs, pe.ctl_ptrs = ga, ca
+        pe.grads_multicast = int(multicast_ptr) if multicast_ptr else None
+        _lib.check(self.lib.drvae_dp_attach(self.h, ctypes.byref(pe)), "dp_attach")
+        self.dp_counts_ptr = int(self.lib.drvae_dp_counts_ptr(self.h))
+
+    def dp_exchange_counts(self, counts, tag):
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.drvae_dp_exchange_counts(self.h, int(counts[0]), int(counts[1]), int(counts[2]), int(tag), self._stream()),
+                       "dp_exchange_counts")
+
+    def dp_adam_step(self, hp, losses_out):
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.drvae_dp_adam_step(self.h, ctypes.byref(hp), _ptr(losses_out), self._stream()), "dp_adam_step")
 
     def infer(self, x1):
         x1 = x1.to(self.device, torch.float32).contiguous()

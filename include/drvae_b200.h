@@ -160,6 +160,30 @@ int drvae_adam_step(drvae_plan_t* plan, const drvae_hparams_t* hp, void* stream)
 int drvae_plan_num_buckets(const drvae_plan_t* plan);
 int drvae_plan_bucket_info(const drvae_plan_t* plan, int index, long long* offset, long long* count);
 int drvae_stream_wait_bucket(drvae_plan_t* plan, int index, void* stream);
+/* Data parallelism over NVLink peer memory (one model, rows of the minibatch sharded over the GPUs of one box).
+ * Every rank keeps its flat gradient (+ its 8 additive loss shares right behind it: drvae_dp_grad_floats() floats) and
+ * a control block of 128 int64 in allocations ALL ranks have mapped; the caller passes the peer pointers
+ * (torch.distributed._symmetric_memory, cudaIpc handles, ...).  Per step:
+ *   drvae_dp_exchange_counts   batch-global normalisers {N, Np, Nlab}: posted to all peers, summed into
+ *                              drvae_dp_counts_ptr() (pass it as drvae_hparams_t.global_counts_dev); also the barrier
+ *                              that keeps a fast rank from overwriting a gradient a slow rank still reads
+ *   drvae_grad_step            with losses_out = own gradient vector + param_count (loss shares join the reduction)
+ *   drvae_dp_adam_step         cross-GPU barrier (tag = step + 1, read from the per-step scalars so it replays inside a
+ *                              CUDA graph) + ONE kernel that sums every rank's gradient over NVLink in rank order and
+ *                              applies Adam and the shadow refresh; global losses -> losses_out (device, 8 floats)
+ * grads_multicast (optional): NVLS multicast mapping of the gradient vectors; the sum is then formed inside the
+ * switch (multimem.ld_reduce).  No NCCL call is involved; results are bit-identical on all ranks. */
+typedef struct {
+  int rank, world;
+  float* const* grad_ptrs;        /* [world] device pointers to every rank's gradient vector (own rank included) */
+  long long* const* ctl_ptrs;     /* [world] device pointers to every rank's control block (zeroed before attach) */
+  float* grads_multicast;         /* or NULL */
+} drvae_dp_peers_t;
+int drvae_dp_attach(drvae_plan_t* plan, const drvae_dp_peers_t* peers);
+long long drvae_dp_grad_floats(const drvae_plan_t* plan);
+const long long* drvae_dp_counts_ptr(const drvae_plan_t* plan);
+int drvae_dp_exchange_counts(drvae_plan_t* plan, long long N, long long Np, long long Nlab, long long tag, void* stream);
+int drvae_dp_adam_step(drvae_plan_t* plan, const drvae_hparams_t* hp, float* losses_out, void* stream);
 int drvae_infer(drvae_plan_t* plan, const float* x1, int N, const drvae_infer_out_t* out, void* stream);
 /* Inference arithmetic.  fp32 != 0 (default): the mu-path is evaluated with fp32 operands and fp32 accumulation from
  * the master parameters, so that class probabilities agree with the reference to ~1e-6 and thresholded predictions

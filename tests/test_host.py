@@ -17,7 +17,7 @@ from drvae_b200.plan import anneal_coef
 
 def test_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "drvae_b200.h")).read()
-    declared = sorted(set(re.findall(r"^(?:const char\*|int|long long)\s+(drvae_[a-z0-9_]+)\s*\(", hdr, re.M)))
+    declared = sorted(set(re.findall(r"^(?:const char\*|const long long\*|int|long long)\s+(drvae_[a-z0-9_]+)\s*\(", hdr, re.M)))
     assert declared, "no declarations parsed"
     lib = _lib.load()
     for name in declared:

@@ -62,6 +62,9 @@ struct DwaLayer {
   long long tab_off;        // g_tab: [3][rcap] (weight row offsets, bias offsets, folded bias constants)
   long long drv_bias_off, drv_clsb_off;
   int drv_clsb_ld;
+  int ld;                   // floats between rows of the weight tensors
+  int w_off[2];             // flat offsets of the weight tensors
+  long long sh_off;         // bf16 shadow of the layer inside the per-model shadow arena
 };
 
 struct DwaParams {
@@ -75,10 +78,13 @@ struct DwaParams {
   long long state_ms;
   float* drv;
   long long drv_ms;
+  bf16* shadow;             // shadow arena (direct-store variant)
+  long long shadow_ms;
   const AdamHyper* adam;
   DebugWord* dbg;
   unsigned long long* trace;
   int trace_id;
+  int debug_flags;            // measurement knob (DRVAE_B200_DWA_DEBUG): 1 = no operand loads / MMA (gradient = 0)
   unsigned long long* stats;  // optional [8] cycle counters of the roles' barrier waits (drvae_debug_dwa_stats)
 };
 
@@ -146,7 +152,7 @@ __device__ __forceinline__ DwaTile dwa_tile(const DwaParams& p, const DwaLayer* 
   t.BN = y.BN;
   const int rows = p.counts[(long long)t.model * p.counts_stride + y.cnt_which];
   t.Kc = (rows + 15) & ~15;
-  t.nkb = (t.Kc + GEMM_BK - 1) / GEMM_BK;
+  t.nkb = (p.debug_flags & 1) ? 0 : (t.Kc + GEMM_BK - 1) / GEMM_BK;
   t.active = !(y.skip_which >= 0 && p.counts[(long long)t.model * p.counts_stride + y.skip_which] == 0);
   return t;
 }
@@ -189,7 +195,7 @@ __global__ void __launch_bounds__(DWA_THREADS, 1) dwadam_kernel(const DwaParams 
     for (int s = 0; s < DWA_NST; ++s) {
       mbar_init(&st_full[s], 1);
       mbar_init(&st_done[s], DWA_EW);
-      mbar_init(&st_empty[s], 1);
+      mbar_init(&st_empty[s], (p.debug_flags & 2) ? DWA_EW : 1);
     }
     mbar_fence_init();
   }
@@ -266,7 +272,7 @@ __global__ void __launch_bounds__(DWA_THREADS, 1) dwadam_kernel(const DwaParams 
   } else if (warp == 2) {
     // ===================== optimizer-state storer =====================
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < p.total_tiles && !(p.debug_flags & 2); tile += gridDim.x) {
       const DwaTile t = dwa_tile(p, L, tile);
       if (!t.active) continue;
       const DwaLayer& y = L[t.layer];
@@ -414,11 +420,28 @@ __global__ void __launch_bounds__(DWA_THREADS, 1) dwadam_kernel(const DwaParams 
           for (int i = 0; i < 4; ++i) pv[i] = sp[i * 128], mv[i] = sm[i * 128], vv[i] = sv[i * 128];
         }
         tmem_ld4_wait(have_acc, accr, acc);  // warp-collective: outside the lane-dependent branches
+        const bool direct = p.debug_flags & 2;
+        if (direct) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&st_empty[s]);  // the stage is in registers: the loader may refill it
+        }
         if (upd) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) adam_update(acc[i], pv[i], mv[i], vv[i], h);
+          if (direct) {
+            const int base = y.w_off[which] + (n + g * 4) * y.ld + (is_w ? kk : kk - 1);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) sp[i * 128] = pv[i], sm[i * 128] = mv[i], sv[i * 128] = vv[i];
+            for (int i = 0; i < 4; ++i) {
+              if (n + g * 4 + i < y.rows_each) {
+                P[base + i * y.ld] = pv[i];
+                M1[base + i * y.ld] = mv[i];
+                V2[base + i * y.ld] = vv[i];
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sp[i * 128] = pv[i], sm[i * 128] = mv[i], sv[i * 128] = vv[i];
+          }
           if (is_w) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) shv[i] = pv[i];
@@ -440,15 +463,31 @@ __global__ void __launch_bounds__(DWA_THREADS, 1) dwadam_kernel(const DwaParams 
         // shadow stage [16 chunks][R rows][8]: columns >= kin (ones / class columns, padding) stay zero.  The four
         // 8-lane groups of a warp write four different chunks whose rows are 256 bytes (= all 32 banks x 2) apart: row
         // order rotated by the group index so that they hit different banks
+        if (direct) {
+          // shadow: lanes pair up (k even, k odd); the even lane stores the bf16 pairs of rows 0-1, the odd lane of rows 2-3
+          const bool even = !(lane & 1);
+          const float x0 = __shfl_xor_sync(0xffffffffu, even ? shv[2] : shv[0], 1);
+          const float x1 = __shfl_xor_sync(0xffffffffu, even ? shv[3] : shv[1], 1);
+          const int ke = kk & ~1;
+          if (has && ke < y.kin) {
+            const int r0 = g * 4 + (even ? 0 : 2);
+            bf16* sh = p.shadow + t.model * p.shadow_ms + y.sh_off + ((long long)(ke >> 3) * y.rcap + t.n0 + sub * DWA_R + r0) * 8 + (ke & 7);
+            const uint32_t w0 = even ? pack_bf16x2(shv[0], x0) : pack_bf16x2(x0, shv[2]);
+            const uint32_t w1 = even ? pack_bf16x2(shv[1], x1) : pack_bf16x2(x1, shv[3]);
+            if (n + r0 < y.rows_each) *reinterpret_cast<uint32_t*>(sh) = w0;
+            if (n + r0 + 1 < y.rows_each) *reinterpret_cast<uint32_t*>(sh + 8) = w1;
+          }
+        } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int r = (i + rot) & 3;
-          const float x = r == 0 ? shv[0] : (r == 1 ? shv[1] : (r == 2 ? shv[2] : shv[3]));
-          ss[r * 8] = __float2bfloat16_rn(x);
+          for (int i = 0; i < 4; ++i) {
+            const int r = (i + rot) & 3;
+            const float x = r == 0 ? shv[0] : (r == 1 ? shv[1] : (r == 2 ? shv[2] : shv[3]));
+            ss[r * 8] = __float2bfloat16_rn(x);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&st_done[s]);
         }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&st_done[s]);
       }
       tc_fence_before();
       __syncwarp();

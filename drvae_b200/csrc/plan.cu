@@ -116,6 +116,7 @@ struct drvae_plan {
     cudaEvent_t* all() { return &ev_fork; }  // 10 consecutive events
   };
   Chain chain[MAX_CHAINS];
+  bool main_prio = true;      // main chain on the plan's high-priority stream (DRVAE_B200_PRIO=0: on the caller's stream)
   int chains = 1;             // model ranges per step (DRVAE_B200_CHAINS; default chosen from n_models at creation)
   cudaEvent_t ev_begin = nullptr;
   bool overlap = true;
@@ -568,9 +569,14 @@ extern "C" int drvae_plan_create(const drvae_arch_t* a, int n_models, drvae_plan
   pl->chains = 1;  // measured (32 models): 0.970 / 1.002 / 1.020 / 1.054 ms for 1 / 2 / 4 / 8 ranges
   if (const char* knob = getenv("DRVAE_B200_CHAINS")) pl->chains = std::max(1, atoi(knob));
   if (const char* knob = getenv("DRVAE_B200_OVERLAP")) pl->overlap = atoi(knob) != 0;
+  if (const char* knob = getenv("DRVAE_B200_PRIO")) pl->main_prio = atoi(knob) != 0;
   for (auto& ch : pl->chain) {
-    cudaStreamCreateWithFlags(&ch.main, cudaStreamNonBlocking);
-    cudaStreamCreateWithFlags(&ch.side, cudaStreamNonBlocking);
+    // the main chain outranks the side branch: when both have CTAs waiting for an SM (the side stream's wide row kernels
+    // vs the next GEMM of the critical path) the critical path goes first
+    int prio_least = 0, prio_greatest = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+    cudaStreamCreateWithPriority(&ch.main, cudaStreamNonBlocking, prio_greatest);
+    cudaStreamCreateWithPriority(&ch.side, cudaStreamNonBlocking, prio_least);
     for (int i = 0; i < 10; ++i) cudaEventCreateWithFlags(ch.all() + i, cudaEventDisableTiming);
   }
   cudaEventCreateWithFlags(&pl->ev_begin, cudaEventDisableTiming);
@@ -818,6 +824,10 @@ int build_dwa(drvae_plan* pl) {
     y.drv_bias_off = W.bias_off;
     y.drv_clsb_off = W.clsb_off;
     y.drv_clsb_ld = W.rcap;
+    y.ld = W.ld;
+    y.w_off[0] = W.w_off[0];
+    y.w_off[1] = W.ntens > 1 ? W.w_off[1] : W.w_off[0];
+    y.sh_off = W.off;
     pl->dwa_layers.push_back(y);
     DwaMaps& m = maps[i];
     const C8Buf& X = *refs[i].X;
@@ -1324,13 +1334,16 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
   // one event per bucket on ONE stream) and not under per-launch profiling
   int K = 1;
   if (!pl->prof_on && !(backward && !fused_adam)) K = std::max(1, std::min({pl->chains, E, (int)drvae_plan::MAX_CHAINS}));
-  if (K > 1) cudaEventRecord(pl->ev_begin, st);
+  const bool own_main = pl->main_prio && !pl->prof_on && !(backward && !fused_adam) && pl->has_fprop && pl->overlap;
+  if (K > 1 || own_main) cudaEventRecord(pl->ev_begin, st);
 
   for (int c = 0; c < K && ex.ok(); ++c) {
     drvae_plan::Chain& ch = pl->chain[c];
     const int m0 = (int)((long long)E * c / K), Ec = (int)((long long)E * (c + 1) / K) - m0;
-    cudaStream_t cm = (c == 0) ? st : ch.main;  // range 0 stays on the caller's stream
-    if (c > 0) cudaStreamWaitEvent(cm, pl->ev_begin, 0);
+    // range 0 stays on the caller's stream unless the plan's own high-priority stream is used for the main chain
+    const bool forked = c > 0 || own_main;
+    cudaStream_t cm = forked ? ch.main : st;
+    if (forked) cudaStreamWaitEvent(cm, pl->ev_begin, 0);
     v.model0 = m0;
     ex.phase = "";
     ex.model0 = m0;
@@ -1348,6 +1361,14 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
       cudaEventRecord(ev, producer);
       cudaStreamWaitEvent(waiter, ev, 0);
     };
+    ex.pre("rowmap");
+    launch_k(rowmap_kernel, dim3(Ec), dim3(ROWMAP_THREADS), 0, cm, 2, v);
+    ex.chk();
+    ex.pre("prep");
+    launch_k(prep_kernel, dim3(round_up(R0b, 128) / PREP_ROWS, cdiv(pl->view.Xc, PREP_SLAB), Ec), dim3(PREP_THREADS), 0, cm, 2, v);
+    ex.chk();
+    // latent noise: on the side stream, forked AFTER prep so that it fills the SMs next to the encoder GEMMs instead of
+    // running in front of prep (it is first needed by sample_q1)
     if (own_eps) {
       const drvae_eps_layout_t& el = pl->epsl;
       EpsSegs sg{};
@@ -1364,7 +1385,7 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
       }
       dim3 g((unsigned)((most + 255) / 256), Ec, 6);
       if (pl->sched & 1) {
-        after(side, ch.ev_begin, cm);  // after this step's scalars (set_dyn) and everything before them
+        after(side, ch.ev_begin, cm);  // after this step's scalars (set_dyn), rowmap and prep
         on(side);
       }
       ex.pre("philox_normal");
@@ -1372,12 +1393,6 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
       ex.chk();
       on(cm);
     }
-    ex.pre("rowmap");
-    launch_k(rowmap_kernel, dim3(Ec), dim3(ROWMAP_THREADS), 0, cm, 2, v);
-    ex.chk();
-    ex.pre("prep");
-    launch_k(prep_kernel, dim3(round_up(R0b, 128) / PREP_ROWS, cdiv(pl->view.Xc, PREP_SLAB), Ec), dim3(PREP_THREADS), 0, cm, 2, v);
-    ex.chk();
 
     // ---- encoder q(z1|x1), shared with q(z2|x2) (DrVAE.py:408,418) ----
     ex.phase = "enc.fwd";
@@ -1544,7 +1559,7 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
       bucket_done();
     }
     if (overlap) cudaStreamWaitEvent(cm, ch.ev_side_end, 0);
-    if (c > 0) {  // join this range into the caller's stream
+    if (forked) {  // join this range into the caller's stream
       cudaEventRecord(ch.ev_end, cm);
       cudaStreamWaitEvent(st, ch.ev_end, 0);
     }
@@ -1568,6 +1583,8 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
     dp.state_ms = pl->P;
     dp.drv = pl->derived.p;
     dp.drv_ms = pl->derived.ms;
+    dp.shadow = pl->shadow.p;
+    dp.shadow_ms = pl->shadow.ms;
     dp.adam = &pl->d_dyn->s.adam;
     dp.dbg = pl->dbg;
     ex.phase = "bwd";
@@ -1575,6 +1592,7 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
     dp.trace = v.trace;
     dp.trace_id = v.trace_id;
     dp.stats = pl->d_dwa_stats;
+    if (const char* knob = getenv("DRVAE_B200_DWA_DEBUG")) dp.debug_flags = atoi(knob);
     cudaError_t r = dwadam_launch(dp, st);
     ex.post();
     if (r != cudaSuccess) ex.err = r;

@@ -1200,14 +1200,18 @@ inline int gemm_pick_stages(int BN) {
   return s;
 }
 
+inline int gemm_current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < 64) ? dev : 0;
+}
 inline int gemm_num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  static int n[64] = {};
+  const int dev = gemm_current_device();
+  if (n[dev] == 0) {
+    if (cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n[dev] <= 0) n[dev] = 148;
   }
-  return n;
+  return n[dev];
 }
 
 // Tensor map of a chunk8 operand buffer: {rcap rows x 16 B (as 2 x 8-byte elements), chunks, models}, box =
@@ -1220,7 +1224,7 @@ typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, 
 inline cudaError_t gemm_c8_map(CUtensorMap* out, const GemmOperand& op, int n_models, int box_rows, int box_chunks) {
   static TmapEncodeFn encode = nullptr;
   static std::mutex mu;
-  typedef std::tuple<const void*, long long, int, int, int, int, int> Key;
+  typedef std::tuple<int, const void*, long long, int, int, int, int, int> Key;  // device first: addresses repeat across GPUs
   static std::map<Key, CUtensorMap> cache;
   std::lock_guard<std::mutex> lock(mu);
   if (!encode) {
@@ -1231,7 +1235,7 @@ inline cudaError_t gemm_c8_map(CUtensorMap* out, const GemmOperand& op, int n_mo
     if (!fp || q != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
     encode = (TmapEncodeFn)fp;
   }
-  const Key key(op.base, op.model_stride, op.rcap, op.nchunks, n_models, box_rows, box_chunks);
+  const Key key(gemm_current_device(), op.base, op.model_stride, op.rcap, op.nchunks, n_models, box_rows, box_chunks);
   auto it = cache.find(key);
   if (it != cache.end()) {
     *out = it->second;
@@ -1275,12 +1279,14 @@ inline cudaError_t gemm_launch_t(GemmProblem p, const EpiParams& e, int n_models
   size_t smem = (size_t)p.nstages * (GEMM_A_STAGE_BYTES + p.BN * GEMM_BK * 2);
   // fused Adam epilogue (scalar and vector form): 24 warps x 72 registers, its HBM stream scales with resident warps
   constexpr int EW = (EPI == EPI_GRAD_ADAM) ? GEMM_ADAM_EPI_WARPS : GEMM_EPI_WARPS;
-  static bool attr_set = false;
-  if (!attr_set) {
+  // (function attributes are per device: one process may drive several GPUs)
+  static bool attr_set[64] = {};
+  const int dev = gemm_current_device();
+  if (!attr_set[dev]) {
     cudaError_t err =
         cudaFuncSetAttribute(gemm_tc_kernel<EPI, EW, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BUDGET + 4096);
     if (err != cudaSuccess) return err;
-    attr_set = true;
+    attr_set[dev] = true;
   }
   // operand tensor maps (see the producer warp of gemm_tc_kernel)
   CUtensorMap tmA, tmB, tmB2;

@@ -106,6 +106,7 @@ struct drvae_plan {
   std::map<std::vector<long long>, GraphEntry> graphs;
   long long graph_clock = 0;
   long long graph_replays = 0;
+  long long graph_failures = 0;  // capture / instantiation failures (those combinations run as plain launches)
   // streams of the step schedule (see run_step): per model range a main stream (range 0 uses the caller's) and a side
   // stream for the label-dependent branch
   static constexpr int MAX_CHAINS = 8;
@@ -1675,7 +1676,10 @@ int step_entry(drvae_plan* pl, int seq, const drvae_batch_t* b, const drvae_nois
         if (rc || err != cudaSuccess || !graph) {
           if (graph) cudaGraphDestroy(graph);
           cudaGetLastError();
-          pl->graph_enabled = false;  // fall back to plain launches for the rest of this plan's life
+          // this (sequence, shape, buffers) combination is launched kernel by kernel from now on; other combinations
+          // may still capture.  The reason is kept for drvae_last_error()-style inspection (drvae_plan_graph_failures).
+          ge.seen = -1000000;
+          pl->graph_failures++;
           if (rc) return rc;
         } else {
           size_t n = 0;
@@ -1696,14 +1700,16 @@ int step_entry(drvae_plan* pl, int seq, const drvae_batch_t* b, const drvae_nois
             ge.graph = graph;
           } else {
             ge.exec = nullptr;
-            pl->graph_enabled = false;
+            ge.seen = -1000000;
+            pl->graph_failures++;
             cudaGraphDestroy(graph);
           }
           pl->launches = l0;
         }
       } else {
         cudaGetLastError();
-        pl->graph_enabled = false;
+        ge.seen = -1000000;
+        pl->graph_failures++;
       }
       if (pl->graphs.size() > 16) {  // bound the cache: drop the least recently used entry
         auto victim = pl->graphs.end();
@@ -1891,6 +1897,7 @@ extern "C" int drvae_set_graph(drvae_plan_t* pl, int enable) {
   return 0;
 }
 extern "C" long long drvae_plan_graph_replays(const drvae_plan_t* pl) { return pl ? pl->graph_replays : -1; }
+extern "C" long long drvae_plan_graph_failures(const drvae_plan_t* pl) { return pl ? pl->graph_failures : -1; }
 
 namespace {
 

@@ -318,6 +318,9 @@ class Plan:
     def graph_replays(self):
         return int(self.lib.drvae_plan_graph_replays(self.h))
 
+    def graph_failures(self):
+        return int(self.lib.drvae_plan_graph_failures(self.h))
+
     def set_gemm_impl(self, impl):
         _lib.check(self.lib.drvae_set_gemm_impl(self.h, {"tc": 0, "simt": 1}[impl]))
 

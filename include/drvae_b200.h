@@ -205,6 +205,8 @@ int drvae_push_scalars(drvae_plan_t* plan, const drvae_noise_t* noise, const drv
                        void* stream);
 int drvae_set_external_scalars(drvae_plan_t* plan, int enable);
 long long drvae_plan_graph_replays(const drvae_plan_t* plan);
+/* Captures that failed (that call shape then runs as plain launches; other shapes still capture): 0 on a healthy plan. */
+long long drvae_plan_graph_failures(const drvae_plan_t* plan);
 /* Step schedule: the ensemble is cut into `chains` contiguous model ranges whose forward + input-gradient chains run on
  * separate streams (their latency-bound kernels overlap); the grouped weight-gradient + Adam launch at the end covers
  * all of them.  Default 1.  Results do not depend on it (bit-identical). */

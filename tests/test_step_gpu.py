@@ -606,6 +606,7 @@ def test_graph_replay_equals_plain_launches(kind):
         assert torch.equal(ev2, ev3)
         res[mode] = (losses, plan.params.cpu().clone(), ev, plan.graph_replays())
     assert res["graph"][3] >= 4 and res["plain"][3] == 0, (res["graph"][3], res["plain"][3])
+    assert plan.graph_failures() == 0
     for a, b in zip(res["graph"][0], res["plain"][0]):
         assert torch.equal(a, b)
     assert torch.equal(res["graph"][1], res["plain"][1])
@@ -785,3 +786,33 @@ def test_device_resident_dataset_indexing_equals_gathered_batches(kind):
             assert plan.graph_replays() >= 2
     assert torch.equal(res["indexed"][0], res["gathered"][0])
     assert torch.equal(res["indexed"][1], res["gathered"][1])
+
+
+@pytest.mark.parametrize("N", (511, 512))
+def test_both_sides_of_the_fused_optimizer_threshold(N):
+    """drvae_train_step fuses Adam into the weight-gradient launch below N * L = 1024 rows (single model) and switches to
+    split-K gradients + the stand-alone optimizer from there on (plan.cu train_is_fused).  One row below and exactly at
+    the threshold: same losses as the emulating oracle, and after the step the parameters of the two regimes agree
+    with what gradient + drvae_adam_step gives."""
+    kind, arch = "drvae", ARCH["tiny"]
+    sd = init_state_dict(kind, seed=SEED_MODEL, **arch)
+    batch = orc.synthetic_batch(N, arch["dim_x"], seed=8)
+    om = orc.OracleModel(sd, orc.default_cfg(kind, L=L))
+    om.iters = 1
+    tape = orc.Tape(seed=17)
+    lo_emu, _ = om.grads(batch, tape, emulate_bf16=True)
+    res = []
+    for mode in ("train", "split"):
+        plan = Plan(kind, L=L, max_batch=N, n_models=1, **arch)
+        plan.load_state_dict(sd)
+        eps = eps_block_from_tape(plan, tape.log, batch["has_x2"], batch["has_y"], noisy=True)
+        hp = plan.hparams(step=1)
+        if mode == "train":
+            out = plan.train_step(batch_fields(kind, batch), hp, eps=eps)
+        else:
+            out = plan.grad_step(batch_fields(kind, batch), hp, eps=eps)
+            plan.adam_step(hp)
+        check_losses(loss_dict(kind, out), lo_emu, 5e-5, "N=%d %s" % (N, mode))
+        res.append(plan.params.cpu().clone())
+    assert torch.allclose(res[0], res[1], rtol=1e-5, atol=2e-7)
+    assert not torch.equal(res[0], torch.zeros_like(res[0]))

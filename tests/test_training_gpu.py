@@ -53,3 +53,50 @@ def test_fit_reduces_the_training_loss_and_learns_the_labels():
     assert float(after["losses"]["RECL"]) > float(before["losses"]["RECL"]), (float(before["losses"]["RECL"]), float(after["losses"]["RECL"]))
     assert after["y_auroc"] > 0.65 and after["y_auroc"] > before["y_auroc"], (before["y_auroc"], after["y_auroc"])
     assert model.finished_training_iters == 30 * len(loader)
+
+
+@pytest.mark.gpu
+def test_ensemble_checkpoints_interchange_with_the_reference_format(tmp_path):
+    """Batched save / load of an ensemble's state_dicts (reference keys, order, shapes: one .pth per member, loadable by
+    DGMMixin.load_params_from_file), and a resume file (parameters + Adam moments + step) that continues bit-exactly."""
+    import numpy as np
+    from helpers import ARCH, L, batch_fields, golden, orc
+    from drvae_b200 import checkpoint as ckpt
+    from drvae_b200.init import init_state_dict
+    from drvae_b200.plan import Plan, anneal_coef
+    kind, arch, N, E = "drvae", ARCH["tiny"], 24, 5
+    sds = [init_state_dict(kind, seed=50 + m, **arch) for m in range(E)]
+    batches = [batch_fields(kind, orc.synthetic_batch(N, arch["dim_x"], seed=m)) for m in range(E)]
+    big = {k: torch.stack([b[k] for b in batches]).contiguous().cuda() for k in batches[0]}
+
+    def fresh():
+        p = Plan(kind, L=L, max_batch=N, n_models=E, **arch)
+        ckpt.load_ensemble(p, sds)
+        return p
+
+    a = fresh()
+    for it in range(3):
+        a.train_step(big, a.hparams(step=it, beta_pert=anneal_coef(it, 1, 0)), seed=2)
+    paths = ckpt.save_ensemble(a, str(tmp_path / "member{:02d}.pth"))
+    ref_keys = [k[3:] for k in golden(kind, "tiny").files if k.startswith("sd/")]
+    for m, path in enumerate(paths):
+        sd = torch.load(path)
+        assert list(sd.keys()) == ref_keys  # the reference's state_dict keys in the reference's order
+        for k, v in sd.items():
+            assert v.is_contiguous() and tuple(v.shape) == tuple(sds[m][k].shape)
+            assert torch.equal(v, a.tensor_views(a.params, m)[k].cpu())
+    b = Plan(kind, L=L, max_batch=N, n_models=E, **arch)
+    ckpt.load_ensemble(b, paths)
+    assert torch.equal(a.params, b.params)
+    # resume: 3 steps + save + 2 steps  ==  load + 2 steps
+    ckpt.save_resume(a, str(tmp_path / "resume.pt"), step=3)
+    c = Plan(kind, L=L, max_batch=N, n_models=E, **arch)
+    step = ckpt.load_resume(c, str(tmp_path / "resume.pt"))
+    assert step == 3
+    for it in range(3, 5):
+        la = a.train_step(big, a.hparams(step=it, beta_pert=1.0), seed=2).cpu().clone()
+        lc = c.train_step(big, c.hparams(step=it, beta_pert=1.0), seed=2).cpu().clone()
+        assert torch.equal(la, lc)
+    assert torch.equal(a.params, c.params) and torch.equal(a.adam_v, c.adam_v)
+    with pytest.raises(ValueError):
+        ckpt.load_ensemble(b, paths[:-1])

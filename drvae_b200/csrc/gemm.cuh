@@ -1262,6 +1262,23 @@ inline cudaError_t gemm_c8_map(CUtensorMap* out, const GemmOperand& op, int n_mo
   return cudaSuccess;
 }
 
+// The three operand tensor maps of one problem (A tile, B tile, second half of a K-major B tile wider than 128 rows).
+inline cudaError_t gemm_make_maps(const GemmProblem& p, int n_models, CUtensorMap* tmA, CUtensorMap* tmB, CUtensorMap* tmB2) {
+  const int ens = p.ens > 0 ? p.ens : n_models;
+  const bool a_mn = p.mode == GEMM_DW, b_mn = p.mode != GEMM_NT;
+  cudaError_t err = a_mn ? gemm_c8_map(tmA, p.A, ens, GEMM_BK, GEMM_BM / 8) : gemm_c8_map(tmA, p.A, ens, GEMM_BM, GEMM_BK / 8);
+  if (err != cudaSuccess) return err;
+  if (b_mn) {
+    err = gemm_c8_map(tmB, p.B, ens, GEMM_BK, p.BN / 8);
+    *tmB2 = *tmB;
+  } else {
+    err = gemm_c8_map(tmB, p.B, ens, p.BN > 128 ? 128 : p.BN, GEMM_BK / 8);
+    if (err == cudaSuccess && p.BN > 128) err = gemm_c8_map(tmB2, p.B, ens, p.BN - 128, GEMM_BK / 8);
+    if (p.BN <= 128) *tmB2 = *tmB;
+  }
+  return err;
+}
+
 template <int EPI, int VEC = 1>
 inline cudaError_t gemm_launch_t(GemmProblem p, const EpiParams& e, int n_models, int impl, cudaStream_t st) {
   p.n_models = n_models;
@@ -1290,18 +1307,7 @@ inline cudaError_t gemm_launch_t(GemmProblem p, const EpiParams& e, int n_models
   }
   // operand tensor maps (see the producer warp of gemm_tc_kernel)
   CUtensorMap tmA, tmB, tmB2;
-  const int ens = p.ens > 0 ? p.ens : n_models;
-  const bool a_mn = p.mode == GEMM_DW, b_mn = p.mode != GEMM_NT;
-  cudaError_t err = a_mn ? gemm_c8_map(&tmA, p.A, ens, GEMM_BK, GEMM_BM / 8) : gemm_c8_map(&tmA, p.A, ens, GEMM_BM, GEMM_BK / 8);
-  if (err != cudaSuccess) return err;
-  if (b_mn) {
-    err = gemm_c8_map(&tmB, p.B, ens, GEMM_BK, p.BN / 8);
-    tmB2 = tmB;
-  } else {
-    err = gemm_c8_map(&tmB, p.B, ens, p.BN > 128 ? 128 : p.BN, GEMM_BK / 8);
-    if (err == cudaSuccess && p.BN > 128) err = gemm_c8_map(&tmB2, p.B, ens, p.BN - 128, GEMM_BK / 8);
-    if (p.BN <= 128) tmB2 = tmB;
-  }
+  cudaError_t err = gemm_make_maps(p, n_models, &tmA, &tmB, &tmB2);
   if (err != cudaSuccess) return err;
   const int grid = total < gemm_num_sms() ? total : gemm_num_sms();  // persistent: one CTA per SM
   return launch_k(gemm_tc_kernel<EPI, EW, VEC>, dim3(grid), dim3((GEMM_PROD_WARPS + 1 + EW) * 32), smem, st, 1, p, e, tmA, tmB, tmB2);

@@ -18,6 +18,7 @@
 #include "optim.cuh"
 #include "plan.h"
 #include "rowops.cuh"
+#include "stepk.cuh"
 
 using namespace drvae;
 
@@ -59,7 +60,7 @@ struct drvae_plan {
   Seg* d_segs = nullptr;
   std::vector<int> h_tabs;  // gradient-epilogue tables of every weight (see make_shadow)
   int* d_tabs = nullptr;
-  int sched = 1;              // measurement knob (DRVAE_B200_SCHED): bit 0 = noise generator, bit 1 = classifier backward on the side stream (measured: 1.037 / 1.027 / 1.048 / 1.048 ms for 0 / 1 / 2 / 3)
+  int sched = 5;              // schedule knob (DRVAE_B200_SCHED): bit 0 = noise generator on the side stream, bit 2 = classifier weight gradient at the tail of the side stream, bit 1 = whole classifier backward on the side stream (measured: 1.037 / 1.027 / 1.048 / 1.048 ms for 0 / 1 / 2 / 3)
   int adam_vec_max = 4;       // debug knob (DRVAE_B200_ADAM_VEC): cap on the vector width of the fused Adam epilogue
   bool wn = false;            // layers.WeightNormLinear instead of nn.Linear
   std::vector<WnRow> wn_rows;
@@ -133,6 +134,11 @@ struct drvae_plan {
   bool dwa_ok = false;       // every layer fits the kernel's layout conditions and the state is bound
   unsigned long long* d_dwa_stats = nullptr;  // drvae_debug_dwa_stats
   bool dwa_enabled = true;   // measurement knob (DRVAE_B200_DWADAM=0: per-layer fused kernels of round 1)
+  // persistent step kernel (stepk.cuh): the forward + input-gradient chain as one cooperative launch
+  bool stepk_enabled = false;          // drvae_set_step_kernel / DRVAE_B200_STEPK (measured slower than the graph of launches: profiles/r02_experiments.md)
+  bool stepk_unsupported = false;      // a recorded sequence did not fit the kernel's tables: this plan launches kernel by kernel
+  unsigned int* d_stepk_bar = nullptr; // {arrival count, generation}
+  long long stepk_launches = 0;
   // data-parallel exchange over peer memory (dp_peer.cuh): attached by drvae_dp_attach
   bool dp_on = false;
   DpPeers dp{};
@@ -566,6 +572,9 @@ extern "C" int drvae_plan_create(const drvae_arch_t* a, int n_models, drvae_plan
   if (const char* knob = getenv("DRVAE_B200_ADAM_VEC")) pl->adam_vec_max = atoi(knob);  // measurement knob
   if (const char* knob = getenv("DRVAE_B200_SCHED")) pl->sched = atoi(knob);
   if (const char* knob = getenv("DRVAE_B200_DWADAM")) pl->dwa_enabled = atoi(knob) != 0;
+  if (const char* knob = getenv("DRVAE_B200_STEPK")) pl->stepk_enabled = atoi(knob) != 0;
+  cudaMalloc(&pl->d_stepk_bar, 2 * sizeof(unsigned int));
+  cudaMemset(pl->d_stepk_bar, 0, 2 * sizeof(unsigned int));
   if (const char* knob = getenv("DRVAE_B200_PDL")) pdl_mask() = atoi(knob);  // measurement knob: programmatic dependent launch
   pl->chains = 1;  // measured (32 models): 0.970 / 1.002 / 1.020 / 1.054 ms for 1 / 2 / 4 / 8 ranges
   if (const char* knob = getenv("DRVAE_B200_CHAINS")) pl->chains = std::max(1, atoi(knob));
@@ -692,6 +701,7 @@ extern "C" int drvae_plan_destroy(drvae_plan_t* pl) {
   if (pl->f32ws) cudaFree(pl->f32ws);
   if (pl->d_trace) cudaFree(pl->d_trace);
   if (pl->d_dwa_stats) cudaFree(pl->d_dwa_stats);
+  if (pl->d_stepk_bar) cudaFree(pl->d_stepk_bar);
   for (auto& ev : pl->bucket_ev) cudaEventDestroy(ev);
   for (auto& ch : pl->chain) {
     for (int i = 0; i < 10; ++i)
@@ -755,6 +765,13 @@ extern "C" int drvae_set_chains(drvae_plan_t* pl, int chains) {
   drop_graphs(pl);
   return 0;
 }
+extern "C" int drvae_set_step_kernel(drvae_plan_t* pl, int enable) {
+  if (!pl) return set_error("drvae_set_step_kernel: null plan");
+  if (pl->stepk_enabled != (enable != 0)) drop_graphs(pl);
+  pl->stepk_enabled = enable != 0;
+  return 0;
+}
+extern "C" long long drvae_plan_step_kernel_launches(const drvae_plan_t* pl) { return pl ? pl->stepk_launches : -1; }
 extern "C" int drvae_debug_side_delay(drvae_plan_t* pl, long long cycles) {
   if (!pl || cycles < 0) return set_error("drvae_debug_side_delay: bad argument");
   pl->side_delay_cycles = cycles;
@@ -915,7 +932,33 @@ struct Exec {
   bool splitk = false;       // split-K weight gradients (large minibatches, unfused path)
   int model0 = 0, Ec = 0;    // model range of the launches being enqueued (Ec = 0: the whole ensemble)
   bool defer_dw = false;     // weight gradients + Adam of every layer in ONE launch at the end of backward (dwadam.cuh)
+  StepRecorder* rec = nullptr;  // non-null: launches are recorded as ops of the persistent step kernel (stepk.cuh)
   bool ok() const { return err == cudaSuccess; }
+  // stream dependencies: real events, or level bookkeeping while recording
+  void ev_record(cudaEvent_t ev, cudaStream_t s) {
+    if (rec)
+      rec->record_event(ev, s);
+    else
+      cudaEventRecord(ev, s);
+  }
+  void ev_wait(cudaStream_t s, cudaEvent_t ev) {
+    if (rec)
+      rec->wait_event(s, ev);
+    else
+      cudaStreamWaitEvent(s, ev, 0);
+  }
+  // one row operation: `per_model` items of STEPK_ROWS rows (or kernel-specific blocks) per ensemble member
+  template <class F>
+  void row_op(int kind, const char* name, int per_model, int arg, F&& real_launch) {
+    if (!ok()) return;
+    if (rec) {
+      rec->add_row(kind, per_model, model0, Ec > 0 ? Ec : pl->E, arg, st, std::string(phase) + ":" + name);
+      return;
+    }
+    pre(name);
+    real_launch();
+    chk();
+  }
   // event bracket around one launch when profiling is on
   void pre(const std::string& op) {
     prof_pre(pl, st, std::string(phase) + ":" + op);
@@ -949,9 +992,15 @@ struct Exec {
     p.dbg = pl->dbg;
     p.desc_variant = 0;
     if (p.ksplit < 1) p.ksplit = 1;
-    pre(op);
     p.model0 = model0;
     p.ens = pl->E;
+    if (rec) {
+      p.trace = nullptr;
+      p.trace_id = 0;
+      rec->add_gemm(epi, p, e, Ec > 0 ? Ec : pl->E, st, std::string(phase) + ":" + op);
+      return;
+    }
+    pre(op);
     p.trace = v.trace;
     p.trace_id = v.trace_id;
     cudaError_t r = gemm_launch(epi, p, e, Ec > 0 ? Ec : pl->E, pl->gemm_impl, st);
@@ -1331,11 +1380,17 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
     if (most >= (1LL << 31)) return set_error("drvae: minibatch too large for the noise generator");
   }
 
+  // Persistent step kernel (stepk.cuh): everything between the input preparation and the grouped dW+Adam launch is
+  // recorded (same code below, same dependencies) and runs as ONE cooperative launch.
+  const bool use_stepk = pl->stepk_enabled && !pl->stepk_unsupported && pl->gemm_impl == GEMM_IMPL_TC &&
+                         !(backward && fused_adam && !ex.defer_dw) && pl->d_stepk_bar != nullptr;
+  StepRecorder recorder;
+
   // model ranges: separate chains only where the gradient buckets are not consumed outside (drvae_grad_step records
   // one event per bucket on ONE stream) and not under per-launch profiling
   int K = 1;
-  if (!pl->prof_on && !(backward && !fused_adam)) K = std::max(1, std::min({pl->chains, E, (int)drvae_plan::MAX_CHAINS}));
-  const bool own_main = pl->main_prio && !pl->prof_on && !(backward && !fused_adam) && pl->has_fprop && pl->overlap;
+  if (!use_stepk && !pl->prof_on && !(backward && !fused_adam)) K = std::max(1, std::min({pl->chains, E, (int)drvae_plan::MAX_CHAINS}));
+  const bool own_main = !use_stepk && pl->main_prio && !pl->prof_on && !(backward && !fused_adam) && pl->has_fprop && pl->overlap;
   if (K > 1 || own_main) cudaEventRecord(pl->ev_begin, st);
 
   for (int c = 0; c < K && ex.ok(); ++c) {
@@ -1351,26 +1406,23 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
     ex.Ec = Ec;
     ex.st = cm;
     auto rows_grid = [&](int rows) { return dim3(cdiv(rows, ROW_WARPS), Ec); };
+    auto row_items = [&](int rows) { return cdiv(rows, STEPK_ROWS); };
     // Two-stream schedule inside a range: everything that is not on the longest dependency chain runs on the range's
     // side stream — the latent-noise generator (next to rowmap / prep / the encoder), the label-dependent branch and
-    // the loss reduction.
+    // the loss reduction.  (While recording for the step kernel the two "streams" only define the levels.)
     const bool overlap = pl->has_fprop && pl->overlap && !pl->prof_on;
     cudaStream_t side = overlap ? ch.side : cm;
     auto on = [&](cudaStream_t s) { ex.st = s; };
     auto after = [&](cudaStream_t waiter, cudaEvent_t ev, cudaStream_t producer) {
       if (!overlap || waiter == producer) return;
+      if (ex.rec) {
+        ex.rec->after(waiter, producer);
+        return;
+      }
       cudaEventRecord(ev, producer);
       cudaStreamWaitEvent(waiter, ev, 0);
     };
-    ex.pre("rowmap");
-    launch_k(rowmap_kernel, dim3(Ec), dim3(ROWMAP_THREADS), 0, cm, 2, v);
-    ex.chk();
-    ex.pre("prep");
-    launch_k(prep_kernel, dim3(round_up(R0b, 128) / PREP_ROWS, cdiv(pl->view.Xc, PREP_SLAB), Ec), dim3(PREP_THREADS), 0, cm, 2, v);
-    ex.chk();
-    // latent noise: on the side stream, forked AFTER prep so that it fills the SMs next to the encoder GEMMs instead of
-    // running in front of prep (it is first needed by sample_q1)
-    if (own_eps) {
+    auto launch_noise = [&]() {
       const drvae_eps_layout_t& el = pl->epsl;
       EpsSegs sg{};
       const long long offs[6] = {el.off_x1, el.off_x2, el.off_z1, el.off_z2, el.off_z2f, el.off_z3};
@@ -1385,14 +1437,38 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
         most = std::max(most, (long long)outer[i] * N * ((inner[i] + 3) / 4));
       }
       dim3 g((unsigned)((most + 255) / 256), Ec, 6);
+      ex.pre("philox_normal");
+      launch_k(philox_normal_kernel, g, dim3(256), 0, ex.st, 2, pl->eps_own, sg, N, pl->Ncap, pl->d_dyn, m0, v.trace, v.trace_id);
+      ex.chk();
+    };
+    // step kernel: the noise generator needs only this step's scalars, so it is forked first and overlaps rowmap / prep
+    if (use_stepk && own_eps) {
+      if (overlap) {
+        after(side, ch.ev_begin, cm);
+        on(side);
+      }
+      launch_noise();
+      on(cm);
+    }
+    ex.pre("rowmap");
+    launch_k(rowmap_kernel, dim3(Ec), dim3(ROWMAP_THREADS), 0, cm, 2, v);
+    ex.chk();
+    ex.pre("prep");
+    launch_k(prep_kernel, dim3(round_up(R0b, 128) / PREP_ROWS, cdiv(pl->view.Xc, PREP_SLAB), Ec), dim3(PREP_THREADS), 0, cm, 2, v);
+    ex.chk();
+    // latent noise: on the side stream, forked AFTER prep so that it fills the SMs next to the encoder GEMMs instead of
+    // running in front of prep (it is first needed by sample_q1)
+    if (own_eps && !use_stepk) {
       if (pl->sched & 1) {
         after(side, ch.ev_begin, cm);  // after this step's scalars (set_dyn), rowmap and prep
         on(side);
       }
-      ex.pre("philox_normal");
-      launch_k(philox_normal_kernel, g, dim3(256), 0, ex.st, 2, pl->eps_own, sg, N, pl->Ncap, pl->d_dyn, m0, v.trace, v.trace_id);
-      ex.chk();
+      launch_noise();
       on(cm);
+    }
+    if (use_stepk) {
+      if (own_eps) after(cm, ch.ev_eps, side);  // the step kernel starts after the noise generator
+      ex.rec = &recorder;
     }
 
     // ---- encoder q(z1|x1), shared with q(z2|x2) (DrVAE.py:408,418) ----
@@ -1400,10 +1476,10 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
     ex.block_hidden_fwd(pl->enc, v.Ain, 0, CNT_R0, R0b);
     ex.gemm_nt(pl->enc.H.back(), 0, pl->enc.head, EPI_STORE_F32,
                ex.epi_f32(v.Q.p, v.Q.ms, 2 * pl->view.Zs, 2 * pl->view.Zs, &pl->enc.head), CNT_R0, R0b);
-    if (own_eps && (pl->sched & 1)) after(cm, ch.ev_eps, side);  // latent noise of this step
-    ex.pre("sample_q1");
-    launch_k(pl->view.Zc <= 128 ? sample_q1_kernel<4> : sample_q1_kernel<MAXJ>, rows_grid(N + PAD_WARPS), dim3(ROW_THREADS), 0, cm, 2, v);
-    ex.chk();
+    if (own_eps && (pl->sched & 1) && !use_stepk) after(cm, ch.ev_eps, side);  // latent noise of this step
+    ex.row_op(SROW_SAMPLE_Q1, "sample_q1", row_items(N + PAD_WARPS), 0, [&]() {
+      launch_k(pl->view.Zc <= 128 ? sample_q1_kernel<4> : sample_q1_kernel<MAXJ>, rows_grid(N + PAD_WARPS), dim3(ROW_THREADS), 0, cm, 2, v);
+    });
     // The label-dependent branch (q(z_top|z1,y) -> p(z1|z_top,y), forward and backward dX: small GEMMs + row kernels
     // that leave most SMs idle) is independent of the decoder branch: side stream between a fork here and a join
     // before the encoder backward.
@@ -1415,25 +1491,30 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
       ex.block_hidden_fwd(pl->z3b, v.Z1e, 0, CNT_F, Fb);
       ex.gemm_nt(pl->z3b.H.back(), 0, pl->z3b.head, EPI_STORE_F32,
                  ex.epi_f32(v.Q3.p, v.Q3.ms, 2 * pl->view.Z3s, 2 * pl->view.Z3s, &pl->z3b.head), CNT_F, Fb);
-      ex.pre("z3_post");
-      launch_k(z3_post_kernel, rows_grid(round_up(Fb, 128)), dim3(ROW_THREADS), 0, ex.st, 2, v);
-      ex.chk();
+      ex.row_op(SROW_Z3_POST, "z3_post", row_items(round_up(Fb, 128)), 0,
+                [&]() { launch_k(pl->view.Z3c <= 128 ? z3_post_kernel<4> : z3_post_kernel<MAXJ>, rows_grid(round_up(Fb, 128)), dim3(ROW_THREADS), 0, ex.st, 2, v); });
       ex.phase = "dz1.fwd";
       ex.block_hidden_fwd(pl->dz1b, v.Z3b, 0, CNT_F, Fb);
       ex.gemm_nt(pl->dz1b.H.back(), 0, pl->dz1b.head, EPI_STORE_F32,
                  ex.epi_f32(v.PZ1.p, v.PZ1.ms, 2 * pl->view.Zs, 2 * pl->view.Zs, &pl->dz1b.head), CNT_F, Fb);
     };
-    auto clf_bwd = [&]() {
+    auto clf_back = [&]() {
       ex.phase = "clf.bwd";
-      ex.pre("clf_back");
-      launch_k(clf_back_kernel, rows_grid(LNb), dim3(ROW_THREADS), 0, ex.st, 2, v);
-      ex.chk();
-      ex.pre("clf_grad_partial");
-      launch_k(clf_grad_partial_kernel, dim3(v.clf_splits, Ec), dim3(256), 0, ex.st, 2, v);
-      ex.chk();
-      ex.pre("clf_grad_reduce");
-      launch_k(clf_grad_reduce_kernel, dim3(cdiv(pl->Y * (pl->clf_in + 1), 8), Ec), dim3(256), 0, ex.st, 2, v);
-      ex.chk();
+      ex.row_op(SROW_CLF_BACK, "clf_back", row_items(LNb), 0,
+                [&]() { launch_k(clf_back_kernel, rows_grid(LNb), dim3(ROW_THREADS), 0, ex.st, 2, v); });
+    };
+    // classifier weight gradient (+ Adam in the fused step): feeds nothing but the optimizer
+    auto clf_grad = [&]() {
+      ex.phase = "clf.bwd";
+      ex.row_op(SROW_CLF_GRAD_PARTIAL, "clf_grad_partial", v.clf_splits, 0,
+                [&]() { launch_k(clf_grad_partial_kernel, dim3(v.clf_splits, Ec), dim3(256), 0, ex.st, 2, v); });
+      ex.row_op(SROW_CLF_GRAD_REDUCE, "clf_grad_reduce", row_items(pl->Y * (pl->clf_in + 1)), 0, [&]() {
+        launch_k(clf_grad_reduce_kernel, dim3(cdiv(pl->Y * (pl->clf_in + 1), 8), Ec), dim3(256), 0, ex.st, 2, v);
+      });
+    };
+    auto clf_bwd = [&]() {
+      clf_back();
+      clf_grad();
     };
     if (pl->has_fprop) {
       on(side);
@@ -1444,40 +1525,38 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
     ex.phase = "T.fwd";
     if (pl->has_T) {
       ex.gemm_nt(v.Zdec, 0, pl->Tsh, EPI_STORE_F32, ex.epi_f32(v.PT.p, v.PT.ms, 2 * pl->view.Zs, 2 * pl->view.Zs, &pl->Tsh), CNT_LN, LNb);
-      ex.pre("T_post");
-      launch_k(pl->view.Zc <= 128 ? T_post_kernel<4> : T_post_kernel<MAXJ>, rows_grid(N + PAD_WARPS), dim3(ROW_THREADS), 0, ex.st, 2, v);
-      ex.chk();
+      ex.row_op(SROW_T_POST, "T_post", row_items(N + PAD_WARPS), 0, [&]() {
+        launch_k(pl->view.Zc <= 128 ? T_post_kernel<4> : T_post_kernel<MAXJ>, rows_grid(N + PAD_WARPS), dim3(ROW_THREADS), 0, ex.st, 2, v);
+      });
     }
     if (pl->has_fprop) {
       // pz1_post weighs unlabeled evaluations by q(y|.), which the classifier in T_post (DrVAE) or
       // sample_q1 (VFAE) has just produced
       after(side, ch.ev_qy, cm);
       on(side);
-      if (pl->side_delay_cycles > 0) spin_kernel<<<1, 1, 0, ex.st>>>(pl->side_delay_cycles);
-      ex.pre("pz1_post");
-      launch_k(pz1_post_kernel, rows_grid(round_up(Fb, 128)), dim3(ROW_THREADS), 0, ex.st, 2, v);
-      ex.chk();
+      if (pl->side_delay_cycles > 0 && !ex.rec) spin_kernel<<<1, 1, 0, ex.st>>>(pl->side_delay_cycles);
+      ex.row_op(SROW_PZ1_POST, "pz1_post", row_items(round_up(Fb, 128)), 0,
+                [&]() { launch_k(pl->view.Zc <= 128 ? pz1_post_kernel<4> : pz1_post_kernel<MAXJ>, rows_grid(round_up(Fb, 128)), dim3(ROW_THREADS), 0, ex.st, 2, v); });
       // clf_back (main stream) reads the per-class KL terms pz1_post has just written (kfp_row)
-      if (overlap && backward && pl->has_clf && !(pl->sched & 2)) cudaEventRecord(ch.ev_kfp, ex.st);
+      if (overlap && backward && pl->has_clf && !(pl->sched & 2)) ex.ev_record(ch.ev_kfp, ex.st);
       if (backward) {
         if (pl->has_clf && (pl->sched & 2)) {
           // classifier backward: needs only q(y|.) (T_post / sample_q1) and the per-class terms pz1_post has just
           // written, so it leaves the main stream's chain; T_back / q_back wait for ev_clf
           clf_bwd();
-          cudaEventRecord(pl->bucket_ev[3], ex.st);  // buckets: dz1, z3 (this stream), dec, clf, ...
-          if (overlap) cudaEventRecord(ch.ev_clf, ex.st);
+          if (!ex.rec) cudaEventRecord(pl->bucket_ev[3], ex.st);  // buckets: dz1, z3 (this stream), dec, clf, ...
+          if (overlap) ex.ev_record(ch.ev_clf, ex.st);
         }
         ex.phase = "dz1.bwd";
         ex.block_bwd(pl->dz1b, v.dY9, v.Z3b, 0, pl->Z3, v.dZ3.p, v.dZ3.ms, CNT_F, Fb);
-        cudaEventRecord(pl->bucket_ev[0], ex.st);
-        ex.pre("z3_back");
-        launch_k(z3_back_kernel, rows_grid(round_up(Fb, 128)), dim3(ROW_THREADS), 0, ex.st, 2, v);
-        ex.chk();
+        if (!ex.rec) cudaEventRecord(pl->bucket_ev[0], ex.st);
+        ex.row_op(SROW_Z3_BACK, "z3_back", row_items(round_up(Fb, 128)), 0,
+                  [&]() { launch_k(pl->view.Z3c <= 128 ? z3_back_kernel<4> : z3_back_kernel<MAXJ>, rows_grid(round_up(Fb, 128)), dim3(ROW_THREADS), 0, ex.st, 2, v); });
         ex.phase = "z3.bwd";
         ex.block_bwd(pl->z3b, v.dY7, v.Z1e, 0, pl->Z, v.dZ1e.p, v.dZ1e.ms, CNT_F, Fb);
-        cudaEventRecord(pl->bucket_ev[1], ex.st);
+        if (!ex.rec) cudaEventRecord(pl->bucket_ev[1], ex.st);
         // what q_back needs from this stream; the loss reduction that follows here is joined at the end of the step only
-        if (overlap) cudaEventRecord(ch.ev_side_bwd, ex.st);
+        if (overlap) ex.ev_record(ch.ev_side_bwd, ex.st);
       }
       on(cm);
     }
@@ -1512,54 +1591,110 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
     after(side, ch.ev_side_fwd, cm);
     on(side);
     ex.phase = "";
-    ex.pre("loss");
-    launch_k(loss_partial_kernel, dim3(v.loss_slices, Ec), dim3(256), 0, ex.st, 2, v);
-    ex.chk();
-    ex.pre("loss_final");
-    launch_k(loss_final_kernel, dim3(Ec), dim3(32), 0, ex.st, 2, v);
-    ex.chk();
-    if (losses_out && ex.ok()) {
+    ex.row_op(SROW_LOSS_PARTIAL, "loss", v.loss_slices, v.loss_slices,
+              [&]() { launch_k(loss_partial_kernel, dim3(v.loss_slices, Ec), dim3(256), 0, ex.st, 2, v); });
+    ex.row_op(SROW_LOSS_FINAL, "loss_final", 1, 0, [&]() { launch_k(loss_final_kernel, dim3(Ec), dim3(32), 0, ex.st, 2, v); });
+    if (losses_out && ex.ok() && !ex.rec) {
       // losses buffer per model is padded to 256 B in the arena; the caller's is dense [E][8]
       ex.err = cudaMemcpy2DAsync(losses_out + 8 * (size_t)m0, 8 * sizeof(float), v.losses.at(m0), v.losses.ms * sizeof(float),
                                  8 * sizeof(float), Ec, cudaMemcpyDeviceToDevice, ex.st);
     }
-    if (overlap) cudaEventRecord(ch.ev_side_end, side);  // everything the side stream does in this step
+    if (overlap) ex.ev_record(ch.ev_side_end, side);  // everything the side stream does in this step
     on(cm);
 
     if (backward && ex.ok()) {
       size_t bk = pl->has_fprop ? 2 : 0;  // buckets 0, 1 (decoder_z1, encoder_z3) were recorded by the side branch
-      auto bucket_done = [&]() { cudaEventRecord(pl->bucket_ev[bk++], ex.st); };
+      auto bucket_done = [&]() {
+        if (!ex.rec) cudaEventRecord(pl->bucket_ev[bk], ex.st);
+        ++bk;
+      };
       ex.phase = "dec.bwd";
       ex.block_bwd(pl->dec, pl->dY5, v.Zdec, 0, pl->Z, v.dZdec.p, v.dZdec.ms, CNT_RD, Rdb);
       bucket_done();
       if (pl->has_clf) {
         if (pl->has_fprop && (pl->sched & 2)) {
           ++bk;  // ran on the side stream right after pz1_post (bucket event recorded there)
-          if (overlap) cudaStreamWaitEvent(cm, ch.ev_clf, 0);
+          if (overlap) ex.ev_wait(cm, ch.ev_clf);
         } else {
-          if (overlap && pl->has_fprop) cudaStreamWaitEvent(cm, ch.ev_kfp, 0);
-          clf_bwd();
-          bucket_done();
+          if (overlap && pl->has_fprop) ex.ev_wait(cm, ch.ev_kfp);
+          if (overlap && forked && (pl->sched & 4)) {
+            // only the input gradient (clf_back) is on the chain towards T_back / q_back; the weight gradient runs on
+            // the caller's stream, which is otherwise idle until this range joins it in front of the dW+Adam launch
+            clf_back();
+            after(st, ch.ev_clf, cm);
+            on(st);
+            clf_grad();
+            bucket_done();
+            on(cm);
+          } else {
+            clf_bwd();
+            bucket_done();
+          }
         }
       }
       if (pl->has_T) {
         ex.phase = "T.bwd";
-        ex.pre("T_back");
-        launch_k(T_back_kernel, rows_grid(N + PAD_WARPS), dim3(ROW_THREADS), 0, ex.st, 2, v);
-        ex.chk();
+        ex.row_op(SROW_T_BACK, "T_back", row_items(N + PAD_WARPS), 0,
+                  [&]() { launch_k(pl->view.Zc <= 128 ? T_back_kernel<4> : T_back_kernel<MAXJ>, rows_grid(N + PAD_WARPS), dim3(ROW_THREADS), 0, ex.st, 2, v); });
         ex.gemm_dx(v.dYT, pl->Tsh, EPI_STORE_F32, ex.epi_f32(v.dZ1T.p, v.dZ1T.ms, pl->Z, pl->Z, nullptr), CNT_LN, LNb);
         ex.gemm_dw(v.dYT, v.Zdec, 0, pl->Tsh, CNT_LN, LNb, pl->arch.kind == DRVAE_KIND_PVAE ? CNT_NP : -1);
         bucket_done();
       }
-      if (overlap) cudaStreamWaitEvent(cm, ch.ev_side_bwd, 0);  // join: q_back sums the side branch's gradients into q(z1|x1)
+      if (overlap) ex.ev_wait(cm, ch.ev_side_bwd);  // join: q_back sums the side branch's gradients into q(z1|x1)
       ex.phase = "enc.bwd";
-      ex.pre("q_back");
-      launch_k(q_back_kernel, rows_grid(N + PAD_WARPS), dim3(ROW_THREADS), 0, ex.st, 2, v);
-      ex.chk();
+      ex.row_op(SROW_Q_BACK, "q_back", row_items(N + PAD_WARPS), 0,
+                [&]() { launch_k(pl->view.Zc <= 128 ? q_back_kernel<4> : q_back_kernel<MAXJ>, rows_grid(N + PAD_WARPS), dim3(ROW_THREADS), 0, ex.st, 2, v); });
       ex.block_bwd(pl->enc, v.dY2, v.Ain, 0, pl->X, nullptr, 0, CNT_R0, R0b);
       bucket_done();
     }
-    if (overlap) cudaStreamWaitEvent(cm, ch.ev_side_end, 0);
+    if (overlap) ex.ev_wait(cm, ch.ev_side_end);
+    if (ex.rec && ex.ok()) {
+      // ---- the recorded chain as one cooperative launch ----
+      ex.rec = nullptr;
+      ex.st = cm;
+      ex.phase = "step";
+      StepParams* sp = new StepParams();
+      std::vector<std::string> tags;
+      int max_items = 1;
+      cudaError_t ferr = recorder.finalize(*sp, tags, max_items);
+      if (ferr == cudaErrorNotSupported) {
+        // more ops than the kernel's tables hold (very deep blocks): this plan keeps the launch-per-kernel schedule.
+        // What has been issued so far (noise, rowmap, prep) is idempotent, so the sequence is simply enqueued again.
+        delete sp;
+        cudaGetLastError();
+        pl->stepk_unsupported = true;
+        return run_step(pl, b, nz, hp, losses_out, st, backward, fused_adam);
+      }
+      if (ferr != cudaSuccess) {
+        delete sp;
+        return set_cuda_error("drvae step kernel tables", ferr);
+      }
+      sp->t.v = v;
+      sp->t.v.trace = nullptr;
+      sp->bar = pl->d_stepk_bar;
+      sp->dbg = pl->dbg;
+      sp->trace = nullptr;
+      sp->trace_id0 = 0;
+      prof_pre(pl, cm, "step:chain");
+      if (pl->trace_on && pl->trace_next + sp->t.n_levels <= pl->trace_cap) {
+        sp->trace = pl->d_trace;
+        sp->trace_id0 = pl->trace_next;
+        pl->trace_next += sp->t.n_levels;
+        for (int l = 0; l < sp->t.n_levels; ++l) pl->trace_tags.push_back("L" + std::to_string(l) + "|" + tags[l]);
+      }
+      cudaError_t lerr = step_kernel_launch(*sp, max_items, cm);
+      delete sp;
+      prof_post(pl, cm);
+      if (lerr != cudaSuccess) ex.err = lerr;
+      pl->launches++;
+      pl->stepk_launches++;
+      if (losses_out && ex.ok()) {
+        ex.err = cudaMemcpy2DAsync(losses_out + 8 * (size_t)m0, 8 * sizeof(float), v.losses.at(m0), v.losses.ms * sizeof(float),
+                                   8 * sizeof(float), Ec, cudaMemcpyDeviceToDevice, cm);
+      }
+      if (backward)
+        for (auto& ev : pl->bucket_ev) cudaEventRecord(ev, cm);  // every gradient bucket is complete when the kernel ends
+    }
     if (forked) {  // join this range into the caller's stream
       cudaEventRecord(ch.ev_end, cm);
       cudaStreamWaitEvent(st, ch.ev_end, 0);

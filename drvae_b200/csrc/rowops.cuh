@@ -21,6 +21,25 @@ constexpr int ROW_THREADS = ROW_WARPS * 32;
 constexpr int PAD_ROWS = 128;           // rows of zero padding kept after the valid rows of a GEMM operand
 constexpr int PAD_WARPS = 16;           // extra "pad duty" warps per launch, each zeroing PAD_ROWS / PAD_WARPS rows
 
+// Resident blocks per SM the row kernels are compiled for (register cap = 65536 / (256 x blocks)).  Measured on the
+// 32-model step (profiles/r02_experiments.md): one wave of rows matters more than spill-free code for the kernels that
+// have one warp per minibatch row.
+#ifndef ROW_LB_SAMPLE
+#define ROW_LB_SAMPLE 4
+#endif
+#ifndef ROW_LB_TPOST
+#define ROW_LB_TPOST 5
+#endif
+#ifndef ROW_LB_TBACK
+#define ROW_LB_TBACK 4
+#endif
+#ifndef ROW_LB_QBACK
+#define ROW_LB_QBACK 4
+#endif
+#ifndef ROW_LB_EVAL
+#define ROW_LB_EVAL 4
+#endif
+
 __device__ __forceinline__ void st_c8(bf16* base, int rcap, int row, int f, float v) {
   base[c8_index(row, f, rcap)] = __float2bfloat16_rn(v);
 }
@@ -303,6 +322,72 @@ __device__ __forceinline__ void classifier_row(const DevView& v, int m, int r, i
   }
 }
 
+// The same classifier with its input taken from registers: feature f = lane + 32 k of z1 (and of z2f when the
+// classifier sees [z1, z2f - z1]).  Same accumulation order as classifier_row (k ascending per lane, then the shuffle
+// tree), so both give bit-identical results; this form has no global round trip for the row the caller has just
+// computed and issues all weight loads back to back.
+template <int J>
+__device__ __forceinline__ void classifier_row_regs(const DevView& v, int m, int r, int i, int lane, const float (&z1)[J],
+                                                    const float (&z2f)[J], bool two) {
+  const float* Wc = v.clf_w.at(m);
+  const float* bc = v.params.at(m) + v.clf_b_off;
+  const bool lb = v.lab.at(m)[i] != 0;
+  const int yi = v.ycls.at(m)[i];
+  float acc[MAXY];
+#pragma unroll
+  for (int j = 0; j < MAXY; ++j) acc[j] = 0.f;
+#pragma unroll
+  for (int k = 0; k < J; ++k) {
+    const int f = lane + 32 * k;
+    if (f < v.Z) {
+      const float a = z1[k];
+      const float d = two ? z2f[k] - a : 0.f;
+#pragma unroll
+      for (int j = 0; j < MAXY; ++j) {
+        if (j < v.Y) {
+          acc[j] = fmaf(Wc[j * v.clf_ld + f], a, acc[j]);
+          if (two) acc[j] = fmaf(Wc[j * v.clf_ld + v.Z + f], d, acc[j]);
+        }
+      }
+    }
+  }
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < MAXY; ++j) {
+    if (j < v.Y) {
+      acc[j] = warp_sum(acc[j]) + bc[j];
+      mx = fmaxf(mx, acc[j]);
+    }
+  }
+  float den = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXY; ++j) {
+    if (j < v.Y) {
+      acc[j] = expf(acc[j] - mx);
+      den += acc[j];
+    }
+  }
+  float yl = 0.f, ycat = 0.f;
+#pragma unroll
+  for (int j = 0; j < MAXY; ++j) {
+    if (j < v.Y) {
+      float q = acc[j] / den;
+      q = fminf(fmaxf(q, 1e-10f), 1.f - 1e-10f);
+      if (lane == 0) v.QY.at(m)[(long long)r * v.Y + j] = q;
+      const float lq = logf(q);
+      if (lb) {
+        if (j == yi) yl = lq;
+      } else {
+        ycat += -q * (v.dyn->s.log_prior[j] - lq);
+      }
+    }
+  }
+  if (lane == 0) {
+    v.yl_row.at(m)[r] = yl;
+    v.ycat_row.at(m)[r] = ycat;
+  }
+}
+
 __device__ __forceinline__ float kl_prior_term(float mu, float lv) { return 0.5f * (-lv - 1.f + mu * mu + expf(lv)); }
 __device__ __forceinline__ float kl_term(float muq, float lvq, float mup, float lvp) {
   const float d = muq - mup;
@@ -317,12 +402,7 @@ __device__ __forceinline__ float kl_term(float muq, float lvq, float mup, float 
 // J: feature slots per lane held in registers (latent dim <= 32 J); 4 covers the README's 100-dim latents within the
 // 48-register budget of 5 blocks per SM, MAXJ is the general case
 template <int J>
-__global__ void __launch_bounds__(ROW_THREADS, 5) sample_q1_kernel(DevView v) {
-  TraceScope trace_scope(v.trace, v.trace_id);
-  pdl_launch_dependents();
-  pdl_wait();
-  const int m = v.model0 + blockIdx.y, lane = threadIdx.x & 31;
-  const int i = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+__device__ __forceinline__ void sample_q1_row(const DevView& v, const int m, const int i, const int lane) {
   const int* cnt = v.counts.at(m);
   const int N = cnt[CNT_N], Np = cnt[CNT_NP], LN = cnt[CNT_LN], Fl = cnt[CNT_FL], F = cnt[CNT_F], Rd = cnt[CNT_RD];
   if (i >= N) {
@@ -379,11 +459,9 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) sample_q1_kernel(DevView v) {
         const int cls = ecnt == 1 ? ycl : jj;
         st_c8(z1e, v.Z1e.rcap, l * Fl + eb + jj, f, (f == v.Z + 1 + cls) ? 1.f : z);
       }
+      n1[k] = z;  // (kept for the classifier below)
     }
-    if (v.has_clf && !v.has_T) {
-      __syncwarp();
-      classifier_row(v, m, r, i, lane);
-    }
+    if (v.has_clf && !v.has_T) classifier_row_regs<J>(v, m, r, i, lane, n1, n1, false);
   }
   if (v.kind == KIND_PVAE) {  // KL(q1 || N(0,I)) and KL(q2 || N(0,I)) with free bits (PVAE.py:330-372)
     float k1 = 0.f, k2 = 0.f;
@@ -401,17 +479,20 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) sample_q1_kernel(DevView v) {
   }
 }
 
+template <int J>
+__global__ void __launch_bounds__(ROW_THREADS, ROW_LB_SAMPLE) sample_q1_kernel(DevView v) {
+  TraceScope trace_scope(v.trace, v.trace_id);
+  pdl_launch_dependents();
+  pdl_wait();
+  sample_q1_row<J>(v, v.model0 + blockIdx.y, blockIdx.x * ROW_WARPS + (threadIdx.x >> 5), threadIdx.x & 31);
+}
+
 // ---------------------------------------------------------------------------------------------
 // T_post: after the p(z2|z1) GEMM.  Residual mean, sample z2f, KL(q(z2|x2) || p(z2|z1)) with free
 // bits for pair rows, and the classifier.
 // ---------------------------------------------------------------------------------------------
 template <int J>
-__global__ void __launch_bounds__(ROW_THREADS, 5) T_post_kernel(DevView v) {
-  TraceScope trace_scope(v.trace, v.trace_id);
-  pdl_launch_dependents();
-  pdl_wait();
-  const int m = v.model0 + blockIdx.y, lane = threadIdx.x & 31;
-  const int i = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+__device__ __forceinline__ void T_post_row(const DevView& v, const int m, const int i, const int lane) {
   const int* cnt = v.counts.at(m);
   const int N = cnt[CNT_N], Np = cnt[CNT_NP], LN = cnt[CNT_LN], LNp = cnt[CNT_LNP], Rd = cnt[CNT_RD];
   if (i >= N) {
@@ -456,14 +537,20 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) T_post_kernel(DevView v) {
         if (q2) kl += kl_term(a_q2m[k], a_q2l[k], pmu, plv);
       }
       if (p >= 0) st_c8(zdec, v.Zdec.rcap, LN + LNp + l * Np + p, f, z2f);
+      a_ef[k] = z2f;  // (kept for the classifier below)
     }
     kl = warp_sum(kl);
     if (lane == 0) v.klz2_row.at(m)[r] = q2 ? fmaxf(kl, v.dyn->s.kl_min) : 0.f;
-    if (v.has_clf) {
-      __syncwarp();
-      classifier_row(v, m, r, i, lane);
-    }
+    if (v.has_clf) classifier_row_regs<J>(v, m, r, i, lane, a_z1, a_ef, v.clf_in > v.Z);
   }
+}
+
+template <int J>
+__global__ void __launch_bounds__(ROW_THREADS, ROW_LB_TPOST) T_post_kernel(DevView v) {
+  TraceScope trace_scope(v.trace, v.trace_id);
+  pdl_launch_dependents();
+  pdl_wait();
+  T_post_row<J>(v, v.model0 + blockIdx.y, blockIdx.x * ROW_WARPS + (threadIdx.x >> 5), threadIdx.x & 31);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -477,12 +564,8 @@ __device__ __forceinline__ void eval_decode(const DevView& v, int m, int e, int 
   jj = v.e_jj.at(m)[el];
 }
 
-__global__ void __launch_bounds__(ROW_THREADS) z3_post_kernel(DevView v) {
-  TraceScope trace_scope(v.trace, v.trace_id);
-  pdl_launch_dependents();
-  pdl_wait();
-  const int m = v.model0 + blockIdx.y, lane = threadIdx.x & 31;
-  const int e = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+template <int J>
+__device__ __forceinline__ void z3_post_row(const DevView& v, const int m, const int e, const int lane) {
   const int* cnt = v.counts.at(m);
   const int F = cnt[CNT_F], Fl = cnt[CNT_FL];
   if (e >= pad128(F)) return;
@@ -496,18 +579,37 @@ __global__ void __launch_bounds__(ROW_THREADS) z3_post_kernel(DevView v) {
   const float* ez = v.eps_z3.at(m) + (((long long)l * v.Ncap + i) * v.Y + jj) * v.Z3;
   bf16* z3b = v.Z3b.at(m);
   const int cls = v.e_cls_full.at(m)[e];
+  float a_mu[J], a_lv[J], a_ez[J];
+#pragma unroll
+  for (int k = 0; k < J; ++k) {  // every load of the row before the first store
+    const int f = lane + 32 * k;
+    const bool in = f < v.Z3;
+    a_mu[k] = in ? q3[f] : 0.f;
+    a_lv[k] = in ? q3[v.Z3s + f] : 0.f;
+    a_ez[k] = in ? ez[f] : 0.f;
+  }
   float kl = 0.f;
-  for (int f = lane; f < v.Z3c; f += 32) {
+#pragma unroll
+  for (int k = 0; k < J; ++k) {
+    const int f = lane + 32 * k;
+    if (f >= v.Z3c) continue;
     float z = (f == v.Z3 || f == v.Z3 + 1 + cls) ? 1.f : 0.f;  // ones column, one-hot class column
     if (f < v.Z3) {
-      const float mu = q3[f], lv = q3[v.Z3s + f];
-      z = mu + expf(0.5f * lv) * ez[f];
-      kl += kl_prior_term(mu, lv);
+      z = a_mu[k] + expf(0.5f * a_lv[k]) * a_ez[k];
+      kl += kl_prior_term(a_mu[k], a_lv[k]);
     }
     st_c8(z3b, v.Z3b.rcap, e, f, z);
   }
   kl = warp_sum(kl);
   if (lane == 0) v.kfp_row.at(m)[e] = fmaxf(kl, v.dyn->s.kl_min);
+}
+
+template <int J>
+__global__ void __launch_bounds__(ROW_THREADS, ROW_LB_EVAL) z3_post_kernel(DevView v) {
+  TraceScope trace_scope(v.trace, v.trace_id);
+  pdl_launch_dependents();
+  pdl_wait();
+  z3_post_row<J>(v, v.model0 + blockIdx.y, blockIdx.x * ROW_WARPS + (threadIdx.x >> 5), threadIdx.x & 31);
 }
 
 // weight of evaluation e in the batch KLD: 1 for the true class of a labeled row, q(y=j) otherwise
@@ -520,12 +622,8 @@ __device__ __forceinline__ float eval_weight(const DevView& v, int m, int l, int
 // pz1_post: fb(KL(q(z1|x1) || p(z1|z_top,y))) per evaluation, its gradients towards the
 // decoder_z1 heads (dY9) and towards q1 (dQ1e).  DrVAE.py:352-355, VFAE.py:253-256.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ROW_THREADS) pz1_post_kernel(DevView v) {
-  TraceScope trace_scope(v.trace, v.trace_id);
-  pdl_launch_dependents();
-  pdl_wait();
-  const int m = v.model0 + blockIdx.y, lane = threadIdx.x & 31;
-  const int e = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+template <int J>
+__device__ __forceinline__ void pz1_post_row(const DevView& v, const int m, const int e, const int lane) {
   const int* cnt = v.counts.at(m);
   const int N = cnt[CNT_N], F = cnt[CNT_F], Fl = cnt[CNT_FL];
   if (e >= pad128(F)) return;
@@ -537,12 +635,25 @@ __global__ void __launch_bounds__(ROW_THREADS) pz1_post_kernel(DevView v) {
   eval_decode(v, m, e, Fl, l, i, jj);
   const float* q1 = v.Q.at(m) + (long long)i * 2 * v.Zs;
   const float* pz = v.PZ1.at(m) + (long long)e * 2 * v.Zs;
+  float a_m1[J], a_l1[J], a_mp[J], a_lp[J];
+#pragma unroll
+  for (int k = 0; k < J; ++k) {  // every load of the row before the reduction
+    const int f = lane + 32 * k;
+    const bool in = f < v.Z;
+    a_m1[k] = in ? q1[f] : 0.f;
+    a_l1[k] = in ? q1[v.Zs + f] : 0.f;
+    a_mp[k] = in ? pz[f] : 0.f;
+    a_lp[k] = in ? pz[v.Zs + f] : 0.f;
+  }
+  const float w = eval_weight(v, m, l, i, jj, N);
+  const float k3 = v.kfp_row.at(m)[e];
   float kl = 0.f;
-  for (int f = lane; f < v.Z; f += 32) kl += kl_term(q1[f], q1[v.Zs + f], pz[f], pz[v.Zs + f]);
+#pragma unroll
+  for (int k = 0; k < J; ++k)
+    if (lane + 32 * k < v.Z) kl += kl_term(a_m1[k], a_l1[k], a_mp[k], a_lp[k]);
   kl = warp_sum(kl);
   const bool act = kl > v.dyn->s.kl_min;
-  const float w = eval_weight(v, m, l, i, jj, N);
-  const float ke = v.kfp_row.at(m)[e] + fmaxf(kl, v.dyn->s.kl_min);
+  const float ke = k3 + fmaxf(kl, v.dyn->s.kl_min);
   __syncwarp();
   if (lane == 0) {
     v.kfp_row.at(m)[e] = ke;
@@ -552,8 +663,11 @@ __global__ void __launch_bounds__(ROW_THREADS) pz1_post_kernel(DevView v) {
   const float cw = act ? v.coefs.at(m)[COEF_KLD] * w : 0.f;
   bf16* dy = v.dY9.at(m);
   float* dq = v.dQ1e.at(m) + (long long)e * 2 * v.Zs;
-  for (int f = lane; f < v.Z; f += 32) {
-    const float mu1 = q1[f], lv1 = q1[v.Zs + f], mup = pz[f], lvp = pz[v.Zs + f];
+#pragma unroll
+  for (int k = 0; k < J; ++k) {
+    const int f = lane + 32 * k;
+    if (f >= v.Z) continue;
+    const float mu1 = a_m1[k], lv1 = a_l1[k], mup = a_mp[k], lvp = a_lp[k];
     const float d = mu1 - mup, ie = expf(-lvp), ev = expf(lv1);
     st_c8(dy, v.dY9.rcap, e, f, -cw * d * ie);
     st_c8(dy, v.dY9.rcap, e, v.Zs + f, cw * 0.5f * (1.f - (d * d + ev) * ie));
@@ -563,16 +677,20 @@ __global__ void __launch_bounds__(ROW_THREADS) pz1_post_kernel(DevView v) {
   zero_c8_gaps(v.dY9, dy, e, v.Z, v.Zs, lane);
 }
 
+template <int J>
+__global__ void __launch_bounds__(ROW_THREADS, ROW_LB_EVAL) pz1_post_kernel(DevView v) {
+  TraceScope trace_scope(v.trace, v.trace_id);
+  pdl_launch_dependents();
+  pdl_wait();
+  pz1_post_row<J>(v, v.model0 + blockIdx.y, blockIdx.x * ROW_WARPS + (threadIdx.x >> 5), threadIdx.x & 31);
+}
+
 // ---------------------------------------------------------------------------------------------
 // z3_back: d loss / d (mu3 | lv3) per evaluation = reparameterisation path (dZ3 from the
 // decoder_z1 input gradient) + the direct prior-KL gradient.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ROW_THREADS) z3_back_kernel(DevView v) {
-  TraceScope trace_scope(v.trace, v.trace_id);
-  pdl_launch_dependents();
-  pdl_wait();
-  const int m = v.model0 + blockIdx.y, lane = threadIdx.x & 31;
-  const int e = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+template <int J>
+__device__ __forceinline__ void z3_back_row(const DevView& v, const int m, const int e, const int lane) {
   const int* cnt = v.counts.at(m);
   const int N = cnt[CNT_N], F = cnt[CNT_F], Fl = cnt[CNT_FL];
   if (e >= pad128(F)) return;
@@ -585,19 +703,42 @@ __global__ void __launch_bounds__(ROW_THREADS) z3_back_kernel(DevView v) {
   const float* q3 = v.Q3.at(m) + (long long)e * 2 * v.Z3s;
   const float* ez = v.eps_z3.at(m) + (((long long)l * v.Ncap + i) * v.Y + jj) * v.Z3;
   const float* dz = v.dZ3.at(m) + (long long)e * v.Z3;
-  float kl = 0.f;
-  for (int f = lane; f < v.Z3; f += 32) kl += kl_prior_term(q3[f], q3[v.Z3s + f]);
-  kl = warp_sum(kl);
+  float a_mu[J], a_lv[J], a_ez[J], a_g[J];
+#pragma unroll
+  for (int k = 0; k < J; ++k) {  // every load of the row before the reduction
+    const int f = lane + 32 * k;
+    const bool in = f < v.Z3;
+    a_mu[k] = in ? q3[f] : 0.f;
+    a_lv[k] = in ? q3[v.Z3s + f] : 0.f;
+    a_ez[k] = in ? ez[f] : 0.f;
+    a_g[k] = in ? dz[f] : 0.f;
+  }
   const float w = eval_weight(v, m, l, i, jj, N);
+  float kl = 0.f;
+#pragma unroll
+  for (int k = 0; k < J; ++k)
+    if (lane + 32 * k < v.Z3) kl += kl_prior_term(a_mu[k], a_lv[k]);
+  kl = warp_sum(kl);
   const float cw = kl > v.dyn->s.kl_min ? v.coefs.at(m)[COEF_KLD] * w : 0.f;
   bf16* dy = v.dY7.at(m);
-  for (int f = lane; f < v.Z3; f += 32) {
-    const float mu = q3[f], lv = q3[v.Z3s + f];
-    const float g = dz[f];
+#pragma unroll
+  for (int k = 0; k < J; ++k) {
+    const int f = lane + 32 * k;
+    if (f >= v.Z3) continue;
+    const float mu = a_mu[k], lv = a_lv[k];
+    const float g = a_g[k];
     st_c8(dy, v.dY7.rcap, e, f, g + cw * mu);
-    st_c8(dy, v.dY7.rcap, e, v.Z3s + f, g * 0.5f * expf(0.5f * lv) * ez[f] + cw * 0.5f * (expf(lv) - 1.f));
+    st_c8(dy, v.dY7.rcap, e, v.Z3s + f, g * 0.5f * expf(0.5f * lv) * a_ez[k] + cw * 0.5f * (expf(lv) - 1.f));
   }
   zero_c8_gaps(v.dY7, dy, e, v.Z3, v.Z3s, lane);
+}
+
+template <int J>
+__global__ void __launch_bounds__(ROW_THREADS, ROW_LB_EVAL) z3_back_kernel(DevView v) {
+  TraceScope trace_scope(v.trace, v.trace_id);
+  pdl_launch_dependents();
+  pdl_wait();
+  z3_back_row<J>(v, v.model0 + blockIdx.y, blockIdx.x * ROW_WARPS + (threadIdx.x >> 5), threadIdx.x & 31);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -606,12 +747,7 @@ __global__ void __launch_bounds__(ROW_THREADS) z3_back_kernel(DevView v) {
 //   unlabeled row : 1/(L N) * d [ sum_j q_j k_j + sum_j q_j (log q_j - log prior_j) ]
 // grid (ceil(LNcap / ROW_WARPS), n_models), one warp per stacked row r = l*N + i
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ROW_THREADS) clf_back_kernel(DevView v) {
-  TraceScope trace_scope(v.trace, v.trace_id);
-  pdl_launch_dependents();
-  pdl_wait();
-  const int m = v.model0 + blockIdx.y, lane = threadIdx.x & 31;
-  const int r = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+__device__ __forceinline__ void clf_back_row(const DevView& v, const int m, const int r, const int lane) {
   const int* cnt = v.counts.at(m);
   const int N = cnt[CNT_N], LN = cnt[CNT_LN], Fl = cnt[CNT_FL];
   if (r >= LN) return;
@@ -647,7 +783,11 @@ __global__ void __launch_bounds__(ROW_THREADS) clf_back_kernel(DevView v) {
   }
   const float* Wc = v.clf_w.at(m);
   const bool two = v.clf_in > v.Z;
-  for (int f = lane; f < v.Z; f += 32) {
+  // (unrolled over the feature slots: the weight loads of all slots are in flight together)
+#pragma unroll
+  for (int k = 0; k < MAXJ; ++k) {
+    const int f = lane + 32 * k;
+    if (f >= v.Z) break;
     float a = 0.f, b = 0.f;
 #pragma unroll
     for (int j = 0; j < MAXY; ++j) {
@@ -661,16 +801,19 @@ __global__ void __launch_bounds__(ROW_THREADS) clf_back_kernel(DevView v) {
   }
 }
 
+__global__ void __launch_bounds__(ROW_THREADS) clf_back_kernel(DevView v) {
+  TraceScope trace_scope(v.trace, v.trace_id);
+  pdl_launch_dependents();
+  pdl_wait();
+  clf_back_row(v, v.model0 + blockIdx.y, blockIdx.x * ROW_WARPS + (threadIdx.x >> 5), threadIdx.x & 31);
+}
+
 // ---------------------------------------------------------------------------------------------
 // T_back: gradient rows of the p(z2|z1) heads (dYT = [d p_mu | d p_lv]), the KL(q2||p) gradient
 // towards q2 (dQ2) and the residual / classifier contributions to d z1 (DZ1).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ROW_THREADS, 5) T_back_kernel(DevView v) {
-  TraceScope trace_scope(v.trace, v.trace_id);
-  pdl_launch_dependents();
-  pdl_wait();
-  const int m = v.model0 + blockIdx.y, lane = threadIdx.x & 31;
-  const int i = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+template <int J>
+__device__ __forceinline__ void T_back_row(const DevView& v, const int m, const int i, const int lane) {
   const int* cnt = v.counts.at(m);
   const int N = cnt[CNT_N], Np = cnt[CNT_NP], LN = cnt[CNT_LN], LNp = cnt[CNT_LNP];
   if (i >= N) {
@@ -684,9 +827,14 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) T_back_kernel(DevView v) {
   const float* q2 = p >= 0 ? v.Q.at(m) + (long long)(N + p) * 2 * v.Zs : nullptr;
   const float ckl = v.coefs.at(m)[COEF_KLZ2];
   bf16* dy = v.dYT.at(m);
-  float a_mu[MAXJ], a_lv[MAXJ];
+  float a_mu[J], a_lv[J], q2m[J], q2l[J];
 #pragma unroll
-  for (int k = 0; k < MAXJ; ++k) a_mu[k] = a_lv[k] = 0.f;
+  for (int k = 0; k < J; ++k) {
+    const int f = lane + 32 * k;
+    a_mu[k] = a_lv[k] = 0.f;
+    q2m[k] = (q2 && f < v.Z) ? q2[f] : 0.f;
+    q2l[k] = (q2 && f < v.Z) ? q2[v.Zs + f] : 0.f;
+  }
   for (int l = 0; l < v.L; ++l) {
     const int r = l * N + i;
     const float* pt = v.PT.at(m) + (long long)r * 2 * v.Zs;
@@ -695,23 +843,35 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) T_back_kernel(DevView v) {
     const bool act = q2 && v.klz2_row.at(m)[r] > v.dyn->s.kl_min;
     float* dz1 = v.DZ1.at(m) + (long long)r * v.Z;
     const float* dz2f_c = v.has_clf ? v.DZ2F.at(m) + (long long)r * v.Z : nullptr;
+    float b_pmu[J], b_plv[J], b_g[J], b_c[J], b_ef[J], b_dz1[J];
 #pragma unroll
-    for (int k = 0; k < MAXJ; ++k) {
+    for (int k = 0; k < J; ++k) {  // every load of this sample before the first store
+      const int f = lane + 32 * k;
+      const bool in = f < v.Z;
+      b_pmu[k] = in ? pt[f] : 0.f;
+      b_plv[k] = in ? pt[v.Zs + f] : 0.f;
+      b_g[k] = (in && dzd) ? dzd[f] : 0.f;
+      b_c[k] = (in && dz2f_c) ? dz2f_c[f] : 0.f;
+      b_ef[k] = in ? ef[f] : 0.f;
+      b_dz1[k] = (in && v.has_clf) ? dz1[f] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < J; ++k) {
       const int f = lane + 32 * k;
       if (f < v.Z) {
-        const float pmu = pt[f], plv = pt[v.Zs + f];
-        float g = (dzd ? dzd[f] : 0.f) + (dz2f_c ? dz2f_c[f] : 0.f);
+        const float pmu = b_pmu[k], plv = b_plv[k];
+        float g = b_g[k] + b_c[k];
         float dpmu = g;
-        float dplv = g * 0.5f * expf(0.5f * plv) * ef[f];
+        float dplv = g * 0.5f * expf(0.5f * plv) * b_ef[k];
         if (act) {
-          const float mu2 = q2[f], lv2 = q2[v.Zs + f];
+          const float mu2 = q2m[k], lv2 = q2l[k];
           const float d = mu2 - pmu, ie = expf(-plv), ev = expf(lv2);
           dpmu += -ckl * d * ie;
           dplv += ckl * 0.5f * (1.f - (d * d + ev) * ie);
           a_mu[k] += ckl * d * ie;
           a_lv[k] += ckl * 0.5f * (ev * ie - 1.f);
         }
-        dz1[f] = (v.has_clf ? dz1[f] : 0.f) + dpmu;  // residual path mu = z1 + ...
+        dz1[f] = b_dz1[k] + dpmu;  // residual path mu = z1 + ...
         st_c8(dy, v.dYT.rcap, r, f, dpmu);
         st_c8(dy, v.dYT.rcap, r, v.Zs + f, dplv);
       }
@@ -721,7 +881,7 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) T_back_kernel(DevView v) {
   if (p >= 0) {
     float* dq2 = v.dQ2.at(m) + (long long)p * 2 * v.Zs;
 #pragma unroll
-    for (int k = 0; k < MAXJ; ++k) {
+    for (int k = 0; k < J; ++k) {
       const int f = lane + 32 * k;
       if (f < v.Z) {
         dq2[f] = a_mu[k];
@@ -731,16 +891,20 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) T_back_kernel(DevView v) {
   }
 }
 
+template <int J>
+__global__ void __launch_bounds__(ROW_THREADS, ROW_LB_TBACK) T_back_kernel(DevView v) {
+  TraceScope trace_scope(v.trace, v.trace_id);
+  pdl_launch_dependents();
+  pdl_wait();
+  T_back_row<J>(v, v.model0 + blockIdx.y, blockIdx.x * ROW_WARPS + (threadIdx.x >> 5), threadIdx.x & 31);
+}
+
 // ---------------------------------------------------------------------------------------------
 // q_back: gradient rows of the encoder heads, dY2 = [d mu | d lv] for q(z1|x1) rows and for
 // q(z2|x2) rows.  Collects every path into z1 / z2 samples and the direct KL gradients.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ROW_THREADS, 5) q_back_kernel(DevView v) {
-  TraceScope trace_scope(v.trace, v.trace_id);
-  pdl_launch_dependents();
-  pdl_wait();
-  const int m = v.model0 + blockIdx.y, lane = threadIdx.x & 31;
-  const int i = blockIdx.x * ROW_WARPS + (threadIdx.x >> 5);
+template <int J>
+__device__ __forceinline__ void q_back_row(const DevView& v, const int m, const int i, const int lane) {
   const int* cnt = v.counts.at(m);
   const int N = cnt[CNT_N], Np = cnt[CNT_NP], LN = cnt[CNT_LN], R0 = cnt[CNT_R0], Fl = cnt[CNT_FL];
   if (i >= N) {
@@ -757,40 +921,91 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) q_back_kernel(DevView v) {
   const bool have_dz1 = v.has_clf || v.has_T;
   bf16* dy = v.dY2.at(m);
   const float cN = v.coefs.at(m)[COEF_INV_N];
-  for (int f = lane; f < v.Z; f += 32) {
-    const float mu = q[f], lv = q[v.Zs + f];
-    const float hs = 0.5f * expf(0.5f * lv);
-    float amu = 0.f, alv = 0.f;
-    for (int l = 0; l < v.L; ++l) {
-      const long long r = (long long)l * N + i;
-      float g = v.dZdec.at(m)[r * v.Z + f];
-      if (have_dz1) g += v.DZ1.at(m)[r * v.Z + f];
-      if (v.has_T) g += v.dZ1T.at(m)[r * v.Z + f];
-      for (int jj = 0; jj < ecnt; ++jj) {
-        const long long e = (long long)l * Fl + eb + jj;
-        g += v.dZ1e.at(m)[e * v.Z + f];
-        amu += v.dQ1e.at(m)[e * 2 * v.Zs + f];
-        alv += v.dQ1e.at(m)[e * 2 * v.Zs + v.Zs + f];
+  const bool pv = v.kind == KIND_PVAE;
+  const float klq1 = pv ? v.klq_row.at(m)[i] : 0.f;
+  const float klq2 = (pv && p >= 0) ? v.klq_row.at(m)[N + p] : 0.f;
+  // Feature f = lane + 32 k.  Per MC sample all gradient rows of this minibatch row are requested together (one
+  // memory round trip per sample and per class evaluation instead of one per feature slot, sample and evaluation);
+  // the sums run in the same order as the reference accumulation: sample-major, evaluations in class order.
+  float mu[J], lv[J], hs[J], amu[J], alv[J];
+#pragma unroll
+  for (int k = 0; k < J; ++k) {
+    const int f = lane + 32 * k;
+    mu[k] = f < v.Z ? q[f] : 0.f;
+    lv[k] = f < v.Z ? q[v.Zs + f] : 0.f;
+    amu[k] = alv[k] = 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < J; ++k) hs[k] = 0.5f * expf(0.5f * lv[k]);
+  for (int l = 0; l < v.L; ++l) {
+    const long long r = (long long)l * N + i;
+    const float* gd = v.dZdec.at(m) + r * v.Z;
+    const float* g1 = v.DZ1.at(m) + r * v.Z;
+    const float* gT = v.dZ1T.at(m) + r * v.Z;
+    const float* e1 = v.eps_z1.at(m) + ((long long)l * v.Ncap + i) * v.Z;
+    const float* g2p = v.dZdec.at(m) + ((long long)LN + (long long)l * Np + p) * v.Z;
+    const float* e2 = v.eps_z2.at(m) + ((long long)l * v.Ncap + i) * v.Z;
+    float g[J], a_e1[J], a_g2[J], a_e2[J];
+#pragma unroll
+    for (int k = 0; k < J; ++k) {
+      const int f = lane + 32 * k;
+      const bool in = f < v.Z;
+      float x = in ? gd[f] : 0.f;
+      const float y1 = (in && have_dz1) ? g1[f] : 0.f;
+      const float yT = (in && v.has_T) ? gT[f] : 0.f;
+      a_e1[k] = in ? e1[f] : 0.f;
+      a_g2[k] = (in && p >= 0) ? g2p[f] : 0.f;
+      a_e2[k] = (in && p >= 0) ? e2[f] : 0.f;
+      if (have_dz1) x += y1;
+      if (v.has_T) x += yT;
+      g[k] = x;
+    }
+    for (int jj = 0; jj < ecnt; ++jj) {
+      const long long e = (long long)l * Fl + eb + jj;
+      const float* ze = v.dZ1e.at(m) + e * v.Z;
+      const float* qe = v.dQ1e.at(m) + e * 2 * v.Zs;
+      float a_ze[J], a_qm[J], a_ql[J];
+#pragma unroll
+      for (int k = 0; k < J; ++k) {
+        const int f = lane + 32 * k;
+        const bool in = f < v.Z;
+        a_ze[k] = in ? ze[f] : 0.f;
+        a_qm[k] = in ? qe[f] : 0.f;
+        a_ql[k] = in ? qe[v.Zs + f] : 0.f;
       }
-      amu += g;
-      alv += g * hs * v.eps_z1.at(m)[((long long)l * v.Ncap + i) * v.Z + f];
+#pragma unroll
+      for (int k = 0; k < J; ++k) {
+        g[k] += a_ze[k];
+        amu[k] += a_qm[k];
+        alv[k] += a_ql[k];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < J; ++k) {
+      amu[k] += g[k];
+      alv[k] += g[k] * hs[k] * a_e1[k];
       if (p >= 0) {
-        const float g2 = v.dZdec.at(m)[((long long)LN + (long long)l * Np + p) * v.Z + f];
-        amu += g2;
-        alv += g2 * hs * v.eps_z2.at(m)[((long long)l * v.Ncap + i) * v.Z + f];
+        amu[k] += a_g2[k];
+        alv[k] += a_g2[k] * hs[k] * a_e2[k];
       }
     }
-    if (v.kind == KIND_PVAE && v.klq_row.at(m)[i] > v.dyn->s.kl_min) {
-      amu += cN * mu;
-      alv += cN * 0.5f * (expf(lv) - 1.f);
+  }
+  const float* q2 = v.Q.at(m) + (long long)(N + (p >= 0 ? p : 0)) * 2 * v.Zs;
+  const float* dq2 = v.dQ2.at(m) + (long long)(p >= 0 ? p : 0) * 2 * v.Zs;
+#pragma unroll
+  for (int k = 0; k < J; ++k) {
+    const int f = lane + 32 * k;
+    if (f >= v.Z) continue;
+    if (pv && klq1 > v.dyn->s.kl_min) {
+      amu[k] += cN * mu[k];
+      alv[k] += cN * 0.5f * (expf(lv[k]) - 1.f);
     }
-    st_c8(dy, v.dY2.rcap, i, f, amu);
-    st_c8(dy, v.dY2.rcap, i, v.Zs + f, alv);
+    st_c8(dy, v.dY2.rcap, i, f, amu[k]);
+    st_c8(dy, v.dY2.rcap, i, v.Zs + f, alv[k]);
     if (p >= 0) {
-      const float* q2 = v.Q.at(m) + (long long)(N + p) * 2 * v.Zs;
-      float bmu = v.has_T ? v.dQ2.at(m)[(long long)p * 2 * v.Zs + f] : 0.f;
-      float blv = v.has_T ? v.dQ2.at(m)[(long long)p * 2 * v.Zs + v.Zs + f] : 0.f;
-      if (v.kind == KIND_PVAE && v.klq_row.at(m)[N + p] > v.dyn->s.kl_min) {
+      float bmu = v.has_T ? dq2[f] : 0.f;
+      float blv = v.has_T ? dq2[v.Zs + f] : 0.f;
+      if (pv && klq2 > v.dyn->s.kl_min) {
         bmu += cN * q2[f];
         blv += cN * 0.5f * (expf(q2[v.Zs + f]) - 1.f);
       }
@@ -802,18 +1017,23 @@ __global__ void __launch_bounds__(ROW_THREADS, 5) q_back_kernel(DevView v) {
   if (p >= 0) zero_c8_gaps(v.dY2, dy, N + p, v.Z, v.Zs, lane);
 }
 
+template <int J>
+__global__ void __launch_bounds__(ROW_THREADS, ROW_LB_QBACK) q_back_kernel(DevView v) {
+  TraceScope trace_scope(v.trace, v.trace_id);
+  pdl_launch_dependents();
+  pdl_wait();
+  q_back_row<J>(v, v.model0 + blockIdx.y, blockIdx.x * ROW_WARPS + (threadIdx.x >> 5), threadIdx.x & 31);
+}
+
 // ---------------------------------------------------------------------------------------------
 // classifier weight gradient: dWc[j][t] = sum_r dlogit[r][j] * u[r][t], u = [z1, z2f - z1, 1]
 // two stages (row-split partials, then a fixed-order reduction) -> deterministic
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) clf_grad_partial_kernel(DevView v) {
-  TraceScope trace_scope(v.trace, v.trace_id);
-  pdl_launch_dependents();
-  pdl_wait();
-  const int m = v.model0 + blockIdx.y, split = blockIdx.x;
+// (m, split): one row split of one model; thread t0 of nthreads cooperating threads
+__device__ __forceinline__ void clf_grad_partial_block(const DevView& v, const int m, const int split, const int t0, const int nthreads) {
   const int LN = v.counts.at(m)[CNT_LN];
   const int width = v.clf_in + 1;
-  for (int t = threadIdx.x; t < width; t += 256) {
+  for (int t = t0; t < width; t += nthreads) {
     float acc[MAXY];
 #pragma unroll
     for (int j = 0; j < MAXY; ++j) acc[j] = 0.f;
@@ -836,15 +1056,17 @@ __global__ void __launch_bounds__(256) clf_grad_partial_kernel(DevView v) {
   }
 }
 
-// grid (ceil(Y * (clf_in + 1) / 8), n_models), block 256: one warp per gradient element, lanes over the row splits
-// (lane l sums splits l, l + 32, ... in order, then a fixed shuffle tree -> deterministic)
-__global__ void __launch_bounds__(256) clf_grad_reduce_kernel(DevView v) {
+__global__ void __launch_bounds__(256) clf_grad_partial_kernel(DevView v) {
   TraceScope trace_scope(v.trace, v.trace_id);
   pdl_launch_dependents();
   pdl_wait();
-  const int m = v.model0 + blockIdx.y, lane = threadIdx.x & 31;
+  clf_grad_partial_block(v, v.model0 + blockIdx.y, blockIdx.x, threadIdx.x, 256);
+}
+
+// grid (ceil(Y * (clf_in + 1) / 8), n_models), block 256: one warp per gradient element, lanes over the row splits
+// (lane l sums splits l, l + 32, ... in order, then a fixed shuffle tree -> deterministic)
+__device__ __forceinline__ void clf_grad_reduce_elem(const DevView& v, const int m, const int k, const int lane) {
   const int width = v.clf_in + 1;
-  const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (k >= v.Y * width) return;
   const int j = k / width, t = k - j * width;
   float s = 0.f;
@@ -865,6 +1087,13 @@ __global__ void __launch_bounds__(256) clf_grad_reduce_kernel(DevView v) {
     V2[idx] = v1;
     P[idx] = pv;
   }
+}
+
+__global__ void __launch_bounds__(256) clf_grad_reduce_kernel(DevView v) {
+  TraceScope trace_scope(v.trace, v.trace_id);
+  pdl_launch_dependents();
+  pdl_wait();
+  clf_grad_reduce_elem(v, v.model0 + blockIdx.y, blockIdx.x * 8 + (threadIdx.x >> 5), threadIdx.x & 31);
 }
 
 
@@ -972,27 +1201,30 @@ __global__ void __launch_bounds__(ROW_THREADS) infer_z2_kernel(DevView v, InferV
 // (DrVAE.py:610-626, PVAE.py:452-465, VFAE.py:438-458).  out: RECL KLD PERT YL MMD ELBO CMPL.
 // With global normalisers (data parallel) the outputs are this shard's additive share.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float block_sum_256(float x, float* sm) {
-  const int t = threadIdx.x;
+// sum over 256 cooperating threads (t = 0 .. 255) in a fixed tree order; `sync` is the barrier of exactly those threads
+// (__syncthreads in the stand-alone kernel, a named barrier inside the persistent step kernel)
+struct SyncBlock {
+  __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+template <class Sync>
+__device__ __forceinline__ float block_sum_256(float x, float* sm, const int t, const Sync& sync) {
   sm[t] = x;
-  __syncthreads();
+  sync();
   for (int o = 128; o > 0; o >>= 1) {
     if (t < o) sm[t] += sm[t + o];
-    __syncthreads();
+    sync();
   }
   const float r = sm[0];
-  __syncthreads();
+  sync();
   return r;
 }
 
 // grid (loss_slices, n_models): slice s reduces rows s, s + slices, ... of every per-row term in a fixed order
-__global__ void __launch_bounds__(256) loss_partial_kernel(DevView v) {
-  TraceScope trace_scope(v.trace, v.trace_id);
-  pdl_launch_dependents();
-  pdl_wait();
-  __shared__ float sm[256];
-  const int m = v.model0 + blockIdx.y, t = threadIdx.x;
-  const int stride = 256 * gridDim.x, first = blockIdx.x * 256 + t;
+// (m, slice) of `nslices`: 256 cooperating threads, t = 0 .. 255
+template <class Sync>
+__device__ __forceinline__ void loss_partial_block(const DevView& v, const int m, const int slice, const int nslices, const int t, float* sm,
+                                                   const Sync& sync) {
+  const int stride = 256 * nslices, first = slice * 256 + t;
   const int* cnt = v.counts.at(m);
   const int LN = cnt[CNT_LN], LNp = cnt[CNT_LNP], Rd = cnt[CNT_RD], F = cnt[CNT_F], R0 = cnt[CNT_R0];
   float a_recl = 0.f, a_pert = 0.f;
@@ -1016,26 +1248,30 @@ __global__ void __launch_bounds__(256) loss_partial_kernel(DevView v) {
     for (int e = first; e < F; e += stride) a_kfp += v.kfpw_row.at(m)[e];
   if (v.kind == KIND_PVAE)
     for (int r = first; r < R0; r += stride) a_klq += v.klq_row.at(m)[r];
-  a_recl = block_sum_256(a_recl, sm);
-  a_pert = block_sum_256(a_pert, sm);
-  a_klz2 = block_sum_256(a_klz2, sm);
-  a_yl = block_sum_256(a_yl, sm);
-  a_ycat = block_sum_256(a_ycat, sm);
-  a_kfp = block_sum_256(a_kfp, sm);
-  a_klq = block_sum_256(a_klq, sm);
+  a_recl = block_sum_256(a_recl, sm, t, sync);
+  a_pert = block_sum_256(a_pert, sm, t, sync);
+  a_klz2 = block_sum_256(a_klz2, sm, t, sync);
+  a_yl = block_sum_256(a_yl, sm, t, sync);
+  a_ycat = block_sum_256(a_ycat, sm, t, sync);
+  a_kfp = block_sum_256(a_kfp, sm, t, sync);
+  a_klq = block_sum_256(a_klq, sm, t, sync);
   if (t == 0) {
-    float* o = v.loss_part.at(m) + blockIdx.x * 8;
+    float* o = v.loss_part.at(m) + slice * 8;
     o[0] = a_recl, o[1] = a_pert, o[2] = a_klz2, o[3] = a_yl, o[4] = a_ycat, o[5] = a_kfp, o[6] = a_klq, o[7] = 0.f;
   }
 }
 
-// grid n_models, one warp: fixed-order sum of the slices, then the reference's normalisation
-__global__ void __launch_bounds__(32) loss_final_kernel(DevView v) {
+__global__ void __launch_bounds__(256) loss_partial_kernel(DevView v) {
   TraceScope trace_scope(v.trace, v.trace_id);
   pdl_launch_dependents();
   pdl_wait();
-  const int m = v.model0 + blockIdx.x;
-  if (threadIdx.x != 0) return;
+  __shared__ float sm[256];
+  loss_partial_block(v, v.model0 + blockIdx.y, blockIdx.x, gridDim.x, threadIdx.x, sm, SyncBlock());
+}
+
+// grid n_models, one warp: fixed-order sum of the slices, then the reference's normalisation
+// one thread per model
+__device__ __forceinline__ void loss_final_model(const DevView& v, const int m) {
   float a[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int s = 0; s < v.loss_slices; ++s)
     for (int k = 0; k < 7; ++k) a[k] += v.loss_part.at(m)[s * 8 + k];
@@ -1055,6 +1291,13 @@ __global__ void __launch_bounds__(32) loss_final_kernel(DevView v) {
   o[5] = ELBO;
   o[6] = CMPL;
   o[7] = 0.f;
+}
+
+__global__ void __launch_bounds__(32) loss_final_kernel(DevView v) {
+  TraceScope trace_scope(v.trace, v.trace_id);
+  pdl_launch_dependents();
+  pdl_wait();
+  if (threadIdx.x == 0) loss_final_model(v, v.model0 + blockIdx.x);
 }
 
 }  // namespace drvae

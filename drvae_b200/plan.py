@@ -321,6 +321,13 @@ class Plan:
     def graph_failures(self):
         return int(self.lib.drvae_plan_graph_failures(self.h))
 
+    def set_step_kernel(self, enable):
+        """Persistent step kernel on (default) / off (one launch per GEMM and row operation)."""
+        _lib.check(self.lib.drvae_set_step_kernel(self.h, 1 if enable else 0))
+
+    def step_kernel_launches(self):
+        return int(self.lib.drvae_plan_step_kernel_launches(self.h))
+
     def set_gemm_impl(self, impl):
         _lib.check(self.lib.drvae_set_gemm_impl(self.h, {"tc": 0, "simt": 1}[impl]))
 

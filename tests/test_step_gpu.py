@@ -816,3 +816,39 @@ def test_both_sides_of_the_fused_optimizer_threshold(N):
         res.append(plan.params.cpu().clone())
     assert torch.allclose(res[0], res[1], rtol=1e-5, atol=2e-7)
     assert not torch.equal(res[0], torch.zeros_like(res[0]))
+
+
+@pytest.mark.parametrize("arch_name", ("tiny", "deep"))
+@pytest.mark.parametrize("kind", KINDS)
+def test_step_kernel_equals_one_launch_per_operation(kind, arch_name):
+    """The persistent step kernel (stepk.cuh) runs the recorded forward + input-gradient chain as one cooperative launch
+    with grid barriers between dependent levels.  Same device code per item, so: bit-identical losses, parameters and
+    eval-mode losses to the schedule that launches every GEMM / row operation separately — for the fused train step,
+    the gradient + stand-alone optimizer path (split-K weight gradients inside the chain) and the loss-only pass."""
+    arch, N, E = ARCH[arch_name], 40, 3
+    sds = [init_state_dict(kind, seed=SEED_MODEL + m, **arch) for m in range(E)]
+    batches = [batch_fields(kind, orc.synthetic_batch(N, arch["dim_x"], seed=20 + m)) for m in range(E)]
+    big = {k: torch.stack([b[k] for b in batches]).contiguous().cuda() for k in batches[0]}
+    res = {}
+    for mode in (True, False):
+        plan = Plan(kind, L=L, max_batch=N, n_models=E, **arch)
+        plan.set_step_kernel(mode)
+        for m in range(E):
+            plan.load_state_dict(sds[m], model=m)
+        losses = []
+        for it in range(5):
+            losses.append(plan.train_step(big, plan.hparams(step=it, beta_pert=anneal_coef(it, 1, 0)), seed=9).cpu().clone())
+        g = plan.grad_step(big, plan.hparams(step=5), seed=9).cpu().clone()
+        grads = plan.grads.cpu().clone()
+        plan.adam_step(plan.hparams(step=5))
+        ev = plan.loss_forward(big, plan.hparams(step=6, training=False), seed=9).cpu().clone()
+        torch.cuda.synchronize()
+        res[mode] = (losses, plan.params.cpu().clone(), g, grads, ev, plan.step_kernel_launches())
+    assert res[True][5] >= 1 and res[False][5] == 0, (res[True][5], res[False][5])  # (graph replays are not counted; the deep gradient path exceeds the op table and falls back)
+    for a, b in zip(res[True][0], res[False][0]):
+        assert torch.equal(a, b)
+    assert torch.equal(res[True][1], res[False][1])
+    assert torch.equal(res[True][2], res[False][2])
+    assert torch.equal(res[True][3], res[False][3])
+    assert torch.equal(res[True][4], res[False][4])
+    assert bool(torch.isfinite(res[True][1]).all())

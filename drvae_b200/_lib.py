@@ -71,7 +71,8 @@ EXPORTS = ["drvae_last_error", "drvae_plan_create", "drvae_plan_destroy", "drvae
            "drvae_plan_launch_count", "drvae_debug_buffer", "drvae_debug_gemm", "drvae_profile_begin",
            "drvae_profile_end", "drvae_plan_num_buckets", "drvae_plan_bucket_info", "drvae_stream_wait_bucket", "drvae_set_graph", "drvae_plan_graph_replays", "drvae_debug_wait_stats",
            "drvae_push_scalars", "drvae_set_external_scalars", "drvae_debug_side_delay", "drvae_plan_tensor_ld", "drvae_set_chains", "drvae_trace_begin", "drvae_trace_end", "drvae_debug_dwa_stats", "drvae_set_infer_precision", "drvae_dp_attach", "drvae_dp_grad_floats",
-           "drvae_dp_counts_ptr", "drvae_dp_exchange_counts", "drvae_dp_adam_step", "drvae_plan_graph_failures", "drvae_set_step_kernel", "drvae_plan_step_kernel_launches"]
+           "drvae_dp_counts_ptr", "drvae_dp_exchange_counts", "drvae_dp_adam_step", "drvae_plan_graph_failures", "drvae_set_step_kernel", "drvae_plan_step_kernel_launches",
+           "drvae_eval_workspace_bytes", "drvae_eval_x_reconstruction"]
 
 
 def load():
@@ -123,6 +124,10 @@ def load():
     lib.drvae_set_graph.argtypes = [c_void_p, c_int]
     lib.drvae_plan_graph_failures.restype = c_ll
     lib.drvae_plan_graph_failures.argtypes = [c_void_p]
+    lib.drvae_eval_workspace_bytes.restype = c_ll
+    lib.drvae_eval_workspace_bytes.argtypes = [c_int, c_int]
+    lib.drvae_eval_x_reconstruction.restype = c_int
+    lib.drvae_eval_x_reconstruction.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
     lib.drvae_set_step_kernel.restype = c_int
     lib.drvae_set_step_kernel.argtypes = [c_void_p, c_int]
     lib.drvae_plan_step_kernel_launches.restype = c_ll

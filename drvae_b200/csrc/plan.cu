@@ -60,7 +60,7 @@ struct drvae_plan {
   Seg* d_segs = nullptr;
   std::vector<int> h_tabs;  // gradient-epilogue tables of every weight (see make_shadow)
   int* d_tabs = nullptr;
-  int sched = 5;              // schedule knob (DRVAE_B200_SCHED): bit 0 = noise generator on the side stream, bit 2 = classifier weight gradient at the tail of the side stream, bit 1 = whole classifier backward on the side stream (measured: 1.037 / 1.027 / 1.048 / 1.048 ms for 0 / 1 / 2 / 3)
+  int sched = 13;              // schedule knob (DRVAE_B200_SCHED): bit 0 = noise generator on the side stream, bit 2 = classifier weight gradient off the dX chain, bit 3 = stand-alone weight-gradient GEMMs (gradient path) on their own stream, bit 1 = whole classifier backward on the side stream (measured: 1.037 / 1.027 / 1.048 / 1.048 ms for 0 / 1 / 2 / 3)
   int adam_vec_max = 4;       // debug knob (DRVAE_B200_ADAM_VEC): cap on the vector width of the fused Adam epilogue
   bool wn = false;            // layers.WeightNormLinear instead of nn.Linear
   std::vector<WnRow> wn_rows;
@@ -114,8 +114,9 @@ struct drvae_plan {
   struct Chain {
     cudaStream_t main = nullptr, side = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_qy = nullptr, ev_side_fwd = nullptr, ev_side_bwd = nullptr, ev_begin = nullptr, ev_eps = nullptr,
-                ev_clf = nullptr, ev_kfp = nullptr, ev_end = nullptr, ev_side_end = nullptr;
-    cudaEvent_t* all() { return &ev_fork; }  // 10 consecutive events
+                ev_clf = nullptr, ev_kfp = nullptr, ev_end = nullptr, ev_side_end = nullptr, ev_dw = nullptr, ev_dw_end = nullptr;
+    static constexpr int N_EVENTS = 12;
+    cudaEvent_t* all() { return &ev_fork; }  // N_EVENTS consecutive events
   };
   Chain chain[MAX_CHAINS];
   bool main_prio = true;      // main chain on the plan's high-priority stream (DRVAE_B200_PRIO=0: on the caller's stream)
@@ -587,7 +588,7 @@ extern "C" int drvae_plan_create(const drvae_arch_t* a, int n_models, drvae_plan
     cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
     cudaStreamCreateWithPriority(&ch.main, cudaStreamNonBlocking, prio_greatest);
     cudaStreamCreateWithPriority(&ch.side, cudaStreamNonBlocking, prio_least);
-    for (int i = 0; i < 10; ++i) cudaEventCreateWithFlags(ch.all() + i, cudaEventDisableTiming);
+    for (int i = 0; i < drvae_plan::Chain::N_EVENTS; ++i) cudaEventCreateWithFlags(ch.all() + i, cudaEventDisableTiming);
   }
   cudaEventCreateWithFlags(&pl->ev_begin, cudaEventDisableTiming);
   pl->bucket_ev.resize(pl->buckets.size());
@@ -704,7 +705,7 @@ extern "C" int drvae_plan_destroy(drvae_plan_t* pl) {
   if (pl->d_stepk_bar) cudaFree(pl->d_stepk_bar);
   for (auto& ev : pl->bucket_ev) cudaEventDestroy(ev);
   for (auto& ch : pl->chain) {
-    for (int i = 0; i < 10; ++i)
+    for (int i = 0; i < drvae_plan::Chain::N_EVENTS; ++i)
       if (ch.all()[i]) cudaEventDestroy(ch.all()[i]);
     if (ch.main) cudaStreamDestroy(ch.main);
     if (ch.side) cudaStreamDestroy(ch.side);
@@ -933,6 +934,10 @@ struct Exec {
   int model0 = 0, Ec = 0;    // model range of the launches being enqueued (Ec = 0: the whole ensemble)
   bool defer_dw = false;     // weight gradients + Adam of every layer in ONE launch at the end of backward (dwadam.cuh)
   StepRecorder* rec = nullptr;  // non-null: launches are recorded as ops of the persistent step kernel (stepk.cuh)
+  // stand-alone weight-gradient GEMMs (gradient path: they feed nothing but the optimizer / the gradient exchange) leave
+  // the dX chain for this stream; each waits for what has been enqueued on the chain's stream so far (its dY and input)
+  cudaStream_t dw_stream = nullptr;
+  cudaEvent_t dw_event = nullptr;
   bool ok() const { return err == cudaSuccess; }
   // stream dependencies: real events, or level bookkeeping while recording
   void ev_record(cudaEvent_t ev, cudaStream_t s) {
@@ -1110,7 +1115,19 @@ struct Exec {
       e.drv_clsb_ld = W.rcap;
       e.adam = &pl->d_dyn->s.adam;
     }
+    const bool aside = dw_stream && !fused && dw_stream != st;
+    cudaStream_t chain_st = st;
+    if (aside) {
+      if (rec) {
+        rec->after(dw_stream, st);
+      } else {
+        cudaEventRecord(dw_event, st);
+        cudaStreamWaitEvent(dw_stream, dw_event, 0);
+      }
+      st = dw_stream;
+    }
     launch(fused ? EPI_GRAD_ADAM : EPI_GRAD, p, e, ((fused ? "gemm_dw_adam." : "gemm_dw.") + sub).c_str());
+    st = chain_st;
   }
 
   EpiParams epi_elu(const Shadow& W, const C8Buf& out, int width, bool class_aug) const {
@@ -1422,6 +1439,15 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
       cudaEventRecord(ev, producer);
       cudaStreamWaitEvent(waiter, ev, 0);
     };
+    // gradient path (stand-alone weight-gradient GEMMs inside the chain): they run on the range's otherwise unused main
+    // stream, next to the dX chain on the caller's stream
+    const bool dw_aside = backward && !fused_adam && !forked && overlap && (pl->sched & 8);
+    ex.dw_stream = dw_aside ? ch.main : nullptr;
+    ex.dw_event = ch.ev_dw;
+    if (dw_aside && !use_stepk) {
+      cudaEventRecord(ch.ev_dw, cm);  // (the split-K path zeroes the gradient buffer on the caller's stream first)
+      cudaStreamWaitEvent(ch.main, ch.ev_dw, 0);
+    }
     auto launch_noise = [&]() {
       const drvae_eps_layout_t& el = pl->epsl;
       EpsSegs sg{};
@@ -1549,12 +1575,12 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
         }
         ex.phase = "dz1.bwd";
         ex.block_bwd(pl->dz1b, v.dY9, v.Z3b, 0, pl->Z3, v.dZ3.p, v.dZ3.ms, CNT_F, Fb);
-        if (!ex.rec) cudaEventRecord(pl->bucket_ev[0], ex.st);
+        if (!ex.rec) cudaEventRecord(pl->bucket_ev[0], ex.dw_stream ? ex.dw_stream : ex.st);
         ex.row_op(SROW_Z3_BACK, "z3_back", row_items(round_up(Fb, 128)), 0,
                   [&]() { launch_k(pl->view.Z3c <= 128 ? z3_back_kernel<4> : z3_back_kernel<MAXJ>, rows_grid(round_up(Fb, 128)), dim3(ROW_THREADS), 0, ex.st, 2, v); });
         ex.phase = "z3.bwd";
         ex.block_bwd(pl->z3b, v.dY7, v.Z1e, 0, pl->Z, v.dZ1e.p, v.dZ1e.ms, CNT_F, Fb);
-        if (!ex.rec) cudaEventRecord(pl->bucket_ev[1], ex.st);
+        if (!ex.rec) cudaEventRecord(pl->bucket_ev[1], ex.dw_stream ? ex.dw_stream : ex.st);
         // what q_back needs from this stream; the loss reduction that follows here is joined at the end of the step only
         if (overlap) ex.ev_record(ch.ev_side_bwd, ex.st);
       }
@@ -1604,8 +1630,8 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
 
     if (backward && ex.ok()) {
       size_t bk = pl->has_fprop ? 2 : 0;  // buckets 0, 1 (decoder_z1, encoder_z3) were recorded by the side branch
-      auto bucket_done = [&]() {
-        if (!ex.rec) cudaEventRecord(pl->bucket_ev[bk], ex.st);
+      auto bucket_done = [&](bool weight_gemm = true) {
+        if (!ex.rec) cudaEventRecord(pl->bucket_ev[bk], (weight_gemm && ex.dw_stream) ? ex.dw_stream : ex.st);
         ++bk;
       };
       ex.phase = "dec.bwd";
@@ -1624,11 +1650,11 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
             after(st, ch.ev_clf, cm);
             on(st);
             clf_grad();
-            bucket_done();
+            bucket_done(false);
             on(cm);
           } else {
             clf_bwd();
-            bucket_done();
+            bucket_done(false);
           }
         }
       }
@@ -1648,6 +1674,14 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
       bucket_done();
     }
     if (overlap) ex.ev_wait(cm, ch.ev_side_end);
+    if (ex.dw_stream) {  // join the weight-gradient stream
+      if (ex.rec) {
+        ex.rec->after(cm, ex.dw_stream);
+      } else {
+        cudaEventRecord(ch.ev_dw_end, ex.dw_stream);
+        cudaStreamWaitEvent(cm, ch.ev_dw_end, 0);
+      }
+    }
     if (ex.rec && ex.ok()) {
       // ---- the recorded chain as one cooperative launch ----
       ex.rec = nullptr;

@@ -123,8 +123,30 @@ def wrap_in_VFAEDataset(sing, pair=None, y_key="y", concat="sing_only", downlabe
 # ------------------------------------------------------------------------------------------------
 # metrics (DGMMixin.py:128-190), batched on the device
 # ------------------------------------------------------------------------------------------------
-def eval_x_reconstruction(x, x_rec, x_rec_sigma=None):
-    """rmse, variance-weighted r2, mean per-row Pearson r, mean per-row Gaussian log-likelihood."""
+def eval_x_reconstruction(x, x_rec, x_rec_sigma=None, mask=None):
+    """rmse, variance-weighted r2, mean per-row Pearson r, mean per-row Gaussian log-likelihood over the rows with
+    mask != 0 (DGMMixin.py:128-158).  CUDA tensors go through drvae_eval_x_reconstruction (fp64 device reductions, one
+    4-double read back); CPU tensors (host-side tests) through the same formulas in torch."""
+    if x.is_cuda:
+        import ctypes
+        from . import _lib
+        lib = _lib.load()
+        x = x.detach().float().contiguous()
+        r = x_rec.detach().float().contiguous()
+        sg = x_rec_sigma.detach().float().contiguous() if x_rec_sigma is not None else None
+        mk = mask.detach().to(torch.int32).contiguous() if mask is not None else None
+        N, X = x.shape
+        ws = torch.empty(int(lib.drvae_eval_workspace_bytes(N, X)), dtype=torch.uint8, device=x.device)
+        out = torch.empty(4, dtype=torch.float64, device=x.device)
+        ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+        _lib.check(lib.drvae_eval_x_reconstruction(ptr(x), ptr(r), ptr(sg), ptr(mk), N, X, ptr(out), ptr(ws),
+                                                   ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)), "eval_x_reconstruction")
+        v = out.cpu().tolist()
+        return {"rmse": v[0], "r2": v[1], "pearr": v[2], "ll": v[3]}
+    if mask is not None:
+        idx = torch.nonzero(mask).view(-1)
+        x, x_rec = x[idx], x_rec[idx]
+        x_rec_sigma = x_rec_sigma[idx] if x_rec_sigma is not None else None
     x = x.double()
     r = x_rec.double()
     out = {}
@@ -189,9 +211,9 @@ def evaluate_performance(model, return_full_data=False, **batch):
     perf.update(("x1_" + k, v) for k, v in m.items())
     parts.append("X1: RMSE: {:.3f} R2: {:.3f} Pearson: {:.3f}".format(perf["x1_rmse"], perf["x1_r2"], perf["x1_pearr"]))
     if model.kind != "vfae":
-        idx = torch.nonzero(batch["has_x2"].to(dev)).view(-1)
-        if len(idx) > 0:
-            m = eval_x_reconstruction(batch["x2"].to(dev)[idx], res["px2"][0][idx], res["px2"][1][idx])
+        hx2 = batch["has_x2"].to(dev)
+        if bool(hx2.ne(0).any()):
+            m = eval_x_reconstruction(batch["x2"].to(dev), res["px2"][0], res["px2"][1], mask=hx2)
             perf.update(("x2_" + k, v) for k, v in m.items())
             parts.append("X2: RMSE: {:.3f} R2: {:.3f} Pearson: {:.3f}".format(perf["x2_rmse"], perf["x2_r2"], perf["x2_pearr"]))
         else:

@@ -191,6 +191,16 @@ int drvae_infer(drvae_plan_t* plan, const float* x1, int N, const drvae_infer_ou
  * with weight norm always use the tensor-core path. */
 int drvae_set_infer_precision(drvae_plan_t* plan, int fp32);
 
+/* Reconstruction metrics of the evaluation path: DeepGenerativeModelMixin.eval_x_reconstruction, src/DGMMixin.py:128-158
+ * (numpy RMSE, sklearn r2_score(multioutput='variance_weighted'), the Python loop of scipy.stats.pearsonr over rows, the
+ * mean per-row Gaussian log-likelihood of src/blocks.py:230-234).  x, x_rec, x_sigma: fp32 [N][X] row-major device
+ * buffers (x_sigma may be NULL: ll = NaN); mask: optional int32 [N], rows with mask == 0 are left out (the reference
+ * indexes the labeled / paired rows first); out: 4 doubles on the device {rmse, r2, pearr, ll}; workspace: device
+ * buffer of drvae_eval_workspace_bytes(N, X) bytes.  fp64 arithmetic like the reference, fixed-order reductions. */
+long long drvae_eval_workspace_bytes(int N, int X);
+int drvae_eval_x_reconstruction(const float* x, const float* x_rec, const float* x_sigma, const int* mask, int N, int X,
+                                double* out, void* workspace, void* stream);
+
 /* Launch mechanism.  With graphs enabled (default) drvae_train_step / drvae_loss_forward replay their launch
  * sequence as a CUDA graph from the third call with the same (N, batch buffers, output buffer, stream) on;
  * per-step scalars live in device memory, so only one kernel node's arguments change between steps.  Calls on

@@ -100,3 +100,36 @@ def test_ensemble_checkpoints_interchange_with_the_reference_format(tmp_path):
     assert torch.equal(a.params, c.params) and torch.equal(a.adam_v, c.adam_v)
     with pytest.raises(ValueError):
         ckpt.load_ensemble(b, paths[:-1])
+
+
+@pytest.mark.gpu
+def test_reconstruction_metrics_kernel_matches_the_reference():
+    """drvae_eval_x_reconstruction (fp64 device reductions) against the outputs of the reference's own
+    eval_x_reconstruction / logp_perx (tests/golden/eval_metrics.npz, oracle/make_golden_eval.py): all rows and a row
+    mask; stored inputs and inputs regenerated from the fixture's seed at the L1000 shape."""
+    import numpy as np
+    from helpers import GOLDEN as GOLDEN_DIR
+    from drvae_b200.training import eval_x_reconstruction
+    g = np.load(os.path.join(GOLDEN_DIR, "eval_metrics.npz"))
+    for name in ("small", "l1000"):
+        N, X, seed = (int(v) for v in g[name + "/shape_seed"])
+        gen = torch.Generator().manual_seed(seed)
+        x = torch.randn(N, X, generator=gen)
+        rec = x + 0.5 * torch.randn(N, X, generator=gen)
+        sg = torch.rand(N, X, generator=gen) * 0.9 + 0.1
+        mask = (torch.arange(N) % 3 != 1).int()
+        if name == "small":
+            assert np.array_equal(x.numpy(), g["small/x"]) and np.array_equal(sg.numpy(), g["small/sg"])
+        for tag, mk in (("all", None), ("masked", mask)):
+            want = g["%s/%s" % (name, tag)]
+            got = eval_x_reconstruction(x.cuda(), rec.cuda(), sg.cuda(), mask=mk.cuda() if mk is not None else None)
+            # rmse / r2 / pearr: the reference works in float64 on the same float32 data (1e-9); its log-likelihood is
+            # evaluated in float32 (blocks.py:233-234), the kernel's in float64 (1e-6 = the reference's own rounding)
+            tol = dict(rmse=1e-9, r2=1e-9, pearr=1e-9, ll=1e-6)
+            for k, w in zip(("rmse", "r2", "pearr", "ll"), want):
+                assert abs(got[k] - w) <= tol[k] * max(1.0, abs(w)), (name, tag, k, got[k], w)
+            host = eval_x_reconstruction(x, rec, sg, mask=mk)  # the torch formulas used by the CPU tests
+            for k, w in zip(("rmse", "r2", "pearr", "ll"), want):
+                assert abs(host[k] - w) <= tol[k] * max(1.0, abs(w)), (name, tag, k, host[k], w)
+    no_sigma = eval_x_reconstruction(x.cuda(), rec.cuda(), None)
+    assert no_sigma["ll"] != no_sigma["ll"] and abs(no_sigma["rmse"] - g["l1000/all"][0]) < 1e-9

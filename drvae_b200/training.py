@@ -304,3 +304,69 @@ def fit(model, train_loader, valid_loader, add_noise=False, verbose=False, early
             model.save_to_file(model_filename)
             model.w2log("* Snapshotting at epoch {}".format(epoch))
     model.w2log("Finished training at: {}".format(time.strftime("%c")))
+
+
+# ------------------------------------------------------------------------------------------------
+# device-resident training loop (run_drvae.py:148-166 WeightedRandomSampler + DataLoader,
+# utils.py:292-327 compute_balanced_weights, DrVAE.py:766-786 the minibatch loop of fit())
+# ------------------------------------------------------------------------------------------------
+def compute_balanced_weights(labels):
+    """utils.compute_balanced_weights(labels, unlabeled_data_ratio=None): every class (cell line id) weighs 1 / its
+    size, so minibatches are expected to hold the same number of samples of each class.  -> float64 tensor."""
+    labels = np.asarray(labels)
+    classes, inverse, counts = np.unique(labels, return_inverse=True, return_counts=True)
+    return torch.from_numpy((1.0 / counts)[inverse]).double()
+
+
+def device_epoch_indices(weights_dev, batch_size, generator=None):
+    """The row indices of ONE epoch, drawn on the device: WeightedRandomSampler(weights, len(weights)) (multinomial with
+    replacement) cut into DataLoader minibatches (drop_last when the dataset holds at least one full batch).
+    -> int32 [n_batches, batch_size] (the last batch is dropped / the single short batch kept, like the reference)."""
+    n = int(weights_dev.numel())
+    idx = torch.multinomial(weights_dev.float(), n, replacement=True, generator=generator).to(torch.int32)
+    if n >= batch_size:
+        nb = n // batch_size
+        return idx[:nb * batch_size].view(nb, batch_size).contiguous()
+    return idx.view(1, n).contiguous()
+
+
+def fit_resident(model, dataset, batch_size, epochs=1, weights=None, add_noise=False, seed=0):
+    """The minibatch loop of fit() with the whole training set resident on the GPU.
+
+    `dataset` is a DrVAEDataset / VFAEDataset (a few thousand x 978 floats).  Its fields are copied to the device once;
+    per epoch ONE device multinomial draw gives every minibatch's row indices, and each step reads the dataset through
+    its indices (drvae_batch_t.row_index): no gather kernel, no per-step host->device traffic, no host synchronisation
+    inside an epoch — the loss terms of all steps stay in a device buffer and are read once at the end of the epoch.
+    From the third step on every step of an epoch is one CUDA-graph replay (same buffers, same shapes).
+    Returns [per-epoch OrderedDict of mean loss terms].  Early stopping / evaluation stay in fit()."""
+    from .plan import LOSS_KEYS
+    dev = model.plan.device
+    fields = {k: getattr(dataset, k) for k in dataset.fields}
+    fields.pop("s", None)
+    batch_all = model._batch_kwargs(**{k: v for k, v in fields.items()})
+    n = int(batch_all["x1"].shape[0])
+    bs = min(int(batch_size), n)
+    model._ensure_capacity(bs)
+    plan = model.plan
+    data = {k: (v.to(dev).float().contiguous() if v.is_floating_point() else v.to(dev).to(torch.int32).contiguous())
+            for k, v in batch_all.items() if v is not None}
+    w = (weights if weights is not None else torch.ones(n, dtype=torch.float64)).to(dev)
+    gen = torch.Generator(device=dev).manual_seed(int(seed))
+    model.add_noise = add_noise
+    model.train()
+    history = []
+    cur = None
+    noise_seed = (int(model.random_seed) << 20) ^ 0x5DEECE66D
+    for _ in range(int(epochs)):
+        idx = device_epoch_indices(w, bs, gen)
+        ring = torch.zeros(idx.shape[0], 8, device=dev)
+        if cur is None or cur.numel() != idx.shape[1]:
+            cur = torch.empty(idx.shape[1], dtype=torch.int32, device=dev)  # fixed address: every step replays one graph
+        for b in range(idx.shape[0]):
+            cur.copy_(idx[b])
+            out = plan.train_step(dict(data, row_index=cur), model._hparams(True), seed=noise_seed)
+            ring[b].copy_(out[0], non_blocking=True)
+            model.finished_training_iters += 1
+        mean = ring.mean(0).cpu()
+        history.append(OrderedDict((k, float(mean[i])) for i, k in enumerate(LOSS_KEYS) if k != "MMD"))
+    return history

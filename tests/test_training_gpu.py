@@ -133,3 +133,40 @@ def test_reconstruction_metrics_kernel_matches_the_reference():
                 assert abs(host[k] - w) <= tol[k] * max(1.0, abs(w)), (name, tag, k, host[k], w)
     no_sigma = eval_x_reconstruction(x.cuda(), rec.cuda(), None)
     assert no_sigma["ll"] != no_sigma["ll"] and abs(no_sigma["rmse"] - g["l1000/all"][0]) < 1e-9
+
+
+@pytest.mark.gpu
+def test_device_resident_fit_trains_without_host_batches():
+    """fit_resident: dataset on the GPU, one device multinomial draw per epoch (the reference's balanced
+    WeightedRandomSampler), steps reading the dataset through row indices and replaying ONE CUDA graph.  The loss falls,
+    the classifier learns, the step counter follows the reference's bookkeeping, and the balanced weights equal
+    utils.compute_balanced_weights."""
+    from drvae_b200 import DrVAE, wrap_in_DrVAEDataset
+    from drvae_b200.cli import synthetic_data, split
+    from drvae_b200.training import compute_balanced_weights, device_epoch_indices, fit_resident
+    sing, pair = synthetic_data(600, dim_x=60, seed=1)
+    tr_s, va_s, _ = split(sing, 1)
+    tr_p, va_p, _ = split(pair, 1)
+    train_ds, _ = wrap_in_DrVAEDataset(tr_s, tr_p)
+    valid_ds, _ = wrap_in_DrVAEDataset(va_s, va_p)
+    model = DrVAE(dim_x=60, dim_s=1, dim_y=2, dim_h_en_z1=[32], dim_h_de_z1=[16], dim_h_en_z2Fz1=[], dim_h_en_z3=[16], dim_h_de_x=[32],
+                  dim_h_clf=[], dim_z1=8, dim_z3=6, type_rec="diag_gaussian", epochs=30, batch_size=60, nonlinearity="elu",
+                  learning_rate=5e-3, L=1, weight_decay=0.0, add_noise_var=0.01, yloss_rate=50., use_MMD=False, pertloss_rate=0.05,
+                  random_seed=3)
+    n = len(train_ds)
+    labels = np.arange(n) % 7  # stand-in for the cell line ids the reference balances by (run_drvae.py:148-151)
+    w = compute_balanced_weights(labels)
+    counts = np.bincount(labels)
+    assert np.allclose(w.numpy(), 1.0 / counts[labels])
+    idx = device_epoch_indices(w.cuda(), 60, torch.Generator(device="cuda").manual_seed(0))
+    assert idx.dtype == torch.int32 and tuple(idx.shape) == (n // 60, 60) and int(idx.min()) >= 0 and int(idx.max()) < n
+    before, _ = model.evaluate_performance_on_dataset(valid_ds)
+    replays0 = model.plan.graph_replays()
+    hist = fit_resident(model, train_ds, batch_size=60, epochs=30, weights=w, add_noise=True, seed=5)
+    after, _ = model.evaluate_performance_on_dataset(valid_ds)
+    assert len(hist) == 30 and all(np.isfinite(h["CMPL"]) for h in hist)
+    assert hist[-1]["CMPL"] < hist[0]["CMPL"], (hist[0]["CMPL"], hist[-1]["CMPL"])
+    assert float(after["losses"]["RECL"]) > float(before["losses"]["RECL"])
+    assert after["y_auroc"] > 0.65 and after["y_auroc"] > before["y_auroc"], (before["y_auroc"], after["y_auroc"])
+    assert model.finished_training_iters == 30 * (n // 60)
+    assert model.plan.graph_replays() - replays0 >= 30 * (n // 60) - 4  # every step after the capture is a replay

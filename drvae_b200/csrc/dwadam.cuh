@@ -34,7 +34,14 @@ constexpr int DWA_MAX_LAYERS = 24;
 constexpr int DWA_R = 16;          // weight rows per state stage
 constexpr int DWA_NST = 4;         // state stages
 constexpr int DWA_OPS = 2;         // operand stages
-constexpr int DWA_EW = 16;         // epilogue warps
+#ifndef DWA_EPI_WARPS
+#define DWA_EPI_WARPS 8
+#endif
+constexpr int DWA_EW = DWA_EPI_WARPS;  // epilogue warps (8 or 16: warp w reads TMEM lane quarter w % 4; measured 16 -> 8: 0.402 -> 0.400 ms, fewer
+                                       // instructions per parameter, profiles/r02_experiments.md)
+constexpr int DWA_RPW = DWA_R * 4 / DWA_EW;  // weight rows of a stage per epilogue warp
+static_assert(DWA_EW % 4 == 0 && DWA_RPW * DWA_EW == DWA_R * 4 && (DWA_RPW == 4 || DWA_RPW == 8), "epilogue geometry");
+static_assert(DWA_EW * 32 >= 256, "the bias staging needs one epilogue thread per tile column");
 constexpr int DWA_THREADS = (4 + DWA_EW) * 32;
 constexpr int DWA_OP_STAGE = GEMM_A_STAGE_BYTES + 256 * GEMM_BK * 2;  // 48 KB
 constexpr int DWA_ARR = DWA_R * 128 * 4;                              // one array of a state stage
@@ -84,7 +91,7 @@ struct DwaParams {
   DebugWord* dbg;
   unsigned long long* trace;
   int trace_id;
-  int debug_flags;            // measurement knob (DRVAE_B200_DWA_DEBUG): 1 = no operand loads / MMA (gradient = 0)
+  int debug_flags;            // measurement knob (DRVAE_B200_DWA_DEBUG): 1 = no operand loads / MMA (gradient = 0: NOT a valid step)
   unsigned long long* stats;  // optional [8] cycle counters of the roles' barrier waits (drvae_debug_dwa_stats)
 };
 
@@ -113,9 +120,9 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
 }
 
 enum { DWS_EPI_ACC = 0, DWS_EPI_STATE, DWS_LOADER_EMPTY, DWS_STORER_DONE, DWS_STORER_READ, DWS_PROD_EMPTY, DWS_MMA_FULL, DWS_CTA_TOTAL };
-#define DWS_T0() const long long dws_t0 = p.stats ? clock64() : 0
+#define DWS_T0() const long long dws_t0 = (STATS && p.stats) ? clock64() : 0
 #define DWS_ADD(acc) \
-  if (p.stats) acc += clock64() - dws_t0
+  if (STATS && p.stats) acc += clock64() - dws_t0
 
 // issue / complete halves of a 4-column TMEM load (the load is in flight across a barrier wait)
 __device__ __forceinline__ void tmem_ld4_issue(uint32_t taddr, uint32_t (&r)[4]) {
@@ -129,6 +136,37 @@ __device__ __forceinline__ void tmem_ld4_wait(bool have, uint32_t (&r)[4], float
   if (have) asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3])::"memory");
 #pragma unroll
   for (int i = 0; i < 4; ++i) v[i] = have ? __uint_as_float(r[i]) : 0.f;
+}
+
+// RPW consecutive fp32 columns of 32 lanes, issue / wait halves
+template <int N>
+__device__ __forceinline__ void tmem_ldN_issue(uint32_t taddr, uint32_t (&r)[N]) {
+  __syncwarp();
+  if constexpr (N == 4) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr)
+                 : "memory");
+  } else if constexpr (N == 8) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+  } else {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+  }
+}
+template <int N>
+__device__ __forceinline__ void tmem_ldN_wait(bool have, uint32_t (&r)[N], float (&v)[N]) {
+  if (have) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] = have ? __uint_as_float(r[i]) : 0.f;
 }
 
 struct DwaTile {
@@ -165,6 +203,8 @@ __device__ __forceinline__ bool dwa_stage_rows(const DwaLayer& y, int s0, int& w
   return which < y.ntens && n < y.rows_each;
 }
 
+// STATS: instrumented instance (role wait counters, drvae_debug_dwa_stats); the production instance has none of it
+template <bool STATS>
 __global__ void __launch_bounds__(DWA_THREADS, 1) dwadam_kernel(const DwaParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t op_full[DWA_OPS], op_empty[DWA_OPS], acc_full[2], acc_empty[2];
@@ -195,7 +235,7 @@ __global__ void __launch_bounds__(DWA_THREADS, 1) dwadam_kernel(const DwaParams 
     for (int s = 0; s < DWA_NST; ++s) {
       mbar_init(&st_full[s], 1);
       mbar_init(&st_done[s], DWA_EW);
-      mbar_init(&st_empty[s], (p.debug_flags & 2) ? DWA_EW : 1);
+      mbar_init(&st_empty[s], 1);
     }
     mbar_fence_init();
   }
@@ -211,7 +251,7 @@ __global__ void __launch_bounds__(DWA_THREADS, 1) dwadam_kernel(const DwaParams 
   const uint32_t tmem_base = tmem_base_s;
   pdl_wait();
   long long w_a = 0, w_b = 0;  // wait-cycle counters of this thread's role (p.stats)
-  const long long cta_t0 = p.stats ? clock64() : 0;
+  const long long cta_t0 = (STATS && p.stats) ? clock64() : 0;
 
   if (warp == 0) {
     // ===================== operand producer =====================
@@ -272,7 +312,7 @@ __global__ void __launch_bounds__(DWA_THREADS, 1) dwadam_kernel(const DwaParams 
   } else if (warp == 2) {
     // ===================== optimizer-state storer =====================
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles && !(p.debug_flags & 2); tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const DwaTile t = dwa_tile(p, L, tile);
       if (!t.active) continue;
       const DwaLayer& y = L[t.layer];
@@ -381,26 +421,27 @@ __global__ void __launch_bounds__(DWA_THREADS, 1) dwadam_kernel(const DwaParams 
       }
       __syncwarp();
       tc_fence_after();
-      const uint32_t taddr = tmem_base + a * 256 + ((uint32_t)(q * 32) << 16) + g * 4;
-      // All 16 warps work on the same stage (4 weight rows each): a stage is occupied for the shortest possible time,
-      // which is what the 4-slot ring needs.  Measured alternatives (profiles/r02_experiments.md): column group g owning
-      // slot g and all 16 rows of its stages (fewer barrier operations per parameter, but no overlap of a slot's load
-      // and its update): 443 -> 503 us; writing p, m, v straight from registers instead of tensor stores: 443 -> 475 us.
-      //
-      // (tensor, row) of a stage's first weight row, tracked incrementally: stages advance by 16 shadow rows and the
-      // stacking blocks are multiples of 16
+      const uint32_t taddr = tmem_base + a * 256 + ((uint32_t)(q * 32) << 16) + g * DWA_RPW;
+      // All epilogue warps work on the same stage (DWA_RPW weight rows each): a stage is occupied for the shortest
+      // possible time, which is what the 4-slot ring needs.  Measured alternatives (profiles/r02_experiments.md): column
+      // group g owning slot g and all 16 rows of its stages: 443 -> 503 us; writing p, m, v straight from registers
+      // instead of tensor stores: 443 -> 475 us (that variant is gone).  The kernel is instruction-issue bound
+      // (ncu: 56 % issue-active with 5 warps per scheduler), so the per-stage bookkeeping is kept out of this loop:
+      // (tensor, row) of a stage's first weight row is tracked incrementally — stages advance by 16 shadow rows and
+      // the stacking blocks are multiples of 16.
       int blk = t.n0 / y.ilv_stride, rem = t.n0 - blk * y.ilv_stride;
-      const int my_off = (g * 4) * 128 + scol;  // this thread's first element inside a stage array
+      const int my_off = (g * DWA_RPW) * 128 + scol;  // this thread's first element inside a stage array
       const bool wc = is_w || is_c;
-      const int rot = lane >> 3;  // shadow rows are written rotated by the lane's chunk: conflict-free 2-byte stores
-      for (int sub = 0; sub < t.BN / DWA_R; ++sub, ++it, rem += DWA_R) {
+      const int ss_off = ((kl >> 3) * DWA_R + g * DWA_RPW) * 8 + (kl & 7);
+      const int nsub = t.BN / DWA_R;
+      for (int sub = 0; sub < nsub; ++sub, ++it, rem += DWA_R) {
         if (rem >= y.ilv_stride) rem -= y.ilv_stride, ++blk;
         const int which = rem >= y.ilv_block ? 1 : 0;
         const int n = blk * y.ilv_block + rem - which * y.ilv_block;
         const bool has = which < y.ntens && n < y.rows_each;
         const int s = it % DWA_NST;
-        uint32_t accr[4];
-        if (have_acc) tmem_ld4_issue(taddr + sub * DWA_R, accr);  // in flight while this warp waits for the stage
+        uint32_t accr[DWA_RPW];
+        if (have_acc) tmem_ldN_issue<DWA_RPW>(taddr + sub * DWA_R, accr);  // in flight while this warp waits for the stage
         if (lane == 0) {
           DWS_T0();
           mbar_wait_sleepy(&st_full[s], (it / DWA_NST) & 1, p.dbg, 0xA2000000u | sub);
@@ -411,83 +452,45 @@ __global__ void __launch_bounds__(DWA_THREADS, 1) dwadam_kernel(const DwaParams 
         float* sp = reinterpret_cast<float*>(st) + my_off;
         float* sm = reinterpret_cast<float*>(st + DWA_ARR) + my_off;
         float* sv = reinterpret_cast<float*>(st + 2 * DWA_ARR) + my_off;
-        bf16* ss = reinterpret_cast<bf16*>(st + 3 * DWA_ARR) + ((kl >> 3) * DWA_R + g * 4) * 8 + (kl & 7);
-        float shv[4] = {0.f, 0.f, 0.f, 0.f};
-        float pv[4], mv[4], vv[4], acc[4];
+        bf16* ss = reinterpret_cast<bf16*>(st + 3 * DWA_ARR) + ss_off;
+        float pv[DWA_RPW], mv[DWA_RPW], vv[DWA_RPW], acc[DWA_RPW];
         const bool upd = has && wc;
         if (upd) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) pv[i] = sp[i * 128], mv[i] = sm[i * 128], vv[i] = sv[i * 128];
+          for (int i = 0; i < DWA_RPW; ++i) pv[i] = sp[i * 128], mv[i] = sm[i * 128], vv[i] = sv[i * 128];
         }
-        tmem_ld4_wait(have_acc, accr, acc);  // warp-collective: outside the lane-dependent branches
-        const bool direct = p.debug_flags & 2;
-        if (direct) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&st_empty[s]);  // the stage is in registers: the loader may refill it
-        }
+        tmem_ldN_wait<DWA_RPW>(have_acc, accr, acc);  // warp-collective: outside the lane-dependent branches
         if (upd) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) adam_update(acc[i], pv[i], mv[i], vv[i], h);
-          if (direct) {
-            const int base = y.w_off[which] + (n + g * 4) * y.ld + (is_w ? kk : kk - 1);
+          for (int i = 0; i < DWA_RPW; ++i) adam_update(acc[i], pv[i], mv[i], vv[i], h);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              if (n + g * 4 + i < y.rows_each) {
-                P[base + i * y.ld] = pv[i];
-                M1[base + i * y.ld] = mv[i];
-                V2[base + i * y.ld] = vv[i];
-              }
-            }
-          } else {
+          for (int i = 0; i < DWA_RPW; ++i) sp[i * 128] = pv[i], sm[i * 128] = mv[i], sv[i * 128] = vv[i];
+          if (!is_w) {  // class columns: the forward reads them as fp32 per-class bias rows
+            float* d = p.drv + t.model * p.drv_ms + y.drv_clsb_off + (long long)(kk - y.kin - 1) * y.drv_clsb_ld + t.n0 + sub * DWA_R +
+                       g * DWA_RPW;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) sp[i * 128] = pv[i], sm[i * 128] = mv[i], sv[i * 128] = vv[i];
-          }
-          if (is_w) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) shv[i] = pv[i];
-          } else {  // class columns: the forward reads them as fp32 per-class bias rows
-            float* d = p.drv + t.model * p.drv_ms + y.drv_clsb_off + (long long)(kk - y.kin - 1) * y.drv_clsb_ld + t.n0 + sub * DWA_R + g * 4;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              if (n + g * 4 + i < y.rows_each) d[i] = pv[i];
+            for (int i = 0; i < DWA_RPW; ++i)
+              if (n + g * DWA_RPW + i < y.rows_each) d[i] = pv[i];
           }
         } else if (has && is_b) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int c = sub * DWA_R + g * 4 + i;  // tile-local weight row
+          for (int i = 0; i < DWA_RPW; ++i) {
+            const int c = sub * DWA_R + g * DWA_RPW + i;  // tile-local weight row
             float pb = bst[c], mb = bst[256 + c], vb = bst[512 + c];
             adam_update(acc[i], pb, mb, vb, h);
             bst[c] = pb, bst[256 + c] = mb, bst[512 + c] = vb;
           }
         }
         // shadow stage [16 chunks][R rows][8]: columns >= kin (ones / class columns, padding) stay zero.  The four
-        // 8-lane groups of a warp write four different chunks whose rows are 256 bytes (= all 32 banks x 2) apart: row
-        // order rotated by the group index so that they hit different banks
-        if (direct) {
-          // shadow: lanes pair up (k even, k odd); the even lane stores the bf16 pairs of rows 0-1, the odd lane of rows 2-3
-          const bool even = !(lane & 1);
-          const float x0 = __shfl_xor_sync(0xffffffffu, even ? shv[2] : shv[0], 1);
-          const float x1 = __shfl_xor_sync(0xffffffffu, even ? shv[3] : shv[1], 1);
-          const int ke = kk & ~1;
-          if (has && ke < y.kin) {
-            const int r0 = g * 4 + (even ? 0 : 2);
-            bf16* sh = p.shadow + t.model * p.shadow_ms + y.sh_off + ((long long)(ke >> 3) * y.rcap + t.n0 + sub * DWA_R + r0) * 8 + (ke & 7);
-            const uint32_t w0 = even ? pack_bf16x2(shv[0], x0) : pack_bf16x2(x0, shv[2]);
-            const uint32_t w1 = even ? pack_bf16x2(shv[1], x1) : pack_bf16x2(x1, shv[3]);
-            if (n + r0 < y.rows_each) *reinterpret_cast<uint32_t*>(sh) = w0;
-            if (n + r0 + 1 < y.rows_each) *reinterpret_cast<uint32_t*>(sh + 8) = w1;
-          }
-        } else {
+        // 8-lane groups of a warp write four chunks 256 bytes apart, i.e. a 4-way bank conflict per store; that costs
+        // shared-memory cycles the kernel has to spare, whereas the conflict-free rotated order cost DWA_RPW^2 selects
+        // per stage on the resource it is short of (issue slots)
+        const bool shw = upd && is_w;
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int r = (i + rot) & 3;
-            const float x = r == 0 ? shv[0] : (r == 1 ? shv[1] : (r == 2 ? shv[2] : shv[3]));
-            ss[r * 8] = __float2bfloat16_rn(x);
-          }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&st_done[s]);
-        }
+        for (int i = 0; i < DWA_RPW; ++i) ss[i * 8] = __float2bfloat16_rn(shw ? pv[i] : 0.f);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&st_done[s]);
       }
       tc_fence_before();
       __syncwarp();
@@ -509,7 +512,7 @@ __global__ void __launch_bounds__(DWA_THREADS, 1) dwadam_kernel(const DwaParams 
       ++j;
     }
   }
-  if (p.stats && lane == 0) {
+  if (STATS && p.stats && lane == 0) {
     if (warp == 0) atomicAdd(p.stats + DWS_PROD_EMPTY, (unsigned long long)w_a);
     if (warp == 1) atomicAdd(p.stats + DWS_LOADER_EMPTY, (unsigned long long)w_a);
     if (warp == 2) atomicAdd(p.stats + DWS_STORER_DONE, (unsigned long long)w_a), atomicAdd(p.stats + DWS_STORER_READ, (unsigned long long)w_b);
@@ -517,7 +520,7 @@ __global__ void __launch_bounds__(DWA_THREADS, 1) dwadam_kernel(const DwaParams 
   }
   tc_fence_before();
   __syncthreads();
-  if (p.stats && threadIdx.x == 0) atomicAdd(p.stats + DWS_CTA_TOTAL, (unsigned long long)(clock64() - cta_t0));
+  if (STATS && p.stats && threadIdx.x == 0) atomicAdd(p.stats + DWS_CTA_TOTAL, (unsigned long long)(clock64() - cta_t0));
   if (warp == 3) tmem_dealloc(tmem_base, 512);
 }
 
@@ -543,12 +546,14 @@ inline cudaError_t dwadam_launch(const DwaParams& p, cudaStream_t st) {
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    cudaError_t err = cudaFuncSetAttribute(dwadam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DWA_SMEM);
+    cudaError_t err = cudaFuncSetAttribute(dwadam_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DWA_SMEM);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(dwadam_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DWA_SMEM);
     if (err != cudaSuccess) return err;
     attr_set[dev] = true;
   }
   const int grid = p.total_tiles < gemm_num_sms() ? p.total_tiles : gemm_num_sms();
-  return launch_k(dwadam_kernel, dim3(grid), dim3(DWA_THREADS), (size_t)DWA_SMEM, st, 1, p);
+  if (p.stats) return launch_k(dwadam_kernel<true>, dim3(grid), dim3(DWA_THREADS), (size_t)DWA_SMEM, st, 1, p);
+  return launch_k(dwadam_kernel<false>, dim3(grid), dim3(DWA_THREADS), (size_t)DWA_SMEM, st, 1, p);
 }
 
 }  // namespace drvae

@@ -395,6 +395,52 @@ __device__ __forceinline__ void epi_chunk(const EpiParams& e, RowCtx& rc, int co
   }
 }
 
+// One (mu, sigma) element of the decoder-loss epilogue.  Reference math: sigma = softplus(s) + 1e-3
+// (src/blocks.py:410-416), log N(t; mu, sigma) (src/blocks.py:230-234) and its gradient towards the two
+// pre-activations, scaled by ncoef = -(loss coefficient of the row).  One exponential serves softplus and its
+// derivative; divisions are reciprocal-multiplies and the transcendentals the flush-to-zero hardware approximations:
+// without .ftz every ex2 / lg2 / rcp carries a denormal-range fix-up (set-predicate + two multiplies), a third of the
+// instructions of a kernel that ncu shows issue-bound (65 % issue-active, profiles/r02_experiments.md).
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_lg2(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// two features at a time: the additions, multiplications and fused multiply-adds as packed fp32 pairs (same IEEE
+// rounding per element); the transcendentals, comparisons and selects stay scalar
+__device__ __forceinline__ float2 decloss_pair(float2 mu, float2 sp, float2 tgt, float ncoef, float2& dmu, float2& dsg) {
+  const float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f, HALF_LOG2PI = 0.9189385332046727f;
+  const float2 x = mul2(make_float2(fminf(sp.x, 20.f), fminf(sp.y, 20.f)), splat2(LOG2E));
+  const float2 ex = make_float2(fast_ex2(x.x), fast_ex2(x.y));
+  const float2 one_ex = add2(ex, splat2(1.f));
+  const float2 l1p = mul2(make_float2(fast_lg2(one_ex.x), fast_lg2(one_ex.y)), splat2(LN2));
+  const float2 tiny = mul2(ex, fma2(splat2(-0.5f), ex, splat2(1.f)));  // log1p(ex) for ex < 1e-3
+  const float2 soft = make_float2(ex.x < 1e-3f ? tiny.x : l1p.x, ex.y < 1e-3f ? tiny.y : l1p.y);
+  const bool bx = sp.x > 20.f, by = sp.y > 20.f;
+  const float2 sg = add2(make_float2(bx ? sp.x : soft.x, by ? sp.y : soft.y), splat2(1e-3f));
+  const float2 sgm = mul2(ex, make_float2(fast_rcp(one_ex.x), fast_rcp(one_ex.y)));
+  const float2 sig = make_float2(bx ? 1.f : sgm.x, by ? 1.f : sgm.y);  // d softplus / d s
+  const float2 inv = make_float2(fast_rcp(sg.x), fast_rcp(sg.y));
+  const float2 t = mul2(fma2(mu, splat2(-1.f), tgt), inv);  // (tgt - mu) / sg
+  const float2 lg = make_float2(fast_lg2(sg.x), fast_lg2(sg.y));
+  const float2 lp = fma2(mul2(splat2(-0.5f), t), t, fma2(splat2(-LN2), lg, splat2(-HALF_LOG2PI)));
+  // d CMPL / d mu = -coef (t - mu) / sg^2 ;  d CMPL / d sg = -coef ((t - mu)^2 / sg^3 - 1 / sg)
+  const float2 c1 = mul2(splat2(ncoef), inv);
+  dmu = mul2(c1, t);
+  dsg = mul2(mul2(c1, fma2(t, t, splat2(-1.f))), sig);
+  return lp;
+}
+
 // Decoder heads: acc_mu / acc_sg are the mu and sigma pre-activations of features
 // [f0, f0+16) of one decoder row.  Reference math: src/blocks.py:410-416 (mu, softplus(.)+1e-3)
 // and :230-234 (Gaussian log-density with sigma parametrisation).
@@ -424,50 +470,48 @@ __device__ __forceinline__ void epi_dec_chunk(const EpiParams& e, RowCtx& rc, in
     }
     return;
   }
-  // EPI_DECLOSS
-  float tg[16];
-  {
-    const float4* t4 = e.tgt4 + rc.model * e.tgt_ms + (long long)(f0 >> 2) * e.tgt_rcap + (rc.trow < 0 ? 0 : rc.trow);
+  // EPI_DECLOSS: two halves of 8 features (bias, targets and gradients of 8 features live at a time: the 96-register
+  // budget of the 640-thread CTA spilled with all 16).  Chunks that lie entirely inside the real features take the
+  // unmasked path; only the last chunk of the last tile masks feature by feature.
+  const bool full = f0 + 16 <= e.X;
+  const float4* t4 = e.tgt4 + rc.model * e.tgt_ms + (long long)(f0 >> 2) * e.tgt_rcap + (rc.trow < 0 ? 0 : rc.trow);
+  uint4* o = reinterpret_cast<uint4*>(e.out_c8 + rc.model * e.out_c8_ms);
+  const long long r = e.out_c8_row0 + rc.row;
+  const float ncoef = -rc.coef;
+  float2 ls2 = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int i = 0; i < 16; i += 4) {
+  for (int hh = 0; hh < 2; ++hh) {
+    float tg[8];
+#pragma unroll
+    for (int i = 0; i < 8; i += 4) {
       float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (rc.trow >= 0 && f0 + i < e.Xc) t = t4[(long long)(i >> 2) * e.tgt_rcap];
+      if (rc.trow >= 0 && f0 + hh * 8 + i < e.Xc) t = t4[(long long)(hh * 2 + (i >> 2)) * e.tgt_rcap];
       tg[i] = t.x, tg[i + 1] = t.y, tg[i + 2] = t.z, tg[i + 3] = t.w;
     }
-  }
-  float dmu[16], dsg[16];
-  float ls = 0.f;
-  const float LOG2PI = 1.8378770664093453f;
+    float dmu[8], dsg[8];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    int f = f0 + i;
-    bool ok = rc.valid && f < e.X;
-    float mu = acc_mu[i] + bmu[i];
-    float sp = acc_sg[i] + bsg[i];
-    // softplus and its derivative from one exponential: e = exp(sp); softplus = log1p(e); sigmoid = e / (1 + e)
-    float ex = __expf(fminf(sp, 20.f));
-    float sg = (sp > 20.f ? sp : (ex < 1e-3f ? ex * (1.f - 0.5f * ex) : __logf(1.f + ex))) + 1e-3f;
-    float sig = sp > 20.f ? 1.f : __fdividef(ex, 1.f + ex);
-    float d = tg[i] - mu;
-    float inv = __fdividef(1.f, sg);
-    float inv2 = inv * inv;
-    float lp = -0.5f * (LOG2PI + 2.f * __logf(sg) + d * d * inv2);
-    ls += ok ? lp : 0.f;
-    // d CMPL / d mu = -coef * (t - mu) / sg^2 ;  d CMPL / d sg = -coef * (-1/sg + (t-mu)^2 / sg^3)
-    float gmu = -rc.coef * d * inv2;
-    float gsg = -rc.coef * (d * d * inv2 * inv - inv);
-    dmu[i] = ok ? gmu : 0.f;
-    dsg[i] = ok ? gsg * sig : 0.f;
+    for (int i = 0; i < 8; i += 2) {
+      const int j = hh * 8 + i;
+      float2 gm, gs;
+      const float2 lp = decloss_pair(add2(make_float2(acc_mu[j], acc_mu[j + 1]), make_float2(bmu[j], bmu[j + 1])),
+                                     add2(make_float2(acc_sg[j], acc_sg[j + 1]), make_float2(bsg[j], bsg[j + 1])),
+                                     make_float2(tg[i], tg[i + 1]), ncoef, gm, gs);
+      if (full) {
+        ls2 = add2(ls2, lp);
+        dmu[i] = gm.x, dmu[i + 1] = gm.y, dsg[i] = gs.x, dsg[i + 1] = gs.y;
+      } else {
+        const bool ok0 = f0 + j < e.X, ok1 = f0 + j + 1 < e.X;
+        ls2 = add2(ls2, make_float2(ok0 ? lp.x : 0.f, ok1 ? lp.y : 0.f));
+        dmu[i] = ok0 ? gm.x : 0.f, dmu[i + 1] = ok1 ? gm.y : 0.f;
+        dsg[i] = ok0 ? gs.x : 0.f, dsg[i + 1] = ok1 ? gs.y : 0.f;
+      }
+    }
+    if (e.write_dy) {
+      o[(long long)((ccol_mu >> 3) + hh) * e.out_c8_rcap + r] = pack_bf16x8(dmu);
+      o[(long long)((ccol_sg >> 3) + hh) * e.out_c8_rcap + r] = pack_bf16x8(dsg);
+    }
   }
-  rc.lsum += ls;
-  if (e.write_dy) {
-    uint4* o = reinterpret_cast<uint4*>(e.out_c8 + rc.model * e.out_c8_ms);
-    long long r = e.out_c8_row0 + rc.row;
-    o[(long long)(ccol_mu >> 3) * e.out_c8_rcap + r] = pack_bf16x8(dmu);
-    o[(long long)((ccol_mu >> 3) + 1) * e.out_c8_rcap + r] = pack_bf16x8(dmu + 8);
-    o[(long long)(ccol_sg >> 3) * e.out_c8_rcap + r] = pack_bf16x8(dsg);
-    o[(long long)((ccol_sg >> 3) + 1) * e.out_c8_rcap + r] = pack_bf16x8(dsg + 8);
-  }
+  rc.lsum += ls2.x + ls2.y;  // (rows beyond the dynamic extent: coef = 0 gives zero gradients, epi_end drops their sum)
 }
 
 template <int EPI>

@@ -428,6 +428,11 @@ def other_workloads(ranks, steps):
                                "ms_per_step": per, "value": BATCH / (per * 1e-3), "unit": UNIT, "launches_per_step": launches / max(steps, 50),
                                "floor_us": floor_us, "frac_of_floor": floor_us / (per * 1e3),
                                "floor": "max(24 B x parameters / measured HBM GB/s, GEMM FLOPs / sustained bf16): launch/latency-bound (SURVEY 8(d))"}
+        # the same step through the persistent step kernel (one cooperative launch for the whole forward + dX chain,
+        # grid barriers between dependent stages): measured next to the default graph of launches, not the default
+        plan.set_step_kernel(True)
+        ms2, launches2, _ = time_steps(plan, devb, max(steps, 50), 5, seed=1)
+        out["%s150" % kind]["persistent_step_kernel"] = {"ms_per_step": ms2 / max(steps, 50), "launches_per_step": launches2 / max(steps, 50)}
         del plan
     M = 32
     for kind in ("pvae", "vfae"):

@@ -60,7 +60,7 @@ struct drvae_plan {
   Seg* d_segs = nullptr;
   std::vector<int> h_tabs;  // gradient-epilogue tables of every weight (see make_shadow)
   int* d_tabs = nullptr;
-  int sched = 13;              // schedule knob (DRVAE_B200_SCHED): bit 0 = noise generator on the side stream, bit 2 = classifier weight gradient off the dX chain, bit 3 = stand-alone weight-gradient GEMMs (gradient path) on their own stream, bit 1 = whole classifier backward on the side stream (measured: 1.037 / 1.027 / 1.048 / 1.048 ms for 0 / 1 / 2 / 3)
+  int sched = 13;              // schedule knob (DRVAE_B200_SCHED): bit 0 = noise generator on the side stream, bit 2 = classifier weight gradient off the dX chain, bit 3 = stand-alone weight-gradient GEMMs (gradient path) on their own stream, bit 4 = DrVAE classifier forward as its own kernel on the side stream (measured: no gain, the side branch becomes the longer chain), bit 5 = classifier input gradient inside T_back (measured slower: T_back 15 -> 43-64 us), bit 1 = whole classifier backward on the side stream (measured: 1.037 / 1.027 / 1.048 / 1.048 ms for 0 / 1 / 2 / 3)
   int adam_vec_max = 4;       // debug knob (DRVAE_B200_ADAM_VEC): cap on the vector width of the fused Adam epilogue
   bool wn = false;            // layers.WeightNormLinear instead of nn.Linear
   std::vector<WnRow> wn_rows;
@@ -1384,6 +1384,8 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
   v.clf_splits = std::max(CLF_SPLITS, std::min(CLF_SPLITS_MAX, cdiv(LNb, 64)));
   v.loss_slices = std::max(1, std::min(LOSS_SLICES_MAX, cdiv(Rdb, 512)));
   ex.splitk = backward && !fused_adam && Rdb >= 2048;
+  v.clf_back_fused = (pl->has_T && pl->has_clf && pl->clf_in > pl->Z && (pl->sched & 32) && !(pl->sched & 2)) ? 1 : 0;
+  v.clf_split = (pl->has_T && pl->has_clf && pl->has_fprop && (pl->sched & 16)) ? 1 : 0;
   ex.defer_dw = backward && fused_adam && pl->dwa_ok && pl->dwa_enabled;
   if (ex.splitk) {
     cudaError_t e0 = cudaMemsetAsync(pl->grads, 0, sizeof(float) * (size_t)pl->P * E, st);
@@ -1556,10 +1558,15 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
       });
     }
     if (pl->has_fprop) {
-      // pz1_post weighs unlabeled evaluations by q(y|.), which the classifier in T_post (DrVAE) or
-      // sample_q1 (VFAE) has just produced
+      // pz1_post weighs unlabeled evaluations by q(y|.), which the classifier (T_post or clf_fwd for DrVAE,
+      // sample_q1 for VFAE) produces
       after(side, ch.ev_qy, cm);
       on(side);
+      if (v.clf_split) {
+        ex.phase = "T.fwd";
+        ex.row_op(SROW_CLF_FWD, "clf_fwd", row_items(LNb), 0,
+                  [&]() { launch_k(clf_fwd_kernel, rows_grid(LNb), dim3(ROW_THREADS), 0, ex.st, 2, v); });
+      }
       if (pl->side_delay_cycles > 0 && !ex.rec) spin_kernel<<<1, 1, 0, ex.st>>>(pl->side_delay_cycles);
       ex.row_op(SROW_PZ1_POST, "pz1_post", row_items(round_up(Fb, 128)), 0,
                 [&]() { launch_k(pl->view.Zc <= 128 ? pz1_post_kernel<4> : pz1_post_kernel<MAXJ>, rows_grid(round_up(Fb, 128)), dim3(ROW_THREADS), 0, ex.st, 2, v); });
@@ -1643,7 +1650,10 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
           if (overlap) ex.ev_wait(cm, ch.ev_clf);
         } else {
           if (overlap && pl->has_fprop) ex.ev_wait(cm, ch.ev_kfp);
-          if (overlap && forked && (pl->sched & 4)) {
+          if (v.clf_back_fused) {
+            // T_back (next) computes d loss / d logits and the classifier's input gradient for its own rows; only the
+            // weight gradient remains, after T_back
+          } else if (overlap && forked && (pl->sched & 4)) {
             // only the input gradient (clf_back) is on the chain towards T_back / q_back; the weight gradient runs on
             // the caller's stream, which is otherwise idle until this range joins it in front of the dW+Adam launch
             clf_back();
@@ -1662,6 +1672,18 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
         ex.phase = "T.bwd";
         ex.row_op(SROW_T_BACK, "T_back", row_items(N + PAD_WARPS), 0,
                   [&]() { launch_k(pl->view.Zc <= 128 ? T_back_kernel<4> : T_back_kernel<MAXJ>, rows_grid(N + PAD_WARPS), dim3(ROW_THREADS), 0, ex.st, 2, v); });
+        if (pl->has_clf && v.clf_back_fused) {
+          if (overlap && forked && (pl->sched & 4)) {
+            after(st, ch.ev_clf, cm);
+            on(st);
+            clf_grad();
+            bucket_done(false);
+            on(cm);
+          } else {
+            clf_grad();
+            bucket_done(false);
+          }
+        }
         ex.gemm_dx(v.dYT, pl->Tsh, EPI_STORE_F32, ex.epi_f32(v.dZ1T.p, v.dZ1T.ms, pl->Z, pl->Z, nullptr), CNT_LN, LNb);
         ex.gemm_dw(v.dYT, v.Zdec, 0, pl->Tsh, CNT_LN, LNb, pl->arch.kind == DRVAE_KIND_PVAE ? CNT_NP : -1);
         bucket_done();

@@ -147,6 +147,8 @@ struct DevView {
   int R0cap, LNcap, Rdcap, Fcap, Flcap;
   int has_pair, has_T, has_clf, has_fprop, clf_in;
   int need_grad;
+  int clf_back_fused;  // 1: T_back computes the classifier's input gradient itself (no clf_back launch; DrVAE)
+  int clf_split;     // 1: the classifier q(y|z1, z2f) runs as its own kernel (clf_fwd_kernel) off the main chain instead of inside T_post
   // batch (caller memory)
   MBuf<const float> x1, x2;
   MBuf<const int> y, has_x2, has_y;

@@ -541,7 +541,7 @@ __device__ __forceinline__ void T_post_row(const DevView& v, const int m, const 
     }
     kl = warp_sum(kl);
     if (lane == 0) v.klz2_row.at(m)[r] = q2 ? fmaxf(kl, v.dyn->s.kl_min) : 0.f;
-    if (v.has_clf) classifier_row_regs<J>(v, m, r, i, lane, a_z1, a_ef, v.clf_in > v.Z);
+    if (v.has_clf && !v.clf_split) classifier_row_regs<J>(v, m, r, i, lane, a_z1, a_ef, v.clf_in > v.Z);
   }
 }
 
@@ -551,6 +551,25 @@ __global__ void __launch_bounds__(ROW_THREADS, ROW_LB_TPOST) T_post_kernel(DevVi
   pdl_launch_dependents();
   pdl_wait();
   T_post_row<J>(v, v.model0 + blockIdx.y, blockIdx.x * ROW_WARPS + (threadIdx.x >> 5), threadIdx.x & 31);
+}
+
+// ---------------------------------------------------------------------------------------------
+// clf_fwd: the classifier q(y | z1, z2f - z1) of DrVAE as its own kernel, one warp per stacked row r = l * N + i.
+// Only the label-dependent branch and the backward need q(y|.), the decoder does not: split from T_post it leaves
+// the main chain (sample z2f -> decoder) for the side stream (DevView::clf_split).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void clf_fwd_row(const DevView& v, const int m, const int r, const int lane) {
+  const int* cnt = v.counts.at(m);
+  const int N = cnt[CNT_N], LN = cnt[CNT_LN];
+  if (r >= LN) return;
+  classifier_row(v, m, r, r % N, lane);
+}
+
+__global__ void __launch_bounds__(ROW_THREADS) clf_fwd_kernel(DevView v) {
+  TraceScope trace_scope(v.trace, v.trace_id);
+  pdl_launch_dependents();
+  pdl_wait();
+  clf_fwd_row(v, v.model0 + blockIdx.y, blockIdx.x * ROW_WARPS + (threadIdx.x >> 5), threadIdx.x & 31);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -747,11 +766,9 @@ __global__ void __launch_bounds__(ROW_THREADS, ROW_LB_EVAL) z3_back_kernel(DevVi
 //   unlabeled row : 1/(L N) * d [ sum_j q_j k_j + sum_j q_j (log q_j - log prior_j) ]
 // grid (ceil(LNcap / ROW_WARPS), n_models), one warp per stacked row r = l*N + i
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void clf_back_row(const DevView& v, const int m, const int r, const int lane) {
-  const int* cnt = v.counts.at(m);
-  const int N = cnt[CNT_N], LN = cnt[CNT_LN], Fl = cnt[CNT_FL];
-  if (r >= LN) return;
-  const int l = r / N, i = r - l * N;
+// d loss / d logits of row r = l * N + i (every lane computes the same values; lane 0 stores them for the weight gradient)
+__device__ __forceinline__ void clf_dlogit_row(const DevView& v, const int m, const int r, const int l, const int i, const int Fl, const int lane,
+                                               float (&dl)[MAXY]) {
   const float* cf = v.coefs.at(m);
   const float* qy = v.QY.at(m) + (long long)r * v.Y;
   const bool lb = v.lab.at(m)[i] != 0;
@@ -775,12 +792,20 @@ __device__ __forceinline__ void clf_back_row(const DevView& v, const int m, cons
       dot += q[j] * g[j];
     }
   }
-  float dl[MAXY];
 #pragma unroll
   for (int j = 0; j < MAXY; ++j) {
     dl[j] = (j < v.Y) ? q[j] * (g[j] - dot) : 0.f;
     if (j < v.Y && lane == 0) v.dlogit.at(m)[(long long)r * v.Y + j] = dl[j];
   }
+}
+
+__device__ __forceinline__ void clf_back_row(const DevView& v, const int m, const int r, const int lane) {
+  const int* cnt = v.counts.at(m);
+  const int N = cnt[CNT_N], LN = cnt[CNT_LN], Fl = cnt[CNT_FL];
+  if (r >= LN) return;
+  const int l = r / N, i = r - l * N;
+  float dl[MAXY];
+  clf_dlogit_row(v, m, r, l, i, Fl, lane, dl);
   const float* Wc = v.clf_w.at(m);
   const bool two = v.clf_in > v.Z;
   // (unrolled over the feature slots: the weight loads of all slots are in flight together)
@@ -842,7 +867,10 @@ __device__ __forceinline__ void T_back_row(const DevView& v, const int m, const 
     const float* dzd = p >= 0 ? v.dZdec.at(m) + (long long)(LN + LNp + l * Np + p) * v.Z : nullptr;
     const bool act = q2 && v.klz2_row.at(m)[r] > v.dyn->s.kl_min;
     float* dz1 = v.DZ1.at(m) + (long long)r * v.Z;
-    const float* dz2f_c = v.has_clf ? v.DZ2F.at(m) + (long long)r * v.Z : nullptr;
+    const bool clf_here = v.has_clf && v.clf_back_fused;  // the classifier's input gradient computed right here
+    const float* dz2f_c = (v.has_clf && !clf_here) ? v.DZ2F.at(m) + (long long)r * v.Z : nullptr;
+    float dl[MAXY];
+    if (clf_here) clf_dlogit_row(v, m, r, l, i, cnt[CNT_FL], lane, dl);
     float b_pmu[J], b_plv[J], b_g[J], b_c[J], b_ef[J], b_dz1[J];
 #pragma unroll
     for (int k = 0; k < J; ++k) {  // every load of this sample before the first store
@@ -853,7 +881,21 @@ __device__ __forceinline__ void T_back_row(const DevView& v, const int m, const 
       b_g[k] = (in && dzd) ? dzd[f] : 0.f;
       b_c[k] = (in && dz2f_c) ? dz2f_c[f] : 0.f;
       b_ef[k] = in ? ef[f] : 0.f;
-      b_dz1[k] = (in && v.has_clf) ? dz1[f] : 0.f;
+      b_dz1[k] = (in && v.has_clf && !clf_here) ? dz1[f] : 0.f;
+      if (clf_here && in) {
+        // d loss / d [z1, z2f - z1] = dlogit . Wc (same sums as clf_back_row): z2f gets b, z1 gets a - b
+        const float* Wc = v.clf_w.at(m);
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int j = 0; j < MAXY; ++j) {
+          if (j < v.Y) {
+            a = fmaf(dl[j], Wc[j * v.clf_ld + f], a);
+            b = fmaf(dl[j], Wc[j * v.clf_ld + v.Z + f], b);
+          }
+        }
+        b_c[k] = b;
+        b_dz1[k] = a - b;
+      }
     }
 #pragma unroll
     for (int k = 0; k < J; ++k) {

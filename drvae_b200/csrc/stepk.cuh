@@ -50,7 +50,8 @@ enum {
   SROW_CLF_GRAD_PARTIAL,
   SROW_CLF_GRAD_REDUCE,
   SROW_LOSS_PARTIAL,
-  SROW_LOSS_FINAL
+  SROW_LOSS_FINAL,
+  SROW_CLF_FWD
 };
 
 struct StepOp {
@@ -356,6 +357,7 @@ __global__ void __launch_bounds__(STEPK_THREADS, 1) step_kernel(const __grid_con
               else
                 T_post_row<MAXJ>(T.v, m, r, lane);
               break;
+            case SROW_CLF_FWD: clf_fwd_row(T.v, m, r, lane); break;
             case SROW_Z3_POST: 
               if (T.v.Z3c <= 128)
                 z3_post_row<4>(T.v, m, r, lane);

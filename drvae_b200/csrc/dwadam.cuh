@@ -43,6 +43,12 @@ constexpr int DWA_RPW = DWA_R * 4 / DWA_EW;  // weight rows of a stage per epilo
 static_assert(DWA_EW % 4 == 0 && DWA_RPW * DWA_EW == DWA_R * 4 && (DWA_RPW == 4 || DWA_RPW == 8), "epilogue geometry");
 static_assert(DWA_EW * 32 >= 256, "the bias staging needs one epilogue thread per tile column");
 constexpr int DWA_THREADS = (4 + DWA_EW) * 32;
+// Register budget.  Compiled for two resident CTAs (80 registers) the kernel would leave half of the register file to
+// the row kernels that run next to the early launch (plan.cu) — measured: the launch alone 0.394 -> 0.408 ms, the step
+// with the early launch the same within noise (0.911-0.918 ms either way), the step without it 0.940 -> 0.951 ms.
+#ifndef DWA_MIN_BLOCKS
+#define DWA_MIN_BLOCKS 1
+#endif
 constexpr int DWA_OP_STAGE = GEMM_A_STAGE_BYTES + 256 * GEMM_BK * 2;  // 48 KB
 constexpr int DWA_ARR = DWA_R * 128 * 4;                              // one array of a state stage
 constexpr int DWA_SHB = DWA_R * 256;                                  // bf16 shadow of a stage: [16 chunks][R][8]
@@ -76,6 +82,7 @@ struct DwaLayer {
 
 struct DwaParams {
   int n_layers, n_models, total_tiles;
+  int tile_begin, tile_end;  // tiles of this launch (the step may run the layers whose inputs are complete early, see plan.cu)
   const DwaLayer* layers;   // device
   const DwaMaps* maps;      // device
   const int* tabs;          // plan-wide gradient-epilogue tables
@@ -205,7 +212,7 @@ __device__ __forceinline__ bool dwa_stage_rows(const DwaLayer& y, int s0, int& w
 
 // STATS: instrumented instance (role wait counters, drvae_debug_dwa_stats); the production instance has none of it
 template <bool STATS>
-__global__ void __launch_bounds__(DWA_THREADS, 1) dwadam_kernel(const DwaParams p) {
+__global__ void __launch_bounds__(DWA_THREADS, DWA_MIN_BLOCKS) dwadam_kernel(const DwaParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t op_full[DWA_OPS], op_empty[DWA_OPS], acc_full[2], acc_empty[2];
   __shared__ __align__(8) uint64_t st_full[DWA_NST], st_done[DWA_NST], st_empty[DWA_NST];
@@ -256,7 +263,7 @@ __global__ void __launch_bounds__(DWA_THREADS, 1) dwadam_kernel(const DwaParams 
   if (warp == 0) {
     // ===================== operand producer =====================
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int tile = p.tile_begin + blockIdx.x; tile < p.tile_end; tile += gridDim.x) {
       const DwaTile t = dwa_tile(p, L, tile);
       if (!t.active) continue;
       const DwaLayer& y = L[t.layer];
@@ -281,7 +288,7 @@ __global__ void __launch_bounds__(DWA_THREADS, 1) dwadam_kernel(const DwaParams 
   } else if (warp == 1) {
     // ===================== optimizer-state loader =====================
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int tile = p.tile_begin + blockIdx.x; tile < p.tile_end; tile += gridDim.x) {
       const DwaTile t = dwa_tile(p, L, tile);
       if (!t.active) continue;
       const DwaLayer& y = L[t.layer];
@@ -312,7 +319,7 @@ __global__ void __launch_bounds__(DWA_THREADS, 1) dwadam_kernel(const DwaParams 
   } else if (warp == 2) {
     // ===================== optimizer-state storer =====================
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int tile = p.tile_begin + blockIdx.x; tile < p.tile_end; tile += gridDim.x) {
       const DwaTile t = dwa_tile(p, L, tile);
       if (!t.active) continue;
       const DwaLayer& y = L[t.layer];
@@ -353,7 +360,7 @@ __global__ void __launch_bounds__(DWA_THREADS, 1) dwadam_kernel(const DwaParams 
       const uint32_t hi = (uint32_t)(d0 >> 32), lo0 = (uint32_t)d0;
       const uint32_t smem0 = smem_u32(op_ring) >> 4, stage16 = (uint32_t)DWA_OP_STAGE >> 4;
       uint32_t it = 0, j = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int tile = p.tile_begin + blockIdx.x; tile < p.tile_end; tile += gridDim.x) {
         const DwaTile t = dwa_tile(p, L, tile);
         if (!t.active) continue;
         const uint32_t idesc = umma_idesc_bf16(t.BN, 1, 1);
@@ -389,7 +396,7 @@ __global__ void __launch_bounds__(DWA_THREADS, 1) dwadam_kernel(const DwaParams 
     const int et = threadIdx.x - 128;      // 0 .. 511
     const AdamHyper h = *p.adam;
     uint32_t it = 0, j = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int tile = p.tile_begin + blockIdx.x; tile < p.tile_end; tile += gridDim.x) {
       const DwaTile t = dwa_tile(p, L, tile);
       if (!t.active) continue;
       const DwaLayer& y = L[t.layer];
@@ -541,7 +548,7 @@ inline cudaError_t dwa_state_map(CUtensorMap* out, float* base, int ld, int rows
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-inline cudaError_t dwadam_launch(const DwaParams& p, cudaStream_t st) {
+inline cudaError_t dwadam_launch(const DwaParams& p, cudaStream_t st, int max_ctas = 0) {
   static bool attr_set[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -551,7 +558,9 @@ inline cudaError_t dwadam_launch(const DwaParams& p, cudaStream_t st) {
     if (err != cudaSuccess) return err;
     attr_set[dev] = true;
   }
-  const int grid = p.total_tiles < gemm_num_sms() ? p.total_tiles : gemm_num_sms();
+  int grid = std::min(p.tile_end - p.tile_begin, gemm_num_sms());
+  if (max_ctas > 0) grid = std::min(grid, max_ctas);
+  if (grid < 1) return cudaSuccess;
   if (p.stats) return launch_k(dwadam_kernel<true>, dim3(grid), dim3(DWA_THREADS), (size_t)DWA_SMEM, st, 1, p);
   return launch_k(dwadam_kernel<false>, dim3(grid), dim3(DWA_THREADS), (size_t)DWA_SMEM, st, 1, p);
 }

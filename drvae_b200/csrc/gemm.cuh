@@ -104,6 +104,7 @@ struct GemmProblem {
   int model0;       // ... starting at this ensemble member
   int ens;          // ensemble members the operand buffers hold (extent of the tensor maps); 0: n_models
   int desc_variant; // debug knob for descriptor bring-up (0 = designed encoding)
+  int max_ctas;     // > 0: cap on the persistent grid (the step reserves SMs for a concurrent launch)
   DebugWord* dbg;
   unsigned long long* trace;  // kernel trace (common.cuh TraceScope)
   int trace_id;
@@ -1353,7 +1354,8 @@ inline cudaError_t gemm_launch_t(GemmProblem p, const EpiParams& e, int n_models
   CUtensorMap tmA, tmB, tmB2;
   cudaError_t err = gemm_make_maps(p, n_models, &tmA, &tmB, &tmB2);
   if (err != cudaSuccess) return err;
-  const int grid = total < gemm_num_sms() ? total : gemm_num_sms();  // persistent: one CTA per SM
+  int grid = total < gemm_num_sms() ? total : gemm_num_sms();  // persistent: one CTA per SM
+  if (p.max_ctas > 0 && grid > p.max_ctas) grid = p.max_ctas;
   return launch_k(gemm_tc_kernel<EPI, EW, VEC>, dim3(grid), dim3((GEMM_PROD_WARPS + 1 + EW) * 32), smem, st, 1, p, e, tmA, tmB, tmB2);
 }
 

@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <functional>
 
 #include <map>
 #include <string>
@@ -135,6 +136,11 @@ struct drvae_plan {
   bool dwa_ok = false;       // every layer fits the kernel's layout conditions and the state is bound
   unsigned long long* d_dwa_stats = nullptr;  // drvae_debug_dwa_stats
   bool dwa_enabled = true;   // measurement knob (DRVAE_B200_DWADAM=0: per-layer fused kernels of round 1)
+  // Early part of the grouped launch: the decoder heads (half of the optimizer state) have all their inputs once the
+  // decoder's dX GEMM has run; their tiles start then, on dwa_early_sms SMs, next to the latency-bound rest of the
+  // backward chain (whose persistent GEMMs are capped to the remaining SMs).  0: one launch at the end.
+  int dwa_early_tiles = 0;   // tiles of the first layer when that layer is the decoder head block
+  int dwa_early_sms = 92;    // DRVAE_B200_DWA_EARLY_SMS (measured on two boxes: 0.939 -> 0.918 ms at 84, 0.953 -> 0.943 at 100; 72 and 116+ lose)
   // persistent step kernel (stepk.cuh): the forward + input-gradient chain as one cooperative launch
   bool stepk_enabled = false;          // drvae_set_step_kernel / DRVAE_B200_STEPK (measured slower than the graph of launches: profiles/r02_experiments.md)
   bool stepk_unsupported = false;      // a recorded sequence did not fit the kernel's tables: this plan launches kernel by kernel
@@ -574,6 +580,7 @@ extern "C" int drvae_plan_create(const drvae_arch_t* a, int n_models, drvae_plan
   if (const char* knob = getenv("DRVAE_B200_SCHED")) pl->sched = atoi(knob);
   if (const char* knob = getenv("DRVAE_B200_DWADAM")) pl->dwa_enabled = atoi(knob) != 0;
   if (const char* knob = getenv("DRVAE_B200_STEPK")) pl->stepk_enabled = atoi(knob) != 0;
+  if (const char* knob = getenv("DRVAE_B200_DWA_EARLY_SMS")) pl->dwa_early_sms = std::max(0, atoi(knob));
   cudaMalloc(&pl->d_stepk_bar, 2 * sizeof(unsigned int));
   cudaMemset(pl->d_stepk_bar, 0, 2 * sizeof(unsigned int));
   if (const char* knob = getenv("DRVAE_B200_PDL")) pdl_mask() = atoi(knob);  // measurement knob: programmatic dependent launch
@@ -869,6 +876,7 @@ int build_dwa(drvae_plan* pl) {
   if (err == cudaSuccess) err = cudaMemcpy(pl->d_dwa_maps, maps.data(), sizeof(DwaMaps) * maps.size(), cudaMemcpyHostToDevice);
   if (err != cudaSuccess) return set_cuda_error("drvae_plan_bind: uploading the grouped weight-gradient tables", err);
   pl->dwa_tiles = tile;
+  pl->dwa_early_tiles = (!refs.empty() && refs[0].W == &pl->dec.head) ? pl->dwa_layers[0].tile_end : 0;
   pl->dwa_ok = true;
   return 0;
 }
@@ -938,6 +946,8 @@ struct Exec {
   // the dX chain for this stream; each waits for what has been enqueued on the chain's stream so far (its dY and input)
   cudaStream_t dw_stream = nullptr;
   cudaEvent_t dw_event = nullptr;
+  int cta_cap = 0;                          // > 0: persistent GEMM grids are capped (SMs reserved for the early dW+Adam launch)
+  std::function<void()> after_head_dx;      // called once after the next block_bwd has enqueued its head dX GEMM
   bool ok() const { return err == cudaSuccess; }
   // stream dependencies: real events, or level bookkeeping while recording
   void ev_record(cudaEvent_t ev, cudaStream_t s) {
@@ -999,6 +1009,7 @@ struct Exec {
     if (p.ksplit < 1) p.ksplit = 1;
     p.model0 = model0;
     p.ens = pl->E;
+    p.max_ctas = cta_cap;
     if (rec) {
       p.trace = nullptr;
       p.trace_id = 0;
@@ -1189,6 +1200,11 @@ struct Exec {
     const int n = (int)b.hidden.size();
     sub = "head";
     gemm_dx(dYh, b.head, EPI_DACT_C8, epi_dact(b.H[n - 1], b.dPre[n - 1], b.widths[n - 1]), dyn_which, row_bound);
+    if (after_head_dx) {
+      auto hook = std::move(after_head_dx);
+      after_head_dx = nullptr;
+      hook();
+    }
     gemm_dw(dYh, b.H[n - 1], 0, b.head, dyn_which, row_bound);
     for (int i = n - 1; i >= 0; --i) {
       const C8Buf& src = (i == 0) ? in : b.H[i - 1];
@@ -1412,6 +1428,52 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
   const bool own_main = !use_stepk && pl->main_prio && !pl->prof_on && !(backward && !fused_adam) && pl->has_fprop && pl->overlap;
   if (K > 1 || own_main) cudaEventRecord(pl->ev_begin, st);
 
+  // grouped weight-gradient + Adam launch over the tiles [t0, t1) (dwadam.cuh)
+  auto launch_dwadam = [&](int t0, int t1, cudaStream_t stream, int max_ctas, const char* tag) {
+    DwaParams dp{};
+    dp.n_layers = (int)pl->dwa_layers.size();
+    dp.n_models = E;
+    dp.total_tiles = pl->dwa_tiles;
+    dp.tile_begin = t0;
+    dp.tile_end = t1;
+    dp.layers = pl->d_dwa_layers;
+    dp.maps = pl->d_dwa_maps;
+    dp.tabs = pl->d_tabs;
+    dp.counts = v.counts.p;
+    dp.counts_stride = (int)v.counts.ms;
+    dp.adam_p = pl->params;
+    dp.adam_m = pl->adam_m;
+    dp.adam_v = pl->adam_v;
+    dp.state_ms = pl->P;
+    dp.drv = pl->derived.p;
+    dp.drv_ms = pl->derived.ms;
+    dp.shadow = pl->shadow.p;
+    dp.shadow_ms = pl->shadow.ms;
+    dp.adam = &pl->d_dyn->s.adam;
+    dp.dbg = pl->dbg;
+    cudaStream_t keep = ex.st;
+    ex.st = stream;
+    ex.phase = "bwd";
+    ex.pre(tag);
+    dp.trace = v.trace;
+    dp.trace_id = v.trace_id;
+    dp.stats = pl->d_dwa_stats;
+    if (const char* knob = getenv("DRVAE_B200_DWA_DEBUG")) dp.debug_flags = atoi(knob);
+    cudaError_t r = dwadam_launch(dp, stream, max_ctas);
+    ex.post();
+    ex.st = keep;
+    if (r != cudaSuccess) ex.err = r;
+    pl->launches++;
+  };
+  // Early part of that launch: the decoder heads' tiles as soon as the decoder's dX GEMM (the last reader of their
+  // weights) has been enqueued, on dwa_early_sms SMs of a low-priority stream; the persistent GEMMs of the rest of
+  // the chain are capped to the other SMs while it runs.
+  bool dwa_early_done = false;
+  const int nsm = gemm_num_sms();
+  const bool dwa_early = backward && ex.defer_dw && !use_stepk && !pl->prof_on && pl->has_fprop && pl->overlap && K == 1 &&
+                         pl->dwa_early_tiles > 0 && pl->dwa_early_tiles < pl->dwa_tiles && pl->dwa_early_sms >= 8 &&
+                         pl->dwa_early_sms <= nsm - 16;
+
   for (int c = 0; c < K && ex.ok(); ++c) {
     drvae_plan::Chain& ch = pl->chain[c];
     const int m0 = (int)((long long)E * c / K), Ec = (int)((long long)E * (c + 1) / K) - m0;
@@ -1580,6 +1642,7 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
           if (!ex.rec) cudaEventRecord(pl->bucket_ev[3], ex.st);  // buckets: dz1, z3 (this stream), dec, clf, ...
           if (overlap) ex.ev_record(ch.ev_clf, ex.st);
         }
+        if (dwa_early) ex.cta_cap = nsm - pl->dwa_early_sms;  // (they run next to the early dW+Adam launch)
         ex.phase = "dz1.bwd";
         ex.block_bwd(pl->dz1b, v.dY9, v.Z3b, 0, pl->Z3, v.dZ3.p, v.dZ3.ms, CNT_F, Fb);
         if (!ex.rec) cudaEventRecord(pl->bucket_ev[0], ex.dw_stream ? ex.dw_stream : ex.st);
@@ -1588,6 +1651,7 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
         ex.phase = "z3.bwd";
         ex.block_bwd(pl->z3b, v.dY7, v.Z1e, 0, pl->Z, v.dZ1e.p, v.dZ1e.ms, CNT_F, Fb);
         if (!ex.rec) cudaEventRecord(pl->bucket_ev[1], ex.dw_stream ? ex.dw_stream : ex.st);
+        ex.cta_cap = 0;
         // what q_back needs from this stream; the loss reduction that follows here is joined at the end of the step only
         if (overlap) ex.ev_record(ch.ev_side_bwd, ex.st);
       }
@@ -1642,6 +1706,17 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
         ++bk;
       };
       ex.phase = "dec.bwd";
+      if (dwa_early) {
+        ex.after_head_dx = [&]() {
+          cudaStream_t es = pl->chain[1].side;
+          cudaEventRecord(pl->chain[1].ev_dw, cm);
+          cudaStreamWaitEvent(es, pl->chain[1].ev_dw, 0);
+          launch_dwadam(0, pl->dwa_early_tiles, es, pl->dwa_early_sms, "dw_adam_early");
+          ex.phase = "dec.bwd";
+          ex.cta_cap = nsm - pl->dwa_early_sms;
+          dwa_early_done = true;
+        };
+      }
       ex.block_bwd(pl->dec, pl->dY5, v.Zdec, 0, pl->Z, v.dZdec.p, v.dZdec.ms, CNT_RD, Rdb);
       bucket_done();
       if (pl->has_clf) {
@@ -1695,6 +1770,7 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
       ex.block_bwd(pl->enc, v.dY2, v.Ain, 0, pl->X, nullptr, 0, CNT_R0, R0b);
       bucket_done();
     }
+    ex.cta_cap = 0;
     if (overlap) ex.ev_wait(cm, ch.ev_side_end);
     if (ex.dw_stream) {  // join the weight-gradient stream
       if (ex.rec) {
@@ -1760,35 +1836,12 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
   ex.model0 = 0;
   ex.Ec = E;
   if (backward && ex.defer_dw && ex.ok()) {
-    DwaParams dp{};
-    dp.n_layers = (int)pl->dwa_layers.size();
-    dp.n_models = E;
-    dp.total_tiles = pl->dwa_tiles;
-    dp.layers = pl->d_dwa_layers;
-    dp.maps = pl->d_dwa_maps;
-    dp.tabs = pl->d_tabs;
-    dp.counts = v.counts.p;
-    dp.counts_stride = (int)v.counts.ms;
-    dp.adam_p = pl->params;
-    dp.adam_m = pl->adam_m;
-    dp.adam_v = pl->adam_v;
-    dp.state_ms = pl->P;
-    dp.drv = pl->derived.p;
-    dp.drv_ms = pl->derived.ms;
-    dp.shadow = pl->shadow.p;
-    dp.shadow_ms = pl->shadow.ms;
-    dp.adam = &pl->d_dyn->s.adam;
-    dp.dbg = pl->dbg;
-    ex.phase = "bwd";
-    ex.pre("dw_adam_all");
-    dp.trace = v.trace;
-    dp.trace_id = v.trace_id;
-    dp.stats = pl->d_dwa_stats;
-    if (const char* knob = getenv("DRVAE_B200_DWA_DEBUG")) dp.debug_flags = atoi(knob);
-    cudaError_t r = dwadam_launch(dp, st);
-    ex.post();
-    if (r != cudaSuccess) ex.err = r;
-    pl->launches++;
+    if (dwa_early_done) {  // the early part runs on its own stream: the rest starts when both are complete
+      cudaEventRecord(pl->chain[1].ev_dw_end, pl->chain[1].side);
+      cudaStreamWaitEvent(st, pl->chain[1].ev_dw_end, 0);
+    }
+    ex.st = st;
+    launch_dwadam(dwa_early_done ? pl->dwa_early_tiles : 0, pl->dwa_tiles, st, 0, dwa_early_done ? "dw_adam_rest" : "dw_adam_all");
   }
   if (!ex.ok()) return set_cuda_error("drvae step launch", ex.err);
   return 0;

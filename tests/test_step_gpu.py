@@ -852,3 +852,31 @@ def test_step_kernel_equals_one_launch_per_operation(kind, arch_name):
     assert torch.equal(res[True][3], res[False][3])
     assert torch.equal(res[True][4], res[False][4])
     assert bool(torch.isfinite(res[True][1]).all())
+
+
+@pytest.mark.parametrize("kind", ("drvae", "vfae"))
+def test_early_part_of_the_grouped_optimizer_launch_changes_nothing(kind, monkeypatch):
+    """The decoder heads' weight-gradient + Adam tiles start right after the decoder dX GEMM on a subset of the SMs,
+    next to the rest of the backward chain, whose persistent GEMMs are capped to the other SMs (plan.cu, dwa_early).
+    Same tiles, different launch grids and timing: losses and parameters must be bit-identical to the single launch at the
+    end of backward (DRVAE_B200_DWA_EARLY_SMS=0), under graph replay as well."""
+    arch, N, E = ARCH["tiny"], 40, 4
+    sds = [init_state_dict(kind, seed=SEED_MODEL + m, **arch) for m in range(E)]
+    batches = [batch_fields(kind, orc.synthetic_batch(N, arch["dim_x"], seed=30 + m)) for m in range(E)]
+    big = {k: torch.stack([b[k] for b in batches]).contiguous().cuda() for k in batches[0]}
+    res = {}
+    for sms in ("0", "92", "16"):
+        monkeypatch.setenv("DRVAE_B200_DWA_EARLY_SMS", sms)
+        plan = Plan(kind, L=L, max_batch=N, n_models=E, **arch)
+        for m in range(E):
+            plan.load_state_dict(sds[m], model=m)
+        l0 = plan.launch_count()
+        losses = [plan.train_step(big, plan.hparams(step=it, beta_pert=anneal_coef(it, 1, 0)), seed=4).cpu().clone() for it in range(6)]
+        torch.cuda.synchronize()
+        res[sms] = (losses, plan.params.cpu().clone(), plan.adam_v.cpu().clone(), (plan.launch_count() - l0) // 6, plan.graph_replays())
+    assert res["92"][3] == res["0"][3] + 1  # one more launch per step: the early part
+    assert res["92"][4] >= 3
+    for sms in ("92", "16"):
+        for a, b in zip(res["0"][0], res[sms][0]):
+            assert torch.equal(a, b)
+        assert torch.equal(res["0"][1], res[sms][1]) and torch.equal(res["0"][2], res[sms][2])

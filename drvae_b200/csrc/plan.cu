@@ -145,6 +145,10 @@ struct drvae_plan {
   bool stepk_enabled = false;          // drvae_set_step_kernel / DRVAE_B200_STEPK (measured slower than the graph of launches: profiles/r02_experiments.md)
   bool stepk_unsupported = false;      // a recorded sequence did not fit the kernel's tables: this plan launches kernel by kernel
   unsigned int* d_stepk_bar = nullptr; // {arrival count, generation}
+  SampleView* d_sview = nullptr;       // device view of the sampling epilogue (EPI_SAMPLE_Q1), written by rowmap_kernel
+  bool fuse_sample = false;            // DRVAE_B200_FUSE_SAMPLE=1: DrVAE's sample_q1 inside the encoder-head GEMM epilogue (bit-identical;
+                                       // measured slower: 64 tiles x 16 warps have less parallelism than one warp per row, and the whole
+                                       // GEMM then waits for the noise generator: profiles/r02_experiments.md)
   long long stepk_launches = 0;
   // data-parallel exchange over peer memory (dp_peer.cuh): attached by drvae_dp_attach
   bool dp_on = false;
@@ -581,6 +585,9 @@ extern "C" int drvae_plan_create(const drvae_arch_t* a, int n_models, drvae_plan
   if (const char* knob = getenv("DRVAE_B200_DWADAM")) pl->dwa_enabled = atoi(knob) != 0;
   if (const char* knob = getenv("DRVAE_B200_STEPK")) pl->stepk_enabled = atoi(knob) != 0;
   if (const char* knob = getenv("DRVAE_B200_DWA_EARLY_SMS")) pl->dwa_early_sms = std::max(0, atoi(knob));
+  if (const char* knob = getenv("DRVAE_B200_FUSE_SAMPLE")) pl->fuse_sample = atoi(knob) != 0;
+  cudaMalloc(&pl->d_sview, sizeof(SampleView));
+  cudaMemset(pl->d_sview, 0, sizeof(SampleView));
   cudaMalloc(&pl->d_stepk_bar, 2 * sizeof(unsigned int));
   cudaMemset(pl->d_stepk_bar, 0, 2 * sizeof(unsigned int));
   if (const char* knob = getenv("DRVAE_B200_PDL")) pdl_mask() = atoi(knob);  // measurement knob: programmatic dependent launch
@@ -710,6 +717,7 @@ extern "C" int drvae_plan_destroy(drvae_plan_t* pl) {
   if (pl->d_trace) cudaFree(pl->d_trace);
   if (pl->d_dwa_stats) cudaFree(pl->d_dwa_stats);
   if (pl->d_stepk_bar) cudaFree(pl->d_stepk_bar);
+  if (pl->d_sview) cudaFree(pl->d_sview);
   for (auto& ev : pl->bucket_ev) cudaEventDestroy(ev);
   for (auto& ch : pl->chain) {
     for (int i = 0; i < drvae_plan::Chain::N_EVENTS; ++i)
@@ -1269,6 +1277,7 @@ int fill_view(drvae_plan* pl, Exec& ex, const drvae_batch_t* b, const drvae_nois
   v.eps_z3 = MBuf<const float>{eps + pl->epsl.off_z3, ems};
   v.own_noise = (nz && nz->eps) ? 0 : 1;
   v.dyn = pl->d_dyn;
+  v.sview_dev = nullptr;
   v.params = MBuf<float>{pl->params, pl->P};
   v.clf_w = pl->wn ? MBuf<const float>{pl->derived.p + pl->clf_eff_off, pl->derived.ms}
                    : MBuf<const float>{pl->params + pl->clf_w_off, pl->P};
@@ -1400,6 +1409,11 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
   v.clf_splits = std::max(CLF_SPLITS, std::min(CLF_SPLITS_MAX, cdiv(LNb, 64)));
   v.loss_slices = std::max(1, std::min(LOSS_SLICES_MAX, cdiv(Rdb, 512)));
   ex.splitk = backward && !fused_adam && Rdb >= 2048;
+  // DrVAE: the reparameterised draws of q(z1|x1) come out of the encoder-head GEMM's epilogue (no sample_q1 launch).
+  // Needs both statistics of a feature in one tile (one N tile) and one model range (the device view is per step).
+  const bool fuse_sample = pl->fuse_sample && pl->has_T && pl->has_fprop && pl->has_clf && pl->enc.head.tiles_n == 1 &&
+                           pl->view.Zc <= 256 && pl->d_sview != nullptr && (pl->chains <= 1 || pl->prof_on || (backward && !fused_adam));
+  if (fuse_sample) v.sview_dev = pl->d_sview;
   v.clf_back_fused = (pl->has_T && pl->has_clf && pl->clf_in > pl->Z && (pl->sched & 32) && !(pl->sched & 2)) ? 1 : 0;
   v.clf_split = (pl->has_T && pl->has_clf && pl->has_fprop && (pl->sched & 16)) ? 1 : 0;
   ex.defer_dw = backward && fused_adam && pl->dwa_ok && pl->dwa_enabled;
@@ -1564,12 +1578,21 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
     // ---- encoder q(z1|x1), shared with q(z2|x2) (DrVAE.py:408,418) ----
     ex.phase = "enc.fwd";
     ex.block_hidden_fwd(pl->enc, v.Ain, 0, CNT_R0, R0b);
-    ex.gemm_nt(pl->enc.H.back(), 0, pl->enc.head, EPI_STORE_F32,
-               ex.epi_f32(v.Q.p, v.Q.ms, 2 * pl->view.Zs, 2 * pl->view.Zs, &pl->enc.head), CNT_R0, R0b);
-    if (own_eps && (pl->sched & 1) && !use_stepk) after(cm, ch.ev_eps, side);  // latent noise of this step
-    ex.row_op(SROW_SAMPLE_Q1, "sample_q1", row_items(N + PAD_WARPS), 0, [&]() {
-      launch_k(pl->view.Zc <= 128 ? sample_q1_kernel<4> : sample_q1_kernel<MAXJ>, rows_grid(N + PAD_WARPS), dim3(ROW_THREADS), 0, cm, 2, v);
-    });
+    if (fuse_sample) {
+      if (own_eps && (pl->sched & 1) && !use_stepk) after(cm, ch.ev_eps, side);  // latent noise of this step
+      EpiParams es = ex.epi_f32(v.Q.p, v.Q.ms, 2 * pl->view.Zs, 2 * pl->view.Zs, &pl->enc.head);
+      es.sview = pl->d_sview;
+      ex.sub = "head+sample";
+      ex.gemm_nt(pl->enc.H.back(), 0, pl->enc.head, EPI_SAMPLE_Q1, es, CNT_R0, R0b);
+      ex.sub = "head";
+    } else {
+      ex.gemm_nt(pl->enc.H.back(), 0, pl->enc.head, EPI_STORE_F32,
+                 ex.epi_f32(v.Q.p, v.Q.ms, 2 * pl->view.Zs, 2 * pl->view.Zs, &pl->enc.head), CNT_R0, R0b);
+      if (own_eps && (pl->sched & 1) && !use_stepk) after(cm, ch.ev_eps, side);  // latent noise of this step
+      ex.row_op(SROW_SAMPLE_Q1, "sample_q1", row_items(N + PAD_WARPS), 0, [&]() {
+        launch_k(pl->view.Zc <= 128 ? sample_q1_kernel<4> : sample_q1_kernel<MAXJ>, rows_grid(N + PAD_WARPS), dim3(ROW_THREADS), 0, cm, 2, v);
+      });
+    }
     // The label-dependent branch (q(z_top|z1,y) -> p(z1|z_top,y), forward and backward dX: small GEMMs + row kernels
     // that leave most SMs idle) is independent of the decoder branch: side stream between a fork here and a join
     // before the encoder backward.
@@ -2265,6 +2288,7 @@ extern "C" int drvae_infer(drvae_plan_t* pl, const float* x1, int N, const drvae
   v.clf_w = pl->wn ? MBuf<const float>{pl->derived.p + pl->clf_eff_off, pl->derived.ms}
                    : MBuf<const float>{pl->params + pl->clf_w_off, pl->P};
   v.dyn = pl->d_dyn;
+  v.sview_dev = nullptr;
   v.own_noise = 0;
   {
     drvae_hparams_t ihp{};  // eval mode: training = 0, add_noise = 0

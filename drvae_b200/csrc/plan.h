@@ -206,6 +206,7 @@ struct DevView {
                             // effective (weight-normalised) copy in the derived arena
   MBuf<float> losses;  // [8]
   const StepDyn* dyn;  // per-step scalars (device memory)
+  SampleView* sview_dev;  // device copy of the sampling epilogue's view (written by rowmap_kernel; null: not used)
   unsigned long long* trace;  // kernel trace buffer (null: off) and this launch's slot
   int trace_id;
 };

@@ -117,6 +117,22 @@ __global__ void __launch_bounds__(ROWMAP_THREADS) rowmap_kernel(DevView v) {
   int p = block_exclusive_scan(np, s_tot, Np);
   int e = block_exclusive_scan(ne, s_tot, Fl);
   (void)block_exclusive_scan(nl, s_tot, Nlab);
+  if (t == 0 && blockIdx.x == 0 && v.sview_dev) {
+    // view of the sampling epilogue of the encoder-head GEMM (gemm.cuh EPI_SAMPLE_Q1): pointers of model 0 + strides
+    SampleView s;
+    s.Z = v.Z, s.Zs = v.Zs, s.Zc = v.Zc, s.L = v.L, s.Ncap = v.Ncap, s.Y = v.Y;
+    s.counts = v.counts.p, s.counts_stride = (int)v.counts.ms;
+    s.pair_of = v.pair_of.p, s.pair_ms = v.pair_of.ms;
+    s.ebase = v.ebase.p, s.ebase_ms = v.ebase.ms;
+    s.lab = v.lab.p, s.lab_ms = v.lab.ms;
+    s.ycls = v.ycls.p, s.ycls_ms = v.ycls.ms;
+    s.eps_z1 = v.eps_z1.p, s.eps_z1_ms = v.eps_z1.ms;
+    s.eps_z2 = v.eps_z2.p, s.eps_z2_ms = v.eps_z2.ms;
+    s.Z1f = v.Z1f.p, s.z1f_ms = v.Z1f.ms;
+    s.zdec = v.Zdec.p, s.zdec_ms = v.Zdec.ms, s.zdec_rcap = v.Zdec.rcap;
+    s.z1e = v.Z1e.p, s.z1e_ms = v.Z1e.ms, s.z1e_rcap = v.Z1e.rcap;
+    *v.sview_dev = s;
+  }
   if (t == 0) {
     int* cnt = v.counts.at(m);
     cnt[CNT_N] = N;

@@ -334,6 +334,7 @@ __global__ void __launch_bounds__(STEPK_THREADS, 1) step_kernel(const __grid_con
             case EPI_DACT_C8: step_gemm_epilogue<EPI_DACT_C8>(p, e, t, tmem_base, a, q, cg, lane, have_acc); break;
             case EPI_DECLOSS: step_gemm_epilogue<EPI_DECLOSS>(p, e, t, tmem_base, a, q, cg, lane, have_acc); break;
             case EPI_GRAD: step_gemm_epilogue<EPI_GRAD>(p, e, t, tmem_base, a, q, cg, lane, have_acc); break;
+            case EPI_SAMPLE_Q1: step_gemm_epilogue<EPI_SAMPLE_Q1>(p, e, t, tmem_base, a, q, cg, lane, have_acc); break;
             default: break;
           }
           tc_fence_before();
@@ -460,7 +461,7 @@ struct StepRecorder {
     cur[w] = std::max(cur[w], cur[p]);
   }
   void add_gemm(int epi, const GemmProblem& p, const EpiParams& e, int n_models, cudaStream_t s, const std::string& tag) {
-    if (epi != EPI_STORE_F32 && epi != EPI_ELU_C8 && epi != EPI_DACT_C8 && epi != EPI_DECLOSS && epi != EPI_GRAD) unsupported = true;
+    if (epi != EPI_STORE_F32 && epi != EPI_ELU_C8 && epi != EPI_DACT_C8 && epi != EPI_DECLOSS && epi != EPI_GRAD && epi != EPI_SAMPLE_Q1) unsupported = true;
     if (p.BN > 256) unsupported = true;
     Rec r{};
     r.op.kind = SOP_GEMM;

@@ -880,3 +880,32 @@ def test_early_part_of_the_grouped_optimizer_launch_changes_nothing(kind, monkey
         for a, b in zip(res["0"][0], res[sms][0]):
             assert torch.equal(a, b)
         assert torch.equal(res["0"][1], res[sms][1]) and torch.equal(res["0"][2], res[sms][2])
+
+
+@pytest.mark.parametrize("arch_name", ("tiny", "deep"))
+def test_sampling_epilogue_of_the_encoder_head_gemm_equals_the_row_kernel(arch_name, monkeypatch):
+    """EPI_SAMPLE_Q1 (gemm.cuh): DrVAE's reparameterised draws of q(z1|x1) written by the encoder-head GEMM's epilogue
+    instead of sample_q1_kernel (DRVAE_B200_FUSE_SAMPLE=1; off by default, measured slower).  Same arithmetic per element:
+    bit-identical losses and parameters, tensor-core and SIMT mainloops, tape noise and Philox noise."""
+    kind, arch, N, E = "drvae", ARCH[arch_name], 40, 3
+    sds = [init_state_dict(kind, seed=SEED_MODEL + m, **arch) for m in range(E)]
+    batches = [batch_fields(kind, orc.synthetic_batch(N, arch["dim_x"], seed=40 + m)) for m in range(E)]
+    big = {k: torch.stack([b[k] for b in batches]).contiguous().cuda() for k in batches[0]}
+    res = {}
+    for fuse in ("0", "1"):
+        monkeypatch.setenv("DRVAE_B200_FUSE_SAMPLE", fuse)
+        for impl in ("tc", "simt"):
+            plan = Plan(kind, L=L, max_batch=N, n_models=E, **arch)
+            plan.set_gemm_impl(impl)
+            for m in range(E):
+                plan.load_state_dict(sds[m], model=m)
+            l0 = plan.launch_count()
+            losses = [plan.train_step(big, plan.hparams(step=it, beta_pert=anneal_coef(it, 1, 0)), seed=6).cpu().clone() for it in range(4)]
+            ev = plan.loss_forward(big, plan.hparams(step=4, training=False), seed=6).cpu().clone()
+            torch.cuda.synchronize()
+            res[fuse, impl] = (losses, plan.params.cpu().clone(), ev, plan.launch_count() - l0)
+    for impl in ("tc", "simt"):
+        assert res["1", impl][3] < res["0", impl][3]  # fewer launches
+        for a, b in zip(res["0", impl][0], res["1", impl][0]):
+            assert torch.equal(a, b)
+        assert torch.equal(res["0", impl][1], res["1", impl][1]) and torch.equal(res["0", impl][2], res["1", impl][2])

@@ -116,7 +116,10 @@ class PeerBackend(PlanBackend):
         torch.cuda.synchronize(dev)
         dist.barrier(self.group)  # every control block is zero before anybody posts a flag
         if multicast is None:
-            multicast = os.environ.get("DRVAE_B200_DP_MULTICAST", "0") != "0"
+            # NVLS multicast mapping (one switch-reduced load per element instead of one load per rank): measured on one
+            # box at 8192 rows: 8 ranks 0.483 -> 0.442 ms per step, 4 ranks 0.471 -> 0.471 (profiles/r02_experiments.md)
+            knob = os.environ.get("DRVAE_B200_DP_MULTICAST")
+            multicast = (knob != "0") if knob is not None else self.world >= 8
         mc = int(getattr(gh, "multicast_ptr", 0) or 0) if multicast else 0
         self.multicast = bool(mc)
         plan.dp_attach(self.rank, self.world, list(gh.buffer_ptrs), list(ch.buffer_ptrs), mc)

@@ -150,3 +150,28 @@ def test_reconstruction_metrics_match_scipy_and_sklearn():
     sgn = sg.double().numpy()
     ll = (-0.5 * (np.log(2 * np.pi) + np.log(sgn ** 2) + (xn - rn) ** 2 / sgn ** 2)).sum(1).mean()
     assert abs(m["ll"] - ll) < 1e-9
+
+
+def test_balanced_sampler_weights_and_epoch_indices():
+    """compute_balanced_weights = utils.compute_balanced_weights(labels, unlabeled_data_ratio=None) (src/utils.py:292-327):
+    every class weighs 1 / its size; device_epoch_indices = WeightedRandomSampler(weights, len(weights)) cut into
+    DataLoader minibatches with drop_last when the dataset holds at least one batch (run_drvae.py:148-166)."""
+    import numpy as np
+    import torch
+    from drvae_b200.training import compute_balanced_weights, device_epoch_indices
+    labels = np.array([3, 3, 3, 7, 7, 9, 3, 9, 9, 9])
+    w = compute_balanced_weights(labels)
+    assert w.dtype == torch.float64
+    want = {3: 1 / 4, 7: 1 / 2, 9: 1 / 4}
+    assert np.allclose(w.numpy(), [want[int(l)] for l in labels])
+    # classes are drawn with equal probability: class totals of the weights are equal
+    for c in (3, 7, 9):
+        assert abs(float(w[torch.from_numpy(labels == c)].sum()) - 1.0) < 1e-12
+    g = torch.Generator().manual_seed(0)
+    idx = device_epoch_indices(w, 4, g)
+    assert idx.dtype == torch.int32 and tuple(idx.shape) == (2, 4) and int(idx.min()) >= 0 and int(idx.max()) < 10
+    short = device_epoch_indices(w, 16, g)  # fewer rows than one batch: a single short batch, like DataLoader(drop_last=False)
+    assert tuple(short.shape) == (1, 10)
+    big = device_epoch_indices(compute_balanced_weights(np.arange(3000) % 3 == 0), 150, g)
+    frac = float((big.long() % 3 == 0).float().mean())
+    assert tuple(big.shape) == (20, 150) and 0.45 < frac < 0.55  # the 1/3 minority class fills half of the draws

@@ -592,6 +592,9 @@ def main():
                                     "algorithmic bytes per launch = 24 B x parameters of the updated layers x models",
                     "algorithmic_bytes": top.get("algorithmic_bytes"), "share_of_step": top["ms_per_launch"] / (ms / args.steps),
                     "timing": "CUDA events around the launch on its own stream, %d steps after the timed region" % PSTEPS,
+                    "note": "timed as ONE launch over all layers (per-launch timing serialises the step); inside the timed step the same "
+                            "tiles are issued in two parts: the decoder heads on 92 SMs next to the tail of the backward chain, the "
+                            "rest on all SMs (profiles/r02_experiments.md 2b)" if top["kernel"] == "bwd:dw_adam_all" else None,
                     "peak_source": "%s (MEASURED_PEAKS.json %s)" % (peaks["which"], "hbm_gbs" if top["bound"] == "hbm" else "bf16_tflops_sustained")}
     step_flops = sum(2.0 * a * b * c for a, b, c in dims.values())
     line = {

@@ -1484,7 +1484,7 @@ int run_step(drvae_plan* pl, const drvae_batch_t* b, const drvae_noise_t* nz, co
   // the chain are capped to the other SMs while it runs.
   bool dwa_early_done = false;
   const int nsm = gemm_num_sms();
-  const bool dwa_early = backward && ex.defer_dw && !use_stepk && !pl->prof_on && pl->has_fprop && pl->overlap && K == 1 &&
+  const bool dwa_early = backward && ex.defer_dw && !use_stepk && !pl->prof_on && pl->overlap && K == 1 &&
                          pl->dwa_early_tiles > 0 && pl->dwa_early_tiles < pl->dwa_tiles && pl->dwa_early_sms >= 8 &&
                          pl->dwa_early_sms <= nsm - 16;
 
